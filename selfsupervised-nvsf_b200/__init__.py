@@ -1,0 +1,14 @@
+"""nvsf_b200 — B200-native (sm_100a) ray-rendering hot path of NVSF.
+
+Importable as ``nvsf_b200`` (shim at the repository root) or via
+``importlib.import_module("selfsupervised-nvsf_b200")``.
+
+Sub-modules
+    raymarching   drop-in for reference ``nvsf.nerf.raymarching.raymarching``
+    _lib          ctypes binding of the C ABI (include/nvsf_b200.h)
+    build         compiles csrc/*.cu into libnvsf_b200.so with nvcc (sm_100a)
+"""
+from . import _lib  # noqa: F401
+from . import raymarching  # noqa: F401
+
+__version__ = "0.1.0"

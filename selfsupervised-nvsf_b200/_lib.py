@@ -1,0 +1,105 @@
+"""ctypes binding of the C-ABI library ``libnvsf_b200.so`` (include/nvsf_b200.h).
+
+This is the whole "thin C-ABI torch-extension layer": tensors are passed as raw
+device pointers plus the current CUDA stream handle; nothing torch-specific
+crosses the boundary.  There is no fallback — if the library is missing or a
+call fails the caller gets an exception.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnvsf_b200.so")
+
+_p = ctypes.c_void_p
+_u32 = ctypes.c_uint32
+_f32 = ctypes.c_float
+_sz = ctypes.c_size_t
+_int = ctypes.c_int
+
+# name -> (restype, argtypes); mirrors include/nvsf_b200.h one to one.
+PROTOTYPES = {
+    "nvsf_abi_version": (_int, []),
+    "nvsf_status_string": (ctypes.c_char_p, [_int]),
+    "nvsf_near_far_from_aabb": (_int, [_p, _p, _p, _u32, _f32, _p, _p, _p]),
+    "nvsf_sph_from_ray": (_int, [_p, _p, _f32, _u32, _p, _p]),
+    "nvsf_morton3D": (_int, [_p, _u32, _p, _p]),
+    "nvsf_morton3D_invert": (_int, [_p, _u32, _p, _p]),
+    "nvsf_packbits": (_int, [_p, _u32, _f32, _p, _p]),
+    "nvsf_march_rays_train_workspace_bytes": (_sz, [_u32]),
+    "nvsf_march_rays_train": (
+        _int,
+        [_p, _p, _p, _f32, _f32, _u32, _u32, _u32, _u32, _u32, _p, _p, _p, _p, _p, _p, _p, _p,
+         _p, _sz, _p],
+    ),
+    "nvsf_march_rays_train_count": (
+        _int,
+        [_p, _p, _p, _f32, _f32, _u32, _u32, _u32, _u32, _p, _p, _p, _p, _p, _p, _sz, _p],
+    ),
+    "nvsf_march_rays_train_write": (
+        _int,
+        [_p, _p, _p, _f32, _f32, _u32, _u32, _u32, _u32, _u32, _p, _p, _p, _p, _p, _p, _p, _p,
+         _u32, _p],
+    ),
+    "nvsf_composite_rays_train_forward": (
+        _int, [_p, _p, _p, _p, _u32, _u32, _f32, _p, _p, _p, _p]),
+    "nvsf_composite_rays_train_backward": (
+        _int, [_p, _p, _p, _p, _p, _p, _p, _p, _u32, _u32, _f32, _p, _p, _p]),
+    "nvsf_march_rays": (
+        _int,
+        [_u32, _u32, _p, _p, _p, _p, _f32, _f32, _u32, _u32, _u32, _p, _p, _p, _p, _p, _p, _p,
+         _u32, _p],
+    ),
+    "nvsf_composite_rays": (_int, [_u32, _u32, _f32, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+}
+
+_lib = None
+
+
+class NvsfError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load (once) and return the ctypes handle; raise loudly if it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: the CUDA library has not been built "
+            "(run `python -c 'import __graft_entry__ as g; g.build()'`). "
+            "nvsf_b200 has no CPU or PyTorch fallback."
+        )
+    handle = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(handle, name)  # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    got = handle.nvsf_abi_version()
+    if got != ABI_VERSION:
+        raise ImportError(f"libnvsf_b200.so ABI {got} != python binding ABI {ABI_VERSION}; rebuild")
+    _lib = handle
+    return _lib
+
+
+ABI_VERSION = 3
+
+
+def check(status, what=""):
+    if status != 0:
+        msg = lib().nvsf_status_string(status).decode()
+        raise NvsfError(f"{what}: {msg} (status {status})")
+
+
+def ptr(t):
+    """Raw device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return t.data_ptr() or None
+
+
+def stream_ptr():
+    import torch
+
+    return torch.cuda.current_stream().cuda_stream or None

@@ -1,0 +1,1095 @@
+// nvsf_b200 — ray-marching operators for sm_100a (Part 1 of include/nvsf_b200.h).
+//
+// Replaces the reference's `_raymarching` extension
+// (reference nvsf/nerf/raymarching/src/raymarching.cu).  Designed for B200, not
+// translated: rays are staged through shared memory with 16-byte loads, sample
+// offsets come from block/warp prefix sums instead of global atomics (so the
+// output order is deterministic), compositing streams each ray's samples through
+// per-warp shared-memory tiles so that global traffic is coalesced while the
+// per-ray arithmetic keeps the reference's exact operation order.
+//
+// Bit-exactness: every floating-point operation that decides a sample position
+// or count is written with explicit rounding intrinsics (__fmaf_rn, __fmul_rn,
+// ...) in the order the reference kernel executes on sm_100a (read from its
+// SASS), so results do not depend on this file's compiler flags.
+#include <float.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kRayBlock = 128;   // rays per CTA for per-ray kernels
+constexpr int kTileBlock = 256;  // rays per CTA for the light utility kernels
+
+// ---------------------------------------------------------------------------
+// near_far_from_aabb  (reference kernel raymarching.cu:105-157)
+// ---------------------------------------------------------------------------
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+k_near_far_from_aabb(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                     const float* __restrict__ aabb, uint32_t N, float min_near,
+                     float* __restrict__ nears, float* __restrict__ fars) {
+    __shared__ __align__(16) float s_o[BLOCK * 3];
+    __shared__ __align__(16) float s_d[BLOCK * 3];
+    const uint32_t base = blockIdx.x * BLOCK;
+    const uint32_t cnt = min((uint32_t)BLOCK, N - base);
+    block_load_floats<BLOCK>(rays_o + (size_t)base * 3, s_o, cnt * 3);
+    block_load_floats<BLOCK>(rays_d + (size_t)base * 3, s_d, cnt * 3);
+    __syncthreads();
+    const uint32_t tid = threadIdx.x;
+    if (tid >= cnt) return;
+    const uint32_t n = base + tid;
+
+    const float ox = s_o[3 * tid], oy = s_o[3 * tid + 1], oz = s_o[3 * tid + 2];
+    const float rdx = __frcp_rn(s_d[3 * tid]);
+    const float rdy = __frcp_rn(s_d[3 * tid + 1]);
+    const float rdz = __frcp_rn(s_d[3 * tid + 2]);
+    const float a0 = __ldg(aabb + 0), a1 = __ldg(aabb + 1), a2 = __ldg(aabb + 2);
+    const float a3 = __ldg(aabb + 3), a4 = __ldg(aabb + 4), a5 = __ldg(aabb + 5);
+
+    float near = __fmul_rn(__fsub_rn(a0, ox), rdx);
+    float far = __fmul_rn(__fsub_rn(a3, ox), rdx);
+    if (near > far) { float c = near; near = far; far = c; }
+
+    float near_y = __fmul_rn(__fsub_rn(a1, oy), rdy);
+    float far_y = __fmul_rn(__fsub_rn(a4, oy), rdy);
+    if (near_y > far_y) { float c = near_y; near_y = far_y; far_y = c; }
+
+    bool miss = (near > far_y) || (near_y > far);
+    if (!miss) {
+        if (near_y > near) near = near_y;
+        if (far_y < far) far = far_y;
+        float near_z = __fmul_rn(__fsub_rn(a2, oz), rdz);
+        float far_z = __fmul_rn(__fsub_rn(a5, oz), rdz);
+        if (near_z > far_z) { float c = near_z; near_z = far_z; far_z = c; }
+        miss = (near > far_z) || (near_z > far);
+        if (!miss) {
+            if (near_z > near) near = near_z;
+            if (far_z < far) far = far_z;
+            if (near < min_near) near = min_near;
+        }
+    }
+    if (miss) near = far = FLT_MAX;
+    nears[n] = near;
+    fars[n] = far;
+}
+
+// ---------------------------------------------------------------------------
+// sph_from_ray  (reference kernel raymarching.cu:183-217)
+// ---------------------------------------------------------------------------
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+k_sph_from_ray(const float* __restrict__ rays_o, const float* __restrict__ rays_d, float radius,
+               uint32_t N, float* __restrict__ coords) {
+    __shared__ __align__(16) float s_o[BLOCK * 3];
+    __shared__ __align__(16) float s_d[BLOCK * 3];
+    const uint32_t base = blockIdx.x * BLOCK;
+    const uint32_t cnt = min((uint32_t)BLOCK, N - base);
+    block_load_floats<BLOCK>(rays_o + (size_t)base * 3, s_o, cnt * 3);
+    block_load_floats<BLOCK>(rays_d + (size_t)base * 3, s_d, cnt * 3);
+    __syncthreads();
+    const uint32_t tid = threadIdx.x;
+    if (tid >= cnt) return;
+    const uint32_t n = base + tid;
+    const float ox = s_o[3 * tid], oy = s_o[3 * tid + 1], oz = s_o[3 * tid + 2];
+    const float dx = s_d[3 * tid], dy = s_d[3 * tid + 1], dz = s_d[3 * tid + 2];
+
+    // || o + t d || = radius, larger root (operation order of the reference on sm_100a)
+    const float A = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+    const float B = __fmaf_rn(oz, dz, __fmaf_rn(ox, dx, __fmul_rn(oy, dy)));
+    const float C = __fmaf_rn(-radius, radius,
+                              __fmaf_rn(oz, oz, __fmaf_rn(ox, ox, __fmul_rn(oy, oy))));
+    const float disc = __fmaf_rn(B, B, -__fmul_rn(A, C));
+    const float t = __fdiv_rn(__fadd_rn(-B, __fsqrt_rn(disc)), A);
+
+    const float x = __fmaf_rn(dx, t, ox), y = __fmaf_rn(dy, t, oy), z = __fmaf_rn(dz, t, oz);
+    const float theta = atan2f(__fsqrt_rn(__fmaf_rn(x, x, __fmul_rn(z, z))), y);
+    const float phi = atan2f(z, x);
+    const float kRPI = 0.3183098861837907f;
+    float2 out;
+    out.x = __fmaf_rn(__fmul_rn(2.0f, theta), kRPI, -1.0f);
+    out.y = __fmul_rn(phi, kRPI);
+    reinterpret_cast<float2*>(coords)[n] = out;
+}
+
+// ---------------------------------------------------------------------------
+// morton3D / morton3D_invert  (reference raymarching.cu:71-95, 237-280)
+// ---------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t spread3(uint32_t v) {
+    // 10 input bits -> every third bit.  Equal to the reference's multiply/mask
+    // form for v < 1024 (the only range a 32-bit 3-D Morton code can hold).
+    v &= 0x3ffu;
+    v = (v | (v << 16)) & 0x030000FFu;
+    v = (v | (v << 8)) & 0x0300F00Fu;
+    v = (v | (v << 4)) & 0x030C30C3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+// The reference's expansion, kept bit-identical for ANY 32-bit input: the public
+// morton3D operator must agree with it even for out-of-range coordinates.
+__host__ __device__ __forceinline__ uint32_t spread3_wide(uint32_t v) {
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+__host__ __device__ __forceinline__ uint32_t compact3(uint32_t x) {
+    x &= 0x49249249u;
+    x = (x | (x >> 2)) & 0xc30c30c3u;
+    x = (x | (x >> 4)) & 0x0f00f00fu;
+    x = (x | (x >> 8)) & 0xff0000ffu;
+    x = (x | (x >> 16)) & 0x0000ffffu;
+    return x;
+}
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+k_morton3D(const int32_t* __restrict__ coords, uint32_t N, int32_t* __restrict__ indices) {
+    __shared__ __align__(16) float s_c[BLOCK * 3];
+    const uint32_t base = blockIdx.x * BLOCK;
+    const uint32_t cnt = min((uint32_t)BLOCK, N - base);
+    block_load_floats<BLOCK>(reinterpret_cast<const float*>(coords) + (size_t)base * 3, s_c,
+                             cnt * 3);
+    __syncthreads();
+    const uint32_t tid = threadIdx.x;
+    if (tid >= cnt) return;
+    const uint32_t x = __float_as_uint(s_c[3 * tid]);
+    const uint32_t y = __float_as_uint(s_c[3 * tid + 1]);
+    const uint32_t z = __float_as_uint(s_c[3 * tid + 2]);
+    indices[base + tid] =
+        (int32_t)(spread3_wide(x) | (spread3_wide(y) << 1) | (spread3_wide(z) << 2));
+}
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+k_morton3D_invert(const int32_t* __restrict__ indices, uint32_t N, int32_t* __restrict__ coords) {
+    __shared__ __align__(16) int32_t s_c[BLOCK * 3];
+    const uint32_t base = blockIdx.x * BLOCK;
+    const uint32_t cnt = min((uint32_t)BLOCK, N - base);
+    const uint32_t tid = threadIdx.x;
+    if (tid < cnt) {
+        // arithmetic shift of a signed int, as in the reference (ind >> k on int)
+        const int32_t ind = __ldg(indices + base + tid);
+        s_c[3 * tid] = (int32_t)compact3((uint32_t)(ind >> 0));
+        s_c[3 * tid + 1] = (int32_t)compact3((uint32_t)(ind >> 1));
+        s_c[3 * tid + 2] = (int32_t)compact3((uint32_t)(ind >> 2));
+    }
+    __syncthreads();
+    int32_t* dst = coords + (size_t)base * 3;
+    const uint32_t nw = cnt * 3;
+    if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+        const uint32_t nv = nw >> 2;
+        for (uint32_t i = tid; i < nv; i += BLOCK)
+            reinterpret_cast<int4*>(dst)[i] = reinterpret_cast<const int4*>(s_c)[i];
+        for (uint32_t i = (nv << 2) + tid; i < nw; i += BLOCK) dst[i] = s_c[i];
+    } else {
+        for (uint32_t i = tid; i < nw; i += BLOCK) dst[i] = s_c[i];
+    }
+}
+
+// ---------------------------------------------------------------------------
+// packbits  (reference kernel raymarching.cu:287-306)
+// ---------------------------------------------------------------------------
+// One warp turns 1024 consecutive densities (8 coalesced float4 loads per lane,
+// all in flight together) into 32 words of bitfield written with one 128-byte
+// store.  Nibbles are merged across lanes with three shuffles.
+constexpr int kPackIters = 8;
+__global__ void __launch_bounds__(256)
+k_packbits_vec(const float4* __restrict__ grid4, uint32_t n_super, float thresh,
+               uint32_t* __restrict__ out) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (warp >= n_super) return;
+    const float4* src = grid4 + (size_t)warp * (kPackIters * 32) + lane;
+    float4 v[kPackIters];
+#pragma unroll
+    for (int it = 0; it < kPackIters; ++it) v[it] = __ldcs(src + it * 32);
+    uint32_t mine = 0;
+#pragma unroll
+    for (int it = 0; it < kPackIters; ++it) {
+        uint32_t x = (v[it].x > thresh ? 1u : 0u) | (v[it].y > thresh ? 2u : 0u) |
+                     (v[it].z > thresh ? 4u : 0u) | (v[it].w > thresh ? 8u : 0u);
+        x |= __shfl_down_sync(0xffffffffu, x, 1) << 4;
+        x |= __shfl_down_sync(0xffffffffu, x, 2) << 8;
+        x |= __shfl_down_sync(0xffffffffu, x, 4) << 16;
+        const uint32_t w = __shfl_sync(0xffffffffu, x, (lane & 3) * 8);
+        if ((lane >> 2) == (uint32_t)it) mine = w;
+    }
+    out[(size_t)warp * 32 + lane] = mine;
+}
+
+__global__ void __launch_bounds__(256)
+k_packbits_scalar(const float* __restrict__ grid, uint32_t first, uint32_t N, float thresh,
+                  uint8_t* __restrict__ bitfield) {
+    const uint32_t n = first + blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const float* g = grid + (size_t)n * 8;
+    uint32_t bits = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) bits |= (__ldg(g + i) > thresh) ? (1u << i) : 0u;
+    bitfield[n] = (uint8_t)bits;
+}
+
+// ---------------------------------------------------------------------------
+// Occupancy-grid DDA shared by the train and inference marchers
+// (reference raymarching.cu:359-439 / 463-533 / 840-927).
+// ---------------------------------------------------------------------------
+struct MarchParams {
+    float bound, dt_gamma, dt_min, dt_max;
+    float Hf, rH, H3f, Hm1f, halfH;
+    int cm1;
+    uint32_t H;
+    int h_pow2;
+};
+
+__device__ __forceinline__ MarchParams make_march_params(float bound, float dt_gamma,
+                                                         uint32_t max_steps, uint32_t C,
+                                                         uint32_t H) {
+    MarchParams p;
+    const float k2sqrt3 = __uint_as_float(0x405DB3D7u);  // 2*SQRT3() as the reference folds it
+    p.bound = bound;
+    p.dt_gamma = dt_gamma;
+    p.Hf = (float)H;
+    p.dt_min = __fdiv_rn(k2sqrt3, (float)max_steps);
+    p.dt_max = __fdiv_rn(__fmul_rn((float)(int)(1u << (C - 1)), k2sqrt3), p.Hf);
+    p.rH = __frcp_rn(p.Hf);
+    p.H3f = (float)(H * H * H);
+    p.Hm1f = (float)(H - 1);
+    p.halfH = 0.5f * p.Hf;
+    p.cm1 = (int)C - 1;
+    p.H = H;
+    p.h_pow2 = (H & (H - 1)) == 0;
+    return p;
+}
+
+struct RayGeom {
+    float ox, oy, oz, dx, dy, dz, rdx, rdy, rdz, sx, sy, sz;
+};
+
+__device__ __forceinline__ RayGeom make_ray(float ox, float oy, float oz, float dx, float dy,
+                                            float dz) {
+    RayGeom r;
+    r.ox = ox; r.oy = oy; r.oz = oz;
+    r.dx = dx; r.dy = dy; r.dz = dz;
+    r.rdx = __frcp_rn(dx); r.rdy = __frcp_rn(dy); r.rdz = __frcp_rn(dz);
+    r.sx = copysignf(1.0f, dx); r.sy = copysignf(1.0f, dy); r.sz = copysignf(1.0f, dz);
+    return r;
+}
+
+__device__ __forceinline__ float clamp_dt(const MarchParams& p, float t) {
+    return fminf(p.dt_max, fmaxf(p.dt_min, __fmul_rn(p.dt_gamma, t)));
+}
+
+// exponent of frexpf(v) for v >= 0, clamped to [0, cm1]  (mip_from_pos / mip_from_dt)
+__device__ __forceinline__ int mip_level(float v, int cm1) {
+    const int f = (__float_as_int(v) >> 23) & 0xff;
+    const int e = (f == 255) ? 0 : f - 126;  // zero/denormals give e <= 0 -> clamped to 0
+    return min(max(e, 0), cm1);
+}
+
+__device__ __forceinline__ int grid_cell(const MarchParams& p, float f) {
+    // reference: (int) clamp(0.5 * (x * mip_rbound + 1) * H, 0, H-1) with the product in double
+    float v;
+    if (p.h_pow2) v = __fmul_rn(f, p.halfH);  // exact, identical to the double path
+    else v = __double2float_rn(__dmul_rn(__dmul_rn((double)f, 0.5), (double)p.H));
+    return (int)fminf(p.Hm1f, fmaxf(v, 0.0f));
+}
+
+struct Probe {
+    float x, y, z, dt;
+    bool occ;
+};
+
+// Evaluates the sample at ray parameter t.  When the cell is empty, *t_skip is
+// the ray parameter of the next voxel boundary (`tt` in the reference).
+__device__ __forceinline__ Probe probe_at(const MarchParams& p, const RayGeom& r,
+                                          const uint8_t* __restrict__ grid, float t,
+                                          float* t_skip) {
+    Probe q;
+    q.x = fminf(p.bound, fmaxf(-p.bound, __fmaf_rn(r.dx, t, r.ox)));
+    q.y = fminf(p.bound, fmaxf(-p.bound, __fmaf_rn(r.dy, t, r.oy)));
+    q.z = fminf(p.bound, fmaxf(-p.bound, __fmaf_rn(r.dz, t, r.oz)));
+    q.dt = clamp_dt(p, t);
+
+    const float mx = fmaxf(fabsf(q.x), fmaxf(fabsf(q.y), fabsf(q.z)));
+    const int level = max(mip_level(mx, p.cm1),
+                          mip_level(__fmul_rn(__fmul_rn(q.dt, p.Hf), 0.5f), p.cm1));
+    const float mip_bound = fminf(__int_as_float((127 + level) << 23), p.bound);
+    const float mip_rbound = __frcp_rn(mip_bound);
+
+    const int nx = grid_cell(p, __fmaf_rn(q.x, mip_rbound, 1.0f));
+    const int ny = grid_cell(p, __fmaf_rn(q.y, mip_rbound, 1.0f));
+    const int nz = grid_cell(p, __fmaf_rn(q.z, mip_rbound, 1.0f));
+
+    const uint32_t morton = spread3((uint32_t)nx) | (spread3((uint32_t)ny) << 1) |
+                            (spread3((uint32_t)nz) << 2);
+    // reference computes level*H3 + morton in float (raymarching.cu:363,407)
+    const uint32_t index = (uint32_t)__fmaf_rn(p.H3f, (float)level, (float)morton);
+    q.occ = (__ldg(grid + (index >> 3)) >> (index & 7u)) & 1u;
+
+    if (!q.occ) {
+        const float ax = __fmaf_rn(r.sx, 0.5f, __fadd_rn((float)nx, 0.5f));
+        const float ay = __fmaf_rn(r.sy, 0.5f, __fadd_rn((float)ny, 0.5f));
+        const float az = __fmaf_rn(r.sz, 0.5f, __fadd_rn((float)nz, 0.5f));
+        const float tx = __fmul_rn(
+            __fmaf_rn(mip_bound, __fmaf_rn(__fmul_rn(ax, p.rH), 2.0f, -1.0f), -q.x), r.rdx);
+        const float ty = __fmul_rn(
+            __fmaf_rn(mip_bound, __fmaf_rn(__fmul_rn(ay, p.rH), 2.0f, -1.0f), -q.y), r.rdy);
+        const float tz = __fmul_rn(
+            __fmaf_rn(mip_bound, __fmaf_rn(__fmul_rn(az, p.rH), 2.0f, -1.0f), -q.z), r.rdz);
+        *t_skip = __fadd_rn(t, fmaxf(0.0f, fminf(tx, fminf(ty, tz))));
+    }
+    return q;
+}
+
+__device__ __forceinline__ float skip_to(const MarchParams& p, float t, float tt) {
+    do {
+        t = __fadd_rn(t, clamp_dt(p, t));
+    } while (t < tt);
+    return t;
+}
+
+__device__ __forceinline__ float first_t(const MarchParams& p, float near, float noise) {
+    return __fmaf_rn(noise, clamp_dt(p, near), near);
+}
+
+// ---------------------------------------------------------------------------
+// march_rays_train, phase 1: per-ray sample counts + per-CTA sums
+// ---------------------------------------------------------------------------
+// workspace layout (uint32 words): [0]=base point counter, [1]=base ray counter,
+// [2..3] pad, [4 .. 4+nblk) CTA sums -> exclusive CTA offsets, then N counts.
+__global__ void __launch_bounds__(kRayBlock)
+k_march_train_count(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                    const uint8_t* __restrict__ grid, float bound, float dt_gamma,
+                    uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
+                    const float* __restrict__ nears, const float* __restrict__ fars,
+                    const float* __restrict__ noises, const int32_t* __restrict__ counter,
+                    uint32_t* __restrict__ ws, uint32_t nblk) {
+    __shared__ __align__(16) float s_o[kRayBlock * 3];
+    __shared__ __align__(16) float s_d[kRayBlock * 3];
+    __shared__ uint32_t s_warp[kRayBlock / 32];
+    const uint32_t base = blockIdx.x * kRayBlock;
+    const uint32_t cnt = min((uint32_t)kRayBlock, N - base);
+    block_load_floats<kRayBlock>(rays_o + (size_t)base * 3, s_o, cnt * 3);
+    block_load_floats<kRayBlock>(rays_d + (size_t)base * 3, s_d, cnt * 3);
+    if (blockIdx.x == 0 && threadIdx.x < 2) ws[threadIdx.x] = (uint32_t)counter[threadIdx.x];
+    __syncthreads();
+
+    const uint32_t tid = threadIdx.x;
+    uint32_t num_steps = 0;
+    if (tid < cnt) {
+        const uint32_t n = base + tid;
+        const MarchParams p = make_march_params(bound, dt_gamma, max_steps, C, H);
+        const RayGeom r = make_ray(s_o[3 * tid], s_o[3 * tid + 1], s_o[3 * tid + 2],
+                                   s_d[3 * tid], s_d[3 * tid + 1], s_d[3 * tid + 2]);
+        const float far = __ldg(fars + n);
+        float t = first_t(p, __ldg(nears + n), __ldg(noises + n));
+        while (t < far && num_steps < max_steps) {
+            float tt;
+            const Probe q = probe_at(p, r, grid, t, &tt);
+            if (q.occ) {
+                ++num_steps;
+                t = __fadd_rn(t, q.dt);
+            } else {
+                t = skip_to(p, t, tt);
+            }
+        }
+        ws[4 + nblk + n] = num_steps;
+    }
+    const uint32_t wsum = warp_reduce_sum(num_steps);
+    if ((tid & 31) == 0) s_warp[tid >> 5] = wsum;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t s = 0;
+#pragma unroll
+        for (int w = 0; w < kRayBlock / 32; ++w) s += s_warp[w];
+        ws[4 + blockIdx.x] = s;
+    }
+}
+
+// phase 1b: exclusive scan of the CTA sums (single CTA), counter update.
+__global__ void __launch_bounds__(1024)
+k_march_train_scan(uint32_t* __restrict__ ws, uint32_t nblk, uint32_t N,
+                   int32_t* __restrict__ counter) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    uint32_t* sums = ws + 4;
+    for (uint32_t start = 0; start < nblk; start += 1024) {
+        const uint32_t i = start + tid;
+        const uint32_t v = i < nblk ? sums[i] : 0u;
+        const uint32_t inc = warp_inclusive_scan(v, lane);
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t w = s_warp[lane];
+            const uint32_t winc = warp_inclusive_scan(w, lane);
+            s_warp[lane] = winc - w;  // exclusive warp offsets
+        }
+        __syncthreads();
+        const uint32_t carry = s_carry;
+        const uint32_t excl = carry + s_warp[warp] + inc - v;
+        if (i < nblk) sums[i] = excl;
+        __syncthreads();
+        if (tid == 1023) s_carry = excl + v;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        counter[0] = (int32_t)(ws[0] + s_carry);
+        counter[1] = (int32_t)(ws[1] + N);
+    }
+}
+
+// phase 1c: intra-CTA prefix sums -> rays[N,3] = (ray id, offset, count).
+__global__ void __launch_bounds__(kRayBlock)
+k_march_train_rows(const uint32_t* __restrict__ ws, uint32_t nblk, uint32_t N,
+                   int32_t* __restrict__ rays) {
+    __shared__ uint32_t s_warp[kRayBlock / 32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t n = blockIdx.x * kRayBlock + tid;
+    const uint32_t c = n < N ? ws[4 + nblk + n] : 0u;
+    const uint32_t inc = warp_inclusive_scan(c, lane);
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    uint32_t woff = 0;
+#pragma unroll
+    for (int w = 0; w < kRayBlock / 32; ++w)
+        if (w < (int)warp) woff += s_warp[w];
+    if (n < N) {
+        const uint32_t row = ws[1] + n;
+        if (row < N) {  // the reference would write out of bounds here; rows are dropped instead
+            const uint32_t off = ws[0] + ws[4 + blockIdx.x] + woff + inc - c;
+            rays[(size_t)row * 3 + 0] = (int32_t)n;
+            rays[(size_t)row * 3 + 1] = (int32_t)off;
+            rays[(size_t)row * 3 + 2] = (int32_t)c;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// march_rays_train, phase 2: emit samples (reference raymarching.cu:463-533)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void zero_rows(float* xyzs, float* dirs, float* deltas, uint32_t r0,
+                                          uint32_t r1, uint32_t tid, uint32_t nthreads) {
+    for (size_t i = (size_t)r0 * 3 + tid; i < (size_t)r1 * 3; i += nthreads) {
+        xyzs[i] = 0.0f;
+        dirs[i] = 0.0f;
+    }
+    for (size_t i = (size_t)r0 * 2 + tid; i < (size_t)r1 * 2; i += nthreads) deltas[i] = 0.0f;
+}
+
+__global__ void __launch_bounds__(kRayBlock)
+k_march_train_write(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                    const uint8_t* __restrict__ grid, float bound, float dt_gamma,
+                    uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
+                    const float* __restrict__ nears, const float* __restrict__ fars,
+                    float* __restrict__ xyzs, float* __restrict__ dirs,
+                    float* __restrict__ deltas, const int32_t* __restrict__ rays,
+                    const int32_t* __restrict__ counter, const float* __restrict__ noises,
+                    uint32_t zero_tail_end) {
+    const uint32_t i = blockIdx.x * kRayBlock + threadIdx.x;
+    if (zero_tail_end > 0) {
+        const uint32_t z1 = min(M, zero_tail_end);
+        const uint32_t z0 = min((uint32_t)counter[0], z1);
+        zero_rows(xyzs, dirs, deltas, z0, z1, i, gridDim.x * kRayBlock);
+    }
+    if (i >= N) return;
+    const uint32_t n = (uint32_t)rays[(size_t)i * 3];
+    const uint32_t offset = (uint32_t)rays[(size_t)i * 3 + 1];
+    const uint32_t num_steps = (uint32_t)rays[(size_t)i * 3 + 2];
+    if (num_steps == 0) return;
+    if (offset + num_steps > M) {
+        // dropped ray (raymarching.cu:457).  Offsets are monotone, so only the first
+        // dropped ray starts inside the buffer; it clears what would stay unwritten.
+        if (zero_tail_end > 0 && offset < M)
+            zero_rows(xyzs, dirs, deltas, offset, min(M, zero_tail_end), 0, 1);
+        return;
+    }
+    const MarchParams p = make_march_params(bound, dt_gamma, max_steps, C, H);
+    const float* o = rays_o + (size_t)n * 3;
+    const float* d = rays_d + (size_t)n * 3;
+    const RayGeom r = make_ray(__ldg(o), __ldg(o + 1), __ldg(o + 2), __ldg(d), __ldg(d + 1),
+                               __ldg(d + 2));
+    const float far = __ldg(fars + n);
+    float t = first_t(p, __ldg(nears + n), __ldg(noises + n));
+    float last_t = t;
+    float* px = xyzs + (size_t)offset * 3;
+    float* pd = dirs + (size_t)offset * 3;
+    float2* pl = reinterpret_cast<float2*>(deltas) + offset;
+    uint32_t step = 0;
+    while (t < far && step < num_steps) {
+        float tt;
+        const Probe q = probe_at(p, r, grid, t, &tt);
+        if (q.occ) {
+            px[0] = q.x; px[1] = q.y; px[2] = q.z;
+            pd[0] = r.dx; pd[1] = r.dy; pd[2] = r.dz;
+            t = __fadd_rn(t, q.dt);
+            *pl = make_float2(q.dt, __fsub_rn(t, last_t));
+            last_t = t;
+            px += 3; pd += 3; ++pl;
+            ++step;
+        } else {
+            t = skip_to(p, t, tt);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// march_rays (inference)  (reference kernel raymarching.cu:809-928)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kRayBlock)
+k_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* __restrict__ rays_alive,
+             const float* __restrict__ rays_t, const float* __restrict__ rays_o,
+             const float* __restrict__ rays_d, float bound, float dt_gamma, uint32_t max_steps,
+             uint32_t C, uint32_t H, const uint8_t* __restrict__ grid,
+             const float* __restrict__ nears, const float* __restrict__ fars,
+             float* __restrict__ xyzs, float* __restrict__ dirs, float* __restrict__ deltas,
+             const float* __restrict__ noises, uint32_t M_padded) {
+    const uint32_t n = blockIdx.x * kRayBlock + threadIdx.x;
+    {
+        const uint32_t used = n_alive * n_step;
+        if (M_padded > used)
+            zero_rows(xyzs, dirs, deltas, used, M_padded, n, gridDim.x * kRayBlock);
+    }
+    if (n >= n_alive) return;
+    const int32_t index = rays_alive[n];
+    float* px = xyzs + (size_t)n * n_step * 3;
+    float* pd = dirs + (size_t)n * n_step * 3;
+    float2* pl = reinterpret_cast<float2*>(deltas) + (size_t)n * n_step;
+    uint32_t step = 0;
+    if (index >= 0) {
+        const MarchParams p = make_march_params(bound, dt_gamma, max_steps, C, H);
+        const float* o = rays_o + (size_t)index * 3;
+        const float* d = rays_d + (size_t)index * 3;
+        const RayGeom r = make_ray(__ldg(o), __ldg(o + 1), __ldg(o + 2), __ldg(d), __ldg(d + 1),
+                                   __ldg(d + 2));
+        const float far = __ldg(fars + index);
+        float t = __ldg(rays_t + index);
+        t = __fmaf_rn(__ldg(noises + n), clamp_dt(p, t), t);
+        float last_t = t;
+        while (t < far && step < n_step) {
+            float tt;
+            const Probe q = probe_at(p, r, grid, t, &tt);
+            if (q.occ) {
+                px[0] = q.x; px[1] = q.y; px[2] = q.z;
+                pd[0] = r.dx; pd[1] = r.dy; pd[2] = r.dz;
+                t = __fadd_rn(t, q.dt);
+                *pl = make_float2(q.dt, __fsub_rn(t, last_t));
+                last_t = t;
+                px += 3; pd += 3; ++pl;
+                ++step;
+            } else {
+                t = skip_to(p, t, tt);
+            }
+        }
+    }
+    for (; step < n_step; ++step) {  // unused slots read as "terminated" (delta == 0)
+        px[0] = px[1] = px[2] = 0.0f;
+        pd[0] = pd[1] = pd[2] = 0.0f;
+        *pl = make_float2(0.0f, 0.0f);
+        px += 3; pd += 3; ++pl;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Compositing.  Each warp owns 32 rays; the rays' sample streams are staged
+// through a per-warp shared-memory tile in chunks of kCK samples with coalesced
+// loads (half a warp per ray), then every lane walks its own ray front to back in
+// exactly the reference's operation order (raymarching.cu:618-645, 734-771).
+// ---------------------------------------------------------------------------
+constexpr int kCK = 16;                 // samples per ray per chunk
+constexpr int kSS = kCK + 1;            // sigma row stride (odd -> conflict free)
+constexpr int kSR = 3 * kCK + 1;        // rgb row stride
+constexpr int kSD = 2 * kCK + 1;        // deltas row stride
+constexpr int kWarpWords = 32 * (kSS + kSR + kSD);
+constexpr int kCompBlock = 128;
+constexpr size_t kCompSmem = (size_t)(kCompBlock / 32) * kWarpWords * sizeof(float);
+
+// exp(-sigma*delta) exactly as the reference's `__expf(-s * d)` executes
+__device__ __forceinline__ float alpha_of(float sigma, float delta) {
+    return __fsub_rn(1.0f, __expf(-__fmul_rn(sigma, delta)));
+}
+
+// Stage samples [k0, k0+need_l) of every live lane's ray into the warp tile.
+__device__ __forceinline__ void stage_chunk(const float* __restrict__ sigmas,
+                                            const float* __restrict__ rgbs,
+                                            const float* __restrict__ deltas, uint32_t first,
+                                            uint32_t need, uint32_t mask, int lane, float* s_sig,
+                                            float* s_rgb, float* s_del) {
+    const int half = lane >> 4, sub = lane & 15;
+#pragma unroll 1
+    for (int p = 0; p < 16; ++p) {
+        if (((mask >> (2 * p)) & 3u) == 0) continue;  // warp-uniform
+        const int src = 2 * p + half;
+        const uint32_t o = __shfl_sync(0xffffffffu, first, src);
+        const uint32_t nd = __shfl_sync(0xffffffffu, need, src);
+        if ((uint32_t)sub < nd) s_sig[src * kSS + sub] = __ldg(sigmas + o + sub);
+        const float* gr = rgbs + (size_t)o * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const uint32_t w = sub + 16 * c;
+            if (w < 3 * nd) s_rgb[src * kSR + w] = __ldg(gr + w);
+        }
+        const float* gd = deltas + (size_t)o * 2;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const uint32_t w = sub + 16 * c;
+            if (w < 2 * nd) s_del[src * kSD + w] = __ldg(gd + w);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kCompBlock)
+k_composite_train_fwd(const float* __restrict__ sigmas, const float* __restrict__ rgbs,
+                      const float* __restrict__ deltas, const int32_t* __restrict__ rays,
+                      uint32_t M, uint32_t N, float T_thresh, float* __restrict__ weights_sum,
+                      float* __restrict__ depth, float* __restrict__ image) {
+    extern __shared__ float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* s_sig = smem + warp * kWarpWords;
+    float* s_rgb = s_sig + 32 * kSS;
+    float* s_del = s_rgb + 32 * kSR;
+
+    const uint32_t i = blockIdx.x * kCompBlock + threadIdx.x;
+    uint32_t index = 0, offset = 0, cnt = 0;
+    const bool valid = i < N;
+    if (valid) {
+        index = (uint32_t)__ldg(rays + (size_t)i * 3);
+        offset = (uint32_t)__ldg(rays + (size_t)i * 3 + 1);
+        cnt = (uint32_t)__ldg(rays + (size_t)i * 3 + 2);
+    }
+    bool live = valid && cnt != 0 && offset + cnt <= M;
+
+    float T = 1.0f, r = 0.f, g = 0.f, b = 0.f, ws = 0.f, t = 0.f, d = 0.f;
+    uint32_t k0 = 0;
+    for (;;) {
+        const uint32_t need = live ? min(cnt - k0, (uint32_t)kCK) : 0u;
+        const uint32_t mask = __ballot_sync(0xffffffffu, need != 0);
+        if (mask == 0) break;
+        stage_chunk(sigmas, rgbs, deltas, offset + k0, need, mask, lane, s_sig, s_rgb, s_del);
+        __syncwarp();
+        const float* ps = s_sig + lane * kSS;
+        const float* pr = s_rgb + lane * kSR;
+        const float* pd = s_del + lane * kSD;
+        for (uint32_t k = 0; k < need; ++k) {
+            const float alpha = alpha_of(ps[k], pd[2 * k]);
+            const float weight = __fmul_rn(alpha, T);
+            r = __fmaf_rn(weight, pr[3 * k], r);
+            g = __fmaf_rn(weight, pr[3 * k + 1], g);
+            b = __fmaf_rn(weight, pr[3 * k + 2], b);
+            t = __fadd_rn(pd[2 * k + 1], t);
+            d = __fmaf_rn(weight, t, d);
+            ws = __fadd_rn(weight, ws);
+            T = __fmul_rn(__fsub_rn(1.0f, alpha), T);
+            if (T < T_thresh) { live = false; break; }
+        }
+        __syncwarp();
+        k0 += kCK;
+        if (k0 >= cnt) live = false;
+    }
+    if (valid) {
+        weights_sum[index] = ws;
+        depth[index] = d;
+        image[(size_t)index * 3] = r;
+        image[(size_t)index * 3 + 1] = g;
+        image[(size_t)index * 3 + 2] = b;
+    }
+}
+
+__global__ void __launch_bounds__(kCompBlock)
+k_composite_train_bwd(const float* __restrict__ grad_weights_sum,
+                      const float* __restrict__ grad_image, const float* __restrict__ sigmas,
+                      const float* __restrict__ rgbs, const float* __restrict__ deltas,
+                      const int32_t* __restrict__ rays, const float* __restrict__ weights_sum,
+                      const float* __restrict__ image, uint32_t M, uint32_t N, float T_thresh,
+                      float* __restrict__ grad_sigmas, float* __restrict__ grad_rgbs) {
+    extern __shared__ float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* s_sig = smem + warp * kWarpWords;
+    float* s_rgb = s_sig + 32 * kSS;
+    float* s_del = s_rgb + 32 * kSR;
+
+    const uint32_t i = blockIdx.x * kCompBlock + threadIdx.x;
+    uint32_t index = 0, offset = 0, cnt = 0;
+    const bool valid = i < N;
+    if (valid) {
+        index = (uint32_t)__ldg(rays + (size_t)i * 3);
+        offset = (uint32_t)__ldg(rays + (size_t)i * 3 + 1);
+        cnt = (uint32_t)__ldg(rays + (size_t)i * 3 + 2);
+    }
+    bool live = valid && cnt != 0 && offset + cnt <= M;
+
+    float gi0 = 0.f, gi1 = 0.f, gi2 = 0.f, gws1 = 0.f, rf = 0.f, gf = 0.f, bf = 0.f;
+    if (live) {
+        gi0 = __ldg(grad_image + (size_t)index * 3);
+        gi1 = __ldg(grad_image + (size_t)index * 3 + 1);
+        gi2 = __ldg(grad_image + (size_t)index * 3 + 2);
+        rf = __ldg(image + (size_t)index * 3);
+        gf = __ldg(image + (size_t)index * 3 + 1);
+        bf = __ldg(image + (size_t)index * 3 + 2);
+        gws1 = __fmul_rn(__ldg(grad_weights_sum + index),
+                         __fsub_rn(1.0f, __ldg(weights_sum + index)));
+    }
+    float T = 1.0f, r = 0.f, g = 0.f, b = 0.f;
+    uint32_t k0 = 0;
+    const int half = lane >> 4, sub = lane & 15;
+    for (;;) {
+        const uint32_t need = live ? min(cnt - k0, (uint32_t)kCK) : 0u;
+        const uint32_t mask = __ballot_sync(0xffffffffu, need != 0);
+        if (mask == 0) break;
+        stage_chunk(sigmas, rgbs, deltas, offset + k0, need, mask, lane, s_sig, s_rgb, s_del);
+        __syncwarp();
+        float* ps = s_sig + lane * kSS;
+        float* pr = s_rgb + lane * kSR;
+        const float* pd = s_del + lane * kSD;
+        uint32_t done = 0;
+        for (uint32_t k = 0; k < need; ++k) {
+            const float d0 = pd[2 * k];
+            const float c0 = pr[3 * k], c1 = pr[3 * k + 1], c2 = pr[3 * k + 2];
+            const float alpha = alpha_of(ps[k], d0);
+            const float weight = __fmul_rn(alpha, T);
+            r = __fmaf_rn(weight, c0, r);
+            g = __fmaf_rn(weight, c1, g);
+            b = __fmaf_rn(weight, c2, b);
+            T = __fmul_rn(__fsub_rn(1.0f, alpha), T);
+            pr[3 * k] = __fmul_rn(gi0, weight);
+            pr[3 * k + 1] = __fmul_rn(gi1, weight);
+            pr[3 * k + 2] = __fmul_rn(gi2, weight);
+            const float t0 = __fmaf_rn(c0, T, -__fsub_rn(rf, r));
+            const float t1 = __fmaf_rn(c1, T, -__fsub_rn(gf, g));
+            const float t2 = __fmaf_rn(c2, T, -__fsub_rn(bf, b));
+            const float acc = __fmaf_rn(gi2, t2, __fmaf_rn(gi0, t0, __fmul_rn(gi1, t1)));
+            ps[k] = __fmul_rn(d0, __fadd_rn(gws1, acc));
+            ++done;
+            if (T < T_thresh) { live = false; break; }
+        }
+        __syncwarp();
+        // coalesced write-back of the gradients produced in this chunk
+        const uint32_t first = offset + k0;
+#pragma unroll 1
+        for (int p = 0; p < 16; ++p) {
+            if (((mask >> (2 * p)) & 3u) == 0) continue;
+            const int src = 2 * p + half;
+            const uint32_t o = __shfl_sync(0xffffffffu, first, src);
+            const uint32_t nd = __shfl_sync(0xffffffffu, done, src);
+            if ((uint32_t)sub < nd) grad_sigmas[o + sub] = s_sig[src * kSS + sub];
+            float* gr = grad_rgbs + (size_t)o * 3;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const uint32_t w = sub + 16 * c;
+                if (w < 3 * nd) gr[w] = s_rgb[src * kSR + w];
+            }
+        }
+        __syncwarp();
+        k0 += kCK;
+        if (k0 >= cnt) live = false;
+    }
+}
+
+// composite_rays (inference, in place)  (reference kernel raymarching.cu:967-1053)
+__global__ void __launch_bounds__(kCompBlock)
+k_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh,
+                 int32_t* __restrict__ rays_alive, float* __restrict__ rays_t,
+                 const float* __restrict__ sigmas, const float* __restrict__ rgbs,
+                 const float* __restrict__ deltas, float* __restrict__ weights_sum,
+                 float* __restrict__ depth, float* __restrict__ image) {
+    extern __shared__ float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* s_sig = smem + warp * kWarpWords;
+    float* s_rgb = s_sig + 32 * kSS;
+    float* s_del = s_rgb + 32 * kSR;
+
+    const uint32_t n = blockIdx.x * kCompBlock + threadIdx.x;
+    const bool valid = n < n_alive;
+    int32_t index = -1;
+    if (valid) index = rays_alive[n];
+    bool live = valid && index >= 0;
+
+    float t = 0.f, ws = 0.f, d = 0.f, r = 0.f, g = 0.f, b = 0.f;
+    if (live) {
+        t = rays_t[index];
+        ws = weights_sum[index];
+        d = depth[index];
+        r = image[(size_t)index * 3];
+        g = image[(size_t)index * 3 + 1];
+        b = image[(size_t)index * 3 + 2];
+    }
+    const bool owner = live;
+    uint32_t step = 0;
+    uint32_t k0 = 0;
+    const uint32_t first = n * n_step;
+    for (;;) {
+        const uint32_t need = live ? min(n_step - k0, (uint32_t)kCK) : 0u;
+        const uint32_t mask = __ballot_sync(0xffffffffu, need != 0);
+        if (mask == 0) break;
+        stage_chunk(sigmas, rgbs, deltas, first + k0, need, mask, lane, s_sig, s_rgb, s_del);
+        __syncwarp();
+        const float* ps = s_sig + lane * kSS;
+        const float* pr = s_rgb + lane * kSR;
+        const float* pd = s_del + lane * kSD;
+        for (uint32_t k = 0; k < need; ++k) {
+            const float d0 = pd[2 * k];
+            if (d0 == 0.0f) { live = false; break; }
+            const float alpha = alpha_of(ps[k], d0);
+            const float T = __fsub_rn(1.0f, ws);
+            const float weight = __fmul_rn(alpha, T);
+            ws = __fadd_rn(ws, weight);
+            t = __fadd_rn(pd[2 * k + 1], t);
+            d = __fmaf_rn(weight, t, d);
+            r = __fmaf_rn(weight, pr[3 * k], r);
+            g = __fmaf_rn(weight, pr[3 * k + 1], g);
+            b = __fmaf_rn(weight, pr[3 * k + 2], b);
+            if (T < T_thresh) { live = false; break; }
+            ++step;
+        }
+        __syncwarp();
+        k0 += kCK;
+        if (k0 >= n_step) live = false;
+    }
+    if (owner) {
+        if (step < n_step) rays_alive[n] = -1;
+        else rays_t[index] = t;
+        weights_sum[index] = ws;
+        depth[index] = d;
+        image[(size_t)index * 3] = r;
+        image[(size_t)index * 3 + 1] = g;
+        image[(size_t)index * 3 + 2] = b;
+    }
+}
+
+bool g_comp_attr_set = false;
+int ensure_comp_attrs() {
+    if (g_comp_attr_set) return NVSF_OK;
+    cudaError_t e;
+    e = cudaFuncSetAttribute(k_composite_train_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)kCompSmem);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(k_composite_train_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)kCompSmem);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(k_composite_rays, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)kCompSmem);
+    if (e != cudaSuccess) return (int)e;
+    g_comp_attr_set = true;
+    return NVSF_OK;
+}
+
+inline bool march_cfg_ok(uint32_t C, uint32_t H, uint32_t max_steps) {
+    // 3x10-bit Morton code; C*H^3 must fit the uint32 index of the reference
+    return C >= 1 && C <= 31 && H >= 1 && H <= 1024 && max_steps >= 1 &&
+           (uint64_t)C * H * H * H <= 0xffffffffull;
+}
+
+}  // namespace
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+extern "C" {
+
+int nvsf_abi_version(void) { return NVSF_B200_ABI_VERSION; }
+
+const char* nvsf_status_string(int status) {
+    if (status == NVSF_OK) return "ok";
+    if (status == NVSF_E_INVALID) return "nvsf: invalid argument";
+    if (status == NVSF_E_WORKSPACE) return "nvsf: workspace too small";
+    if (status > 0) return cudaGetErrorString((cudaError_t)status);
+    return "nvsf: unknown status";
+}
+
+int nvsf_near_far_from_aabb(const float* rays_o, const float* rays_d, const float* aabb,
+                            uint32_t N, float min_near, float* nears, float* fars,
+                            void* stream) {
+    if (N == 0) return NVSF_OK;
+    if (!rays_o || !rays_d || !aabb || !nears || !fars) return NVSF_E_INVALID;
+    k_near_far_from_aabb<kTileBlock>
+        <<<nvsf_div_up(N, (uint32_t)kTileBlock), kTileBlock, 0, (cudaStream_t)stream>>>(
+            rays_o, rays_d, aabb, N, min_near, nears, fars);
+    return nvsf_launch_status();
+}
+
+int nvsf_sph_from_ray(const float* rays_o, const float* rays_d, float radius, uint32_t N,
+                      float* coords, void* stream) {
+    if (N == 0) return NVSF_OK;
+    if (!rays_o || !rays_d || !coords) return NVSF_E_INVALID;
+    k_sph_from_ray<kTileBlock>
+        <<<nvsf_div_up(N, (uint32_t)kTileBlock), kTileBlock, 0, (cudaStream_t)stream>>>(
+            rays_o, rays_d, radius, N, coords);
+    return nvsf_launch_status();
+}
+
+int nvsf_morton3D(const int32_t* coords, uint32_t N, int32_t* indices, void* stream) {
+    if (N == 0) return NVSF_OK;
+    if (!coords || !indices) return NVSF_E_INVALID;
+    k_morton3D<kTileBlock>
+        <<<nvsf_div_up(N, (uint32_t)kTileBlock), kTileBlock, 0, (cudaStream_t)stream>>>(
+            coords, N, indices);
+    return nvsf_launch_status();
+}
+
+int nvsf_morton3D_invert(const int32_t* indices, uint32_t N, int32_t* coords, void* stream) {
+    if (N == 0) return NVSF_OK;
+    if (!coords || !indices) return NVSF_E_INVALID;
+    k_morton3D_invert<kTileBlock>
+        <<<nvsf_div_up(N, (uint32_t)kTileBlock), kTileBlock, 0, (cudaStream_t)stream>>>(
+            indices, N, coords);
+    return nvsf_launch_status();
+}
+
+int nvsf_packbits(const float* grid, uint32_t N, float density_thresh, uint8_t* bitfield,
+                  void* stream) {
+    if (N == 0) return NVSF_OK;
+    if (!grid || !bitfield) return NVSF_E_INVALID;
+    cudaStream_t s = (cudaStream_t)stream;
+    uint32_t done = 0;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(grid) & 15u) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(bitfield) & 3u) == 0);
+    const uint32_t bytes_per_super = kPackIters * 32 * 4 / 8;  // 128 bytes out per warp pass
+    if (aligned && N >= bytes_per_super) {
+        const uint32_t n_super = N / bytes_per_super;
+        const uint32_t warps_per_block = 256 / 32;
+        k_packbits_vec<<<nvsf_div_up(n_super, warps_per_block), 256, 0, s>>>(
+            reinterpret_cast<const float4*>(grid), n_super, density_thresh,
+            reinterpret_cast<uint32_t*>(bitfield));
+        done = n_super * bytes_per_super;
+    }
+    if (done < N) {
+        k_packbits_scalar<<<nvsf_div_up(N - done, 256u), 256, 0, s>>>(grid, done, N,
+                                                                      density_thresh, bitfield);
+    }
+    return nvsf_launch_status();
+}
+
+size_t nvsf_march_rays_train_workspace_bytes(uint32_t N) {
+    const size_t nblk = nvsf_div_up((size_t)N, (size_t)kRayBlock);
+    return (4 + nblk + (size_t)N) * sizeof(uint32_t);
+}
+
+int nvsf_march_rays_train_count(const float* rays_o, const float* rays_d, const uint8_t* grid,
+                                float bound, float dt_gamma, uint32_t max_steps, uint32_t N,
+                                uint32_t C, uint32_t H, const float* nears, const float* fars,
+                                int32_t* rays, int32_t* counter, const float* noises,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+    if (N == 0) return NVSF_OK;
+    if (!rays_o || !rays_d || !grid || !nears || !fars || !rays || !counter || !noises ||
+        !workspace)
+        return NVSF_E_INVALID;
+    if (!march_cfg_ok(C, H, max_steps)) return NVSF_E_INVALID;
+    if (workspace_bytes < nvsf_march_rays_train_workspace_bytes(N)) return NVSF_E_WORKSPACE;
+    cudaStream_t s = (cudaStream_t)stream;
+    const uint32_t nblk = nvsf_div_up(N, (uint32_t)kRayBlock);
+    uint32_t* ws = reinterpret_cast<uint32_t*>(workspace);
+    k_march_train_count<<<nblk, kRayBlock, 0, s>>>(rays_o, rays_d, grid, bound, dt_gamma,
+                                                   max_steps, N, C, H, nears, fars, noises,
+                                                   counter, ws, nblk);
+    k_march_train_scan<<<1, 1024, 0, s>>>(ws, nblk, N, counter);
+    k_march_train_rows<<<nblk, kRayBlock, 0, s>>>(ws, nblk, N, rays);
+    return nvsf_launch_status();
+}
+
+int nvsf_march_rays_train_write(const float* rays_o, const float* rays_d, const uint8_t* grid,
+                                float bound, float dt_gamma, uint32_t max_steps, uint32_t N,
+                                uint32_t C, uint32_t H, uint32_t M, const float* nears,
+                                const float* fars, float* xyzs, float* dirs, float* deltas,
+                                const int32_t* rays, const int32_t* counter,
+                                const float* noises, uint32_t zero_tail_end, void* stream) {
+    if (N == 0) return NVSF_OK;
+    if (!rays_o || !rays_d || !grid || !nears || !fars || !rays || !counter || !noises)
+        return NVSF_E_INVALID;
+    if (M > 0 && (!xyzs || !dirs || !deltas)) return NVSF_E_INVALID;
+    if (!march_cfg_ok(C, H, max_steps)) return NVSF_E_INVALID;
+    const uint32_t nblk = nvsf_div_up(N, (uint32_t)kRayBlock);
+    k_march_train_write<<<nblk, kRayBlock, 0, (cudaStream_t)stream>>>(
+        rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears, fars, xyzs, dirs,
+        deltas, rays, counter, noises, zero_tail_end);
+    return nvsf_launch_status();
+}
+
+int nvsf_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t* grid,
+                          float bound, float dt_gamma, uint32_t max_steps, uint32_t N,
+                          uint32_t C, uint32_t H, uint32_t M, const float* nears,
+                          const float* fars, float* xyzs, float* dirs, float* deltas,
+                          int32_t* rays, int32_t* counter, const float* noises,
+                          void* workspace, size_t workspace_bytes, void* stream) {
+    int st = nvsf_march_rays_train_count(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C,
+                                         H, nears, fars, rays, counter, noises, workspace,
+                                         workspace_bytes, stream);
+    if (st != NVSF_OK) return st;
+    return nvsf_march_rays_train_write(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C,
+                                       H, M, nears, fars, xyzs, dirs, deltas, rays, counter,
+                                       noises, 0u, stream);
+}
+
+int nvsf_composite_rays_train_forward(const float* sigmas, const float* rgbs,
+                                      const float* deltas, const int32_t* rays, uint32_t M,
+                                      uint32_t N, float T_thresh, float* weights_sum,
+                                      float* depth, float* image, void* stream) {
+    if (N == 0) return NVSF_OK;
+    if (!rays || !weights_sum || !depth || !image) return NVSF_E_INVALID;
+    if (M > 0 && (!sigmas || !rgbs || !deltas)) return NVSF_E_INVALID;
+    int st = ensure_comp_attrs();
+    if (st != NVSF_OK) return st;
+    k_composite_train_fwd<<<nvsf_div_up(N, (uint32_t)kCompBlock), kCompBlock, kCompSmem,
+                            (cudaStream_t)stream>>>(sigmas, rgbs, deltas, rays, M, N, T_thresh,
+                                                    weights_sum, depth, image);
+    return nvsf_launch_status();
+}
+
+int nvsf_composite_rays_train_backward(const float* grad_weights_sum, const float* grad_image,
+                                       const float* sigmas, const float* rgbs,
+                                       const float* deltas, const int32_t* rays,
+                                       const float* weights_sum, const float* image,
+                                       uint32_t M, uint32_t N, float T_thresh,
+                                       float* grad_sigmas, float* grad_rgbs, void* stream) {
+    if (N == 0 || M == 0) return NVSF_OK;
+    if (!grad_weights_sum || !grad_image || !sigmas || !rgbs || !deltas || !rays ||
+        !weights_sum || !image || !grad_sigmas || !grad_rgbs)
+        return NVSF_E_INVALID;
+    int st = ensure_comp_attrs();
+    if (st != NVSF_OK) return st;
+    k_composite_train_bwd<<<nvsf_div_up(N, (uint32_t)kCompBlock), kCompBlock, kCompSmem,
+                            (cudaStream_t)stream>>>(grad_weights_sum, grad_image, sigmas, rgbs,
+                                                    deltas, rays, weights_sum, image, M, N,
+                                                    T_thresh, grad_sigmas, grad_rgbs);
+    return nvsf_launch_status();
+}
+
+int nvsf_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive,
+                    const float* rays_t, const float* rays_o, const float* rays_d, float bound,
+                    float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H,
+                    const uint8_t* grid, const float* nears, const float* fars, float* xyzs,
+                    float* dirs, float* deltas, const float* noises, uint32_t M_padded,
+                    void* stream) {
+    if (n_alive == 0 && M_padded == 0) return NVSF_OK;
+    if (!xyzs || !dirs || !deltas) return NVSF_E_INVALID;
+    if (n_alive > 0 && (!rays_alive || !rays_t || !rays_o || !rays_d || !grid || !nears ||
+                        !fars || !noises || n_step == 0))
+        return NVSF_E_INVALID;
+    if (!march_cfg_ok(C, H, max_steps)) return NVSF_E_INVALID;
+    const uint32_t nblk = n_alive > 0 ? nvsf_div_up(n_alive, (uint32_t)kRayBlock) : 1u;
+    k_march_rays<<<nblk, kRayBlock, 0, (cudaStream_t)stream>>>(
+        n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H,
+        grid, nears, fars, xyzs, dirs, deltas, noises, M_padded);
+    return nvsf_launch_status();
+}
+
+int nvsf_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t* rays_alive,
+                        float* rays_t, const float* sigmas, const float* rgbs,
+                        const float* deltas, float* weights_sum, float* depth, float* image,
+                        void* stream) {
+    if (n_alive == 0 || n_step == 0) return NVSF_OK;
+    if (!rays_alive || !rays_t || !sigmas || !rgbs || !deltas || !weights_sum || !depth ||
+        !image)
+        return NVSF_E_INVALID;
+    int st = ensure_comp_attrs();
+    if (st != NVSF_OK) return st;
+    k_composite_rays<<<nvsf_div_up(n_alive, (uint32_t)kCompBlock), kCompBlock, kCompSmem,
+                       (cudaStream_t)stream>>>(n_alive, n_step, T_thresh, rays_alive, rays_t,
+                                               sigmas, rgbs, deltas, weights_sum, depth, image);
+    return nvsf_launch_status();
+}
+
+}  // extern "C"
