@@ -275,8 +275,11 @@ def test_composite_rays_train_forward_backward(pkg, oracle, ref_ext, fill, T_thr
     (ws * dev(g_ws)).sum().add((image * dev(g_img)).sum()).add(depth.sum()).backward()
     egs, egr = oracle.composite_rays_train_backward(g_ws, g_img, sig, rgb, host(deltas), rays_h,
                                                     host(ws), host(image), T_thresh)
-    rel_close(host(sig_t.grad), egs, rtol=2e-5, atol=1e-6 * scale, what="grad_sigmas")
-    rel_close(host(rgb_t.grad), egr, what="grad_rgbs")
+    # per-sample gradients carry alpha = 1 - exp(-sigma*delta) un-summed: for tiny sigma*delta the
+    # oracle's exp2f and the GPU's ex2.approx differ by ~2^-22 ABSOLUTE in alpha, so the bound is
+    # absolute here (the reference-extension comparison below is bit-exact).
+    rel_close(host(sig_t.grad), egs, rtol=2e-5, atol=2e-5, what="grad_sigmas")
+    rel_close(host(rgb_t.grad), egr, rtol=1e-5, atol=5e-6, what="grad_rgbs")
     if ref_ext is not None:
         rws = torch.empty(N, device="cuda"); rde = torch.empty(N, device="cuda"); rim = torch.empty(N, 3, device="cuda")
         ref_ext.composite_rays_train_forward(dev(sig), dev(rgb), deltas, dev(rays_h), M, N, T_thresh, rws, rde, rim)

@@ -1,0 +1,139 @@
+"""Micro-benchmark of the ray-marching operators: this repo's kernels vs the reference
+extension rebuilt for sm_100a (when oracle/_ref is present), CUDA-event timed, L2 flushed
+between iterations.  Development tool; bench.py is the judged benchmark."""
+import importlib
+import importlib.util
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import cases  # noqa: E402
+
+S = cases.S
+pkg = importlib.import_module("selfsupervised-nvsf_b200")
+rm = pkg.raymarching
+L = pkg._lib.lib()
+C, H, BOUND = S.CASCADE, S.GRID_SIZE, S.BOUND
+
+
+def load_ref():
+    path = os.path.join(ROOT, "oracle", "_ref", "_raymarching_ref.so")
+    if not os.path.exists(path):
+        return None
+    spec = importlib.util.spec_from_file_location("_raymarching_ref", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+_flush = None
+
+
+def timeit(fn, iters=10, warm=3):
+    global _flush
+    if _flush is None:
+        _flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(iters):
+        _flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return float(np.median(ts))
+
+
+def main():
+    ref = load_ref()
+    res = []
+    for kind, n in [("lidar", 4096), ("lidar", -1), ("camera", -1)]:
+        for fill in ["full", "shell", "random5"]:
+            o, d, nears, fars, noises = cases.march_inputs(kind, n, seed=1, perturb=True)
+            N = o.shape[0]
+            bf = cases.bitfield(fill, seed=2)
+            t_o, t_d, t_bf, t_n, t_f, t_no = map(dev, (o, d, bf, nears, fars, noises))
+            x, dd, l, r = rm.march_rays_train(t_o, t_d, BOUND, t_bf, C, H, t_n, t_f, None, -1, False, -1, True, S.DT_GAMMA, 1024, t_no)
+            M = x.shape[0]
+            ws_bytes = L.nvsf_march_rays_train_workspace_bytes(N)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+            counter = torch.zeros(2, dtype=torch.int32, device="cuda")
+            rays = torch.empty(N, 3, dtype=torch.int32, device="cuda")
+            X = torch.empty(max(M, 1), 3, device="cuda"); D = torch.empty(max(M, 1), 3, device="cuda"); Dl = torch.empty(max(M, 1), 2, device="cuda")
+
+            def ours():
+                counter.zero_()
+                st = L.nvsf_march_rays_train(t_o.data_ptr(), t_d.data_ptr(), t_bf.data_ptr(), BOUND, S.DT_GAMMA, 1024, N, C, H, M,
+                                             t_n.data_ptr(), t_f.data_ptr(), X.data_ptr(), D.data_ptr(), Dl.data_ptr(), rays.data_ptr(),
+                                             counter.data_ptr(), t_no.data_ptr(), ws.data_ptr(), ws_bytes, torch.cuda.current_stream().cuda_stream)
+                assert st == 0
+            t_ours = timeit(ours)
+            row = dict(op="march_rays_train", kind=kind, fill=fill, N=N, M=M, ms=t_ours,
+                       GBps=(48 * N + 32 * M) / t_ours / 1e6)
+            if ref is not None:
+                def theirs():
+                    counter.zero_()
+                    ref.march_rays_train(t_o, t_d, t_bf, BOUND, S.DT_GAMMA, 1024, N, C, H, max(M, 1), t_n, t_f, X, D, Dl, rays, counter, t_no)
+                row["ref_ms"] = timeit(theirs)
+            res.append(row); print(json.dumps(row), flush=True)
+            if M == 0:
+                continue
+            sig, rgb = cases.field_values(M, seed=3); sig *= 30
+            t_s, t_c = dev(sig), dev(rgb)
+            rm.march_rays_train(t_o, t_d, BOUND, t_bf, C, H, t_n, t_f, None, -1, False, -1, True, S.DT_GAMMA, 1024, t_no)
+            rays = r.contiguous()
+            wsum = torch.empty(N, device="cuda"); dep = torch.empty(N, device="cuda"); img = torch.empty(N, 3, device="cuda")
+            st = torch.cuda.current_stream().cuda_stream
+
+            def cf():
+                assert L.nvsf_composite_rays_train_forward(t_s.data_ptr(), t_c.data_ptr(), l.data_ptr(), rays.data_ptr(), M, N, 1e-4,
+                                                           wsum.data_ptr(), dep.data_ptr(), img.data_ptr(), st) == 0
+            t1 = timeit(cf)
+            row = dict(op="composite_fwd", kind=kind, fill=fill, N=N, M=M, ms=t1, GBps=(24 * M + 32 * N) / t1 / 1e6)
+            if ref is not None:
+                row["ref_ms"] = timeit(lambda: ref.composite_rays_train_forward(t_s, t_c, l, rays, M, N, 1e-4, wsum, dep, img))
+            res.append(row); print(json.dumps(row), flush=True)
+            gws = torch.randn(N, device="cuda"); gim = torch.randn(N, 3, device="cuda")
+            gs = torch.zeros(M, device="cuda"); gr = torch.zeros(M, 3, device="cuda")
+
+            def cb():
+                assert L.nvsf_composite_rays_train_backward(gws.data_ptr(), gim.data_ptr(), t_s.data_ptr(), t_c.data_ptr(), l.data_ptr(),
+                                                            rays.data_ptr(), wsum.data_ptr(), img.data_ptr(), M, N, 1e-4, gs.data_ptr(),
+                                                            gr.data_ptr(), st) == 0
+            t2 = timeit(cb)
+            row = dict(op="composite_bwd", kind=kind, fill=fill, N=N, M=M, ms=t2, GBps=(40 * M + 48 * N) / t2 / 1e6)
+            if ref is not None:
+                row["ref_ms"] = timeit(lambda: ref.composite_rays_train_backward(gws, gim, t_s, t_c, l, rays, wsum, img, M, N, 1e-4, gs, gr))
+            res.append(row); print(json.dumps(row), flush=True)
+    # light ops
+    o, d = S.camera_rays(-1, seed=0)
+    t_o, t_d, t_a = dev(o), dev(d), dev(S.AABB)
+    N = o.shape[0]
+    n_, f_ = torch.empty(N, device="cuda"), torch.empty(N, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    t = timeit(lambda: L.nvsf_near_far_from_aabb(t_o.data_ptr(), t_d.data_ptr(), t_a.data_ptr(), N, 0.01, n_.data_ptr(), f_.data_ptr(), st))
+    row = dict(op="near_far", N=N, ms=t, GBps=32 * N / t / 1e6)
+    if ref is not None:
+        row["ref_ms"] = timeit(lambda: ref.near_far_from_aabb(t_o, t_d, t_a, N, 0.01, n_, f_))
+    print(json.dumps(row), flush=True)
+    g = dev(S.density_grid("random5"))
+    out = torch.empty(g.numel() // 8, dtype=torch.uint8, device="cuda")
+    t = timeit(lambda: L.nvsf_packbits(g.data_ptr(), out.numel(), 0.01, out.data_ptr(), st))
+    row = dict(op="packbits", N=out.numel(), ms=t, GBps=(g.numel() * 4 + out.numel()) / t / 1e6)
+    if ref is not None:
+        row["ref_ms"] = timeit(lambda: ref.packbits(g, out.numel(), 0.01, out))
+    print(json.dumps(row), flush=True)
+
+
+if __name__ == "__main__":
+    main()
