@@ -33,7 +33,7 @@ extern "C" {
 #define NVSF_E_WORKSPACE (-2) /* workspace too small */
 
 /* ABI version of this header; bumped on any signature change. */
-#define NVSF_B200_ABI_VERSION 3
+#define NVSF_B200_ABI_VERSION 4
 int nvsf_abi_version(void);
 /* Human-readable text for a status returned by any nvsf_* call. */
 const char* nvsf_status_string(int status);
@@ -138,6 +138,95 @@ int nvsf_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive
 int nvsf_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t* rays_alive,
                         float* rays_t, const float* sigmas, const float* rgbs,
                         const float* deltas, float* weights_sum, float* depth, float* image,
+                        void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* Part 2 — field (encoders + heads) and uniform-sample renderer               */
+/* ------------------------------------------------------------------------- */
+
+/* One level of a tcnn-style multiresolution grid (tiny-cuda-nn GridEncoding: scale =
+ * exp2(l*log2(per_level_scale))*base-1, res = ceil(scale)+1, size = min(align8(res^D), 2^log2T)
+ * entries, offset = first entry of the level, hashed = res^D > size).  Computed on the host. */
+#define NVSF_MAX_LEVELS 16
+#define NVSF_MAX_PLANE_SCALES 8
+typedef struct {
+    float scale;
+    uint32_t res, size, offset, hashed;
+} nvsf_grid_level_t;
+
+/* Architecture of the reference field (network_dynamic.py:13-192, hash_field.py:92-141,
+ * flow_field.py:41-103, planes_field.py:142-194).  Fixed by this build (checked, else
+ * NVSF_E_INVALID): 4 features per hash level (= the 4 temporal basis functions of HashGridT),
+ * 8 features per flow-grid level, 8 features per plane, 64 hidden units, 15 geometry features,
+ * sigma net 120->64->16, head nets (87|31)->64->64->(1|3), flow MLP 32->64->64->6. */
+typedef struct {
+    float bound;              /* scene box [-bound, bound]^3 */
+    float density_scale;      /* NeRFRenderer.density_scale */
+    uint32_t active_sensor;   /* doubles the exponent (renderer_dynamic.py:187-189) */
+    uint32_t num_frames;      /* frame_idx = int(t*(num_frames-1)) */
+    uint32_t time_resolution; /* time slices of HashGridT == time rows of the planes */
+    uint32_t hs_levels;       /* static 3-D hash grid (HashGrid4D.hash_static), must be 8 */
+    uint32_t hs_entries;
+    nvsf_grid_level_t hs[NVSF_MAX_LEVELS];
+    uint32_t hd_levels;       /* dynamic 2-D hash grids, planes xy / xz / yz, must be 8 */
+    uint32_t hd_entries[3];   /* entries per time slice */
+    nvsf_grid_level_t hd[3][NVSF_MAX_LEVELS];
+    uint32_t fl_levels;       /* flow 3-D hash grid (FlowField.grid_enc), must be 16 */
+    uint32_t fl_entries;
+    nvsf_grid_level_t fl[NVSF_MAX_LEVELS];
+    uint32_t pl_scales;       /* K-planes scales, must be 4 */
+    uint32_t pl_res[NVSF_MAX_PLANE_SCALES]; /* spatial resolution per scale */
+} nvsf_field_config_t;
+
+/* fp32 master parameters of ONE modality (lidar or camera) in the reference's own layouts
+ * (tcnn flat `params`, Planes4D [1,F,H,W] tensors concatenated scale-major then plane-major in
+ * itertools.combinations(range(4),2) order, nn.Linear [out,in] weights). */
+typedef struct {
+    const float* hash_static;  /* hash_encoder_*.hash_static.params */
+    const float* hash_dynamic; /* hash_encoder_*.hash_dynamic.{0,1,2}.hash_t.{k}.params, concatenated */
+    const float* planes;       /* planes_encoder_*.planes.{s}.{c} */
+    const float* flow_grid;    /* flow_net.grid_enc.params */
+    const float* flow_mlp;     /* flow_net.mlp.{0,2,4}.weight */
+    const float* sigma_net;    /* sigma_net.params */
+    const float* head_a;       /* lidar: intensity_net.params ; camera: color_net.params */
+    const float* head_b;       /* lidar: raydrop_net.params   ; camera: NULL */
+} nvsf_field_params_t;
+
+/* Bytes of the packed-field workspace for this config (device memory, caller-owned). */
+size_t nvsf_field_workspace_bytes(const nvsf_field_config_t* cfg);
+
+/* Re-pack the fp32 master parameters into the kernel layouts (fp16 static hash table, channel-
+ * last planes, fp16 MLP weights).  Call after every parameter update. lidar != 0 selects the
+ * LiDAR heads (Frequency direction encoding, intensity + raydrop nets). */
+int nvsf_field_pack_params(const nvsf_field_config_t* cfg, const nvsf_field_params_t* params,
+                           uint32_t lidar, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Collapse everything that depends only on the frame time t (device scalar `time`, the [1,1]
+ * tensor the reference passes around) into small tables: the time-slice blend + cubic temporal
+ * basis of HashGridT (hash_field.py:65-88) and of FlowField.interpT (flow_field.py:105-114), and
+ * the time rows of the (x,t),(y,t),(z,t) planes, for the three query times t, (f+1)/F, (f-1)/F
+ * of network_dynamic.py:242-271.  Call after nvsf_field_pack_params and whenever t changes. */
+int nvsf_field_pack_time(const nvsf_field_config_t* cfg, const nvsf_field_params_t* params,
+                         const float* time, void* workspace, size_t workspace_bytes, void* stream);
+
+/* replaces NeRFNetwork.density (network_dynamic.py:213-287) for n points x [n,3] in
+ * [-bound,bound]: sigma [n] f32, geo [n,16] f16 (column 0 = raw sigma logit, 1..15 = geo_feat).
+ * Optional debug outputs (may be NULL): features [n,128] f16 (the 120 sigma-net inputs in the
+ * reference's concat order, network_dynamic.py:276, zero padded) and flow [n,6] f32. */
+int nvsf_field_density(const nvsf_field_config_t* cfg, const void* workspace, const float* x,
+                       uint32_t n, float* sigma, void* geo, void* features, float* flow,
+                       void* stream);
+
+/* replaces NeRFRenderer.run (renderer_dynamic.py:109-265) for N rays with S uniform samples.
+ * nears/fars [N]; noise [N,S] in [0,1) or NULL (perturb=False); bg_color used for camera only.
+ * scratch: N*S*(4+32) bytes (sigma f32 + geo f16[16] per sample).
+ * Outputs: depth [N], image [N,2|3], weights_sum [N]; weights/z_vals [N,S] optional (NULL ok). */
+size_t nvsf_render_uniform_scratch_bytes(uint32_t N, uint32_t S);
+int nvsf_render_uniform(const nvsf_field_config_t* cfg, const void* workspace, uint32_t lidar,
+                        const float* rays_o, const float* rays_d, const float* nears,
+                        const float* fars, const float* noise, uint32_t N, uint32_t S,
+                        float bg_color, void* scratch, size_t scratch_bytes, float* depth,
+                        float* image, float* weights_sum, float* weights, float* z_vals,
                         void* stream);
 
 #ifdef __cplusplus

@@ -15,6 +15,15 @@ layout shared by the oracle and the product:
 `style`: 'init' mimics the reference initialisers (tables U(-1e-4,1e-4), space planes U(0.1,0.5),
 time planes 1, Xavier-uniform MLPs, last flow layer N(0,1e-3)); 'trained' uses larger tables
 (U(-1,1)), perturbed time planes and a stronger flow so that every branch matters numerically.
+
+Conditioning note.  The warped queries evaluate the dynamic hash grids at x + flow(x); at the
+finest level (resolution 32768) one cell is 3e-5 wide, so ANY half-precision evaluation of the
+flow MLP (the reference runs it under fp16 autocast, tcnn runs everything in fp16) moves the
+query by a visible fraction of a cell.  With white-noise tables that makes the output
+discontinuous in the flow and no two implementations can agree to 1e-2.  'trained' therefore
+lets the amplitude of the DYNAMIC hash tables decay with the level (0.5^level), as the tables
+of a trained multiresolution grid do, which keeps the comparison well conditioned without
+removing any branch.
 """
 import numpy as np
 import torch
@@ -56,13 +65,26 @@ def make_params(cfg, seed=0, style="trained", as_torch=True):
                 chunks.append(((rng.random(o * i, dtype=np.float32) * 2 - 1) * np.float32(b)))
         return np.concatenate(chunks)
 
+    def dyn_table():
+        v = table(sz["hash_dynamic"])
+        if style == "init":
+            return v
+        F, Tn, off = cfg.n_features_hash, cfg.time_resolution, 0
+        for pi in range(3):
+            for _ in range(Tn):
+                for l, lv in enumerate(cfg.dyn_levels[pi]):
+                    a, b = off + lv["offset"] * F, off + (lv["offset"] + lv["size"]) * F
+                    v[a:b] *= np.float32(0.5 ** l)
+                off += cfg.dyn_entries[pi] * F
+        return v
+
     h = cfg.hidden
     fin = cfg.flow_levels * cfg.flow_features // 4
     p = {}
     for m in ("lidar", "camera"):
-        p[m] = dict(hash_static=table(sz["hash_static"]), hash_dynamic=table(sz["hash_dynamic"]), planes=planes())
+        p[m] = dict(hash_static=table(sz["hash_static"]), hash_dynamic=dyn_table(), planes=planes())
     p["flow_grid"] = table(sz["flow_grid"])
-    p["flow_mlp"] = xavier([(h, fin), (h, h), (6, h)], last_std=1e-3 if style == "init" else 2e-2)
+    p["flow_mlp"] = xavier([(h, fin), (h, h), (6, h)], last_std=1e-3)
     p["sigma_net"] = xavier([(h, 128), (16, h)])
     if style != "init":
         p["sigma_net"] *= np.float32(0.5)

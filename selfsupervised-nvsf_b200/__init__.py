@@ -5,10 +5,13 @@ Importable as ``nvsf_b200`` (shim at the repository root) or via
 
 Sub-modules
     raymarching   drop-in for reference ``nvsf.nerf.raymarching.raymarching``
+    field         NeRFNetwork: density / flow / run / render of the reference model on the GPU kernels
     _lib          ctypes binding of the C ABI (include/nvsf_b200.h)
     build         compiles csrc/*.cu into libnvsf_b200.so with nvcc (sm_100a)
 """
 from . import _lib  # noqa: F401
 from . import raymarching  # noqa: F401
+from . import field  # noqa: F401
+from .field import NeRFNetwork  # noqa: F401
 
 __version__ = "0.1.0"

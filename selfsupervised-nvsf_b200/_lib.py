@@ -51,6 +51,14 @@ PROTOTYPES = {
          _u32, _p],
     ),
     "nvsf_composite_rays": (_int, [_u32, _u32, _f32, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    # Part 2 (struct pointers are refined to typed pointers in field.py)
+    "nvsf_field_workspace_bytes": (_sz, [_p]),
+    "nvsf_field_pack_params": (_int, [_p, _p, _u32, _p, _sz, _p]),
+    "nvsf_field_pack_time": (_int, [_p, _p, _p, _p, _sz, _p]),
+    "nvsf_field_density": (_int, [_p, _p, _p, _u32, _p, _p, _p, _p, _p]),
+    "nvsf_render_uniform_scratch_bytes": (_sz, [_u32, _u32]),
+    "nvsf_render_uniform": (_int, [_p, _p, _u32, _p, _p, _p, _p, _p, _u32, _u32, _f32, _p, _sz, _p,
+                                   _p, _p, _p, _p, _p]),
 }
 
 _lib = None
@@ -83,7 +91,7 @@ def lib():
     return _lib
 
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 def check(status, what=""):

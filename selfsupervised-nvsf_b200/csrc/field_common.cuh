@@ -1,0 +1,253 @@
+// Shared definitions of the field kernels: packed-workspace layout, time tables, warp-level
+// tensor-core helpers (mma.sync m16n8k16, fp16 in / fp32 accumulate) for the small MLPs.
+#pragma once
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+constexpr int kHidden = 64;       // n_neurons of every MLP (main_nvsf.py:53-59)
+constexpr int kFeat = 128;        // sigma-net input: 120 features zero-padded to 128
+constexpr int kGeo = 16;          // sigma-net output: logit + 15 geo features
+constexpr int kHashF = 4;         // features per hash level == temporal basis functions
+constexpr int kFlowF = 8;
+constexpr int kPlaneF = 8;
+constexpr int kHsLevels = 8, kHdLevels = 8, kFlLevels = 16, kPlScales = 4;
+constexpr int kFlowIn = 32;       // flow MLP input = 16 levels x (8/4) features
+
+// ---- per-call time tables (device), written by k_time_setup ---------------------------------
+struct TimeInfo {
+    float t[3];       // query times: t, (f+1)/F, (f-1)/F   (network_dynamic.py:244,260)
+    int valid[3];     // [0]=1, [1]= f < F-1, [2]= f > 0      (network_dynamic.py:242,258)
+    float lag[3][4];  // cubic Lagrange basis at t[q] on nodes {0,1/3,2/3,1} (hash_field.py:65-74)
+    int k1[3], k2[3]; // time slices floor/ceil(t*(Tres-1))   (hash_field.py:79-81)
+    float wk[3];      // idx - k1
+    int y0[3], y1[3]; // time rows of the (.,t) planes (grid_sample align_corners, border)
+    float wy[3];
+};
+
+// ---- packed workspace -------------------------------------------------------------------------
+// All offsets in bytes, 256-byte aligned.
+struct WsLayout {
+    size_t time;      // TimeInfo
+    size_t hs16;      // __half [hs_entries][4]                     static hash table in fp16
+    size_t pls;       // float  per scale: [3 planes xy,xz,yz][R][R][8]   channel-last space planes
+    size_t dyn;       // float  [3 queries][sum_p hd_entries[p]]    time-collapsed dynamic hash
+    size_t flow;      // float2 [fl_entries]                        time-collapsed flow grid
+    size_t pld;       // float  [3 queries] per scale: [3 planes xt,yt,zt][R][8]
+    size_t mlp;       // __half smem images of the MLP weights
+    size_t total;
+    size_t pls_scale[NVSF_MAX_PLANE_SCALES];  // float offsets inside pls
+    size_t pld_scale[NVSF_MAX_PLANE_SCALES];  // float offsets inside one query of pld
+    size_t pls_floats, pld_floats_per_q, dyn_per_q;
+    size_t dyn_plane[3];                      // float offsets inside one query of dyn
+};
+
+// MLP weight images (in halves), padded row strides so ldmatrix rows hit distinct banks.
+constexpr int kLdK32 = 40, kLdK64 = 72, kLdK128 = 136, kLdK16 = 24;
+constexpr int kFlowW1 = 0;                                   // [64][40]
+constexpr int kFlowW2 = kFlowW1 + kHidden * kLdK32;          // [64][72]
+constexpr int kFlowW3 = kFlowW2 + kHidden * kLdK64;          // [8][72]   rows 6,7 zero
+constexpr int kSigW1 = kFlowW3 + 8 * kLdK64;                 // [64][136]
+constexpr int kSigW2 = kSigW1 + kHidden * kLdK128;           // [16][72]
+constexpr int kDensityWHalves = kSigW2 + kGeo * kLdK64;      // end of the density-kernel image
+// head nets (2 slots; camera uses slot 0 only): per slot
+constexpr int kHeadDirMax = 72;                              // Frequency: 72, SH: 16
+constexpr int kHeadW1d = 0;                                  // [64][72]  direction part of layer 1
+constexpr int kHeadW1g = kHeadW1d + kHidden * kHeadDirMax;   // [64][24]  geo part (col 0 = 0)
+constexpr int kHeadW2 = kHeadW1g + kHidden * kLdK16;         // [64][72]
+constexpr int kHeadW3 = kHeadW2 + kHidden * kLdK64;          // [8][72]
+constexpr int kHeadHalves = kHeadW3 + 8 * kLdK64;
+constexpr int kHeadBase = (kDensityWHalves + 7) / 8 * 8;
+constexpr int kMlpHalves = kHeadBase + 2 * kHeadHalves;
+
+static inline size_t ws_align(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static inline bool field_cfg_ok(const nvsf_field_config_t* c) {
+    if (!c) return false;
+    if (c->hs_levels != kHsLevels || c->hd_levels != kHdLevels || c->fl_levels != kFlLevels ||
+        c->pl_scales != kPlScales)
+        return false;
+    if (c->time_resolution < 1 || c->num_frames < 1 || !(c->bound > 0.f)) return false;
+    for (int s = 0; s < kPlScales; ++s)
+        if (c->pl_res[s] < 2) return false;
+    return true;
+}
+
+static inline WsLayout make_ws_layout(const nvsf_field_config_t* c) {
+    WsLayout L;
+    size_t off = 0;
+    L.time = off; off = ws_align(off + sizeof(TimeInfo));
+    L.hs16 = off; off = ws_align(off + (size_t)c->hs_entries * kHashF * sizeof(__half));
+    size_t f = 0;
+    for (int s = 0; s < kPlScales; ++s) {
+        L.pls_scale[s] = f;
+        f += (size_t)3 * c->pl_res[s] * c->pl_res[s] * kPlaneF;
+    }
+    L.pls_floats = f;
+    L.pls = off; off = ws_align(off + f * sizeof(float));
+    size_t d = 0;
+    for (int p = 0; p < 3; ++p) { L.dyn_plane[p] = d; d += c->hd_entries[p]; }
+    L.dyn_per_q = d;
+    L.dyn = off; off = ws_align(off + 3 * d * sizeof(float));
+    L.flow = off; off = ws_align(off + (size_t)c->fl_entries * sizeof(float2));
+    size_t g = 0;
+    for (int s = 0; s < kPlScales; ++s) {
+        L.pld_scale[s] = g;
+        g += (size_t)3 * c->pl_res[s] * kPlaneF;
+    }
+    L.pld_floats_per_q = g;
+    L.pld = off; off = ws_align(off + 3 * g * sizeof(float));
+    L.mlp = off; off = ws_align(off + (size_t)kMlpHalves * sizeof(__half));
+    L.total = off;
+    return L;
+}
+
+// ---- device pointers into the packed workspace (kernel argument) -------------------------------
+struct FieldPtrs {
+    const uint2* hs16;
+    const float* pls;
+    const float* dyn;
+    const float2* flow;
+    const float* pld;
+    const __half* mlp;
+    const TimeInfo* ti;
+    uint32_t pls_scale[kPlScales];
+    uint32_t pld_scale[kPlScales];
+    uint32_t pld_per_q, dyn_per_q;
+    uint32_t dyn_plane[3];
+};
+
+FieldPtrs nvsf_make_field_ptrs(const nvsf_field_config_t* cfg, const void* workspace);
+// Density kernel launcher shared by field.cu (explicit points) and render.cu (points from rays).
+int nvsf_launch_density(const nvsf_field_config_t* cfg, const void* workspace, const float* x,
+                        const float* rays_o, const float* rays_d, const float* nears,
+                        const float* fars, const float* noise, uint32_t S, size_t n, float* sigma,
+                        void* geo, void* features, float* flow, cudaStream_t stream);
+
+// ---- tensor-core helpers ------------------------------------------------------------------------
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm_x2(uint32_t (&r)[2], const void* p) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];\n"
+                 : "=r"(r[0]), "=r"(r[1]) : "r"(a));
+}
+// D(16x8,f32) += A(16x16,f16,row) * B(16x8,f16,col)
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0,
+                                         uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, "
+        "{%8,%9}, {%0,%1,%2,%3};\n"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
+    __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// One warp: acc[2 m-tiles][NT n-tiles] += A[32 x 16*KT] (registers) * W^T, W in smem [8*NT][ldw].
+template <int KT, int NT>
+__device__ __forceinline__ void warp_gemm_regA(const uint32_t (&a)[2][KT][4], const __half* W,
+                                               int ldw, float (&acc)[2][NT][4], int lane) {
+#pragma unroll
+    for (int kk = 0; kk < KT; ++kk) {
+#pragma unroll
+        for (int j = 0; j < NT; j += 2) {
+            if (j + 1 < NT) {
+                uint32_t b[4];
+                ldsm_x4(b, W + ((j + (lane >> 4)) * 8 + (lane & 7)) * ldw + kk * 16 +
+                               ((lane >> 3) & 1) * 8);
+                mma16816(acc[0][j], a[0][kk], b[0], b[1]);
+                mma16816(acc[1][j], a[1][kk], b[0], b[1]);
+                mma16816(acc[0][j + 1], a[0][kk], b[2], b[3]);
+                mma16816(acc[1][j + 1], a[1][kk], b[2], b[3]);
+            } else {
+                uint32_t b[2];
+                ldsm_x2(b, W + (j * 8 + (lane & 7)) * ldw + kk * 16 + ((lane >> 3) & 1) * 8);
+                mma16816(acc[0][j], a[0][kk], b[0], b[1]);
+                mma16816(acc[1][j], a[1][kk], b[0], b[1]);
+            }
+        }
+    }
+}
+
+// Load the A fragments of a [32 x 16*KT] fp16 tile in shared memory (row stride lda halves).
+template <int KT>
+__device__ __forceinline__ void load_a_frags(const __half* A, int lda, uint32_t (&a)[2][KT][4],
+                                             int lane) {
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int kk = 0; kk < KT; ++kk)
+            ldsm_x4(a[mt][kk], A + (mt * 16 + (lane & 15)) * lda + kk * 16 + (lane >> 4) * 8);
+}
+
+// ReLU + fp16 pack: accumulators of a layer with 8*NT outputs -> A fragments of the next layer.
+template <int NT>
+__device__ __forceinline__ void relu_to_a(const float (&acc)[2][NT][4],
+                                          uint32_t (&a)[2][NT / 2][4]) {
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int kk = 0; kk < NT / 2; ++kk) {
+            const float(&c0)[4] = acc[mt][2 * kk];
+            const float(&c1)[4] = acc[mt][2 * kk + 1];
+            a[mt][kk][0] = pack_half2(fmaxf(c0[0], 0.f), fmaxf(c0[1], 0.f));
+            a[mt][kk][1] = pack_half2(fmaxf(c0[2], 0.f), fmaxf(c0[3], 0.f));
+            a[mt][kk][2] = pack_half2(fmaxf(c1[0], 0.f), fmaxf(c1[1], 0.f));
+            a[mt][kk][3] = pack_half2(fmaxf(c1[2], 0.f), fmaxf(c1[3], 0.f));
+        }
+}
+
+template <int NT>
+__device__ __forceinline__ void zero_acc(float (&acc)[2][NT][4]) {
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[mt][j][i] = 0.f;
+}
+
+// Block-wide copy of 16-byte units global -> shared.
+__device__ __forceinline__ void block_copy16(void* dst, const void* src, int n16, int tid,
+                                             int nthreads) {
+    const uint4* s = reinterpret_cast<const uint4*>(src);
+    uint4* d = reinterpret_cast<uint4*>(dst);
+    for (int i = tid; i < n16; i += nthreads) d[i] = __ldg(s + i);
+}
+
+// ---- encoders -----------------------------------------------------------------------------------
+struct LevelArgs {
+    float scale;
+    uint32_t res, size, offset, hashed;
+};
+__device__ __forceinline__ LevelArgs lv(const nvsf_grid_level_t& g) {
+    LevelArgs a;
+    a.scale = g.scale; a.res = g.res; a.size = g.size; a.offset = g.offset; a.hashed = g.hashed;
+    return a;
+}
+
+// tcnn grid position: pos = scale*x + 0.5, cell = floor(pos), w = pos - cell
+__device__ __forceinline__ void grid_pos(float scale, float x, uint32_t& cell, float& w) {
+    const float p = fmaf(scale, x, 0.5f);
+    const float f = floorf(p);
+    cell = (uint32_t)(int)f;
+    w = p - f;
+}
+
+// Hashed levels always have a power-of-two size (2^log2_hashmap_size); dense ones need the modulo.
+__device__ __forceinline__ uint32_t idx2(const LevelArgs& L, uint32_t cx, uint32_t cy) {
+    if (L.hashed) return (cx ^ (cy * 2654435761u)) & (L.size - 1);
+    return (cx + cy * L.res) % L.size;
+}
+__device__ __forceinline__ uint32_t idx3(const LevelArgs& L, uint32_t cx, uint32_t cy,
+                                         uint32_t cz) {
+    if (L.hashed) return (cx ^ (cy * 2654435761u) ^ (cz * 805459861u)) & (L.size - 1);
+    return (cx + cy * L.res + cz * L.res * L.res) % L.size;
+}

@@ -1,0 +1,381 @@
+"""Host side of the B200 field + uniform renderer: mirrors the reference's model interface.
+
+`NeRFNetwork` here presents the surface of the reference's
+``nvsf.nerf.models.network_dynamic.NeRFNetwork`` (which subclasses ``NeRFRenderer``,
+renderer_dynamic.py:67-326) for the hot path:
+
+    density(x, t, cal_lidar_color)           -> {"sigma", "geo_feat"}     network_dynamic.py:213-287
+    flow(x, t)                               -> {"flow_forward", "flow_backward"}         :197-211
+    run(rays_o, rays_d, time, cal_lidar_color, num_steps, upsample_steps, bg_color, perturb, **kw)
+    render(rays_o, rays_d, time, cal_lidar_color, staged, max_ray_batch, **kw)
+                                             -> dict with the reference's keys   renderer_dynamic.py:109-326
+
+Everything is computed by the sm_100a kernels behind include/nvsf_b200.h; there is no PyTorch
+fallback.  Parameters are fp32 `nn.Parameter`s in the reference's own memory layouts (tcnn flat
+`params`, Planes4D [1,F,H,W] tensors, nn.Linear weights), concatenated per encoder:
+
+    hash_static_{lidar,camera}    == hash_encoder_*.hash_static.params
+    hash_dynamic_{lidar,camera}   == cat(hash_encoder_*.hash_dynamic.{p}.hash_t.{k}.params  for p, k)
+    planes_{lidar,camera}         == cat(planes_encoder_*.planes.{s}.{c}.flatten()       for s, c)
+    flow_grid, flow_mlp           == flow_net.grid_enc.params, cat(flow_net.mlp.{0,2,4}.weight)
+    sigma_net, intensity_net, raydrop_net, color_net  == the tcnn `params` of the same name
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from . import raymarching
+from ._lib import check, ptr, stream_ptr
+
+MAX_LEVELS = 16
+MAX_PLANE_SCALES = 8
+PLANE_COMBS = [(0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3)]
+
+
+class GridLevel(ctypes.Structure):
+    _fields_ = [("scale", ctypes.c_float), ("res", ctypes.c_uint32), ("size", ctypes.c_uint32),
+                ("offset", ctypes.c_uint32), ("hashed", ctypes.c_uint32)]
+
+
+class FieldConfigC(ctypes.Structure):
+    _fields_ = [
+        ("bound", ctypes.c_float), ("density_scale", ctypes.c_float),
+        ("active_sensor", ctypes.c_uint32), ("num_frames", ctypes.c_uint32),
+        ("time_resolution", ctypes.c_uint32),
+        ("hs_levels", ctypes.c_uint32), ("hs_entries", ctypes.c_uint32),
+        ("hs", GridLevel * MAX_LEVELS),
+        ("hd_levels", ctypes.c_uint32), ("hd_entries", ctypes.c_uint32 * 3),
+        ("hd", (GridLevel * MAX_LEVELS) * 3),
+        ("fl_levels", ctypes.c_uint32), ("fl_entries", ctypes.c_uint32),
+        ("fl", GridLevel * MAX_LEVELS),
+        ("pl_scales", ctypes.c_uint32), ("pl_res", ctypes.c_uint32 * MAX_PLANE_SCALES),
+    ]
+
+
+class FieldParamsC(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in
+                ("hash_static", "hash_dynamic", "planes", "flow_grid", "flow_mlp", "sigma_net",
+                 "head_a", "head_b")]
+
+
+def grid_levels(n_dims, n_levels, base_resolution, per_level_scale, log2_hashmap_size):
+    """Per-level geometry of a tcnn multiresolution grid (tiny-cuda-nn GridEncoding):
+    scale = exp2(l * log2(per_level_scale)) * base - 1, res = ceil(scale) + 1,
+    size = min(next_multiple(res^D, 8), 2^log2_hashmap_size), hashed iff res^D > size."""
+    log2_pls = np.log2(np.float32(per_level_scale), dtype=np.float32)
+    out, offset = [], 0
+    for l in range(n_levels):
+        scale = np.float32(np.exp2(np.float32(l) * log2_pls, dtype=np.float32)
+                           * np.float32(base_resolution) - np.float32(1.0))
+        res = int(np.ceil(scale)) + 1
+        dense = res ** n_dims
+        size = min((min(dense, (2 ** 32 - 1) // 2) + 7) // 8 * 8, 1 << log2_hashmap_size)
+        out.append((float(scale), res, size, offset, int(dense > size)))
+        offset += size
+    return out, offset
+
+
+def _fill_levels(dst, levels):
+    for i, (scale, res, size, offset, hashed) in enumerate(levels):
+        dst[i].scale, dst[i].res, dst[i].size, dst[i].offset, dst[i].hashed = scale, res, size, offset, hashed
+
+
+_L = None
+
+
+def _setup_lib():
+    global _L
+    if _L is not None:
+        return _L
+    L = _lib.lib()
+    P = ctypes.c_void_p
+    cfgp, prmp = ctypes.POINTER(FieldConfigC), ctypes.POINTER(FieldParamsC)
+    L.nvsf_field_workspace_bytes.argtypes = [cfgp]
+    L.nvsf_field_pack_params.argtypes = [cfgp, prmp, ctypes.c_uint32, P, ctypes.c_size_t, P]
+    L.nvsf_field_pack_time.argtypes = [cfgp, prmp, P, P, ctypes.c_size_t, P]
+    L.nvsf_field_density.argtypes = [cfgp, P, P, ctypes.c_uint32, P, P, P, P, P]
+    L.nvsf_render_uniform.argtypes = [cfgp, P, ctypes.c_uint32, P, P, P, P, P, ctypes.c_uint32,
+                                      ctypes.c_uint32, ctypes.c_float, P, ctypes.c_size_t, P, P, P,
+                                      P, P, P]
+    _L = L
+    return L
+
+
+class NeRFNetwork(nn.Module):
+    """B200 field + renderer with the reference NeRFNetwork's constructor arguments
+    (network_dynamic.py:13-38; renderer kwargs renderer_dynamic.py:68-78)."""
+
+    def __init__(self, min_resolution=32, base_resolution=512, max_resolution=32768,
+                 time_resolution=25, n_levels_plane=4, n_features_per_level_plane=8,
+                 n_levels_hash=8, n_features_per_level_hash=4, log2_hashmap_size=19,
+                 num_layers_flow=3, hidden_dim_flow=64, num_layers_sigma=2, hidden_dim_sigma=64,
+                 geo_feat_dim=15, num_layers_lidar=3, hidden_dim_lidar=64, num_layers_color=3,
+                 hidden_dim_color=64, out_color_dim=3, out_lidar_color_dim=2, num_frames=51,
+                 bound=1, density_scale=1, min_near=0.01, min_near_lidar=0.01,
+                 lidar_max_depth=0.81, density_thresh=0.01, bg_radius=-1, active_sensor=False,
+                 hash_size_dynamic=(15, 13, 13), flow_levels=16, flow_features=8,
+                 flow_base_resolution=32, flow_max_resolution=8192, flow_log2_hashmap_size=18,
+                 device="cuda", **kwargs):
+        super().__init__()
+        fixed = dict(n_levels_plane=(n_levels_plane, 4), n_features_per_level_plane=(n_features_per_level_plane, 8),
+                     n_levels_hash=(n_levels_hash, 8), n_features_per_level_hash=(n_features_per_level_hash, 4),
+                     num_layers_flow=(num_layers_flow, 3), hidden_dim_flow=(hidden_dim_flow, 64),
+                     num_layers_sigma=(num_layers_sigma, 2), hidden_dim_sigma=(hidden_dim_sigma, 64),
+                     geo_feat_dim=(geo_feat_dim, 15), num_layers_lidar=(num_layers_lidar, 3),
+                     hidden_dim_lidar=(hidden_dim_lidar, 64), num_layers_color=(num_layers_color, 3),
+                     hidden_dim_color=(hidden_dim_color, 64), out_color_dim=(out_color_dim, 3),
+                     out_lidar_color_dim=(out_lidar_color_dim, 2), flow_levels=(flow_levels, 16),
+                     flow_features=(flow_features, 8))
+        for k, (got, want) in fixed.items():
+            if got != want:
+                raise ValueError(f"nvsf_b200 kernels are built for {k}={want} (the reference default), got {got}")
+        if bg_radius > 0:
+            raise ValueError("bg_radius > 0 is not supported (the reference asserts bg_radius <= 0, main_nvsf.py:171)")
+        self.bound = float(bound)
+        self.cascade = 1 + math.ceil(math.log2(bound))
+        self.grid_size = 128
+        self.density_scale, self.min_near = float(density_scale), float(min_near)
+        self.min_near_lidar, self.lidar_max_depth = float(min_near_lidar), float(lidar_max_depth)
+        self.density_thresh, self.bg_radius, self.active_sensor = density_thresh, bg_radius, bool(active_sensor)
+        self.out_color_dim, self.out_lidar_color_dim = 3, 2
+        self.num_frames, self.time_resolution = int(num_frames), int(time_resolution)
+
+        hash_pls = float(np.exp2(np.log2(max_resolution / base_resolution) / (n_levels_hash - 1)))
+        flow_pls = float(np.exp2(np.log2(flow_max_resolution / flow_base_resolution) / (flow_levels - 1)))
+        self._hs, hs_entries = grid_levels(3, 8, base_resolution, hash_pls, log2_hashmap_size)
+        self._hd, hd_entries = [], []
+        for h in hash_size_dynamic:
+            lv, tot = grid_levels(2, 8, base_resolution, hash_pls, h)
+            self._hd.append(lv)
+            hd_entries.append(tot)
+        self._fl, fl_entries = grid_levels(3, 16, flow_base_resolution, flow_pls, flow_log2_hashmap_size)
+        self._pl_res = [min_resolution * 2 ** s for s in range(4)]
+
+        c = FieldConfigC()
+        c.bound, c.density_scale, c.active_sensor = self.bound, self.density_scale, int(self.active_sensor)
+        c.num_frames, c.time_resolution = self.num_frames, self.time_resolution
+        c.hs_levels, c.hs_entries = 8, hs_entries
+        _fill_levels(c.hs, self._hs)
+        c.hd_levels = 8
+        for p in range(3):
+            c.hd_entries[p] = hd_entries[p]
+            _fill_levels(c.hd[p], self._hd[p])
+        c.fl_levels, c.fl_entries = 16, fl_entries
+        _fill_levels(c.fl, self._fl)
+        c.pl_scales = 4
+        for s in range(4):
+            c.pl_res[s] = self._pl_res[s]
+        self._cfg = c
+
+        T = self.time_resolution
+        n_planes = sum(8 * r[a] * r[b] for R in self._pl_res for r in [(R, R, R, T)] for (a, b) in PLANE_COMBS)
+        sizes = dict(hash_static=hs_entries * 4, hash_dynamic=sum(T * e * 4 for e in hd_entries),
+                     planes=n_planes)
+        self.param_sizes = dict(sizes, flow_grid=fl_entries * 8, flow_mlp=64 * 32 + 64 * 64 + 6 * 64,
+                                sigma_net=64 * 128 + 16 * 64, intensity_net=64 * 96 + 64 * 64 + 16 * 64,
+                                raydrop_net=64 * 96 + 64 * 64 + 16 * 64, color_net=64 * 32 + 64 * 64 + 16 * 64)
+        dev = torch.device(device)
+
+        def table(n):  # tcnn grids: U(-1e-4, 1e-4)
+            return nn.Parameter(torch.empty(n, device=dev).uniform_(-1e-4, 1e-4))
+
+        def xavier(shapes, last_std=None):
+            chunks = []
+            for i, (o, k) in enumerate(shapes):
+                if last_std is not None and i == len(shapes) - 1:
+                    chunks.append(torch.randn(o * k, device=dev) * last_std)
+                else:
+                    b = math.sqrt(6.0 / (o + k))
+                    chunks.append(torch.empty(o * k, device=dev).uniform_(-b, b))
+            return nn.Parameter(torch.cat(chunks))
+
+        for m in ("lidar", "camera"):
+            setattr(self, f"hash_static_{m}", table(sizes["hash_static"]))
+            setattr(self, f"hash_dynamic_{m}", table(sizes["hash_dynamic"]))
+            chunks = []  # planes_field.py:47-50: time planes = 1, space planes U(0.1, 0.5)
+            for R in self._pl_res:
+                r = (R, R, R, T)
+                for (a, b) in PLANE_COMBS:
+                    n = 8 * r[a] * r[b]
+                    chunks.append(torch.ones(n, device=dev) if 3 in (a, b)
+                                  else torch.empty(n, device=dev).uniform_(0.1, 0.5))
+            setattr(self, f"planes_{m}", nn.Parameter(torch.cat(chunks)))
+        self.flow_grid = table(self.param_sizes["flow_grid"])
+        self.flow_mlp = xavier([(64, 32), (64, 64), (6, 64)], last_std=1e-3)  # flow_field.py:103
+        self.sigma_net = xavier([(64, 128), (16, 64)])
+        self.intensity_net = xavier([(64, 96), (64, 64), (16, 64)])
+        self.raydrop_net = xavier([(64, 96), (64, 64), (16, 64)])
+        self.color_net = xavier([(64, 32), (64, 64), (16, 64)])
+        self.register_buffer("aabb_train", torch.tensor([-bound, -bound, -bound, bound, bound, bound],
+                                                        dtype=torch.float32, device=dev))
+        self.register_buffer("aabb_infer", self.aabb_train.clone())
+        self._ws = {}      # modality -> workspace tensor
+        self._packed = {}  # modality -> (param versions, time key)
+
+    # ------------------------------------------------------------------ parameters
+    def load_flat_params(self, p):
+        """Load parameters given in the layout of this module's docstring
+        ({'lidar': {...}, 'camera': {...}, 'flow_grid': ..., ...})."""
+        with torch.no_grad():
+            for m in ("lidar", "camera"):
+                for k in ("hash_static", "hash_dynamic", "planes"):
+                    getattr(self, f"{k}_{m}").copy_(torch.as_tensor(p[m][k]))
+            for k in ("flow_grid", "flow_mlp", "sigma_net", "intensity_net", "raydrop_net", "color_net"):
+                getattr(self, k).copy_(torch.as_tensor(p[k]))
+        self._packed.clear()
+
+    def _params_c(self, lidar):
+        m = "lidar" if lidar else "camera"
+        ps = FieldParamsC()
+        ps.hash_static = ptr(getattr(self, f"hash_static_{m}"))
+        ps.hash_dynamic = ptr(getattr(self, f"hash_dynamic_{m}"))
+        ps.planes = ptr(getattr(self, f"planes_{m}"))
+        ps.flow_grid, ps.flow_mlp, ps.sigma_net = ptr(self.flow_grid), ptr(self.flow_mlp), ptr(self.sigma_net)
+        if lidar:
+            ps.head_a, ps.head_b = ptr(self.intensity_net), ptr(self.raydrop_net)
+        else:
+            ps.head_a, ps.head_b = ptr(self.color_net), None
+        return ps
+
+    def _version_key(self, lidar):
+        m = "lidar" if lidar else "camera"
+        names = [f"hash_static_{m}", f"hash_dynamic_{m}", f"planes_{m}", "flow_grid", "flow_mlp", "sigma_net"]
+        names += ["intensity_net", "raydrop_net"] if lidar else ["color_net"]
+        return tuple((getattr(self, n)._version, getattr(self, n).data_ptr()) for n in names)
+
+    def prepare(self, time, lidar, force=False):
+        """Pack parameters (if they changed) and collapse the time-dependent tables for `time`
+        (a float or the reference's [1,1] tensor; no host sync when it is a CUDA tensor)."""
+        L = _setup_lib()
+        dev = self.sigma_net.device
+        nbytes = L.nvsf_field_workspace_bytes(ctypes.byref(self._cfg))
+        if nbytes == 0:
+            raise _lib.NvsfError("unsupported field configuration")
+        ws = self._ws.get(lidar)
+        if ws is None or ws.numel() < nbytes or ws.device != dev:
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            self._ws[lidar] = ws
+            force = True
+        if torch.is_tensor(time):
+            t_dev = time.detach().to(device=dev, dtype=torch.float32).reshape(-1)[:1].contiguous()
+            t_key = None  # unknown value on the host: always re-collapse (cheap)
+        else:
+            t_dev = torch.tensor([float(time)], dtype=torch.float32, device=dev)
+            t_key = float(time)
+        vkey = self._version_key(lidar)
+        prev = self._packed.get(lidar)
+        pc = self._params_c(lidar)
+        st = stream_ptr()
+        if force or prev is None or prev[0] != vkey:
+            check(L.nvsf_field_pack_params(ctypes.byref(self._cfg), ctypes.byref(pc), int(lidar), ptr(ws),
+                                           ws.numel(), st), "field_pack_params")
+            prev = None
+        if prev is None or t_key is None or prev[1] != t_key:
+            check(L.nvsf_field_pack_time(ctypes.byref(self._cfg), ctypes.byref(pc), ptr(t_dev), ptr(ws),
+                                         ws.numel(), st), "field_pack_time")
+        self._packed[lidar] = (vkey, t_key)
+        return ws
+
+    # ------------------------------------------------------------------ field API
+    def _density_raw(self, x, t, lidar, want_features=False, want_flow=False):
+        L = _setup_lib()
+        x = x.detach().to(device=self.sigma_net.device, dtype=torch.float32).contiguous().view(-1, 3)
+        n = x.shape[0]
+        ws = self.prepare(t, lidar)
+        sigma = torch.empty(n, dtype=torch.float32, device=x.device)
+        geo = torch.empty(n, 16, dtype=torch.float16, device=x.device)
+        feats = torch.empty(n, 128, dtype=torch.float16, device=x.device) if want_features else None
+        flow = torch.empty(n, 6, dtype=torch.float32, device=x.device) if want_flow else None
+        check(L.nvsf_field_density(ctypes.byref(self._cfg), ptr(ws), ptr(x), n, ptr(sigma), ptr(geo),
+                                   ptr(feats), ptr(flow), stream_ptr()), "field_density")
+        return sigma, geo, feats, flow
+
+    @torch.no_grad()
+    def density(self, x, t=None, cal_lidar_color=False, **kwargs):
+        """x [N,3] in [-bound,bound] -> {'sigma' [N] f32, 'geo_feat' [N,15] f16}."""
+        sigma, geo, _, _ = self._density_raw(x, t, bool(cal_lidar_color))
+        return {"sigma": sigma, "geo_feat": geo[:, 1:]}
+
+    @torch.no_grad()
+    def flow(self, x, t):
+        _, _, _, f = self._density_raw(x, t, True, want_flow=True)
+        return {"flow_forward": f[:, :3], "flow_backward": f[:, 3:]}
+
+    @torch.no_grad()
+    def features(self, x, t, cal_lidar_color=False):
+        """Debug/test hook: the 120 sigma-net inputs [N,120] (fp16) and the flow [N,6]."""
+        _, _, feats, f = self._density_raw(x, t, bool(cal_lidar_color), want_features=True, want_flow=True)
+        return feats[:, :120], f
+
+    # ------------------------------------------------------------------ renderer API
+    @torch.no_grad()
+    def run(self, rays_o, rays_d, time, cal_lidar_color=False, num_steps=768, upsample_steps=128,
+            bg_color=None, perturb=False, noise=None, return_weights=True, **kwargs):
+        """NeRFRenderer.run (renderer_dynamic.py:109-265).  `noise` [N,num_steps] optionally
+        supplies the stratified-sampling jitter that perturb=True otherwise draws with torch.rand."""
+        L = _setup_lib()
+        lidar = bool(cal_lidar_color)
+        self.out_dim = self.out_lidar_color_dim if lidar else self.out_color_dim
+        dev = self.sigma_net.device
+        prefix = rays_o.shape[:-1]
+        o = rays_o.detach().to(device=dev, dtype=torch.float32).contiguous().view(-1, 3)
+        d = rays_d.detach().to(device=dev, dtype=torch.float32).contiguous().view(-1, 3)
+        N, S = o.shape[0], int(num_steps)
+        if lidar:
+            nears = torch.full((N,), self.min_near_lidar, dtype=torch.float32, device=dev)
+            fars = torch.full((N,), self.lidar_max_depth, dtype=torch.float32, device=dev)
+        else:
+            aabb = self.aabb_train if self.training else self.aabb_infer
+            nears, fars = raymarching.near_far_from_aabb(o, d, aabb, self.min_near)
+        if noise is None and perturb:
+            noise = torch.rand(N, S, dtype=torch.float32, device=dev)
+        if noise is not None:
+            noise = noise.to(device=dev, dtype=torch.float32).contiguous()
+        ws = self.prepare(time, lidar)
+        nch = self.out_dim
+        depth = torch.empty(N, dtype=torch.float32, device=dev)
+        image = torch.empty(N, nch, dtype=torch.float32, device=dev)
+        wsum = torch.empty(N, dtype=torch.float32, device=dev)
+        weights = torch.empty(N, S, dtype=torch.float32, device=dev) if return_weights else None
+        z_vals = torch.empty(N, S, dtype=torch.float32, device=dev) if return_weights else None
+        sbytes = L.nvsf_render_uniform_scratch_bytes(N, S)
+        scratch = torch.empty(sbytes, dtype=torch.uint8, device=dev)
+        bg = 1.0 if bg_color is None else float(bg_color)
+        check(L.nvsf_render_uniform(ctypes.byref(self._cfg), ptr(ws), int(lidar), ptr(o), ptr(d), ptr(nears),
+                                    ptr(fars), ptr(noise), N, S, bg, ptr(scratch), sbytes, ptr(depth),
+                                    ptr(image), ptr(wsum), ptr(weights), ptr(z_vals), stream_ptr()),
+              "render_uniform")
+        sfx = "_lidar" if lidar else ""
+        out = {"depth" + sfx: depth.view(*prefix), "image" + sfx: image.view(*prefix, nch),
+               "weights_sum" + sfx: wsum}
+        if return_weights:
+            out["weights"], out["z_vals"] = weights, z_vals
+        return out
+
+    @torch.no_grad()
+    def render(self, rays_o, rays_d, time, cal_lidar_color=False, staged=False, max_ray_batch=4096, **kwargs):
+        """NeRFRenderer.render (renderer_dynamic.py:267-326).  staged=True returns only depth and
+        image like the reference; the whole frame is rendered by one launch pair per
+        `frame_ray_batch` rays (default: all) instead of a Python loop of 4096-ray chunks —
+        `max_ray_batch` is accepted for signature compatibility."""
+        if not staged:
+            return self.run(rays_o, rays_d, time, cal_lidar_color=cal_lidar_color, **kwargs)
+        lidar = bool(cal_lidar_color)
+        B, N = rays_o.shape[:2]
+        chunk = int(kwargs.pop("frame_ray_batch", 0)) or N
+        keys = ["depth_lidar", "image_lidar"] if lidar else ["depth", "image"]
+        depth, image = [], []
+        for b in range(B):
+            for head in range(0, N, chunk):
+                r = self.run(rays_o[b:b + 1, head:head + chunk], rays_d[b:b + 1, head:head + chunk],
+                             time[b:b + 1] if torch.is_tensor(time) else time, cal_lidar_color=lidar,
+                             return_weights=False, **kwargs)
+                depth.append(r[keys[0]])
+                image.append(r[keys[1]])
+        depth = torch.cat(depth, dim=1).view(B, N) if len(depth) > 1 else depth[0].view(B, N)
+        image = torch.cat(image, dim=1).view(B, N, -1) if len(image) > 1 else image[0].view(B, N, -1)
+        return {keys[0]: depth, keys[1]: image}

@@ -1,0 +1,173 @@
+"""Parity of the sm_100a field + uniform renderer against the CPU oracle (oracle/field_oracle.py,
+itself pinned to the reference modules by tests/test_field_oracle_golden.py).
+
+Tolerances (BASELINE.json north_star): 1e-2 relative for anything that passes through the fp16
+MLPs (sigma, geo features, colours, composited outputs of the uniform renderer); encoder features
+are compared at fp16 resolution (they are stored as fp16 for the tensor cores)."""
+import os
+
+import numpy as np
+import pytest
+
+import field_cases as FC
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+S = FC.S
+TIMES = [0.0, 0.5, 31.0 / 63.0, 1.0, 0.2]
+
+
+@pytest.fixture(scope="module")
+def model(pkg):
+    m = pkg.NeRFNetwork(time_resolution=S.TIME_RESOLUTION, num_frames=S.NUM_FRAMES, bound=S.BOUND,
+                        min_near=S.MIN_NEAR, min_near_lidar=S.MIN_NEAR_LIDAR, lidar_max_depth=S.LIDAR_MAX_DEPTH)
+    m.load_flat_params(FC.oracle_params())
+    return m.eval()
+
+
+@pytest.fixture(scope="module")
+def orc():
+    from oracle.field_oracle import FieldOracle
+    return FieldOracle(FC.oracle_config(), FC.oracle_params())
+
+
+def pts(n, seed):
+    rng = np.random.default_rng(seed)
+    x = ((rng.random((n, 3), dtype=np.float32) * 2 - 1) * np.float32(1.95)).astype(np.float32)
+    x[:8] = np.float32(S.BOUND) * np.sign(x[:8])
+    return x
+
+
+def host(t):
+    return t.detach().float().cpu().numpy()
+
+
+def close(a, b, rtol, atol, what):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    err = np.abs(a - b) - (atol + rtol * np.abs(b))
+    assert (err <= 0).all(), f"{what}: worst excess {err.max():.3e}, max abs err {np.abs(a - b).max():.3e}"
+
+
+BLOCKS = [("plane_static", slice(0, 32)), ("plane_dynamic", slice(32, 64)),
+          ("hash_static", slice(64, 96)), ("hash_dynamic", slice(96, 120))]
+
+
+@pytest.mark.parametrize("ti", range(len(TIMES)))
+@pytest.mark.parametrize("lidar", [True, False])
+def test_encoder_features_exact_positions(pkg, ti, lidar):
+    """Zero flow (last flow layer = 0): all three queries sit at x, so every block of the
+    120-vector (K-planes static/dynamic, hash static/dynamic, blended over t, t1, t2) must agree
+    with the oracle to the resolution of the fp16 feature tile."""
+    from oracle.field_oracle import FieldOracle
+    p = dict(FC.oracle_params())
+    p["flow_mlp"] = p["flow_mlp"].clone()
+    p["flow_mlp"][-6 * 64:] = 0
+    m = pkg.NeRFNetwork(time_resolution=S.TIME_RESOLUTION, num_frames=S.NUM_FRAMES, bound=S.BOUND).eval()
+    m.load_flat_params(p)
+    x = pts(512, 7)
+    t = TIMES[ti]
+    with torch.no_grad():
+        ef, eflow = FieldOracle(FC.oracle_config(), p).features(torch.from_numpy(x), t, lidar)
+    gf, gflow = m.features(torch.from_numpy(x).cuda(), torch.tensor([[t]], device="cuda"), lidar)
+    assert not host(gflow).any() and not eflow.numpy().any()
+    ef, gf = ef.numpy(), host(gf)
+    for name, sl in BLOCKS:
+        scale = np.abs(ef[:, sl]).max()
+        close(gf[:, sl], ef[:, sl], 1e-3, 1e-3 * scale, f"{name} t={t}")
+
+
+@pytest.mark.parametrize("ti", range(len(TIMES)))
+@pytest.mark.parametrize("lidar", [True, False])
+def test_encoder_features_and_flow(model, orc, ti, lidar):
+    """With the flow on: the flow itself, and the blocks at a tolerance that allows for the
+    fp16 flow MLP moving the warped queries (see oracle/field_init.py, conditioning note)."""
+    x = pts(512, 7)
+    t = TIMES[ti]
+    with torch.no_grad():
+        ef, eflow = orc.features(torch.from_numpy(x), t, lidar)
+    gf, gflow = model.features(torch.from_numpy(x).cuda(), torch.tensor([[t]], device="cuda"), lidar)
+    close(host(gflow), eflow.numpy(), 5e-3, 2e-5, "flow")
+    assert np.abs(eflow.numpy()).max() > 1e-3
+    ef, gf = ef.numpy(), host(gf)
+    for name, sl in BLOCKS:
+        scale = np.abs(ef[:, sl]).max()
+        close(gf[:, sl], ef[:, sl], 3e-3, 5e-3 * scale, f"{name} t={t}")
+
+
+@pytest.mark.parametrize("ti", range(len(TIMES)))
+@pytest.mark.parametrize("lidar", [True, False])
+def test_density_vs_oracle_and_golden(model, orc, ti, lidar):
+    gold = np.load(os.path.join(GOLDEN, "field_ref.npz"))
+    x = gold["x"]
+    t = float(gold["times"][ti])
+    r = model.density(torch.from_numpy(x).cuda(), torch.tensor([[t]], device="cuda"), lidar)
+    assert r["sigma"].dtype == torch.float32 and r["sigma"].shape == (256,) and r["geo_feat"].shape == (256, 15)
+    k = f"den_t{ti}_{'l' if lidar else 'c'}_"
+    close(host(r["sigma"]), gold[k + "sigma"], 1e-2, 0, "sigma vs reference modules")
+    close(host(r["geo_feat"]), gold[k + "geo"], 1e-2, 1e-2 * np.abs(gold[k + "geo"]).max(), "geo_feat")
+    with torch.no_grad():
+        o = orc.density(torch.from_numpy(x), t, lidar)
+    close(host(r["sigma"]), o["sigma"].numpy(), 1e-2, 0, "sigma vs oracle")
+    f = model.flow(torch.from_numpy(x).cuda(), t)   # python float time is accepted too
+    got = np.concatenate([host(f["flow_forward"]), host(f["flow_backward"])], -1)
+    close(got, gold[f"flow_t{ti}"], 5e-3, 2e-5, "flow vs reference modules")
+
+
+@pytest.mark.parametrize("ds", [1, 60])
+@pytest.mark.parametrize("lidar", [True, False])
+@pytest.mark.parametrize("perturb", [0, 1])
+def test_run_vs_reference_golden(pkg, ds, lidar, perturb):
+    gold = np.load(os.path.join(GOLDEN, "field_ref.npz"))
+    m = pkg.NeRFNetwork(time_resolution=S.TIME_RESOLUTION, num_frames=S.NUM_FRAMES, bound=S.BOUND,
+                        min_near=S.MIN_NEAR, min_near_lidar=S.MIN_NEAR_LIDAR, lidar_max_depth=S.LIDAR_MAX_DEPTH,
+                        density_scale=float(ds)).eval()
+    m.load_flat_params(FC.oracle_params())
+    k = f"ds{ds}_run_{'l' if lidar else 'c'}{perturb}_"
+    o, d = torch.from_numpy(gold[k + "o"]).cuda()[None], torch.from_numpy(gold[k + "d"]).cuda()[None]
+    noise = torch.from_numpy(gold[k + "noise"]).cuda() if perturb else None
+    r = m.render(o, d, torch.tensor([[0.3]], device="cuda"), cal_lidar_color=lidar, staged=False, num_steps=40,
+                 perturb=bool(perturb), noise=noise)
+    sfx = "_lidar" if lidar else ""
+    assert r["depth" + sfx].shape == (1, 48) and r["image" + sfx].shape == (1, 48, 2 if lidar else 3)
+    close(host(r["z_vals"]), gold[k + "z_vals"], 1e-6, 1e-7, "z_vals")
+    close(host(r["weights"]), gold[k + "weights"], 1e-2, 1e-5, "weights")
+    close(host(r["weights_sum" + sfx]), gold[k + "weights_sum"], 1e-2, 1e-5, "weights_sum")
+    close(host(r["depth" + sfx]).reshape(-1), gold[k + "depth"], 1e-2, 1e-5, "depth")
+    close(host(r["image" + sfx]).reshape(48, -1), gold[k + "image"], 1e-2, 1e-4, "image")
+
+
+def test_full_lidar_frame_properties(model, orc):
+    """66x1030 frame, 128 samples: staged render == run on sub-batches; spot rays match the oracle."""
+    o, d = S.lidar_rays(-1, seed=0)
+    to, td = torch.from_numpy(o).cuda()[None], torch.from_numpy(d).cuda()[None]
+    t = torch.tensor([[0.5]], device="cuda")
+    full = model.render(to, td, t, cal_lidar_color=True, staged=True, num_steps=128)
+    assert set(full) == {"depth_lidar", "image_lidar"} and full["depth_lidar"].shape == (1, 67980)
+    img = host(full["image_lidar"])[0]
+    assert np.isfinite(img).all() and (img >= 0).all() and (img <= 1).all()
+    sub = model.render(to[:, 5000:9096], td[:, 5000:9096], t, cal_lidar_color=True, staged=False, num_steps=128)
+    np.testing.assert_allclose(host(sub["depth_lidar"]), host(full["depth_lidar"])[:, 5000:9096], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(host(sub["image_lidar"]), host(full["image_lidar"])[:, 5000:9096], rtol=1e-6, atol=1e-7)
+    ws = host(sub["weights_sum_lidar"]); w = host(sub["weights"])
+    np.testing.assert_allclose(w.sum(1), ws, rtol=1e-5)
+    assert (ws <= 1 + 1e-5).all()
+    idx = np.arange(0, 67980, 997)
+    with torch.no_grad():
+        e = orc.run(torch.from_numpy(o[idx]), torch.from_numpy(d[idx]), 0.5, True, 128)
+    close(host(full["depth_lidar"])[0, idx], e["depth"].numpy(), 1e-2, 1e-5, "depth")
+    close(img[idx], e["image"].numpy(), 1e-2, 1e-4, "image")
+
+
+def test_params_repack_on_update(model):
+    x = torch.from_numpy(pts(64, 3)).cuda()
+    a = model.density(x, 0.4, True)["sigma"].clone()
+    with torch.no_grad():
+        model.sigma_net.mul_(1.5)
+    b = model.density(x, 0.4, True)["sigma"]
+    assert not torch.allclose(a, b)
+    with torch.no_grad():
+        model.sigma_net.div_(1.5)
+    c = model.density(x, 0.4, True)["sigma"]
+    torch.testing.assert_close(a, c, rtol=1e-3, atol=1e-5)
