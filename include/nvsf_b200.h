@@ -33,7 +33,7 @@ extern "C" {
 #define NVSF_E_WORKSPACE (-2) /* workspace too small */
 
 /* ABI version of this header; bumped on any signature change. */
-#define NVSF_B200_ABI_VERSION 4
+#define NVSF_B200_ABI_VERSION 5
 int nvsf_abi_version(void);
 /* Human-readable text for a status returned by any nvsf_* call. */
 const char* nvsf_status_string(int status);
@@ -222,6 +222,18 @@ int nvsf_field_density(const nvsf_field_config_t* cfg, const void* workspace, co
  * scratch: N*S*(4+32) bytes (sigma f32 + geo f16[16] per sample).
  * Outputs: depth [N], image [N,2|3], weights_sum [N]; weights/z_vals [N,S] optional (NULL ok). */
 size_t nvsf_render_uniform_scratch_bytes(uint32_t N, uint32_t S);
+/* The two phases of nvsf_render_uniform, callable separately (bench.py times them apart):
+ * phase 1 evaluates the field for all N*S samples into scratch, phase 2 composites. */
+int nvsf_render_uniform_density(const nvsf_field_config_t* cfg, const void* workspace,
+                                const float* rays_o, const float* rays_d, const float* nears,
+                                const float* fars, const float* noise, uint32_t N, uint32_t S,
+                                void* scratch, size_t scratch_bytes, void* stream);
+int nvsf_render_uniform_composite(const nvsf_field_config_t* cfg, const void* workspace,
+                                  uint32_t lidar, const float* rays_d, const float* nears,
+                                  const float* fars, const float* noise, uint32_t N, uint32_t S,
+                                  float bg_color, const void* scratch, size_t scratch_bytes,
+                                  float* depth, float* image, float* weights_sum, float* weights,
+                                  float* z_vals, void* stream);
 int nvsf_render_uniform(const nvsf_field_config_t* cfg, const void* workspace, uint32_t lidar,
                         const float* rays_o, const float* rays_d, const float* nears,
                         const float* fars, const float* noise, uint32_t N, uint32_t S,

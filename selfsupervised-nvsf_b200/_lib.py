@@ -57,6 +57,9 @@ PROTOTYPES = {
     "nvsf_field_pack_time": (_int, [_p, _p, _p, _p, _sz, _p]),
     "nvsf_field_density": (_int, [_p, _p, _p, _u32, _p, _p, _p, _p, _p]),
     "nvsf_render_uniform_scratch_bytes": (_sz, [_u32, _u32]),
+    "nvsf_render_uniform_density": (_int, [_p, _p, _p, _p, _p, _p, _p, _u32, _u32, _p, _sz, _p]),
+    "nvsf_render_uniform_composite": (_int, [_p, _p, _u32, _p, _p, _p, _p, _u32, _u32, _f32, _p, _sz,
+                                             _p, _p, _p, _p, _p, _p]),
     "nvsf_render_uniform": (_int, [_p, _p, _u32, _p, _p, _p, _p, _p, _u32, _u32, _f32, _p, _sz, _p,
                                    _p, _p, _p, _p, _p]),
 }
@@ -91,7 +94,7 @@ def lib():
     return _lib
 
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 def check(status, what=""):

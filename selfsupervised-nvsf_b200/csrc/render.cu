@@ -256,15 +256,34 @@ size_t nvsf_render_uniform_scratch_bytes(uint32_t N, uint32_t S) {
     return ws_align(n * sizeof(float)) + ws_align(n * kGeo * sizeof(__half));
 }
 
-int nvsf_render_uniform(const nvsf_field_config_t* cfg, const void* workspace, uint32_t lidar,
-                        const float* rays_o, const float* rays_d, const float* nears,
-                        const float* fars, const float* noise, uint32_t N, uint32_t S,
-                        float bg_color, void* scratch, size_t scratch_bytes, float* depth,
-                        float* image, float* weights_sum, float* weights, float* z_vals,
-                        void* stream) {
+/* phase 1: field evaluation of all N*S samples into scratch (sigma f32, geo f16[16]) */
+int nvsf_render_uniform_density(const nvsf_field_config_t* cfg, const void* workspace,
+                                const float* rays_o, const float* rays_d, const float* nears,
+                                const float* fars, const float* noise, uint32_t N, uint32_t S,
+                                void* scratch, size_t scratch_bytes, void* stream) {
     if (N == 0) return NVSF_OK;
     if (!field_cfg_ok(cfg) || !workspace || !rays_o || !rays_d || !nears || !fars || !scratch ||
-        !depth || !image || !weights_sum || S == 0)
+        S == 0)
+        return NVSF_E_INVALID;
+    if (scratch_bytes < nvsf_render_uniform_scratch_bytes(N, S)) return NVSF_E_WORKSPACE;
+    const size_t n = (size_t)N * S;
+    float* sigma = reinterpret_cast<float*>(scratch);
+    __half* geo = reinterpret_cast<__half*>(reinterpret_cast<unsigned char*>(scratch) +
+                                            ws_align(n * sizeof(float)));
+    return nvsf_launch_density(cfg, workspace, nullptr, rays_o, rays_d, nears, fars, noise, S, n,
+                               sigma, geo, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+/* phase 2: compositing + colour heads from scratch */
+int nvsf_render_uniform_composite(const nvsf_field_config_t* cfg, const void* workspace,
+                                  uint32_t lidar, const float* rays_d, const float* nears,
+                                  const float* fars, const float* noise, uint32_t N, uint32_t S,
+                                  float bg_color, const void* scratch, size_t scratch_bytes,
+                                  float* depth, float* image, float* weights_sum, float* weights,
+                                  float* z_vals, void* stream) {
+    if (N == 0) return NVSF_OK;
+    if (!field_cfg_ok(cfg) || !workspace || !rays_d || !nears || !fars || !scratch || !depth ||
+        !image || !weights_sum || S == 0)
         return NVSF_E_INVALID;
     if ((weights == nullptr) != (z_vals == nullptr)) return NVSF_E_INVALID;
     if (scratch_bytes < nvsf_render_uniform_scratch_bytes(N, S)) return NVSF_E_WORKSPACE;
@@ -272,12 +291,9 @@ int nvsf_render_uniform(const nvsf_field_config_t* cfg, const void* workspace, u
     if (st != NVSF_OK) return st;
     cudaStream_t s = (cudaStream_t)stream;
     const size_t n = (size_t)N * S;
-    float* sigma = reinterpret_cast<float*>(scratch);
-    __half* geo = reinterpret_cast<__half*>(reinterpret_cast<unsigned char*>(scratch) +
-                                            ws_align(n * sizeof(float)));
-    st = nvsf_launch_density(cfg, workspace, nullptr, rays_o, rays_d, nears, fars, noise, S, n,
-                             sigma, geo, nullptr, nullptr, s);
-    if (st != NVSF_OK) return st;
+    const float* sigma = reinterpret_cast<const float*>(scratch);
+    const __half* geo = reinterpret_cast<const __half*>(
+        reinterpret_cast<const unsigned char*>(scratch) + ws_align(n * sizeof(float)));
     const FieldPtrs P = nvsf_make_field_ptrs(cfg, workspace);
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -293,6 +309,20 @@ int nvsf_render_uniform(const nvsf_field_config_t* cfg, const void* workspace, u
             weights_sum, weights, z_vals);
     }
     return nvsf_launch_status();
+}
+
+int nvsf_render_uniform(const nvsf_field_config_t* cfg, const void* workspace, uint32_t lidar,
+                        const float* rays_o, const float* rays_d, const float* nears,
+                        const float* fars, const float* noise, uint32_t N, uint32_t S,
+                        float bg_color, void* scratch, size_t scratch_bytes, float* depth,
+                        float* image, float* weights_sum, float* weights, float* z_vals,
+                        void* stream) {
+    int st = nvsf_render_uniform_density(cfg, workspace, rays_o, rays_d, nears, fars, noise, N, S,
+                                         scratch, scratch_bytes, stream);
+    if (st != NVSF_OK) return st;
+    return nvsf_render_uniform_composite(cfg, workspace, lidar, rays_d, nears, fars, noise, N, S,
+                                         bg_color, scratch, scratch_bytes, depth, image,
+                                         weights_sum, weights, z_vals, stream);
 }
 
 }  // extern "C"

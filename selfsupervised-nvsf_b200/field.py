@@ -98,6 +98,11 @@ def _setup_lib():
     L.nvsf_field_pack_params.argtypes = [cfgp, prmp, ctypes.c_uint32, P, ctypes.c_size_t, P]
     L.nvsf_field_pack_time.argtypes = [cfgp, prmp, P, P, ctypes.c_size_t, P]
     L.nvsf_field_density.argtypes = [cfgp, P, P, ctypes.c_uint32, P, P, P, P, P]
+    L.nvsf_render_uniform_density.argtypes = [cfgp, P, P, P, P, P, P, ctypes.c_uint32, ctypes.c_uint32, P,
+                                              ctypes.c_size_t, P]
+    L.nvsf_render_uniform_composite.argtypes = [cfgp, P, ctypes.c_uint32, P, P, P, P, ctypes.c_uint32,
+                                                ctypes.c_uint32, ctypes.c_float, P, ctypes.c_size_t, P, P,
+                                                P, P, P, P]
     L.nvsf_render_uniform.argtypes = [cfgp, P, ctypes.c_uint32, P, P, P, P, P, ctypes.c_uint32,
                                       ctypes.c_uint32, ctypes.c_float, P, ctypes.c_size_t, P, P, P,
                                       P, P, P]
