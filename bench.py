@@ -156,8 +156,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--ref-rays", type=int, default=48, help="rays per step of the CPU reference arm")
-    ap.add_argument("--cpu-rays", type=int, default=64, help="rays of the cpu_baseline sample")
+    ap.add_argument("--ref-rays", type=int, default=512, help="rays per step of the CPU reference arm")
+    ap.add_argument("--cpu-rays", type=int, default=2048, help="rays of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -314,15 +314,15 @@ __device__ __forceinline__ float uniform_z(float near, float far, uint32_t k, ui
 // ------------------------------------------------------------------------------------------------
 // the density kernel
 // ------------------------------------------------------------------------------------------------
-constexpr int kTile = 128;  // samples per CTA tile, one warp per 32 rows
+constexpr int kTile = 256;  // samples per CTA tile, one warp per 32 rows
 constexpr int kXld = kLdK128;
+constexpr int kFlowCol = 32;  // the 6 flow outputs (fp32) are staged in row bytes [64,96)
 constexpr size_t kDensitySmem = (size_t)kDensityWHalves * sizeof(__half) +
-                                (size_t)kTile * kXld * sizeof(__half) +
-                                (size_t)kTile * 8 * sizeof(float);
+                                (size_t)kTile * kXld * sizeof(__half);
 
 template <bool FROM_RAYS>
-__global__ void __launch_bounds__(kTile, 3)
-k_field_density(const nvsf_field_config_t cfg, const FieldPtrs P, const float* __restrict__ xin,
+__global__ void __launch_bounds__(kTile, 2)
+k_field_density(const __grid_constant__ nvsf_field_config_t cfg, const __grid_constant__ FieldPtrs P, const float* __restrict__ xin,
                 const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                 const float* __restrict__ nears, const float* __restrict__ fars,
                 const float* __restrict__ noise, uint32_t S, size_t n,
@@ -331,13 +331,12 @@ k_field_density(const nvsf_field_config_t cfg, const FieldPtrs P, const float* _
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __half* Wsm = reinterpret_cast<__half*>(smem_raw);
     __half* Xs = Wsm + kDensityWHalves;
-    float* flow_s = reinterpret_cast<float*>(Xs + kTile * kXld);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     block_copy16(Wsm, P.mlp, kDensityWHalves * (int)sizeof(__half) / 16, tid, kTile);
     __syncthreads();
 
-    const TimeInfo ti = *P.ti;
+    const int valid1 = P.ti->valid[1], valid2 = P.ti->valid[2];
     __half* xrow = Xs + tid * kXld;
     const __half* Aw = Xs + warp * 32 * kXld;
     const float inv2b = 1.0f / (2.0f * cfg.bound);
@@ -368,14 +367,9 @@ k_field_density(const nvsf_field_config_t cfg, const FieldPtrs P, const float* _
 
         // ---- phase 1: flow-grid features -> Xs[:, 0:32]  (flow_field.py:124-128) ----
 #pragma unroll 1
-        for (int l4 = 0; l4 < kFlLevels; l4 += 4) {
-            float v[8];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float2 f = hash3_f2(P.flow, lv(cfg.fl[l4 + j]), x, y, z);
-                v[2 * j] = f.x; v[2 * j + 1] = f.y;
-            }
-            st8(xrow, 2 * l4, v);
+        for (int l = 0; l < kFlLevels; ++l) {
+            const float2 f = hash3_f2(P.flow, lv(cfg.fl[l]), x, y, z);
+            *reinterpret_cast<uint32_t*>(xrow + 2 * l) = pack_half2(f.x, f.y);
         }
         __syncwarp();
 
@@ -399,9 +393,11 @@ k_field_density(const nvsf_field_config_t cfg, const FieldPtrs P, const float* _
             const int gq = lane >> 2, tq = lane & 3;
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt) {
-                float* r0 = flow_s + (warp * 32 + mt * 16 + gq) * 8 + 2 * tq;
-                *reinterpret_cast<float2*>(r0) = make_float2(o[mt][0][0], o[mt][0][1]);
-                *reinterpret_cast<float2*>(r0 + 64) = make_float2(o[mt][0][2], o[mt][0][3]);
+                __half* r0 = Xs + (warp * 32 + mt * 16 + gq) * kXld + kFlowCol;
+                *reinterpret_cast<float2*>(reinterpret_cast<float*>(r0) + 2 * tq) =
+                    make_float2(o[mt][0][0], o[mt][0][1]);
+                *reinterpret_cast<float2*>(reinterpret_cast<float*>(r0 + 8 * kXld) + 2 * tq) =
+                    make_float2(o[mt][0][2], o[mt][0][3]);
             }
         }
         __syncwarp();
@@ -409,7 +405,8 @@ k_field_density(const nvsf_field_config_t cfg, const FieldPtrs P, const float* _
         // ---- phase 3: the 120 sigma-net inputs ----
         float fl[6];
 #pragma unroll
-        for (int i = 0; i < 6; ++i) fl[i] = flow_s[tid * 8 + i];
+        for (int i = 0; i < 6; ++i) fl[i] = reinterpret_cast<const float*>(xrow + kFlowCol)[i];
+        __syncwarp();
         if (flow_out && live) {
 #pragma unroll
             for (int i = 0; i < 6; ++i) flow_out[g * 6 + i] = fl[i];
@@ -419,10 +416,10 @@ k_field_density(const nvsf_field_config_t cfg, const FieldPtrs P, const float* _
         float qx[3], qy[3], qz[3];
         int qi[3];
         qx[0] = x; qy[0] = y; qz[0] = z; qi[0] = 0;
-        qx[1] = ti.valid[1] ? x + fl[0] : x; qy[1] = ti.valid[1] ? y + fl[1] : y;
-        qz[1] = ti.valid[1] ? z + fl[2] : z; qi[1] = ti.valid[1] ? 1 : 0;
-        qx[2] = ti.valid[2] ? x + fl[3] : x; qy[2] = ti.valid[2] ? y + fl[4] : y;
-        qz[2] = ti.valid[2] ? z + fl[5] : z; qi[2] = ti.valid[2] ? 2 : 0;
+        qx[1] = valid1 ? x + fl[0] : x; qy[1] = valid1 ? y + fl[1] : y;
+        qz[1] = valid1 ? z + fl[2] : z; qi[1] = valid1 ? 1 : 0;
+        qx[2] = valid2 ? x + fl[3] : x; qy[2] = valid2 ? y + fl[4] : y;
+        qz[2] = valid2 ? z + fl[5] : z; qi[2] = valid2 ? 2 : 0;
 
         // (a) static planes: product of xy, xz, yz per scale -> cols [0,32)
 #pragma unroll 1
@@ -455,29 +452,32 @@ k_field_density(const nvsf_field_config_t cfg, const FieldPtrs P, const float* _
         }
         // (c) static 3-D hash -> [64,96)
 #pragma unroll 1
-        for (int l2 = 0; l2 < kHsLevels; l2 += 2) {
-            float v[8];
-            hash3_f4(P.hs16, lv(cfg.hs[l2]), x, y, z, v);
-            hash3_f4(P.hs16, lv(cfg.hs[l2 + 1]), x, y, z, v + 4);
-            st8(xrow, 64 + 4 * l2, v);
+        for (int l = 0; l < kHsLevels; ++l) {
+            float v[4];
+            hash3_f4(P.hs16, lv(cfg.hs[l]), x, y, z, v);
+            uint2 o2;
+            o2.x = pack_half2(v[0], v[1]); o2.y = pack_half2(v[2], v[3]);
+            *reinterpret_cast<uint2*>(xrow + 64 + 4 * l) = o2;
         }
-        // (d) dynamic 2-D hashes xy, xz, yz -> [96,120)
+        // (d) dynamic 2-D hashes xy, xz, yz -> [96,120): 0.5 f(x,t) + 0.25 (f(x1,t1) + f(x2,t2))
 #pragma unroll 1
         for (int p = 0; p < 3; ++p) {
-            float acc8[8];
+            float u[3], w[3];
+            const float* tab[3];
 #pragma unroll
             for (int q = 0; q < 3; ++q) {
-                const float* tab = P.dyn + (size_t)qi[q] * P.dyn_per_q + P.dyn_plane[p];
-                const float u = p == 2 ? qy[q] : qx[q];
-                const float w = p == 0 ? qy[q] : qz[q];
-                const float wq = q == 0 ? 0.5f : 0.25f;
-#pragma unroll
-                for (int l = 0; l < kHdLevels; ++l) {
-                    const float f = hash2_f1(tab, lv(cfg.hd[p][l]), u, w);
-                    acc8[l] = q == 0 ? wq * f : fmaf(wq, f, acc8[l]);
-                }
+                u[q] = p == 2 ? qy[q] : qx[q];
+                w[q] = p == 0 ? qy[q] : qz[q];
+                tab[q] = P.dyn + (size_t)qi[q] * P.dyn_per_q + P.dyn_plane[p];
             }
-            st8(xrow, 96 + 8 * p, acc8);
+#pragma unroll 1
+            for (int l = 0; l < kHdLevels; ++l) {
+                const LevelArgs L = lv(cfg.hd[p][l]);
+                const float f0 = hash2_f1(tab[0], L, u[0], w[0]);
+                const float f1 = hash2_f1(tab[1], L, u[1], w[1]);
+                const float f2 = hash2_f1(tab[2], L, u[2], w[2]);
+                xrow[96 + 8 * p + l] = __float2half_rn(0.5f * f0 + 0.25f * (f1 + f2));
+            }
         }
         {
             const float zero8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};

@@ -39,7 +39,7 @@ __device__ __forceinline__ float sigmoidf_(float h) { return 1.0f / (1.0f + expf
 
 template <bool LIDAR>
 __global__ void __launch_bounds__(kRWarps * 32)
-k_render_composite(const nvsf_field_config_t cfg, const __half* __restrict__ mlp,
+k_render_composite(const __grid_constant__ nvsf_field_config_t cfg, const __half* __restrict__ mlp,
                    const float* __restrict__ rays_d, const float* __restrict__ nears,
                    const float* __restrict__ fars, const float* __restrict__ noise,
                    const float* __restrict__ sigma, const __half* __restrict__ geo, uint32_t N,
