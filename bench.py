@@ -180,6 +180,8 @@ def main():
     S = importlib.import_module("selfsupervised-nvsf_b200.synth")
     F = pkg.field
     L = F._setup_lib()
+    if "NVSF_DENSITY_MODE" in os.environ:  # development A/B switch; default = library default
+        F.check(L.nvsf_set_option(b"density_mode", int(os.environ["NVSF_DENSITY_MODE"])), "set_option")
 
     # ---- model: random init exactly as the reference initialisers, same on every rank ----
     cfg_kw = dict(bound=S.BOUND, num_frames=S.NUM_FRAMES, time_resolution=S.TIME_RESOLUTION, min_near=S.MIN_NEAR,

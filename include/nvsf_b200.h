@@ -33,7 +33,7 @@ extern "C" {
 #define NVSF_E_WORKSPACE (-2) /* workspace too small */
 
 /* ABI version of this header; bumped on any signature change. */
-#define NVSF_B200_ABI_VERSION 5
+#define NVSF_B200_ABI_VERSION 6
 int nvsf_abi_version(void);
 /* Human-readable text for a status returned by any nvsf_* call. */
 const char* nvsf_status_string(int status);
@@ -212,14 +212,21 @@ int nvsf_field_pack_time(const nvsf_field_config_t* cfg, const nvsf_field_params
 /* replaces NeRFNetwork.density (network_dynamic.py:213-287) for n points x [n,3] in
  * [-bound,bound]: sigma [n] f32, geo [n,16] f16 (column 0 = raw sigma logit, 1..15 = geo_feat).
  * Optional debug outputs (may be NULL): features [n,128] f16 (the 120 sigma-net inputs in the
- * reference's concat order, network_dynamic.py:276, zero padded) and flow [n,6] f32. */
+ * reference's concat order, network_dynamic.py:276, zero padded) and flow [n,6] f32.
+ * scratch (nvsf_field_density_scratch_bytes(n), may be NULL -> fused kernel). */
+size_t nvsf_field_density_scratch_bytes(uint32_t n);
 int nvsf_field_density(const nvsf_field_config_t* cfg, const void* workspace, const float* x,
                        uint32_t n, float* sigma, void* geo, void* features, float* flow,
-                       void* stream);
+                       void* scratch, size_t scratch_bytes, void* stream);
+
+/* Tuning switches.  "density_mode": 1 (default) = staged density evaluation (flow stage, lean
+ * gather stage at high occupancy, MLP stage; needs the scratch buffer), 0 = single fused kernel. */
+int nvsf_set_option(const char* name, int value);
 
 /* replaces NeRFRenderer.run (renderer_dynamic.py:109-265) for N rays with S uniform samples.
  * nears/fars [N]; noise [N,S] in [0,1) or NULL (perturb=False); bg_color used for camera only.
- * scratch: N*S*(4+32) bytes (sigma f32 + geo f16[16] per sample).
+ * scratch: nvsf_render_uniform_scratch_bytes(N,S) = N*S*(4+32) bytes (sigma f32 + geo f16[16] per
+ * sample) + the staged-density intermediates of one chunk.
  * Outputs: depth [N], image [N,2|3], weights_sum [N]; weights/z_vals [N,S] optional (NULL ok). */
 size_t nvsf_render_uniform_scratch_bytes(uint32_t N, uint32_t S);
 /* The two phases of nvsf_render_uniform, callable separately (bench.py times them apart):

@@ -55,7 +55,9 @@ PROTOTYPES = {
     "nvsf_field_workspace_bytes": (_sz, [_p]),
     "nvsf_field_pack_params": (_int, [_p, _p, _u32, _p, _sz, _p]),
     "nvsf_field_pack_time": (_int, [_p, _p, _p, _p, _sz, _p]),
-    "nvsf_field_density": (_int, [_p, _p, _p, _u32, _p, _p, _p, _p, _p]),
+    "nvsf_field_density_scratch_bytes": (_sz, [_u32]),
+    "nvsf_field_density": (_int, [_p, _p, _p, _u32, _p, _p, _p, _p, _p, _sz, _p]),
+    "nvsf_set_option": (_int, [ctypes.c_char_p, _int]),
     "nvsf_render_uniform_scratch_bytes": (_sz, [_u32, _u32]),
     "nvsf_render_uniform_density": (_int, [_p, _p, _p, _p, _p, _p, _p, _u32, _u32, _p, _sz, _p]),
     "nvsf_render_uniform_composite": (_int, [_p, _p, _u32, _p, _p, _p, _p, _u32, _u32, _f32, _p, _sz,
@@ -94,7 +96,7 @@ def lib():
     return _lib
 
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 
 def check(status, what=""):

@@ -118,11 +118,21 @@ struct FieldPtrs {
 };
 
 FieldPtrs nvsf_make_field_ptrs(const nvsf_field_config_t* cfg, const void* workspace);
-// Density kernel launcher shared by field.cu (explicit points) and render.cu (points from rays).
+// Density launcher shared by field.cu (explicit points) and render.cu (points from rays).
+// split_scratch != NULL and density mode 1 select the staged variant (field_split.cu).
 int nvsf_launch_density(const nvsf_field_config_t* cfg, const void* workspace, const float* x,
                         const float* rays_o, const float* rays_d, const float* nears,
                         const float* fars, const float* noise, uint32_t S, size_t n, float* sigma,
-                        void* geo, void* features, float* flow, cudaStream_t stream);
+                        void* geo, void* features, float* flow, void* split_scratch,
+                        cudaStream_t stream);
+constexpr size_t kSplitChunk = (size_t)4 << 20;  // samples per chunk of the staged variant
+size_t nvsf_density_split_scratch_bytes(size_t n);
+int nvsf_launch_density_split(const nvsf_field_config_t* cfg, const void* workspace,
+                              const float* x, const float* rays_o, const float* rays_d,
+                              const float* nears, const float* fars, const float* noise,
+                              uint32_t S, size_t n, float* sigma, void* geo, void* features,
+                              float* flow, void* split_scratch, cudaStream_t stream);
+int nvsf_density_mode();
 
 // ---- tensor-core helpers ------------------------------------------------------------------------
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
@@ -251,3 +261,140 @@ __device__ __forceinline__ uint32_t idx3(const LevelArgs& L, uint32_t cx, uint32
     if (L.hashed) return (cx ^ (cy * 2654435761u) ^ (cz * 805459861u)) & (L.size - 1);
     return (cx + cy * L.res + cz * L.res * L.res) % L.size;
 }
+
+// ---- per-sample encoder primitives ----------------------------------------------------------
+__device__ __forceinline__ void st8(__half* row, int col, const float (&v)[8]) {
+    uint4 o;
+    o.x = pack_half2(v[0], v[1]); o.y = pack_half2(v[2], v[3]);
+    o.z = pack_half2(v[4], v[5]); o.w = pack_half2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(row + col) = o;
+}
+
+// grid_sample unnormalise (align_corners=True) + border clamp
+__device__ __forceinline__ void plane_coord(float p, uint32_t R, uint32_t& i0, uint32_t& i1,
+                                            float& w) {
+    float f = ((p * 2.0f - 1.0f) + 1.0f) * 0.5f * (float)(R - 1);
+    f = fminf(fmaxf(f, 0.f), (float)(R - 1));
+    const float fl = floorf(f);
+    i0 = (uint32_t)fl;
+    i1 = min(i0 + 1, R - 1);
+    w = f - fl;
+}
+
+__device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+// bilinear sample of a channel-last [R][R][8] plane at (pa -> column, pb -> row); out *= sample
+__device__ __forceinline__ void plane2d_mul(const float* __restrict__ base, uint32_t R, float pa,
+                                            float pb, float (&out)[8], bool first) {
+    uint32_t x0, x1, y0, y1;
+    float wx, wy;
+    plane_coord(pa, R, x0, x1, wx);
+    plane_coord(pb, R, y0, y1, wy);
+    float a[8], b[8], c[8], d[8];
+    ld8(base + ((size_t)y0 * R + x0) * 8, a);
+    ld8(base + ((size_t)y0 * R + x1) * 8, b);
+    ld8(base + ((size_t)y1 * R + x0) * 8, c);
+    ld8(base + ((size_t)y1 * R + x1) * 8, d);
+    const float w00 = (1.f - wx) * (1.f - wy), w01 = wx * (1.f - wy), w10 = (1.f - wx) * wy,
+                w11 = wx * wy;
+#pragma unroll
+    for (int f = 0; f < 8; ++f) {
+        const float s = w00 * a[f] + w01 * b[f] + w10 * c[f] + w11 * d[f];
+        out[f] = first ? s : out[f] * s;
+    }
+}
+
+// linear sample of a time-collapsed [R][8] row table
+__device__ __forceinline__ void plane1d_mul(const float* __restrict__ base, uint32_t R, float pa,
+                                            float (&out)[8], bool first) {
+    uint32_t x0, x1;
+    float wx;
+    plane_coord(pa, R, x0, x1, wx);
+    float a[8], b[8];
+    ld8(base + (size_t)x0 * 8, a);
+    ld8(base + (size_t)x1 * 8, b);
+#pragma unroll
+    for (int f = 0; f < 8; ++f) {
+        const float s = (1.f - wx) * a[f] + wx * b[f];
+        out[f] = first ? s : out[f] * s;
+    }
+}
+
+// one level of the 3-D fp16 static hash grid (4 features)
+__device__ __forceinline__ void hash3_f4(const uint2* __restrict__ tab, const LevelArgs& L,
+                                         float x, float y, float z, float* out) {
+    uint32_t cx, cy, cz;
+    float wx, wy, wz;
+    grid_pos(L.scale, x, cx, wx);
+    grid_pos(L.scale, y, cy, wy);
+    grid_pos(L.scale, z, cz, wz);
+    uint2 v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        v[c] = __ldg(tab + L.offset + idx3(L, cx + (c & 1), cy + ((c >> 1) & 1), cz + (c >> 2)));
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const float w = ((c & 1) ? wx : 1.f - wx) * ((c & 2) ? wy : 1.f - wy) *
+                        ((c & 4) ? wz : 1.f - wz);
+        const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&v[c].x));
+        const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&v[c].y));
+        a0 = fmaf(w, lo.x, a0); a1 = fmaf(w, lo.y, a1);
+        a2 = fmaf(w, hi.x, a2); a3 = fmaf(w, hi.y, a3);
+    }
+    out[0] = a0; out[1] = a1; out[2] = a2; out[3] = a3;
+}
+
+// one level of a time-collapsed 2-D dynamic hash grid (1 value)
+__device__ __forceinline__ float hash2_f1(const float* __restrict__ tab, const LevelArgs& L,
+                                          float u, float v) {
+    uint32_t cu, cv;
+    float wu, wv;
+    grid_pos(L.scale, u, cu, wu);
+    grid_pos(L.scale, v, cv, wv);
+    const float t00 = __ldg(tab + L.offset + idx2(L, cu, cv));
+    const float t10 = __ldg(tab + L.offset + idx2(L, cu + 1, cv));
+    const float t01 = __ldg(tab + L.offset + idx2(L, cu, cv + 1));
+    const float t11 = __ldg(tab + L.offset + idx2(L, cu + 1, cv + 1));
+    return (1.f - wu) * (1.f - wv) * t00 + wu * (1.f - wv) * t10 + (1.f - wu) * wv * t01 +
+           wu * wv * t11;
+}
+
+// one level of the time-collapsed 3-D flow grid (2 values)
+__device__ __forceinline__ float2 hash3_f2(const float2* __restrict__ tab, const LevelArgs& L,
+                                           float x, float y, float z) {
+    uint32_t cx, cy, cz;
+    float wx, wy, wz;
+    grid_pos(L.scale, x, cx, wx);
+    grid_pos(L.scale, y, cy, wy);
+    grid_pos(L.scale, z, cz, wz);
+    float2 v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        v[c] = __ldg(tab + L.offset + idx3(L, cx + (c & 1), cy + ((c >> 1) & 1), cz + (c >> 2)));
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const float w = ((c & 1) ? wx : 1.f - wx) * ((c & 2) ? wy : 1.f - wy) *
+                        ((c & 4) ? wz : 1.f - wz);
+        a0 = fmaf(w, v[c].x, a0);
+        a1 = fmaf(w, v[c].y, a1);
+    }
+    return make_float2(a0, a1);
+}
+
+// z value of uniform sample k of S in [near, far]  (torch.linspace(0,1,S), renderer_dynamic.py:155-164)
+__device__ __forceinline__ float uniform_z(float near, float far, uint32_t k, uint32_t S,
+                                           const float* __restrict__ noise, size_t g) {
+    const float step = 1.0f / (float)(S > 1 ? S - 1 : 1);
+    const float lin = (k < S / 2) ? step * (float)k : 1.0f - step * (float)(S - 1 - k);
+    float z = near + (far - near) * lin;
+    if (noise) z = z + (__ldg(noise + g) - 0.5f) * ((far - near) / (float)S);
+    return z;
+}
+

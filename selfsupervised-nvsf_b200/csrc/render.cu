@@ -253,7 +253,8 @@ extern "C" {
 
 size_t nvsf_render_uniform_scratch_bytes(uint32_t N, uint32_t S) {
     const size_t n = (size_t)N * S;
-    return ws_align(n * sizeof(float)) + ws_align(n * kGeo * sizeof(__half));
+    return ws_align(n * sizeof(float)) + ws_align(n * kGeo * sizeof(__half)) +
+           nvsf_density_split_scratch_bytes(n);
 }
 
 /* phase 1: field evaluation of all N*S samples into scratch (sigma f32, geo f16[16]) */
@@ -270,8 +271,9 @@ int nvsf_render_uniform_density(const nvsf_field_config_t* cfg, const void* work
     float* sigma = reinterpret_cast<float*>(scratch);
     __half* geo = reinterpret_cast<__half*>(reinterpret_cast<unsigned char*>(scratch) +
                                             ws_align(n * sizeof(float)));
+    void* split = reinterpret_cast<unsigned char*>(geo) + ws_align(n * kGeo * sizeof(__half));
     return nvsf_launch_density(cfg, workspace, nullptr, rays_o, rays_d, nears, fars, noise, S, n,
-                               sigma, geo, nullptr, nullptr, (cudaStream_t)stream);
+                               sigma, geo, nullptr, nullptr, split, (cudaStream_t)stream);
 }
 
 /* phase 2: compositing + colour heads from scratch */

@@ -97,7 +97,7 @@ def _setup_lib():
     L.nvsf_field_workspace_bytes.argtypes = [cfgp]
     L.nvsf_field_pack_params.argtypes = [cfgp, prmp, ctypes.c_uint32, P, ctypes.c_size_t, P]
     L.nvsf_field_pack_time.argtypes = [cfgp, prmp, P, P, ctypes.c_size_t, P]
-    L.nvsf_field_density.argtypes = [cfgp, P, P, ctypes.c_uint32, P, P, P, P, P]
+    L.nvsf_field_density.argtypes = [cfgp, P, P, ctypes.c_uint32, P, P, P, P, P, ctypes.c_size_t, P]
     L.nvsf_render_uniform_density.argtypes = [cfgp, P, P, P, P, P, P, ctypes.c_uint32, ctypes.c_uint32, P,
                                               ctypes.c_size_t, P]
     L.nvsf_render_uniform_composite.argtypes = [cfgp, P, ctypes.c_uint32, P, P, P, P, ctypes.c_uint32,
@@ -295,8 +295,10 @@ class NeRFNetwork(nn.Module):
         geo = torch.empty(n, 16, dtype=torch.float16, device=x.device)
         feats = torch.empty(n, 128, dtype=torch.float16, device=x.device) if want_features else None
         flow = torch.empty(n, 6, dtype=torch.float32, device=x.device) if want_flow else None
+        sbytes = L.nvsf_field_density_scratch_bytes(n)
+        scratch = torch.empty(max(sbytes, 16), dtype=torch.uint8, device=x.device)
         check(L.nvsf_field_density(ctypes.byref(self._cfg), ptr(ws), ptr(x), n, ptr(sigma), ptr(geo),
-                                   ptr(feats), ptr(flow), stream_ptr()), "field_density")
+                                   ptr(feats), ptr(flow), ptr(scratch), sbytes, stream_ptr()), "field_density")
         return sigma, geo, feats, flow
 
     @torch.no_grad()

@@ -171,3 +171,24 @@ def test_params_repack_on_update(model):
         model.sigma_net.div_(1.5)
     c = model.density(x, 0.4, True)["sigma"]
     torch.testing.assert_close(a, c, rtol=1e-3, atol=1e-5)
+
+
+def test_density_modes_agree(pkg, model):
+    """The staged density evaluation (mode 1, default) and the single fused kernel (mode 0) run the
+    same arithmetic: sigma / geo / rendered outputs agree to fp16-tile rounding."""
+    L = pkg._lib.lib()
+    x = torch.from_numpy(pts(3000, 11)).cuda()
+    o, d = S.lidar_rays(300, seed=4)
+    to, td = torch.from_numpy(o).cuda()[None], torch.from_numpy(d).cuda()[None]
+    res = {}
+    try:
+        for mode in (0, 1):
+            assert L.nvsf_set_option(b"density_mode", mode) == 0
+            den = model.density(x, 0.37, True)
+            r = model.render(to, td, torch.tensor([[0.37]], device="cuda"), cal_lidar_color=True, num_steps=96)
+            res[mode] = (host(den["sigma"]), host(den["geo_feat"]), host(r["depth_lidar"]), host(r["image_lidar"]))
+    finally:
+        L.nvsf_set_option(b"density_mode", 1)
+    assert L.nvsf_set_option(b"density_mode", 7) == -1 and L.nvsf_set_option(b"nope", 0) == -1
+    for a, b, name in zip(res[0], res[1], ("sigma", "geo", "depth", "image")):
+        close(a, b, 2e-3, 2e-3 * np.abs(b).max(), name)
