@@ -28,6 +28,19 @@ from . import tcnn_standin as T
 PLANE_COMBS = list(itertools.combinations(range(4), 2))  # (0,1),(0,2),(0,3),(1,2),(1,3),(2,3)
 
 
+class _TruncExp(torch.autograd.Function):
+    """trunc_exp (activation.py:6-20): exp forward, gradient g * exp(clamp(x, -15, 15))."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return torch.exp(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g * torch.exp(ctx.saved_tensors[0].clamp(-15, 15))
+
+
 class FieldConfig:
     """Sizes of the reference field at its defaults (main_nvsf.py:44-60, hash_field.py:95-101,
     flow_field.py:50-55) — every number can be shrunk for tests."""
@@ -192,12 +205,14 @@ class FieldOracle:
         if frame_idx < c.num_frames - 1:
             x1 = xn + flow[:, :3]
             t1 = float(np.float32((frame_idx + 1) / c.num_frames))
-            hash_1 = self._hash_dynamic(mod, x1, t1)
+            with torch.no_grad():  # network_dynamic.py:245-249: the warped hash query carries no gradient
+                hash_1 = self._hash_dynamic(mod, x1, t1)
             plane_1 = self._planes(mod, torch.cat([x1, torch.full_like(tcol, t1)], -1), "dynamic")
         if frame_idx > 0:
             x2 = xn + flow[:, 3:]
             t2 = float(np.float32((frame_idx - 1) / c.num_frames))
-            hash_2 = self._hash_dynamic(mod, x2, t2)
+            with torch.no_grad():  # network_dynamic.py:261-265
+                hash_2 = self._hash_dynamic(mod, x2, t2)
             plane_2 = self._planes(mod, torch.cat([x2, torch.full_like(tcol, t2)], -1), "dynamic")
         plane_d = 0.5 * plane_d + 0.25 * (plane_1 + plane_2)
         hash_d = 0.5 * hash_d + 0.25 * (hash_1 + hash_2)
@@ -207,7 +222,7 @@ class FieldOracle:
         feats, _ = self.features(x, t, lidar)
         hdim = self.cfg.hidden
         h = mlp(self.p["sigma_net"], [(hdim, 128), (16, hdim)], feats, 1 + self.cfg.geo_feat_dim)
-        return {"sigma": torch.exp(h[:, 0]), "geo_feat": h[:, 1:]}
+        return {"sigma": _TruncExp.apply(h[:, 0]), "geo_feat": h[:, 1:]}
 
     def color(self, d, geo_feat, lidar, mask=None):
         out_dim = 2 if lidar else 3

@@ -27,3 +27,63 @@ def oracle_params(seed=0, style="trained"):
 def rel_err(a, b, floor=1e-6):
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
     return float((np.abs(a - b) / (np.abs(b) + floor)).max())
+
+
+# ---- gradient cases (tests/golden/field_grad_ref.npz, oracle/make_golden_grad.py) -------------------
+GRAD_CASES = ["l_mid", "c_mid", "l_first", "c_last"]
+GRAD_SHARED = ("flow_grid", "flow_mlp", "sigma_net", "intensity_net", "raydrop_net", "color_net")
+GRAD_NAMES = ("hash_static", "hash_dynamic", "planes") + GRAD_SHARED
+
+
+def grad_case(gold, tag):
+    k = tag + "_"
+    lidar, t, ds, perturb = gold[k + "meta"].tolist()
+    return dict(lidar=bool(lidar), t=float(t), ds=float(ds), o=gold[k + "o"], d=gold[k + "d"],
+                noise=gold[k + "noise"] if perturb else None,
+                coef={n: gold[k + "coef_" + n] for n in "abce"})
+
+
+def linear_loss(out, coef, to=lambda a: torch.from_numpy(a)):
+    """The fixed functional of the render outputs the gradient goldens were taken for."""
+    n = coef["a"].shape[0]
+    return ((to(coef["a"]) * out["depth"].reshape(-1)).sum() + (to(coef["b"]) * out["image"].reshape(n, -1)).sum()
+            + (to(coef["c"]) * out["weights"]).sum() + (to(coef["e"]) * out["weights_sum"]).sum())
+
+
+def oracle_grads(case, params=None):
+    """Autograd gradients of the CPU oracle for one gradient case, in the flat parameter layout."""
+    from oracle.field_oracle import FieldOracle
+    from oracle import raymarching_oracle as RO
+    base = params if params is not None else oracle_params()
+    mod = "lidar" if case["lidar"] else "camera"
+    leaf = {mod: {k: v.clone().requires_grad_(True) for k, v in base[mod].items()}}
+    for k in GRAD_SHARED:
+        leaf[k] = base[k].clone().requires_grad_(True)
+    orc = FieldOracle(oracle_config(density_scale=case["ds"]), leaf)
+    nears = fars = None
+    if not case["lidar"]:
+        n, f = RO.near_far_from_aabb(case["o"], case["d"], S.AABB, S.MIN_NEAR)
+        nears, fars = torch.from_numpy(n), torch.from_numpy(f)
+    S_ = case["coef"]["c"].shape[1]
+    out = orc.run(torch.from_numpy(case["o"]), torch.from_numpy(case["d"]), case["t"], case["lidar"], S_, nears,
+                  fars, None if case["noise"] is None else torch.from_numpy(case["noise"]))
+    loss = linear_loss(out, case["coef"])
+    loss.backward()
+    g = {k: (v.grad if v.grad is not None else torch.zeros_like(v)).numpy() for k, v in leaf[mod].items()}
+    for k in GRAD_SHARED:
+        g[k] = (leaf[k].grad if leaf[k].grad is not None else torch.zeros_like(leaf[k])).numpy()
+    return g, float(loss.item()), out
+
+
+def check_grad_summary(gold, tag, name, g, rtol, what):
+    """Compare a full gradient tensor with the fixture's summary of the reference gradient."""
+    k = f"{tag}_g_{name}_"
+    idx, val, l2 = gold[k + "idx"], gold[k + "val"], float(gold[k + "l2"])
+    if l2 == 0.0:
+        assert not np.any(g), (what, tag, name, "expected an all-zero gradient")
+        return
+    got = np.asarray(g, np.float64).reshape(-1)
+    err = np.sqrt(((got[idx] - val.astype(np.float64)) ** 2).sum()) / np.sqrt((val.astype(np.float64) ** 2).sum())
+    assert err < rtol, (what, tag, name, "sampled entries", err)
+    assert abs(np.sqrt((got ** 2).sum()) - l2) < rtol * l2, (what, tag, name, "l2", np.sqrt((got ** 2).sum()), l2)
+    assert abs(got.sum() - float(gold[k + "sum"])) < rtol * max(l2, abs(float(gold[k + "sum"]))), (what, tag, name, "sum")
