@@ -33,7 +33,7 @@ extern "C" {
 #define NVSF_E_WORKSPACE (-2) /* workspace too small */
 
 /* ABI version of this header; bumped on any signature change. */
-#define NVSF_B200_ABI_VERSION 6
+#define NVSF_B200_ABI_VERSION 7
 int nvsf_abi_version(void);
 /* Human-readable text for a status returned by any nvsf_* call. */
 const char* nvsf_status_string(int status);
@@ -247,6 +247,65 @@ int nvsf_render_uniform(const nvsf_field_config_t* cfg, const void* workspace, u
                         float bg_color, void* scratch, size_t scratch_bytes, float* depth,
                         float* image, float* weights_sum, float* weights, float* z_vals,
                         void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* Part 3 — training: forward that keeps its intermediates, and the backward     */
+/* ------------------------------------------------------------------------- */
+
+/* fp32 gradient buffers of ONE modality, same layouts and sizes as nvsf_field_params_t.  The
+ * backward ACCUMULATES into them (+=); the caller zero-fills (or keeps accumulating, like
+ * autograd's .grad).  This is what loss.backward() leaves in the `.grad` of the reference's
+ * tcnn `params`, Planes4D parameters and nn.Linear weights (trainer.py:1332). */
+typedef struct {
+    float* hash_static;
+    float* hash_dynamic;
+    float* planes;
+    float* flow_grid;
+    float* flow_mlp;
+    float* sigma_net;
+    float* head_a; /* lidar: intensity_net ; camera: color_net */
+    float* head_b; /* lidar: raydrop_net   ; camera: NULL */
+} nvsf_field_grads_t;
+
+/* Bytes of the per-call buffer in which the training forward keeps, per sample: sigma f32,
+ * sigma-net output f16[16], flow f32[8], the 120 sigma-net inputs f16[128], the flow-MLP inputs
+ * f16[32] and the head colours f32[4]  (444 B per sample). */
+size_t nvsf_render_uniform_saved_bytes(uint32_t N, uint32_t S);
+/* Bytes of backward scratch (bf16 weight images, time-collapsed gradient tables, per-chunk
+ * activation gradients; rays are processed in chunks of ~6 M samples). */
+size_t nvsf_render_uniform_backward_scratch_bytes(const nvsf_field_config_t* cfg, uint32_t N,
+                                                  uint32_t S);
+
+/* Test/debug aid: byte offsets of the per-sample arrays inside `saved` (sigma, geo, flow, feats,
+ * flowfeat, rgbs) and inside the backward scratch (dgeo16 f32[.,16], dfeat f32[.,128], dflow
+ * f32[.,8], dflowfeat f32[.,32] of the LAST chunk), then rays per chunk and total scratch bytes:
+ * out[12]. */
+void nvsf_render_uniform_debug_layout(const nvsf_field_config_t* cfg, uint32_t N, uint32_t S,
+                                      size_t* out);
+
+/* NeRFRenderer.run (renderer_dynamic.py:109-265) in training mode: same outputs as
+ * nvsf_render_uniform (weights and z_vals are mandatory), intermediates kept in `saved`. */
+int nvsf_render_uniform_train_forward(const nvsf_field_config_t* cfg, const void* workspace,
+                                      uint32_t lidar, const float* rays_o, const float* rays_d,
+                                      const float* nears, const float* fars, const float* noise,
+                                      uint32_t N, uint32_t S, float bg_color, void* saved,
+                                      size_t saved_bytes, float* depth, float* image,
+                                      float* weights_sum, float* weights, float* z_vals,
+                                      void* stream);
+
+/* Backward of the above: given dL/d(depth) [N], dL/d(image) [N,2|3], dL/d(weights_sum) [N] and
+ * dL/d(weights) [N,S] (each may be NULL = zero), accumulates dL/d(parameters) into `grads`.
+ * `workspace` must still hold the tables packed for the forward's time; `params` are the fp32
+ * masters (MLP weights are re-packed to bf16); `weights` is the forward's output. */
+int nvsf_render_uniform_backward(const nvsf_field_config_t* cfg, const void* workspace,
+                                 const nvsf_field_params_t* params, uint32_t lidar,
+                                 const float* rays_o, const float* rays_d, const float* nears,
+                                 const float* fars, const float* noise, uint32_t N, uint32_t S,
+                                 float bg_color, const void* saved, size_t saved_bytes,
+                                 const float* weights, const float* g_depth, const float* g_image,
+                                 const float* g_weights_sum, const float* g_weights,
+                                 const nvsf_field_grads_t* grads, void* scratch,
+                                 size_t scratch_bytes, void* stream);
 
 #ifdef __cplusplus
 }

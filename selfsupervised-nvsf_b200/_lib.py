@@ -64,6 +64,14 @@ PROTOTYPES = {
                                              _p, _p, _p, _p, _p, _p]),
     "nvsf_render_uniform": (_int, [_p, _p, _u32, _p, _p, _p, _p, _p, _u32, _u32, _f32, _p, _sz, _p,
                                    _p, _p, _p, _p, _p]),
+    # Part 3 — training
+    "nvsf_render_uniform_saved_bytes": (_sz, [_u32, _u32]),
+    "nvsf_render_uniform_backward_scratch_bytes": (_sz, [_p, _u32, _u32]),
+    "nvsf_render_uniform_debug_layout": (None, [_p, _u32, _u32, _p]),
+    "nvsf_render_uniform_train_forward": (_int, [_p, _p, _u32, _p, _p, _p, _p, _p, _u32, _u32, _f32, _p,
+                                                 _sz, _p, _p, _p, _p, _p, _p]),
+    "nvsf_render_uniform_backward": (_int, [_p, _p, _p, _u32, _p, _p, _p, _p, _p, _u32, _u32, _f32, _p,
+                                            _sz, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
 }
 
 _lib = None
@@ -96,7 +104,7 @@ def lib():
     return _lib
 
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 
 def check(status, what=""):

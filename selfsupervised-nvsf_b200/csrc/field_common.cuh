@@ -127,12 +127,27 @@ int nvsf_launch_density(const nvsf_field_config_t* cfg, const void* workspace, c
                         cudaStream_t stream);
 constexpr size_t kSplitChunk = (size_t)4 << 20;  // samples per chunk of the staged variant
 size_t nvsf_density_split_scratch_bytes(size_t n);
+// Intermediates of the staged evaluation that the training forward keeps for the backward pass.
+struct DensityKeep {
+    float* flow;        // [n,8]   flow MLP output (6 used)
+    __half* feats;      // [n,128] sigma-net input
+    __half* flowfeat;   // [n,32]  flow MLP input
+};
 int nvsf_launch_density_split(const nvsf_field_config_t* cfg, const void* workspace,
                               const float* x, const float* rays_o, const float* rays_d,
                               const float* nears, const float* fars, const float* noise,
                               uint32_t S, size_t n, float* sigma, void* geo, void* features,
-                              float* flow, void* split_scratch, cudaStream_t stream);
+                              float* flow, void* split_scratch, cudaStream_t stream,
+                              const DensityKeep* keep = nullptr);
 int nvsf_density_mode();
+// Compositing + heads launcher (render.cu); scratch = sigma f32 [N*S] then geo f16 [N*S,16];
+// rgbs (f32 [N*S,4], may be NULL) receives the per-sample colours for the backward pass.
+int nvsf_render_composite_launch(const nvsf_field_config_t* cfg, const void* workspace,
+                                 uint32_t lidar, const float* rays_d, const float* nears,
+                                 const float* fars, const float* noise, uint32_t N, uint32_t S,
+                                 float bg_color, const void* scratch, size_t scratch_bytes,
+                                 float* depth, float* image, float* weights_sum, float* weights,
+                                 float* z_vals, void* rgbs, void* stream);
 
 // ---- tensor-core helpers ------------------------------------------------------------------------
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {

@@ -58,7 +58,8 @@ k_flow_stage(const __grid_constant__ nvsf_field_config_t cfg, const __grid_const
              const float* __restrict__ xin, const float* __restrict__ rays_o,
              const float* __restrict__ rays_d, const float* __restrict__ nears,
              const float* __restrict__ fars, const float* __restrict__ noise, uint32_t S,
-             size_t begin, size_t count, float* __restrict__ flow_out) {
+             size_t begin, size_t count, float* __restrict__ flow_out,
+             __half* __restrict__ flowfeat_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __half* Wsm = reinterpret_cast<__half*>(smem_raw);
     __half* Xs = Wsm + kFlowWHalves;
@@ -79,6 +80,12 @@ k_flow_stage(const __grid_constant__ nvsf_field_config_t cfg, const __grid_const
         for (int l = 0; l < kFlLevels; ++l) {
             const float2 f = hash3_f2(P.flow, lv(cfg.fl[l]), x, y, z);
             *reinterpret_cast<uint32_t*>(xrow + 2 * l) = pack_half2(f.x, f.y);
+        }
+        if (flowfeat_out && live) {  // kept for the backward pass (input of the flow MLP)
+            const uint4* s = reinterpret_cast<const uint4*>(xrow);
+            uint4* d = reinterpret_cast<uint4*>(flowfeat_out + li * kFlowIn);
+#pragma unroll
+            for (int i = 0; i < kFlowIn / 8; ++i) d[i] = s[i];
         }
         __syncwarp();
         float acc[2][8][4];
@@ -304,7 +311,8 @@ int nvsf_launch_density_split(const nvsf_field_config_t* cfg, const void* worksp
                               const float* x, const float* rays_o, const float* rays_d,
                               const float* nears, const float* fars, const float* noise,
                               uint32_t S, size_t n, float* sigma, void* geo, void* features,
-                              float* flow, void* split_scratch, cudaStream_t stream) {
+                              float* flow, void* split_scratch, cudaStream_t stream,
+                              const DensityKeep* keep) {
     int st = ensure_attrs();
     if (st != NVSF_OK) return st;
     const FieldPtrs P = nvsf_make_field_ptrs(cfg, workspace);
@@ -317,17 +325,23 @@ int nvsf_launch_density_split(const nvsf_field_config_t* cfg, const void* worksp
                                                  ws_align(chunk * 8 * sizeof(float)));
     for (size_t begin = 0; begin < n; begin += chunk) {
         const size_t count = std::min(chunk, n - begin);
+        __half* ff = nullptr;
+        if (keep) {  // training: the intermediates of every chunk are kept for the backward pass
+            flow_buf = keep->flow + begin * 8;
+            feat_buf = keep->feats + begin * kFeat;
+            ff = keep->flowfeat + begin * kFlowIn;
+        }
         const size_t tiles = (count + kSTile - 1) / kSTile;
         const int grid_p = (int)std::min<size_t>(tiles, (size_t)sms * 2);
         if (x) {
             k_flow_stage<false><<<grid_p, kSTile, kFlowStageSmem, stream>>>(
-                *cfg, P, x, nullptr, nullptr, nullptr, nullptr, nullptr, 1, begin, count, flow_buf);
+                *cfg, P, x, nullptr, nullptr, nullptr, nullptr, nullptr, 1, begin, count, flow_buf, ff);
             k_encode_stage<false><<<(unsigned)tiles, 256, 0, stream>>>(
                 *cfg, P, x, nullptr, nullptr, nullptr, nullptr, nullptr, 1, begin, count, flow_buf,
                 feat_buf);
         } else {
             k_flow_stage<true><<<grid_p, kSTile, kFlowStageSmem, stream>>>(
-                *cfg, P, nullptr, rays_o, rays_d, nears, fars, noise, S, begin, count, flow_buf);
+                *cfg, P, nullptr, rays_o, rays_d, nears, fars, noise, S, begin, count, flow_buf, ff);
             k_encode_stage<true><<<(unsigned)tiles, 256, 0, stream>>>(
                 *cfg, P, nullptr, rays_o, rays_d, nears, fars, noise, S, begin, count, flow_buf,
                 feat_buf);

@@ -45,7 +45,8 @@ k_render_composite(const __grid_constant__ nvsf_field_config_t cfg, const __half
                    const float* __restrict__ sigma, const __half* __restrict__ geo, uint32_t N,
                    uint32_t S, float bg_color, float* __restrict__ depth_out,
                    float* __restrict__ image_out, float* __restrict__ ws_out,
-                   float* __restrict__ weights_out, float* __restrict__ z_out) {
+                   float* __restrict__ weights_out, float* __restrict__ z_out,
+                   float* __restrict__ rgbs_out /* [N*S,4] kept for the backward pass, or NULL */) {
     constexpr int NETS = LIDAR ? 2 : 1;
     constexpr int NDIR = LIDAR ? 72 : 16;
     constexpr int NCH = LIDAR ? 2 : 3;
@@ -154,7 +155,10 @@ k_render_composite(const __grid_constant__ nvsf_field_config_t cfg, const __half
             dep = fmaf(w, z, dep);
             if (weights_out && in) { weights_out[g] = w; z_out[g] = z; }
             const bool m = w > 1e-4f;  // renderer_dynamic.py:202
-            if (__ballot_sync(0xffffffffu, m) == 0) continue;
+            if (__ballot_sync(0xffffffffu, m) == 0) {
+                if (rgbs_out && in) *reinterpret_cast<float4*>(rgbs_out + g * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+                continue;
+            }
 
             // ---- heads on this 32-sample chunk ----
             {
@@ -169,6 +173,11 @@ k_render_composite(const __grid_constant__ nvsf_field_config_t cfg, const __half
             __syncwarp();
             uint32_t a[2][1][4];
             load_a_frags<1>(geo_s, kGeoLd, a, lane);
+            if (rgbs_out) {  // the staged geo rows are in registers now: reuse them to stage colours
+                __syncwarp();
+                reinterpret_cast<float4*>(geo_s)[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+                __syncwarp();
+            }
             const float wm = m ? w : 0.f;
             const float w0 = __shfl_sync(0xffffffffu, wm, gq), w1 = __shfl_sync(0xffffffffu, wm, gq + 8),
                         w2 = __shfl_sync(0xffffffffu, wm, gq + 16), w3 = __shfl_sync(0xffffffffu, wm, gq + 24);
@@ -194,26 +203,47 @@ k_render_composite(const __grid_constant__ nvsf_field_config_t cfg, const __half
                 float o[2][1][4];
                 zero_acc<1>(o);
                 warp_gemm_regA<4, 1>(a2, Wn + kHeadW3, kLdK64, o, lane);
+                // colours of rows gq, gq+8, gq+16, gq+24; columns 2tq, 2tq+1 of the output layer
+                const float s00 = sigmoidf_(o[0][0][0]), s01 = sigmoidf_(o[0][0][1]),
+                            s10 = sigmoidf_(o[0][0][2]), s11 = sigmoidf_(o[0][0][3]),
+                            s20 = sigmoidf_(o[1][0][0]), s21 = sigmoidf_(o[1][0][1]),
+                            s30 = sigmoidf_(o[1][0][2]), s31 = sigmoidf_(o[1][0][3]);
                 if (LIDAR) {
                     // h = [raydrop, intensity] (network_dynamic.py:317): slot 0 = intensity, 1 = raydrop
                     if (tq == 0) {
-                        const float s = w0 * sigmoidf_(o[0][0][0]) + w1 * sigmoidf_(o[0][0][2]) +
-                                        w2 * sigmoidf_(o[1][0][0]) + w3 * sigmoidf_(o[1][0][2]);
+                        const float s = w0 * s00 + w1 * s10 + w2 * s20 + w3 * s30;
                         if (net == 0) img[1] += s; else img[0] += s;
+                        if (rgbs_out) {
+                            const int ch = net == 0 ? 1 : 0;
+                            float* cs = reinterpret_cast<float*>(geo_s);  // [32][4] colour staging
+                            cs[gq * 4 + ch] = w0 > 0.f ? s00 : 0.f;
+                            cs[(gq + 8) * 4 + ch] = w1 > 0.f ? s10 : 0.f;
+                            cs[(gq + 16) * 4 + ch] = w2 > 0.f ? s20 : 0.f;
+                            cs[(gq + 24) * 4 + ch] = w3 > 0.f ? s30 : 0.f;
+                        }
                     }
                 } else {
                     if (tq == 0) {
-                        img[0] += w0 * sigmoidf_(o[0][0][0]) + w1 * sigmoidf_(o[0][0][2]) +
-                                  w2 * sigmoidf_(o[1][0][0]) + w3 * sigmoidf_(o[1][0][2]);
-                        img[1] += w0 * sigmoidf_(o[0][0][1]) + w1 * sigmoidf_(o[0][0][3]) +
-                                  w2 * sigmoidf_(o[1][0][1]) + w3 * sigmoidf_(o[1][0][3]);
+                        img[0] += w0 * s00 + w1 * s10 + w2 * s20 + w3 * s30;
+                        img[1] += w0 * s01 + w1 * s11 + w2 * s21 + w3 * s31;
                     } else if (tq == 1) {
-                        img[2] += w0 * sigmoidf_(o[0][0][0]) + w1 * sigmoidf_(o[0][0][2]) +
-                                  w2 * sigmoidf_(o[1][0][0]) + w3 * sigmoidf_(o[1][0][2]);
+                        img[2] += w0 * s00 + w1 * s10 + w2 * s20 + w3 * s30;
+                    }
+                    if (rgbs_out && tq < 2) {
+                        const float z1 = tq == 0 ? 1.f : 0.f;  // output column 3 is padding
+                        float2* cs = reinterpret_cast<float2*>(geo_s);  // [32][2 x float2] colour staging
+                        cs[gq * 2 + tq] = make_float2(w0 > 0.f ? s00 : 0.f, w0 > 0.f ? s01 * z1 : 0.f);
+                        cs[(gq + 8) * 2 + tq] = make_float2(w1 > 0.f ? s10 : 0.f, w1 > 0.f ? s11 * z1 : 0.f);
+                        cs[(gq + 16) * 2 + tq] = make_float2(w2 > 0.f ? s20 : 0.f, w2 > 0.f ? s21 * z1 : 0.f);
+                        cs[(gq + 24) * 2 + tq] = make_float2(w3 > 0.f ? s30 : 0.f, w3 > 0.f ? s31 * z1 : 0.f);
                     }
                 }
             }
             __syncwarp();
+            if (rgbs_out) {
+                if (in) *reinterpret_cast<float4*>(rgbs_out + g * 4) = reinterpret_cast<const float4*>(geo_s)[lane];
+                __syncwarp();
+            }
         }
         // ---- reduce over the warp and write the ray ----
 #pragma unroll
@@ -283,12 +313,26 @@ int nvsf_render_uniform_composite(const nvsf_field_config_t* cfg, const void* wo
                                   float bg_color, const void* scratch, size_t scratch_bytes,
                                   float* depth, float* image, float* weights_sum, float* weights,
                                   float* z_vals, void* stream) {
+    return nvsf_render_composite_launch(cfg, workspace, lidar, rays_d, nears, fars, noise, N, S,
+                                        bg_color, scratch, scratch_bytes, depth, image, weights_sum,
+                                        weights, z_vals, nullptr, stream);
+}
+
+}  // extern "C"
+
+int nvsf_render_composite_launch(const nvsf_field_config_t* cfg, const void* workspace,
+                                 uint32_t lidar, const float* rays_d, const float* nears,
+                                 const float* fars, const float* noise, uint32_t N, uint32_t S,
+                                 float bg_color, const void* scratch, size_t scratch_bytes,
+                                 float* depth, float* image, float* weights_sum, float* weights,
+                                 float* z_vals, void* rgbs, void* stream) {
     if (N == 0) return NVSF_OK;
     if (!field_cfg_ok(cfg) || !workspace || !rays_d || !nears || !fars || !scratch || !depth ||
         !image || !weights_sum || S == 0)
         return NVSF_E_INVALID;
     if ((weights == nullptr) != (z_vals == nullptr)) return NVSF_E_INVALID;
-    if (scratch_bytes < nvsf_render_uniform_scratch_bytes(N, S)) return NVSF_E_WORKSPACE;
+    if (scratch_bytes < ws_align((size_t)N * S * sizeof(float)) + (size_t)N * S * kGeo * sizeof(__half))
+        return NVSF_E_WORKSPACE;
     int st = ensure_attrs();
     if (st != NVSF_OK) return st;
     cudaStream_t s = (cudaStream_t)stream;
@@ -304,14 +348,16 @@ int nvsf_render_uniform_composite(const nvsf_field_config_t* cfg, const void* wo
     if (lidar) {
         k_render_composite<true><<<blocks, kRWarps * 32, render_smem<true>(), s>>>(
             *cfg, P.mlp, rays_d, nears, fars, noise, sigma, geo, N, S, bg_color, depth, image,
-            weights_sum, weights, z_vals);
+            weights_sum, weights, z_vals, reinterpret_cast<float*>(rgbs));
     } else {
         k_render_composite<false><<<blocks, kRWarps * 32, render_smem<false>(), s>>>(
             *cfg, P.mlp, rays_d, nears, fars, noise, sigma, geo, N, S, bg_color, depth, image,
-            weights_sum, weights, z_vals);
+            weights_sum, weights, z_vals, reinterpret_cast<float*>(rgbs));
     }
     return nvsf_launch_status();
 }
+
+extern "C" {
 
 int nvsf_render_uniform(const nvsf_field_config_t* cfg, const void* workspace, uint32_t lidar,
                         const float* rays_o, const float* rays_d, const float* nears,

@@ -1,0 +1,1283 @@
+// nvsf_b200 — training path of the uniform-sample renderer: forward that keeps its per-sample
+// intermediates, and the backward pass down to the fp32 master parameters (sm_100a).
+//
+// Replaces what autograd does for the reference's train_step (reference nvsf/nerf/trainer.py:193-200,
+// 491-499 -> renderer_dynamic.py:109-265 -> network_dynamic.py:213-332): the backward of the
+// cumprod compositing, of the masked colour heads, of trunc_exp (activation.py:14-19), of the
+// sigma / flow MLPs (tcnn FullyFusedMLP and nn.Linear backward), of grid_sample (planes, including
+// the coordinate gradient that carries the only gradient of the flow field) and the atomicAdd
+// scatter of the tcnn hash-grid backward.  Gradient semantics follow the reference exactly: the
+// warped dynamic-HASH queries are evaluated under no_grad (network_dynamic.py:245-249, 261-265),
+// the warped PLANE queries are differentiable, a missing neighbour frame falls back to the
+// un-warped feature (:238-239), the colour mask w > 1e-4 is not differentiated.
+//
+// B200-first structure (one launch sequence per chunk of rays, all intermediates fp32 or bf16):
+//   k_composite_bwd   one warp per ray: two sweeps over the ray (total of dL/dw * w, then the
+//                     suffix form of the cumprod backward) -> dL/d(sigma logit)
+//   k_mlp_bwd<Heads>  128-row tiles, fp16 mma.sync (power-of-two gradient scale per launch): re-computes the hidden activations from the
+//                     kept geo features + direction encoding, back-propagates w * dL/dimage *
+//                     c(1-c), accumulates dW in registers across the tiles of a persistent CTA
+//   k_mlp_bwd<Sigma>  same kernel template on the kept 120 sigma-net inputs -> dL/dfeatures
+//   k_encode_bwd      one thread per sample: re-gathers the plane texels (product rule), scatters
+//                     the plane gradients with WARP-AGGREGATED vector reds (consecutive samples
+//                     of a ray fall into runs of equal texels: segmented shuffle reduction, one
+//                     red.v4 per run instead of one per lane), the hash gradients with red.v4 /
+//                     red.f32 into the time-collapsed gradient tables, and emits dL/dflow
+//   k_mlp_bwd<Flow>   flow MLP backward -> dL/d(flow-grid features)
+//   k_flowgrid_bwd    red.v2 scatter into the time-collapsed flow-grid gradient
+//   k_expand_*        collapsed gradient tables -> the reference parameter layouts (the transpose
+//                     of the time collapse of field.cu; linear, so exact)
+#include <algorithm>
+
+#include "mlp_bwd.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// fp16 weight images for the backward kernels (row strides of mlp_bwd.cuh)
+// ------------------------------------------------------------------------------------------------
+constexpr int kBLdK32 = 40, kBLdK96 = 104, kBLdK128 = 136;
+constexpr int kB_FlowW1 = 0;                                  // [64][40]
+constexpr int kB_FlowW2 = kB_FlowW1 + kHidden * kBLdK32;      // [64][72]
+constexpr int kB_FlowW3 = kB_FlowW2 + kHidden * kLdH;         // [16][72] rows 6..15 zero
+constexpr int kB_SigW1 = kB_FlowW3 + 16 * kLdH;               // [64][136]
+constexpr int kB_SigW2 = kB_SigW1 + kHidden * kBLdK128;       // [16][72]
+constexpr int kB_Head = kB_SigW2 + 16 * kLdH;                 // 2 slots
+constexpr int kB_HeadW1 = 0;                                  // [64][104] (camera: [64][40])
+constexpr int kB_HeadW2 = kB_HeadW1 + kHidden * kBLdK96;      // [64][72]
+constexpr int kB_HeadW3 = kB_HeadW2 + kHidden * kLdH;         // [16][72]
+constexpr int kB_HeadHalves = kB_HeadW3 + 16 * kLdH;
+constexpr int kB_Total = kB_Head + 2 * kB_HeadHalves;
+
+__global__ void k_pack_matrix_bf16(const float* __restrict__ src, int src_ld, int rows, int cols,
+                                   bf16* __restrict__ dst, int dst_ld) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * cols) return;
+    const int r = i / cols, c = i - r * cols;
+    dst[r * dst_ld + c] = __float2half_rn(__ldg(src + r * src_ld + c));
+}
+
+// ------------------------------------------------------------------------------------------------
+// the generic MLP backward tile kernel
+// ------------------------------------------------------------------------------------------------
+struct MlpGrads {
+    float* w1;  // [64][LDG1]
+    float* w2;  // [64][64]   (NHID == 2)
+    float* wo;  // [OUT_ROWS][64]
+};
+
+template <class T>
+constexpr size_t mlp_bwd_smem() {
+    constexpr int ldx = T::KIN + 8;
+    size_t halves = (size_t)kHidden * ldx + (T::NHID == 2 ? (size_t)kHidden * kLdH : 0) + 16 * kLdH;
+    halves += (size_t)kBwdRows * ldx + (size_t)kBwdRows * kLdH * (2 * T::NHID) + (size_t)kBwdRows * kLdD;
+    return halves * sizeof(bf16);
+}
+
+template <class T>
+__global__ void __launch_bounds__(kBwdWarps * 32)
+k_mlp_bwd(const typename T::Args A, const bf16* __restrict__ w1g, const bf16* __restrict__ w2g,
+          const bf16* __restrict__ wog, size_t n, MlpGrads G, const float* __restrict__ scale2) {
+    constexpr int KIN = T::KIN, NHID = T::NHID, LDX = KIN + 8, KT = KIN / 16;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    bf16* W1 = reinterpret_cast<bf16*>(smem_raw);
+    bf16* W2 = W1 + kHidden * LDX;
+    bf16* Wo = W2 + (NHID == 2 ? kHidden * kLdH : 0);
+    bf16* Xs = Wo + 16 * kLdH;
+    bf16* H1s = Xs + kBwdRows * LDX;
+    bf16* H2s = H1s + kBwdRows * kLdH;                        // NHID == 2 only
+    bf16* dH1s = H1s + kBwdRows * kLdH * NHID;
+    bf16* dH2s = dH1s + kBwdRows * kLdH;                      // NHID == 2 only
+    bf16* Ds = dH1s + kBwdRows * kLdH * NHID;
+    bf16* HLs = NHID == 2 ? H2s : H1s;                        // last hidden activations
+    bf16* dHLs = NHID == 2 ? dH2s : dH1s;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gq = lane >> 2, tq = lane & 3;
+    const float scale = __ldg(scale2), inv_scale = __ldg(scale2 + 1);  // power of two and its inverse
+    block_copy16(W1, w1g, kHidden * LDX * 2 / 16, tid, kBwdWarps * 32);
+    if (NHID == 2) block_copy16(W2, w2g, kHidden * kLdH * 2 / 16, tid, kBwdWarps * 32);
+    block_copy16(Wo, wog, 16 * kLdH * 2 / 16, tid, kBwdWarps * 32);
+    // hidden tiles start finite (skipped warps leave their rows untouched; 0 * NaN would poison dW)
+    for (int i = tid; i < kBwdRows * kLdH * NHID * 2 / 8; i += kBwdWarps * 32)
+        reinterpret_cast<uint4*>(H1s)[i] = make_uint4(0, 0, 0, 0);
+
+    // weight-gradient accumulators, live across all tiles of this CTA
+    const int mt = warp & 3, nh = warp >> 2;
+    float accW1[KT][4], accW2[4][4], accWo[1][4];
+    zero1<KT>(accW1);
+    zero1<4>(accW2);
+    zero1<1>(accWo);
+    __syncthreads();
+
+    const size_t n_tiles = (n + kBwdRows - 1) / kBwdRows;
+    for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const size_t row0 = tile * kBwdRows;
+        T::fill(A, row0, n, Xs, Ds, tid, scale);
+        __syncthreads();
+
+        // ---- per-warp chain on rows [16 warp, 16 warp + 16) ----
+        const int r0 = warp * 16;
+        bool active;
+        {
+            const uint4* d = reinterpret_cast<const uint4*>(Ds + (r0 + (lane >> 1)) * kLdD + (lane & 1) * 8);
+            const uint4 v = *d;
+            // -0.0 (0x8000) also counts as zero
+            active = __any_sync(0xffffffffu, ((v.x | v.y | v.z | v.w) & 0x7fff7fffu) != 0);
+        }
+        if (!active) {
+            for (int i = lane; i < 16 * kLdH / 8; i += 32) {
+                reinterpret_cast<uint4*>(dH1s + r0 * kLdH)[i] = make_uint4(0, 0, 0, 0);
+                if (NHID == 2) reinterpret_cast<uint4*>(dH2s + r0 * kLdH)[i] = make_uint4(0, 0, 0, 0);
+            }
+            T::sink_zero(A, row0 + r0, n, lane);
+        } else {
+            float h1[8][4], h2[8][4], d1[8][4];
+            {
+                uint32_t ax[KT][4];
+                load_a16<KT>(Xs + r0 * LDX, LDX, ax, lane);
+                zero1<8>(h1);
+                gemm_nt<KT, 8>(ax, W1, LDX, h1, lane);
+            }
+            store_acc64<true>(h1, H1s + r0 * kLdH, lane);
+            if (NHID == 2) {
+                uint32_t a1[4][4];
+                acc_to_a<true>(h1, a1);
+                zero1<8>(h2);
+                gemm_nt<4, 8>(a1, W2, kLdH, h2, lane);
+                store_acc64<true>(h2, H2s + r0 * kLdH, lane);
+            }
+            // dH_last = (dOut * Wo) * relu'
+            {
+                uint32_t ad[1][4];
+                load_a16<1>(Ds + r0 * kLdD, kLdD, ad, lane);
+                zero1<8>(d1);
+                gemm_nn<1, 8>(ad, Wo, kLdH, 0, d1, lane);
+            }
+            if (NHID == 2) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) d1[j][i] = h2[j][i] > 0.f ? d1[j][i] : 0.f;
+                store_acc64<false>(d1, dH2s + r0 * kLdH, lane);
+                uint32_t a2[4][4];
+                acc_to_a<false>(d1, a2);
+                zero1<8>(d1);
+                gemm_nn<4, 8>(a2, W2, kLdH, 0, d1, lane);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) d1[j][i] = h1[j][i] > 0.f ? d1[j][i] : 0.f;
+            store_acc64<false>(d1, dH1s + r0 * kLdH, lane);
+            // dX = dH1 * W1 on the columns the caller needs
+            uint32_t a1[4][4];
+            acc_to_a<false>(d1, a1);
+#pragma unroll
+            for (int c = 0; c < T::DX_CHUNKS; ++c) {
+                float dx[T::DX_NT][4];
+                zero1<T::DX_NT>(dx);
+                gemm_nn<4, T::DX_NT>(a1, W1, LDX, T::DX_N0 + c * T::DX_NT * 8, dx, lane);
+#pragma unroll
+                for (int j = 0; j < T::DX_NT; ++j) {
+                    const int col = T::DX_N0 + (c * T::DX_NT + j) * 8 + 2 * tq;
+                    T::sink(A, row0 + r0 + gq, n, col, dx[j][0] * inv_scale, dx[j][1] * inv_scale);
+                    T::sink(A, row0 + r0 + gq + 8, n, col, dx[j][2] * inv_scale, dx[j][3] * inv_scale);
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- weight gradients over the 128 rows of the tile ----
+        gemm_tn<KT>(dH1s, kLdH, 16 * mt, Xs, LDX, nh * (KIN / 2), accW1, lane);
+        if (NHID == 2) gemm_tn<4>(dH2s, kLdH, 16 * mt, H1s, kLdH, nh * 32, accW2, lane);
+        gemm_tn<1>(Ds, kLdD, 0, HLs, kLdH, 8 * warp, accWo, lane);
+        __syncthreads();
+    }
+    (void)dHLs;
+    flush_dw<KT>(accW1, G.w1, T::LDG1, 16 * mt, nh * (KIN / 2), kHidden, T::LDG1, inv_scale, lane);
+    if (NHID == 2) flush_dw<4>(accW2, G.w2, kHidden, 16 * mt, nh * 32, kHidden, kHidden, inv_scale, lane);
+    flush_dw<1>(accWo, G.wo, kHidden, 0, 8 * warp, T::OUT_ROWS, kHidden, inv_scale, lane);
+}
+
+// ---- sigma net: X = kept features, dOut = (d logit, d geo), dX = d features ----------------------
+struct SigmaT {
+    static constexpr int KIN = 128, NHID = 1, LDG1 = 128, OUT_ROWS = 16;
+    static constexpr int DX_N0 = 0, DX_NT = 8, DX_CHUNKS = 2;
+    struct Args {
+        const __half* feats;   // [n,128]
+        const float* dgeo16;   // [n,16]
+        float* dfeat;          // [n,128]
+    };
+    static __device__ __forceinline__ void fill(const Args& A, size_t row0, size_t n, bf16* Xs,
+                                                bf16* Ds, int tid, float scale) {
+        constexpr int LDX = KIN + 8;
+#pragma unroll 4
+        for (int i = tid; i < kBwdRows * 16; i += kBwdWarps * 32) {
+            const int r = i >> 4, c = i & 15;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (row0 + r < n) v = __ldcs(reinterpret_cast<const uint4*>(A.feats + (row0 + r) * 128) + c);
+            *reinterpret_cast<uint4*>(Xs + r * LDX + c * 8) = v;
+        }
+        for (int i = tid; i < kBwdRows * 4; i += kBwdWarps * 32) {
+            const int r = i >> 2, c = i & 3;
+            uint2 o = make_uint2(0, 0);
+            if (row0 + r < n) {
+                const float4 g = __ldg(reinterpret_cast<const float4*>(A.dgeo16 + (row0 + r) * 16) + c);
+                o.x = pack_bf2(scale * g.x, scale * g.y); o.y = pack_bf2(scale * g.z, scale * g.w);
+            }
+            *reinterpret_cast<uint2*>(Ds + r * kLdD + c * 4) = o;
+        }
+    }
+    static __device__ __forceinline__ void sink(const Args& A, size_t row, size_t n, int col, float a,
+                                                float b) {
+        if (row < n && col < 120) *reinterpret_cast<float2*>(A.dfeat + row * 128 + col) = make_float2(a, b);
+    }
+    // rows without gradient are skipped by k_encode_bwd (it tests dgeo16), nothing to write
+    static __device__ __forceinline__ void sink_zero(const Args&, size_t, size_t, int) {}
+};
+
+// ---- flow MLP: X = kept flow-grid features, dOut = d flow, dX = d flow-grid features ------------
+struct FlowT {
+    static constexpr int KIN = 32, NHID = 2, LDG1 = 32, OUT_ROWS = 6;
+    static constexpr int DX_N0 = 0, DX_NT = 4, DX_CHUNKS = 1;
+    struct Args {
+        const __half* flowfeat;  // [n,32]
+        const float* dflow;      // [n,8]  (6 used, 2 zero)
+        float* dflowfeat;        // [n,32]
+    };
+    static __device__ __forceinline__ void fill(const Args& A, size_t row0, size_t n, bf16* Xs,
+                                                bf16* Ds, int tid, float scale) {
+        constexpr int LDX = KIN + 8;
+        for (int i = tid; i < kBwdRows * 4; i += kBwdWarps * 32) {
+            const int r = i >> 2, c = i & 3;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            uint2 o = make_uint2(0, 0);
+            if (row0 + r < n) {
+                v = __ldcs(reinterpret_cast<const uint4*>(A.flowfeat + (row0 + r) * 32) + c);
+                if (c < 2) {
+                    const float4 g = __ldg(reinterpret_cast<const float4*>(A.dflow + (row0 + r) * 8) + c);
+                    o.x = pack_bf2(scale * g.x, scale * g.y); o.y = pack_bf2(scale * g.z, scale * g.w);
+                }
+            }
+            *reinterpret_cast<uint4*>(Xs + r * LDX + c * 8) = v;
+            *reinterpret_cast<uint2*>(Ds + r * kLdD + c * 4) = o;
+        }
+    }
+    static __device__ __forceinline__ void sink(const Args& A, size_t row, size_t n, int col, float a,
+                                                float b) {
+        if (row < n) *reinterpret_cast<float2*>(A.dflowfeat + row * 32 + col) = make_float2(a, b);
+    }
+    static __device__ __forceinline__ void sink_zero(const Args&, size_t, size_t, int) {}
+};
+
+// ---- colour heads: X = [direction encoding | geo features], dOut from the kept colours --------
+__device__ __forceinline__ void sh4_eval(float dx, float dy, float dz, float (&v)[16]) {
+    const float x = ((dx + 1.0f) * 0.5f) * 2.0f - 1.0f, y = ((dy + 1.0f) * 0.5f) * 2.0f - 1.0f,
+                z = ((dz + 1.0f) * 0.5f) * 2.0f - 1.0f;
+    const float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
+    v[0] = 0.28209479177387814f;
+    v[1] = -0.48860251190291987f * y;
+    v[2] = 0.48860251190291987f * z;
+    v[3] = -0.48860251190291987f * x;
+    v[4] = 1.0925484305920792f * xy;
+    v[5] = -1.0925484305920792f * yz;
+    v[6] = 0.94617469575755997f * z2 - 0.31539156525251999f;
+    v[7] = -1.0925484305920792f * xz;
+    v[8] = 0.54627421529603959f * x2 - 0.54627421529603959f * y2;
+    v[9] = 0.59004358992664352f * y * (-3.0f * x2 + y2);
+    v[10] = 2.8906114426405538f * xy * z;
+    v[11] = 0.45704579946446572f * y * (1.0f - 5.0f * z2);
+    v[12] = 0.3731763325901154f * z * (5.0f * z2 - 3.0f);
+    v[13] = 0.45704579946446572f * x * (1.0f - 5.0f * z2);
+    v[14] = 1.4453057213202769f * z * (x2 - y2);
+    v[15] = 0.59004358992664352f * x * (-x2 + 3.0f * y2);
+}
+
+template <bool LIDAR>
+struct HeadT {
+    static constexpr int KIN = LIDAR ? 96 : 32, NHID = 2, LDG1 = KIN, OUT_ROWS = 16;
+    static constexpr int NDIR = LIDAR ? 72 : 16;
+    static constexpr int DX_N0 = NDIR, DX_NT = 2, DX_CHUNKS = 1;
+    struct Args {
+        const __half* geo;      // [n,16]  col 0 = sigma logit, 1..15 = geo features
+        const float* rgbs;      // [n,4]   kept colours (0 where masked out)
+        const float* weights;   // [n]
+        const float* g_image;   // [N,NCH]
+        const float* rays_d;    // [N,3]
+        float* dgeo16;          // [n,16]  cols 1..15 written (or accumulated)
+        uint32_t S;
+        int net;                // lidar: 0 = intensity_net (image channel 1), 1 = raydrop_net (channel 0)
+        int accumulate;
+    };
+    static __device__ __forceinline__ void fill(const Args& A, size_t row0, size_t n, bf16* Xs,
+                                                bf16* Ds, int tid, float scale) {
+        constexpr int LDX = KIN + 8;
+        const int r = tid >> 1, half = tid & 1;
+        const size_t g = row0 + r;
+        bf16* xr = Xs + r * LDX;
+        if (g >= n) {
+            for (int c = half * (KIN / 2); c < (half + 1) * (KIN / 2); c += 8)
+                *reinterpret_cast<uint4*>(xr + c) = make_uint4(0, 0, 0, 0);
+            if (half == 0) {
+                *reinterpret_cast<uint4*>(Ds + r * kLdD) = make_uint4(0, 0, 0, 0);
+                *reinterpret_cast<uint4*>(Ds + r * kLdD + 8) = make_uint4(0, 0, 0, 0);
+            }
+            return;
+        }
+        const size_t ray = g / A.S;
+        const float dx = __ldg(A.rays_d + ray * 3), dy = __ldg(A.rays_d + ray * 3 + 1),
+                    dz = __ldg(A.rays_d + ray * 3 + 2);
+        // geo features: 16 halves; cols NDIR + (0..14) = geo[1..15], col NDIR+15 = 0
+        const uint4 g0 = __ldg(reinterpret_cast<const uint4*>(A.geo + g * 16));
+        const uint4 g1 = __ldg(reinterpret_cast<const uint4*>(A.geo + g * 16) + 1);
+        const __half* gh0 = reinterpret_cast<const __half*>(&g0);
+        const __half* gh1 = reinterpret_cast<const __half*>(&g1);
+        if (LIDAR) {
+            // tcnn Frequency (12 octaves) of (d+1)/2: this thread fills 36 of the 72 columns
+            for (int j = half * 36; j < half * 36 + 36; j += 2) {
+                const int dim = j / 24, oct = (j >> 1) % 12;
+                const float v = ((dim == 0 ? dx : (dim == 1 ? dy : dz)) + 1.0f) * 0.5f;
+                const float a = scalbnf(v, oct);
+                *reinterpret_cast<uint32_t*>(xr + j) = pack_bf2(sinpif(a), sinpif(a + 0.5f));
+            }
+        } else {
+            float sh[16];
+            sh4_eval(dx, dy, dz, sh);
+#pragma unroll
+            for (int j = 0; j < 8; j += 2)
+                *reinterpret_cast<uint32_t*>(xr + half * 8 + j) =
+                    pack_bf2(half ? sh[8 + j] : sh[j], half ? sh[9 + j] : sh[j + 1]);
+        }
+        if (half == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) {
+                const float a = __half2float(j + 1 < 8 ? gh0[j + 1] : gh1[j + 1 - 8]);
+                const float b = __half2float(j + 2 < 8 ? gh0[j + 2] : gh1[j + 2 - 8]);
+                *reinterpret_cast<uint32_t*>(xr + NDIR + j) = pack_bf2(a, b);
+            }
+            // output gradient: w * dL/dimage[ch] * c (1 - c) on the samples that passed the mask
+            const float w = __ldg(A.weights + g), ws = scale * w;
+            uint4 o0 = make_uint4(0, 0, 0, 0);
+            if (w > 1e-4f) {
+                const float4 cc = __ldg(reinterpret_cast<const float4*>(A.rgbs + g * 4));
+                const float2 c01 = make_float2(cc.x, cc.y), c23 = make_float2(cc.z, cc.w);
+                if (LIDAR) {
+                    const int ch = A.net == 0 ? 1 : 0;
+                    const float c = ch ? c01.y : c01.x;
+                    o0.x = pack_bf2(ws * __ldg(A.g_image + ray * 2 + ch) * c * (1.f - c), 0.f);
+                } else {
+                    const float* gi = A.g_image + ray * 3;
+                    o0.x = pack_bf2(ws * __ldg(gi) * c01.x * (1.f - c01.x),
+                                    ws * __ldg(gi + 1) * c01.y * (1.f - c01.y));
+                    o0.y = pack_bf2(ws * __ldg(gi + 2) * c23.x * (1.f - c23.x), 0.f);
+                }
+            }
+            *reinterpret_cast<uint4*>(Ds + r * kLdD) = o0;
+            *reinterpret_cast<uint4*>(Ds + r * kLdD + 8) = make_uint4(0, 0, 0, 0);
+        } else {
+            // geo[9..15] -> cols NDIR+8 .. NDIR+14, col NDIR+15 = 0; lidar: cols 88..95 = 0
+#pragma unroll
+            for (int j = 8; j < 16; j += 2) {
+                const float a = __half2float(gh1[j + 1 - 8]);
+                const float b = j + 2 < 16 ? __half2float(gh1[j + 2 - 8]) : 0.f;
+                *reinterpret_cast<uint32_t*>(xr + NDIR + j) = pack_bf2(a, b);
+            }
+            if (LIDAR) *reinterpret_cast<uint4*>(xr + 88) = make_uint4(0, 0, 0, 0);
+        }
+    }
+    static __device__ __forceinline__ void sink(const Args& A, size_t row, size_t n, int col, float a,
+                                                float b) {
+        if (row >= n) return;
+        const int k = col - NDIR + 1;  // geo index of `a`; `b` is k + 1
+        float* p = A.dgeo16 + row * 16;
+        if (A.accumulate) {
+            p[k] += a;
+            if (k + 1 < 16) p[k + 1] += b;
+        } else {
+            p[k] = a;
+            if (k + 1 < 16) p[k + 1] = b;
+        }
+    }
+    static __device__ __forceinline__ void sink_zero(const Args& A, size_t row0, size_t n, int lane) {
+        if (A.accumulate) return;
+        // 16 rows x 15 floats (cols 1..15)
+        for (int i = lane; i < 16 * 15; i += 32) {
+            const int r = i / 15, c = i - r * 15 + 1;
+            if (row0 + r < n) A.dgeo16[(row0 + r) * 16 + c] = 0.f;
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// power-of-two gradient scale of one k_mlp_bwd launch: scale * max|dOut| ~ 16 (fp16 keeps 12 binades
+// of head-room for the growth through the layers and 14 + 10 below for the small rows)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_absmax(const float* __restrict__ x, size_t n, float mul, unsigned* __restrict__ out) {
+    float m = 0.f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        m = fmaxf(m, fabsf(__ldg(x + i)));
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+    m *= mul;
+    if ((threadIdx.x & 31) == 0 && m > 0.f && m < INFINITY) atomicMax(out, __float_as_uint(m));
+}
+__global__ void k_make_scale(const unsigned* __restrict__ mx, float* __restrict__ scale2) {
+    const float m = __uint_as_float(*mx);
+    float s = 1.0f;
+    if (m > 0.f) {
+        int e = 0;
+        frexpf(m, &e);                 // m = f * 2^e, f in [0.5, 1)
+        e = min(max(5 - e, -100), 100);  // scale * m in [8, 16)
+        s = scalbnf(1.0f, e);
+    }
+    scale2[0] = s;
+    scale2[1] = 1.0f / s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// compositing backward: one warp per ray
+// ------------------------------------------------------------------------------------------------
+template <bool LIDAR>
+__global__ void __launch_bounds__(128)
+k_composite_bwd(const __grid_constant__ nvsf_field_config_t cfg, const float* __restrict__ nears,
+                const float* __restrict__ fars, const float* __restrict__ noise,
+                const float* __restrict__ sigma, const __half* __restrict__ geo,
+                const float* __restrict__ rgbs, const float* __restrict__ weights, uint32_t N,
+                uint32_t S, float bg_color, const float* __restrict__ g_depth,
+                const float* __restrict__ g_image, const float* __restrict__ g_wsum,
+                const float* __restrict__ g_weights, float* __restrict__ dgeo16) {
+    constexpr int NCH = LIDAR ? 2 : 3;
+    const int lane = threadIdx.x & 31;
+    const uint32_t r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= N) return;
+    const float near = __ldg(nears + r), far = __ldg(fars + r);
+    const float kexp = (cfg.active_sensor ? 2.0f : 1.0f) * cfg.density_scale;
+    const float gd = g_depth ? __ldg(g_depth + r) : 0.f;
+    float gi[NCH], gsum = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        gi[c] = g_image ? __ldg(g_image + (size_t)r * NCH + c) : 0.f;
+        gsum += gi[c];
+    }
+    // camera: image += (1 - weights_sum) * bg  (renderer_dynamic.py:236-237)
+    const float gws = (g_wsum ? __ldg(g_wsum + r) : 0.f) - (LIDAR ? 0.f : bg_color * gsum);
+
+    auto dl_dw = [&](size_t g, float z) {
+        const float4 cc = __ldg(reinterpret_cast<const float4*>(rgbs + g * 4));
+        float q = gi[0] * cc.x + gi[1] * cc.y;
+        if (!LIDAR) q += gi[2] * cc.z;
+        float v = gws + gd * z + q;
+        if (g_weights) v += __ldg(g_weights + g);
+        return v;
+    };
+
+    // sweep 1: total = sum_i dL/dw_i * w_i
+    float tot = 0.f;
+    for (uint32_t i = lane; i < S; i += 32) {
+        const size_t g = (size_t)r * S + i;
+        const float z = uniform_z(near, far, i, S, noise, g);
+        tot = fmaf(dl_dw(g, z), __ldg(weights + g), tot);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, d);
+
+    // sweep 2: transmittance scan as in the forward; dL/dalpha_i = dL/dw_i T_i - (sum_{j>i} dL/dw_j w_j) / v_i
+    float carry = 1.0f, prefix = 0.f;
+    for (uint32_t c0 = 0; c0 < S; c0 += 32) {
+        const uint32_t i = c0 + lane;
+        const bool in = i < S;
+        const size_t g = (size_t)r * S + (in ? i : S - 1);
+        const float z = uniform_z(near, far, in ? i : S - 1, S, noise, g);
+        float delta;
+        if (i + 1 < S) delta = uniform_z(near, far, i + 1, S, noise, g + 1) - z;
+        else delta = (far - near) / (float)S;
+        const float sg = in ? __ldg(sigma + g) : 0.f;
+        const float e = in ? expf(((-kexp * delta)) * sg) : 1.f;   // 1 - alpha
+        const float v = e + 1e-15f;
+        float incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const float o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl *= o;
+        }
+        float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) excl = 1.0f;
+        const float T = carry * excl;
+        carry *= __shfl_sync(0xffffffffu, incl, 31);
+        const float w = in ? __ldg(weights + g) : 0.f;
+        const float dw = in ? dl_dw(g, z) : 0.f;
+        float p = dw * w;  // inclusive prefix of dL/dw_j w_j
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const float o = __shfl_up_sync(0xffffffffu, p, d);
+            if (lane >= d) p += o;
+        }
+        const float sfx = tot - (prefix + p);
+        prefix += __shfl_sync(0xffffffffu, p, 31);
+        if (in) {
+            // d alpha / d sigma = kexp * delta * (1 - alpha)
+            const float dsig = kexp * delta * (e * dw * T - sfx * (e / v));
+            const float h0 = __half2float(geo[g * kGeo]);
+            dgeo16[g * 16] = dsig * expf(fminf(fmaxf(h0, -15.f), 15.f));  // activation.py:17-19
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// encoder backward
+// ------------------------------------------------------------------------------------------------
+struct GradTables {      // time-collapsed / channel-last gradient tables (scratch, zeroed per call)
+    float* pls;          // layout of WsLayout::pls
+    float* pld;          // [3 queries][pld_per_q]
+    float* dyn;          // [dyn_per_q]      (un-warped query only: the warped ones carry no gradient)
+    float* flow;         // float2 [fl_entries]
+    float* hs;           // fp32 [hs_entries][4]: the caller's hash_static gradient itself
+};
+
+__device__ __forceinline__ void red4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void red2(float* p, float a, float b) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void red1(float* p, float a) {
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(a) : "memory");
+}
+
+// Runs of equal keys over consecutive lanes (consecutive samples of a ray fall into the same
+// texel): `heads` has a bit for every lane that starts a run; seg_sum leaves in each head lane the
+// sum over its run.
+struct Runs {
+    unsigned heads;
+    bool head;
+    bool take[5];  // lane adds the value of lane + (1 << k): no run starts in (lane, lane + (1 << k)]
+};
+__device__ __forceinline__ Runs make_runs(uint32_t key, int lane) {
+    Runs r;
+    const uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
+    r.head = lane == 0 || prev != key;
+    r.heads = __ballot_sync(0xffffffffu, r.head);
+    const unsigned above = (r.heads >> lane) >> 1;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const int d = 1 << k;
+        r.take[k] = (lane + d < 32) && ((above & ((1u << d) - 1u)) == 0u);
+    }
+    return r;
+}
+__device__ __forceinline__ float seg_sum(float v, const Runs& r) {
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const float o = __shfl_down_sync(0xffffffffu, v, 1 << k);
+        if (r.take[k]) v += o;
+    }
+    return v;
+}
+
+// add w * g[0..7] for a run of lanes to an 8-float texel
+__device__ __forceinline__ void scatter8(float* texel, float w, const float (&g)[8], const Runs& r) {
+    float s[8];
+#pragma unroll
+    for (int f = 0; f < 8; ++f) s[f] = seg_sum(w * g[f], r);
+    if (r.head) {
+        red4(texel, s[0], s[1], s[2], s[3]);
+        red4(texel + 4, s[4], s[5], s[6], s[7]);
+    }
+}
+
+struct Bilin {
+    uint32_t x0, x1, y0, y1;
+    float wx, wy;
+};
+__device__ __forceinline__ void sample2d(const float* __restrict__ base, uint32_t R, float pa, float pb,
+                                         Bilin& b, float (&out)[8]) {
+    plane_coord(pa, R, b.x0, b.x1, b.wx);
+    plane_coord(pb, R, b.y0, b.y1, b.wy);
+    float a[8], bb[8], c[8], d[8];
+    ld8(base + ((size_t)b.y0 * R + b.x0) * 8, a);
+    ld8(base + ((size_t)b.y0 * R + b.x1) * 8, bb);
+    ld8(base + ((size_t)b.y1 * R + b.x0) * 8, c);
+    ld8(base + ((size_t)b.y1 * R + b.x1) * 8, d);
+    const float w00 = (1.f - b.wx) * (1.f - b.wy), w01 = b.wx * (1.f - b.wy),
+                w10 = (1.f - b.wx) * b.wy, w11 = b.wx * b.wy;
+#pragma unroll
+    for (int f = 0; f < 8; ++f) out[f] = w00 * a[f] + w01 * bb[f] + w10 * c[f] + w11 * d[f];
+}
+__device__ __forceinline__ void scatter2d(float* __restrict__ base, uint32_t R, const Bilin& b,
+                                          const float (&g)[8], bool live) {
+    const Runs r = make_runs(live ? b.y0 * R + b.x0 : 0xffffffffu, threadIdx.x & 31);
+    scatter8(base + ((size_t)b.y0 * R + b.x0) * 8, (1.f - b.wx) * (1.f - b.wy), g, r);
+    scatter8(base + ((size_t)b.y0 * R + b.x1) * 8, b.wx * (1.f - b.wy), g, r);
+    scatter8(base + ((size_t)b.y1 * R + b.x0) * 8, (1.f - b.wx) * b.wy, g, r);
+    scatter8(base + ((size_t)b.y1 * R + b.x1) * 8, b.wx * b.wy, g, r);
+}
+
+struct Lin {
+    uint32_t x0, x1;
+    float wx;
+    float dcoord;  // d(texel coordinate)/d(p): R-1 inside the grid, 0 where grid_sample clamps
+};
+__device__ __forceinline__ void sample1d(const float* __restrict__ base, uint32_t R, float pa, Lin& l,
+                                         float (&out)[8], float (&slope)[8]) {
+    plane_coord(pa, R, l.x0, l.x1, l.wx);
+    const float f = ((pa * 2.0f - 1.0f) + 1.0f) * 0.5f * (float)(R - 1);
+    l.dcoord = (f > 0.f && f < (float)(R - 1)) ? (float)(R - 1) : 0.f;
+    float a[8], b[8];
+    ld8(base + (size_t)l.x0 * 8, a);
+    ld8(base + (size_t)l.x1 * 8, b);
+#pragma unroll
+    for (int f2 = 0; f2 < 8; ++f2) {
+        out[f2] = (1.f - l.wx) * a[f2] + l.wx * b[f2];
+        slope[f2] = b[f2] - a[f2];
+    }
+}
+__device__ __forceinline__ void scatter1d(float* __restrict__ base, const Lin& l, const float (&g)[8],
+                                          bool live) {
+    const Runs r = make_runs(live ? l.x0 : 0xffffffffu, threadIdx.x & 31);
+    scatter8(base + (size_t)l.x0 * 8, 1.f - l.wx, g, r);
+    scatter8(base + (size_t)l.x1 * 8, l.wx, g, r);
+}
+
+template <bool FROM_RAYS>
+__global__ void __launch_bounds__(256)
+k_encode_bwd(const __grid_constant__ nvsf_field_config_t cfg, const __grid_constant__ FieldPtrs P,
+             const GradTables G, const float* __restrict__ xin, const float* __restrict__ rays_o,
+             const float* __restrict__ rays_d, const float* __restrict__ nears,
+             const float* __restrict__ fars, const float* __restrict__ noise, uint32_t S,
+             size_t begin, size_t count, const float* __restrict__ flow_in /* [.,8] global index */,
+             const float* __restrict__ dgeo16 /* chunk-local */, const float* __restrict__ dfeat,
+             float* __restrict__ dflow_out, const float* __restrict__ scale2) {
+    const size_t li = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool inb = li < count;
+    // Rows whose sigma-net output gradient is zero AS THE SIGMA BACKWARD SAW IT (scaled, fp16) have
+    // zero feature gradient; k_mlp_bwd<SigmaT> does not even write dfeat for warps of such rows.
+    bool live = false;
+    if (inb) {
+        const float sc = __ldg(scale2);
+        const float4* d = reinterpret_cast<const float4*>(dgeo16 + li * 16);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float4 v = __ldg(d + i);
+            live = live || ((pack_half2(sc * v.x, sc * v.y) | pack_half2(sc * v.z, sc * v.w)) & 0x7fff7fffu) != 0;
+        }
+    }
+    if (inb && !live) {
+        float4* o = reinterpret_cast<float4*>(dflow_out + li * 8);
+        o[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+        o[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (__ballot_sync(0xffffffffu, live) == 0) return;
+
+    float x = 0.5f, y = 0.5f, z = 0.5f;
+    float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f), f1 = f0;
+    if (inb) {
+        // same arithmetic as the forward (field_split.cu sample_position)
+        const size_t g = begin + li;
+        float px, py, pz;
+        if (FROM_RAYS) {
+            const size_t r = g / S;
+            const uint32_t k = (uint32_t)(g - r * S);
+            const float zz = uniform_z(__ldg(nears + r), __ldg(fars + r), k, S, noise, g);
+            px = __ldg(rays_o + r * 3 + 0) + __ldg(rays_d + r * 3 + 0) * zz;
+            py = __ldg(rays_o + r * 3 + 1) + __ldg(rays_d + r * 3 + 1) * zz;
+            pz = __ldg(rays_o + r * 3 + 2) + __ldg(rays_d + r * 3 + 2) * zz;
+            px = fminf(fmaxf(px, -cfg.bound), cfg.bound);
+            py = fminf(fmaxf(py, -cfg.bound), cfg.bound);
+            pz = fminf(fmaxf(pz, -cfg.bound), cfg.bound);
+        } else {
+            px = __ldg(xin + g * 3 + 0); py = __ldg(xin + g * 3 + 1); pz = __ldg(xin + g * 3 + 2);
+        }
+        const float inv2b = 1.0f / (2.0f * cfg.bound);
+        x = (px + cfg.bound) * inv2b; y = (py + cfg.bound) * inv2b; z = (pz + cfg.bound) * inv2b;
+        f0 = __ldg(reinterpret_cast<const float4*>(flow_in + g * 8));
+        f1 = __ldg(reinterpret_cast<const float4*>(flow_in + g * 8) + 1);
+    }
+    const int valid1 = P.ti->valid[1], valid2 = P.ti->valid[2];
+    float qx[3], qy[3], qz[3];
+    int qi[3];
+    qx[0] = x; qy[0] = y; qz[0] = z; qi[0] = 0;
+    qx[1] = valid1 ? x + f0.x : x; qy[1] = valid1 ? y + f0.y : y;
+    qz[1] = valid1 ? z + f0.z : z; qi[1] = valid1 ? 1 : 0;
+    qx[2] = valid2 ? x + f0.w : x; qy[2] = valid2 ? y + f1.x : y;
+    qz[2] = valid2 ? z + f1.y : z; qi[2] = valid2 ? 2 : 0;
+    const float* df = dfeat + li * 128;
+    const float lv_ = live ? 1.f : 0.f;
+
+    // (a) space planes: f = A(xy) * B(xz) * C(yz)
+#pragma unroll 1
+    for (int s = 0; s < kPlScales; ++s) {
+        const uint32_t R = cfg.pl_res[s];
+        const float* base = P.pls + P.pls_scale[s];
+        float* gbase = G.pls + P.pls_scale[s];
+        float g8[8], A[8], B[8], C[8];
+        if (live) ld8(df + 8 * s, g8);
+        else {
+#pragma unroll
+            for (int f = 0; f < 8; ++f) g8[f] = 0.f;
+        }
+        Bilin ba, bb, bc;
+        sample2d(base, R, x, y, ba, A);
+        sample2d(base + (size_t)R * R * 8, R, x, z, bb, B);
+        sample2d(base + (size_t)2 * R * R * 8, R, y, z, bc, C);
+        float d8[8];
+#pragma unroll
+        for (int f = 0; f < 8; ++f) d8[f] = g8[f] * B[f] * C[f];
+        scatter2d(gbase, R, ba, d8, live);
+#pragma unroll
+        for (int f = 0; f < 8; ++f) d8[f] = g8[f] * A[f] * C[f];
+        scatter2d(gbase + (size_t)R * R * 8, R, bb, d8, live);
+#pragma unroll
+        for (int f = 0; f < 8; ++f) d8[f] = g8[f] * A[f] * B[f];
+        scatter2d(gbase + (size_t)2 * R * R * 8, R, bc, d8, live);
+    }
+
+    // (b) time planes (collapsed rows): sum_q wq * A_q(x_q) * B_q(y_q) * C_q(z_q); the warped
+    // queries also give dL/dflow through the coordinate gradient of grid_sample
+    float dfl[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+    for (int s = 0; s < kPlScales; ++s) {
+        const uint32_t R = cfg.pl_res[s];
+        float g8[8];
+        if (live) ld8(df + 32 + 8 * s, g8);
+        else {
+#pragma unroll
+            for (int f = 0; f < 8; ++f) g8[f] = 0.f;
+        }
+#pragma unroll 1
+        for (int q = 0; q < 3; ++q) {
+            const size_t toff = (size_t)qi[q] * P.pld_per_q + P.pld_scale[s];
+            const float* base = P.pld + toff;
+            float* gbase = G.pld + toff;
+            const float wq = q == 0 ? 0.5f : 0.25f;
+            float A[8], B[8], C[8], sa[8], sb[8], sc[8];
+            Lin la, lb, lc;
+            sample1d(base, R, qx[q], la, A, sa);
+            sample1d(base + (size_t)R * 8, R, qy[q], lb, B, sb);
+            sample1d(base + (size_t)2 * R * 8, R, qz[q], lc, C, sc);
+            float d8[8], gx = 0.f, gy = 0.f, gz = 0.f;
+#pragma unroll
+            for (int f = 0; f < 8; ++f) {
+                const float gw = wq * g8[f];
+                d8[f] = gw * B[f] * C[f];
+                gx = fmaf(d8[f], sa[f], gx);
+                gy = fmaf(gw * A[f] * C[f], sb[f], gy);
+                gz = fmaf(gw * A[f] * B[f], sc[f], gz);
+            }
+            scatter1d(gbase, la, d8, live);
+#pragma unroll
+            for (int f = 0; f < 8; ++f) d8[f] = wq * g8[f] * A[f] * C[f];
+            scatter1d(gbase + (size_t)R * 8, lb, d8, live);
+#pragma unroll
+            for (int f = 0; f < 8; ++f) d8[f] = wq * g8[f] * A[f] * B[f];
+            scatter1d(gbase + (size_t)2 * R * 8, lc, d8, live);
+            if (q > 0 && qi[q] != 0) {
+                dfl[3 * (q - 1) + 0] += gx * la.dcoord;
+                dfl[3 * (q - 1) + 1] += gy * lb.dcoord;
+                dfl[3 * (q - 1) + 2] += gz * lc.dcoord;
+            }
+        }
+    }
+    if (inb && live) {
+        float4* o = reinterpret_cast<float4*>(dflow_out + li * 8);
+        o[0] = make_float4(dfl[0], dfl[1], dfl[2], dfl[3]);
+        o[1] = make_float4(dfl[4], dfl[5], 0.f, 0.f);
+    }
+    if (!live) return;  // no warp-collective operations below
+
+    // (c) static 3-D hash: tcnn grid backward, fp32 vector reds into the caller's gradient
+#pragma unroll 1
+    for (int l = 0; l < kHsLevels; ++l) {
+        const LevelArgs L = lv(cfg.hs[l]);
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(df + 64 + 4 * l));
+        uint32_t cx, cy, cz;
+        float wx, wy, wz;
+        grid_pos(L.scale, x, cx, wx);
+        grid_pos(L.scale, y, cy, wy);
+        grid_pos(L.scale, z, cz, wz);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const float w = ((c & 1) ? wx : 1.f - wx) * ((c & 2) ? wy : 1.f - wy) *
+                            ((c & 4) ? wz : 1.f - wz);
+            const uint32_t idx = L.offset + idx3(L, cx + (c & 1), cy + ((c >> 1) & 1), cz + (c >> 2));
+            red4(G.hs + (size_t)idx * 4, w * g4.x, w * g4.y, w * g4.z, w * g4.w);
+        }
+    }
+    // (d) dynamic 2-D hashes: gradient through the un-warped query only; a missing neighbour
+    // frame re-uses the un-warped feature (network_dynamic.py:238-239) -> factor 0.5 + 0.25 each
+    const float fac = lv_ * (0.5f + (valid1 ? 0.f : 0.25f) + (valid2 ? 0.f : 0.25f));
+#pragma unroll 1
+    for (int p = 0; p < 3; ++p) {
+        const float u = p == 2 ? y : x, w2 = p == 0 ? y : z;
+        float* tab = G.dyn + P.dyn_plane[p];
+#pragma unroll 1
+        for (int l = 0; l < kHdLevels; ++l) {
+            const LevelArgs L = lv(cfg.hd[p][l]);
+            const float gs = fac * __ldg(df + 96 + 8 * p + l);
+            uint32_t cu, cv;
+            float wu, wv;
+            grid_pos(L.scale, u, cu, wu);
+            grid_pos(L.scale, w2, cv, wv);
+            red1(tab + L.offset + idx2(L, cu, cv), (1.f - wu) * (1.f - wv) * gs);
+            red1(tab + L.offset + idx2(L, cu + 1, cv), wu * (1.f - wv) * gs);
+            red1(tab + L.offset + idx2(L, cu, cv + 1), (1.f - wu) * wv * gs);
+            red1(tab + L.offset + idx2(L, cu + 1, cv + 1), wu * wv * gs);
+        }
+    }
+}
+
+// flow-grid scatter: dL/d(collapsed flow grid) from dL/d(flow-grid features)
+template <bool FROM_RAYS>
+__global__ void __launch_bounds__(256)
+k_flowgrid_bwd(const __grid_constant__ nvsf_field_config_t cfg, float* __restrict__ gflow,
+               const float* __restrict__ xin, const float* __restrict__ rays_o,
+               const float* __restrict__ rays_d, const float* __restrict__ nears,
+               const float* __restrict__ fars, const float* __restrict__ noise, uint32_t S,
+               size_t begin, size_t count, const float* __restrict__ dflow,
+               const float* __restrict__ dflowfeat, const float* __restrict__ scale2) {
+    const size_t li = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= count) return;
+    {   // same zero test as k_mlp_bwd<FlowT> (scaled fp16): it leaves dflowfeat unwritten for such rows
+        const float sc = __ldg(scale2);
+        const float4 a = __ldg(reinterpret_cast<const float4*>(dflow + li * 8));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(dflow + li * 8) + 1);
+        if (((pack_half2(sc * a.x, sc * a.y) | pack_half2(sc * a.z, sc * a.w) | pack_half2(sc * b.x, sc * b.y)) &
+             0x7fff7fffu) == 0)
+            return;
+    }
+    const size_t g = begin + li;
+    float px, py, pz;
+    if (FROM_RAYS) {
+        const size_t r = g / S;
+        const uint32_t k = (uint32_t)(g - r * S);
+        const float zz = uniform_z(__ldg(nears + r), __ldg(fars + r), k, S, noise, g);
+        px = __ldg(rays_o + r * 3 + 0) + __ldg(rays_d + r * 3 + 0) * zz;
+        py = __ldg(rays_o + r * 3 + 1) + __ldg(rays_d + r * 3 + 1) * zz;
+        pz = __ldg(rays_o + r * 3 + 2) + __ldg(rays_d + r * 3 + 2) * zz;
+        px = fminf(fmaxf(px, -cfg.bound), cfg.bound);
+        py = fminf(fmaxf(py, -cfg.bound), cfg.bound);
+        pz = fminf(fmaxf(pz, -cfg.bound), cfg.bound);
+    } else {
+        px = __ldg(xin + g * 3 + 0); py = __ldg(xin + g * 3 + 1); pz = __ldg(xin + g * 3 + 2);
+    }
+    const float inv2b = 1.0f / (2.0f * cfg.bound);
+    const float x = (px + cfg.bound) * inv2b, y = (py + cfg.bound) * inv2b, z = (pz + cfg.bound) * inv2b;
+#pragma unroll 1
+    for (int l = 0; l < kFlLevels; ++l) {
+        const LevelArgs L = lv(cfg.fl[l]);
+        const float2 g2 = __ldg(reinterpret_cast<const float2*>(dflowfeat + li * 32 + 2 * l));
+        uint32_t cx, cy, cz;
+        float wx, wy, wz;
+        grid_pos(L.scale, x, cx, wx);
+        grid_pos(L.scale, y, cy, wy);
+        grid_pos(L.scale, z, cz, wz);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const float w = ((c & 1) ? wx : 1.f - wx) * ((c & 2) ? wy : 1.f - wy) *
+                            ((c & 4) ? wz : 1.f - wz);
+            const uint32_t idx = L.offset + idx3(L, cx + (c & 1), cy + ((c >> 1) & 1), cz + (c >> 2));
+            red2(gflow + (size_t)idx * 2, w * g2.x, w * g2.y);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// collapsed gradient tables -> reference parameter layouts (transpose of the packing in field.cu)
+// ------------------------------------------------------------------------------------------------
+struct PlaneDst {
+    uint32_t off[kPlScales][6];
+};
+
+// space planes: channel-last [R][R][8] -> += [8][R][R]
+__global__ void k_expand_planes_static(const float* __restrict__ g, PlaneDst dst, uint32_t res,
+                                       uint32_t scale, float* __restrict__ planes_grad) {
+    const uint32_t combo = blockIdx.y == 0 ? 0u : (blockIdx.y == 1 ? 1u : 3u);
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= res * res) return;
+    float v[8];
+    ld8(g + ((size_t)blockIdx.y * res * res + i) * 8, v);
+    float* d = planes_grad + dst.off[scale][combo];
+#pragma unroll
+    for (int f = 0; f < 8; ++f) d[(size_t)f * res * res + i] += v[f];
+}
+
+// time planes: per query [R][8] -> += rows y0 / y1 of [8][Tres][R]
+__global__ void k_expand_planes_dyn(const float* __restrict__ g, size_t per_q, PlaneDst dst,
+                                    uint32_t res, uint32_t tres, uint32_t scale,
+                                    const TimeInfo* __restrict__ ti, float* __restrict__ planes_grad) {
+    const uint32_t p = blockIdx.y;
+    const uint32_t combo = p == 0 ? 2u : (p == 1 ? 4u : 5u);
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= res) return;
+    float* d = planes_grad + dst.off[scale][combo];
+    for (int q = 0; q < 3; ++q) {   // sequential per thread: queries may share a time row
+        if (!ti->valid[q]) continue;
+        float v[8];
+        ld8(g + q * per_q + ((size_t)p * res + x) * 8, v);
+        const int y0 = ti->y0[q], y1 = ti->y1[q];
+        const float w = ti->wy[q];
+#pragma unroll
+        for (int f = 0; f < 8; ++f) {
+            d[((size_t)f * tres + y0) * res + x] += (1.0f - w) * v[f];
+            d[((size_t)f * tres + y1) * res + x] += w * v[f];
+        }
+    }
+}
+
+// dynamic hash: grad[k][e][i] += blend_k * lag[0][i] * g[e] for the two blended time slices
+__global__ void k_expand_dyn(const float* __restrict__ g, uint32_t entries,
+                             const TimeInfo* __restrict__ ti, float* __restrict__ slices_grad) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= entries) return;
+    const float v = __ldg(g + e);
+    if (v == 0.f) return;
+    const int k1 = ti->k1[0], k2 = ti->k2[0];
+    const float w = ti->wk[0];
+    const float l0 = ti->lag[0][0], l1 = ti->lag[0][1], l2 = ti->lag[0][2], l3 = ti->lag[0][3];
+    float4* t = reinterpret_cast<float4*>(slices_grad);
+    const float wa = k1 == k2 ? 1.0f : 1.0f - w;
+    float4 a = t[(size_t)k1 * entries + e];
+    a.x += wa * l0 * v; a.y += wa * l1 * v; a.z += wa * l2 * v; a.w += wa * l3 * v;
+    t[(size_t)k1 * entries + e] = a;
+    if (k1 != k2) {
+        float4 b = t[(size_t)k2 * entries + e];
+        b.x += w * l0 * v; b.y += w * l1 * v; b.z += w * l2 * v; b.w += w * l3 * v;
+        t[(size_t)k2 * entries + e] = b;
+    }
+}
+
+// flow grid: grad[e][2i+c] += lag[0][i] * g[e][c]
+__global__ void k_expand_flow(const float2* __restrict__ g, uint32_t entries,
+                              const TimeInfo* __restrict__ ti, float* __restrict__ grid_grad) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= entries) return;
+    const float2 v = __ldg(g + e);
+    if (v.x == 0.f && v.y == 0.f) return;
+    const float l0 = ti->lag[0][0], l1 = ti->lag[0][1], l2 = ti->lag[0][2], l3 = ti->lag[0][3];
+    float4* t = reinterpret_cast<float4*>(grid_grad) + 2 * (size_t)e;
+    float4 a = t[0], b = t[1];
+    a.x += l0 * v.x; a.y += l0 * v.y; a.z += l1 * v.x; a.w += l1 * v.y;
+    b.x += l2 * v.x; b.y += l2 * v.y; b.z += l3 * v.x; b.w += l3 * v.y;
+    t[0] = a; t[1] = b;
+}
+
+PlaneDst make_plane_dst(const nvsf_field_config_t* c) {
+    PlaneDst s;
+    uint32_t off = 0;
+    const int comb[6][2] = {{0, 1}, {0, 2}, {0, 3}, {1, 2}, {1, 3}, {2, 3}};
+    for (int sc = 0; sc < kPlScales; ++sc) {
+        const uint32_t r[4] = {c->pl_res[sc], c->pl_res[sc], c->pl_res[sc], c->time_resolution};
+        for (int k = 0; k < 6; ++k) {
+            s.off[sc][k] = off;
+            off += kPlaneF * r[comb[k][0]] * r[comb[k][1]];
+        }
+    }
+    return s;
+}
+
+// ---- buffers ---------------------------------------------------------------------------------------
+struct SavedLayout {   // per-sample intermediates kept by the training forward
+    size_t sigma, geo, flow, feats, flowfeat, rgbs, total;
+};
+SavedLayout make_saved(size_t n) {
+    SavedLayout L;
+    size_t off = 0;
+    L.sigma = off; off = ws_align(off + n * sizeof(float));
+    L.geo = off; off = ws_align(off + n * kGeo * sizeof(__half));   // sigma + geo: the renderer's scratch layout
+    L.flow = off; off = ws_align(off + n * 8 * sizeof(float));
+    L.feats = off; off = ws_align(off + n * kFeat * sizeof(__half));
+    L.flowfeat = off; off = ws_align(off + n * kFlowIn * sizeof(__half));
+    L.rgbs = off; off = ws_align(off + n * 4 * sizeof(float));
+    L.total = off;
+    return L;
+}
+
+constexpr size_t kBwdChunkSamples = (size_t)6 << 20;  // samples per backward chunk (whole rays)
+
+struct BwdLayout {
+    size_t scales;                     // 4 x {unsigned max bits, pad, float scale, float 1/scale}
+    size_t wimg;                       // fp16 weight images
+    size_t g_pls, g_pld, g_dyn, g_flow; // collapsed gradient tables
+    size_t tables_end;
+    size_t dgeo16, dfeat, dflow, dflowfeat;
+    size_t total;
+    uint32_t chunk_rays;
+};
+BwdLayout make_bwd(const nvsf_field_config_t* cfg, uint32_t N, uint32_t S) {
+    const WsLayout W = make_ws_layout(cfg);
+    BwdLayout L;
+    size_t off = 0;
+    L.scales = off; off = ws_align(off + 64);
+    L.wimg = off; off = ws_align(off + (size_t)kB_Total * sizeof(bf16));
+    L.g_pls = off; off = ws_align(off + W.pls_floats * sizeof(float));
+    L.g_pld = off; off = ws_align(off + 3 * W.pld_floats_per_q * sizeof(float));
+    L.g_dyn = off; off = ws_align(off + W.dyn_per_q * sizeof(float));
+    L.g_flow = off; off = ws_align(off + (size_t)cfg->fl_entries * sizeof(float2));
+    L.tables_end = off;
+    const uint32_t cr = (uint32_t)std::max<size_t>(1, kBwdChunkSamples / std::max<uint32_t>(S, 1));
+    L.chunk_rays = std::min<uint32_t>(N, cr);
+    const size_t cs = (size_t)L.chunk_rays * S;
+    L.dgeo16 = off; off = ws_align(off + cs * 16 * sizeof(float));
+    L.dfeat = off; off = ws_align(off + cs * 128 * sizeof(float));
+    L.dflow = off; off = ws_align(off + cs * 8 * sizeof(float));
+    L.dflowfeat = off; off = ws_align(off + cs * 32 * sizeof(float));
+    L.total = off;
+    return L;
+}
+
+template <class T>
+int launch_mlp_bwd(const typename T::Args& A, const bf16* w1, const bf16* w2, const bf16* wo, size_t n,
+                   MlpGrads G, const float* scale2, int sms, cudaStream_t s) {
+    static bool attr = false;
+    static int per_sm = 1;
+    constexpr size_t smem = mlp_bwd_smem<T>();
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(k_mlp_bwd<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mlp_bwd<T>, kBwdWarps * 32, smem);
+        if (per_sm < 1) per_sm = 1;
+        attr = true;
+    }
+    const size_t tiles = (n + kBwdRows - 1) / kBwdRows;
+    const int grid = (int)std::min<size_t>(tiles, (size_t)sms * per_sm);
+    k_mlp_bwd<T><<<grid, kBwdWarps * 32, smem, s>>>(A, w1, w2, wo, n, G, scale2);
+    return NVSF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t nvsf_render_uniform_saved_bytes(uint32_t N, uint32_t S) {
+    return make_saved((size_t)N * S).total;
+}
+
+size_t nvsf_render_uniform_backward_scratch_bytes(const nvsf_field_config_t* cfg, uint32_t N,
+                                                  uint32_t S) {
+    if (!field_cfg_ok(cfg)) return 0;
+    return make_bwd(cfg, N, S).total;
+}
+
+void nvsf_render_uniform_debug_layout(const nvsf_field_config_t* cfg, uint32_t N, uint32_t S,
+                                      size_t* out) {
+    const SavedLayout SL = make_saved((size_t)N * S);
+    const BwdLayout BL = make_bwd(cfg, N, S);
+    const size_t v[12] = {SL.sigma, SL.geo, SL.flow, SL.feats, SL.flowfeat, SL.rgbs, BL.dgeo16, BL.dfeat,
+                          BL.dflow, BL.dflowfeat, (size_t)BL.chunk_rays, BL.total};
+    for (int i = 0; i < 12; ++i) out[i] = v[i];
+}
+
+int nvsf_render_uniform_train_forward(const nvsf_field_config_t* cfg, const void* workspace,
+                                      uint32_t lidar, const float* rays_o, const float* rays_d,
+                                      const float* nears, const float* fars, const float* noise,
+                                      uint32_t N, uint32_t S, float bg_color, void* saved,
+                                      size_t saved_bytes, float* depth, float* image,
+                                      float* weights_sum, float* weights, float* z_vals,
+                                      void* stream) {
+    if (N == 0) return NVSF_OK;
+    if (!field_cfg_ok(cfg) || !workspace || !rays_o || !rays_d || !nears || !fars || !saved ||
+        !depth || !image || !weights_sum || !weights || !z_vals || S == 0)
+        return NVSF_E_INVALID;
+    const size_t n = (size_t)N * S;
+    const SavedLayout L = make_saved(n);
+    if (saved_bytes < L.total) return NVSF_E_WORKSPACE;
+    unsigned char* sv = reinterpret_cast<unsigned char*>(saved);
+    DensityKeep keep;
+    keep.flow = reinterpret_cast<float*>(sv + L.flow);
+    keep.feats = reinterpret_cast<__half*>(sv + L.feats);
+    keep.flowfeat = reinterpret_cast<__half*>(sv + L.flowfeat);
+    int st = nvsf_launch_density_split(cfg, workspace, nullptr, rays_o, rays_d, nears, fars, noise, S,
+                                       n, reinterpret_cast<float*>(sv + L.sigma), sv + L.geo, nullptr,
+                                       nullptr, nullptr, (cudaStream_t)stream, &keep);
+    if (st != NVSF_OK) return st;
+    return nvsf_render_composite_launch(cfg, workspace, lidar, rays_d, nears, fars, noise, N, S,
+                                        bg_color, sv, L.flow, depth, image, weights_sum, weights,
+                                        z_vals, sv + L.rgbs, stream);
+}
+
+int nvsf_render_uniform_backward(const nvsf_field_config_t* cfg, const void* workspace,
+                                 const nvsf_field_params_t* params, uint32_t lidar,
+                                 const float* rays_o, const float* rays_d, const float* nears,
+                                 const float* fars, const float* noise, uint32_t N, uint32_t S,
+                                 float bg_color, const void* saved, size_t saved_bytes,
+                                 const float* weights, const float* g_depth, const float* g_image,
+                                 const float* g_weights_sum, const float* g_weights,
+                                 const nvsf_field_grads_t* grads, void* scratch,
+                                 size_t scratch_bytes, void* stream) {
+    if (N == 0) return NVSF_OK;
+    if (!field_cfg_ok(cfg) || !workspace || !params || !rays_o || !rays_d || !nears || !fars ||
+        !saved || !weights || !grads || !scratch || S == 0)
+        return NVSF_E_INVALID;
+    if (!grads->hash_static || !grads->hash_dynamic || !grads->planes || !grads->flow_grid ||
+        !grads->flow_mlp || !grads->sigma_net || !grads->head_a || (lidar && !grads->head_b))
+        return NVSF_E_INVALID;
+    if (!params->flow_mlp || !params->sigma_net || !params->head_a || (lidar && !params->head_b))
+        return NVSF_E_INVALID;
+    const size_t n = (size_t)N * S;
+    const SavedLayout SL = make_saved(n);
+    if (saved_bytes < SL.total) return NVSF_E_WORKSPACE;
+    const BwdLayout BL = make_bwd(cfg, N, S);
+    if (scratch_bytes < BL.total) return NVSF_E_WORKSPACE;
+    cudaStream_t s = (cudaStream_t)stream;
+    const unsigned char* sv = reinterpret_cast<const unsigned char*>(saved);
+    unsigned char* sc = reinterpret_cast<unsigned char*>(scratch);
+    const FieldPtrs P = nvsf_make_field_ptrs(cfg, workspace);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+
+    // bf16 weight images
+    bf16* wimg = reinterpret_cast<bf16*>(sc + BL.wimg);
+    cudaMemsetAsync(wimg, 0, (size_t)kB_Total * sizeof(bf16), s);
+    auto pack = [&](const float* src, int src_ld, int rows, int cols, bf16* dst, int dst_ld) {
+        k_pack_matrix_bf16<<<nvsf_div_up(rows * cols, 256), 256, 0, s>>>(src, src_ld, rows, cols, dst, dst_ld);
+    };
+    const int H = kHidden;
+    pack(params->flow_mlp, kFlowIn, H, kFlowIn, wimg + kB_FlowW1, kBLdK32);
+    pack(params->flow_mlp + H * kFlowIn, H, H, H, wimg + kB_FlowW2, kLdH);
+    pack(params->flow_mlp + H * kFlowIn + H * H, H, 6, H, wimg + kB_FlowW3, kLdH);
+    pack(params->sigma_net, kFeat, H, kFeat, wimg + kB_SigW1, kBLdK128);
+    pack(params->sigma_net + H * kFeat, H, kGeo, H, wimg + kB_SigW2, kLdH);
+    const int kin = lidar ? 96 : 32, n_out = lidar ? 1 : 3;
+    const float* heads[2] = {params->head_a, lidar ? params->head_b : nullptr};
+    float* head_grads[2] = {grads->head_a, lidar ? grads->head_b : nullptr};
+    for (int h = 0; h < 2; ++h) {
+        if (!heads[h]) continue;
+        bf16* hm = wimg + kB_Head + h * kB_HeadHalves;
+        pack(heads[h], kin, H, kin, hm + kB_HeadW1, kin + 8);
+        pack(heads[h] + H * kin, H, H, H, hm + kB_HeadW2, kLdH);
+        pack(heads[h] + H * kin + H * H, H, n_out, H, hm + kB_HeadW3, kLdH);
+    }
+    // collapsed gradient tables
+    cudaMemsetAsync(sc + BL.g_pls, 0, BL.tables_end - BL.g_pls, s);
+    GradTables G;
+    G.pls = reinterpret_cast<float*>(sc + BL.g_pls);
+    G.pld = reinterpret_cast<float*>(sc + BL.g_pld);
+    G.dyn = reinterpret_cast<float*>(sc + BL.g_dyn);
+    G.flow = reinterpret_cast<float*>(sc + BL.g_flow);
+    G.hs = grads->hash_static;
+
+    const float* sigma = reinterpret_cast<const float*>(sv + SL.sigma);
+    const __half* geo = reinterpret_cast<const __half*>(sv + SL.geo);
+    const float* flow = reinterpret_cast<const float*>(sv + SL.flow);
+    const __half* feats = reinterpret_cast<const __half*>(sv + SL.feats);
+    const __half* flowfeat = reinterpret_cast<const __half*>(sv + SL.flowfeat);
+    const float* rgbs = reinterpret_cast<const float*>(sv + SL.rgbs);
+    float* dgeo16 = reinterpret_cast<float*>(sc + BL.dgeo16);
+    float* dfeat = reinterpret_cast<float*>(sc + BL.dfeat);
+    float* dflow = reinterpret_cast<float*>(sc + BL.dflow);
+    float* dflowfeat = reinterpret_cast<float*>(sc + BL.dflowfeat);
+    const int nch = lidar ? 2 : 3;
+
+    for (uint32_t r0 = 0; r0 < N; r0 += BL.chunk_rays) {
+        const uint32_t nr = std::min<uint32_t>(BL.chunk_rays, N - r0);
+        const size_t begin = (size_t)r0 * S, count = (size_t)nr * S;
+        const float* noise_c = noise ? noise + begin : nullptr;
+        // 1. compositing backward -> d sigma-logit
+        {
+            const unsigned blocks = nvsf_div_up(nr, 4u);
+            if (lidar)
+                k_composite_bwd<true><<<blocks, 128, 0, s>>>(
+                    *cfg, nears + r0, fars + r0, noise_c, sigma + begin, geo + begin * kGeo,
+                    rgbs + begin * 4, weights + begin, nr, S, bg_color, g_depth ? g_depth + r0 : nullptr,
+                    g_image ? g_image + (size_t)r0 * nch : nullptr,
+                    g_weights_sum ? g_weights_sum + r0 : nullptr, g_weights ? g_weights + begin : nullptr,
+                    dgeo16);
+            else
+                k_composite_bwd<false><<<blocks, 128, 0, s>>>(
+                    *cfg, nears + r0, fars + r0, noise_c, sigma + begin, geo + begin * kGeo,
+                    rgbs + begin * 4, weights + begin, nr, S, bg_color, g_depth ? g_depth + r0 : nullptr,
+                    g_image ? g_image + (size_t)r0 * nch : nullptr,
+                    g_weights_sum ? g_weights_sum + r0 : nullptr, g_weights ? g_weights + begin : nullptr,
+                    dgeo16);
+        }
+        // power-of-two scales of the three fp16 MLP backward stages of this chunk
+        unsigned char* scl = sc + BL.scales;
+        cudaMemsetAsync(scl, 0, 64, s);
+        auto make_scale = [&](int slot, const float* x, size_t cnt, float mul) {
+            unsigned* mx = reinterpret_cast<unsigned*>(scl + 16 * slot);
+            const unsigned blocks = (unsigned)std::min<size_t>(nvsf_div_up(cnt, (size_t)1024), (size_t)sms * 4);
+            k_absmax<<<blocks, 256, 0, s>>>(x, cnt, mul, mx);
+            k_make_scale<<<1, 1, 0, s>>>(mx, reinterpret_cast<float*>(mx) + 2);
+            return reinterpret_cast<const float*>(mx) + 2;
+        };
+        // 2. colour heads backward -> d geo (cols 1..15 of dgeo16), head weight gradients
+        int st = NVSF_OK;
+        if (g_image) {
+            const float* scale_h = make_scale(0, g_image + (size_t)r0 * nch, (size_t)nr * nch, 0.25f);
+            for (int h = 0; h < (lidar ? 2 : 1) && st == NVSF_OK; ++h) {
+                const bf16* hm = wimg + kB_Head + h * kB_HeadHalves;
+                MlpGrads MG;
+                MG.w1 = head_grads[h];
+                MG.w2 = head_grads[h] + H * kin;
+                MG.wo = head_grads[h] + H * kin + H * H;
+                if (lidar) {
+                    HeadT<true>::Args A{geo + begin * kGeo, rgbs + begin * 4, weights + begin,
+                                        g_image + (size_t)r0 * 2, rays_d + (size_t)r0 * 3, dgeo16, S, h, h};
+                    st = launch_mlp_bwd<HeadT<true>>(A, hm + kB_HeadW1, hm + kB_HeadW2, hm + kB_HeadW3,
+                                                     count, MG, scale_h, sms, s);
+                } else {
+                    HeadT<false>::Args A{geo + begin * kGeo, rgbs + begin * 4, weights + begin,
+                                         g_image + (size_t)r0 * 3, rays_d + (size_t)r0 * 3, dgeo16, S, 0, 0};
+                    st = launch_mlp_bwd<HeadT<false>>(A, hm + kB_HeadW1, hm + kB_HeadW2, hm + kB_HeadW3,
+                                                      count, MG, scale_h, sms, s);
+                }
+            }
+        } else {
+            cudaMemset2DAsync(dgeo16 + 1, 16 * sizeof(float), 0, 15 * sizeof(float), count, s);
+        }
+        if (st != NVSF_OK) return st;
+        // 3. sigma net backward -> d features
+        const float* scale_s = nullptr;
+        {
+            SigmaT::Args A{feats + begin * kFeat, dgeo16, dfeat};
+            MlpGrads MG{grads->sigma_net, nullptr, grads->sigma_net + H * kFeat};
+            scale_s = make_scale(1, dgeo16, count * 16, 1.0f);
+            st = launch_mlp_bwd<SigmaT>(A, wimg + kB_SigW1, nullptr, wimg + kB_SigW2, count, MG, scale_s, sms, s);
+            if (st != NVSF_OK) return st;
+        }
+        // 4. encoders backward -> table gradients, d flow
+        {
+            const unsigned blocks = (unsigned)nvsf_div_up(count, (size_t)256);
+            k_encode_bwd<true><<<blocks, 256, 0, s>>>(*cfg, P, G, nullptr, rays_o, rays_d, nears, fars,
+                                                      noise, S, begin, count, flow, dgeo16, dfeat, dflow, scale_s);
+        }
+        // 5. flow MLP backward -> d flow-grid features; 6. flow-grid scatter
+        {
+            FlowT::Args A{flowfeat + begin * kFlowIn, dflow, dflowfeat};
+            MlpGrads MG{grads->flow_mlp, grads->flow_mlp + H * kFlowIn, grads->flow_mlp + H * kFlowIn + H * H};
+            const float* scale_f = make_scale(2, dflow, count * 8, 1.0f);
+            st = launch_mlp_bwd<FlowT>(A, wimg + kB_FlowW1, wimg + kB_FlowW2, wimg + kB_FlowW3, count, MG,
+                                       scale_f, sms, s);
+            if (st != NVSF_OK) return st;
+            const unsigned blocks = (unsigned)nvsf_div_up(count, (size_t)256);
+            k_flowgrid_bwd<true><<<blocks, 256, 0, s>>>(*cfg, G.flow, nullptr, rays_o, rays_d, nears, fars,
+                                                        noise, S, begin, count, dflow, dflowfeat, scale_f);
+        }
+    }
+    // 7. collapsed tables -> parameter gradients
+    const PlaneDst dst = make_plane_dst(cfg);
+    const WsLayout W = make_ws_layout(cfg);
+    for (int scl = 0; scl < kPlScales; ++scl) {
+        const uint32_t R = cfg->pl_res[scl];
+        k_expand_planes_static<<<dim3(nvsf_div_up(R * R, 256u), 3), 256, 0, s>>>(
+            G.pls + W.pls_scale[scl], dst, R, scl, grads->planes);
+        k_expand_planes_dyn<<<dim3(nvsf_div_up(R, 128u), 3), 128, 0, s>>>(
+            G.pld + W.pld_scale[scl], W.pld_floats_per_q, dst, R, cfg->time_resolution, scl, P.ti,
+            grads->planes);
+    }
+    {
+        float* slices = grads->hash_dynamic;
+        for (int p = 0; p < 3; ++p) {
+            const uint32_t e = cfg->hd_entries[p];
+            k_expand_dyn<<<nvsf_div_up(e, 256u), 256, 0, s>>>(G.dyn + W.dyn_plane[p], e, P.ti, slices);
+            slices += (size_t)cfg->time_resolution * e * kHashF;
+        }
+    }
+    k_expand_flow<<<nvsf_div_up(cfg->fl_entries, 256u), 256, 0, s>>>(
+        reinterpret_cast<const float2*>(G.flow), cfg->fl_entries, P.ti, grads->flow_grid);
+    return nvsf_launch_status();
+}
+
+}  // extern "C"

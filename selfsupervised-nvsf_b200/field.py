@@ -106,8 +106,102 @@ def _setup_lib():
     L.nvsf_render_uniform.argtypes = [cfgp, P, ctypes.c_uint32, P, P, P, P, P, ctypes.c_uint32,
                                       ctypes.c_uint32, ctypes.c_float, P, ctypes.c_size_t, P, P, P,
                                       P, P, P]
+    L.nvsf_render_uniform_backward_scratch_bytes.argtypes = [cfgp, ctypes.c_uint32, ctypes.c_uint32]
+    L.nvsf_render_uniform_train_forward.argtypes = [cfgp, P, ctypes.c_uint32, P, P, P, P, P, ctypes.c_uint32,
+                                                    ctypes.c_uint32, ctypes.c_float, P, ctypes.c_size_t, P, P,
+                                                    P, P, P, P]
+    L.nvsf_render_uniform_backward.argtypes = [cfgp, P, prmp, ctypes.c_uint32, P, P, P, P, P, ctypes.c_uint32,
+                                               ctypes.c_uint32, ctypes.c_float, P, ctypes.c_size_t, P, P, P, P,
+                                               P, prmp, P, ctypes.c_size_t, P]
     _L = L
     return L
+
+
+PARAM_ORDER_SHARED = ("flow_grid", "flow_mlp", "sigma_net")
+
+
+def _param_names(lidar):
+    """Parameters a render of one modality depends on, in nvsf_field_params_t order."""
+    m = "lidar" if lidar else "camera"
+    return ([f"hash_static_{m}", f"hash_dynamic_{m}", f"planes_{m}"] + list(PARAM_ORDER_SHARED)
+            + (["intensity_net", "raydrop_net"] if lidar else ["color_net"]))
+
+
+class _RenderUniformTrain(torch.autograd.Function):
+    """NeRFRenderer.run with autograd (what train_step differentiates, trainer.py:193-200,491-499):
+    forward keeps the per-sample intermediates, backward calls nvsf_render_uniform_backward and
+    returns the gradients of the fp32 master parameters in their own layouts.
+
+    If a parameter already owns a contiguous `.grad` and `model.fused_grad_accumulation` is set,
+    the kernels accumulate straight into it (no temporary, no extra add pass) and autograd
+    receives None for that input."""
+
+    @staticmethod
+    def forward(ctx, model, lidar, o, d, nears, fars, noise, S, bg, *params):
+        L = _setup_lib()
+        dev = o.device
+        N = o.shape[0]
+        nch = 2 if lidar else 3
+        ws = model._ws[lidar]
+        depth = torch.empty(N, dtype=torch.float32, device=dev)
+        image = torch.empty(N, nch, dtype=torch.float32, device=dev)
+        wsum = torch.empty(N, dtype=torch.float32, device=dev)
+        weights = torch.empty(N, S, dtype=torch.float32, device=dev)
+        z_vals = torch.empty(N, S, dtype=torch.float32, device=dev)
+        nbytes = L.nvsf_render_uniform_saved_bytes(N, S)
+        saved = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        check(L.nvsf_render_uniform_train_forward(ctypes.byref(model._cfg), ptr(ws), int(lidar), ptr(o), ptr(d),
+                                                  ptr(nears), ptr(fars), ptr(noise), N, S, bg, ptr(saved),
+                                                  saved.numel(), ptr(depth), ptr(image), ptr(wsum), ptr(weights),
+                                                  ptr(z_vals), stream_ptr()), "render_uniform_train_forward")
+        ctx.model, ctx.lidar, ctx.S, ctx.bg = model, lidar, S, bg
+        ctx.tensors = (o, d, nears, fars, noise, saved, weights, ws)
+        ctx.time_key = model._packed[lidar]
+        ctx.mark_non_differentiable(z_vals)
+        return depth, image, wsum, weights, z_vals
+
+    @staticmethod
+    def backward(ctx, g_depth, g_image, g_wsum, g_weights, _g_z):
+        L = _setup_lib()
+        model, lidar, S = ctx.model, ctx.lidar, ctx.S
+        o, d, nears, fars, noise, saved, weights, ws = ctx.tensors
+        if model._ws.get(lidar) is not ws or model._packed.get(lidar) != ctx.time_key:
+            raise _lib.NvsfError("the packed field tables changed between forward and backward "
+                                 "(another render of the same modality ran in between)")
+        dev, N = o.device, o.shape[0]
+        names = _param_names(lidar)
+        params = [getattr(model, n) for n in names]
+        fused = bool(getattr(model, "fused_grad_accumulation", False))
+        grads, ret = [], []
+        for p in params:
+            if fused and p.grad is not None and p.grad.is_contiguous() and p.grad.dtype == torch.float32:
+                grads.append(p.grad)
+                ret.append(None)
+            else:
+                g = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                grads.append(g)
+                ret.append(g)
+        gc = FieldParamsC()
+        for field, g in zip(("hash_static", "hash_dynamic", "planes", "flow_grid", "flow_mlp", "sigma_net",
+                             "head_a", "head_b"), grads + [None]):
+            setattr(gc, field, ptr(g))
+
+        def prep(g):
+            return None if g is None else g.to(dtype=torch.float32).contiguous()
+
+        g_depth, g_image, g_wsum, g_weights = prep(g_depth), prep(g_image), prep(g_wsum), prep(g_weights)
+        pc = model._params_c(lidar)
+        sbytes = L.nvsf_render_uniform_backward_scratch_bytes(ctypes.byref(model._cfg), N, S)
+        scratch = torch.empty(sbytes, dtype=torch.uint8, device=dev)
+        check(L.nvsf_render_uniform_backward(ctypes.byref(model._cfg), ptr(ws), ctypes.byref(pc), int(lidar),
+                                             ptr(o), ptr(d), ptr(nears), ptr(fars), ptr(noise), N, S, ctx.bg,
+                                             ptr(saved), saved.numel(), ptr(weights), ptr(g_depth), ptr(g_image),
+                                             ptr(g_wsum), ptr(g_weights), ctypes.byref(gc), ptr(scratch),
+                                             scratch.numel(), stream_ptr()), "render_uniform_backward")
+        if getattr(model, "_debug_keep", False):  # tests/tools: look at the intermediates
+            model._debug = dict(saved=saved, scratch=scratch, N=N, S=S)
+        ctx.tensors = None
+        return (None,) * 9 + tuple(ret)
 
 
 class NeRFNetwork(nn.Module):
@@ -319,19 +413,24 @@ class NeRFNetwork(nn.Module):
         return feats[:, :120], f
 
     # ------------------------------------------------------------------ renderer API
-    @torch.no_grad()
     def run(self, rays_o, rays_d, time, cal_lidar_color=False, num_steps=768, upsample_steps=128,
             bg_color=None, perturb=False, noise=None, return_weights=True, **kwargs):
         """NeRFRenderer.run (renderer_dynamic.py:109-265).  `noise` [N,num_steps] optionally
-        supplies the stratified-sampling jitter that perturb=True otherwise draws with torch.rand."""
-        L = _setup_lib()
-        lidar = bool(cal_lidar_color)
-        self.out_dim = self.out_lidar_color_dim if lidar else self.out_color_dim
+        supplies the stratified-sampling jitter that perturb=True otherwise draws with torch.rand.
+        With autograd enabled and parameters that require grad the call is differentiable
+        w.r.t. the field parameters (depth, image, weights_sum, weights)."""
+        if torch.is_grad_enabled() and any(getattr(self, n).requires_grad for n in _param_names(bool(cal_lidar_color))):
+            return self._run_train(rays_o, rays_d, time, bool(cal_lidar_color), int(num_steps), bg_color, perturb,
+                                   noise)
+        with torch.no_grad():
+            return self._run_infer(rays_o, rays_d, time, cal_lidar_color, num_steps, bg_color, perturb, noise,
+                                   return_weights)
+
+    def _rays_setup(self, rays_o, rays_d, lidar, S, perturb, noise):
         dev = self.sigma_net.device
-        prefix = rays_o.shape[:-1]
         o = rays_o.detach().to(device=dev, dtype=torch.float32).contiguous().view(-1, 3)
         d = rays_d.detach().to(device=dev, dtype=torch.float32).contiguous().view(-1, 3)
-        N, S = o.shape[0], int(num_steps)
+        N = o.shape[0]
         if lidar:
             nears = torch.full((N,), self.min_near_lidar, dtype=torch.float32, device=dev)
             fars = torch.full((N,), self.lidar_max_depth, dtype=torch.float32, device=dev)
@@ -341,7 +440,33 @@ class NeRFNetwork(nn.Module):
         if noise is None and perturb:
             noise = torch.rand(N, S, dtype=torch.float32, device=dev)
         if noise is not None:
-            noise = noise.to(device=dev, dtype=torch.float32).contiguous()
+            noise = noise.detach().to(device=dev, dtype=torch.float32).contiguous()
+        return o, d, nears, fars, noise
+
+    def _run_train(self, rays_o, rays_d, time, lidar, S, bg_color, perturb, noise):
+        self.out_dim = self.out_lidar_color_dim if lidar else self.out_color_dim
+        prefix = rays_o.shape[:-1]
+        with torch.no_grad():
+            o, d, nears, fars, noise = self._rays_setup(rays_o, rays_d, lidar, S, perturb, noise)
+            self.prepare(time, lidar)
+        bg = 1.0 if bg_color is None else float(bg_color)
+        params = [getattr(self, n) for n in _param_names(lidar)]
+        depth, image, wsum, weights, z_vals = _RenderUniformTrain.apply(self, lidar, o, d, nears, fars, noise, S,
+                                                                        bg, *params)
+        sfx = "_lidar" if lidar else ""
+        return {"depth" + sfx: depth.view(*prefix), "image" + sfx: image.view(*prefix, self.out_dim),
+                "weights_sum" + sfx: wsum, "weights": weights, "z_vals": z_vals}
+
+    def _run_infer(self, rays_o, rays_d, time, cal_lidar_color, num_steps, bg_color, perturb, noise,
+                   return_weights):
+        L = _setup_lib()
+        lidar = bool(cal_lidar_color)
+        self.out_dim = self.out_lidar_color_dim if lidar else self.out_color_dim
+        dev = self.sigma_net.device
+        prefix = rays_o.shape[:-1]
+        S = int(num_steps)
+        o, d, nears, fars, noise = self._rays_setup(rays_o, rays_d, lidar, S, perturb, noise)
+        N = o.shape[0]
         ws = self.prepare(time, lidar)
         nch = self.out_dim
         depth = torch.empty(N, dtype=torch.float32, device=dev)
@@ -363,7 +488,6 @@ class NeRFNetwork(nn.Module):
             out["weights"], out["z_vals"] = weights, z_vals
         return out
 
-    @torch.no_grad()
     def render(self, rays_o, rays_d, time, cal_lidar_color=False, staged=False, max_ray_batch=4096, **kwargs):
         """NeRFRenderer.render (renderer_dynamic.py:267-326).  staged=True returns only depth and
         image like the reference; the whole frame is rendered by one launch pair per

