@@ -150,6 +150,76 @@ def run_reference(args):
     }))
 
 
+def bench_train(pkg, S, cfg_kw, dev, rank, world, rays, steps, warmup):
+    """Joint training step (BASELINE configs[2] at 4096+4096 rays, configs[4] at 32768+32768 rays per
+    GPU): per step, pinned host rays -> device, LiDAR render + loss + backward, camera render +
+    loss + backward (NeRFNetwork.render with autograd, 768 samples/ray, perturb=True), gradient
+    all-reduce over NCCL overlapped per group (dist.GradSync), Adam step (optim.FlatAdam), loss
+    read back to the host.  Returns whole-job rays/s from the max-over-ranks device time."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    torch.manual_seed(0)   # same initial replica on every rank
+    model = pkg.NeRFNetwork(device=dev, **cfg_kw).train()
+    opt = pkg.optim.FlatAdam(model, lr=1e-2)
+    lo, ld = S.lidar_rays(rays, seed=100 + rank)
+    co, cd = S.camera_rays(rays, seed=200 + rank)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    lo_h, ld_h, co_h, cd_h = pin(lo), pin(ld), pin(co), pin(cd)
+    g = torch.Generator(device=dev).manual_seed(7 + rank)
+    gt_d = torch.rand(rays, device=dev, generator=g) * 0.8
+    gt_i = torch.rand(rays, 2, device=dev, generator=g)
+    gt_c = torch.rand(rays, 3, device=dev, generator=g)
+    loss_h = torch.zeros(1).pin_memory()
+    t = torch.tensor([[0.4]], device=dev)
+
+    def step():
+        a, b = lo_h.to(dev, non_blocking=True), ld_h.to(dev, non_blocking=True)
+        c, d = co_h.to(dev, non_blocking=True), cd_h.to(dev, non_blocking=True)
+        opt.zero_grad()
+        ol = model.render(a[None], b[None], t, cal_lidar_color=True, staged=False, num_steps=NUM_STEPS, perturb=True)
+        l1 = (ol["depth_lidar"].view(-1) - gt_d).abs().mean() + ((ol["image_lidar"].view(-1, 2) - gt_i) ** 2).mean()
+        l1.backward()
+        opt.sync.reduce_group("lidar")      # overlaps the camera render
+        oc = model.render(c[None], d[None], t, cal_lidar_color=False, staged=False, num_steps=NUM_STEPS, perturb=True)
+        l2 = ((oc["image"].view(-1, 3) - gt_c) ** 2).mean()
+        l2.backward()
+        opt.sync.reduce_group("camera")
+        opt.sync.reduce_group("shared")
+        opt.sync.wait()
+        opt.step()
+        loss_h.copy_((l1 + l2).detach().view(1), non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        step()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    barrier()
+    ms = max(e0.elapsed_time(e1), 0.0)
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    tm = torch.tensor([max(ms, wall_ms)], device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    ms_max = float(tm.item())
+    grad_bytes = opt.sync.flat.numel() * 4
+    del model, opt
+    torch.cuda.empty_cache()
+    return {"value": world * 2 * rays * steps / (ms_max * 1e-3), "unit": "rays/s", "ms_per_step": ms_max / steps,
+            "rays_per_gpu": {"lidar": rays, "camera": rays}, "samples_per_ray": NUM_STEPS, "steps": steps,
+            "final_loss": float(loss_h.item()), "allreduce_bytes_per_step": grad_bytes if world > 1 else 0,
+            "includes": "h2d rays, fwd+bwd of both modalities, grad all-reduce (N>1), Adam step, table re-pack, d2h loss"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -159,6 +229,8 @@ def main():
     ap.add_argument("--ref-rays", type=int, default=512, help="rays per step of the CPU reference arm")
     ap.add_argument("--cpu-rays", type=int, default=2048, help="rays of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the train_step sub-benchmarks")
+    ap.add_argument("--train-steps", type=int, default=5)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -280,6 +352,16 @@ def main():
         dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
     e2e_value = world * N * args.steps / (float(t_max.item()) * 1e-3)
 
+    # ---- joint training step (configs[2]; configs[4] = 64 K rays per GPU when N > 1) ----
+    train = {}
+    if not args.no_train:
+        del scratch
+        torch.cuda.empty_cache()
+        train["train_step"] = bench_train(pkg, S, cfg_kw, dev, rank, world, 4096, args.train_steps, 3)
+        if world > 1:
+            train["train_step_64k_rays_per_gpu"] = bench_train(pkg, S, cfg_kw, dev, rank, world, 32768,
+                                                               max(args.train_steps // 2, 2), 2)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -310,6 +392,7 @@ def main():
                      "bytes_per_sample": DENSITY_BYTES_PER_SAMPLE, "survey_bytes_per_sample": SURVEY_BYTES_PER_SAMPLE,
                      "samples_per_launch": n_samples, "launch_ms": dens_ms},
     }
+    out.update(train)
     if want_cpu:
         torch.set_num_threads(os.cpu_count() or 1)
         orc = make_oracle(cfg_kw, params)

@@ -307,6 +307,15 @@ int nvsf_render_uniform_backward(const nvsf_field_config_t* cfg, const void* wor
                                  const nvsf_field_grads_t* grads, void* scratch,
                                  size_t scratch_bytes, void* stream);
 
+/* torch.optim.Adam step as the reference configures it (main_nvsf.py:350-352: betas (0.9, 0.99),
+ * eps 1e-15, no weight decay) over one flat fp32 segment of n parameters (16-byte aligned
+ * pointers): m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+ * with g = grad_scale * grads[i] (1/world_size and the inverse loss scale fold in here).
+ * `step` is the 1-based step count t. */
+int nvsf_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, size_t n,
+                   float lr, float beta1, float beta2, float eps, uint32_t step, float grad_scale,
+                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,12 +6,16 @@ Importable as ``nvsf_b200`` (shim at the repository root) or via
 Sub-modules
     raymarching   drop-in for reference ``nvsf.nerf.raymarching.raymarching``
     field         NeRFNetwork: density / flow / run / render of the reference model on the GPU kernels
+    dist          ray sharding + flat-buffer gradient all-reduce (one process per GPU)
+    optim         Adam over the flat parameter / gradient buffers (CUDA kernel)
     _lib          ctypes binding of the C ABI (include/nvsf_b200.h)
     build         compiles csrc/*.cu into libnvsf_b200.so with nvcc (sm_100a)
 """
 from . import _lib  # noqa: F401
 from . import raymarching  # noqa: F401
 from . import field  # noqa: F401
+from . import dist  # noqa: F401
+from . import optim  # noqa: F401
 from .field import NeRFNetwork  # noqa: F401
 
 __version__ = "0.1.0"

@@ -72,6 +72,7 @@ PROTOTYPES = {
                                                  _sz, _p, _p, _p, _p, _p, _p]),
     "nvsf_render_uniform_backward": (_int, [_p, _p, _p, _u32, _p, _p, _p, _p, _p, _u32, _u32, _f32, _p,
                                             _sz, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "nvsf_adam_step": (_int, [_p, _p, _p, _p, _sz, _f32, _f32, _f32, _f32, _u32, _f32, _p]),
 }
 
 _lib = None

@@ -472,29 +472,44 @@ k_composite_bwd(const __grid_constant__ nvsf_field_config_t cfg, const float* __
         return v;
     };
 
-    // sweep 1: total = sum_i dL/dw_i * w_i
-    float tot = 0.f;
-    for (uint32_t i = lane; i < S; i += 32) {
-        const size_t g = (size_t)r * S + i;
-        const float z = uniform_z(near, far, i, S, noise, g);
-        tot = fmaf(dl_dw(g, z), __ldg(weights + g), tot);
-    }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, d);
-
-    // sweep 2: transmittance scan as in the forward; dL/dalpha_i = dL/dw_i T_i - (sum_{j>i} dL/dw_j w_j) / v_i
-    float carry = 1.0f, prefix = 0.f;
-    for (uint32_t c0 = 0; c0 < S; c0 += 32) {
-        const uint32_t i = c0 + lane;
-        const bool in = i < S;
-        const size_t g = (size_t)r * S + (in ? i : S - 1);
-        const float z = uniform_z(near, far, in ? i : S - 1, S, noise, g);
-        float delta;
+    // sweep 1 (front to back): transmittance at the start of every 32-sample chunk
+    extern __shared__ float chunk_T[];   // [warps][ceil(S/32)]
+    const uint32_t n_chunks = (S + 31) / 32;
+    float* myT = chunk_T + (threadIdx.x >> 5) * n_chunks;
+    auto one_minus_alpha = [&](uint32_t i, size_t g, float& z, float& delta) {
+        z = uniform_z(near, far, i, S, noise, g);
         if (i + 1 < S) delta = uniform_z(near, far, i + 1, S, noise, g + 1) - z;
         else delta = (far - near) / (float)S;
-        const float sg = in ? __ldg(sigma + g) : 0.f;
-        const float e = in ? expf(((-kexp * delta)) * sg) : 1.f;   // 1 - alpha
-        const float v = e + 1e-15f;
+        return expf((-kexp * delta) * __ldg(sigma + g));
+    };
+    {
+        float carry = 1.0f;
+        for (uint32_t c = 0; c < n_chunks; ++c) {
+            const uint32_t i = c * 32 + lane;
+            float v = 1.0f;
+            if (i < S) {
+                float z, delta;
+                // exactly the forward's factor: alpha is rounded to fp32 first (renderer_dynamic.py:185-191)
+                v = (1.0f - (1.0f - one_minus_alpha(i, (size_t)r * S + i, z, delta))) + 1e-15f;
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) v *= __shfl_xor_sync(0xffffffffu, v, d);
+            if (lane == 0) myT[c] = carry;
+            carry *= v;
+        }
+    }
+    __syncwarp();
+    // sweep 2 (back to front): dL/dalpha_i = dL/dw_i T_i - (sum_{j>i} dL/dw_j w_j) / v_i.  The suffix
+    // sum is accumulated from the far end, so samples behind a saturated ray get EXACTLY zero
+    // (they are skipped by every later stage of the backward).
+    float suffix = 0.f;
+    for (int c = (int)n_chunks - 1; c >= 0; --c) {
+        const uint32_t i = (uint32_t)c * 32 + lane;
+        const bool in = i < S;
+        const size_t g = (size_t)r * S + (in ? i : S - 1);
+        float z, delta;
+        const float e = one_minus_alpha(in ? i : S - 1, g, z, delta);   // exp(-k delta sigma)
+        const float v = in ? (1.0f - (1.0f - e)) + 1e-15f : 1.0f;       // the forward's cumprod factor
         float incl = v;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -503,21 +518,23 @@ k_composite_bwd(const __grid_constant__ nvsf_field_config_t cfg, const float* __
         }
         float excl = __shfl_up_sync(0xffffffffu, incl, 1);
         if (lane == 0) excl = 1.0f;
-        const float T = carry * excl;
-        carry *= __shfl_sync(0xffffffffu, incl, 31);
+        const float T = myT[c] * excl;
         const float w = in ? __ldg(weights + g) : 0.f;
         const float dw = in ? dl_dw(g, z) : 0.f;
-        float p = dw * w;  // inclusive prefix of dL/dw_j w_j
+        float sfx = dw * w;  // inclusive suffix of dL/dw_j w_j inside the chunk
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            const float o = __shfl_up_sync(0xffffffffu, p, d);
-            if (lane >= d) p += o;
+            const float o = __shfl_down_sync(0xffffffffu, sfx, d);
+            if (lane + d < 32) sfx += o;
         }
-        const float sfx = tot - (prefix + p);
-        prefix += __shfl_sync(0xffffffffu, p, 31);
+        const float chunk_sum = __shfl_sync(0xffffffffu, sfx, 0);
+        float after = __shfl_down_sync(0xffffffffu, sfx, 1);
+        if (lane == 31) after = 0.f;
+        after += suffix;   // sum over j > i
+        suffix += chunk_sum;
         if (in) {
-            // d alpha / d sigma = kexp * delta * (1 - alpha)
-            const float dsig = kexp * delta * (e * dw * T - sfx * (e / v));
+            // d alpha / d sigma = kexp * delta * exp(-k delta sigma)
+            const float dsig = kexp * delta * e * (dw * T - after / v);
             const float h0 = __half2float(geo[g * kGeo]);
             dgeo16[g * 16] = dsig * expf(fminf(fmaxf(h0, -15.f), 15.f));  // activation.py:17-19
         }
@@ -1119,6 +1136,7 @@ int nvsf_render_uniform_backward(const nvsf_field_config_t* cfg, const void* wor
     if (saved_bytes < SL.total) return NVSF_E_WORKSPACE;
     const BwdLayout BL = make_bwd(cfg, N, S);
     if (scratch_bytes < BL.total) return NVSF_E_WORKSPACE;
+    if (S > 96 * 1024) return NVSF_E_INVALID;  // per-warp chunk table of k_composite_bwd (48 KB of smem)
     cudaStream_t s = (cudaStream_t)stream;
     const unsigned char* sv = reinterpret_cast<const unsigned char*>(saved);
     unsigned char* sc = reinterpret_cast<unsigned char*>(scratch);
@@ -1177,15 +1195,16 @@ int nvsf_render_uniform_backward(const nvsf_field_config_t* cfg, const void* wor
         // 1. compositing backward -> d sigma-logit
         {
             const unsigned blocks = nvsf_div_up(nr, 4u);
+            const size_t cb_smem = (size_t)4 * ((S + 31) / 32) * sizeof(float);
             if (lidar)
-                k_composite_bwd<true><<<blocks, 128, 0, s>>>(
+                k_composite_bwd<true><<<blocks, 128, cb_smem, s>>>(
                     *cfg, nears + r0, fars + r0, noise_c, sigma + begin, geo + begin * kGeo,
                     rgbs + begin * 4, weights + begin, nr, S, bg_color, g_depth ? g_depth + r0 : nullptr,
                     g_image ? g_image + (size_t)r0 * nch : nullptr,
                     g_weights_sum ? g_weights_sum + r0 : nullptr, g_weights ? g_weights + begin : nullptr,
                     dgeo16);
             else
-                k_composite_bwd<false><<<blocks, 128, 0, s>>>(
+                k_composite_bwd<false><<<blocks, 128, cb_smem, s>>>(
                     *cfg, nears + r0, fars + r0, noise_c, sigma + begin, geo + begin * kGeo,
                     rgbs + begin * 4, weights + begin, nr, S, bg_color, g_depth ? g_depth + r0 : nullptr,
                     g_image ? g_image + (size_t)r0 * nch : nullptr,

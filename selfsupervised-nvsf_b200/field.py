@@ -495,6 +495,10 @@ class NeRFNetwork(nn.Module):
         `max_ray_batch` is accepted for signature compatibility."""
         if not staged:
             return self.run(rays_o, rays_d, time, cal_lidar_color=cal_lidar_color, **kwargs)
+        with torch.no_grad():  # staged rendering is the evaluation path (trainer.py:658-903, under no_grad)
+            return self._render_staged(rays_o, rays_d, time, cal_lidar_color, kwargs)
+
+    def _render_staged(self, rays_o, rays_d, time, cal_lidar_color, kwargs):
         lidar = bool(cal_lidar_color)
         B, N = rays_o.shape[:2]
         chunk = int(kwargs.pop("frame_ray_batch", 0)) or N

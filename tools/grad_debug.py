@@ -76,3 +76,9 @@ orc_rgb = None
 for i in k:
     print("  dgeo row", i, "ray", i // S, "k", i % S, "err", eg[i], "|cuda|", np.linalg.norm(dgeo16[i, 1:]), "|oracle|", np.linalg.norm(dh[i, 1:]), "w", wv[i], "rgb", rg[i])
 print("rows with oracle dgeo != 0:", int((np.abs(dh[:, 1:]).sum(1) > 0).sum()), " cuda:", int((np.abs(dgeo16[:, 1:]).sum(1) > 0).sum()))
+oz = (np.abs(dh).sum(1) == 0); cz = (np.abs(dgeo16).sum(1) == 0)
+print("rows: oracle zero", int(oz.sum()), "cuda zero", int(cz.sum()), "oracle zero & cuda nonzero", int((oz & ~cz).sum()))
+for i in np.flatnonzero(oz & ~cz)[:12]:
+    print("   row", i, "ray", i // S, "k", i % S, "cuda dlogit", dgeo16[i, 0], "|dgeo|", np.abs(dgeo16[i, 1:]).max(), "w", wv[i], "sigma", r["sigma"].detach().numpy().reshape(-1)[i])
+ofz = (np.abs(df).sum(1) == 0); cfz = (np.abs(dfeat).sum(1) == 0)
+print("dfeat rows: oracle zero", int(ofz.sum()), "cuda zero", int(cfz.sum()))
