@@ -37,6 +37,10 @@ NUM_STEPS = 768
 #   outputs sigma f32 + geo f16[16]                             =   36
 DENSITY_BYTES_PER_SAMPLE = 512 + 1152 + 1024 + 1536 + 2304 + 36
 SURVEY_BYTES_PER_SAMPLE = 13312 + 48  # the reference's un-collapsed gathers
+# The dominant kernel is the gather stage k_encode_stage: everything above except the
+# flow grid (flow stage) and the outputs (sigma stage), plus its own streams: flow in (8 x f32 = 32 B)
+# and the 128 fp16 sigma-net inputs out (256 B).
+ENCODE_BYTES_PER_SAMPLE = 512 + 1152 + 1536 + 2304 + 32 + 256
 
 
 def peaks():
@@ -307,6 +311,8 @@ def main():
 
     for k in range(args.warmup):
         step(k)
+    torch.cuda.synchronize()
+    F.check(L.nvsf_set_option(b"stage_timing", 1), "set_option")   # CUDA events around every stage launch
     sampler = ClockSampler(local) if rank == 0 else None
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -319,6 +325,10 @@ def main():
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
+    stage_ms = (ctypes.c_float * 3)()
+    stage_launches = ctypes.c_uint32(0)
+    F.check(L.nvsf_stage_timing_read(stage_ms, ctypes.byref(stage_launches)), "stage_timing_read")
+    F.check(L.nvsf_set_option(b"stage_timing", 0), "set_option")
     clocks = sampler.stop() if sampler else None
     t_max = torch.tensor([ms_total], device=dev)
     if world > 1:
@@ -369,11 +379,16 @@ def main():
 
     pk, pk_kind = peaks()
     n_samples = N * Sn
-    achieved = DENSITY_BYTES_PER_SAMPLE * n_samples / (dens_ms * 1e-3) / 1e9
-    traffic = None
-    tr_path = os.path.join(ROOT, "profiles", "density_dram_bytes_per_launch.json")
-    if os.path.exists(tr_path):
-        traffic = json.load(open(tr_path)).get("dram_bytes_per_launch")
+    n_launch = max(int(stage_launches.value), 1)            # chunks of the staged evaluation, all timed steps
+    flow_ms, enc_ms, sig_ms = (float(stage_ms[i]) / args.steps for i in range(3))
+    enc_launch_ms = float(stage_ms[1]) / n_launch            # average duration of one k_encode_stage launch
+    samples_per_launch = n_samples * args.steps / n_launch
+    achieved = ENCODE_BYTES_PER_SAMPLE * samples_per_launch / (enc_launch_ms * 1e-3) / 1e9
+    traffic, limiter = None, None
+    tr_path = os.path.join(ROOT, "profiles", "encode_stage_ncu.json")
+    if os.path.exists(tr_path):   # from the committed ncu --set full capture of this command
+        tr = json.load(open(tr_path))
+        traffic, limiter = tr.get("dram_bytes_per_launch"), tr.get("limiter")
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -382,15 +397,20 @@ def main():
                                "768 uniform samples/ray, random-init NVSF field (BASELINE configs[1])",
                    "rays_per_gpu": N, "samples_per_ray": Sn, "parallelism": f"rays x{world} (one frame per GPU, no collective)",
                    "l2": "per-step working set 1.9 GB of per-sample scratch + 128 MB tables exceeds the 126 MB L2; no flush",
-                   "kernel_ms": {"field_density": dens_ms, "composite_heads": comp_ms,
+                   "kernel_ms": {"field_density": dens_ms, "flow_stage": flow_ms, "encode_stage": enc_ms,
+                                 "sigma_stage": sig_ms, "composite_heads": comp_ms,
                                  "time_collapse_and_gaps": ms_total / args.steps - dens_ms - comp_ms}},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(2 * N * 3 * 4), "d2h_bytes_per_step": int(N * 3 * 4)},
-        "gpu_launches": launches_per_step * args.steps,
-        "roofline": {"bound": "hbm", "kernel": "k_field_density", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+        "gpu_launches": (9 + 1 + 3 * n_launch // args.steps) * args.steps,
+        "roofline": {"bound": "hbm", "kernel": "k_encode_stage", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk_kind,
-                     "bytes_per_sample": DENSITY_BYTES_PER_SAMPLE, "survey_bytes_per_sample": SURVEY_BYTES_PER_SAMPLE,
-                     "samples_per_launch": n_samples, "launch_ms": dens_ms},
+                     "bytes_per_sample": ENCODE_BYTES_PER_SAMPLE, "survey_bytes_per_sample": SURVEY_BYTES_PER_SAMPLE,
+                     "samples_per_launch": samples_per_launch, "launch_ms": enc_launch_ms,
+                     "launches_per_step": n_launch / args.steps, "share_of_step": enc_ms / (ms_total / args.steps),
+                     "limiter": limiter,
+                     "note": "algorithmic bytes are table gathers; the 75 MB of tables are L2 resident, so the "
+                             "achieved figure may exceed the HBM peak while DRAM traffic stays far below it"},
     }
     out.update(train)
     if want_cpu:

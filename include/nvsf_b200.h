@@ -222,6 +222,10 @@ int nvsf_field_density(const nvsf_field_config_t* cfg, const void* workspace, co
 /* Tuning switches.  "density_mode": 1 (default) = staged density evaluation (flow stage, lean
  * gather stage at high occupancy, MLP stage; needs the scratch buffer), 0 = single fused kernel. */
 int nvsf_set_option(const char* name, int value);
+/* "stage_timing": 1 records CUDA events on the launching stream around the three kernels of every
+ * chunk of the staged density evaluation; nvsf_stage_timing_read sums them since the last read:
+ * ms3 = {flow stage, encode (gather) stage, sigma stage} in milliseconds, *launches = chunks. */
+int nvsf_stage_timing_read(float* ms3, uint32_t* launches);
 
 /* replaces NeRFRenderer.run (renderer_dynamic.py:109-265) for N rays with S uniform samples.
  * nears/fars [N]; noise [N,S] in [0,1) or NULL (perturb=False); bg_color used for camera only.

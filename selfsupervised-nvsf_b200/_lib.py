@@ -9,7 +9,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnvsf_b200.so")
+# NVSF_B200_LIB: development override (A/B builds of the same sources); default = the in-tree library
+LIB_PATH = os.environ.get("NVSF_B200_LIB") or os.path.join(_HERE, "libnvsf_b200.so")
 
 _p = ctypes.c_void_p
 _u32 = ctypes.c_uint32
@@ -58,6 +59,7 @@ PROTOTYPES = {
     "nvsf_field_density_scratch_bytes": (_sz, [_u32]),
     "nvsf_field_density": (_int, [_p, _p, _p, _u32, _p, _p, _p, _p, _p, _sz, _p]),
     "nvsf_set_option": (_int, [ctypes.c_char_p, _int]),
+    "nvsf_stage_timing_read": (_int, [_p, _p]),
     "nvsf_render_uniform_scratch_bytes": (_sz, [_u32, _u32]),
     "nvsf_render_uniform_density": (_int, [_p, _p, _p, _p, _p, _p, _p, _u32, _u32, _p, _sz, _p]),
     "nvsf_render_uniform_composite": (_int, [_p, _p, _u32, _p, _p, _p, _p, _u32, _u32, _f32, _p, _sz,

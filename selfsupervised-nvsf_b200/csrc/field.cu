@@ -605,6 +605,10 @@ int nvsf_set_option(const char* name, int value) {
         g_density_mode_value = value;
         return NVSF_OK;
     }
+    if (std::string(name) == "stage_timing") {
+        nvsf_stage_timing_enable(value);
+        return NVSF_OK;
+    }
     return NVSF_E_INVALID;
 }
 

@@ -140,6 +140,7 @@ int nvsf_launch_density_split(const nvsf_field_config_t* cfg, const void* worksp
                               float* flow, void* split_scratch, cudaStream_t stream,
                               const DensityKeep* keep = nullptr);
 int nvsf_density_mode();
+void nvsf_stage_timing_enable(int on);
 // Compositing + heads launcher (render.cu); scratch = sigma f32 [N*S] then geo f16 [N*S,16];
 // rgbs (f32 [N*S,4], may be NULL) receives the per-sample colours for the backward pass.
 int nvsf_render_composite_launch(const nvsf_field_config_t* cfg, const void* workspace,
@@ -266,15 +267,21 @@ __device__ __forceinline__ void grid_pos(float scale, float x, uint32_t& cell, f
     w = p - f;
 }
 
-// Hashed levels always have a power-of-two size (2^log2_hashmap_size); dense ones need the modulo.
+// Hashed levels always have a power-of-two size (2^log2_hashmap_size).  Dense ones wrap with
+// tcnn's `% size`; there the linear index is below res^D + res^(D-1) + .. <= 2 * size for
+// coordinates in [0, res] (x in [0,1]), so one conditional subtraction is the same modulo — and
+// keeps a 20-instruction integer division out of every unrolled corner (instruction cache).
+__device__ __forceinline__ uint32_t wrap_dense(uint32_t lin, uint32_t size) {
+    return lin >= size ? (lin - size < size ? lin - size : lin % size) : lin;
+}
 __device__ __forceinline__ uint32_t idx2(const LevelArgs& L, uint32_t cx, uint32_t cy) {
     if (L.hashed) return (cx ^ (cy * 2654435761u)) & (L.size - 1);
-    return (cx + cy * L.res) % L.size;
+    return wrap_dense(cx + cy * L.res, L.size);
 }
 __device__ __forceinline__ uint32_t idx3(const LevelArgs& L, uint32_t cx, uint32_t cy,
                                          uint32_t cz) {
     if (L.hashed) return (cx ^ (cy * 2654435761u) ^ (cz * 805459861u)) & (L.size - 1);
-    return (cx + cy * L.res + cz * L.res * L.res) % L.size;
+    return wrap_dense(cx + cy * L.res + cz * L.res * L.res, L.size);
 }
 
 // ---- per-sample encoder primitives ----------------------------------------------------------
@@ -339,6 +346,10 @@ __device__ __forceinline__ void plane1d_mul(const float* __restrict__ base, uint
         out[f] = first ? s : out[f] * s;
     }
 }
+
+// (Measured and rejected on B200: fetching the two x-corners of a cell edge with one double-width
+// load when their indices differ only in bit 0 — true for every even cx on a hashed level — cuts
+// a quarter of the L1 wavefronts but the select/branch overhead made the gather stage 18 % slower.)
 
 // one level of the 3-D fp16 static hash grid (4 features)
 __device__ __forceinline__ void hash3_f4(const uint2* __restrict__ tab, const LevelArgs& L,

@@ -12,11 +12,20 @@
 // frame is processed in chunks so the intermediates stay small.  Selected with
 // nvsf_set_option("density_mode", 1); mode 0 is the fused kernel.
 #include <algorithm>
+#include <string>
+#include <vector>
 
 #include "field_common.cuh"
 
 namespace {
 
+#ifndef NVSF_ENC_UNROLL_D
+#define NVSF_ENC_UNROLL_D 1
+#endif
+// Measured on B200 (LiDAR frame, encode stage): level pairs fully unrolled 31.1 ms, x2 29.2 ms, rolled
+// (1 pair per iteration) 28.0 ms; rolling further (single levels, rolled queries) is slower again
+// (29.3-29.7 ms): the kernel trades instruction-cache misses against loads in flight.
+constexpr int kEncUnrollD = NVSF_ENC_UNROLL_D;  // level-pair unrolling of the 2-D hash loop of k_encode_stage
 constexpr int kSTile = 256;
 constexpr int kFld = 56;      // flow-stage tile row: 32 features + 8 fp32 flow slots (+pad), halves
 constexpr int kFlowWHalves = kSigW1;  // the flow MLP part of the weight image
@@ -194,7 +203,11 @@ k_encode_stage(const __grid_constant__ nvsf_field_config_t cfg,
     }
     // (d) collapsed 2-D hashes -> [96,120), zero pad [120,128)
 #pragma unroll 1
+#ifdef NVSF_EXP_SKIP
+    for (int p = 0; p < NVSF_EXP_SKIP; ++p) {
+#else
     for (int p = 0; p < 3; ++p) {
+#endif
         float u[3], w[3];
         const float* tab[3];
 #pragma unroll
@@ -203,19 +216,24 @@ k_encode_stage(const __grid_constant__ nvsf_field_config_t cfg,
             w[q] = p == 0 ? qy[q] : qz[q];
             tab[q] = P.dyn + (size_t)qi[q] * P.dyn_per_q + P.dyn_plane[p];
         }
-        uint32_t packed[4];
-#pragma unroll
-        for (int l = 0; l < kHdLevels; l += 2) {
+        uint32_t packed[4] = {0u, 0u, 0u, 0u};
+#pragma unroll kEncUnrollD
+        for (int l2 = 0; l2 < kHdLevels / 2; ++l2) {
             float r2[2];
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                const LevelArgs L = lv(cfg.hd[p][l + j]);
+                const LevelArgs L = lv(cfg.hd[p][2 * l2 + j]);
                 const float a = hash2_f1(tab[0], L, u[0], w[0]);
                 const float b = hash2_f1(tab[1], L, u[1], w[1]);
                 const float c = hash2_f1(tab[2], L, u[2], w[2]);
                 r2[j] = 0.5f * a + 0.25f * (b + c);
             }
-            packed[l / 2] = pack_half2(r2[0], r2[1]);
+            const uint32_t pk = pack_half2(r2[0], r2[1]);
+            // rolled loop: select the destination register without dynamic indexing
+            packed[0] = l2 == 0 ? pk : packed[0];
+            packed[1] = l2 == 1 ? pk : packed[1];
+            packed[2] = l2 == 2 ? pk : packed[2];
+            packed[3] = l2 == 3 ? pk : packed[3];
         }
         *reinterpret_cast<uint4*>(row + 96 + 8 * p) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
     }
@@ -283,6 +301,24 @@ k_sigma_stage(const __half* __restrict__ mlp, const __half* __restrict__ feat, s
     }
 }
 
+// Optional per-stage timing with CUDA events on the launching stream (bench.py's roofline): four
+// events per chunk, read back (and reset) by nvsf_stage_timing_read.
+struct StageProf {
+    bool on = false;
+    std::vector<cudaEvent_t> ev;
+    size_t used = 0;
+    cudaEvent_t next(cudaStream_t s) {
+        if (used == ev.size()) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            ev.push_back(e);
+        }
+        cudaEvent_t e = ev[used++];
+        cudaEventRecord(e, s);
+        return e;
+    }
+} g_prof;
+
 bool g_attr = false;
 int ensure_attrs() {
     if (g_attr) return NVSF_OK;
@@ -333,21 +369,26 @@ int nvsf_launch_density_split(const nvsf_field_config_t* cfg, const void* worksp
         }
         const size_t tiles = (count + kSTile - 1) / kSTile;
         const int grid_p = (int)std::min<size_t>(tiles, (size_t)sms * 2);
+        if (g_prof.on) g_prof.next(stream);
         if (x) {
             k_flow_stage<false><<<grid_p, kSTile, kFlowStageSmem, stream>>>(
                 *cfg, P, x, nullptr, nullptr, nullptr, nullptr, nullptr, 1, begin, count, flow_buf, ff);
+            if (g_prof.on) g_prof.next(stream);
             k_encode_stage<false><<<(unsigned)tiles, 256, 0, stream>>>(
                 *cfg, P, x, nullptr, nullptr, nullptr, nullptr, nullptr, 1, begin, count, flow_buf,
                 feat_buf);
         } else {
             k_flow_stage<true><<<grid_p, kSTile, kFlowStageSmem, stream>>>(
                 *cfg, P, nullptr, rays_o, rays_d, nears, fars, noise, S, begin, count, flow_buf, ff);
+            if (g_prof.on) g_prof.next(stream);
             k_encode_stage<true><<<(unsigned)tiles, 256, 0, stream>>>(
                 *cfg, P, nullptr, rays_o, rays_d, nears, fars, noise, S, begin, count, flow_buf,
                 feat_buf);
         }
+        if (g_prof.on) g_prof.next(stream);
         k_sigma_stage<<<grid_p, kSTile, kSigmaStageSmem, stream>>>(
             P.mlp, feat_buf, count, sigma + begin, reinterpret_cast<__half*>(geo) + begin * kGeo);
+        if (g_prof.on) g_prof.next(stream);
         if (features)
             cudaMemcpyAsync(reinterpret_cast<__half*>(features) + begin * kFeat, feat_buf,
                             count * kFeat * sizeof(__half), cudaMemcpyDeviceToDevice, stream);
@@ -357,4 +398,28 @@ int nvsf_launch_density_split(const nvsf_field_config_t* cfg, const void* worksp
         }
     }
     return nvsf_launch_status();
+}
+
+// ---- stage timing (see StageProf) -------------------------------------------------------------------
+void nvsf_stage_timing_enable(int on) {
+    g_prof.on = on != 0;
+    g_prof.used = 0;
+}
+
+extern "C" int nvsf_stage_timing_read(float* ms3, uint32_t* launches) {
+    if (!ms3) return NVSF_E_INVALID;
+    ms3[0] = ms3[1] = ms3[2] = 0.f;
+    const size_t groups = g_prof.used / 4;
+    for (size_t g = 0; g < groups; ++g) {
+        cudaError_t e = cudaEventSynchronize(g_prof.ev[4 * g + 3]);
+        if (e != cudaSuccess) return (int)e;
+        for (int k = 0; k < 3; ++k) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, g_prof.ev[4 * g + k], g_prof.ev[4 * g + k + 1]);
+            ms3[k] += ms;
+        }
+    }
+    if (launches) *launches = (uint32_t)groups;
+    g_prof.used = 0;
+    return NVSF_OK;
 }
