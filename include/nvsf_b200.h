@@ -33,7 +33,7 @@ extern "C" {
 #define NVSF_E_WORKSPACE (-2) /* workspace too small */
 
 /* ABI version of this header; bumped on any signature change. */
-#define NVSF_B200_ABI_VERSION 7
+#define NVSF_B200_ABI_VERSION 8
 int nvsf_abi_version(void);
 /* Human-readable text for a status returned by any nvsf_* call. */
 const char* nvsf_status_string(int status);
@@ -106,6 +106,19 @@ int nvsf_march_rays_train_write(const float* rays_o, const float* rays_d, const 
                                 const float* fars, float* xyzs, float* dirs, float* deltas,
                                 const int32_t* rays, const int32_t* counter,
                                 const float* noises, uint32_t zero_tail_end, void* stream);
+
+/* Phase 2 given the workspace phase 1 (`_count`) filled for the SAME rays: phase 1 keeps (t, dt)
+ * of the first 16 samples of every ray there, so rays with <= 16 samples are emitted without a
+ * second walk through the occupancy grid and longer rays resume behind their 16th sample.
+ * workspace == NULL behaves exactly like nvsf_march_rays_train_write.  Results are bit-identical
+ * either way. */
+int nvsf_march_rays_train_write_ws(const float* rays_o, const float* rays_d, const uint8_t* grid,
+                                   float bound, float dt_gamma, uint32_t max_steps, uint32_t N,
+                                   uint32_t C, uint32_t H, uint32_t M, const float* nears,
+                                   const float* fars, float* xyzs, float* dirs, float* deltas,
+                                   const int32_t* rays, const int32_t* counter,
+                                   const float* noises, uint32_t zero_tail_end,
+                                   const void* workspace, size_t workspace_bytes, void* stream);
 
 /* replaces composite_rays_train_forward (raymarching.h:45-54, kernel raymarching.cu:578-655). */
 int nvsf_composite_rays_train_forward(const float* sigmas, const float* rgbs,

@@ -42,6 +42,11 @@ PROTOTYPES = {
         [_p, _p, _p, _f32, _f32, _u32, _u32, _u32, _u32, _u32, _p, _p, _p, _p, _p, _p, _p, _p,
          _u32, _p],
     ),
+    "nvsf_march_rays_train_write_ws": (
+        _int,
+        [_p, _p, _p, _f32, _f32, _u32, _u32, _u32, _u32, _u32, _p, _p, _p, _p, _p, _p, _p, _p,
+         _u32, _p, _sz, _p],
+    ),
     "nvsf_composite_rays_train_forward": (
         _int, [_p, _p, _p, _p, _u32, _u32, _f32, _p, _p, _p, _p]),
     "nvsf_composite_rays_train_backward": (
@@ -107,7 +112,7 @@ def lib():
     return _lib
 
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 
 def check(status, what=""):

@@ -27,17 +27,42 @@ def is_stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def _compile_one(nvcc, src, obj, verbose):
+    cmd = [nvcc, "-c"] + [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else []) + [
+        "-o", obj, src]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    return src, r
+
+
 def build(force=False, verbose=False):
+    """One nvcc -c per csrc/*.cu in parallel (objects cached under csrc/_obj, rebuilt when the
+    source or any header is newer), then one link into libnvsf_b200.so."""
     if not force and not is_stale():
         return OUT
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + sources()
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    objdir = os.path.join(CSRC, "_obj")
+    os.makedirs(objdir, exist_ok=True)
+    hdrs = glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(HERE, "..", "include", "*.h"))
+    hdr_t = max(os.path.getmtime(h) for h in hdrs)
+    jobs, objs = [], []
+    for src in sources():
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        if force or verbose or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_t):
+            jobs.append((src, obj))
+    with ThreadPoolExecutor(max_workers=max(1, min(len(jobs), os.cpu_count() or 1))) as ex:
+        for src, r in ex.map(lambda j: _compile_one(nvcc, j[0], j[1], verbose), jobs):
+            if r.returncode != 0:
+                sys.stderr.write(r.stdout + r.stderr)
+                raise RuntimeError(f"nvcc failed on {os.path.basename(src)}")
+            if verbose:
+                sys.stderr.write(r.stderr)
+    r = subprocess.run([nvcc, "-shared", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a",
+                        "-o", OUT] + objs, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
-        raise RuntimeError("nvcc failed building libnvsf_b200.so")
-    if verbose:
-        sys.stderr.write(r.stderr)
+        raise RuntimeError("nvcc failed linking libnvsf_b200.so")
     return OUT
 
 

@@ -598,11 +598,17 @@ int nvsf_field_density(const nvsf_field_config_t* cfg, const void* workspace, co
 }
 
 static int g_density_mode_value = 1;
+static int g_march_mode_value = 1;
 int nvsf_set_option(const char* name, int value) {
     if (!name) return NVSF_E_INVALID;
     if (std::string(name) == "density_mode") {
         if (value != 0 && value != 1) return NVSF_E_INVALID;
         g_density_mode_value = value;
+        return NVSF_OK;
+    }
+    if (std::string(name) == "march_mode") {
+        if (value != 0 && value != 1) return NVSF_E_INVALID;
+        g_march_mode_value = value;
         return NVSF_OK;
     }
     if (std::string(name) == "stage_timing") {
@@ -615,3 +621,4 @@ int nvsf_set_option(const char* name, int value) {
 }  // extern "C"
 
 int nvsf_density_mode() { return g_density_mode_value; }
+int nvsf_march_mode() { return g_march_mode_value; }

@@ -16,6 +16,8 @@
 
 #include "common.cuh"
 
+int nvsf_march_mode();  // field.cu: option "march_mode" (1 = warp-cooperative emission, default)
+
 namespace {
 
 constexpr int kRayBlock = 128;   // rays per CTA for per-ray kernels
@@ -357,6 +359,16 @@ __device__ __forceinline__ float first_t(const MarchParams& p, float near, float
 // ---------------------------------------------------------------------------
 // march_rays_train, phase 1: per-ray sample counts + per-CTA sums
 // ---------------------------------------------------------------------------
+// (t, dt) of the first kStash samples of every ray, [ray/32][kStash][ray%32] so that the 32
+// lanes of a warp touch one 256-byte row per sample.  Sparse rays (<= kStash samples, the common
+// case behind an occupancy grid) are then emitted by phase 2 without a second DDA walk, and
+// longer rays resume after their kStash-th sample instead of re-crossing the empty space in
+// front of the surface.
+constexpr int kStash = 16;
+__host__ __device__ __forceinline__ size_t stash_index(uint32_t n, uint32_t s) {
+    return ((size_t)(n >> 5) * kStash + s) * 32 + (n & 31u);
+}
+
 // workspace layout (uint32 words): [0]=base point counter, [1]=base ray counter,
 // [2..3] pad, [4 .. 4+nblk) CTA sums -> exclusive CTA offsets, then N counts.
 __global__ void __launch_bounds__(kRayBlock)
@@ -365,7 +377,7 @@ k_march_train_count(const float* __restrict__ rays_o, const float* __restrict__ 
                     uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
                     const float* __restrict__ nears, const float* __restrict__ fars,
                     const float* __restrict__ noises, const int32_t* __restrict__ counter,
-                    uint32_t* __restrict__ ws, uint32_t nblk) {
+                    uint32_t* __restrict__ ws, uint32_t nblk, float2* __restrict__ stash) {
     __shared__ __align__(16) float s_o[kRayBlock * 3];
     __shared__ __align__(16) float s_d[kRayBlock * 3];
     __shared__ uint32_t s_warp[kRayBlock / 32];
@@ -389,6 +401,8 @@ k_march_train_count(const float* __restrict__ rays_o, const float* __restrict__ 
             float tt;
             const Probe q = probe_at(p, r, grid, t, &tt);
             if (q.occ) {
+                // the first kStash samples are kept so that phase 2 need not walk to them again
+                if (num_steps < (uint32_t)kStash) stash[stash_index(n, num_steps)] = make_float2(t, q.dt);
                 ++num_steps;
                 t = __fadd_rn(t, q.dt);
             } else {
@@ -591,6 +605,261 @@ k_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* __restrict__ rays
         pd[0] = pd[1] = pd[2] = 0.0f;
         *pl = make_float2(0.0f, 0.0f);
         px += 3; pd += 3; ++pl;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Warp-cooperative sample emission (default path of both marchers).
+//
+// A thread-per-ray marcher stores 32 B per sample with eight 4-byte stores whose
+// 32 lanes hit 32 different rays' segments: every warp store touches 32 sectors
+// for 128 useful bytes, and the kernel runs at the L2's partial-sector write
+// rate (6 % of HBM bandwidth, as the reference's).  Here a lane still walks its
+// own ray through the occupancy grid — the DDA is inherently serial — but only
+// stages (t, dt) of up to K accepted samples in shared memory.  The warp then
+// writes each ray's K-sample run together: positions are re-evaluated from
+// (o, d, t) with the same FMA + clamp, so every bit equals the serial kernel's,
+// while global stores are contiguous 128-byte rows.
+// ---------------------------------------------------------------------------
+constexpr uint32_t kSmallMarch = 148u * 32u * 16u;  // below this, 1-warp CTAs
+constexpr int kMK = 16;           // staged samples per ray per round
+constexpr int kMS = kMK + 1;      // staging row stride (odd -> lanes of one ray hit distinct banks)
+
+struct MarchStage {
+    float t[32 * kMS];            // ray parameter of each staged sample   [lane][kMS]
+    float dt[32 * kMS];           // its step
+    float4 ray[32 * 2];           // (ox, oy, oz, dx), (dy, dz, -, -) of the lane's ray
+    uint4 meta[32];               // x = exclusive prefix sum of the staged counts (train) or the
+                                  //     staged count (inference), y = output row of the ray's
+                                  //     first staged sample, z = bits of `last_t` at round start
+    uint8_t owner[32 * kMK];      // flattened staged sample -> lane
+};
+
+struct LaneMarch {
+    float t, far, last_t;
+    uint32_t step, limit;
+    bool active;
+};
+
+// Emits staged sample s of lane j's ray to output row `row`: one lane per sample, neighbouring
+// lanes write neighbouring rows (streaming stores: the outputs are not read again by this
+// kernel and must not evict the occupancy bitfield from L1).  Same operations as the serial
+// kernels (reference raymarching.cu:498-507), so every bit is identical.
+__device__ __forceinline__ void emit_sample(const MarchStage& st, uint32_t j, uint32_t s,
+                                            size_t row, float last_t, float bound,
+                                            float* __restrict__ xyzs, float* __restrict__ dirs,
+                                            float* __restrict__ deltas) {
+    const float4 a = st.ray[2 * j];
+    const float4 b = st.ray[2 * j + 1];
+    const float t = st.t[j * kMS + s], dt = st.dt[j * kMS + s];
+    const float prev = s > 0 ? __fadd_rn(st.t[j * kMS + s - 1], st.dt[j * kMS + s - 1]) : last_t;
+    float* px = xyzs + row * 3;
+    float* pd = dirs + row * 3;
+    __stcs(px + 0, fminf(bound, fmaxf(-bound, __fmaf_rn(a.w, t, a.x))));
+    __stcs(px + 1, fminf(bound, fmaxf(-bound, __fmaf_rn(b.x, t, a.y))));
+    __stcs(px + 2, fminf(bound, fmaxf(-bound, __fmaf_rn(b.y, t, a.z))));
+    __stcs(pd + 0, a.w);
+    __stcs(pd + 1, b.x);
+    __stcs(pd + 2, b.y);
+    __stcs(reinterpret_cast<float2*>(deltas) + row,
+           make_float2(dt, __fsub_rn(__fadd_rn(t, dt), prev)));
+}
+
+__device__ __forceinline__ void zero_sample(size_t row, float* __restrict__ xyzs,
+                                            float* __restrict__ dirs,
+                                            float* __restrict__ deltas) {
+    float* px = xyzs + row * 3;
+    float* pd = dirs + row * 3;
+    __stcs(px + 0, 0.0f); __stcs(px + 1, 0.0f); __stcs(px + 2, 0.0f);
+    __stcs(pd + 0, 0.0f); __stcs(pd + 1, 0.0f); __stcs(pd + 2, 0.0f);
+    __stcs(reinterpret_cast<float2*>(deltas) + row, make_float2(0.0f, 0.0f));
+}
+
+// One round of the per-lane DDA.  The warp iterates in lockstep (exactly how SIMT executes the
+// serial per-ray loop) and the round ends as soon as ANY lane has staged kMK samples or every ray
+// is finished — lanes in the middle of a long empty stretch simply continue in the next round,
+// so the total number of DDA iterations equals the serial kernel's.  Must be called by all 32
+// lanes.  Returns the number of samples this lane staged.
+__device__ __forceinline__ uint32_t march_round(const MarchParams& p, const RayGeom& r,
+                                                const uint8_t* __restrict__ grid, MarchStage& st,
+                                                int lane, LaneMarch& m) {
+    uint32_t cnt = 0;
+    while (true) {
+        if (m.active) {
+            float tt;
+            const Probe q = probe_at(p, r, grid, m.t, &tt);
+            if (q.occ) {
+                st.t[lane * kMS + cnt] = m.t;
+                st.dt[lane * kMS + cnt] = q.dt;
+                m.t = __fadd_rn(m.t, q.dt);
+                m.last_t = m.t;
+                ++cnt;
+                ++m.step;
+            } else {
+                m.t = skip_to(p, m.t, tt);
+            }
+            m.active = m.t < m.far && m.step < m.limit;
+        }
+        if (__any_sync(0xffffffffu, cnt >= (uint32_t)kMK) || !__any_sync(0xffffffffu, m.active))
+            break;
+    }
+    return cnt;
+}
+
+// Flattened emission of everything staged in this round: lane-per-sample, `owner` maps the
+// flattened sample index to the staging lane, meta[j] = (first flattened index, first output row,
+// last_t at round start) of lane j.  Must be called by all 32 lanes.
+__device__ __forceinline__ void emit_round(MarchStage& st, int lane, uint32_t cnt, uint32_t row0,
+                                           float last_t0, float bound, float* __restrict__ xyzs,
+                                           float* __restrict__ dirs, float* __restrict__ deltas) {
+    const uint32_t inc = warp_inclusive_scan(cnt, lane);
+    const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+    st.meta[lane] = make_uint4(inc - cnt, row0, __float_as_uint(last_t0), 0u);
+    for (uint32_t s = 0; s < cnt; ++s) st.owner[inc - cnt + s] = (uint8_t)lane;
+    __syncwarp();
+    for (uint32_t q = lane; q < total; q += 32) {
+        const uint32_t j = st.owner[q];
+        const uint4 mj = st.meta[j];
+        const uint32_t s = q - mj.x;
+        emit_sample(st, j, s, (size_t)mj.y + s, __uint_as_float(mj.z), bound, xyzs, dirs, deltas);
+    }
+    __syncwarp();
+}
+
+// march_rays_train, phase 2, warp-cooperative (reference raymarching.cu:463-533).
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+k_march_train_write_coop(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                         const uint8_t* __restrict__ grid, float bound, float dt_gamma,
+                         uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
+                         const float* __restrict__ nears, const float* __restrict__ fars,
+                         float* __restrict__ xyzs, float* __restrict__ dirs,
+                         float* __restrict__ deltas, const int32_t* __restrict__ rays,
+                         const int32_t* __restrict__ counter, const float* __restrict__ noises,
+                         uint32_t zero_tail_end, const float2* __restrict__ stash) {
+    __shared__ MarchStage s_stage[BLOCK / 32];
+    const uint32_t i = blockIdx.x * BLOCK + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    MarchStage& st = s_stage[threadIdx.x >> 5];
+    if (zero_tail_end > 0) {
+        const uint32_t z1 = min(M, zero_tail_end);
+        const uint32_t z0 = min((uint32_t)counter[0], z1);
+        zero_rows(xyzs, dirs, deltas, z0, z1, i, gridDim.x * BLOCK);
+    }
+    const MarchParams p = make_march_params(bound, dt_gamma, max_steps, C, H);
+    uint32_t offset = 0, n = 0;
+    LaneMarch m = {0.0f, 0.0f, 0.0f, 0u, 0u, false};
+    float ox = 0.f, oy = 0.f, oz = 0.f, dx = 1.f, dy = 1.f, dz = 1.f;
+    if (i < N) {
+        n = (uint32_t)rays[(size_t)i * 3];
+        offset = (uint32_t)rays[(size_t)i * 3 + 1];
+        m.limit = n < N ? (uint32_t)rays[(size_t)i * 3 + 2] : 0u;   // rows nobody wrote: skip
+        if (m.limit > 0 && offset + m.limit > M) {
+            // dropped ray (raymarching.cu:457).  Offsets are monotone, so only the first
+            // dropped ray starts inside the buffer; it clears what would stay unwritten.
+            if (zero_tail_end > 0 && offset < M)
+                zero_rows(xyzs, dirs, deltas, offset, min(M, zero_tail_end), 0, 1);
+            m.limit = 0;
+        }
+        if (m.limit > 0) {
+            const float* o = rays_o + (size_t)n * 3;
+            const float* d = rays_d + (size_t)n * 3;
+            ox = __ldg(o); oy = __ldg(o + 1); oz = __ldg(o + 2);
+            dx = __ldg(d); dy = __ldg(d + 1); dz = __ldg(d + 2);
+            m.far = __ldg(fars + n);
+            m.t = first_t(p, __ldg(nears + n), __ldg(noises + n));
+            m.last_t = m.t;
+            m.active = m.t < m.far;
+        }
+    }
+    st.ray[2 * lane] = make_float4(ox, oy, oz, dx);
+    st.ray[2 * lane + 1] = make_float4(dy, dz, 0.0f, 0.0f);
+    const RayGeom r = make_ray(ox, oy, oz, dx, dy, dz);
+    if (stash != nullptr) {
+        // round 0: the samples phase 1 kept; the walk resumes behind the last of them
+        static_assert(kStash <= kMK, "stash must fit one staging round");
+        const uint32_t c0 = min(m.limit, (uint32_t)kStash);
+        const float last_t0 = m.last_t;
+        for (uint32_t s = 0; s < c0; ++s) {
+            const float2 v = __ldcs(stash + stash_index(n, s));
+            st.t[lane * kMS + s] = v.x;
+            st.dt[lane * kMS + s] = v.y;
+            m.t = __fadd_rn(v.x, v.y);
+        }
+        if (c0 > 0) {
+            m.last_t = m.t;
+            m.step = c0;
+            m.active = m.t < m.far && m.step < m.limit;
+        }
+        emit_round(st, lane, c0, offset, last_t0, bound, xyzs, dirs, deltas);
+    }
+    while (__any_sync(0xffffffffu, m.active)) {
+        const uint32_t row0 = offset + m.step;
+        const float last_t0 = m.last_t;
+        const uint32_t cnt = march_round(p, r, grid, st, lane, m);
+        emit_round(st, lane, cnt, row0, last_t0, bound, xyzs, dirs, deltas);
+    }
+}
+
+// march_rays (inference), warp-cooperative (reference kernel raymarching.cu:809-928).  The 32
+// rays of a warp own the contiguous rows [n0*n_step, (n0+32)*n_step); every slot is written
+// (zeros where a ray produced no sample, so the caller need not pre-zero), kMK slots per ray
+// per round.
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+k_march_rays_coop(uint32_t n_alive, uint32_t n_step, const int32_t* __restrict__ rays_alive,
+                  const float* __restrict__ rays_t, const float* __restrict__ rays_o,
+                  const float* __restrict__ rays_d, float bound, float dt_gamma,
+                  uint32_t max_steps, uint32_t C, uint32_t H, const uint8_t* __restrict__ grid,
+                  const float* __restrict__ nears, const float* __restrict__ fars,
+                  float* __restrict__ xyzs, float* __restrict__ dirs, float* __restrict__ deltas,
+                  const float* __restrict__ noises, uint32_t M_padded) {
+    __shared__ MarchStage s_stage[BLOCK / 32];
+    const uint32_t n = blockIdx.x * BLOCK + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    MarchStage& st = s_stage[threadIdx.x >> 5];
+    {
+        const uint32_t used = n_alive * n_step;
+        if (M_padded > used)
+            zero_rows(xyzs, dirs, deltas, used, M_padded, n, gridDim.x * BLOCK);
+    }
+    const uint32_t n0 = n - lane;            // first ray of this warp
+    if (n0 >= n_alive) return;               // warp-uniform
+    const uint32_t nrays = min(32u, n_alive - n0);
+    const MarchParams p = make_march_params(bound, dt_gamma, max_steps, C, H);
+    LaneMarch m = {0.0f, 0.0f, 0.0f, 0u, n_step, false};
+    float ox = 0.f, oy = 0.f, oz = 0.f, dx = 1.f, dy = 1.f, dz = 1.f;
+    if (n < n_alive) {
+        const int32_t index = rays_alive[n];
+        if (index >= 0) {
+            const float* o = rays_o + (size_t)index * 3;
+            const float* d = rays_d + (size_t)index * 3;
+            ox = __ldg(o); oy = __ldg(o + 1); oz = __ldg(o + 2);
+            dx = __ldg(d); dy = __ldg(d + 1); dz = __ldg(d + 2);
+            m.far = __ldg(fars + index);
+            m.t = __ldg(rays_t + index);
+            m.t = __fmaf_rn(__ldg(noises + n), clamp_dt(p, m.t), m.t);
+            m.last_t = m.t;
+            m.active = m.t < m.far;
+        }
+    }
+    st.ray[2 * lane] = make_float4(ox, oy, oz, dx);
+    st.ray[2 * lane + 1] = make_float4(dy, dz, 0.0f, 0.0f);
+    const RayGeom r = make_ray(ox, oy, oz, dx, dy, dz);
+    const uint32_t base_row = n * n_step;    // rows [n*n_step, (n+1)*n_step) belong to this ray
+    while (__any_sync(0xffffffffu, m.active)) {
+        const uint32_t row0 = base_row + m.step;
+        const float last_t0 = m.last_t;
+        const uint32_t cnt = march_round(p, r, grid, st, lane, m);
+        emit_round(st, lane, cnt, row0, last_t0, bound, xyzs, dirs, deltas);
+    }
+    // unused slots read as "terminated" (delta == 0): the warp's rows are one contiguous block
+    st.meta[lane] = make_uint4(m.step, 0u, 0u, 0u);
+    __syncwarp();
+    const uint32_t slots = nrays * n_step;
+    for (uint32_t q = lane; q < slots; q += 32) {
+        const uint32_t j = q / n_step, s = q - j * n_step;
+        if (s >= st.meta[j].x) zero_sample((size_t)n0 * n_step + q, xyzs, dirs, deltas);
     }
 }
 
@@ -963,9 +1232,14 @@ int nvsf_packbits(const float* grid, uint32_t N, float density_thresh, uint8_t* 
     return nvsf_launch_status();
 }
 
-size_t nvsf_march_rays_train_workspace_bytes(uint32_t N) {
+static size_t march_stash_offset(uint32_t N) {   // bytes, 16-byte aligned
     const size_t nblk = nvsf_div_up((size_t)N, (size_t)kRayBlock);
-    return (4 + nblk + (size_t)N) * sizeof(uint32_t);
+    return ((4 + nblk + (size_t)N) * sizeof(uint32_t) + 15) & ~(size_t)15;
+}
+
+size_t nvsf_march_rays_train_workspace_bytes(uint32_t N) {
+    return march_stash_offset(N) +
+           nvsf_div_up((size_t)N, (size_t)32) * 32 * kStash * sizeof(float2);
 }
 
 int nvsf_march_rays_train_count(const float* rays_o, const float* rays_d, const uint8_t* grid,
@@ -982,11 +1256,48 @@ int nvsf_march_rays_train_count(const float* rays_o, const float* rays_d, const 
     cudaStream_t s = (cudaStream_t)stream;
     const uint32_t nblk = nvsf_div_up(N, (uint32_t)kRayBlock);
     uint32_t* ws = reinterpret_cast<uint32_t*>(workspace);
+    float2* stash = reinterpret_cast<float2*>(reinterpret_cast<char*>(workspace) +
+                                              march_stash_offset(N));
     k_march_train_count<<<nblk, kRayBlock, 0, s>>>(rays_o, rays_d, grid, bound, dt_gamma,
                                                    max_steps, N, C, H, nears, fars, noises,
-                                                   counter, ws, nblk);
+                                                   counter, ws, nblk, stash);
     k_march_train_scan<<<1, 1024, 0, s>>>(ws, nblk, N, counter);
     k_march_train_rows<<<nblk, kRayBlock, 0, s>>>(ws, nblk, N, rays);
+    return nvsf_launch_status();
+}
+
+int nvsf_march_rays_train_write_ws(const float* rays_o, const float* rays_d, const uint8_t* grid,
+                                   float bound, float dt_gamma, uint32_t max_steps, uint32_t N,
+                                   uint32_t C, uint32_t H, uint32_t M, const float* nears,
+                                   const float* fars, float* xyzs, float* dirs, float* deltas,
+                                   const int32_t* rays, const int32_t* counter,
+                                   const float* noises, uint32_t zero_tail_end,
+                                   const void* workspace, size_t workspace_bytes, void* stream) {
+    if (N == 0) return NVSF_OK;
+    if (!rays_o || !rays_d || !grid || !nears || !fars || !rays || !counter || !noises)
+        return NVSF_E_INVALID;
+    if (M > 0 && (!xyzs || !dirs || !deltas)) return NVSF_E_INVALID;
+    if (!march_cfg_ok(C, H, max_steps)) return NVSF_E_INVALID;
+    if (workspace && workspace_bytes < nvsf_march_rays_train_workspace_bytes(N))
+        return NVSF_E_WORKSPACE;
+    const float2* stash =
+        workspace ? reinterpret_cast<const float2*>(reinterpret_cast<const char*>(workspace) +
+                                                    march_stash_offset(N))
+                  : nullptr;
+    const uint32_t nblk = nvsf_div_up(N, (uint32_t)kRayBlock);
+    // few rays: one warp per CTA so that every SM gets work (the walk is latency bound)
+    if (nvsf_march_mode() && N <= kSmallMarch)
+        k_march_train_write_coop<32><<<nvsf_div_up(N, 32u), 32, 0, (cudaStream_t)stream>>>(
+            rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears, fars, xyzs, dirs,
+            deltas, rays, counter, noises, zero_tail_end, stash);
+    else if (nvsf_march_mode())
+        k_march_train_write_coop<kRayBlock><<<nblk, kRayBlock, 0, (cudaStream_t)stream>>>(
+            rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears, fars, xyzs, dirs,
+            deltas, rays, counter, noises, zero_tail_end, stash);
+    else
+        k_march_train_write<<<nblk, kRayBlock, 0, (cudaStream_t)stream>>>(
+            rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears, fars, xyzs, dirs,
+            deltas, rays, counter, noises, zero_tail_end);
     return nvsf_launch_status();
 }
 
@@ -996,16 +1307,9 @@ int nvsf_march_rays_train_write(const float* rays_o, const float* rays_d, const 
                                 const float* fars, float* xyzs, float* dirs, float* deltas,
                                 const int32_t* rays, const int32_t* counter,
                                 const float* noises, uint32_t zero_tail_end, void* stream) {
-    if (N == 0) return NVSF_OK;
-    if (!rays_o || !rays_d || !grid || !nears || !fars || !rays || !counter || !noises)
-        return NVSF_E_INVALID;
-    if (M > 0 && (!xyzs || !dirs || !deltas)) return NVSF_E_INVALID;
-    if (!march_cfg_ok(C, H, max_steps)) return NVSF_E_INVALID;
-    const uint32_t nblk = nvsf_div_up(N, (uint32_t)kRayBlock);
-    k_march_train_write<<<nblk, kRayBlock, 0, (cudaStream_t)stream>>>(
-        rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears, fars, xyzs, dirs,
-        deltas, rays, counter, noises, zero_tail_end);
-    return nvsf_launch_status();
+    return nvsf_march_rays_train_write_ws(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C,
+                                          H, M, nears, fars, xyzs, dirs, deltas, rays, counter,
+                                          noises, zero_tail_end, nullptr, 0, stream);
 }
 
 int nvsf_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t* grid,
@@ -1018,9 +1322,9 @@ int nvsf_march_rays_train(const float* rays_o, const float* rays_d, const uint8_
                                          H, nears, fars, rays, counter, noises, workspace,
                                          workspace_bytes, stream);
     if (st != NVSF_OK) return st;
-    return nvsf_march_rays_train_write(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C,
-                                       H, M, nears, fars, xyzs, dirs, deltas, rays, counter,
-                                       noises, 0u, stream);
+    return nvsf_march_rays_train_write_ws(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C,
+                                          H, M, nears, fars, xyzs, dirs, deltas, rays, counter,
+                                          noises, 0u, workspace, workspace_bytes, stream);
 }
 
 int nvsf_composite_rays_train_forward(const float* sigmas, const float* rgbs,
@@ -1070,9 +1374,19 @@ int nvsf_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive
         return NVSF_E_INVALID;
     if (!march_cfg_ok(C, H, max_steps)) return NVSF_E_INVALID;
     const uint32_t nblk = n_alive > 0 ? nvsf_div_up(n_alive, (uint32_t)kRayBlock) : 1u;
-    k_march_rays<<<nblk, kRayBlock, 0, (cudaStream_t)stream>>>(
-        n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H,
-        grid, nears, fars, xyzs, dirs, deltas, noises, M_padded);
+    if (nvsf_march_mode() && n_alive <= kSmallMarch)
+        k_march_rays_coop<32><<<n_alive > 0 ? nvsf_div_up(n_alive, 32u) : 1u, 32, 0,
+                                (cudaStream_t)stream>>>(
+            n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H,
+            grid, nears, fars, xyzs, dirs, deltas, noises, M_padded);
+    else if (nvsf_march_mode())
+        k_march_rays_coop<kRayBlock><<<nblk, kRayBlock, 0, (cudaStream_t)stream>>>(
+            n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H,
+            grid, nears, fars, xyzs, dirs, deltas, noises, M_padded);
+    else
+        k_march_rays<<<nblk, kRayBlock, 0, (cudaStream_t)stream>>>(
+            n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H,
+            grid, nears, fars, xyzs, dirs, deltas, noises, M_padded);
     return nvsf_launch_status();
 }
 

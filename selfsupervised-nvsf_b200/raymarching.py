@@ -186,9 +186,11 @@ class _march_rays_train(Function):
         dirs = alloc(M, 3, dtype=_f32, device=dev)
         deltas = alloc(M, 2, dtype=_f32, device=dev)
         # phase 2: emit samples; rows not covered by a ray are zero-filled by the kernel
-        check(L.nvsf_march_rays_train_write(*geom, M, ptr(nears), ptr(fars), ptr(xyzs),
-                                            ptr(dirs), ptr(deltas), ptr(rays),
-                                            ptr(step_counter), ptr(noises), M, st),
+        # (the workspace still holds the first samples of every ray from phase 1)
+        check(L.nvsf_march_rays_train_write_ws(*geom, M, ptr(nears), ptr(fars), ptr(xyzs),
+                                               ptr(dirs), ptr(deltas), ptr(rays),
+                                               ptr(step_counter), ptr(noises), M, ptr(ws),
+                                               ws_bytes, st),
               "march_rays_train(write)")
         return xyzs, dirs, deltas, rays
 

@@ -80,6 +80,25 @@ def main():
             t_ours = timeit(ours)
             row = dict(op="march_rays_train", kind=kind, fill=fill, N=N, M=M, ms=t_ours,
                        GBps=(48 * N + 32 * M) / t_ours / 1e6)
+            cs = torch.cuda.current_stream().cuda_stream
+
+            def count_only():
+                counter.zero_()
+                assert L.nvsf_march_rays_train_count(t_o.data_ptr(), t_d.data_ptr(), t_bf.data_ptr(), BOUND, S.DT_GAMMA, 1024, N, C, H,
+                                                     t_n.data_ptr(), t_f.data_ptr(), rays.data_ptr(), counter.data_ptr(), t_no.data_ptr(),
+                                                     ws.data_ptr(), ws_bytes, cs) == 0
+
+            def write_only():
+                assert L.nvsf_march_rays_train_write_ws(t_o.data_ptr(), t_d.data_ptr(), t_bf.data_ptr(), BOUND, S.DT_GAMMA, 1024, N, C, H, M,
+                                                        t_n.data_ptr(), t_f.data_ptr(), X.data_ptr(), D.data_ptr(), Dl.data_ptr(),
+                                                        rays.data_ptr(), counter.data_ptr(), t_no.data_ptr(), 0, ws.data_ptr(),
+                                                        ws_bytes, cs) == 0
+            row["count_ms"] = timeit(count_only)
+            row["write_coop_ms"] = timeit(write_only)
+            assert L.nvsf_set_option(b"march_mode", 0) == 0
+            row["write_serial_ms"] = timeit(write_only)
+            row["serial_ms"] = timeit(ours)
+            assert L.nvsf_set_option(b"march_mode", 1) == 0
             if ref is not None:
                 def theirs():
                     counter.zero_()
