@@ -33,7 +33,7 @@ extern "C" {
 #define NVSF_E_WORKSPACE (-2) /* workspace too small */
 
 /* ABI version of this header; bumped on any signature change. */
-#define NVSF_B200_ABI_VERSION 8
+#define NVSF_B200_ABI_VERSION 9
 int nvsf_abi_version(void);
 /* Human-readable text for a status returned by any nvsf_* call. */
 const char* nvsf_status_string(int status);
@@ -232,6 +232,18 @@ int nvsf_field_density(const nvsf_field_config_t* cfg, const void* workspace, co
                        uint32_t n, float* sigma, void* geo, void* features, float* flow,
                        void* scratch, size_t scratch_bytes, void* stream);
 
+/* replaces NeRFNetwork.color (network_dynamic.py:290-332) for n samples with their own view
+ * directions dirs [n,3]: LiDAR = Frequency(12) of (d+1)/2 (72) + geo_feat (15) -> intensity_net,
+ * raydrop_net -> sigmoid, columns [raydrop, intensity]; camera = SH(4) (16) + geo_feat -> color_net
+ * -> sigmoid, 3 columns.  geo: fp16 matrix [n, geo_ld] whose columns geo_off .. geo_off+14 are
+ * geo_feat (the geo16 rows written by nvsf_field_density: geo_ld = 16, geo_off = 1).  mask [n]
+ * (bytes, NULL = all): rows with mask == 0 are written as zeros (network_dynamic.py:297-307,327).
+ * out f32 [n, out_ld], out_ld in [channels, 4]; extra columns are zero (out_ld = 3 feeds the
+ * 3-channel compositors directly for LiDAR).  workspace must be packed for the same modality. */
+int nvsf_field_color(const nvsf_field_config_t* cfg, const void* workspace, uint32_t lidar,
+                     const float* dirs, const void* geo, uint32_t geo_ld, uint32_t geo_off,
+                     const uint8_t* mask, uint32_t n, float* out, uint32_t out_ld, void* stream);
+
 /* Tuning switches.  "density_mode": 1 (default) = staged density evaluation (flow stage, lean
  * gather stage at high occupancy, MLP stage; needs the scratch buffer), 0 = single fused kernel. */
 int nvsf_set_option(const char* name, int value);
@@ -332,6 +344,53 @@ int nvsf_render_uniform_backward(const nvsf_field_config_t* cfg, const void* wor
 int nvsf_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, size_t n,
                    float lr, float beta1, float beta2, float eps, uint32_t step, float grad_scale,
                    void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* Part 4 — callers either side of the marcher: ray generation, occupancy grid  */
+/* ------------------------------------------------------------------------- */
+
+/* replaces get_lidar_rays (dataset/dataset_utils.py:369-536) for one pose [4,4] (row-major,
+ * device): pixel id p = row*W + col from inds [n] (int64, NULL = all pixels 0..n-1 in row-major
+ * order), beta = -(col - W/2)/W * fov_hoz/180*pi, alpha = (fov_up - row/H*fov)/180*pi,
+ * d = (cos a cos b, cos a sin b, sin a) R^T, o = translation.  rays_o / rays_d [n,3]. */
+int nvsf_get_lidar_rays(const float* pose, const int64_t* inds, uint32_t n, uint32_t H, uint32_t W,
+                        float fov_up, float fov, float fov_hoz, float* rays_o, float* rays_d,
+                        void* stream);
+
+/* replaces get_rays (dataset/dataset_utils.py:539-687): d = normalize((col+0.5-cx)/fx,
+ * (row+0.5-cy)/fy, 1) R^T. */
+int nvsf_get_rays(const float* pose, const int64_t* inds, uint32_t n, uint32_t H, uint32_t W,
+                  float fx, float fy, float cx, float cy, float* rays_o, float* rays_d,
+                  void* stream);
+
+/* Occupancy-grid maintenance producing the `density_bitfield` that march_rays_train / march_rays
+ * read (raymarching.py:179,379).  The reference ships only morton3D / packbits and no update
+ * loop; this follows torch-ngp's update_extra_state, whose raymarching extension the reference
+ * carries.  All steps stay on the device.
+ *
+ * nvsf_grid_cell_points: sample point of every cell, xyz [C*H^3,3] in the grid's own [C][Morton]
+ *   order: (2*coords/(H-1) - 1) * (b_c - b_c/H) + (noise*2 - 1) * b_c/H with b_c = min(2^c, bound);
+ *   noise [C*H^3,3] in [0,1) or NULL (cell centres).
+ * nvsf_grid_accumulate: tmp = sigma*density_scale (first != 0) or max(tmp, sigma*density_scale)
+ *   (union over several frame times of a dynamic scene).
+ * nvsf_grid_update: grid = max(grid*decay, tmp) where grid >= 0 and tmp >= 0; stats[0] =
+ *   mean(clamp(grid, 0)), stats[1] = min(stats[0], density_thresh); bitfield = packbits(grid,
+ *   stats[1]).  n = C*H^3 (multiple of 8), workspace nvsf_grid_update_workspace_bytes(n). */
+int nvsf_grid_cell_points(uint32_t C, uint32_t H, float bound, const float* noise, float* xyz,
+                          void* stream);
+int nvsf_grid_accumulate(float* tmp_grid, const float* sigma, uint32_t n, float density_scale,
+                         uint32_t first, void* stream);
+size_t nvsf_grid_update_workspace_bytes(uint32_t n);
+int nvsf_grid_update(float* density_grid, const float* tmp_grid, uint32_t n, float decay,
+                     float density_thresh, uint8_t* bitfield, float* stats, void* workspace,
+                     size_t workspace_bytes, void* stream);
+
+/* Order-preserving compaction out = rays_alive[rays_alive >= 0] of the inference loop around
+ * march_rays / composite_rays (composite_rays marks finished rays with -1, raymarching.cu:1049);
+ * *n_out (device int32) receives the number kept. */
+size_t nvsf_compact_alive_workspace_bytes(uint32_t n);
+int nvsf_compact_alive(const int32_t* rays_alive, uint32_t n, int32_t* out, int32_t* n_out,
+                       void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

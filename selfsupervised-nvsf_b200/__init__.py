@@ -5,7 +5,9 @@ Importable as ``nvsf_b200`` (shim at the repository root) or via
 
 Sub-modules
     raymarching   drop-in for reference ``nvsf.nerf.raymarching.raymarching``
-    field         NeRFNetwork: density / flow / run / render of the reference model on the GPU kernels
+    field         NeRFNetwork: density / color / flow / run / render of the reference model on the GPU
+                  kernels, plus the occupancy-grid update and the march_rays* render loops (run_cuda)
+    rays          get_lidar_rays / get_rays (reference dataset_utils.py) generated on the device
     dist          ray sharding + flat-buffer gradient all-reduce (one process per GPU)
     optim         Adam over the flat parameter / gradient buffers (CUDA kernel)
     _lib          ctypes binding of the C ABI (include/nvsf_b200.h)
@@ -14,6 +16,7 @@ Sub-modules
 from . import _lib  # noqa: F401
 from . import raymarching  # noqa: F401
 from . import field  # noqa: F401
+from . import rays  # noqa: F401
 from . import dist  # noqa: F401
 from . import optim  # noqa: F401
 from .field import NeRFNetwork  # noqa: F401

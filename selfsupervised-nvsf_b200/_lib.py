@@ -80,6 +80,16 @@ PROTOTYPES = {
     "nvsf_render_uniform_backward": (_int, [_p, _p, _p, _u32, _p, _p, _p, _p, _p, _u32, _u32, _f32, _p,
                                             _sz, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "nvsf_adam_step": (_int, [_p, _p, _p, _p, _sz, _f32, _f32, _f32, _f32, _u32, _f32, _p]),
+    "nvsf_field_color": (_int, [_p, _p, _u32, _p, _p, _u32, _u32, _p, _u32, _p, _u32, _p]),
+    # Part 4 — ray generation, occupancy grid, alive-list compaction
+    "nvsf_get_lidar_rays": (_int, [_p, _p, _u32, _u32, _u32, _f32, _f32, _f32, _p, _p, _p]),
+    "nvsf_get_rays": (_int, [_p, _p, _u32, _u32, _u32, _f32, _f32, _f32, _f32, _p, _p, _p]),
+    "nvsf_grid_cell_points": (_int, [_u32, _u32, _f32, _p, _p, _p]),
+    "nvsf_grid_accumulate": (_int, [_p, _p, _u32, _f32, _u32, _p]),
+    "nvsf_grid_update_workspace_bytes": (_sz, [_u32]),
+    "nvsf_grid_update": (_int, [_p, _p, _u32, _f32, _f32, _p, _p, _p, _sz, _p]),
+    "nvsf_compact_alive_workspace_bytes": (_sz, [_u32]),
+    "nvsf_compact_alive": (_int, [_p, _u32, _p, _p, _p, _sz, _p]),
 }
 
 _lib = None
@@ -112,7 +122,7 @@ def lib():
     return _lib
 
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 
 def check(status, what=""):

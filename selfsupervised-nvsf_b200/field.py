@@ -6,9 +6,15 @@ renderer_dynamic.py:67-326) for the hot path:
 
     density(x, t, cal_lidar_color)           -> {"sigma", "geo_feat"}     network_dynamic.py:213-287
     flow(x, t)                               -> {"flow_forward", "flow_backward"}         :197-211
+    color(x, d, geo_feat, mask, cal_lidar_color) -> [N, 2|3] f32                          :290-332
     run(rays_o, rays_d, time, cal_lidar_color, num_steps, upsample_steps, bg_color, perturb, **kw)
     render(rays_o, rays_d, time, cal_lidar_color, staged, max_ray_batch, **kw)
                                              -> dict with the reference's keys   renderer_dynamic.py:109-326
+    update_extra_state(time, ...), run_cuda(rays_o, rays_d, time, ...)
+                                             -> occupancy-grid update and the march_rays* / composite_rays*
+                                                render loops around the operators of raymarching.py (the
+                                                reference ships the operators but not these callers; they
+                                                follow torch-ngp, where the operators come from)
 
 Everything is computed by the sm_100a kernels behind include/nvsf_b200.h; there is no PyTorch
 fallback.  Parameters are fp32 `nn.Parameter`s in the reference's own memory layouts (tcnn flat
@@ -113,6 +119,8 @@ def _setup_lib():
     L.nvsf_render_uniform_backward.argtypes = [cfgp, P, prmp, ctypes.c_uint32, P, P, P, P, P, ctypes.c_uint32,
                                                ctypes.c_uint32, ctypes.c_float, P, ctypes.c_size_t, P, P, P, P,
                                                P, prmp, P, ctypes.c_size_t, P]
+    L.nvsf_field_color.argtypes = [cfgp, P, ctypes.c_uint32, P, P, ctypes.c_uint32, ctypes.c_uint32, P,
+                                   ctypes.c_uint32, P, ctypes.c_uint32, P]
     _L = L
     return L
 
@@ -411,6 +419,199 @@ class NeRFNetwork(nn.Module):
         """Debug/test hook: the 120 sigma-net inputs [N,120] (fp16) and the flow [N,6]."""
         _, _, feats, f = self._density_raw(x, t, bool(cal_lidar_color), want_features=True, want_flow=True)
         return feats[:, :120], f
+
+    def _color_raw(self, d, geo16, lidar, mask=None, out_ld=None, geo_ld=16, geo_off=1):
+        """Heads on n samples; the workspace must be packed for `lidar` (prepare())."""
+        L = _setup_lib()
+        n = d.shape[0]
+        nch = 2 if lidar else 3
+        out_ld = out_ld or nch
+        out = torch.empty(n, out_ld, dtype=torch.float32, device=d.device)
+        check(L.nvsf_field_color(ctypes.byref(self._cfg), ptr(self._ws[lidar]), int(lidar), ptr(d), ptr(geo16),
+                                 geo_ld, geo_off, ptr(mask), n, ptr(out), out_ld, stream_ptr()), "field_color")
+        return out
+
+    @torch.no_grad()
+    def color(self, x, d, geo_feat, mask=None, cal_lidar_color=False, **kwargs):
+        """NeRFNetwork.color (network_dynamic.py:290-332): d [N,3] view directions in [-1,1],
+        geo_feat [N,15] (the slice `density()` returns, or any fp16/fp32 matrix), mask [N] bool
+        or None -> [N, 2] (raydrop, intensity) or [N, 3] rgb, zeros where mask is False.  `x`
+        is accepted and unused beyond its shape, as in the reference."""
+        lidar = bool(cal_lidar_color)
+        dev = self.sigma_net.device
+        if self._ws.get(lidar) is None or self._packed.get(lidar) is None or \
+                self._packed[lidar][0] != self._version_key(lidar):
+            self.prepare(0.0 if self._packed.get(lidar) is None or self._packed[lidar][1] is None
+                         else self._packed[lidar][1], lidar)
+        d = d.detach().to(device=dev, dtype=torch.float32).contiguous().view(-1, 3)
+        n = d.shape[0]
+        g = geo_feat.detach()
+        if (g.dtype == torch.float16 and g.dim() == 2 and g.shape == (n, 15) and g.stride() == (16, 1)
+                and g.storage_offset() >= 1 and g.device == dev
+                and (g.data_ptr() - 2) % 16 == 0):
+            # the view density() returned: columns 1..15 of the kernel's geo16 rows, used in place
+            base, geo_ld, geo_off = g.data_ptr() - 2, 16, 1
+            geo_ptr = ctypes.c_void_p(base)
+            keep = g
+        else:
+            keep = g.to(device=dev, dtype=torch.float16).contiguous().view(n, 15)
+            geo_ptr, geo_ld, geo_off = ptr(keep), 15, 0
+        m = None
+        if mask is not None:
+            m = mask.detach().to(device=dev).reshape(-1).to(torch.uint8).contiguous()
+        L = _setup_lib()
+        nch = 2 if lidar else 3
+        out = torch.empty(n, nch, dtype=torch.float32, device=dev)
+        check(L.nvsf_field_color(ctypes.byref(self._cfg), ptr(self._ws[lidar]), int(lidar), ptr(d), geo_ptr,
+                                 geo_ld, geo_off, ptr(m), n, ptr(out), nch, stream_ptr()), "field_color")
+        del keep
+        return out
+
+    def forward(self, x, d, t=None, cal_lidar_color=False, out_ld=None):
+        """sigma [N] and colours [N, 2|3] of samples (x, d): density + color in two launches
+        (what the march_rays* callers evaluate per batch of samples)."""
+        lidar = bool(cal_lidar_color)
+        with torch.no_grad():
+            sigma, geo16, _, _ = self._density_raw(x, t, lidar)
+            d = d.detach().to(device=sigma.device, dtype=torch.float32).contiguous().view(-1, 3)
+            rgbs = self._color_raw(d, geo16, lidar, out_ld=out_ld)
+        return sigma, rgbs
+
+    # ------------------------------------------------------------------ occupancy grid
+    def _grid_state(self, lidar):
+        st = getattr(self, "_grid", None)
+        if st is None:
+            st = self._grid = {}
+        if lidar not in st:
+            dev = self.sigma_net.device
+            n = self.cascade * self.grid_size ** 3
+            st[lidar] = dict(density_grid=torch.zeros(self.cascade, self.grid_size ** 3, device=dev),
+                             density_bitfield=torch.zeros(n // 8, dtype=torch.uint8, device=dev),
+                             stats=torch.zeros(2, device=dev), iter_density=0)
+        return st[lidar]
+
+    def density_bitfield(self, cal_lidar_color=False):
+        return self._grid_state(bool(cal_lidar_color))["density_bitfield"]
+
+    def density_grid(self, cal_lidar_color=False):
+        return self._grid_state(bool(cal_lidar_color))["density_grid"]
+
+    def mean_density(self, cal_lidar_color=False):
+        """Device scalar (no host sync): mean of clamp(density_grid, 0) after the last update."""
+        return self._grid_state(bool(cal_lidar_color))["stats"][0]
+
+    @torch.no_grad()
+    def update_extra_state(self, time=0.0, cal_lidar_color=False, decay=0.95, perturb=True, noise=None):
+        """Full occupancy-grid update (torch-ngp NeRFRenderer.update_extra_state, the caller the
+        reference's morton3D / packbits operators were written for): evaluate sigma at one
+        jittered point per cell and cascade, grid = max(grid*decay, sigma*density_scale),
+        density_thresh' = min(mean(grid), density_thresh), density_bitfield = packbits(grid).
+        `time` may be a list of frame times: a cell is kept if it is occupied at any of them
+        (one bitfield serves a dynamic scene because march_rays* take no time argument).
+        `noise` [C*H^3, 3] in [0,1) optionally supplies the jitter."""
+        L = _lib.lib()
+        lidar = bool(cal_lidar_color)
+        st = self._grid_state(lidar)
+        dev = self.sigma_net.device
+        C, H = self.cascade, self.grid_size
+        n = C * H ** 3
+        if noise is None and perturb:
+            noise = torch.rand(n, 3, dtype=torch.float32, device=dev)
+        if noise is not None:
+            noise = noise.detach().to(device=dev, dtype=torch.float32).contiguous()
+        xyz = torch.empty(n, 3, dtype=torch.float32, device=dev)
+        check(L.nvsf_grid_cell_points(C, H, self.bound, ptr(noise), ptr(xyz), stream_ptr()), "grid_cell_points")
+        tmp = torch.empty(n, dtype=torch.float32, device=dev)
+        times = list(time) if isinstance(time, (list, tuple)) else [time]
+        for k, t in enumerate(times):
+            sigma, _, _, _ = self._density_raw(xyz, t, lidar)
+            check(L.nvsf_grid_accumulate(ptr(tmp), ptr(sigma), n, self.density_scale, int(k == 0), stream_ptr()),
+                  "grid_accumulate")
+        wbytes = L.nvsf_grid_update_workspace_bytes(n)
+        ws = torch.empty(wbytes, dtype=torch.uint8, device=dev)
+        check(L.nvsf_grid_update(ptr(st["density_grid"]), ptr(tmp), n, float(decay), float(self.density_thresh),
+                                 ptr(st["density_bitfield"]), ptr(st["stats"]), ptr(ws), wbytes, stream_ptr()),
+              "grid_update")
+        st["iter_density"] += 1
+        return st["density_bitfield"]
+
+    # ------------------------------------------------------------------ march_rays* render loops
+    @torch.no_grad()
+    def run_cuda(self, rays_o, rays_d, time, cal_lidar_color=False, dt_gamma=0.0, bg_color=None, perturb=False,
+                 max_steps=1024, T_thresh=1e-4, one_shot=None, noises=None, density_bitfield=None,
+                 step_scale=16, **kwargs):
+        """Occupancy-skipping render built from the raymarching operators (the `cuda_ray` path of
+        torch-ngp's NeRFRenderer.run_cuda, which raymarching.py:171-510 was written for).
+
+        one_shot=True  (default in training mode): near_far -> march_rays_train -> density -> color ->
+                       composite_rays_train over ALL samples of the frame, one host read (the sample count).
+        one_shot=False (default in eval mode): the alive-ray loop march_rays(n_step) -> density -> color ->
+                       composite_rays -> compaction until every ray has terminated.  n_step is
+                       `step_scale` x torch-ngp's max(min(N // n_alive, 8), 1): the composited result does
+                       not depend on it, a B200 wants few, large launches.
+        Outputs use run()'s keys: depth = sum w*t (not normalised), image [.., 2|3], weights_sum.
+        LiDAR: near/far are the constants of renderer_dynamic.py:141-146 and no background is added."""
+        lidar = bool(cal_lidar_color)
+        prefix = rays_o.shape[:-1]
+        o, d, nears, fars, _ = self._rays_setup(rays_o, rays_d, lidar, 1, False, None)
+        N = o.shape[0]
+        dev = o.device
+        nch = 2 if lidar else 3
+        bits = density_bitfield if density_bitfield is not None else self.density_bitfield(lidar)
+        self.prepare(time, lidar)
+        if one_shot is None:
+            one_shot = self.training
+        if noises is None and perturb:
+            noises = torch.rand(N, dtype=torch.float32, device=dev)
+        if one_shot:
+            xyzs, dirs, deltas, rays = raymarching.march_rays_train(
+                o, d, self.bound, bits, self.cascade, self.grid_size, nears, fars, None, -1, noises is not None,
+                -1, True, dt_gamma, max_steps, noises)
+            sigmas, rgbs = self.forward(xyzs, dirs, time, lidar, out_ld=3)
+            if self.density_scale != 1:
+                sigmas = sigmas * self.density_scale
+            weights_sum, depth, image = raymarching.composite_rays_train(sigmas, rgbs, deltas, rays, T_thresh)
+            n_samples = xyzs.shape[0]
+        else:
+            L = _lib.lib()
+            weights_sum = torch.zeros(N, dtype=torch.float32, device=dev)
+            depth = torch.zeros(N, dtype=torch.float32, device=dev)
+            image = torch.zeros(N, 3, dtype=torch.float32, device=dev)
+            rays_alive = torch.arange(N, dtype=torch.int32, device=dev)
+            spare = torch.empty(N, dtype=torch.int32, device=dev)
+            rays_t = nears.clone()
+            n_dev = torch.empty(1, dtype=torch.int32, device=dev)
+            n_host = torch.empty(1, dtype=torch.int32).pin_memory()
+            cbytes = L.nvsf_compact_alive_workspace_bytes(N)
+            cws = torch.empty(max(cbytes, 16), dtype=torch.uint8, device=dev)
+            n_alive, step, n_samples = N, 0, 0
+            while step < max_steps and n_alive > 0:
+                n_step = max(min(N // n_alive, 8), 1) * int(step_scale)
+                nz = noises if (noises is not None and step == 0) else None
+                xyzs, dirs, deltas = raymarching.march_rays(
+                    n_alive, n_step, rays_alive, rays_t, o, d, self.bound, bits, self.cascade, self.grid_size,
+                    nears, fars, -1, nz is not None, dt_gamma, max_steps, nz)
+                sigmas, rgbs = self.forward(xyzs, dirs, time, lidar, out_ld=3)
+                if self.density_scale != 1:
+                    sigmas = sigmas * self.density_scale
+                raymarching.composite_rays(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum,
+                                           depth, image, T_thresh)
+                check(L.nvsf_compact_alive(ptr(rays_alive), n_alive, ptr(spare), ptr(n_dev), ptr(cws), cbytes,
+                                           stream_ptr()), "compact_alive")
+                n_host.copy_(n_dev, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                rays_alive, spare = spare, rays_alive
+                n_samples += n_alive * n_step
+                n_alive = int(n_host[0])
+                step += n_step
+        image = image[:, :nch]
+        if not lidar:
+            bg = 1.0 if bg_color is None else bg_color
+            image = image + (1 - weights_sum).unsqueeze(-1) * bg
+        sfx = "_lidar" if lidar else ""
+        self.last_run_cuda_samples = n_samples
+        return {"depth" + sfx: depth.view(*prefix), "image" + sfx: image.reshape(*prefix, nch),
+                "weights_sum" + sfx: weights_sum}
 
     # ------------------------------------------------------------------ renderer API
     def run(self, rays_o, rays_d, time, cal_lidar_color=False, num_steps=768, upsample_steps=128,
