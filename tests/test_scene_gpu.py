@@ -305,7 +305,9 @@ def test_run_cuda_vs_oracle(model, orc, SO, lidar, one_shot):
 
 def test_run_cuda_loop_independent_of_step_size(model):
     """The alive-ray loop composites the same samples in the same order whatever n_step is, and
-    equals the one-shot path with the same T_thresh."""
+    equals the one-shot path with the same T_thresh — up to fp32 rounding of the restart point:
+    composite_rays stores t = sum(deltas[:,1]) and march_rays resumes from it (raymarching.cu:
+    846,1046), which differs in the last bits from the marcher's own running t."""
     N = 4096
     o, d = S.camera_rays(N, seed=1)
     to, td = torch.from_numpy(o).cuda()[None], torch.from_numpy(d).cuda()[None]
@@ -315,8 +317,8 @@ def test_run_cuda_loop_independent_of_step_size(model):
     b = model.run_cuda(to, td, 0.25, one_shot=False, step_scale=1, **kw)
     c = model.run_cuda(to, td, 0.25, one_shot=True, **kw)
     for k in ("depth", "image", "weights_sum"):
-        np.testing.assert_array_equal(host(a[k]), host(b[k]))
-        np.testing.assert_allclose(host(a[k]), host(c[k]), rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(host(a[k]), host(b[k]), rtol=5e-5, atol=1e-6)
+        np.testing.assert_allclose(host(a[k]), host(c[k]), rtol=5e-5, atol=1e-6)
     assert float(a["weights_sum"].max()) > 0.05
 
 
