@@ -224,6 +224,61 @@ def bench_train(pkg, S, cfg_kw, dev, rank, world, rays, steps, warmup):
             "includes": "h2d rays, fwd+bwd of both modalities, grad all-reduce (N>1), Adam step, table re-pack, d2h loss"}
 
 
+def bench_camera_march(pkg, S, model, dev, rank, world, steps, warmup):
+    """BASELINE configs[3]: camera novel-view render 376x1408 RGB with occupancy-grid skipping, ONE
+    frame whose rays are sharded across the ranks (contiguous ray ranges, dist.shard_range; no
+    collective).  Per step through the public API: pinned host rays of this rank's shard -> device,
+    NeRFNetwork.run_cuda (near_far -> march_rays_train -> density -> color heads ->
+    composite_rays_train) against a synthetic street-shell occupancy bitfield, image -> host.
+    value = frame rays / max-over-ranks time ("strong")."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    o, d = S.camera_rays(-1, seed=0)
+    n_all = o.shape[0]
+    lo, hi = pkg.dist.shard_range(n_all, rank, world)
+    o_pin = torch.from_numpy(np.ascontiguousarray(o[lo:hi]))[None].pin_memory()
+    d_pin = torch.from_numpy(np.ascontiguousarray(d[lo:hi]))[None].pin_memory()
+    img_h = torch.empty(1, hi - lo, 3).pin_memory()
+    bits = torch.from_numpy(S.packbits_np(S.density_grid("shell"), 0.01)).to(dev)
+    t = torch.tensor([[0.5]], device=dev)
+
+    def step():
+        ro, rd = o_pin.to(dev, non_blocking=True), d_pin.to(dev, non_blocking=True)
+        r = model.run_cuda(ro, rd, t, cal_lidar_color=False, dt_gamma=S.DT_GAMMA, T_thresh=1e-2,
+                           density_bitfield=bits, one_shot=True)
+        img_h.copy_(r["image"], non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        step()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    barrier()
+    ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
+    tm = torch.tensor([ms, float(model.last_run_cuda_samples)], device=dev)
+    if world > 1:
+        mx = tm.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tm, op=dist.ReduceOp.SUM)
+        ms, samples = float(mx[0]), int(tm[1])
+    else:
+        samples = int(tm[1])
+    return {"value": n_all * steps / (ms * 1e-3), "unit": "rays/s", "ms_per_frame": ms / steps, "rays": n_all,
+            "samples": samples, "steps": steps, "scaling": "strong", "occupancy_grid": "synthetic street shell, 2x128^3",
+            "includes": "h2d rays of the shard, near_far, march (count+scan+write), density, colour heads, "
+                        "compositing, d2h image; one host read of the sample count per frame"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -234,6 +289,7 @@ def main():
     ap.add_argument("--cpu-rays", type=int, default=2048, help="rays of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the train_step sub-benchmarks")
+    ap.add_argument("--no-march", action="store_true", help="skip the camera occupancy-skipping render sub-benchmark")
     ap.add_argument("--train-steps", type=int, default=5)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -364,9 +420,11 @@ def main():
 
     # ---- joint training step (configs[2]; configs[4] = 64 K rays per GPU when N > 1) ----
     train = {}
+    del scratch
+    torch.cuda.empty_cache()
+    if not args.no_march:
+        train["camera_march_render"] = bench_camera_march(pkg, S, model, dev, rank, world, args.train_steps, 3)
     if not args.no_train:
-        del scratch
-        torch.cuda.empty_cache()
         train["train_step"] = bench_train(pkg, S, cfg_kw, dev, rank, world, 4096, args.train_steps, 3)
         if world > 1:
             train["train_step_64k_rays_per_gpu"] = bench_train(pkg, S, cfg_kw, dev, rank, world, 32768,

@@ -108,6 +108,11 @@ def run_cuda(field, rays_o, rays_d, t, lidar, bitfield, C, H, bound, nears, fars
         m = int(cnt[0])
         sig, rgb = shade(xyzs[:m], dirs[:m])
         ws, depth, image = RO.composite_rays_train_forward(sig, rgb, deltas[:m], rays, T_thresh)
+        # train compositing measures t from the first marching position (raymarching.cu:372-375,626-627)
+        dt_min = f32(2 * np.sqrt(3) / max_steps)
+        dt_max = f32(2 * np.sqrt(3) * 2 ** (C - 1) / H)
+        t0 = np.asarray(nears, f32) + np.clip(np.asarray(nears, f32) * f32(dt_gamma), dt_min, dt_max) * nz
+        depth = depth + ws * t0
         n_samples = m
     else:
         ws, depth, image = np.zeros(N, f32), np.zeros(N, f32), np.zeros((N, 3), f32)

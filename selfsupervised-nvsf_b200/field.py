@@ -552,7 +552,8 @@ class NeRFNetwork(nn.Module):
                        only when most rays terminate early.  n_step is `step_scale` x torch-ngp's
                        max(min(N // n_alive, 8), 1): the composited result does not depend on it (up to
                        fp32 rounding of the restart point), a B200 wants few, large launches.
-        Outputs use run()'s keys: depth = sum w*t (not normalised), image [.., 2|3], weights_sum.
+        Outputs use run()'s keys: depth = sum w*t (absolute distance along the ray, not normalised),
+        image [.., 2|3], weights_sum.
         LiDAR: near/far are the constants of renderer_dynamic.py:141-146 and no background is added."""
         lidar = bool(cal_lidar_color)
         prefix = rays_o.shape[:-1]
@@ -574,6 +575,15 @@ class NeRFNetwork(nn.Module):
             if self.density_scale != 1:
                 sigmas = sigmas * self.density_scale
             weights_sum, depth, image = raymarching.composite_rays_train(sigmas, rgbs, deltas, rays, T_thresh)
+            # composite_rays_train accumulates t from 0 at the ray's first marching position
+            # (raymarching.cu:372-375,626-627) while composite_rays starts from rays_t = near
+            # (:1003): make the one-shot depth absolute like run()'s sum(w * z)
+            t0 = nears
+            if noises is not None:
+                dt_min = 2 * math.sqrt(3) / max_steps
+                dt_max = 2 * math.sqrt(3) * 2 ** (self.cascade - 1) / self.grid_size
+                t0 = nears + (nears * dt_gamma).clamp(dt_min, dt_max) * noises.to(nears.dtype)
+            depth = depth + weights_sum * t0
             n_samples = xyzs.shape[0]
         else:
             L = _lib.lib()
