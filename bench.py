@@ -381,7 +381,7 @@ def main():
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
-    stage_ms = (ctypes.c_float * 3)()
+    stage_ms = (ctypes.c_float * 4)()
     stage_launches = ctypes.c_uint32(0)
     F.check(L.nvsf_stage_timing_read(stage_ms, ctypes.byref(stage_launches)), "stage_timing_read")
     F.check(L.nvsf_set_option(b"stage_timing", 0), "set_option")
@@ -438,8 +438,8 @@ def main():
     pk, pk_kind = peaks()
     n_samples = N * Sn
     n_launch = max(int(stage_launches.value), 1)            # chunks of the staged evaluation, all timed steps
-    flow_ms, enc_ms, sig_ms = (float(stage_ms[i]) / args.steps for i in range(3))
-    enc_launch_ms = float(stage_ms[1]) / n_launch            # average duration of one k_encode_stage launch
+    flow_ms, dyn_ms, enc_ms, sig_ms = (float(stage_ms[i]) / args.steps for i in range(4))
+    enc_launch_ms = float(stage_ms[2]) / n_launch            # average duration of one k_encode_stage launch
     samples_per_launch = n_samples * args.steps / n_launch
     achieved = ENCODE_BYTES_PER_SAMPLE * samples_per_launch / (enc_launch_ms * 1e-3) / 1e9
     traffic, limiter = None, None
@@ -455,7 +455,7 @@ def main():
                                "768 uniform samples/ray, random-init NVSF field (BASELINE configs[1])",
                    "rays_per_gpu": N, "samples_per_ray": Sn, "parallelism": f"rays x{world} (one frame per GPU, no collective)",
                    "l2": "per-step working set 1.9 GB of per-sample scratch + 128 MB tables exceeds the 126 MB L2; no flush",
-                   "kernel_ms": {"field_density": dens_ms, "flow_stage": flow_ms, "encode_stage": enc_ms,
+                   "kernel_ms": {"field_density": dens_ms, "flow_stage": flow_ms, "dyn_stage": dyn_ms, "encode_stage": enc_ms,
                                  "sigma_stage": sig_ms, "composite_heads": comp_ms,
                                  "time_collapse_and_gaps": ms_total / args.steps - dens_ms - comp_ms}},
         "clocks": clocks,

@@ -244,13 +244,18 @@ int nvsf_field_color(const nvsf_field_config_t* cfg, const void* workspace, uint
                      const float* dirs, const void* geo, uint32_t geo_ld, uint32_t geo_off,
                      const uint8_t* mask, uint32_t n, float* out, uint32_t out_ld, void* stream);
 
-/* Tuning switches.  "density_mode": 1 (default) = staged density evaluation (flow stage, lean
- * gather stage at high occupancy, MLP stage; needs the scratch buffer), 0 = single fused kernel. */
+/* Tuning switches.  "density_mode": 1 = staged density evaluation (flow stage, lean gather stage
+ * at high occupancy, MLP stage; needs the scratch buffer), 2 = staged, with the 72 time-collapsed
+ * 2-D hash tables gathered from shared memory (TMA-staged, k_dyn_stage), 0 = single fused kernel.
+ * "dyn_tile" (samples per work item), "dyn_overhead", "split_chunk" (units of 64 K samples) tune
+ * the staged evaluation. */
 int nvsf_set_option(const char* name, int value);
-/* "stage_timing": 1 records CUDA events on the launching stream around the three kernels of every
+int nvsf_density_mode_get(void); /* current "density_mode" */
+/* "stage_timing": 1 records CUDA events on the launching stream around the kernels of every
  * chunk of the staged density evaluation; nvsf_stage_timing_read sums them since the last read:
- * ms3 = {flow stage, encode (gather) stage, sigma stage} in milliseconds, *launches = chunks. */
-int nvsf_stage_timing_read(float* ms3, uint32_t* launches);
+ * ms4 = {flow stage, dyn stage (0 unless density_mode 2), encode (gather) stage, sigma stage} in
+ * milliseconds, *launches = chunks. */
+int nvsf_stage_timing_read(float* ms4, uint32_t* launches);
 
 /* replaces NeRFRenderer.run (renderer_dynamic.py:109-265) for N rays with S uniform samples.
  * nears/fars [N]; noise [N,S] in [0,1) or NULL (perturb=False); bg_color used for camera only.

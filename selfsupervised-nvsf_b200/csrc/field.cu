@@ -125,7 +125,9 @@ __global__ void k_collapse_planes_dyn(const float* __restrict__ planes, PlaneSrc
 // (HashGridT.forward + interpT, hash_field.py:65-88; both are linear in the table entries)
 __global__ void k_collapse_dyn(const float* __restrict__ slices /* [Tres][entries][4] */,
                                uint32_t entries, const TimeInfo* __restrict__ ti,
-                               float* __restrict__ dst /* + q*per_q */, size_t per_q) {
+                               float* __restrict__ dst /* + q*per_q */,
+                               __half* __restrict__ dst16 /* fp16 mirror, same indexing */,
+                               size_t per_q) {
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= entries) return;
     const float4* tab = reinterpret_cast<const float4*>(slices);
@@ -144,8 +146,10 @@ __global__ void k_collapse_dyn(const float* __restrict__ slices /* [Tres][entrie
             v = make_float4(wa * a.x + w * b.x, wa * a.y + w * b.y, wa * a.z + w * b.z,
                             wa * a.w + w * b.w);
         }
-        dst[q * per_q + e] = ti->lag[q][0] * v.x + ti->lag[q][1] * v.y + ti->lag[q][2] * v.z +
-                             ti->lag[q][3] * v.w;
+        const float o = ti->lag[q][0] * v.x + ti->lag[q][1] * v.y + ti->lag[q][2] * v.z +
+                        ti->lag[q][3] * v.w;
+        dst[q * per_q + e] = o;
+        dst16[q * per_q + e] = __float2half_rn(o);
     }
 }
 
@@ -443,6 +447,7 @@ FieldPtrs nvsf_make_field_ptrs(const nvsf_field_config_t* cfg, const void* works
     P.hs16 = reinterpret_cast<const uint2*>(w + L.hs16);
     P.pls = reinterpret_cast<const float*>(w + L.pls);
     P.dyn = reinterpret_cast<const float*>(w + L.dyn);
+    P.dyn16 = reinterpret_cast<const __half*>(w + L.dyn16);
     P.flow = reinterpret_cast<const float2*>(w + L.flow);
     P.pld = reinterpret_cast<const float*>(w + L.pld);
     P.mlp = reinterpret_cast<const __half*>(w + L.mlp);
@@ -462,7 +467,7 @@ int nvsf_launch_density(const nvsf_field_config_t* cfg, const void* workspace, c
                         const float* fars, const float* noise, uint32_t S, size_t n, float* sigma,
                         void* geo, void* features, float* flow, void* split_scratch,
                         cudaStream_t stream) {
-    if (split_scratch && nvsf_density_mode() == 1)
+    if (split_scratch && nvsf_density_mode() >= 1)
         return nvsf_launch_density_split(cfg, workspace, x, rays_o, rays_d, nears, fars, noise, S, n,
                                          sigma, geo, features, flow, split_scratch, stream);
     int st = ensure_density_attr();
@@ -567,7 +572,8 @@ int nvsf_field_pack_time(const nvsf_field_config_t* cfg, const nvsf_field_params
     for (int p = 0; p < 3; ++p) {
         const uint32_t e = cfg->hd_entries[p];
         k_collapse_dyn<<<nvsf_div_up(e, 256u), 256, 0, s>>>(
-            slices, e, ti, reinterpret_cast<float*>(w + L.dyn) + L.dyn_plane[p], L.dyn_per_q);
+            slices, e, ti, reinterpret_cast<float*>(w + L.dyn) + L.dyn_plane[p],
+            reinterpret_cast<__half*>(w + L.dyn16) + L.dyn_plane[p], L.dyn_per_q);
         slices += (size_t)cfg->time_resolution * e * kHashF;
     }
     // flow grid
@@ -602,7 +608,7 @@ static int g_march_mode_value = 1;
 int nvsf_set_option(const char* name, int value) {
     if (!name) return NVSF_E_INVALID;
     if (std::string(name) == "density_mode") {
-        if (value != 0 && value != 1) return NVSF_E_INVALID;
+        if (value < 0 || value > 2) return NVSF_E_INVALID;
         g_density_mode_value = value;
         return NVSF_OK;
     }
@@ -615,8 +621,10 @@ int nvsf_set_option(const char* name, int value) {
         nvsf_stage_timing_enable(value);
         return NVSF_OK;
     }
-    return NVSF_E_INVALID;
+    return nvsf_split_set_option(name, value);
 }
+
+int nvsf_density_mode_get(void) { return g_density_mode_value; }
 
 }  // extern "C"
 

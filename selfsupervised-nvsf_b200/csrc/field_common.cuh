@@ -35,6 +35,7 @@ struct WsLayout {
     size_t flow;      // float2 [fl_entries]                        time-collapsed flow grid
     size_t pld;       // float  [3 queries] per scale: [3 planes xt,yt,zt][R][8]
     size_t mlp;       // __half smem images of the MLP weights
+    size_t dyn16;     // __half [3 queries][sum_p hd_entries[p]]    fp16 mirror of dyn (shared-memory staging)
     size_t total;
     size_t pls_scale[NVSF_MAX_PLANE_SCALES];  // float offsets inside pls
     size_t pld_scale[NVSF_MAX_PLANE_SCALES];  // float offsets inside one query of pld
@@ -98,6 +99,7 @@ static inline WsLayout make_ws_layout(const nvsf_field_config_t* c) {
     L.pld_floats_per_q = g;
     L.pld = off; off = ws_align(off + 3 * g * sizeof(float));
     L.mlp = off; off = ws_align(off + (size_t)kMlpHalves * sizeof(__half));
+    L.dyn16 = off; off = ws_align(off + 3 * d * sizeof(__half));
     L.total = off;
     return L;
 }
@@ -107,6 +109,7 @@ struct FieldPtrs {
     const uint2* hs16;
     const float* pls;
     const float* dyn;
+    const __half* dyn16;
     const float2* flow;
     const float* pld;
     const __half* mlp;
@@ -141,6 +144,7 @@ int nvsf_launch_density_split(const nvsf_field_config_t* cfg, const void* worksp
                               const DensityKeep* keep = nullptr);
 int nvsf_density_mode();
 void nvsf_stage_timing_enable(int on);
+int nvsf_split_set_option(const char* name, int value);
 // Compositing + heads launcher (render.cu); scratch = sigma f32 [N*S] then geo f16 [N*S,16];
 // rgbs (f32 [N*S,4], may be NULL) receives the per-sample colours for the backward pass.
 int nvsf_render_composite_launch(const nvsf_field_config_t* cfg, const void* workspace,
@@ -259,11 +263,22 @@ __device__ __forceinline__ LevelArgs lv(const nvsf_grid_level_t& g) {
     return a;
 }
 
+// floor(p) for |p| < 2^22 without the quarter-rate F2I / FRND conversions: adding 1.5 * 2^23 with
+// round-toward-minus-infinity lands in the binade [2^23, 2^24) whose ulp is 1, so the sum IS
+// floor(p) + bias, its bit pattern minus the bias pattern is the (signed) integer, and subtracting
+// the bias back is exact.  Bit-identical to floorf() + (int) cast on that range.
+__device__ __forceinline__ float floor_int(float p, int& i) {
+    const float t = __fadd_rd(p, 12582912.0f);
+    i = __float_as_int(t) - 0x4B400000;
+    return t - 12582912.0f;
+}
+
 // tcnn grid position: pos = scale*x + 0.5, cell = floor(pos), w = pos - cell
 __device__ __forceinline__ void grid_pos(float scale, float x, uint32_t& cell, float& w) {
     const float p = fmaf(scale, x, 0.5f);
-    const float f = floorf(p);
-    cell = (uint32_t)(int)f;
+    int c;   // |p| < 2^22 for x in [0,1] (+ flow) and scale <= 32768; any other p still yields an
+    const float f = floor_int(p, c);  // in-range table index below (hash mask / wrap_dense)
+    cell = (uint32_t)c;
     w = p - f;
 }
 
@@ -297,8 +312,9 @@ __device__ __forceinline__ void plane_coord(float p, uint32_t R, uint32_t& i0, u
                                             float& w) {
     float f = ((p * 2.0f - 1.0f) + 1.0f) * 0.5f * (float)(R - 1);
     f = fminf(fmaxf(f, 0.f), (float)(R - 1));
-    const float fl = floorf(f);
-    i0 = (uint32_t)fl;
+    int fi;
+    const float fl = floor_int(f, fi);   // 0 <= f <= R-1 < 2^22
+    i0 = (uint32_t)fi;
     i1 = min(i0 + 1, R - 1);
     w = f - fl;
 }

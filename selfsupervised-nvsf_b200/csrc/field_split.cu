@@ -140,14 +140,17 @@ __device__ __forceinline__ void st8g(__half* row, int col, const float (&v)[8]) 
     *reinterpret_cast<uint4*>(row + col) = o;
 }
 
-template <bool FROM_RAYS>
+// DYN_PRE: the 24 dynamic-hash features were produced by k_dyn_stage (planar fp16 rows
+// dyn_in[c * dyn_stride + sample], c = plane * 8 + level) and are only merged into the row here.
+template <bool FROM_RAYS, bool DYN_PRE>
 __global__ void __launch_bounds__(256, 4)
 k_encode_stage(const __grid_constant__ nvsf_field_config_t cfg,
                const __grid_constant__ FieldPtrs P, const float* __restrict__ xin,
                const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                const float* __restrict__ nears, const float* __restrict__ fars,
                const float* __restrict__ noise, uint32_t S, size_t begin, size_t count,
-               const float* __restrict__ flow_in, __half* __restrict__ feat_out) {
+               const float* __restrict__ flow_in, __half* __restrict__ feat_out,
+               const unsigned short* __restrict__ dyn_in, size_t dyn_stride) {
     const size_t li = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (li >= count) return;
     float x, y, z;
@@ -202,12 +205,18 @@ k_encode_stage(const __grid_constant__ nvsf_field_config_t cfg,
         st8g(row, 64 + 4 * l, v);
     }
     // (d) collapsed 2-D hashes -> [96,120), zero pad [120,128)
+    if constexpr (DYN_PRE) {
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+            uint32_t h[8];
+#pragma unroll
+            for (int l = 0; l < 8; ++l) h[l] = __ldcs(dyn_in + (size_t)(8 * p + l) * dyn_stride + li);
+            *reinterpret_cast<uint4*>(row + 96 + 8 * p) =
+                make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
+        }
+    } else {
 #pragma unroll 1
-#ifdef NVSF_EXP_SKIP
-    for (int p = 0; p < NVSF_EXP_SKIP; ++p) {
-#else
     for (int p = 0; p < 3; ++p) {
-#endif
         float u[3], w[3];
         const float* tab[3];
 #pragma unroll
@@ -237,7 +246,236 @@ k_encode_stage(const __grid_constant__ nvsf_field_config_t cfg,
         }
         *reinterpret_cast<uint4*>(row + 96 + 8 * p) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
     }
+    }
     *reinterpret_cast<uint4*>(row + 120) = make_uint4(0, 0, 0, 0);
+}
+
+
+// ---- stage 2a: dynamic 2-D hashes, tables staged in shared memory ---------------------------------
+// ncu on k_encode_stage (profiles/encode_stage_ncu.json): 288 of its ~590 loads per sample are the
+// 4-byte corner gathers of the 72 time-collapsed 2-D hash tables (3 planes x 8 levels x 3 query
+// times); on the fine levels every lane of a warp hits its own 32-byte sector, so the kernel is
+// bound by L1TEX wavefronts.  Those tables are small — 2^13..2^15 entries each — so this stage
+// turns the problem around: a CTA (1024 threads, one per SM) copies the fp16 tables of a "type"
+// (one plane, up to 4 consecutive levels, the 3 query times: <= 192 KB) into shared memory with
+// cp.async.bulk (TMA, completion on an mbarrier) and then streams tiles of samples through them:
+// a scattered 2-byte gather costs a bank-conflict degree (~3 cycles per warp) instead of up to
+// 32 L1 wavefronts.  Types are handed out dynamically (one atomic tile counter per type; a CTA
+// keeps its tables until its type runs dry, then helps the next one).  Output: planar fp16 rows
+// dyn_out[c * stride + sample], c = plane * 8 + level, merged into the feature rows by
+// k_encode_stage<., true>.  Price: the sample positions (rays + 32 B of flow) are re-read once
+// per type from L2, and the table values are rounded to fp16 (they are fp16 parameters blended in
+// fp32; the extra rounding is below the fp16 resolution of the feature rows themselves).
+constexpr int kDynThreads = 1024;
+constexpr int kDynMaxCombo = 4;
+constexpr int kDynMaxTypes = 24;
+constexpr size_t kDynTableBytes = 192 * 1024;
+
+struct DynPlan {
+    uint32_t ntypes, tile, tiles, stride;
+    uint32_t tab_off[kDynMaxTypes][kDynMaxCombo];  // halves; the 3 query tables follow each other
+    uint16_t cta_first[kDynMaxTypes];              // first CTA that starts on this type
+    uint8_t ncombo[kDynMaxTypes], plane[kDynMaxTypes], level0[kDynMaxTypes];
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy (TMA engine); bytes % 16 == 0, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::
+            "r"(smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// one level of a time-collapsed 2-D hash grid, table in shared memory (fp16); same arithmetic as
+// hash2_f1.  HASHED is hoisted out of the corner loop so that the four gathers issue back to back.
+template <bool HASHED>
+__device__ __forceinline__ float hash2_sm(const __half* __restrict__ tab, const LevelArgs& L,
+                                          float u, float v) {
+    uint32_t cu, cv;
+    float wu, wv;
+    grid_pos(L.scale, u, cu, wu);
+    grid_pos(L.scale, v, cv, wv);
+    uint32_t i00, i10, i01, i11;
+    if (HASHED) {
+        const uint32_t m = L.size - 1, h0 = cv * 2654435761u, h1 = h0 + 2654435761u;
+        i00 = (cu ^ h0) & m; i10 = ((cu + 1) ^ h0) & m;
+        i01 = (cu ^ h1) & m; i11 = ((cu + 1) ^ h1) & m;
+    } else {
+        i00 = idx2(L, cu, cv); i10 = idx2(L, cu + 1, cv);
+        i01 = idx2(L, cu, cv + 1); i11 = idx2(L, cu + 1, cv + 1);
+    }
+    const float t00 = __half2float(tab[i00]), t10 = __half2float(tab[i10]);
+    const float t01 = __half2float(tab[i01]), t11 = __half2float(tab[i11]);
+    return (1.f - wu) * (1.f - wv) * t00 + wu * (1.f - wv) * t10 + (1.f - wu) * wv * t01 +
+           wu * wv * t11;
+}
+template <bool HASHED>
+__device__ __forceinline__ float dyn_combo(const __half* __restrict__ t0, const LevelArgs& L,
+                                           const float (&u)[3], const float (&w)[3]) {
+    const float a = hash2_sm<HASHED>(t0, L, u[0], w[0]);
+    const float b = hash2_sm<HASHED>(t0 + L.size, L, u[1], w[1]);
+    const float c = hash2_sm<HASHED>(t0 + 2 * L.size, L, u[2], w[2]);
+    return 0.5f * a + 0.25f * (b + c);
+}
+
+template <bool FROM_RAYS>
+__global__ void __launch_bounds__(kDynThreads, 1)
+k_dyn_stage(const __grid_constant__ nvsf_field_config_t cfg, const __grid_constant__ FieldPtrs P,
+            const __grid_constant__ DynPlan plan, const float* __restrict__ xin,
+            const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+            const float* __restrict__ nears, const float* __restrict__ fars,
+            const float* __restrict__ noise, uint32_t S, size_t begin, size_t count,
+            const float* __restrict__ flow_in, __half* __restrict__ dyn_out,
+            uint32_t* __restrict__ next_tile) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __half* tabs = reinterpret_cast<__half*>(smem_raw);
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t s_tile;
+    const int tid = threadIdx.x;
+    if (tid == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    const int ntypes = (int)plan.ntypes;
+    int type = 0;
+    for (int t = 1; t < ntypes; ++t)
+        if (blockIdx.x >= plan.cta_first[t]) type = t;
+    int loaded = -1;
+    uint32_t parity = 0;
+    const int valid1 = P.ti->valid[1], valid2 = P.ti->valid[2];
+    for (int tried = 0; tried < ntypes;) {
+        if (tid == 0) s_tile = atomicAdd(next_tile + type, 1u);
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        __syncthreads();  // s_tile may be rewritten; nobody still reads the previous tables
+        if (tile >= plan.tiles) {
+            type = type + 1 == ntypes ? 0 : type + 1;
+            ++tried;
+            continue;
+        }
+        tried = 0;
+        const int p = plan.plane[type], l0 = plan.level0[type], nc = plan.ncombo[type];
+        if (loaded != type) {
+            if (tid == 0) {
+                uint32_t bytes = 0;
+                for (int j = 0; j < nc; ++j) bytes += 3u * cfg.hd[p][l0 + j].size * 2u;
+                mbar_expect_tx(&bar, bytes);
+                for (int j = 0; j < nc; ++j) {
+                    const uint32_t size = cfg.hd[p][l0 + j].size;
+                    for (int q = 0; q < 3; ++q) {
+                        const int qq = q == 0 ? 0 : (q == 1 ? (valid1 ? 1 : 0) : (valid2 ? 2 : 0));
+                        bulk_g2s(tabs + plan.tab_off[type][j] + (size_t)q * size,
+                                 P.dyn16 + (size_t)qq * P.dyn_per_q + P.dyn_plane[p] +
+                                     cfg.hd[p][l0 + j].offset,
+                                 size * 2u, &bar);
+                    }
+                }
+            }
+            mbar_wait(&bar, parity);
+            parity ^= 1u;
+            loaded = type;
+        }
+        const size_t base = (size_t)tile * plan.tile;
+        const uint32_t nloc = (uint32_t)min((size_t)plan.tile, count - base);
+        for (uint32_t i = tid; i < nloc; i += kDynThreads) {
+            const size_t li = base + i;
+            float x, y, z;
+            sample_position<FROM_RAYS>(cfg, begin + li, xin, rays_o, rays_d, nears, fars, noise, S,
+                                       x, y, z);
+            const float4 f0 = __ldg(reinterpret_cast<const float4*>(flow_in + li * 8));
+            const float4 f1 = __ldg(reinterpret_cast<const float4*>(flow_in + li * 8) + 1);
+            const float x1 = valid1 ? x + f0.x : x, y1 = valid1 ? y + f0.y : y,
+                        z1 = valid1 ? z + f0.z : z;
+            const float x2 = valid2 ? x + f0.w : x, y2 = valid2 ? y + f1.x : y,
+                        z2 = valid2 ? z + f1.y : z;
+            float u[3], w[3];
+            u[0] = p == 2 ? y : x;   w[0] = p == 0 ? y : z;
+            u[1] = p == 2 ? y1 : x1; w[1] = p == 0 ? y1 : z1;
+            u[2] = p == 2 ? y2 : x2; w[2] = p == 0 ? y2 : z2;
+            __half* out = dyn_out + (size_t)(8 * p + l0) * plan.stride + li;
+#pragma unroll 1
+            for (int j = 0; j < nc; ++j) {
+                const LevelArgs L = lv(cfg.hd[p][l0 + j]);
+                const __half* t0 = tabs + plan.tab_off[type][j];
+                const float r = L.hashed ? dyn_combo<true>(t0, L, u, w) : dyn_combo<false>(t0, L, u, w);
+                __stcs(reinterpret_cast<unsigned short*>(out + (size_t)j * plan.stride),
+                       __half_as_ushort(__float2half_rn(r)));
+            }
+        }
+    }
+}
+
+// Host side: pack consecutive levels of one plane into types whose tables fit the budget, and hand
+// the CTAs out in proportion to the per-sample cost of each type.  Returns false when a level does
+// not fit / is not 16-byte granular (the caller then uses the plain gather stage).
+int g_dyn_tile = 8192;       // samples per work item            (option "dyn_tile")
+int g_dyn_overhead = 6;      // per-sample fixed cost in gathers  (option "dyn_overhead")
+size_t g_split_chunk = kSplitChunk;  // samples per chunk          (option "split_chunk", units of 64 K)
+
+bool make_dyn_plan(const nvsf_field_config_t* cfg, const FieldPtrs& P, size_t count, size_t stride,
+                   int ctas, DynPlan& plan) {
+    int nt = 0;
+    for (int p = 0; p < 3; ++p) {
+        int l = 0;
+        while (l < kHdLevels) {
+            if (nt == kDynMaxTypes) return false;
+            size_t used = 0;
+            int nc = 0;
+            while (l + nc < kHdLevels && nc < kDynMaxCombo) {
+                const nvsf_grid_level_t& g = cfg->hd[p][l + nc];
+                const size_t bytes = (size_t)3 * g.size * sizeof(__half);
+                if ((g.size * sizeof(__half)) % 16 || (g.offset * sizeof(__half)) % 16) return false;
+                if (used + bytes > kDynTableBytes) break;
+                plan.tab_off[nt][nc] = (uint32_t)(used / sizeof(__half));
+                used += bytes;
+                ++nc;
+            }
+            if (nc == 0) return false;
+            plan.plane[nt] = (uint8_t)p;
+            plan.level0[nt] = (uint8_t)l;
+            plan.ncombo[nt] = (uint8_t)nc;
+            ++nt;
+            l += nc;
+        }
+        if ((P.dyn_plane[p] * sizeof(__half)) % 16) return false;
+    }
+    if ((P.dyn_per_q * sizeof(__half)) % 16) return false;
+    plan.ntypes = (uint32_t)nt;
+    plan.tile = (uint32_t)g_dyn_tile;
+    plan.tiles = (uint32_t)((count + plan.tile - 1) / plan.tile);
+    plan.stride = (uint32_t)stride;
+    double total = 0.0, acc = 0.0;
+    for (int t = 0; t < nt; ++t) total += 12.0 * plan.ncombo[t] + g_dyn_overhead;
+    for (int t = 0; t < nt; ++t) {
+        plan.cta_first[t] = (uint16_t)std::min<double>(ctas - 1, acc / total * ctas + 0.5);
+        acc += 12.0 * plan.ncombo[t] + g_dyn_overhead;
+    }
+    plan.cta_first[0] = 0;
+    return true;
 }
 
 // ---- stage 3: sigma MLP -------------------------------------------------------------------------
@@ -301,8 +539,8 @@ k_sigma_stage(const __half* __restrict__ mlp, const __half* __restrict__ feat, s
     }
 }
 
-// Optional per-stage timing with CUDA events on the launching stream (bench.py's roofline): four
-// events per chunk, read back (and reset) by nvsf_stage_timing_read.
+// Optional per-stage timing with CUDA events on the launching stream (bench.py's roofline): five
+// events per chunk (flow | dyn | encode | sigma), read back (and reset) by nvsf_stage_timing_read.
 struct StageProf {
     bool on = false;
     std::vector<cudaEvent_t> ev;
@@ -318,6 +556,7 @@ struct StageProf {
         return e;
     }
 } g_prof;
+constexpr int kProfEvents = 5;
 
 bool g_attr = false;
 int ensure_attrs() {
@@ -332,16 +571,35 @@ int ensure_attrs() {
     e = cudaFuncSetAttribute(k_sigma_stage, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)kSigmaStageSmem);
     if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(k_dyn_stage<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)kDynTableBytes);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(k_dyn_stage<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)kDynTableBytes);
+    if (e != cudaSuccess) return (int)e;
     g_attr = true;
     return NVSF_OK;
 }
 
+// split scratch: flow f32 [chunk,8] | feats f16 [chunk,128] | dyn f16 [24][chunk] | tile counters
+struct SplitScratch {
+    size_t flow, feat, dyn, counters, total;
+};
+SplitScratch split_layout(size_t n) {
+    const size_t chunk = std::min<size_t>(n, kSplitChunk);   // sized for the largest chunk option
+    SplitScratch L;
+    size_t off = 0;
+    L.flow = off; off += ws_align(chunk * 8 * sizeof(float));
+    L.feat = off; off += ws_align(chunk * kFeat * sizeof(__half));
+    L.dyn = off; off += ws_align(chunk * 3 * kHdLevels * sizeof(__half));
+    L.counters = off; off += ws_align(kDynMaxTypes * sizeof(uint32_t));
+    L.total = off;
+    return L;
+}
+
 }  // namespace
 
-size_t nvsf_density_split_scratch_bytes(size_t n) {
-    const size_t chunk = std::min<size_t>(n, kSplitChunk);
-    return ws_align(chunk * 8 * sizeof(float)) + ws_align(chunk * kFeat * sizeof(__half));
-}
+size_t nvsf_density_split_scratch_bytes(size_t n) { return split_layout(n).total; }
 
 int nvsf_launch_density_split(const nvsf_field_config_t* cfg, const void* workspace,
                               const float* x, const float* rays_o, const float* rays_d,
@@ -355,10 +613,16 @@ int nvsf_launch_density_split(const nvsf_field_config_t* cfg, const void* worksp
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const size_t chunk = std::min<size_t>(n, kSplitChunk);
-    float* flow_buf = reinterpret_cast<float*>(split_scratch);
-    __half* feat_buf = reinterpret_cast<__half*>(reinterpret_cast<unsigned char*>(split_scratch) +
-                                                 ws_align(chunk * 8 * sizeof(float)));
+    const SplitScratch SL = split_layout(n);
+    const size_t chunk = std::min<size_t>(n, std::min<size_t>(g_split_chunk, kSplitChunk));
+    unsigned char* sc = reinterpret_cast<unsigned char*>(split_scratch);
+    float* flow_buf = reinterpret_cast<float*>(sc + SL.flow);
+    __half* feat_buf = reinterpret_cast<__half*>(sc + SL.feat);
+    __half* dyn_buf = reinterpret_cast<__half*>(sc + SL.dyn);
+    uint32_t* counters = reinterpret_cast<uint32_t*>(sc + SL.counters);
+    // mode 2: dynamic hashes from shared-memory-staged tables (needs the scratch buffer; the
+    // training forward passes none and keeps the plain gather stage)
+    const bool want_dyn = split_scratch != nullptr && nvsf_density_mode() == 2;
     for (size_t begin = 0; begin < n; begin += chunk) {
         const size_t count = std::min(chunk, n - begin);
         __half* ff = nullptr;
@@ -369,21 +633,46 @@ int nvsf_launch_density_split(const nvsf_field_config_t* cfg, const void* worksp
         }
         const size_t tiles = (count + kSTile - 1) / kSTile;
         const int grid_p = (int)std::min<size_t>(tiles, (size_t)sms * 2);
+        DynPlan plan;
+        const bool dyn_pre = want_dyn && make_dyn_plan(cfg, P, count, count, sms, plan);
+        const int grid_d = dyn_pre ? (int)std::min<size_t>((size_t)plan.ntypes * plan.tiles, (size_t)sms) : 0;
+        if (dyn_pre) cudaMemsetAsync(counters, 0, kDynMaxTypes * sizeof(uint32_t), stream);
+        const unsigned short* dyn_in = reinterpret_cast<const unsigned short*>(dyn_buf);
         if (g_prof.on) g_prof.next(stream);
         if (x) {
             k_flow_stage<false><<<grid_p, kSTile, kFlowStageSmem, stream>>>(
                 *cfg, P, x, nullptr, nullptr, nullptr, nullptr, nullptr, 1, begin, count, flow_buf, ff);
             if (g_prof.on) g_prof.next(stream);
-            k_encode_stage<false><<<(unsigned)tiles, 256, 0, stream>>>(
-                *cfg, P, x, nullptr, nullptr, nullptr, nullptr, nullptr, 1, begin, count, flow_buf,
-                feat_buf);
+            if (dyn_pre)
+                k_dyn_stage<false><<<grid_d, kDynThreads, kDynTableBytes, stream>>>(
+                    *cfg, P, plan, x, nullptr, nullptr, nullptr, nullptr, nullptr, 1, begin, count,
+                    flow_buf, dyn_buf, counters);
+            if (g_prof.on) g_prof.next(stream);
+            if (dyn_pre)
+                k_encode_stage<false, true><<<(unsigned)tiles, 256, 0, stream>>>(
+                    *cfg, P, x, nullptr, nullptr, nullptr, nullptr, nullptr, 1, begin, count, flow_buf,
+                    feat_buf, dyn_in, count);
+            else
+                k_encode_stage<false, false><<<(unsigned)tiles, 256, 0, stream>>>(
+                    *cfg, P, x, nullptr, nullptr, nullptr, nullptr, nullptr, 1, begin, count, flow_buf,
+                    feat_buf, nullptr, 0);
         } else {
             k_flow_stage<true><<<grid_p, kSTile, kFlowStageSmem, stream>>>(
                 *cfg, P, nullptr, rays_o, rays_d, nears, fars, noise, S, begin, count, flow_buf, ff);
             if (g_prof.on) g_prof.next(stream);
-            k_encode_stage<true><<<(unsigned)tiles, 256, 0, stream>>>(
-                *cfg, P, nullptr, rays_o, rays_d, nears, fars, noise, S, begin, count, flow_buf,
-                feat_buf);
+            if (dyn_pre)
+                k_dyn_stage<true><<<grid_d, kDynThreads, kDynTableBytes, stream>>>(
+                    *cfg, P, plan, nullptr, rays_o, rays_d, nears, fars, noise, S, begin, count,
+                    flow_buf, dyn_buf, counters);
+            if (g_prof.on) g_prof.next(stream);
+            if (dyn_pre)
+                k_encode_stage<true, true><<<(unsigned)tiles, 256, 0, stream>>>(
+                    *cfg, P, nullptr, rays_o, rays_d, nears, fars, noise, S, begin, count, flow_buf,
+                    feat_buf, dyn_in, count);
+            else
+                k_encode_stage<true, false><<<(unsigned)tiles, 256, 0, stream>>>(
+                    *cfg, P, nullptr, rays_o, rays_d, nears, fars, noise, S, begin, count, flow_buf,
+                    feat_buf, nullptr, 0);
         }
         if (g_prof.on) g_prof.next(stream);
         k_sigma_stage<<<grid_p, kSTile, kSigmaStageSmem, stream>>>(
@@ -400,23 +689,44 @@ int nvsf_launch_density_split(const nvsf_field_config_t* cfg, const void* worksp
     return nvsf_launch_status();
 }
 
+// ---- tuning options of the staged evaluation (nvsf_set_option falls through to here) -------------
+int nvsf_split_set_option(const char* name, int value) {
+    const std::string k(name);
+    if (k == "dyn_tile") {
+        if (value < 1024 || value > (1 << 22)) return NVSF_E_INVALID;
+        g_dyn_tile = value;
+        return NVSF_OK;
+    }
+    if (k == "dyn_overhead") {
+        if (value < 0 || value > 1000) return NVSF_E_INVALID;
+        g_dyn_overhead = value;
+        return NVSF_OK;
+    }
+    if (k == "split_chunk") {  // units of 64 K samples, at most kSplitChunk
+        if (value < 1 || (size_t)value * 65536 > kSplitChunk) return NVSF_E_INVALID;
+        g_split_chunk = (size_t)value * 65536;
+        return NVSF_OK;
+    }
+    return NVSF_E_INVALID;
+}
+
 // ---- stage timing (see StageProf) -------------------------------------------------------------------
 void nvsf_stage_timing_enable(int on) {
     g_prof.on = on != 0;
     g_prof.used = 0;
 }
 
-extern "C" int nvsf_stage_timing_read(float* ms3, uint32_t* launches) {
-    if (!ms3) return NVSF_E_INVALID;
-    ms3[0] = ms3[1] = ms3[2] = 0.f;
-    const size_t groups = g_prof.used / 4;
+extern "C" int nvsf_stage_timing_read(float* ms4, uint32_t* launches) {
+    if (!ms4) return NVSF_E_INVALID;
+    ms4[0] = ms4[1] = ms4[2] = ms4[3] = 0.f;
+    const size_t groups = g_prof.used / kProfEvents;
     for (size_t g = 0; g < groups; ++g) {
-        cudaError_t e = cudaEventSynchronize(g_prof.ev[4 * g + 3]);
+        cudaError_t e = cudaEventSynchronize(g_prof.ev[kProfEvents * g + kProfEvents - 1]);
         if (e != cudaSuccess) return (int)e;
-        for (int k = 0; k < 3; ++k) {
+        for (int k = 0; k < kProfEvents - 1; ++k) {
             float ms = 0.f;
-            cudaEventElapsedTime(&ms, g_prof.ev[4 * g + k], g_prof.ev[4 * g + k + 1]);
-            ms3[k] += ms;
+            cudaEventElapsedTime(&ms, g_prof.ev[kProfEvents * g + k], g_prof.ev[kProfEvents * g + k + 1]);
+            ms4[k] += ms;
         }
     }
     if (launches) *launches = (uint32_t)groups;

@@ -27,6 +27,7 @@ fallback.  Parameters are fp32 `nn.Parameter`s in the reference's own memory lay
     sigma_net, intensity_net, raydrop_net, color_net  == the tcnn `params` of the same name
 """
 import ctypes
+import os
 import math
 
 import numpy as np
@@ -121,6 +122,10 @@ def _setup_lib():
                                                P, prmp, P, ctypes.c_size_t, P]
     L.nvsf_field_color.argtypes = [cfgp, P, ctypes.c_uint32, P, P, ctypes.c_uint32, ctypes.c_uint32, P,
                                    ctypes.c_uint32, P, ctypes.c_uint32, P]
+    # development switches (A/B runs of the staged density evaluation): NVSF_OPT="density_mode=2,dyn_tile=8192"
+    for kv in filter(None, os.environ.get("NVSF_OPT", "").split(",")):
+        k, v = kv.split("=")
+        check(L.nvsf_set_option(k.strip().encode(), int(v)), f"set_option({kv})")
     _L = L
     return L
 

@@ -173,22 +173,55 @@ def test_params_repack_on_update(model):
     torch.testing.assert_close(a, c, rtol=1e-3, atol=1e-5)
 
 
-def test_density_modes_agree(pkg, model):
-    """The staged density evaluation (mode 1, default) and the single fused kernel (mode 0) run the
-    same arithmetic: sigma / geo / rendered outputs agree to fp16-tile rounding."""
+@pytest.mark.parametrize("t", [0.37, 0.0, 1.0])
+def test_density_modes_agree(pkg, model, t):
+    """The staged density evaluation (mode 1), its variant with the dynamic 2-D hash tables staged
+    in shared memory (mode 2: fp16 table copies, k_dyn_stage) and the single fused kernel (mode 0)
+    run the same arithmetic: features / sigma / geo / rendered outputs agree to fp16 rounding.
+    t = 0 and t = 1 exercise the first/last-frame aliasing of the warped queries."""
     L = pkg._lib.lib()
-    x = torch.from_numpy(pts(3000, 11)).cuda()
+    x = torch.from_numpy(pts(40000, 11)).cuda()
     o, d = S.lidar_rays(300, seed=4)
     to, td = torch.from_numpy(o).cuda()[None], torch.from_numpy(d).cuda()[None]
     res = {}
+    prev = L.nvsf_density_mode_get()
     try:
-        for mode in (0, 1):
+        for mode in (0, 1, 2):
             assert L.nvsf_set_option(b"density_mode", mode) == 0
-            den = model.density(x, 0.37, True)
-            r = model.render(to, td, torch.tensor([[0.37]], device="cuda"), cal_lidar_color=True, num_steps=96)
-            res[mode] = (host(den["sigma"]), host(den["geo_feat"]), host(r["depth_lidar"]), host(r["image_lidar"]))
+            den = model.density(x, t, True)
+            feats, _ = model.features(x, t, True)
+            r = model.render(to, td, torch.tensor([[t]], device="cuda"), cal_lidar_color=True, num_steps=96)
+            res[mode] = (host(den["sigma"]), host(den["geo_feat"]), host(r["depth_lidar"]), host(r["image_lidar"]),
+                         host(feats))
     finally:
-        L.nvsf_set_option(b"density_mode", 1)
+        L.nvsf_set_option(b"density_mode", prev)
     assert L.nvsf_set_option(b"density_mode", 7) == -1 and L.nvsf_set_option(b"nope", 0) == -1
-    for a, b, name in zip(res[0], res[1], ("sigma", "geo", "depth", "image")):
-        close(a, b, 2e-3, 2e-3 * np.abs(b).max(), name)
+    for mode in (0, 2):
+        for a, b, name in zip(res[mode], res[1], ("sigma", "geo", "depth", "image", "features")):
+            close(a, b, 2e-3, 2e-3 * np.abs(b).max(), f"mode {mode} {name}")
+    # the static blocks do not depend on the mode at all
+    assert np.array_equal(res[2][4][:, :96], res[1][4][:, :96])
+
+
+def test_dyn_stage_tiles_and_chunks(pkg, model):
+    """Mode 2 with small work items and chunks (several tiles per table type, several chunks per
+    call, a ragged tail) equals mode 2 with the defaults bit for bit, for explicit points and for
+    the ray path."""
+    L = pkg._lib.lib()
+    x = torch.from_numpy(pts(150001, 5)).cuda()
+    o, d = S.lidar_rays(700, seed=9)
+    to, td = torch.from_numpy(o).cuda()[None], torch.from_numpy(d).cuda()[None]
+    prev = L.nvsf_density_mode_get()
+    out = []
+    try:
+        assert L.nvsf_set_option(b"density_mode", 2) == 0
+        for tile, chunk in ((8192, 64), (1024, 1)):
+            assert L.nvsf_set_option(b"dyn_tile", tile) == 0 and L.nvsf_set_option(b"split_chunk", chunk) == 0
+            den = model.density(x, 0.6, False)
+            r = model.render(to, td, torch.tensor([[0.6]], device="cuda"), cal_lidar_color=True, num_steps=128)
+            out.append((host(den["sigma"]), host(den["geo_feat"]), host(r["depth_lidar"]), host(r["image_lidar"])))
+    finally:
+        L.nvsf_set_option(b"dyn_tile", 8192); L.nvsf_set_option(b"split_chunk", 64)
+        L.nvsf_set_option(b"density_mode", prev)
+    for a, b in zip(*out):
+        assert np.array_equal(a, b)
