@@ -28,6 +28,8 @@ sys.path.insert(0, ROOT)
 METRIC = "lidar_frame_render_rays_per_sec"
 UNIT = "rays/s"
 NUM_STEPS = 768
+WORKLOAD = ("KITTI-360-shaped LiDAR range image 66x1030 full-frame render (depth/intensity/raydrop), "
+            "768 uniform samples/ray, random-init NVSF field (BASELINE configs[1])")
 # algorithmic bytes the density kernel must move per sample ("density kernel"):
 #   static hash 8 lvl x 8 corners x 8 B                         =  512
 #   collapsed dynamic hash 3 queries x 3 planes x 8 lvl x 4 x 4 B = 1152
@@ -37,10 +39,23 @@ NUM_STEPS = 768
 #   outputs sigma f32 + geo f16[16]                             =   36
 DENSITY_BYTES_PER_SAMPLE = 512 + 1152 + 1024 + 1536 + 2304 + 36
 SURVEY_BYTES_PER_SAMPLE = 13312 + 48  # the reference's un-collapsed gathers
-# The dominant kernel is the gather stage k_encode_stage: everything above except the
-# flow grid (flow stage) and the outputs (sigma stage), plus its own streams: flow in (8 x f32 = 32 B)
-# and the 128 fp16 sigma-net inputs out (256 B).
-ENCODE_BYTES_PER_SAMPLE = 512 + 1152 + 1536 + 2304 + 32 + 256
+# Per-stage algorithmic bytes per sample of the staged density evaluation; the
+# roofline object describes whichever stage took the largest share of the timed steps.
+#   mode 1 (fp32 collapsed tables):  flow stage  = flow grid 16 x 8 x 8 B + 32 B flow out
+#                                    encode stage = static hash 512 + collapsed dyn hash 1152 + space planes
+#                                                   1536 + time planes 2304 + flow in 32 + feature row out 256
+#   mode 2 (fp16 mirrors, default):  flow stage  = 16 x 8 x 4 B + 32
+#                                    dyn stage   = 288 two-byte gathers from shared-memory tables (576) +
+#                                                  flow in 32 + 24 fp16 values out 48
+#                                    encode stage = static hash 512 + fp16 space planes 768 + fp16 time planes
+#                                                   1152 + dyn in 48 + flow in 32 + feature row out 256
+#   sigma stage (both)               = feature row in 256 + sigma f32 + geo f16[16] out 36
+STAGE_BYTES = {
+    1: {"flow_stage": 1024 + 32, "dyn_stage": 0, "encode_stage": 512 + 1152 + 1536 + 2304 + 32 + 256, "sigma_stage": 256 + 36},
+    2: {"flow_stage": 512 + 32, "dyn_stage": 576 + 32 + 48, "encode_stage": 512 + 768 + 1152 + 48 + 32 + 256, "sigma_stage": 256 + 36},
+}
+STAGE_KERNEL = {"flow_stage": "k_flow_stage", "dyn_stage": "k_dyn_stage", "encode_stage": "k_encode_stage",
+                "sigma_stage": "k_sigma_stage"}
 
 
 def peaks():
@@ -146,8 +161,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "KITTI-360-shaped LiDAR range image 66x1030 full-frame render, 768 samples/ray",
-                   "rays": 67980, "samples_per_ray": NUM_STEPS},
+        "config": {"workload": WORKLOAD, "rays_per_gpu": 67980, "samples_per_ray": NUM_STEPS,
+                   "parallelism": "host cores of rank 0"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -439,20 +454,24 @@ def main():
     n_samples = N * Sn
     n_launch = max(int(stage_launches.value), 1)            # chunks of the staged evaluation, all timed steps
     flow_ms, dyn_ms, enc_ms, sig_ms = (float(stage_ms[i]) / args.steps for i in range(4))
-    enc_launch_ms = float(stage_ms[2]) / n_launch            # average duration of one k_encode_stage launch
+    mode = int(L.nvsf_density_mode_get())
+    stage_step_ms = {"flow_stage": flow_ms, "dyn_stage": dyn_ms, "encode_stage": enc_ms, "sigma_stage": sig_ms}
+    top = max(stage_step_ms, key=stage_step_ms.get)          # the dominant kernel of the step
+    top_bytes = STAGE_BYTES.get(mode, STAGE_BYTES[1])[top]
+    top_launch_ms = stage_step_ms[top] * args.steps / n_launch   # average duration of one launch of it
     samples_per_launch = n_samples * args.steps / n_launch
-    achieved = ENCODE_BYTES_PER_SAMPLE * samples_per_launch / (enc_launch_ms * 1e-3) / 1e9
+    achieved = top_bytes * samples_per_launch / (top_launch_ms * 1e-3) / 1e9
     traffic, limiter = None, None
-    tr_path = os.path.join(ROOT, "profiles", "encode_stage_ncu.json")
+    tr_path = os.path.join(ROOT, "profiles", "dominant_stage_ncu.json")
     if os.path.exists(tr_path):   # from the committed ncu --set full capture of this command
-        tr = json.load(open(tr_path))
+        tr = json.load(open(tr_path)).get(f"mode{mode}", {}).get(top, {})
         traffic, limiter = tr.get("dram_bytes_per_launch"), tr.get("limiter")
+    kernels_per_chunk = 4 if mode == 2 else 3
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f16", "data": "synthetic",
-        "config": {"workload": "KITTI-360-shaped LiDAR range image 66x1030 full-frame render (depth/intensity/raydrop), "
-                               "768 uniform samples/ray, random-init NVSF field (BASELINE configs[1])",
+        "config": {"workload": WORKLOAD,
                    "rays_per_gpu": N, "samples_per_ray": Sn, "parallelism": f"rays x{world} (one frame per GPU, no collective)",
                    "l2": "per-step working set 1.9 GB of per-sample scratch + 128 MB tables exceeds the 126 MB L2; no flush",
                    "kernel_ms": {"field_density": dens_ms, "flow_stage": flow_ms, "dyn_stage": dyn_ms, "encode_stage": enc_ms,
@@ -460,12 +479,14 @@ def main():
                                  "time_collapse_and_gaps": ms_total / args.steps - dens_ms - comp_ms}},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(2 * N * 3 * 4), "d2h_bytes_per_step": int(N * 3 * 4)},
-        "gpu_launches": (9 + 1 + 3 * n_launch // args.steps) * args.steps,
-        "roofline": {"bound": "hbm", "kernel": "k_encode_stage", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+        "gpu_launches": (9 + 1 + kernels_per_chunk * n_launch // args.steps) * args.steps,
+        "roofline": {"bound": "hbm", "kernel": STAGE_KERNEL[top], "density_mode": mode, "achieved": achieved,
+                     "peak": pk["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk_kind,
-                     "bytes_per_sample": ENCODE_BYTES_PER_SAMPLE, "survey_bytes_per_sample": SURVEY_BYTES_PER_SAMPLE,
-                     "samples_per_launch": samples_per_launch, "launch_ms": enc_launch_ms,
-                     "launches_per_step": n_launch / args.steps, "share_of_step": enc_ms / (ms_total / args.steps),
+                     "bytes_per_sample": top_bytes, "survey_bytes_per_sample": SURVEY_BYTES_PER_SAMPLE,
+                     "samples_per_launch": samples_per_launch, "launch_ms": top_launch_ms,
+                     "launches_per_step": n_launch / args.steps,
+                     "share_of_step": stage_step_ms[top] / (ms_total / args.steps),
                      "limiter": limiter,
                      "note": "algorithmic bytes are table gathers; the 75 MB of tables are L2 resident, so the "
                              "achieved figure may exceed the HBM peak while DRAM traffic stays far below it"},

@@ -84,7 +84,8 @@ struct PlaneSrc {  // offsets (floats) of the reference's [1,8,H,W] tensors insi
 
 // space planes (combinations xy, xz, yz) [8][R][R] -> channel-last [R][R][8]
 __global__ void k_pack_planes_static(const float* __restrict__ planes, PlaneSrc src,
-                                     uint32_t res, uint32_t scale, float* __restrict__ dst) {
+                                     uint32_t res, uint32_t scale, float* __restrict__ dst,
+                                     __half* __restrict__ dst16) {
     const uint32_t combo = blockIdx.y == 0 ? 0u : (blockIdx.y == 1 ? 1u : 3u);
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= res * res) return;
@@ -95,13 +96,16 @@ __global__ void k_pack_planes_static(const float* __restrict__ planes, PlaneSrc 
     float4* d = reinterpret_cast<float4*>(dst + ((size_t)blockIdx.y * res * res + i) * 8);
     d[0] = make_float4(v[0], v[1], v[2], v[3]);
     d[1] = make_float4(v[4], v[5], v[6], v[7]);
+    reinterpret_cast<uint4*>(dst16)[(size_t)blockIdx.y * res * res + i] =
+        make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]),
+                   pack_half2(v[6], v[7]));
 }
 
 // time planes (combinations xt, yt, zt) [8][Tres][R] -> per query: time-blended rows [R][8]
 __global__ void k_collapse_planes_dyn(const float* __restrict__ planes, PlaneSrc src,
                                       uint32_t res, uint32_t tres, uint32_t scale,
                                       const TimeInfo* __restrict__ ti, float* __restrict__ dst,
-                                      size_t per_q) {
+                                      __half* __restrict__ dst16, size_t per_q) {
     const uint32_t p = blockIdx.y, q = blockIdx.z;
     const uint32_t combo = p == 0 ? 2u : (p == 1 ? 4u : 5u);
     const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -119,6 +123,9 @@ __global__ void k_collapse_planes_dyn(const float* __restrict__ planes, PlaneSrc
     float4* d = reinterpret_cast<float4*>(dst + q * per_q + ((size_t)p * res + x) * 8);
     d[0] = make_float4(v[0], v[1], v[2], v[3]);
     d[1] = make_float4(v[4], v[5], v[6], v[7]);
+    *reinterpret_cast<uint4*>(dst16 + q * per_q + ((size_t)p * res + x) * 8) =
+        make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]),
+                   pack_half2(v[6], v[7]));
 }
 
 // dynamic hash: out[q][e] = sum_i lag[q][i] * ((k2-idx) * G[k1][e][i] + (idx-k1) * G[k2][e][i])
@@ -156,7 +163,7 @@ __global__ void k_collapse_dyn(const float* __restrict__ slices /* [Tres][entrie
 // flow grid: out[e][c] = sum_i lag[0][i] * F[e][2i+c]   (FlowField.interpT, flow_field.py:105-114)
 __global__ void k_collapse_flow(const float* __restrict__ grid /* [entries][8] */,
                                 uint32_t entries, const TimeInfo* __restrict__ ti,
-                                float2* __restrict__ dst) {
+                                float2* __restrict__ dst, __half2* __restrict__ dst16) {
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= entries) return;
     const float4 a = __ldcs(reinterpret_cast<const float4*>(grid) + 2 * (size_t)e);
@@ -166,6 +173,7 @@ __global__ void k_collapse_flow(const float* __restrict__ grid /* [entries][8] *
     o.x = l0 * round_h(a.x) + l1 * round_h(a.z) + l2 * round_h(b.x) + l3 * round_h(b.z);
     o.y = l0 * round_h(a.y) + l1 * round_h(a.w) + l2 * round_h(b.y) + l3 * round_h(b.w);
     dst[e] = o;
+    dst16[e] = __floats2half2_rn(o.x, o.y);
 }
 
 // fp32 [rows][src_ld] sub-block -> fp16 [rows][dst_ld] sub-block
@@ -448,6 +456,9 @@ FieldPtrs nvsf_make_field_ptrs(const nvsf_field_config_t* cfg, const void* works
     P.pls = reinterpret_cast<const float*>(w + L.pls);
     P.dyn = reinterpret_cast<const float*>(w + L.dyn);
     P.dyn16 = reinterpret_cast<const __half*>(w + L.dyn16);
+    P.pls16 = reinterpret_cast<const __half*>(w + L.pls16);
+    P.pld16 = reinterpret_cast<const __half*>(w + L.pld16);
+    P.flow16 = reinterpret_cast<const __half2*>(w + L.flow16);
     P.flow = reinterpret_cast<const float2*>(w + L.flow);
     P.pld = reinterpret_cast<const float*>(w + L.pld);
     P.mlp = reinterpret_cast<const __half*>(w + L.mlp);
@@ -524,7 +535,8 @@ int nvsf_field_pack_params(const nvsf_field_config_t* cfg, const nvsf_field_para
         const uint32_t R = cfg->pl_res[sc];
         dim3 grid(nvsf_div_up(R * R, 256u), 3);
         k_pack_planes_static<<<grid, 256, 0, s>>>(
-            prm->planes, src, R, sc, reinterpret_cast<float*>(w + L.pls) + L.pls_scale[sc]);
+            prm->planes, src, R, sc, reinterpret_cast<float*>(w + L.pls) + L.pls_scale[sc],
+            reinterpret_cast<__half*>(w + L.pls16) + L.pls_scale[sc]);
     }
     // MLP weights -> fp16 shared-memory images
     __half* m = reinterpret_cast<__half*>(w + L.mlp);
@@ -578,7 +590,8 @@ int nvsf_field_pack_time(const nvsf_field_config_t* cfg, const nvsf_field_params
     }
     // flow grid
     k_collapse_flow<<<nvsf_div_up(cfg->fl_entries, 256u), 256, 0, s>>>(
-        prm->flow_grid, cfg->fl_entries, ti, reinterpret_cast<float2*>(w + L.flow));
+        prm->flow_grid, cfg->fl_entries, ti, reinterpret_cast<float2*>(w + L.flow),
+        reinterpret_cast<__half2*>(w + L.flow16));
     // time planes
     const PlaneSrc src = make_plane_src(cfg);
     for (int sc = 0; sc < kPlScales; ++sc) {
@@ -586,7 +599,8 @@ int nvsf_field_pack_time(const nvsf_field_config_t* cfg, const nvsf_field_params
         dim3 grid(nvsf_div_up(R, 128u), 3, 3);
         k_collapse_planes_dyn<<<grid, 128, 0, s>>>(
             prm->planes, src, R, cfg->time_resolution, sc, ti,
-            reinterpret_cast<float*>(w + L.pld) + L.pld_scale[sc], L.pld_floats_per_q);
+            reinterpret_cast<float*>(w + L.pld) + L.pld_scale[sc],
+            reinterpret_cast<__half*>(w + L.pld16) + L.pld_scale[sc], L.pld_floats_per_q);
     }
     return nvsf_launch_status();
 }
@@ -603,7 +617,7 @@ int nvsf_field_density(const nvsf_field_config_t* cfg, const void* workspace, co
                                sigma, geo, features, flow, scratch, (cudaStream_t)stream);
 }
 
-static int g_density_mode_value = 1;
+static int g_density_mode_value = 2;
 static int g_march_mode_value = 1;
 int nvsf_set_option(const char* name, int value) {
     if (!name) return NVSF_E_INVALID;

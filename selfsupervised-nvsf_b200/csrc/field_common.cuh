@@ -36,6 +36,9 @@ struct WsLayout {
     size_t pld;       // float  [3 queries] per scale: [3 planes xt,yt,zt][R][8]
     size_t mlp;       // __half smem images of the MLP weights
     size_t dyn16;     // __half [3 queries][sum_p hd_entries[p]]    fp16 mirror of dyn (shared-memory staging)
+    size_t pls16;     // __half mirror of pls (same element offsets): one 16-byte texel
+    size_t pld16;     // __half mirror of pld
+    size_t flow16;    // __half2 [fl_entries]                       fp16 mirror of flow
     size_t total;
     size_t pls_scale[NVSF_MAX_PLANE_SCALES];  // float offsets inside pls
     size_t pld_scale[NVSF_MAX_PLANE_SCALES];  // float offsets inside one query of pld
@@ -100,6 +103,9 @@ static inline WsLayout make_ws_layout(const nvsf_field_config_t* c) {
     L.pld = off; off = ws_align(off + 3 * g * sizeof(float));
     L.mlp = off; off = ws_align(off + (size_t)kMlpHalves * sizeof(__half));
     L.dyn16 = off; off = ws_align(off + 3 * d * sizeof(__half));
+    L.pls16 = off; off = ws_align(off + f * sizeof(__half));
+    L.pld16 = off; off = ws_align(off + 3 * g * sizeof(__half));
+    L.flow16 = off; off = ws_align(off + (size_t)c->fl_entries * sizeof(__half2));
     L.total = off;
     return L;
 }
@@ -110,6 +116,9 @@ struct FieldPtrs {
     const float* pls;
     const float* dyn;
     const __half* dyn16;
+    const __half* pls16;
+    const __half* pld16;
+    const __half2* flow16;
     const float2* flow;
     const float* pld;
     const __half* mlp;
@@ -363,6 +372,52 @@ __device__ __forceinline__ void plane1d_mul(const float* __restrict__ base, uint
     }
 }
 
+// fp16 mirrors of the plane tables: one texel = 8 halves = one 16-byte load (half the register
+// write-back bytes of the fp32 texel, which is what bounds the gather stage: ncu
+// l1tex__data_pipe_lsu_wavefronts 89 %, profiles/r01_dyn_encode_ncu.txt).  Interpolation in fp32.
+__device__ __forceinline__ void ld8h(const __half* p, float (&v)[8]) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(p));
+    const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&a.x));
+    const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&a.y));
+    const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&a.z));
+    const float2 f3 = __half22float2(*reinterpret_cast<const __half2*>(&a.w));
+    v[0] = f0.x; v[1] = f0.y; v[2] = f1.x; v[3] = f1.y;
+    v[4] = f2.x; v[5] = f2.y; v[6] = f3.x; v[7] = f3.y;
+}
+__device__ __forceinline__ void plane2d_mul_h(const __half* __restrict__ base, uint32_t R, float pa,
+                                              float pb, float (&out)[8], bool first) {
+    uint32_t x0, x1, y0, y1;
+    float wx, wy;
+    plane_coord(pa, R, x0, x1, wx);
+    plane_coord(pb, R, y0, y1, wy);
+    float a[8], b[8], c[8], d[8];
+    ld8h(base + ((size_t)y0 * R + x0) * 8, a);
+    ld8h(base + ((size_t)y0 * R + x1) * 8, b);
+    ld8h(base + ((size_t)y1 * R + x0) * 8, c);
+    ld8h(base + ((size_t)y1 * R + x1) * 8, d);
+    const float w00 = (1.f - wx) * (1.f - wy), w01 = wx * (1.f - wy), w10 = (1.f - wx) * wy,
+                w11 = wx * wy;
+#pragma unroll
+    for (int f = 0; f < 8; ++f) {
+        const float s = w00 * a[f] + w01 * b[f] + w10 * c[f] + w11 * d[f];
+        out[f] = first ? s : out[f] * s;
+    }
+}
+__device__ __forceinline__ void plane1d_mul_h(const __half* __restrict__ base, uint32_t R, float pa,
+                                              float (&out)[8], bool first) {
+    uint32_t x0, x1;
+    float wx;
+    plane_coord(pa, R, x0, x1, wx);
+    float a[8], b[8];
+    ld8h(base + (size_t)x0 * 8, a);
+    ld8h(base + (size_t)x1 * 8, b);
+#pragma unroll
+    for (int f = 0; f < 8; ++f) {
+        const float s = (1.f - wx) * a[f] + wx * b[f];
+        out[f] = first ? s : out[f] * s;
+    }
+}
+
 // (Measured and rejected on B200: fetching the two x-corners of a cell edge with one double-width
 // load when their indices differ only in bit 0 — true for every even cx on a hashed level — cuts
 // a quarter of the L1 wavefronts but the select/branch overhead made the gather stage 18 % slower.)
@@ -426,6 +481,30 @@ __device__ __forceinline__ float2 hash3_f2(const float2* __restrict__ tab, const
                         ((c & 4) ? wz : 1.f - wz);
         a0 = fmaf(w, v[c].x, a0);
         a1 = fmaf(w, v[c].y, a1);
+    }
+    return make_float2(a0, a1);
+}
+
+// same from the fp16 mirror (4-byte entries: half the L2 footprint and register write-back)
+__device__ __forceinline__ float2 hash3_h2(const __half2* __restrict__ tab, const LevelArgs& L,
+                                           float x, float y, float z) {
+    uint32_t cx, cy, cz;
+    float wx, wy, wz;
+    grid_pos(L.scale, x, cx, wx);
+    grid_pos(L.scale, y, cy, wy);
+    grid_pos(L.scale, z, cz, wz);
+    __half2 v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        v[c] = __ldg(tab + L.offset + idx3(L, cx + (c & 1), cy + ((c >> 1) & 1), cz + (c >> 2)));
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const float w = ((c & 1) ? wx : 1.f - wx) * ((c & 2) ? wy : 1.f - wy) *
+                        ((c & 4) ? wz : 1.f - wz);
+        const float2 f = __half22float2(v[c]);
+        a0 = fmaf(w, f.x, a0);
+        a1 = fmaf(w, f.y, a1);
     }
     return make_float2(a0, a1);
 }

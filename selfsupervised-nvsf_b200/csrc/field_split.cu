@@ -44,8 +44,16 @@ __device__ __forceinline__ void sample_position(const nvsf_field_config_t& cfg, 
                                                 float& x, float& y, float& z) {
     float px, py, pz;
     if (FROM_RAYS) {
-        const size_t r = g / S;
-        const uint32_t k = (uint32_t)(g - r * S);
+        size_t r;
+        uint32_t k;
+        if ((g >> 32) == 0) {  // 32-bit division: the 64-bit one costs ~100 instructions per call
+            const uint32_t g32 = (uint32_t)g, r32 = g32 / S;
+            r = r32;
+            k = g32 - r32 * S;
+        } else {
+            r = g / S;
+            k = (uint32_t)(g - r * S);
+        }
         const float zz = uniform_z(__ldg(nears + r), __ldg(fars + r), k, S, noise, g);
         px = __ldg(rays_o + r * 3 + 0) + __ldg(rays_d + r * 3 + 0) * zz;
         py = __ldg(rays_o + r * 3 + 1) + __ldg(rays_d + r * 3 + 1) * zz;
@@ -61,7 +69,7 @@ __device__ __forceinline__ void sample_position(const nvsf_field_config_t& cfg, 
 }
 
 // ---- stage 1: flow -----------------------------------------------------------------------------
-template <bool FROM_RAYS>
+template <bool FROM_RAYS, bool TAB16>
 __global__ void __launch_bounds__(kSTile, 2)
 k_flow_stage(const __grid_constant__ nvsf_field_config_t cfg, const __grid_constant__ FieldPtrs P,
              const float* __restrict__ xin, const float* __restrict__ rays_o,
@@ -87,7 +95,8 @@ k_flow_stage(const __grid_constant__ nvsf_field_config_t cfg, const __grid_const
                                        x, y, z);
 #pragma unroll 2
         for (int l = 0; l < kFlLevels; ++l) {
-            const float2 f = hash3_f2(P.flow, lv(cfg.fl[l]), x, y, z);
+            const float2 f = TAB16 ? hash3_h2(P.flow16, lv(cfg.fl[l]), x, y, z)
+                                   : hash3_f2(P.flow, lv(cfg.fl[l]), x, y, z);
             *reinterpret_cast<uint32_t*>(xrow + 2 * l) = pack_half2(f.x, f.y);
         }
         if (flowfeat_out && live) {  // kept for the backward pass (input of the flow MLP)
@@ -167,6 +176,37 @@ k_encode_stage(const __grid_constant__ nvsf_field_config_t cfg,
     qz[2] = valid2 ? z + f1.y : z; qi[2] = valid2 ? 2 : 0;
     __half* row = feat_out + li * kFeat;
 
+    // (a) space planes -> [0,32), (b) collapsed time planes -> [32,64); with DYN_PRE (mode 2) from
+    // the fp16 texel mirrors (one 16-byte load per texel)
+    if constexpr (DYN_PRE) {
+#pragma unroll 1
+        for (int s = 0; s < kPlScales; ++s) {
+            const uint32_t R = cfg.pl_res[s];
+            const __half* base = P.pls16 + P.pls_scale[s];
+            float v[8];
+            plane2d_mul_h(base, R, x, y, v, true);
+            plane2d_mul_h(base + (size_t)R * R * 8, R, x, z, v, false);
+            plane2d_mul_h(base + (size_t)2 * R * R * 8, R, y, z, v, false);
+            st8g(row, 8 * s, v);
+        }
+#pragma unroll 1
+        for (int s = 0; s < kPlScales; ++s) {
+            const uint32_t R = cfg.pl_res[s];
+            float acc8[8];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const __half* base = P.pld16 + (size_t)qi[q] * P.pld_per_q + P.pld_scale[s];
+                float v[8];
+                plane1d_mul_h(base, R, qx[q], v, true);
+                plane1d_mul_h(base + (size_t)R * 8, R, qy[q], v, false);
+                plane1d_mul_h(base + (size_t)2 * R * 8, R, qz[q], v, false);
+                const float wq = q == 0 ? 0.5f : 0.25f;
+#pragma unroll
+                for (int f = 0; f < 8; ++f) acc8[f] = q == 0 ? wq * v[f] : fmaf(wq, v[f], acc8[f]);
+            }
+            st8g(row, 32 + 8 * s, acc8);
+        }
+    } else {
     // (a) space planes -> [0,32)
 #pragma unroll 1
     for (int s = 0; s < kPlScales; ++s) {
@@ -195,6 +235,7 @@ k_encode_stage(const __grid_constant__ nvsf_field_config_t cfg,
             for (int f = 0; f < 8; ++f) acc8[f] = q == 0 ? wq * v[f] : fmaf(wq, v[f], acc8[f]);
         }
         st8g(row, 32 + 8 * s, acc8);
+    }
     }
     // (c) static 3-D hash -> [64,96)
 #pragma unroll 1
@@ -332,8 +373,9 @@ __device__ __forceinline__ float hash2_sm(const __half* __restrict__ tab, const 
     }
     const float t00 = __half2float(tab[i00]), t10 = __half2float(tab[i10]);
     const float t01 = __half2float(tab[i01]), t11 = __half2float(tab[i11]);
-    return (1.f - wu) * (1.f - wv) * t00 + wu * (1.f - wv) * t10 + (1.f - wu) * wv * t01 +
-           wu * wv * t11;
+    // nested-lerp form (6 instead of 11 floating-point instructions; this kernel is issue bound)
+    const float a = fmaf(wu, t10 - t00, t00), b = fmaf(wu, t11 - t01, t01);
+    return fmaf(wv, b - a, a);
 }
 template <bool HASHED>
 __device__ __forceinline__ float dyn_combo(const __half* __restrict__ t0, const LevelArgs& L,
@@ -562,10 +604,16 @@ bool g_attr = false;
 int ensure_attrs() {
     if (g_attr) return NVSF_OK;
     cudaError_t e;
-    e = cudaFuncSetAttribute(k_flow_stage<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    e = cudaFuncSetAttribute(k_flow_stage<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)kFlowStageSmem);
     if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(k_flow_stage<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    e = cudaFuncSetAttribute(k_flow_stage<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)kFlowStageSmem);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(k_flow_stage<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)kFlowStageSmem);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(k_flow_stage<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)kFlowStageSmem);
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(k_sigma_stage, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -640,8 +688,12 @@ int nvsf_launch_density_split(const nvsf_field_config_t* cfg, const void* worksp
         const unsigned short* dyn_in = reinterpret_cast<const unsigned short*>(dyn_buf);
         if (g_prof.on) g_prof.next(stream);
         if (x) {
-            k_flow_stage<false><<<grid_p, kSTile, kFlowStageSmem, stream>>>(
-                *cfg, P, x, nullptr, nullptr, nullptr, nullptr, nullptr, 1, begin, count, flow_buf, ff);
+            if (dyn_pre)
+                k_flow_stage<false, true><<<grid_p, kSTile, kFlowStageSmem, stream>>>(
+                    *cfg, P, x, nullptr, nullptr, nullptr, nullptr, nullptr, 1, begin, count, flow_buf, ff);
+            else
+                k_flow_stage<false, false><<<grid_p, kSTile, kFlowStageSmem, stream>>>(
+                    *cfg, P, x, nullptr, nullptr, nullptr, nullptr, nullptr, 1, begin, count, flow_buf, ff);
             if (g_prof.on) g_prof.next(stream);
             if (dyn_pre)
                 k_dyn_stage<false><<<grid_d, kDynThreads, kDynTableBytes, stream>>>(
@@ -657,8 +709,12 @@ int nvsf_launch_density_split(const nvsf_field_config_t* cfg, const void* worksp
                     *cfg, P, x, nullptr, nullptr, nullptr, nullptr, nullptr, 1, begin, count, flow_buf,
                     feat_buf, nullptr, 0);
         } else {
-            k_flow_stage<true><<<grid_p, kSTile, kFlowStageSmem, stream>>>(
-                *cfg, P, nullptr, rays_o, rays_d, nears, fars, noise, S, begin, count, flow_buf, ff);
+            if (dyn_pre)
+                k_flow_stage<true, true><<<grid_p, kSTile, kFlowStageSmem, stream>>>(
+                    *cfg, P, nullptr, rays_o, rays_d, nears, fars, noise, S, begin, count, flow_buf, ff);
+            else
+                k_flow_stage<true, false><<<grid_p, kSTile, kFlowStageSmem, stream>>>(
+                    *cfg, P, nullptr, rays_o, rays_d, nears, fars, noise, S, begin, count, flow_buf, ff);
             if (g_prof.on) g_prof.next(stream);
             if (dyn_pre)
                 k_dyn_stage<true><<<grid_d, kDynThreads, kDynTableBytes, stream>>>(

@@ -147,7 +147,8 @@ def test_full_lidar_frame_properties(model, orc):
     assert set(full) == {"depth_lidar", "image_lidar"} and full["depth_lidar"].shape == (1, 67980)
     img = host(full["image_lidar"])[0]
     assert np.isfinite(img).all() and (img >= 0).all() and (img <= 1).all()
-    sub = model.render(to[:, 5000:9096], td[:, 5000:9096], t, cal_lidar_color=True, staged=False, num_steps=128)
+    with torch.no_grad():   # same (inference) kernels as the staged render; with autograd on, run() takes the training forward
+        sub = model.render(to[:, 5000:9096], td[:, 5000:9096], t, cal_lidar_color=True, staged=False, num_steps=128)
     np.testing.assert_allclose(host(sub["depth_lidar"]), host(full["depth_lidar"])[:, 5000:9096], rtol=1e-6, atol=1e-7)
     np.testing.assert_allclose(host(sub["image_lidar"]), host(full["image_lidar"])[:, 5000:9096], rtol=1e-6, atol=1e-7)
     ws = host(sub["weights_sum_lidar"]); w = host(sub["weights"])
@@ -199,8 +200,8 @@ def test_density_modes_agree(pkg, model, t):
     for mode in (0, 2):
         for a, b, name in zip(res[mode], res[1], ("sigma", "geo", "depth", "image", "features")):
             close(a, b, 2e-3, 2e-3 * np.abs(b).max(), f"mode {mode} {name}")
-    # the static blocks do not depend on the mode at all
-    assert np.array_equal(res[2][4][:, :96], res[1][4][:, :96])
+    # the static hash block does not depend on the mode at all (mode 2 reads the planes from fp16 texels)
+    assert np.array_equal(res[2][4][:, 64:96], res[1][4][:, 64:96])
 
 
 def test_dyn_stage_tiles_and_chunks(pkg, model):
