@@ -418,11 +418,56 @@ __device__ __forceinline__ void plane1d_mul_h(const __half* __restrict__ base, u
     }
 }
 
-// (Measured and rejected on B200: fetching the two x-corners of a cell edge with one double-width
-// load when their indices differ only in bit 0 — true for every even cx on a hashed level — cuts
-// a quarter of the L1 wavefronts but the select/branch overhead made the gather stage 18 % slower.)
+// Paired variant of hash3_f4 for hashed levels: the hash multiplies x by 1, so for even cx the two
+// x-corners of a cell edge are the entries i0 and i0 ^ 1 — one aligned 16-byte load fetches both;
+// odd cx needs a second, predicated 8-byte load (half of the lanes on a fine level).  Per edge the
+// L1 sees ~1.5 divergent requests instead of 2.  (First measured when the gather stage was
+// instruction bound — 18 % slower; it is L1-data-pipe bound since the fp16 texel mirrors.)
+__device__ __forceinline__ void hash3_f4_pair(const uint2* __restrict__ tab, const LevelArgs& L,
+                                              float x, float y, float z, float* out) {
+    uint32_t cx, cy, cz;
+    float wx, wy, wz;
+    grid_pos(L.scale, x, cx, wx);
+    grid_pos(L.scale, y, cy, wy);
+    grid_pos(L.scale, z, cz, wz);
+    const uint32_t m = L.size - 1;
+    const bool odd = cx & 1u;
+    const uint2* base = tab + L.offset;
+    uint2 v[8];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const uint32_t h = ((cy + (e & 1)) * 2654435761u) ^ ((cz + (e >> 1)) * 805459861u);
+        const uint32_t i0 = (cx ^ h) & m;
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(base + (i0 & ~1u)));
+        const bool hi = i0 & 1u;
+        v[2 * e] = hi ? make_uint2(q.z, q.w) : make_uint2(q.x, q.y);
+        uint2 nb = hi ? make_uint2(q.x, q.y) : make_uint2(q.z, q.w);
+        if (odd) nb = __ldg(base + (((cx + 1) ^ h) & m));
+        v[2 * e + 1] = nb;
+    }
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const float w = ((c & 1) ? wx : 1.f - wx) * ((c & 2) ? wy : 1.f - wy) *
+                        ((c & 4) ? wz : 1.f - wz);
+        const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&v[c].x));
+        const float2 hi2 = __half22float2(*reinterpret_cast<const __half2*>(&v[c].y));
+        a0 = fmaf(w, lo.x, a0); a1 = fmaf(w, lo.y, a1);
+        a2 = fmaf(w, hi2.x, a2); a3 = fmaf(w, hi2.y, a3);
+    }
+    out[0] = a0; out[1] = a1; out[2] = a2; out[3] = a3;
+}
+
+// 8-byte read-only load that does not allocate in L1: the fine hashed levels never hit there (4 MB
+// of random entries per level) and would only evict the plane texels and coarse levels that do
+__device__ __forceinline__ uint2 ldg_na(const uint2* p) {
+    uint2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];\n" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
 
 // one level of the 3-D fp16 static hash grid (4 features)
+template <bool NOALLOC = false>
 __device__ __forceinline__ void hash3_f4(const uint2* __restrict__ tab, const LevelArgs& L,
                                          float x, float y, float z, float* out) {
     uint32_t cx, cy, cz;
@@ -432,8 +477,10 @@ __device__ __forceinline__ void hash3_f4(const uint2* __restrict__ tab, const Le
     grid_pos(L.scale, z, cz, wz);
     uint2 v[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c)
-        v[c] = __ldg(tab + L.offset + idx3(L, cx + (c & 1), cy + ((c >> 1) & 1), cz + (c >> 2)));
+    for (int c = 0; c < 8; ++c) {
+        const uint2* p = tab + L.offset + idx3(L, cx + (c & 1), cy + ((c >> 1) & 1), cz + (c >> 2));
+        v[c] = NOALLOC ? ldg_na(p) : __ldg(p);
+    }
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
     for (int c = 0; c < 8; ++c) {

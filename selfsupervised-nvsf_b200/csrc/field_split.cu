@@ -31,7 +31,8 @@ constexpr int kFld = 56;      // flow-stage tile row: 32 features + 8 fp32 flow 
 constexpr int kFlowWHalves = kSigW1;  // the flow MLP part of the weight image
 constexpr size_t kFlowStageSmem = (size_t)kFlowWHalves * 2 + (size_t)kSTile * kFld * 2;
 constexpr int kSigWHalves = kDensityWHalves - kSigW1;
-constexpr size_t kSigmaStageSmem = (size_t)kSigWHalves * 2 + (size_t)kSTile * kLdK128 * 2;
+constexpr int kSigTile = 384;  // rows per CTA tile of the sigma stage: 12 warps x 32 rows, 1 CTA per SM
+constexpr size_t kSigmaStageSmem = (size_t)kSigWHalves * 2 + (size_t)2 * kSigTile * kLdK128 * 2;  // two tile buffers per warp (223 KB)
 
 template <bool FROM_RAYS>
 __device__ __forceinline__ void sample_position(const nvsf_field_config_t& cfg, size_t g,
@@ -76,7 +77,7 @@ k_flow_stage(const __grid_constant__ nvsf_field_config_t cfg, const __grid_const
              const float* __restrict__ rays_d, const float* __restrict__ nears,
              const float* __restrict__ fars, const float* __restrict__ noise, uint32_t S,
              size_t begin, size_t count, float* __restrict__ flow_out,
-             __half* __restrict__ flowfeat_out) {
+             __half* __restrict__ flowfeat_out, float* __restrict__ qpos, size_t qstride) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __half* Wsm = reinterpret_cast<__half*>(smem_raw);
     __half* Xs = Wsm + kFlowWHalves;
@@ -134,8 +135,20 @@ k_flow_stage(const __grid_constant__ nvsf_field_config_t cfg, const __grid_const
         if (live) {
             const float4* s = reinterpret_cast<const float4*>(xrow + 32);
             float4* d = reinterpret_cast<float4*>(flow_out + li * 8);
-            d[0] = s[0];
-            d[1] = s[1];
+            const float4 f0 = s[0], f1 = s[1];
+            d[0] = f0;
+            d[1] = f1;
+            if (qpos) {  // the three query positions, planar [q * 3 + axis][sample], for k_dyn_stage
+                const int valid1 = P.ti->valid[1], valid2 = P.ti->valid[2];
+                float* q = qpos + li;
+                q[0] = x; q[qstride] = y; q[2 * qstride] = z;
+                q[3 * qstride] = valid1 ? x + f0.x : x;
+                q[4 * qstride] = valid1 ? y + f0.y : y;
+                q[5 * qstride] = valid1 ? z + f0.z : z;
+                q[6 * qstride] = valid2 ? x + f0.w : x;
+                q[7 * qstride] = valid2 ? y + f1.x : y;
+                q[8 * qstride] = valid2 ? z + f1.y : z;
+            }
         }
         __syncwarp();
     }
@@ -151,7 +164,7 @@ __device__ __forceinline__ void st8g(__half* row, int col, const float (&v)[8]) 
 
 // DYN_PRE: the 24 dynamic-hash features were produced by k_dyn_stage (planar fp16 rows
 // dyn_in[c * dyn_stride + sample], c = plane * 8 + level) and are only merged into the row here.
-template <bool FROM_RAYS, bool DYN_PRE>
+template <bool FROM_RAYS, bool DYN_PRE, bool PAIR>
 __global__ void __launch_bounds__(256, 4)
 k_encode_stage(const __grid_constant__ nvsf_field_config_t cfg,
                const __grid_constant__ FieldPtrs P, const float* __restrict__ xin,
@@ -159,7 +172,7 @@ k_encode_stage(const __grid_constant__ nvsf_field_config_t cfg,
                const float* __restrict__ nears, const float* __restrict__ fars,
                const float* __restrict__ noise, uint32_t S, size_t begin, size_t count,
                const float* __restrict__ flow_in, __half* __restrict__ feat_out,
-               const unsigned short* __restrict__ dyn_in, size_t dyn_stride) {
+               const unsigned short* __restrict__ dyn_in, size_t dyn_stride, int noalloc_from) {
     const size_t li = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (li >= count) return;
     float x, y, z;
@@ -241,8 +254,16 @@ k_encode_stage(const __grid_constant__ nvsf_field_config_t cfg,
 #pragma unroll 1
     for (int l = 0; l < kHsLevels; l += 2) {
         float v[8];
-        hash3_f4(P.hs16, lv(cfg.hs[l]), x, y, z, v);
-        hash3_f4(P.hs16, lv(cfg.hs[l + 1]), x, y, z, v + 4);
+        if (PAIR && cfg.hs[l].hashed && cfg.hs[l + 1].hashed) {
+            hash3_f4_pair(P.hs16, lv(cfg.hs[l]), x, y, z, v);
+            hash3_f4_pair(P.hs16, lv(cfg.hs[l + 1]), x, y, z, v + 4);
+        } else if (noalloc_from <= l) {
+            hash3_f4<true>(P.hs16, lv(cfg.hs[l]), x, y, z, v);
+            hash3_f4<true>(P.hs16, lv(cfg.hs[l + 1]), x, y, z, v + 4);
+        } else {
+            hash3_f4(P.hs16, lv(cfg.hs[l]), x, y, z, v);
+            hash3_f4(P.hs16, lv(cfg.hs[l + 1]), x, y, z, v + 4);
+        }
         st8g(row, 64 + 4 * l, v);
     }
     // (d) collapsed 2-D hashes -> [96,120), zero pad [120,128)
@@ -393,7 +414,7 @@ k_dyn_stage(const __grid_constant__ nvsf_field_config_t cfg, const __grid_consta
             const float* __restrict__ rays_o, const float* __restrict__ rays_d,
             const float* __restrict__ nears, const float* __restrict__ fars,
             const float* __restrict__ noise, uint32_t S, size_t begin, size_t count,
-            const float* __restrict__ flow_in, __half* __restrict__ dyn_out,
+            const float* __restrict__ qpos, __half* __restrict__ dyn_out,
             uint32_t* __restrict__ next_tile) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __half* tabs = reinterpret_cast<__half*>(smem_raw);
@@ -443,21 +464,17 @@ k_dyn_stage(const __grid_constant__ nvsf_field_config_t cfg, const __grid_consta
         }
         const size_t base = (size_t)tile * plan.tile;
         const uint32_t nloc = (uint32_t)min((size_t)plan.tile, count - base);
+        // plane p reads axes (a0, a1) = xy / xz / yz of the three query positions k_flow_stage left
+        // in qpos (planar, coalesced): no per-visit recomputation of the sample position
+        const int a0 = p == 2 ? 1 : 0, a1 = p == 0 ? 1 : 2;
         for (uint32_t i = tid; i < nloc; i += kDynThreads) {
             const size_t li = base + i;
-            float x, y, z;
-            sample_position<FROM_RAYS>(cfg, begin + li, xin, rays_o, rays_d, nears, fars, noise, S,
-                                       x, y, z);
-            const float4 f0 = __ldg(reinterpret_cast<const float4*>(flow_in + li * 8));
-            const float4 f1 = __ldg(reinterpret_cast<const float4*>(flow_in + li * 8) + 1);
-            const float x1 = valid1 ? x + f0.x : x, y1 = valid1 ? y + f0.y : y,
-                        z1 = valid1 ? z + f0.z : z;
-            const float x2 = valid2 ? x + f0.w : x, y2 = valid2 ? y + f1.x : y,
-                        z2 = valid2 ? z + f1.y : z;
             float u[3], w[3];
-            u[0] = p == 2 ? y : x;   w[0] = p == 0 ? y : z;
-            u[1] = p == 2 ? y1 : x1; w[1] = p == 0 ? y1 : z1;
-            u[2] = p == 2 ? y2 : x2; w[2] = p == 0 ? y2 : z2;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                u[q] = __ldg(qpos + (size_t)(3 * q + a0) * plan.stride + li);
+                w[q] = __ldg(qpos + (size_t)(3 * q + a1) * plan.stride + li);
+            }
             __half* out = dyn_out + (size_t)(8 * p + l0) * plan.stride + li;
 #pragma unroll 1
             for (int j = 0; j < nc; ++j) {
@@ -521,33 +538,58 @@ bool make_dyn_plan(const nvsf_field_config_t* cfg, const FieldPtrs& P, size_t co
 }
 
 // ---- stage 3: sigma MLP -------------------------------------------------------------------------
-__global__ void __launch_bounds__(kSTile, 2)
+// DRAM-stream bound (256 B in, 36 B out per sample).  Every warp owns two 32-row tile buffers and
+// prefetches its next 8 KB of feature rows with cp.async (16-byte LDGSTS, L1 bypass) while the
+// tensor cores work on the current one; ncu before the double buffering: 54 % of the HBM peak,
+// long_scoreboard on the tile loads (profiles/r01_stages_v2_ncu_full.txt).
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem);
+    const int bytes = valid ? 16 : 0;  // src-size 0: the 16 bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gmem), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+__device__ __forceinline__ void sigma_prefetch(__half* buf, const __half* __restrict__ feat,
+                                               size_t row0, size_t count, int lane) {
+#pragma unroll 4
+    for (int i = 0; i < 16; ++i) {
+        const int piece = i * 32 + lane;  // 16-byte piece index within the 8 KB block
+        const int r = piece >> 4, c = piece & 15;
+        const bool ok = row0 + r < count;
+        cp_async16(buf + r * kLdK128 + c * 8, feat + (ok ? row0 + r : 0) * kFeat + c * 8, ok);
+    }
+}
+
+__global__ void __launch_bounds__(kSigTile, 1)
 k_sigma_stage(const __half* __restrict__ mlp, const __half* __restrict__ feat, size_t count,
               float* __restrict__ sigma_out, __half* __restrict__ geo_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __half* Wsm = reinterpret_cast<__half*>(smem_raw);   // image starting at kSigW1
     __half* Xs = Wsm + kSigWHalves;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    block_copy16(Wsm, mlp + kSigW1, kSigWHalves * 2 / 16, tid, kSTile);
-    __syncthreads();
     const __half* W1 = Wsm;                          // [64][136]
     const __half* W2 = Wsm + (kSigW2 - kSigW1);      // [16][72]
-    __half* Aw = Xs + warp * 32 * kLdK128;
-    const size_t n_tiles = (count + kSTile - 1) / kSTile;
-    for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const size_t row0 = tile * kSTile + warp * 32;
-        // coalesced copy of this warp's 32 rows x 256 B into the padded tile
+    __half* bufs[2] = {Xs + (size_t)(2 * warp) * 32 * kLdK128, Xs + (size_t)(2 * warp + 1) * 32 * kLdK128};
+    const size_t n_tiles = (count + kSigTile - 1) / kSigTile;
+    size_t tile = blockIdx.x;
+    if (tile < n_tiles) sigma_prefetch(bufs[0], feat, tile * kSigTile + warp * 32, count, lane);
+    cp_async_commit();
+    block_copy16(Wsm, mlp + kSigW1, kSigWHalves * 2 / 16, tid, kSigTile);
+    __syncthreads();
+    int cur = 0;
+    for (; tile < n_tiles; tile += gridDim.x, cur ^= 1) {
+        const size_t row0 = tile * kSigTile + warp * 32;
+        const size_t next = tile + gridDim.x;
+        if (next < n_tiles) sigma_prefetch(bufs[cur ^ 1], feat, next * kSigTile + warp * 32, count, lane);
+        cp_async_commit();
+        cp_async_wait<1>();
         __syncwarp();
-#pragma unroll 4
-        for (int i = 0; i < 16; ++i) {
-            const int piece = i * 32 + lane;  // 16-byte piece index within the 8 KB block
-            const int r = piece >> 4, c = piece & 15;
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (row0 + r < count)
-                v = __ldcs(reinterpret_cast<const uint4*>(feat + (row0 + r) * kFeat) + c);
-            *reinterpret_cast<uint4*>(Aw + r * kLdK128 + c * 8) = v;
-        }
-        __syncwarp();
+        const __half* Aw = bufs[cur];
         float acc[2][8][4];
         zero_acc<8>(acc);
 #pragma unroll
@@ -557,6 +599,7 @@ k_sigma_stage(const __half* __restrict__ mlp, const __half* __restrict__ feat, s
             ldsm_x4(a[1][0], Aw + (16 + (lane & 15)) * kLdK128 + kk * 16 + (lane >> 4) * 8);
             warp_gemm_regA<1, 8>(a, W1 + kk * 16, kLdK128, acc, lane);
         }
+        __syncwarp();  // every lane has read its fragments before the buffer is refilled
         uint32_t a2[2][4][4];
         relu_to_a<8>(acc, a2);
         float o[2][2][4];
@@ -579,6 +622,7 @@ k_sigma_stage(const __half* __restrict__ mlp, const __half* __restrict__ feat, s
                 }
             }
     }
+    cp_async_wait<0>();
 }
 
 // Optional per-stage timing with CUDA events on the launching stream (bench.py's roofline): five
@@ -629,9 +673,26 @@ int ensure_attrs() {
     return NVSF_OK;
 }
 
-// split scratch: flow f32 [chunk,8] | feats f16 [chunk,128] | dyn f16 [24][chunk] | tile counters
+int g_enc_pair = 0;  // paired x-corner loads of the static hash (option "enc_pair"); measured neutral on B200
+                     // (13.10 vs 13.16 ms per frame in the gather stage), so off by default
+
+int g_enc_noalloc = 8;  // first static-hash level gathered with L1::no_allocate (option "enc_noalloc"; 8 = none)
+
+template <bool FROM_RAYS, class... A>
+void launch_encode(bool dyn_pre, bool pair, unsigned tiles, cudaStream_t stream, A... a) {
+    if (dyn_pre) {
+        if (pair) k_encode_stage<FROM_RAYS, true, true><<<tiles, 256, 0, stream>>>(a...);
+        else k_encode_stage<FROM_RAYS, true, false><<<tiles, 256, 0, stream>>>(a...);
+    } else {
+        if (pair) k_encode_stage<FROM_RAYS, false, true><<<tiles, 256, 0, stream>>>(a...);
+        else k_encode_stage<FROM_RAYS, false, false><<<tiles, 256, 0, stream>>>(a...);
+    }
+}
+
+// split scratch: flow f32 [chunk,8] | feats f16 [chunk,128] | dyn f16 [24][chunk] | qpos f32 [9][chunk]
+// | tile counters
 struct SplitScratch {
-    size_t flow, feat, dyn, counters, total;
+    size_t flow, feat, dyn, qpos, counters, total;
 };
 SplitScratch split_layout(size_t n) {
     const size_t chunk = std::min<size_t>(n, kSplitChunk);   // sized for the largest chunk option
@@ -640,6 +701,7 @@ SplitScratch split_layout(size_t n) {
     L.flow = off; off += ws_align(chunk * 8 * sizeof(float));
     L.feat = off; off += ws_align(chunk * kFeat * sizeof(__half));
     L.dyn = off; off += ws_align(chunk * 3 * kHdLevels * sizeof(__half));
+    L.qpos = off; off += ws_align(chunk * 9 * sizeof(float));
     L.counters = off; off += ws_align(kDynMaxTypes * sizeof(uint32_t));
     L.total = off;
     return L;
@@ -667,6 +729,7 @@ int nvsf_launch_density_split(const nvsf_field_config_t* cfg, const void* worksp
     float* flow_buf = reinterpret_cast<float*>(sc + SL.flow);
     __half* feat_buf = reinterpret_cast<__half*>(sc + SL.feat);
     __half* dyn_buf = reinterpret_cast<__half*>(sc + SL.dyn);
+    float* qpos_buf = reinterpret_cast<float*>(sc + SL.qpos);
     uint32_t* counters = reinterpret_cast<uint32_t*>(sc + SL.counters);
     // mode 2: dynamic hashes from shared-memory-staged tables (needs the scratch buffer; the
     // training forward passes none and keeps the plain gather stage)
@@ -690,48 +753,43 @@ int nvsf_launch_density_split(const nvsf_field_config_t* cfg, const void* worksp
         if (x) {
             if (dyn_pre)
                 k_flow_stage<false, true><<<grid_p, kSTile, kFlowStageSmem, stream>>>(
-                    *cfg, P, x, nullptr, nullptr, nullptr, nullptr, nullptr, 1, begin, count, flow_buf, ff);
+                    *cfg, P, x, nullptr, nullptr, nullptr, nullptr, nullptr, 1, begin, count, flow_buf, ff,
+                    qpos_buf, count);
             else
                 k_flow_stage<false, false><<<grid_p, kSTile, kFlowStageSmem, stream>>>(
-                    *cfg, P, x, nullptr, nullptr, nullptr, nullptr, nullptr, 1, begin, count, flow_buf, ff);
+                    *cfg, P, x, nullptr, nullptr, nullptr, nullptr, nullptr, 1, begin, count, flow_buf, ff,
+                    nullptr, 0);
             if (g_prof.on) g_prof.next(stream);
             if (dyn_pre)
                 k_dyn_stage<false><<<grid_d, kDynThreads, kDynTableBytes, stream>>>(
                     *cfg, P, plan, x, nullptr, nullptr, nullptr, nullptr, nullptr, 1, begin, count,
-                    flow_buf, dyn_buf, counters);
+                    qpos_buf, dyn_buf, counters);
             if (g_prof.on) g_prof.next(stream);
-            if (dyn_pre)
-                k_encode_stage<false, true><<<(unsigned)tiles, 256, 0, stream>>>(
-                    *cfg, P, x, nullptr, nullptr, nullptr, nullptr, nullptr, 1, begin, count, flow_buf,
-                    feat_buf, dyn_in, count);
-            else
-                k_encode_stage<false, false><<<(unsigned)tiles, 256, 0, stream>>>(
-                    *cfg, P, x, nullptr, nullptr, nullptr, nullptr, nullptr, 1, begin, count, flow_buf,
-                    feat_buf, nullptr, 0);
+            launch_encode<false>(dyn_pre, g_enc_pair != 0, (unsigned)tiles, stream, *cfg, P, x, nullptr,
+                                 nullptr, nullptr, nullptr, nullptr, 1, begin, count, flow_buf,
+                                 feat_buf, dyn_pre ? dyn_in : nullptr, dyn_pre ? count : 0, g_enc_noalloc);
         } else {
             if (dyn_pre)
                 k_flow_stage<true, true><<<grid_p, kSTile, kFlowStageSmem, stream>>>(
-                    *cfg, P, nullptr, rays_o, rays_d, nears, fars, noise, S, begin, count, flow_buf, ff);
+                    *cfg, P, nullptr, rays_o, rays_d, nears, fars, noise, S, begin, count, flow_buf, ff,
+                    qpos_buf, count);
             else
                 k_flow_stage<true, false><<<grid_p, kSTile, kFlowStageSmem, stream>>>(
-                    *cfg, P, nullptr, rays_o, rays_d, nears, fars, noise, S, begin, count, flow_buf, ff);
+                    *cfg, P, nullptr, rays_o, rays_d, nears, fars, noise, S, begin, count, flow_buf, ff,
+                    nullptr, 0);
             if (g_prof.on) g_prof.next(stream);
             if (dyn_pre)
                 k_dyn_stage<true><<<grid_d, kDynThreads, kDynTableBytes, stream>>>(
                     *cfg, P, plan, nullptr, rays_o, rays_d, nears, fars, noise, S, begin, count,
-                    flow_buf, dyn_buf, counters);
+                    qpos_buf, dyn_buf, counters);
             if (g_prof.on) g_prof.next(stream);
-            if (dyn_pre)
-                k_encode_stage<true, true><<<(unsigned)tiles, 256, 0, stream>>>(
-                    *cfg, P, nullptr, rays_o, rays_d, nears, fars, noise, S, begin, count, flow_buf,
-                    feat_buf, dyn_in, count);
-            else
-                k_encode_stage<true, false><<<(unsigned)tiles, 256, 0, stream>>>(
-                    *cfg, P, nullptr, rays_o, rays_d, nears, fars, noise, S, begin, count, flow_buf,
-                    feat_buf, nullptr, 0);
+            launch_encode<true>(dyn_pre, g_enc_pair != 0, (unsigned)tiles, stream, *cfg, P, nullptr,
+                                rays_o, rays_d, nears, fars, noise, S, begin, count, flow_buf,
+                                feat_buf, dyn_pre ? dyn_in : nullptr, dyn_pre ? count : 0, g_enc_noalloc);
         }
         if (g_prof.on) g_prof.next(stream);
-        k_sigma_stage<<<grid_p, kSTile, kSigmaStageSmem, stream>>>(
+        k_sigma_stage<<<(int)std::min<size_t>((count + kSigTile - 1) / kSigTile, (size_t)sms), kSigTile,
+                        kSigmaStageSmem, stream>>>(
             P.mlp, feat_buf, count, sigma + begin, reinterpret_cast<__half*>(geo) + begin * kGeo);
         if (g_prof.on) g_prof.next(stream);
         if (features)
@@ -756,6 +814,16 @@ int nvsf_split_set_option(const char* name, int value) {
     if (k == "dyn_overhead") {
         if (value < 0 || value > 1000) return NVSF_E_INVALID;
         g_dyn_overhead = value;
+        return NVSF_OK;
+    }
+    if (k == "enc_noalloc") {
+        if (value < 0 || value > 8) return NVSF_E_INVALID;
+        g_enc_noalloc = value;
+        return NVSF_OK;
+    }
+    if (k == "enc_pair") {
+        if (value != 0 && value != 1) return NVSF_E_INVALID;
+        g_enc_pair = value;
         return NVSF_OK;
     }
     if (k == "split_chunk") {  // units of 64 K samples, at most kSplitChunk

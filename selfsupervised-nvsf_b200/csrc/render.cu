@@ -17,6 +17,12 @@
 namespace {
 
 constexpr int kRWarps = 4;
+// resident CTAs per SM the register allocation is tuned for: 4 -> <= 128 registers (16 warps/SM,
+// 24 bytes of spills) instead of 150 registers / 12 warps; the kernel is latency bound (ncu: stall
+// `wait` + long_scoreboard at 14 % occupancy, profiles/r01_composite_v1_ncu_full.txt)
+#ifndef NVSF_RENDER_MIN_CTAS
+#define NVSF_RENDER_MIN_CTAS 4
+#endif
 constexpr int kGeoLd = kLdK16;  // 24 halves per staged geo row
 constexpr int kWarpScratchBytes = 32 * kGeoLd * 2 + 2 * kHidden * 4 + kHeadDirMax * 4;
 
@@ -38,7 +44,7 @@ __device__ __forceinline__ float uniform_z2(float near, float far, uint32_t k, u
 __device__ __forceinline__ float sigmoidf_(float h) { return 1.0f / (1.0f + expf(-h)); }
 
 template <bool LIDAR>
-__global__ void __launch_bounds__(kRWarps * 32)
+__global__ void __launch_bounds__(kRWarps * 32, NVSF_RENDER_MIN_CTAS)
 k_render_composite(const __grid_constant__ nvsf_field_config_t cfg, const __half* __restrict__ mlp,
                    const float* __restrict__ rays_d, const float* __restrict__ nears,
                    const float* __restrict__ fars, const float* __restrict__ noise,
