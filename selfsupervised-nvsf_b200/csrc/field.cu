@@ -462,6 +462,7 @@ FieldPtrs nvsf_make_field_ptrs(const nvsf_field_config_t* cfg, const void* works
     P.flow = reinterpret_cast<const float2*>(w + L.flow);
     P.pld = reinterpret_cast<const float*>(w + L.pld);
     P.mlp = reinterpret_cast<const __half*>(w + L.mlp);
+    P.mlp_tc = w + L.mlp_tc;
     for (int s = 0; s < kPlScales; ++s) {
         P.pls_scale[s] = (uint32_t)L.pls_scale[s];
         P.pld_scale[s] = (uint32_t)L.pld_scale[s];
@@ -565,6 +566,7 @@ int nvsf_field_pack_params(const nvsf_field_config_t* cfg, const nvsf_field_para
         pack(heads[h] + H * in_pad, H, 0, H, H, hm + kHeadW2, kLdK64, 0);
         pack(heads[h] + H * in_pad + H * H, H, 0, n_out, H, hm + kHeadW3, kLdK64, 0);
     }
+    nvsf_pack_sigma_tc(m, w + L.mlp_tc, s);  // swizzled K-major operand images of the sigma net
     return nvsf_launch_status();
 }
 

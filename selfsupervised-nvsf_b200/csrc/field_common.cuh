@@ -39,6 +39,7 @@ struct WsLayout {
     size_t pls16;     // __half mirror of pls (same element offsets): one 16-byte texel
     size_t pld16;     // __half mirror of pld
     size_t flow16;    // __half2 [fl_entries]                       fp16 mirror of flow
+    size_t mlp_tc;    // sigma-net operand images for tcgen05.mma (sigma_tc.cu), 18 KB
     size_t total;
     size_t pls_scale[NVSF_MAX_PLANE_SCALES];  // float offsets inside pls
     size_t pld_scale[NVSF_MAX_PLANE_SCALES];  // float offsets inside one query of pld
@@ -106,6 +107,7 @@ static inline WsLayout make_ws_layout(const nvsf_field_config_t* c) {
     L.pls16 = off; off = ws_align(off + f * sizeof(__half));
     L.pld16 = off; off = ws_align(off + 3 * g * sizeof(__half));
     L.flow16 = off; off = ws_align(off + (size_t)c->fl_entries * sizeof(__half2));
+    L.mlp_tc = off; off = ws_align(off + (size_t)(kHidden * kFeat + kGeo * kHidden) * sizeof(__half));
     L.total = off;
     return L;
 }
@@ -122,6 +124,7 @@ struct FieldPtrs {
     const float2* flow;
     const float* pld;
     const __half* mlp;
+    const void* mlp_tc;
     const TimeInfo* ti;
     uint32_t pls_scale[kPlScales];
     uint32_t pld_scale[kPlScales];
@@ -152,6 +155,10 @@ int nvsf_launch_density_split(const nvsf_field_config_t* cfg, const void* worksp
                               float* flow, void* split_scratch, cudaStream_t stream,
                               const DensityKeep* keep = nullptr);
 int nvsf_density_mode();
+// tcgen05 sigma stage (sigma_tc.cu)
+void nvsf_pack_sigma_tc(const __half* mlp, void* dst, cudaStream_t stream);
+int nvsf_launch_sigma_tc(const void* wimg, const __half* feat, size_t count, float* sigma,
+                         __half* geo, int sms, cudaStream_t stream);
 void nvsf_stage_timing_enable(int on);
 int nvsf_split_set_option(const char* name, int value);
 // Compositing + heads launcher (render.cu); scratch = sigma f32 [N*S] then geo f16 [N*S,16];
@@ -458,16 +465,10 @@ __device__ __forceinline__ void hash3_f4_pair(const uint2* __restrict__ tab, con
     out[0] = a0; out[1] = a1; out[2] = a2; out[3] = a3;
 }
 
-// 8-byte read-only load that does not allocate in L1: the fine hashed levels never hit there (4 MB
-// of random entries per level) and would only evict the plane texels and coarse levels that do
-__device__ __forceinline__ uint2 ldg_na(const uint2* p) {
-    uint2 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];\n" : "=r"(v.x), "=r"(v.y) : "l"(p));
-    return v;
-}
-
+// (Measured and rejected on B200: ld.global.nc.L1::no_allocate for the fine hashed levels — the
+// gather stage went from 13.1 to 17.7 ms per frame; the x-neighbour of a corner sits in the same
+// 32-byte sector three times out of four and is an L1 hit only if the first load allocated.)
 // one level of the 3-D fp16 static hash grid (4 features)
-template <bool NOALLOC = false>
 __device__ __forceinline__ void hash3_f4(const uint2* __restrict__ tab, const LevelArgs& L,
                                          float x, float y, float z, float* out) {
     uint32_t cx, cy, cz;
@@ -477,10 +478,8 @@ __device__ __forceinline__ void hash3_f4(const uint2* __restrict__ tab, const Le
     grid_pos(L.scale, z, cz, wz);
     uint2 v[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        const uint2* p = tab + L.offset + idx3(L, cx + (c & 1), cy + ((c >> 1) & 1), cz + (c >> 2));
-        v[c] = NOALLOC ? ldg_na(p) : __ldg(p);
-    }
+    for (int c = 0; c < 8; ++c)
+        v[c] = __ldg(tab + L.offset + idx3(L, cx + (c & 1), cy + ((c >> 1) & 1), cz + (c >> 2)));
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
     for (int c = 0; c < 8; ++c) {

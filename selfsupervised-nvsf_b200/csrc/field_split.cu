@@ -172,7 +172,7 @@ k_encode_stage(const __grid_constant__ nvsf_field_config_t cfg,
                const float* __restrict__ nears, const float* __restrict__ fars,
                const float* __restrict__ noise, uint32_t S, size_t begin, size_t count,
                const float* __restrict__ flow_in, __half* __restrict__ feat_out,
-               const unsigned short* __restrict__ dyn_in, size_t dyn_stride, int noalloc_from) {
+               const unsigned short* __restrict__ dyn_in, size_t dyn_stride) {
     const size_t li = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (li >= count) return;
     float x, y, z;
@@ -257,9 +257,6 @@ k_encode_stage(const __grid_constant__ nvsf_field_config_t cfg,
         if (PAIR && cfg.hs[l].hashed && cfg.hs[l + 1].hashed) {
             hash3_f4_pair(P.hs16, lv(cfg.hs[l]), x, y, z, v);
             hash3_f4_pair(P.hs16, lv(cfg.hs[l + 1]), x, y, z, v + 4);
-        } else if (noalloc_from <= l) {
-            hash3_f4<true>(P.hs16, lv(cfg.hs[l]), x, y, z, v);
-            hash3_f4<true>(P.hs16, lv(cfg.hs[l + 1]), x, y, z, v + 4);
         } else {
             hash3_f4(P.hs16, lv(cfg.hs[l]), x, y, z, v);
             hash3_f4(P.hs16, lv(cfg.hs[l + 1]), x, y, z, v + 4);
@@ -673,10 +670,10 @@ int ensure_attrs() {
     return NVSF_OK;
 }
 
+int g_sigma_tc = 1;  // sigma stage on tcgen05 / TMEM (sigma_tc.cu) instead of mma.sync (option "sigma_tc"):
+                     // 3.33 -> 2.51 ms per LiDAR frame on B200, at the DRAM floor of the 292 B/sample it streams
 int g_enc_pair = 0;  // paired x-corner loads of the static hash (option "enc_pair"); measured neutral on B200
                      // (13.10 vs 13.16 ms per frame in the gather stage), so off by default
-
-int g_enc_noalloc = 8;  // first static-hash level gathered with L1::no_allocate (option "enc_noalloc"; 8 = none)
 
 template <bool FROM_RAYS, class... A>
 void launch_encode(bool dyn_pre, bool pair, unsigned tiles, cudaStream_t stream, A... a) {
@@ -767,7 +764,7 @@ int nvsf_launch_density_split(const nvsf_field_config_t* cfg, const void* worksp
             if (g_prof.on) g_prof.next(stream);
             launch_encode<false>(dyn_pre, g_enc_pair != 0, (unsigned)tiles, stream, *cfg, P, x, nullptr,
                                  nullptr, nullptr, nullptr, nullptr, 1, begin, count, flow_buf,
-                                 feat_buf, dyn_pre ? dyn_in : nullptr, dyn_pre ? count : 0, g_enc_noalloc);
+                                 feat_buf, dyn_pre ? dyn_in : nullptr, dyn_pre ? count : 0);
         } else {
             if (dyn_pre)
                 k_flow_stage<true, true><<<grid_p, kSTile, kFlowStageSmem, stream>>>(
@@ -785,12 +782,18 @@ int nvsf_launch_density_split(const nvsf_field_config_t* cfg, const void* worksp
             if (g_prof.on) g_prof.next(stream);
             launch_encode<true>(dyn_pre, g_enc_pair != 0, (unsigned)tiles, stream, *cfg, P, nullptr,
                                 rays_o, rays_d, nears, fars, noise, S, begin, count, flow_buf,
-                                feat_buf, dyn_pre ? dyn_in : nullptr, dyn_pre ? count : 0, g_enc_noalloc);
+                                feat_buf, dyn_pre ? dyn_in : nullptr, dyn_pre ? count : 0);
         }
         if (g_prof.on) g_prof.next(stream);
-        k_sigma_stage<<<(int)std::min<size_t>((count + kSigTile - 1) / kSigTile, (size_t)sms), kSigTile,
-                        kSigmaStageSmem, stream>>>(
-            P.mlp, feat_buf, count, sigma + begin, reinterpret_cast<__half*>(geo) + begin * kGeo);
+        if (g_sigma_tc) {
+            st = nvsf_launch_sigma_tc(P.mlp_tc, feat_buf, count, sigma + begin,
+                                      reinterpret_cast<__half*>(geo) + begin * kGeo, sms, stream);
+            if (st != NVSF_OK) return st;
+        } else {
+            k_sigma_stage<<<(int)std::min<size_t>((count + kSigTile - 1) / kSigTile, (size_t)sms), kSigTile,
+                            kSigmaStageSmem, stream>>>(
+                P.mlp, feat_buf, count, sigma + begin, reinterpret_cast<__half*>(geo) + begin * kGeo);
+        }
         if (g_prof.on) g_prof.next(stream);
         if (features)
             cudaMemcpyAsync(reinterpret_cast<__half*>(features) + begin * kFeat, feat_buf,
@@ -816,9 +819,9 @@ int nvsf_split_set_option(const char* name, int value) {
         g_dyn_overhead = value;
         return NVSF_OK;
     }
-    if (k == "enc_noalloc") {
-        if (value < 0 || value > 8) return NVSF_E_INVALID;
-        g_enc_noalloc = value;
+    if (k == "sigma_tc") {
+        if (value != 0 && value != 1) return NVSF_E_INVALID;
+        g_sigma_tc = value;
         return NVSF_OK;
     }
     if (k == "enc_pair") {

@@ -226,3 +226,23 @@ def test_dyn_stage_tiles_and_chunks(pkg, model):
         L.nvsf_set_option(b"density_mode", prev)
     for a, b in zip(*out):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("n", [128 * 37, 100001])
+def test_sigma_stage_tcgen05_matches_mma_sync(pkg, model, n):
+    """The sigma MLP on tcgen05.mma / TMEM (csrc/sigma_tc.cu, option sigma_tc) against the mma.sync
+    stage: same fp16 operands, fp32 accumulation in a different order -> agreement to fp16 rounding
+    of the hidden layer; covers full tiles and a ragged tail."""
+    L = pkg._lib.lib()
+    x = torch.from_numpy(pts(n, 21)).cuda()
+    out = {}
+    try:
+        for tc in (0, 1):
+            assert L.nvsf_set_option(b"sigma_tc", tc) == 0
+            den = model.density(x, 0.45, True)
+            torch.cuda.synchronize()
+            out[tc] = (host(den["sigma"]), host(den["geo_feat"]))
+    finally:
+        L.nvsf_set_option(b"sigma_tc", 1)
+    close(out[1][0], out[0][0], 2e-3, 0, "sigma tcgen05 vs mma.sync")
+    close(out[1][1], out[0][1], 2e-3, 2e-3 * np.abs(out[0][1]).max(), "geo tcgen05 vs mma.sync")
