@@ -159,6 +159,10 @@ int nvsf_density_mode();
 void nvsf_pack_sigma_tc(const __half* mlp, void* dst, cudaStream_t stream);
 int nvsf_launch_sigma_tc(const void* wimg, const __half* feat, size_t count, float* sigma,
                          __half* geo, int sms, cudaStream_t stream);
+// gather stage fused with the sigma MLP (mode 2 intermediates: query positions + dyn rows)
+int nvsf_launch_encode_sigma_tc(const nvsf_field_config_t* cfg, const FieldPtrs& P, const float* qpos,
+                                const void* dyn_in, size_t stride, size_t count, float* sigma,
+                                __half* geo, int sms, cudaStream_t stream);
 void nvsf_stage_timing_enable(int on);
 int nvsf_split_set_option(const char* name, int value);
 // Compositing + heads launcher (render.cu); scratch = sigma f32 [N*S] then geo f16 [N*S,16];

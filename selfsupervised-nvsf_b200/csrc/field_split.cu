@@ -670,6 +670,7 @@ int ensure_attrs() {
     return NVSF_OK;
 }
 
+int g_fuse_sigma = 1;  // mode 2: gather stage fused with the sigma MLP on tcgen05 (option "fuse_sigma")
 int g_sigma_tc = 1;  // sigma stage on tcgen05 / TMEM (sigma_tc.cu) instead of mma.sync (option "sigma_tc"):
                      // 3.33 -> 2.51 ms per LiDAR frame on B200, at the DRAM floor of the 292 B/sample it streams
 int g_enc_pair = 0;  // paired x-corner loads of the static hash (option "enc_pair"); measured neutral on B200
@@ -746,6 +747,7 @@ int nvsf_launch_density_split(const nvsf_field_config_t* cfg, const void* worksp
         const int grid_d = dyn_pre ? (int)std::min<size_t>((size_t)plan.ntypes * plan.tiles, (size_t)sms) : 0;
         if (dyn_pre) cudaMemsetAsync(counters, 0, kDynMaxTypes * sizeof(uint32_t), stream);
         const unsigned short* dyn_in = reinterpret_cast<const unsigned short*>(dyn_buf);
+        const bool fused = dyn_pre && !keep && !features && g_fuse_sigma != 0;
         if (g_prof.on) g_prof.next(stream);
         if (x) {
             if (dyn_pre)
@@ -762,9 +764,11 @@ int nvsf_launch_density_split(const nvsf_field_config_t* cfg, const void* worksp
                     *cfg, P, plan, x, nullptr, nullptr, nullptr, nullptr, nullptr, 1, begin, count,
                     qpos_buf, dyn_buf, counters);
             if (g_prof.on) g_prof.next(stream);
-            launch_encode<false>(dyn_pre, g_enc_pair != 0, (unsigned)tiles, stream, *cfg, P, x, nullptr,
-                                 nullptr, nullptr, nullptr, nullptr, 1, begin, count, flow_buf,
-                                 feat_buf, dyn_pre ? dyn_in : nullptr, dyn_pre ? count : 0);
+            if (!fused) {
+                launch_encode<false>(dyn_pre, g_enc_pair != 0, (unsigned)tiles, stream, *cfg, P, x,
+                                     nullptr, nullptr, nullptr, nullptr, nullptr, 1, begin, count,
+                                     flow_buf, feat_buf, dyn_pre ? dyn_in : nullptr, dyn_pre ? count : 0);
+            }
         } else {
             if (dyn_pre)
                 k_flow_stage<true, true><<<grid_p, kSTile, kFlowStageSmem, stream>>>(
@@ -780,12 +784,21 @@ int nvsf_launch_density_split(const nvsf_field_config_t* cfg, const void* worksp
                     *cfg, P, plan, nullptr, rays_o, rays_d, nears, fars, noise, S, begin, count,
                     qpos_buf, dyn_buf, counters);
             if (g_prof.on) g_prof.next(stream);
-            launch_encode<true>(dyn_pre, g_enc_pair != 0, (unsigned)tiles, stream, *cfg, P, nullptr,
-                                rays_o, rays_d, nears, fars, noise, S, begin, count, flow_buf,
-                                feat_buf, dyn_pre ? dyn_in : nullptr, dyn_pre ? count : 0);
+            if (!fused) {
+                launch_encode<true>(dyn_pre, g_enc_pair != 0, (unsigned)tiles, stream, *cfg, P, nullptr,
+                                    rays_o, rays_d, nears, fars, noise, S, begin, count, flow_buf,
+                                    feat_buf, dyn_pre ? dyn_in : nullptr, dyn_pre ? count : 0);
+            }
+        }
+        if (fused) {  // gather stage + sigma MLP in one tcgen05 kernel: the feature rows stay on the SM
+            st = nvsf_launch_encode_sigma_tc(cfg, P, qpos_buf, dyn_buf, count, count, sigma + begin,
+                                             reinterpret_cast<__half*>(geo) + begin * kGeo, sms, stream);
+            if (st != NVSF_OK) return st;
         }
         if (g_prof.on) g_prof.next(stream);
-        if (g_sigma_tc) {
+        if (fused) {
+            // sigma and geo were produced by the fused kernel
+        } else if (g_sigma_tc) {
             st = nvsf_launch_sigma_tc(P.mlp_tc, feat_buf, count, sigma + begin,
                                       reinterpret_cast<__half*>(geo) + begin * kGeo, sms, stream);
             if (st != NVSF_OK) return st;
@@ -817,6 +830,11 @@ int nvsf_split_set_option(const char* name, int value) {
     if (k == "dyn_overhead") {
         if (value < 0 || value > 1000) return NVSF_E_INVALID;
         g_dyn_overhead = value;
+        return NVSF_OK;
+    }
+    if (k == "fuse_sigma") {
+        if (value != 0 && value != 1) return NVSF_E_INVALID;
+        g_fuse_sigma = value;
         return NVSF_OK;
     }
     if (k == "sigma_tc") {

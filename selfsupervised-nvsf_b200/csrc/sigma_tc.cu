@@ -14,104 +14,11 @@
 // twelve instructions per 128 samples and the other 127 only move data.
 #include <algorithm>
 
-#include "field_common.cuh"
+#include "umma.cuh"
 
 namespace {
 
-constexpr int kRows = 128;                         // UMMA M
-constexpr uint32_t kW1Bytes = kHidden * kFeat * 2; // 2 K blocks of [64 rows][128 B]
-constexpr uint32_t kW2Bytes = kGeo * kHidden * 2;  // 1 K block of [16 rows][128 B]
-constexpr uint32_t kXBytes = kRows * kFeat * 2;    // 2 K blocks of [128 rows][128 B]
-constexpr uint32_t kOffW1 = 0, kOffW2 = kW1Bytes, kOffX = kOffW2 + kW2Bytes;
-constexpr uint32_t kOffBar = kOffX + kXBytes;
-constexpr size_t kTcSmem = kOffBar + 16 + 1024;    // + slack to align the base to 1024 B
-constexpr uint32_t kTmemCols = 64;
-static_assert(kOffX % 1024 == 0, "swizzled tiles start on 1024-byte boundaries");
-
-// byte offset of 16-byte chunk `chunk` (0..7) of row `row` inside one [rows][128 B] K block with the
-// 128-byte swizzle (Swizzle<3,4,3>: chunk index xor row mod 8)
-__host__ __device__ __forceinline__ uint32_t swz(uint32_t row, uint32_t chunk) {
-    return row * 128u + ((chunk ^ (row & 7u)) << 4);
-}
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-    return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
-    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(bar),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void cp_async16(uint32_t smem, const void* gmem, bool valid) {
-    const int bytes = valid ? 16 : 0;  // src-size 0: zero fill
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem), "l"(gmem), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void fence_async_smem() {
-    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_before() {
-    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_after() {
-    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-}
-
-// UMMA shared-memory matrix descriptor, K-major, SWIZZLE_128B: start address, LBO (unused for a
-// swizzled K-major operand, 1), SBO = 1024 B between 8-row groups, version 1 (sm_100), layout 2.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-    uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
-// instruction descriptor of kind::f16: fp16 A and B (K-major both), fp32 D, M x N
-__host__ __device__ constexpr uint32_t umma_idesc(int M, int N) {
-    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t a, uint64_t b, uint32_t idesc,
-                                         uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d),
-        "l"(a), "l"(b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar)
-                 : "memory");
-}
-// 16 consecutive fp32 columns of this thread's TMEM lane
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
-          "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
-          "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() {
-    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-}
+using namespace umma;
 
 // packed fp16 MLP image (field_common.cuh: W1 at kSigW1 [64][136], W2 at kSigW2 [16][72]) -> the
 // swizzled K-major operand images [W1 K block 0][W1 K block 1][W2], copied verbatim to shared memory
@@ -249,6 +156,221 @@ k_sigma_stage_tc(const unsigned char* __restrict__ wimg, const __half* __restric
 
 bool g_tc_attr = false;
 
+// ---- gather stage fused with the sigma MLP ---------------------------------------------------------
+// The feature rows never leave the SM: a CTA of 8 warpgroups (1024 threads, one CTA per SM, 64
+// registers per thread like the plain gather stage) — every warpgroup is an independent 128-sample
+// UMMA tile with its own [128 rows][128 B] shared-memory operand tile, mbarrier, named barrier and
+// 64 TMEM columns.  A thread gathers the features of its own sample (its row); the sigma-net input
+// is consumed in two K halves that accumulate in TMEM:
+//   half 0: space planes (32) + collapsed time planes (32)   -> tile -> 4 x tcgen05.mma (D1  = ..)
+//   half 1: static hash (32) + dyn rows (24) + zero pad (8)  -> tile -> 4 x tcgen05.mma (D1 += ..)
+//   H = relu(D1) fp16 -> tile -> 4 x tcgen05.mma (D2 = H W2^T) -> sigma = exp(D2[:,0]), geo
+// The tile is re-used three times per sample block; a warpgroup waits on its own mbarrier before each
+// refill (4 of the 32 warps pause for the ~0.5 us of an MMA batch, the other 28 keep gathering).
+// Against the staged pair k_encode_stage -> k_sigma_stage this removes the 256 B/sample feature row
+// from DRAM (written with one L1 tag per lane, read back by the sigma stage) and one launch.
+constexpr int kFusedWG = 8;
+constexpr int kFusedThreads = kFusedWG * kRows;
+constexpr uint32_t kFTile = kRows * 128;                         // one K block of 128 rows
+constexpr uint32_t kFOffX = kOffW2 + kW2Bytes;
+constexpr uint32_t kFOffBar = kFOffX + kFusedWG * kFTile;
+constexpr size_t kFusedSmem = kFOffBar + 8 * kFusedWG + 16 + 1024;
+static_assert(kFOffX % 1024 == 0, "swizzled tiles start on 1024-byte boundaries");
+
+__device__ __forceinline__ void wg_barrier(uint32_t wg) {
+    asm volatile("bar.sync %0, 128;\n" ::"r"(wg + 1u) : "memory");
+}
+__device__ __forceinline__ void st_chunk(unsigned char* tile, uint32_t row, uint32_t chunk,
+                                         const float (&v)[8]) {
+    uint4 o;
+    o.x = pack_half2(v[0], v[1]); o.y = pack_half2(v[2], v[3]);
+    o.z = pack_half2(v[4], v[5]); o.w = pack_half2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(tile + swz(row, chunk)) = o;
+}
+
+__global__ void __launch_bounds__(kFusedThreads, 1)
+k_encode_sigma_tc(const __grid_constant__ nvsf_field_config_t cfg,
+                  const __grid_constant__ FieldPtrs P, const float* __restrict__ qpos,
+                  const unsigned short* __restrict__ dyn_in, size_t stride, size_t count,
+                  float* __restrict__ sigma_out, __half* __restrict__ geo_out) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    unsigned char* sm = smem_raw + (base - raw);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + kFOffBar + 8 * kFusedWG);
+    const uint32_t tid = threadIdx.x, wg = tid >> 7, t = tid & 127u;
+
+    for (uint32_t i = tid; i < (kW1Bytes + kW2Bytes) / 16; i += kFusedThreads)
+        reinterpret_cast<uint4*>(sm)[i] = __ldg(reinterpret_cast<const uint4*>(P.mlp_tc) + i);
+    if (tid < (uint32_t)kFusedWG) mbar_init(base + kFOffBar + 8 * tid, 1);
+    if (tid < 32) {
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(
+                         smem_u32(tmem_slot)),
+                     "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t tcol = tmem + wg * 64u;                       // this warpgroup's 64 columns
+    const uint32_t tlane = tcol + ((((tid >> 5) & 3u) * 32u) << 16);  // this warp's 32 lanes
+    const uint32_t xs = base + kFOffX + wg * kFTile;
+    unsigned char* xg = sm + kFOffX + wg * kFTile;
+    const uint32_t bar = base + kFOffBar + 8 * wg;
+    constexpr uint32_t kIdesc1 = umma_idesc(kRows, kHidden), kIdesc2 = umma_idesc(kRows, kGeo);
+    const int qi1 = P.ti->valid[1] ? 1 : 0, qi2 = P.ti->valid[2] ? 2 : 0;
+
+    uint32_t phase = 0;
+    const size_t n_tiles = (count + kRows - 1) / kRows;
+    for (size_t tile = (size_t)blockIdx.x * kFusedWG + wg; tile < n_tiles;
+         tile += (size_t)gridDim.x * kFusedWG) {
+        const size_t li = tile * kRows + t;
+        const bool live = li < count;
+        const size_t lc = live ? li : count - 1;   // dead rows of the last tile repeat a valid sample
+        float qx[3], qy[3], qz[3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            qx[q] = __ldg(qpos + (size_t)(3 * q + 0) * stride + lc);
+            qy[q] = __ldg(qpos + (size_t)(3 * q + 1) * stride + lc);
+            qz[q] = __ldg(qpos + (size_t)(3 * q + 2) * stride + lc);
+        }
+        // ---- half 0: planes --------------------------------------------------------------------
+#pragma unroll 1
+        for (int s = 0; s < kPlScales; ++s) {
+            const uint32_t R = cfg.pl_res[s];
+            const __half* b0 = P.pls16 + P.pls_scale[s];
+            float v[8];
+            plane2d_mul_h(b0, R, qx[0], qy[0], v, true);
+            plane2d_mul_h(b0 + (size_t)R * R * 8, R, qx[0], qz[0], v, false);
+            plane2d_mul_h(b0 + (size_t)2 * R * R * 8, R, qy[0], qz[0], v, false);
+            st_chunk(xg, t, s, v);
+        }
+#pragma unroll 1
+        for (int s = 0; s < kPlScales; ++s) {
+            const uint32_t R = cfg.pl_res[s];
+            float acc8[8];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const int qq = q == 0 ? 0 : (q == 1 ? qi1 : qi2);
+                const __half* b0 = P.pld16 + (size_t)qq * P.pld_per_q + P.pld_scale[s];
+                float v[8];
+                plane1d_mul_h(b0, R, qx[q], v, true);
+                plane1d_mul_h(b0 + (size_t)R * 8, R, qy[q], v, false);
+                plane1d_mul_h(b0 + (size_t)2 * R * 8, R, qz[q], v, false);
+                const float wq = q == 0 ? 0.5f : 0.25f;
+#pragma unroll
+                for (int f = 0; f < 8; ++f) acc8[f] = q == 0 ? wq * v[f] : fmaf(wq, v[f], acc8[f]);
+            }
+            st_chunk(xg, t, 4 + s, acc8);
+        }
+        fence_async_smem();
+        tc_fence_before();
+        wg_barrier(wg);
+        if (t == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (uint32_t k = 0; k < 4; ++k)
+                umma_f16(tcol, umma_desc(xs + k * 32), umma_desc(base + kOffW1 + k * 32), kIdesc1, k);
+            umma_commit(bar);
+        }
+        // ---- half 1: static hash, dyn rows -----------------------------------------------------
+#pragma unroll 1
+        for (int l = 0; l < kHsLevels; l += 2) {
+            float v[8];
+            hash3_f4(P.hs16, lv(cfg.hs[l]), qx[0], qy[0], qz[0], v);
+            hash3_f4(P.hs16, lv(cfg.hs[l + 1]), qx[0], qy[0], qz[0], v + 4);
+            if (l == 0) {  // the first-half MMAs must have read the tile before it is refilled
+                mbar_wait(bar, phase);
+                phase ^= 1u;
+            }
+            st_chunk(xg, t, l >> 1, v);
+        }
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+            uint32_t h[8];
+#pragma unroll
+            for (int l = 0; l < 8; ++l) h[l] = __ldcs(dyn_in + (size_t)(8 * p + l) * stride + lc);
+            *reinterpret_cast<uint4*>(xg + swz(t, 4 + p)) =
+                make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
+        }
+        *reinterpret_cast<uint4*>(xg + swz(t, 7)) = make_uint4(0, 0, 0, 0);
+        fence_async_smem();
+        tc_fence_before();
+        wg_barrier(wg);
+        if (t == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (uint32_t k = 0; k < 4; ++k)
+                umma_f16(tcol, umma_desc(xs + k * 32),
+                         umma_desc(base + kOffW1 + kHidden * 128 + k * 32), kIdesc1, 1u);
+            umma_commit(bar);
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+        tc_fence_after();
+        // ---- H = relu(D1) -> tile ----------------------------------------------------------------
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint32_t v[16];
+            tmem_ld16(tlane + q * 16, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float f[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = fmaxf(__uint_as_float(v[8 * h + j]), 0.f);
+                st_chunk(xg, t, 2 * q + h, f);
+            }
+        }
+        fence_async_smem();
+        tc_fence_before();
+        wg_barrier(wg);
+        if (t == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (uint32_t k = 0; k < 4; ++k)
+                umma_f16(tcol, umma_desc(xs + k * 32), umma_desc(base + kOffW2 + k * 32), kIdesc2, k);
+            umma_commit(bar);
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+        tc_fence_after();
+        {
+            uint32_t v[16];
+            tmem_ld16(tlane, v);
+            tmem_ld_wait();
+            if (live) {
+                sigma_out[li] = expf(__uint_as_float(v[0]));
+                uint4 a, b;
+                a.x = pack_half2(__uint_as_float(v[0]), __uint_as_float(v[1]));
+                a.y = pack_half2(__uint_as_float(v[2]), __uint_as_float(v[3]));
+                a.z = pack_half2(__uint_as_float(v[4]), __uint_as_float(v[5]));
+                a.w = pack_half2(__uint_as_float(v[6]), __uint_as_float(v[7]));
+                b.x = pack_half2(__uint_as_float(v[8]), __uint_as_float(v[9]));
+                b.y = pack_half2(__uint_as_float(v[10]), __uint_as_float(v[11]));
+                b.z = pack_half2(__uint_as_float(v[12]), __uint_as_float(v[13]));
+                b.w = pack_half2(__uint_as_float(v[14]), __uint_as_float(v[15]));
+                uint4* g = reinterpret_cast<uint4*>(geo_out + li * kGeo);
+                g[0] = a;
+                g[1] = b;
+            }
+        }
+        // the next tile's first MMA batch is issued behind a warpgroup barrier that every thread
+        // reaches only after this tcgen05.ld has completed (tc_fence_before precedes that barrier)
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (tid < 32)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(512u)
+                     : "memory");
+}
+
+bool g_fused_attr = false;
+
 }  // namespace
 
 size_t nvsf_sigma_tc_image_bytes() { return kW1Bytes + kW2Bytes; }
@@ -270,5 +392,21 @@ int nvsf_launch_sigma_tc(const void* wimg, const __half* feat, size_t count, flo
     const int grid = (int)std::min<size_t>(tiles, (size_t)sms * 4);
     k_sigma_stage_tc<<<grid, kRows, kTcSmem, stream>>>(reinterpret_cast<const unsigned char*>(wimg), feat,
                                                         count, sigma, geo);
+    return NVSF_OK;
+}
+
+int nvsf_launch_encode_sigma_tc(const nvsf_field_config_t* cfg, const FieldPtrs& P, const float* qpos,
+                                const void* dyn_in, size_t stride, size_t count, float* sigma,
+                                __half* geo, int sms, cudaStream_t stream) {
+    if (!g_fused_attr) {
+        cudaError_t e = cudaFuncSetAttribute(k_encode_sigma_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)kFusedSmem);
+        if (e != cudaSuccess) return (int)e;
+        g_fused_attr = true;
+    }
+    const size_t tiles = (count + kRows - 1) / kRows;
+    const int grid = (int)std::min<size_t>((tiles + kFusedWG - 1) / kFusedWG, (size_t)sms);
+    k_encode_sigma_tc<<<grid, kFusedThreads, kFusedSmem, stream>>>(
+        *cfg, P, qpos, reinterpret_cast<const unsigned short*>(dyn_in), stride, count, sigma, geo);
     return NVSF_OK;
 }

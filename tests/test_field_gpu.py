@@ -246,3 +246,28 @@ def test_sigma_stage_tcgen05_matches_mma_sync(pkg, model, n):
         L.nvsf_set_option(b"sigma_tc", 1)
     close(out[1][0], out[0][0], 2e-3, 0, "sigma tcgen05 vs mma.sync")
     close(out[1][1], out[0][1], 2e-3, 2e-3 * np.abs(out[0][1]).max(), "geo tcgen05 vs mma.sync")
+
+
+@pytest.mark.parametrize("n", [1024 * 9, 100001])
+def test_fused_gather_sigma_tcgen05_matches_staged(pkg, model, n):
+    """Mode 2 with the gather stage fused with the sigma MLP (k_encode_sigma_tc: feature rows written
+    straight into the swizzled UMMA operand tile, two K halves accumulated in TMEM) against the staged
+    pair k_encode_stage -> k_sigma_stage_tc: identical features, so sigma / geo / rendered outputs agree
+    to the rounding of the fp32 accumulation order."""
+    L = pkg._lib.lib()
+    x = torch.from_numpy(pts(n, 23)).cuda()
+    o, d = S.lidar_rays(500, seed=12)
+    to, td = torch.from_numpy(o).cuda()[None], torch.from_numpy(d).cuda()[None]
+    out = {}
+    try:
+        for fuse in (0, 1):
+            assert L.nvsf_set_option(b"fuse_sigma", fuse) == 0
+            den = model.density(x, 0.45, False)
+            with torch.no_grad():
+                r = model.render(to, td, torch.tensor([[0.45]], device="cuda"), cal_lidar_color=True, num_steps=96)
+            torch.cuda.synchronize()
+            out[fuse] = (host(den["sigma"]), host(den["geo_feat"]), host(r["depth_lidar"]), host(r["image_lidar"]))
+    finally:
+        L.nvsf_set_option(b"fuse_sigma", 1)
+    for a, b, name in zip(out[1], out[0], ("sigma", "geo", "depth", "image")):
+        close(a, b, 1e-3, 1e-3 * np.abs(b).max(), f"fused vs staged {name}")
