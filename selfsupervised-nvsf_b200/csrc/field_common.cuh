@@ -39,7 +39,7 @@ struct WsLayout {
     size_t pls16;     // __half mirror of pls (same element offsets): one 16-byte texel
     size_t pld16;     // __half mirror of pld
     size_t flow16;    // __half2 [fl_entries]                       fp16 mirror of flow
-    size_t mlp_tc;    // sigma-net operand images for tcgen05.mma (sigma_tc.cu), 18 KB
+    size_t mlp_tc;    // sigma-net and flow-MLP operand images for tcgen05.mma (sigma_tc.cu), 2 x 18 KB
     size_t total;
     size_t pls_scale[NVSF_MAX_PLANE_SCALES];  // float offsets inside pls
     size_t pld_scale[NVSF_MAX_PLANE_SCALES];  // float offsets inside one query of pld
@@ -107,7 +107,7 @@ static inline WsLayout make_ws_layout(const nvsf_field_config_t* c) {
     L.pls16 = off; off = ws_align(off + f * sizeof(__half));
     L.pld16 = off; off = ws_align(off + 3 * g * sizeof(__half));
     L.flow16 = off; off = ws_align(off + (size_t)c->fl_entries * sizeof(__half2));
-    L.mlp_tc = off; off = ws_align(off + (size_t)(kHidden * kFeat + kGeo * kHidden) * sizeof(__half));
+    L.mlp_tc = off; off = ws_align(off + 2 * (size_t)(kHidden * kFeat + kGeo * kHidden) * sizeof(__half));
     L.total = off;
     return L;
 }
@@ -159,6 +159,11 @@ int nvsf_density_mode();
 void nvsf_pack_sigma_tc(const __half* mlp, void* dst, cudaStream_t stream);
 int nvsf_launch_sigma_tc(const void* wimg, const __half* feat, size_t count, float* sigma,
                          __half* geo, int sms, cudaStream_t stream);
+// flow stage on tcgen05 (mode 2): flow [n,8] + planar query positions qpos[9][stride]
+int nvsf_launch_flow_tc(const nvsf_field_config_t* cfg, const FieldPtrs& P, const float* x,
+                        const float* rays_o, const float* rays_d, const float* nears, const float* fars,
+                        const float* noise, uint32_t S, size_t begin, size_t count, float* flow_out,
+                        float* qpos, size_t stride, int sms, cudaStream_t stream);
 // gather stage fused with the sigma MLP (mode 2 intermediates: query positions + dyn rows)
 int nvsf_launch_encode_sigma_tc(const nvsf_field_config_t* cfg, const FieldPtrs& P, const float* qpos,
                                 const void* dyn_in, size_t stride, size_t count, float* sigma,
@@ -569,3 +574,39 @@ __device__ __forceinline__ float uniform_z(float near, float far, uint32_t k, ui
     return z;
 }
 
+// normalised position in [0,1]^3 of sample g: explicit point xin[g], or uniform sample g % S of ray
+// g / S (renderer_dynamic.py:155-169: linspace z, optional jitter, clip to the box)
+template <bool FROM_RAYS>
+__device__ __forceinline__ void sample_position(const nvsf_field_config_t& cfg, size_t g,
+                                                const float* __restrict__ xin,
+                                                const float* __restrict__ rays_o,
+                                                const float* __restrict__ rays_d,
+                                                const float* __restrict__ nears,
+                                                const float* __restrict__ fars,
+                                                const float* __restrict__ noise, uint32_t S,
+                                                float& x, float& y, float& z) {
+    float px, py, pz;
+    if (FROM_RAYS) {
+        size_t r;
+        uint32_t k;
+        if ((g >> 32) == 0) {  // 32-bit division: the 64-bit one costs ~100 instructions per call
+            const uint32_t g32 = (uint32_t)g, r32 = g32 / S;
+            r = r32;
+            k = g32 - r32 * S;
+        } else {
+            r = g / S;
+            k = (uint32_t)(g - r * S);
+        }
+        const float zz = uniform_z(__ldg(nears + r), __ldg(fars + r), k, S, noise, g);
+        px = __ldg(rays_o + r * 3 + 0) + __ldg(rays_d + r * 3 + 0) * zz;
+        py = __ldg(rays_o + r * 3 + 1) + __ldg(rays_d + r * 3 + 1) * zz;
+        pz = __ldg(rays_o + r * 3 + 2) + __ldg(rays_d + r * 3 + 2) * zz;
+        px = fminf(fmaxf(px, -cfg.bound), cfg.bound);
+        py = fminf(fmaxf(py, -cfg.bound), cfg.bound);
+        pz = fminf(fmaxf(pz, -cfg.bound), cfg.bound);
+    } else {
+        px = __ldg(xin + g * 3 + 0); py = __ldg(xin + g * 3 + 1); pz = __ldg(xin + g * 3 + 2);
+    }
+    const float inv2b = 1.0f / (2.0f * cfg.bound);
+    x = (px + cfg.bound) * inv2b; y = (py + cfg.bound) * inv2b; z = (pz + cfg.bound) * inv2b;
+}

@@ -34,41 +34,6 @@ constexpr int kSigWHalves = kDensityWHalves - kSigW1;
 constexpr int kSigTile = 384;  // rows per CTA tile of the sigma stage: 12 warps x 32 rows, 1 CTA per SM
 constexpr size_t kSigmaStageSmem = (size_t)kSigWHalves * 2 + (size_t)2 * kSigTile * kLdK128 * 2;  // two tile buffers per warp (223 KB)
 
-template <bool FROM_RAYS>
-__device__ __forceinline__ void sample_position(const nvsf_field_config_t& cfg, size_t g,
-                                                const float* __restrict__ xin,
-                                                const float* __restrict__ rays_o,
-                                                const float* __restrict__ rays_d,
-                                                const float* __restrict__ nears,
-                                                const float* __restrict__ fars,
-                                                const float* __restrict__ noise, uint32_t S,
-                                                float& x, float& y, float& z) {
-    float px, py, pz;
-    if (FROM_RAYS) {
-        size_t r;
-        uint32_t k;
-        if ((g >> 32) == 0) {  // 32-bit division: the 64-bit one costs ~100 instructions per call
-            const uint32_t g32 = (uint32_t)g, r32 = g32 / S;
-            r = r32;
-            k = g32 - r32 * S;
-        } else {
-            r = g / S;
-            k = (uint32_t)(g - r * S);
-        }
-        const float zz = uniform_z(__ldg(nears + r), __ldg(fars + r), k, S, noise, g);
-        px = __ldg(rays_o + r * 3 + 0) + __ldg(rays_d + r * 3 + 0) * zz;
-        py = __ldg(rays_o + r * 3 + 1) + __ldg(rays_d + r * 3 + 1) * zz;
-        pz = __ldg(rays_o + r * 3 + 2) + __ldg(rays_d + r * 3 + 2) * zz;
-        px = fminf(fmaxf(px, -cfg.bound), cfg.bound);
-        py = fminf(fmaxf(py, -cfg.bound), cfg.bound);
-        pz = fminf(fmaxf(pz, -cfg.bound), cfg.bound);
-    } else {
-        px = __ldg(xin + g * 3 + 0); py = __ldg(xin + g * 3 + 1); pz = __ldg(xin + g * 3 + 2);
-    }
-    const float inv2b = 1.0f / (2.0f * cfg.bound);
-    x = (px + cfg.bound) * inv2b; y = (py + cfg.bound) * inv2b; z = (pz + cfg.bound) * inv2b;
-}
-
 // ---- stage 1: flow -----------------------------------------------------------------------------
 template <bool FROM_RAYS, bool TAB16>
 __global__ void __launch_bounds__(kSTile, 2)
@@ -670,6 +635,7 @@ int ensure_attrs() {
     return NVSF_OK;
 }
 
+int g_flow_tc = 1;     // mode 2: flow stage on tcgen05 (sigma_tc.cu k_flow_tc, option "flow_tc")
 int g_fuse_sigma = 1;  // mode 2: gather stage fused with the sigma MLP on tcgen05 (option "fuse_sigma")
 int g_sigma_tc = 1;  // sigma stage on tcgen05 / TMEM (sigma_tc.cu) instead of mma.sync (option "sigma_tc"):
                      // 3.33 -> 2.51 ms per LiDAR frame on B200, at the DRAM floor of the 292 B/sample it streams
@@ -748,9 +714,14 @@ int nvsf_launch_density_split(const nvsf_field_config_t* cfg, const void* worksp
         if (dyn_pre) cudaMemsetAsync(counters, 0, kDynMaxTypes * sizeof(uint32_t), stream);
         const unsigned short* dyn_in = reinterpret_cast<const unsigned short*>(dyn_buf);
         const bool fused = dyn_pre && !keep && !features && g_fuse_sigma != 0;
+        const bool flow_tc = dyn_pre && !keep && g_flow_tc != 0;
         if (g_prof.on) g_prof.next(stream);
         if (x) {
-            if (dyn_pre)
+            if (flow_tc) {
+                st = nvsf_launch_flow_tc(cfg, P, x, nullptr, nullptr, nullptr, nullptr, nullptr, 1, begin,
+                                         count, flow_buf, qpos_buf, count, sms, stream);
+                if (st != NVSF_OK) return st;
+            } else if (dyn_pre)
                 k_flow_stage<false, true><<<grid_p, kSTile, kFlowStageSmem, stream>>>(
                     *cfg, P, x, nullptr, nullptr, nullptr, nullptr, nullptr, 1, begin, count, flow_buf, ff,
                     qpos_buf, count);
@@ -770,7 +741,11 @@ int nvsf_launch_density_split(const nvsf_field_config_t* cfg, const void* worksp
                                      flow_buf, feat_buf, dyn_pre ? dyn_in : nullptr, dyn_pre ? count : 0);
             }
         } else {
-            if (dyn_pre)
+            if (flow_tc) {
+                st = nvsf_launch_flow_tc(cfg, P, nullptr, rays_o, rays_d, nears, fars, noise, S, begin,
+                                         count, flow_buf, qpos_buf, count, sms, stream);
+                if (st != NVSF_OK) return st;
+            } else if (dyn_pre)
                 k_flow_stage<true, true><<<grid_p, kSTile, kFlowStageSmem, stream>>>(
                     *cfg, P, nullptr, rays_o, rays_d, nears, fars, noise, S, begin, count, flow_buf, ff,
                     qpos_buf, count);
@@ -830,6 +805,11 @@ int nvsf_split_set_option(const char* name, int value) {
     if (k == "dyn_overhead") {
         if (value < 0 || value > 1000) return NVSF_E_INVALID;
         g_dyn_overhead = value;
+        return NVSF_OK;
+    }
+    if (k == "flow_tc") {
+        if (value != 0 && value != 1) return NVSF_E_INVALID;
+        g_flow_tc = value;
         return NVSF_OK;
     }
     if (k == "fuse_sigma") {

@@ -35,6 +35,27 @@ __global__ void k_pack_sigma_tc(const __half* __restrict__ mlp, unsigned char* _
     }
 }
 
+
+// flow MLP (flow_field.py:87-103: 32 -> 64 -> 64 -> 6, no bias) operand images, same sizes as the
+// sigma images: [W1: 64 rows x 128 B, K = 32 uses the first 64 B][W2: 64 rows x 128 B][W3: 16 rows x
+// 128 B, rows 6..15 zero].  `dst` is zero-filled by the caller.
+__global__ void k_pack_flow_tc(const __half* __restrict__ mlp, unsigned char* __restrict__ dst) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;  // one 16-byte chunk each
+    if (i < (uint32_t)kHidden * 4) {                           // W1 [64][32]
+        const uint32_t r = i >> 2, c = i & 3;
+        const uint4 v = *reinterpret_cast<const uint4*>(mlp + kFlowW1 + r * kLdK32 + c * 8);
+        *reinterpret_cast<uint4*>(dst + swz(r, c)) = v;
+    } else if (i < (uint32_t)kHidden * 12) {                   // W2 [64][64]
+        const uint32_t j = i - kHidden * 4, r = j >> 3, c = j & 7;
+        const uint4 v = *reinterpret_cast<const uint4*>(mlp + kFlowW2 + r * kLdK64 + c * 8);
+        *reinterpret_cast<uint4*>(dst + kHidden * 128 + swz(r, c)) = v;
+    } else if (i < (uint32_t)kHidden * 12 + 8 * 8) {           // W3 [8][64] (rows 6, 7 are zero)
+        const uint32_t j = i - kHidden * 12, r = j >> 3, c = j & 7;
+        const uint4 v = *reinterpret_cast<const uint4*>(mlp + kFlowW3 + r * kLdK64 + c * 8);
+        *reinterpret_cast<uint4*>(dst + 2 * kHidden * 128 + swz(r, c)) = v;
+    }
+}
+
 __global__ void __launch_bounds__(kRows, 4)
 k_sigma_stage_tc(const unsigned char* __restrict__ wimg, const __half* __restrict__ feat,
                  size_t count, float* __restrict__ sigma_out, __half* __restrict__ geo_out) {
@@ -371,13 +392,162 @@ k_encode_sigma_tc(const __grid_constant__ nvsf_field_config_t cfg,
 
 bool g_fused_attr = false;
 
+// ---- flow stage on tcgen05 -------------------------------------------------------------------------
+// FlowField.forward (flow_field.py:116-133) for 128-sample warpgroup tiles: the 16-level collapsed
+// flow-grid gather fills K = 32 of the operand tile, then three chained tcgen05.mma batches
+// (32 -> 64 relu, 64 -> 64 relu, 64 -> 16 of which 6 are the flow) with the hidden activations going
+// TMEM -> registers -> the same tile.  The mma.sync flow stage needs 128 registers for its
+// accumulators and runs its gathers at 24 % occupancy (stall long_scoreboard); here the accumulators
+// live in TMEM and the gather threads stay at 64 registers, 32 warps per SM.
+// Outputs: flow [n,8] f32 (6 used) and the three query positions, planar qpos[9][stride].
+template <bool FROM_RAYS>
+__global__ void __launch_bounds__(kFusedThreads, 1)
+k_flow_tc(const __grid_constant__ nvsf_field_config_t cfg, const __grid_constant__ FieldPtrs P,
+          const float* __restrict__ xin, const float* __restrict__ rays_o,
+          const float* __restrict__ rays_d, const float* __restrict__ nears,
+          const float* __restrict__ fars, const float* __restrict__ noise, uint32_t S, size_t begin,
+          size_t count, float* __restrict__ flow_out, float* __restrict__ qpos, size_t stride) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    unsigned char* sm = smem_raw + (base - raw);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + kFOffBar + 8 * kFusedWG);
+    const uint32_t tid = threadIdx.x, wg = tid >> 7, t = tid & 127u;
+    const unsigned char* wimg = reinterpret_cast<const unsigned char*>(P.mlp_tc) + (kW1Bytes + kW2Bytes);
+
+    for (uint32_t i = tid; i < (kW1Bytes + kW2Bytes) / 16; i += kFusedThreads)
+        reinterpret_cast<uint4*>(sm)[i] = __ldg(reinterpret_cast<const uint4*>(wimg) + i);
+    if (tid < (uint32_t)kFusedWG) mbar_init(base + kFOffBar + 8 * tid, 1);
+    if (tid < 32) {
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(
+                         smem_u32(tmem_slot)),
+                     "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t tcol = tmem + wg * 64u;
+    const uint32_t tlane = tcol + ((((tid >> 5) & 3u) * 32u) << 16);
+    const uint32_t xs = base + kFOffX + wg * kFTile;
+    unsigned char* xg = sm + kFOffX + wg * kFTile;
+    const uint32_t bar = base + kFOffBar + 8 * wg;
+    const uint32_t w1 = base, w2 = base + kHidden * 128, w3 = base + 2 * kHidden * 128;
+    constexpr uint32_t kIdesc64 = umma_idesc(kRows, kHidden), kIdesc16 = umma_idesc(kRows, 16);
+    const int valid1 = P.ti->valid[1], valid2 = P.ti->valid[2];
+
+    uint32_t phase = 0;
+    const size_t n_tiles = (count + kRows - 1) / kRows;
+    for (size_t tile = (size_t)blockIdx.x * kFusedWG + wg; tile < n_tiles;
+         tile += (size_t)gridDim.x * kFusedWG) {
+        const size_t li = tile * kRows + t;
+        const bool live = li < count;
+        float x, y, z;
+        sample_position<FROM_RAYS>(cfg, begin + (live ? li : count - 1), xin, rays_o, rays_d, nears, fars,
+                                   noise, S, x, y, z);
+        // flow-grid features: 4 levels -> 8 halves -> one 16-byte chunk
+#pragma unroll 1
+        for (int c = 0; c < kFlLevels / 4; ++c) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = hash3_h2(P.flow16, lv(cfg.fl[4 * c + j]), x, y, z);
+                v[2 * j] = f.x;
+                v[2 * j + 1] = f.y;
+            }
+            st_chunk(xg, t, c, v);
+        }
+        fence_async_smem();
+        tc_fence_before();
+        wg_barrier(wg);
+        if (t == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (uint32_t k = 0; k < kFlowIn / 16; ++k)
+                umma_f16(tcol, umma_desc(xs + k * 32), umma_desc(w1 + k * 32), kIdesc64, k);
+            umma_commit(bar);
+        }
+        // two hidden layers: D -> relu -> fp16 tile -> next MMA batch
+#pragma unroll 1
+        for (int layer = 0; layer < 2; ++layer) {
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+            tc_fence_after();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint32_t v[16];
+                tmem_ld16(tlane + q * 16, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    float f[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) f[j] = fmaxf(__uint_as_float(v[8 * h + j]), 0.f);
+                    st_chunk(xg, t, 2 * q + h, f);
+                }
+            }
+            fence_async_smem();
+            tc_fence_before();
+            wg_barrier(wg);
+            if (t == 0) {
+                tc_fence_after();
+                const uint32_t wb = layer == 0 ? w2 : w3;
+                const uint32_t idesc = layer == 0 ? kIdesc64 : kIdesc16;
+#pragma unroll
+                for (uint32_t k = 0; k < kHidden / 16; ++k)
+                    umma_f16(tcol, umma_desc(xs + k * 32), umma_desc(wb + k * 32), idesc, k);
+                umma_commit(bar);
+            }
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+        tc_fence_after();
+        {
+            uint32_t v[16];
+            tmem_ld16(tlane, v);
+            tmem_ld_wait();
+            if (live) {
+                const float4 f0 = make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]),
+                                              __uint_as_float(v[2]), __uint_as_float(v[3]));
+                const float4 f1 = make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]),
+                                              __uint_as_float(v[6]), __uint_as_float(v[7]));
+                float4* d = reinterpret_cast<float4*>(flow_out + li * 8);
+                d[0] = f0;
+                d[1] = f1;
+                float* q = qpos + li;
+                q[0] = x; q[stride] = y; q[2 * stride] = z;
+                q[3 * stride] = valid1 ? x + f0.x : x;
+                q[4 * stride] = valid1 ? y + f0.y : y;
+                q[5 * stride] = valid1 ? z + f0.z : z;
+                q[6 * stride] = valid2 ? x + f0.w : x;
+                q[7 * stride] = valid2 ? y + f1.x : y;
+                q[8 * stride] = valid2 ? z + f1.y : z;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (tid < 32)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(512u)
+                     : "memory");
+}
+
+bool g_flow_attr = false;
+
 }  // namespace
 
-size_t nvsf_sigma_tc_image_bytes() { return kW1Bytes + kW2Bytes; }
+size_t nvsf_sigma_tc_image_bytes() { return 2 * (size_t)(kW1Bytes + kW2Bytes); }
 
+// [sigma-net images][flow-MLP images], 18 KB each
 void nvsf_pack_sigma_tc(const __half* mlp, void* dst, cudaStream_t stream) {
-    k_pack_sigma_tc<<<nvsf_div_up(kHidden * 16 + kGeo * 8, 128), 128, 0, stream>>>(
-        mlp, reinterpret_cast<unsigned char*>(dst));
+    unsigned char* d = reinterpret_cast<unsigned char*>(dst);
+    cudaMemsetAsync(d, 0, nvsf_sigma_tc_image_bytes(), stream);
+    k_pack_sigma_tc<<<nvsf_div_up(kHidden * 16 + kGeo * 8, 128), 128, 0, stream>>>(mlp, d);
+    k_pack_flow_tc<<<nvsf_div_up(kHidden * 12 + 64, 128), 128, 0, stream>>>(mlp, d + kW1Bytes + kW2Bytes);
 }
 
 int nvsf_launch_sigma_tc(const void* wimg, const __half* feat, size_t count, float* sigma,
@@ -408,5 +578,29 @@ int nvsf_launch_encode_sigma_tc(const nvsf_field_config_t* cfg, const FieldPtrs&
     const int grid = (int)std::min<size_t>((tiles + kFusedWG - 1) / kFusedWG, (size_t)sms);
     k_encode_sigma_tc<<<grid, kFusedThreads, kFusedSmem, stream>>>(
         *cfg, P, qpos, reinterpret_cast<const unsigned short*>(dyn_in), stride, count, sigma, geo);
+    return NVSF_OK;
+}
+
+int nvsf_launch_flow_tc(const nvsf_field_config_t* cfg, const FieldPtrs& P, const float* x,
+                        const float* rays_o, const float* rays_d, const float* nears, const float* fars,
+                        const float* noise, uint32_t S, size_t begin, size_t count, float* flow_out,
+                        float* qpos, size_t stride, int sms, cudaStream_t stream) {
+    if (!g_flow_attr) {
+        cudaError_t e = cudaFuncSetAttribute(k_flow_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)kFusedSmem);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaFuncSetAttribute(k_flow_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)kFusedSmem);
+        if (e != cudaSuccess) return (int)e;
+        g_flow_attr = true;
+    }
+    const size_t tiles = (count + kRows - 1) / kRows;
+    const int grid = (int)std::min<size_t>((tiles + kFusedWG - 1) / kFusedWG, (size_t)sms);
+    if (x)
+        k_flow_tc<false><<<grid, kFusedThreads, kFusedSmem, stream>>>(
+            *cfg, P, x, nullptr, nullptr, nullptr, nullptr, nullptr, 1, begin, count, flow_out, qpos, stride);
+    else
+        k_flow_tc<true><<<grid, kFusedThreads, kFusedSmem, stream>>>(
+            *cfg, P, nullptr, rays_o, rays_d, nears, fars, noise, S, begin, count, flow_out, qpos, stride);
     return NVSF_OK;
 }

@@ -271,3 +271,26 @@ def test_fused_gather_sigma_tcgen05_matches_staged(pkg, model, n):
         L.nvsf_set_option(b"fuse_sigma", 1)
     for a, b, name in zip(out[1], out[0], ("sigma", "geo", "depth", "image")):
         close(a, b, 1e-3, 1e-3 * np.abs(b).max(), f"fused vs staged {name}")
+
+
+@pytest.mark.parametrize("t", [0.45, 0.0])
+def test_flow_stage_tcgen05_matches_mma_sync(pkg, model, t):
+    """Flow stage on tcgen05 (k_flow_tc: flow-grid gather into the UMMA operand tile, three chained
+    MMA batches through TMEM) against the mma.sync flow stage: flow, and everything downstream."""
+    L = pkg._lib.lib()
+    x = torch.from_numpy(pts(70001, 29)).cuda()
+    out = {}
+    try:
+        for tc in (0, 1):
+            assert L.nvsf_set_option(b"flow_tc", tc) == 0
+            f = model.flow(x, t)
+            den = model.density(x, t, True)
+            torch.cuda.synchronize()
+            out[tc] = (np.concatenate([host(f["flow_forward"]), host(f["flow_backward"])], -1),
+                       host(den["sigma"]), host(den["geo_feat"]))
+    finally:
+        L.nvsf_set_option(b"flow_tc", 1)
+    assert np.abs(out[0][0]).max() > 1e-4
+    close(out[1][0], out[0][0], 2e-3, 2e-3 * np.abs(out[0][0]).max(), "flow tcgen05 vs mma.sync")
+    close(out[1][1], out[0][1], 2e-3, 0, "sigma")
+    close(out[1][2], out[0][2], 2e-3, 2e-3 * np.abs(out[0][2]).max(), "geo")
