@@ -44,18 +44,30 @@ SURVEY_BYTES_PER_SAMPLE = 13312 + 48  # the reference's un-colla
 #   mode 1 (fp32 collapsed tables):  flow stage  = flow grid 16 x 8 x 8 B + 32 B flow out
 #                                    encode stage = static hash 512 + collapsed dyn hash 1152 + space planes
 #                                                   1536 + time planes 2304 + flow in 32 + feature row out 256
-#   mode 2 (fp16 mirrors, default):  flow stage  = 16 x 8 x 4 B + 32
+#                                    sigma stage  = feature row in 256 + sigma f32 + geo f16[16] out 36
+#   mode 2 (fp16 mirrors, default):  flow stage  = 16 x 8 x 4 B + flow out 32 + query positions out 36
 #                                    dyn stage   = 288 two-byte gathers from shared-memory tables (576) +
-#                                                  flow in 32 + 24 fp16 values out 48
-#                                    encode stage = static hash 512 + fp16 space planes 768 + fp16 time planes
-#                                                   1152 + dyn in 48 + flow in 32 + feature row out 256
-#   sigma stage (both)               = feature row in 256 + sigma f32 + geo f16[16] out 36
-STAGE_BYTES = {
-    1: {"flow_stage": 1024 + 32, "dyn_stage": 0, "encode_stage": 512 + 1152 + 1536 + 2304 + 32 + 256, "sigma_stage": 256 + 36},
-    2: {"flow_stage": 512 + 32, "dyn_stage": 576 + 32 + 48, "encode_stage": 512 + 768 + 1152 + 48 + 32 + 256, "sigma_stage": 256 + 36},
-}
-STAGE_KERNEL = {"flow_stage": "k_flow_stage", "dyn_stage": "k_dyn_stage", "encode_stage": "k_encode_stage",
-                "sigma_stage": "k_sigma_stage"}
+#                                                  query positions in 36 + 24 fp16 values out 48
+#                                    encode stage (fused with the sigma MLP, tcgen05) = static hash 512 +
+#                                                  fp16 space planes 768 + fp16 time planes 1152 + dyn in 48 +
+#                                                  query positions in 36 + sigma / geo out 36
+#                                    (un-fused: + feature row out 256 instead of the 36; sigma stage 256 + 36)
+def stage_table(L):
+    """(bytes per sample, kernel name) per stage for the options the library is running with."""
+    opt = lambda k: int(L.nvsf_get_option(k))
+    mode = opt(b"density_mode")
+    if mode != 2:
+        return mode, {"flow_stage": (1024 + 32, "k_flow_stage"), "dyn_stage": (0, "-"),
+                      "encode_stage": (512 + 1152 + 1536 + 2304 + 32 + 256, "k_encode_stage"),
+                      "sigma_stage": (256 + 36, "k_sigma_stage_tc" if opt(b"sigma_tc") else "k_sigma_stage")}
+    fused = bool(opt(b"fuse_sigma"))
+    return mode, {
+        "flow_stage": (512 + 32 + 36, "k_flow_tc" if opt(b"flow_tc") else "k_flow_stage"),
+        "dyn_stage": (576 + 36 + 48, "k_dyn_stage"),
+        "encode_stage": (512 + 768 + 1152 + 48 + 36 + (36 if fused else 256),
+                         "k_encode_sigma_tc" if fused else "k_encode_stage"),
+        "sigma_stage": (0 if fused else 256 + 36, "-" if fused else
+                        ("k_sigma_stage_tc" if opt(b"sigma_tc") else "k_sigma_stage"))}
 
 
 def peaks():
@@ -454,19 +466,19 @@ def main():
     n_samples = N * Sn
     n_launch = max(int(stage_launches.value), 1)            # chunks of the staged evaluation, all timed steps
     flow_ms, dyn_ms, enc_ms, sig_ms = (float(stage_ms[i]) / args.steps for i in range(4))
-    mode = int(L.nvsf_density_mode_get())
+    mode, table = stage_table(L)
     stage_step_ms = {"flow_stage": flow_ms, "dyn_stage": dyn_ms, "encode_stage": enc_ms, "sigma_stage": sig_ms}
     top = max(stage_step_ms, key=stage_step_ms.get)          # the dominant kernel of the step
-    top_bytes = STAGE_BYTES.get(mode, STAGE_BYTES[1])[top]
+    top_bytes, top_kernel = table[top]
     top_launch_ms = stage_step_ms[top] * args.steps / n_launch   # average duration of one launch of it
     samples_per_launch = n_samples * args.steps / n_launch
     achieved = top_bytes * samples_per_launch / (top_launch_ms * 1e-3) / 1e9
     traffic, limiter = None, None
     tr_path = os.path.join(ROOT, "profiles", "dominant_stage_ncu.json")
     if os.path.exists(tr_path):   # from the committed ncu --set full capture of this command
-        tr = json.load(open(tr_path)).get(f"mode{mode}", {}).get(top, {})
+        tr = json.load(open(tr_path)).get(top_kernel, {})
         traffic, limiter = tr.get("dram_bytes_per_launch"), tr.get("limiter")
-    kernels_per_chunk = 4 if mode == 2 else 3
+    kernels_per_chunk = sum(1 for b, k in table.values() if k != "-")
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -480,7 +492,7 @@ def main():
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(2 * N * 3 * 4), "d2h_bytes_per_step": int(N * 3 * 4)},
         "gpu_launches": (9 + 1 + kernels_per_chunk * n_launch // args.steps) * args.steps,
-        "roofline": {"bound": "hbm", "kernel": STAGE_KERNEL[top], "density_mode": mode, "achieved": achieved,
+        "roofline": {"bound": "hbm", "kernel": top_kernel, "density_mode": mode, "achieved": achieved,
                      "peak": pk["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk_kind,
                      "bytes_per_sample": top_bytes, "survey_bytes_per_sample": SURVEY_BYTES_PER_SAMPLE,
@@ -488,7 +500,10 @@ def main():
                      "launches_per_step": n_launch / args.steps,
                      "share_of_step": stage_step_ms[top] / (ms_total / args.steps),
                      "limiter": limiter,
-                     "note": "algorithmic bytes are table gathers; the 75 MB of tables are L2 resident, so the "
+                     "stages": {k: {"kernel": table[k][1], "ms_per_step": stage_step_ms[k], "bytes_per_sample": table[k][0],
+                                    "achieved_gbs": (table[k][0] * n_samples / (stage_step_ms[k] * 1e-3) / 1e9
+                                                     if stage_step_ms[k] > 0.1 else None)} for k in table},
+                     "note": "algorithmic bytes are table gathers; the 40 MB of fp16 tables are L2 resident, so the "
                              "achieved figure may exceed the HBM peak while DRAM traffic stays far below it"},
     }
     out.update(train)

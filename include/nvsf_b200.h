@@ -33,7 +33,7 @@ extern "C" {
 #define NVSF_E_WORKSPACE (-2) /* workspace too small */
 
 /* ABI version of this header; bumped on any signature change. */
-#define NVSF_B200_ABI_VERSION 9
+#define NVSF_B200_ABI_VERSION 10
 int nvsf_abi_version(void);
 /* Human-readable text for a status returned by any nvsf_* call. */
 const char* nvsf_status_string(int status);
@@ -244,12 +244,17 @@ int nvsf_field_color(const nvsf_field_config_t* cfg, const void* workspace, uint
                      const float* dirs, const void* geo, uint32_t geo_ld, uint32_t geo_off,
                      const uint8_t* mask, uint32_t n, float* out, uint32_t out_ld, void* stream);
 
-/* Tuning switches.  "density_mode": 1 = staged density evaluation (flow stage, lean gather stage
- * at high occupancy, MLP stage; needs the scratch buffer), 2 = staged, with the 72 time-collapsed
- * 2-D hash tables gathered from shared memory (TMA-staged, k_dyn_stage), 0 = single fused kernel.
+/* Tuning switches.  "density_mode": 2 (default) = staged density evaluation on fp16 table mirrors:
+ * flow stage, the 72 time-collapsed 2-D hash tables gathered from shared memory (TMA-staged,
+ * k_dyn_stage), gather stage, sigma MLP; 1 = staged on the fp32 collapsed tables without the dyn stage
+ * (what the training forward runs); 0 = single fused mma.sync kernel.
+ * Mode-2 sub-switches (all default 1): "flow_tc" = flow stage on tcgen05 / TMEM, "fuse_sigma" = gather
+ * stage fused with the sigma MLP on tcgen05 (feature rows stay on the SM), "sigma_tc" = stand-alone
+ * sigma stage on tcgen05 (when not fused).  "enc_pair" (default 0) = paired static-hash corner loads.
  * "dyn_tile" (samples per work item), "dyn_overhead", "split_chunk" (units of 64 K samples) tune
- * the staged evaluation. */
+ * the staged evaluation.  nvsf_get_option returns the current value (NVSF_E_INVALID: unknown name). */
 int nvsf_set_option(const char* name, int value);
+int nvsf_get_option(const char* name);
 int nvsf_density_mode_get(void); /* current "density_mode" */
 /* "stage_timing": 1 records CUDA events on the launching stream around the kernels of every
  * chunk of the staged density evaluation; nvsf_stage_timing_read sums them since the last read:

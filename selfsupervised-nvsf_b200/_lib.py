@@ -65,6 +65,7 @@ PROTOTYPES = {
     "nvsf_field_density": (_int, [_p, _p, _p, _u32, _p, _p, _p, _p, _p, _sz, _p]),
     "nvsf_set_option": (_int, [ctypes.c_char_p, _int]),
     "nvsf_density_mode_get": (_int, []),
+    "nvsf_get_option": (_int, [ctypes.c_char_p]),
     "nvsf_stage_timing_read": (_int, [_p, _p]),
     "nvsf_render_uniform_scratch_bytes": (_sz, [_u32, _u32]),
     "nvsf_render_uniform_density": (_int, [_p, _p, _p, _p, _p, _p, _p, _u32, _u32, _p, _sz, _p]),
@@ -123,7 +124,7 @@ def lib():
     return _lib
 
 
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 
 def check(status, what=""):

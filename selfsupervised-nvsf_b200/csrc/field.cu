@@ -641,6 +641,12 @@ int nvsf_set_option(const char* name, int value) {
 }
 
 int nvsf_density_mode_get(void) { return g_density_mode_value; }
+int nvsf_get_option(const char* name) {
+    if (!name) return NVSF_E_INVALID;
+    if (std::string(name) == "density_mode") return g_density_mode_value;
+    if (std::string(name) == "march_mode") return g_march_mode_value;
+    return nvsf_split_get_option(name);
+}
 
 }  // extern "C"
 

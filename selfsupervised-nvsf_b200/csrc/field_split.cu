@@ -835,6 +835,18 @@ int nvsf_split_set_option(const char* name, int value) {
     return NVSF_E_INVALID;
 }
 
+int nvsf_split_get_option(const char* name) {
+    const std::string k(name);
+    if (k == "dyn_tile") return g_dyn_tile;
+    if (k == "dyn_overhead") return g_dyn_overhead;
+    if (k == "split_chunk") return (int)(g_split_chunk / 65536);
+    if (k == "enc_pair") return g_enc_pair;
+    if (k == "sigma_tc") return g_sigma_tc;
+    if (k == "fuse_sigma") return g_fuse_sigma;
+    if (k == "flow_tc") return g_flow_tc;
+    return NVSF_E_INVALID;
+}
+
 // ---- stage timing (see StageProf) -------------------------------------------------------------------
 void nvsf_stage_timing_enable(int on) {
     g_prof.on = on != 0;

@@ -23,7 +23,7 @@ done
 cat gpurun_out/ab.txt
 if [ "${NCU:-1}" = "1" ]; then
 NVSF_OPT=${NCU_OPT:-density_mode=2} timeout 600 ncu --set full --clock-control none --import-source on \
-  -k regex:"k_flow_stage|k_dyn_stage|k_encode_stage|k_sigma_stage" -s 12 -c 4 -f -o gpurun_out/stages \
+  -k regex:"k_flow_tc|k_dyn_stage|k_encode_sigma_tc|k_render_composite" -s 9 -c 4 -f -o gpurun_out/stages \
   python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-train --no-march > gpurun_out/ncu.log 2>&1
 tail -3 gpurun_out/ncu.log
 fi
