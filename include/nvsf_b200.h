@@ -308,7 +308,8 @@ typedef struct {
 
 /* Bytes of the per-call buffer in which the training forward keeps, per sample: sigma f32,
  * sigma-net output f16[16], flow f32[8], the 120 sigma-net inputs f16[128], the flow-MLP inputs
- * f16[32] and the head colours f32[4]  (444 B per sample). */
+ * f16[32] and the head colours f32[4]  (444 B per sample), plus the density_mode-2 intermediates of
+ * one chunk (84 B per sample). */
 size_t nvsf_render_uniform_saved_bytes(uint32_t N, uint32_t S);
 /* Bytes of backward scratch (bf16 weight images, time-collapsed gradient tables, per-chunk
  * activation gradients; rays are processed in chunks of ~6 M samples). */

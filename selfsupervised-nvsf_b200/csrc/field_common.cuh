@@ -142,6 +142,7 @@ int nvsf_launch_density(const nvsf_field_config_t* cfg, const void* workspace, c
                         cudaStream_t stream);
 constexpr size_t kSplitChunk = (size_t)4 << 20;  // samples per chunk of the staged variant
 size_t nvsf_density_split_scratch_bytes(size_t n);
+size_t nvsf_density_keep_scratch_bytes(size_t n);  // mode-2 intermediates of the training forward
 // Intermediates of the staged evaluation that the training forward keeps for the backward pass.
 struct DensityKeep {
     float* flow;        // [n,8]   flow MLP output (6 used)
@@ -163,7 +164,7 @@ int nvsf_launch_sigma_tc(const void* wimg, const __half* feat, size_t count, flo
 int nvsf_launch_flow_tc(const nvsf_field_config_t* cfg, const FieldPtrs& P, const float* x,
                         const float* rays_o, const float* rays_d, const float* nears, const float* fars,
                         const float* noise, uint32_t S, size_t begin, size_t count, float* flow_out,
-                        float* qpos, size_t stride, int sms, cudaStream_t stream);
+                        float* qpos, size_t stride, __half* flowfeat, int sms, cudaStream_t stream);
 // gather stage fused with the sigma MLP (mode 2 intermediates: query positions + dyn rows)
 int nvsf_launch_encode_sigma_tc(const nvsf_field_config_t* cfg, const FieldPtrs& P, const float* qpos,
                                 const void* dyn_in, size_t stride, size_t count, float* sigma,

@@ -658,12 +658,13 @@ void launch_encode(bool dyn_pre, bool pair, unsigned tiles, cudaStream_t stream,
 struct SplitScratch {
     size_t flow, feat, dyn, qpos, counters, total;
 };
-SplitScratch split_layout(size_t n) {
+SplitScratch split_layout(size_t n, bool keep = false) {
     const size_t chunk = std::min<size_t>(n, kSplitChunk);   // sized for the largest chunk option
     SplitScratch L;
     size_t off = 0;
-    L.flow = off; off += ws_align(chunk * 8 * sizeof(float));
-    L.feat = off; off += ws_align(chunk * kFeat * sizeof(__half));
+    // the training forward keeps flow / feats of every sample itself: only the mode-2 intermediates
+    L.flow = off; off += keep ? 0 : ws_align(chunk * 8 * sizeof(float));
+    L.feat = off; off += keep ? 0 : ws_align(chunk * kFeat * sizeof(__half));
     L.dyn = off; off += ws_align(chunk * 3 * kHdLevels * sizeof(__half));
     L.qpos = off; off += ws_align(chunk * 9 * sizeof(float));
     L.counters = off; off += ws_align(kDynMaxTypes * sizeof(uint32_t));
@@ -673,6 +674,7 @@ SplitScratch split_layout(size_t n) {
 
 }  // namespace
 
+size_t nvsf_density_keep_scratch_bytes(size_t n) { return split_layout(n, true).total; }
 size_t nvsf_density_split_scratch_bytes(size_t n) { return split_layout(n).total; }
 
 int nvsf_launch_density_split(const nvsf_field_config_t* cfg, const void* workspace,
@@ -687,7 +689,7 @@ int nvsf_launch_density_split(const nvsf_field_config_t* cfg, const void* worksp
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const SplitScratch SL = split_layout(n);
+    const SplitScratch SL = split_layout(n, keep != nullptr);
     const size_t chunk = std::min<size_t>(n, std::min<size_t>(g_split_chunk, kSplitChunk));
     unsigned char* sc = reinterpret_cast<unsigned char*>(split_scratch);
     float* flow_buf = reinterpret_cast<float*>(sc + SL.flow);
@@ -695,8 +697,8 @@ int nvsf_launch_density_split(const nvsf_field_config_t* cfg, const void* worksp
     __half* dyn_buf = reinterpret_cast<__half*>(sc + SL.dyn);
     float* qpos_buf = reinterpret_cast<float*>(sc + SL.qpos);
     uint32_t* counters = reinterpret_cast<uint32_t*>(sc + SL.counters);
-    // mode 2: dynamic hashes from shared-memory-staged tables (needs the scratch buffer; the
-    // training forward passes none and keeps the plain gather stage)
+    // mode 2: fp16 table mirrors, dynamic hashes from shared-memory-staged tables (needs the scratch
+    // buffer for the dyn rows and query positions; the training forward passes the lean layout)
     const bool want_dyn = split_scratch != nullptr && nvsf_density_mode() == 2;
     for (size_t begin = 0; begin < n; begin += chunk) {
         const size_t count = std::min(chunk, n - begin);
@@ -714,12 +716,12 @@ int nvsf_launch_density_split(const nvsf_field_config_t* cfg, const void* worksp
         if (dyn_pre) cudaMemsetAsync(counters, 0, kDynMaxTypes * sizeof(uint32_t), stream);
         const unsigned short* dyn_in = reinterpret_cast<const unsigned short*>(dyn_buf);
         const bool fused = dyn_pre && !keep && !features && g_fuse_sigma != 0;
-        const bool flow_tc = dyn_pre && !keep && g_flow_tc != 0;
+        const bool flow_tc = dyn_pre && g_flow_tc != 0;
         if (g_prof.on) g_prof.next(stream);
         if (x) {
             if (flow_tc) {
                 st = nvsf_launch_flow_tc(cfg, P, x, nullptr, nullptr, nullptr, nullptr, nullptr, 1, begin,
-                                         count, flow_buf, qpos_buf, count, sms, stream);
+                                         count, flow_buf, qpos_buf, count, ff, sms, stream);
                 if (st != NVSF_OK) return st;
             } else if (dyn_pre)
                 k_flow_stage<false, true><<<grid_p, kSTile, kFlowStageSmem, stream>>>(
@@ -743,7 +745,7 @@ int nvsf_launch_density_split(const nvsf_field_config_t* cfg, const void* worksp
         } else {
             if (flow_tc) {
                 st = nvsf_launch_flow_tc(cfg, P, nullptr, rays_o, rays_d, nears, fars, noise, S, begin,
-                                         count, flow_buf, qpos_buf, count, sms, stream);
+                                         count, flow_buf, qpos_buf, count, ff, sms, stream);
                 if (st != NVSF_OK) return st;
             } else if (dyn_pre)
                 k_flow_stage<true, true><<<grid_p, kSTile, kFlowStageSmem, stream>>>(

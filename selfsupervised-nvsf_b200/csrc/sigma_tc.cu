@@ -406,7 +406,8 @@ k_flow_tc(const __grid_constant__ nvsf_field_config_t cfg, const __grid_constant
           const float* __restrict__ xin, const float* __restrict__ rays_o,
           const float* __restrict__ rays_d, const float* __restrict__ nears,
           const float* __restrict__ fars, const float* __restrict__ noise, uint32_t S, size_t begin,
-          size_t count, float* __restrict__ flow_out, float* __restrict__ qpos, size_t stride) {
+          size_t count, float* __restrict__ flow_out, float* __restrict__ qpos, size_t stride,
+          __half* __restrict__ flowfeat_out /* [n,32] kept for the backward pass, or NULL */) {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -460,6 +461,9 @@ k_flow_tc(const __grid_constant__ nvsf_field_config_t cfg, const __grid_constant
                 v[2 * j + 1] = f.y;
             }
             st_chunk(xg, t, c, v);
+            if (flowfeat_out && live)
+                *reinterpret_cast<uint4*>(flowfeat_out + li * kFlowIn + 8 * c) =
+                    *reinterpret_cast<const uint4*>(xg + swz(t, c));
         }
         fence_async_smem();
         tc_fence_before();
@@ -584,7 +588,7 @@ int nvsf_launch_encode_sigma_tc(const nvsf_field_config_t* cfg, const FieldPtrs&
 int nvsf_launch_flow_tc(const nvsf_field_config_t* cfg, const FieldPtrs& P, const float* x,
                         const float* rays_o, const float* rays_d, const float* nears, const float* fars,
                         const float* noise, uint32_t S, size_t begin, size_t count, float* flow_out,
-                        float* qpos, size_t stride, int sms, cudaStream_t stream) {
+                        float* qpos, size_t stride, __half* flowfeat, int sms, cudaStream_t stream) {
     if (!g_flow_attr) {
         cudaError_t e = cudaFuncSetAttribute(k_flow_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)kFusedSmem);
@@ -598,9 +602,11 @@ int nvsf_launch_flow_tc(const nvsf_field_config_t* cfg, const FieldPtrs& P, cons
     const int grid = (int)std::min<size_t>((tiles + kFusedWG - 1) / kFusedWG, (size_t)sms);
     if (x)
         k_flow_tc<false><<<grid, kFusedThreads, kFusedSmem, stream>>>(
-            *cfg, P, x, nullptr, nullptr, nullptr, nullptr, nullptr, 1, begin, count, flow_out, qpos, stride);
+            *cfg, P, x, nullptr, nullptr, nullptr, nullptr, nullptr, 1, begin, count, flow_out, qpos, stride,
+            flowfeat);
     else
         k_flow_tc<true><<<grid, kFusedThreads, kFusedSmem, stream>>>(
-            *cfg, P, nullptr, rays_o, rays_d, nears, fars, noise, S, begin, count, flow_out, qpos, stride);
+            *cfg, P, nullptr, rays_o, rays_d, nears, fars, noise, S, begin, count, flow_out, qpos, stride,
+            flowfeat);
     return NVSF_OK;
 }

@@ -994,7 +994,7 @@ PlaneDst make_plane_dst(const nvsf_field_config_t* c) {
 
 // ---- buffers ---------------------------------------------------------------------------------------
 struct SavedLayout {   // per-sample intermediates kept by the training forward
-    size_t sigma, geo, flow, feats, flowfeat, rgbs, total;
+    size_t sigma, geo, flow, feats, flowfeat, rgbs, split, total;
 };
 SavedLayout make_saved(size_t n) {
     SavedLayout L;
@@ -1005,6 +1005,7 @@ SavedLayout make_saved(size_t n) {
     L.feats = off; off = ws_align(off + n * kFeat * sizeof(__half));
     L.flowfeat = off; off = ws_align(off + n * kFlowIn * sizeof(__half));
     L.rgbs = off; off = ws_align(off + n * 4 * sizeof(float));
+    L.split = off; off = ws_align(off + nvsf_density_keep_scratch_bytes(n));  // density_mode 2 intermediates
     L.total = off;
     return L;
 }
@@ -1106,7 +1107,7 @@ int nvsf_render_uniform_train_forward(const nvsf_field_config_t* cfg, const void
     keep.flowfeat = reinterpret_cast<__half*>(sv + L.flowfeat);
     int st = nvsf_launch_density_split(cfg, workspace, nullptr, rays_o, rays_d, nears, fars, noise, S,
                                        n, reinterpret_cast<float*>(sv + L.sigma), sv + L.geo, nullptr,
-                                       nullptr, nullptr, (cudaStream_t)stream, &keep);
+                                       nullptr, sv + L.split, (cudaStream_t)stream, &keep);
     if (st != NVSF_OK) return st;
     return nvsf_render_composite_launch(cfg, workspace, lidar, rays_d, nears, fars, noise, N, S,
                                         bg_color, sv, L.flow, depth, image, weights_sum, weights,

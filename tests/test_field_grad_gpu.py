@@ -142,24 +142,25 @@ def test_fused_grad_accumulation_and_repeat(pkg, gold):
 
 
 def test_train_forward_equals_inference_forward(pkg, gold):
-    """The training forward runs the staged evaluation on the fp32 collapsed tables (what the
-    backward re-gathers from): bit-identical to the inference forward in density_mode 1, and
-    within the fp16 resolution of the table mirrors in the default mode 2."""
+    """The training forward runs the same staged pipeline as inference but keeps its intermediates
+    (un-fused gather stage writing the feature rows): bit-identical in density_mode 1; in the default
+    mode 2 inference accumulates the sigma net inside the fused tcgen05 kernel, so the two agree to
+    fp32 accumulation-order rounding."""
     L = pkg._lib.lib()
     case = FC.grad_case(gold, "l_mid")
-    m = make_model(pkg, case["ds"])
-    _, out = run_case(m, case)
     prev = L.nvsf_density_mode_get()
     try:
         for mode in (1, 2):
             assert L.nvsf_set_option(b"density_mode", mode) == 0
+            m = make_model(pkg, case["ds"])
+            _, out = run_case(m, case)
             with torch.no_grad():
                 _, ref = run_case(m, case)
             for k in ("depth", "image", "weights", "weights_sum"):
                 if mode == 1:
                     assert torch.equal(out[k].detach(), ref[k]), k
                 else:
-                    torch.testing.assert_close(out[k].detach(), ref[k], rtol=2e-3, atol=2e-5, msg=k)
+                    torch.testing.assert_close(out[k].detach(), ref[k], rtol=1e-3, atol=1e-5, msg=k)
+            assert out["depth"].requires_grad and not ref["depth"].requires_grad
     finally:
         L.nvsf_set_option(b"density_mode", prev)
-    assert out["depth"].requires_grad and not ref["depth"].requires_grad
