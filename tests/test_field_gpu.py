@@ -294,3 +294,23 @@ def test_flow_stage_tcgen05_matches_mma_sync(pkg, model, t):
     close(out[1][0], out[0][0], 2e-3, 2e-3 * np.abs(out[0][0]).max(), "flow tcgen05 vs mma.sync")
     close(out[1][1], out[0][1], 2e-3, 0, "sigma")
     close(out[1][2], out[0][2], 2e-3, 2e-3 * np.abs(out[0][2]).max(), "geo")
+
+
+@pytest.mark.parametrize("n", [1, 7, 127, 129, 1025])
+def test_tiny_and_ragged_point_counts(pkg, model, orc, n):
+    """Counts below and just above one 128-sample UMMA tile / one 1024-thread CTA through the
+    default tcgen05 pipeline: every sample equals the same sample evaluated inside a large batch,
+    and the oracle within the field tolerance."""
+    x = pts(2048, 31)
+    big = model.density(torch.from_numpy(x).cuda(), 0.37, True)
+    small = model.density(torch.from_numpy(x[:n]).cuda(), 0.37, True)
+    assert small["sigma"].shape == (n,) and small["geo_feat"].shape == (n, 15)
+    assert torch.equal(small["sigma"], big["sigma"][:n]) and torch.equal(small["geo_feat"], big["geo_feat"][:n])
+    with torch.no_grad():
+        o = orc.density(torch.from_numpy(x[:n]), 0.37, True)
+    close(host(small["sigma"]), o["sigma"].numpy(), 1e-2, 0, "sigma vs oracle")
+
+
+def test_empty_point_set(model):
+    r = model.density(torch.empty(0, 3, device="cuda"), 0.5, True)
+    assert r["sigma"].shape == (0,) and r["geo_feat"].shape == (0, 15)
