@@ -198,17 +198,6 @@ constexpr uint32_t kFOffBar = kFOffX + kFusedWG * kFTile;
 constexpr size_t kFusedSmem = kFOffBar + 8 * kFusedWG + 16 + 1024;
 static_assert(kFOffX % 1024 == 0, "swizzled tiles start on 1024-byte boundaries");
 
-__device__ __forceinline__ void wg_barrier(uint32_t wg) {
-    asm volatile("bar.sync %0, 128;\n" ::"r"(wg + 1u) : "memory");
-}
-__device__ __forceinline__ void st_chunk(unsigned char* tile, uint32_t row, uint32_t chunk,
-                                         const float (&v)[8]) {
-    uint4 o;
-    o.x = pack_half2(v[0], v[1]); o.y = pack_half2(v[2], v[3]);
-    o.z = pack_half2(v[4], v[5]); o.w = pack_half2(v[6], v[7]);
-    *reinterpret_cast<uint4*>(tile + swz(row, chunk)) = o;
-}
-
 __global__ void __launch_bounds__(kFusedThreads, 1)
 k_encode_sigma_tc(const __grid_constant__ nvsf_field_config_t cfg,
                   const __grid_constant__ FieldPtrs P, const float* __restrict__ qpos,

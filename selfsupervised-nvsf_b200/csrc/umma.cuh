@@ -100,4 +100,31 @@ __device__ __forceinline__ void tmem_ld_wait() {
     asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 }
 
+// named barrier of one 128-thread warpgroup (barrier 0 is __syncthreads)
+__device__ __forceinline__ void wg_barrier(uint32_t wg) {
+    asm volatile("bar.sync %0, 128;\n" ::"r"(wg + 1u) : "memory");
+}
+__device__ __forceinline__ void st_chunk(unsigned char* tile, uint32_t row, uint32_t chunk,
+                                         const float (&v)[8]) {
+    uint4 o;
+    o.x = pack_half2(v[0], v[1]); o.y = pack_half2(v[2], v[3]);
+    o.z = pack_half2(v[4], v[5]); o.w = pack_half2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(tile + swz(row, chunk)) = o;
+}
+
+// warpgroup-wide OR of a per-thread flag (named barrier with reduction)
+__device__ __forceinline__ bool wg_any(uint32_t wg, bool flag) {
+    uint32_t r;
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q;\n"
+        "setp.ne.u32 q, %1, 0;\n"
+        "bar.red.or.pred p, %2, 128, q;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(r)
+        : "r"((uint32_t)flag), "r"(wg + 1u)
+        : "memory");
+    return r != 0;
+}
 }  // namespace umma
