@@ -172,6 +172,8 @@ int nvsf_launch_encode_sigma_tc(const nvsf_field_config_t* cfg, const FieldPtrs&
 void nvsf_stage_timing_enable(int on);
 int nvsf_split_set_option(const char* name, int value);
 int nvsf_split_get_option(const char* name);
+int nvsf_train_set_option(const char* name, int value);  // train.cu
+int nvsf_train_get_option(const char* name);
 // Compositing + heads launcher (render.cu); scratch = sigma f32 [N*S] then geo f16 [N*S,16];
 // rgbs (f32 [N*S,4], may be NULL) receives the per-sample colours for the backward pass.
 int nvsf_render_composite_launch(const nvsf_field_config_t* cfg, const void* workspace,

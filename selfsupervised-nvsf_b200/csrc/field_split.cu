@@ -834,7 +834,7 @@ int nvsf_split_set_option(const char* name, int value) {
         g_split_chunk = (size_t)value * 65536;
         return NVSF_OK;
     }
-    return NVSF_E_INVALID;
+    return nvsf_train_set_option(name, value);
 }
 
 int nvsf_split_get_option(const char* name) {
@@ -846,7 +846,7 @@ int nvsf_split_get_option(const char* name) {
     if (k == "sigma_tc") return g_sigma_tc;
     if (k == "fuse_sigma") return g_fuse_sigma;
     if (k == "flow_tc") return g_flow_tc;
-    return NVSF_E_INVALID;
+    return nvsf_train_get_option(name);
 }
 
 // ---- stage timing (see StageProf) -------------------------------------------------------------------

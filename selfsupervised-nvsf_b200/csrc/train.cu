@@ -28,6 +28,7 @@
 //   k_expand_*        collapsed gradient tables -> the reference parameter layouts (the transpose
 //                     of the time collapse of field.cu; linear, so exact)
 #include <algorithm>
+#include <string>
 
 #include "mlp_bwd.cuh"
 
@@ -316,6 +317,24 @@ struct HeadT {
         const int r = tid >> 1, half = tid & 1;
         const size_t g = row0 + r;
         bf16* xr = Xs + r * LDX;
+        if (LIDAR) {
+            // tcnn Frequency (12 octaves) of (d+1)/2 is constant along a ray: evaluate the 72 columns
+            // once per ray of the tile (36 threads x one sin/cos pair) into the tile row of the ray's
+            // first sample; the other rows copy it below.  (Per-row evaluation was 60 % of this
+            // kernel's instructions, profiles/r01_train_bwd_v2_ncu_full.txt.)
+            const size_t last = (row0 + kBwdRows < n ? row0 + kBwdRows : n) - 1;
+            const size_t ray_a = row0 / A.S;
+            const int nr = (int)(last / A.S - ray_a) + 1;
+            for (int t = tid; t < nr * 36; t += kBwdWarps * 32) {
+                const int rl = t / 36, j = 2 * (t - rl * 36);
+                const size_t ry = ray_a + rl;
+                const size_t first = ry * A.S > row0 ? ry * A.S : row0;
+                const int dim = j / 24, oct = (j >> 1) % 12;
+                const float v = (__ldg(A.rays_d + ry * 3 + dim) + 1.0f) * 0.5f;
+                const float a = scalbnf(v, oct);
+                *reinterpret_cast<uint32_t*>(Xs + (first - row0) * LDX + j) = pack_bf2(sinpif(a), sinpif(a + 0.5f));
+            }
+        }
         if (g >= n) {
             for (int c = half * (KIN / 2); c < (half + 1) * (KIN / 2); c += 8)
                 *reinterpret_cast<uint4*>(xr + c) = make_uint4(0, 0, 0, 0);
@@ -323,6 +342,7 @@ struct HeadT {
                 *reinterpret_cast<uint4*>(Ds + r * kLdD) = make_uint4(0, 0, 0, 0);
                 *reinterpret_cast<uint4*>(Ds + r * kLdD + 8) = make_uint4(0, 0, 0, 0);
             }
+            if (LIDAR) __syncthreads();
             return;
         }
         const size_t ray = g / A.S;
@@ -333,15 +353,7 @@ struct HeadT {
         const uint4 g1 = __ldg(reinterpret_cast<const uint4*>(A.geo + g * 16) + 1);
         const __half* gh0 = reinterpret_cast<const __half*>(&g0);
         const __half* gh1 = reinterpret_cast<const __half*>(&g1);
-        if (LIDAR) {
-            // tcnn Frequency (12 octaves) of (d+1)/2: this thread fills 36 of the 72 columns
-            for (int j = half * 36; j < half * 36 + 36; j += 2) {
-                const int dim = j / 24, oct = (j >> 1) % 12;
-                const float v = ((dim == 0 ? dx : (dim == 1 ? dy : dz)) + 1.0f) * 0.5f;
-                const float a = scalbnf(v, oct);
-                *reinterpret_cast<uint32_t*>(xr + j) = pack_bf2(sinpif(a), sinpif(a + 0.5f));
-            }
-        } else {
+        if (!LIDAR) {
             float sh[16];
             sh4_eval(dx, dy, dz, sh);
 #pragma unroll
@@ -384,6 +396,16 @@ struct HeadT {
                 *reinterpret_cast<uint32_t*>(xr + NDIR + j) = pack_bf2(a, b);
             }
             if (LIDAR) *reinterpret_cast<uint4*>(xr + 88) = make_uint4(0, 0, 0, 0);
+        }
+        if (LIDAR) {
+            __syncthreads();
+            const size_t first = ray * A.S > row0 ? ray * A.S : row0;
+            if (first != g) {   // 36 halves = 9 x 8 bytes of the ray's encoding
+                const uint2* src = reinterpret_cast<const uint2*>(Xs + (first - row0) * LDX + half * 36);
+                uint2* dst = reinterpret_cast<uint2*>(xr + half * 36);
+#pragma unroll
+                for (int i = 0; i < 9; ++i) dst[i] = src[i];
+            }
         }
     }
     static __device__ __forceinline__ void sink(const Args& A, size_t row, size_t n, int col, float a,
@@ -544,6 +566,8 @@ k_composite_bwd(const __grid_constant__ nvsf_field_config_t cfg, const float* __
 // ------------------------------------------------------------------------------------------------
 // encoder backward
 // ------------------------------------------------------------------------------------------------
+int g_enc_bwd_ctas = 2;  // nvsf_set_option("enc_bwd_ctas", 2 | 3)
+
 struct GradTables {      // time-collapsed / channel-last gradient tables (scratch, zeroed per call)
     float* pls;          // layout of WsLayout::pls
     float* pld;          // [3 queries][pld_per_q]
@@ -563,44 +587,62 @@ __device__ __forceinline__ void red1(float* p, float a) {
 }
 
 // Runs of equal keys over consecutive lanes (consecutive samples of a ray fall into the same
-// texel): `heads` has a bit for every lane that starts a run; seg_sum leaves in each head lane the
-// sum over its run.
+// cell): `heads` has a bit for every lane that starts a run; seg_sum leaves in each head lane the
+// sum over its run.  `nsteps` (warp-uniform) is the number of doubling steps the longest run needs.
 struct Runs {
     unsigned heads;
     bool head;
+    int nsteps;
     bool take[5];  // lane adds the value of lane + (1 << k): no run starts in (lane, lane + (1 << k)]
 };
-__device__ __forceinline__ Runs make_runs(uint32_t key, int lane) {
+__device__ __forceinline__ Runs runs_from_heads(bool head, int lane) {
     Runs r;
-    const uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
-    r.head = lane == 0 || prev != key;
-    r.heads = __ballot_sync(0xffffffffu, r.head);
+    r.head = head;
+    r.heads = __ballot_sync(0xffffffffu, head);
     const unsigned above = (r.heads >> lane) >> 1;
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
         const int d = 1 << k;
         r.take[k] = (lane + d < 32) && ((above & ((1u << d) - 1u)) == 0u);
     }
+    // step k is needed iff some run is longer than 2^k lanes, i.e. 2^k consecutive non-head lanes
+    const unsigned z1 = ~r.heads, z2 = z1 & (z1 >> 1), z4 = z2 & (z2 >> 2), z8 = z4 & (z4 >> 4),
+                   z16 = z8 & (z8 >> 8);
+    r.nsteps = (z1 != 0u) + (z2 != 0u) + (z4 != 0u) + (z8 != 0u) + (z16 != 0u);
     return r;
 }
 __device__ __forceinline__ float seg_sum(float v, const Runs& r) {
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
-        const float o = __shfl_down_sync(0xffffffffu, v, 1 << k);
-        if (r.take[k]) v += o;
+        if (k < r.nsteps) {
+            const float o = __shfl_down_sync(0xffffffffu, v, 1 << k);
+            if (r.take[k]) v += o;
+        }
     }
     return v;
 }
 
-// add w * g[0..7] for a run of lanes to an 8-float texel
-__device__ __forceinline__ void scatter8(float* texel, float w, const float (&g)[8], const Runs& r) {
-    float s[8];
-#pragma unroll
-    for (int f = 0; f < 8; ++f) s[f] = seg_sum(w * g[f], r);
-    if (r.head) {
-        red4(texel, s[0], s[1], s[2], s[3]);
-        red4(texel + 4, s[4], s[5], s[6], s[7]);
-    }
+// Transposed run reduction of the plane scatters.  The lane that owns a sample stages its eight
+// channel gradients and the texel (index, weights, "last sample of its run inside this group of 8")
+// in shared memory; then lane (q, f) walks the 8 consecutive samples of group q for channel f,
+// accumulates the corner sums in registers while the texel stays the same and issues one red per
+// corner when it changes: the 8 lanes of a group add 32 contiguous bytes.  Replaces a segmented
+// shuffle reduction of 32 (2-D) / 16 (1-D) values per lane, which was 2/3 of k_encode_bwd's
+// instructions (profiles/r01_train_bwd_v2_ncu_full.txt: SHFL 23 %, predicated FADD 27 %).
+struct __align__(16) WarpStage {
+    float d[36 * 8];  // row(s) = s + (s >> 3): the four groups read different banks
+    uint4 info[32];
+};
+__device__ __forceinline__ void stage_rows(WarpStage& st, int lane, const float (&g)[8], uint32_t idx0,
+                                           float wx, float wy, uint32_t flags) {
+    const uint32_t nxt = __shfl_down_sync(0xffffffffu, idx0, 1);
+    if ((lane & 7) == 7 || nxt != idx0) flags |= 4u;
+    __syncwarp();  // the previous scatter's readers are done
+    float4* row = reinterpret_cast<float4*>(st.d + (lane + (lane >> 3)) * 8);
+    row[0] = make_float4(g[0], g[1], g[2], g[3]);
+    row[1] = make_float4(g[4], g[5], g[6], g[7]);
+    st.info[lane] = make_uint4(idx0, __float_as_uint(wx), __float_as_uint(wy), flags);
+    __syncwarp();
 }
 
 struct Bilin {
@@ -622,12 +664,31 @@ __device__ __forceinline__ void sample2d(const float* __restrict__ base, uint32_
     for (int f = 0; f < 8; ++f) out[f] = w00 * a[f] + w01 * bb[f] + w10 * c[f] + w11 * d[f];
 }
 __device__ __forceinline__ void scatter2d(float* __restrict__ base, uint32_t R, const Bilin& b,
-                                          const float (&g)[8], bool live) {
-    const Runs r = make_runs(live ? b.y0 * R + b.x0 : 0xffffffffu, threadIdx.x & 31);
-    scatter8(base + ((size_t)b.y0 * R + b.x0) * 8, (1.f - b.wx) * (1.f - b.wy), g, r);
-    scatter8(base + ((size_t)b.y0 * R + b.x1) * 8, b.wx * (1.f - b.wy), g, r);
-    scatter8(base + ((size_t)b.y1 * R + b.x0) * 8, (1.f - b.wx) * b.wy, g, r);
-    scatter8(base + ((size_t)b.y1 * R + b.x1) * 8, b.wx * b.wy, g, r);
+                                          const float (&g)[8], WarpStage& st, int lane) {
+    stage_rows(st, lane, g, b.y0 * R + b.x0, b.wx, b.wy,
+               (b.x1 != b.x0 ? 1u : 0u) | (b.y1 != b.y0 ? 2u : 0u));
+    const int q = lane >> 3, f = lane & 7;
+    float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint4 in = st.info[8 * q + i];
+        const float v = st.d[(9 * q + i) * 8 + f];
+        const float wx = __uint_as_float(in.y), wy = __uint_as_float(in.z);
+        const float v0 = v * (1.f - wx), v1 = v * wx;
+        a00 = fmaf(v0, 1.f - wy, a00);
+        a01 = fmaf(v1, 1.f - wy, a01);
+        a10 = fmaf(v0, wy, a10);
+        a11 = fmaf(v1, wy, a11);
+        if (in.w & 4u) {
+            float* t = base + (size_t)in.x * 8 + f;
+            const uint32_t ox = (in.w & 1u) ? 8u : 0u, oy = (in.w & 2u) ? R * 8u : 0u;
+            red1(t, a00);
+            red1(t + ox, a01);
+            red1(t + oy, a10);
+            red1(t + ox + oy, a11);
+            a00 = a01 = a10 = a11 = 0.f;
+        }
+    }
 }
 
 struct Lin {
@@ -650,14 +711,29 @@ __device__ __forceinline__ void sample1d(const float* __restrict__ base, uint32_
     }
 }
 __device__ __forceinline__ void scatter1d(float* __restrict__ base, const Lin& l, const float (&g)[8],
-                                          bool live) {
-    const Runs r = make_runs(live ? l.x0 : 0xffffffffu, threadIdx.x & 31);
-    scatter8(base + (size_t)l.x0 * 8, 1.f - l.wx, g, r);
-    scatter8(base + (size_t)l.x1 * 8, l.wx, g, r);
+                                          WarpStage& st, int lane) {
+    stage_rows(st, lane, g, l.x0, l.wx, 0.f, l.x1 != l.x0 ? 1u : 0u);
+    const int q = lane >> 3, f = lane & 7;
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint4 in = st.info[8 * q + i];
+        const float v = st.d[(9 * q + i) * 8 + f];
+        const float wx = __uint_as_float(in.y);
+        a0 = fmaf(v, 1.f - wx, a0);
+        a1 = fmaf(v, wx, a1);
+        if (in.w & 4u) {
+            float* t = base + (size_t)in.x * 8 + f;
+            red1(t, a0);
+            red1(t + ((in.w & 1u) ? 8u : 0u), a1);
+            a0 = a1 = 0.f;
+        }
+    }
 }
 
-template <bool FROM_RAYS>
-__global__ void __launch_bounds__(256)
+// MIN_CTAS 2 = 128 registers / 16 warps per SM; 3 = 80 registers (80 bytes of spills) / 24 warps
+template <bool FROM_RAYS, int MIN_CTAS>
+__global__ void __launch_bounds__(256, MIN_CTAS)
 k_encode_bwd(const __grid_constant__ nvsf_field_config_t cfg, const __grid_constant__ FieldPtrs P,
              const GradTables G, const float* __restrict__ xin, const float* __restrict__ rays_o,
              const float* __restrict__ rays_d, const float* __restrict__ nears,
@@ -685,6 +761,9 @@ k_encode_bwd(const __grid_constant__ nvsf_field_config_t cfg, const __grid_const
         o[1] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     if (__ballot_sync(0xffffffffu, live) == 0) return;
+    __shared__ WarpStage stage[8];
+    const int lane = threadIdx.x & 31;
+    WarpStage& st = stage[threadIdx.x >> 5];
 
     float x = 0.5f, y = 0.5f, z = 0.5f;
     float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f), f1 = f0;
@@ -740,13 +819,13 @@ k_encode_bwd(const __grid_constant__ nvsf_field_config_t cfg, const __grid_const
         float d8[8];
 #pragma unroll
         for (int f = 0; f < 8; ++f) d8[f] = g8[f] * B[f] * C[f];
-        scatter2d(gbase, R, ba, d8, live);
+        scatter2d(gbase, R, ba, d8, st, lane);
 #pragma unroll
         for (int f = 0; f < 8; ++f) d8[f] = g8[f] * A[f] * C[f];
-        scatter2d(gbase + (size_t)R * R * 8, R, bb, d8, live);
+        scatter2d(gbase + (size_t)R * R * 8, R, bb, d8, st, lane);
 #pragma unroll
         for (int f = 0; f < 8; ++f) d8[f] = g8[f] * A[f] * B[f];
-        scatter2d(gbase + (size_t)2 * R * R * 8, R, bc, d8, live);
+        scatter2d(gbase + (size_t)2 * R * R * 8, R, bc, d8, st, lane);
     }
 
     // (b) time planes (collapsed rows): sum_q wq * A_q(x_q) * B_q(y_q) * C_q(z_q); the warped
@@ -781,13 +860,13 @@ k_encode_bwd(const __grid_constant__ nvsf_field_config_t cfg, const __grid_const
                 gy = fmaf(gw * A[f] * C[f], sb[f], gy);
                 gz = fmaf(gw * A[f] * B[f], sc[f], gz);
             }
-            scatter1d(gbase, la, d8, live);
+            scatter1d(gbase, la, d8, st, lane);
 #pragma unroll
             for (int f = 0; f < 8; ++f) d8[f] = wq * g8[f] * A[f] * C[f];
-            scatter1d(gbase + (size_t)R * 8, lb, d8, live);
+            scatter1d(gbase + (size_t)R * 8, lb, d8, st, lane);
 #pragma unroll
             for (int f = 0; f < 8; ++f) d8[f] = wq * g8[f] * A[f] * B[f];
-            scatter1d(gbase + (size_t)2 * R * 8, lc, d8, live);
+            scatter1d(gbase + (size_t)2 * R * 8, lc, d8, st, lane);
             if (q > 0 && qi[q] != 0) {
                 dfl[3 * (q - 1) + 0] += gx * la.dcoord;
                 dfl[3 * (q - 1) + 1] += gy * lb.dcoord;
@@ -800,24 +879,47 @@ k_encode_bwd(const __grid_constant__ nvsf_field_config_t cfg, const __grid_const
         o[0] = make_float4(dfl[0], dfl[1], dfl[2], dfl[3]);
         o[1] = make_float4(dfl[4], dfl[5], 0.f, 0.f);
     }
-    if (!live) return;  // no warp-collective operations below
-
-    // (c) static 3-D hash: tcnn grid backward, fp32 vector reds into the caller's gradient
+    // (c) static 3-D hash: tcnn grid backward, fp32 vector reds into the caller's gradient.
+    // The hash scatters are bound by atomic throughput (about one red lane-operation per two
+    // clocks per SM, whatever its width): on the coarse levels, where consecutive samples of a
+    // ray share a cell (a warp holds at most 16 runs), the corner products are summed over each
+    // run with shuffles first and only the head lane of a run issues the reds.
+    const bool plive = __shfl_up_sync(0xffffffffu, (int)live, 1) != 0;
+    const bool edge = lane == 0 || !live || !plive;
 #pragma unroll 1
     for (int l = 0; l < kHsLevels; ++l) {
         const LevelArgs L = lv(cfg.hs[l]);
-        const float4 g4 = __ldg(reinterpret_cast<const float4*>(df + 64 + 4 * l));
+        float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (live) g4 = __ldg(reinterpret_cast<const float4*>(df + 64 + 4 * l));
         uint32_t cx, cy, cz;
         float wx, wy, wz;
         grid_pos(L.scale, x, cx, wx);
         grid_pos(L.scale, y, cy, wy);
         grid_pos(L.scale, z, cz, wz);
+        const bool head = edge | (__shfl_up_sync(0xffffffffu, cx, 1) != cx) |
+                          (__shfl_up_sync(0xffffffffu, cy, 1) != cy) |
+                          (__shfl_up_sync(0xffffffffu, cz, 1) != cz);
+        const Runs r = runs_from_heads(head, lane);
+        if (__popc(r.heads) <= 16) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const float w = ((c & 1) ? wx : 1.f - wx) * ((c & 2) ? wy : 1.f - wy) *
-                            ((c & 4) ? wz : 1.f - wz);
-            const uint32_t idx = L.offset + idx3(L, cx + (c & 1), cy + ((c >> 1) & 1), cz + (c >> 2));
-            red4(G.hs + (size_t)idx * 4, w * g4.x, w * g4.y, w * g4.z, w * g4.w);
+            for (int c = 0; c < 8; ++c) {
+                const float w = ((c & 1) ? wx : 1.f - wx) * ((c & 2) ? wy : 1.f - wy) *
+                                ((c & 4) ? wz : 1.f - wz);
+                const float s0 = seg_sum(w * g4.x, r), s1 = seg_sum(w * g4.y, r),
+                            s2 = seg_sum(w * g4.z, r), s3 = seg_sum(w * g4.w, r);
+                if (head && live) {
+                    const uint32_t idx = L.offset + idx3(L, cx + (c & 1), cy + ((c >> 1) & 1), cz + (c >> 2));
+                    red4(G.hs + (size_t)idx * 4, s0, s1, s2, s3);
+                }
+            }
+        } else if (live) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float w = ((c & 1) ? wx : 1.f - wx) * ((c & 2) ? wy : 1.f - wy) *
+                                ((c & 4) ? wz : 1.f - wz);
+                const uint32_t idx = L.offset + idx3(L, cx + (c & 1), cy + ((c >> 1) & 1), cz + (c >> 2));
+                red4(G.hs + (size_t)idx * 4, w * g4.x, w * g4.y, w * g4.z, w * g4.w);
+            }
         }
     }
     // (d) dynamic 2-D hashes: gradient through the un-warped query only; a missing neighbour
@@ -830,15 +932,28 @@ k_encode_bwd(const __grid_constant__ nvsf_field_config_t cfg, const __grid_const
 #pragma unroll 1
         for (int l = 0; l < kHdLevels; ++l) {
             const LevelArgs L = lv(cfg.hd[p][l]);
-            const float gs = fac * __ldg(df + 96 + 8 * p + l);
+            const float gs = live ? fac * __ldg(df + 96 + 8 * p + l) : 0.f;
             uint32_t cu, cv;
             float wu, wv;
             grid_pos(L.scale, u, cu, wu);
             grid_pos(L.scale, w2, cv, wv);
-            red1(tab + L.offset + idx2(L, cu, cv), (1.f - wu) * (1.f - wv) * gs);
-            red1(tab + L.offset + idx2(L, cu + 1, cv), wu * (1.f - wv) * gs);
-            red1(tab + L.offset + idx2(L, cu, cv + 1), (1.f - wu) * wv * gs);
-            red1(tab + L.offset + idx2(L, cu + 1, cv + 1), wu * wv * gs);
+            const bool head = edge | (__shfl_up_sync(0xffffffffu, cu, 1) != cu) |
+                              (__shfl_up_sync(0xffffffffu, cv, 1) != cv);
+            const Runs r = runs_from_heads(head, lane);
+            float v00 = (1.f - wu) * (1.f - wv) * gs, v01 = wu * (1.f - wv) * gs,
+                  v10 = (1.f - wu) * wv * gs, v11 = wu * wv * gs;
+            bool emit = live;
+            if (__popc(r.heads) <= 16) {
+                v00 = seg_sum(v00, r); v01 = seg_sum(v01, r);
+                v10 = seg_sum(v10, r); v11 = seg_sum(v11, r);
+                emit = head && live;
+            }
+            if (emit) {
+                red1(tab + L.offset + idx2(L, cu, cv), v00);
+                red1(tab + L.offset + idx2(L, cu + 1, cv), v01);
+                red1(tab + L.offset + idx2(L, cu, cv + 1), v10);
+                red1(tab + L.offset + idx2(L, cu + 1, cv + 1), v11);
+            }
         }
     }
 }
@@ -853,47 +968,75 @@ k_flowgrid_bwd(const __grid_constant__ nvsf_field_config_t cfg, float* __restric
                size_t begin, size_t count, const float* __restrict__ dflow,
                const float* __restrict__ dflowfeat, const float* __restrict__ scale2) {
     const size_t li = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (li >= count) return;
-    {   // same zero test as k_mlp_bwd<FlowT> (scaled fp16): it leaves dflowfeat unwritten for such rows
+    const int lane = threadIdx.x & 31;
+    bool live = li < count;
+    if (live) {   // same zero test as k_mlp_bwd<FlowT> (scaled fp16): it leaves dflowfeat unwritten for such rows
         const float sc = __ldg(scale2);
         const float4 a = __ldg(reinterpret_cast<const float4*>(dflow + li * 8));
         const float4 b = __ldg(reinterpret_cast<const float4*>(dflow + li * 8) + 1);
-        if (((pack_half2(sc * a.x, sc * a.y) | pack_half2(sc * a.z, sc * a.w) | pack_half2(sc * b.x, sc * b.y)) &
-             0x7fff7fffu) == 0)
-            return;
+        live = ((pack_half2(sc * a.x, sc * a.y) | pack_half2(sc * a.z, sc * a.w) | pack_half2(sc * b.x, sc * b.y)) &
+                0x7fff7fffu) != 0;
     }
-    const size_t g = begin + li;
-    float px, py, pz;
-    if (FROM_RAYS) {
-        const size_t r = g / S;
-        const uint32_t k = (uint32_t)(g - r * S);
-        const float zz = uniform_z(__ldg(nears + r), __ldg(fars + r), k, S, noise, g);
-        px = __ldg(rays_o + r * 3 + 0) + __ldg(rays_d + r * 3 + 0) * zz;
-        py = __ldg(rays_o + r * 3 + 1) + __ldg(rays_d + r * 3 + 1) * zz;
-        pz = __ldg(rays_o + r * 3 + 2) + __ldg(rays_d + r * 3 + 2) * zz;
-        px = fminf(fmaxf(px, -cfg.bound), cfg.bound);
-        py = fminf(fmaxf(py, -cfg.bound), cfg.bound);
-        pz = fminf(fmaxf(pz, -cfg.bound), cfg.bound);
-    } else {
-        px = __ldg(xin + g * 3 + 0); py = __ldg(xin + g * 3 + 1); pz = __ldg(xin + g * 3 + 2);
+    if (__ballot_sync(0xffffffffu, live) == 0) return;
+    float x = 0.5f, y = 0.5f, z = 0.5f;
+    if (live) {
+        const size_t g = begin + li;
+        float px, py, pz;
+        if (FROM_RAYS) {
+            const size_t r = g / S;
+            const uint32_t k = (uint32_t)(g - r * S);
+            const float zz = uniform_z(__ldg(nears + r), __ldg(fars + r), k, S, noise, g);
+            px = __ldg(rays_o + r * 3 + 0) + __ldg(rays_d + r * 3 + 0) * zz;
+            py = __ldg(rays_o + r * 3 + 1) + __ldg(rays_d + r * 3 + 1) * zz;
+            pz = __ldg(rays_o + r * 3 + 2) + __ldg(rays_d + r * 3 + 2) * zz;
+            px = fminf(fmaxf(px, -cfg.bound), cfg.bound);
+            py = fminf(fmaxf(py, -cfg.bound), cfg.bound);
+            pz = fminf(fmaxf(pz, -cfg.bound), cfg.bound);
+        } else {
+            px = __ldg(xin + g * 3 + 0); py = __ldg(xin + g * 3 + 1); pz = __ldg(xin + g * 3 + 2);
+        }
+        const float inv2b = 1.0f / (2.0f * cfg.bound);
+        x = (px + cfg.bound) * inv2b; y = (py + cfg.bound) * inv2b; z = (pz + cfg.bound) * inv2b;
     }
-    const float inv2b = 1.0f / (2.0f * cfg.bound);
-    const float x = (px + cfg.bound) * inv2b, y = (py + cfg.bound) * inv2b, z = (pz + cfg.bound) * inv2b;
+    // The kernel is bound by the L2 atomic units (ncu: issue slots 9 % busy, lg_throttle), and on
+    // the coarse levels consecutive samples of a ray sit in the same cell (a LiDAR ray has 110
+    // samples per cell on level 0, 4 on level 9).  Where a warp holds at most 16 runs of equal
+    // cells, the 16 corner x feature products are summed over each run with shuffles and only the
+    // first lane of a run issues the 8 reds.
 #pragma unroll 1
     for (int l = 0; l < kFlLevels; ++l) {
         const LevelArgs L = lv(cfg.fl[l]);
-        const float2 g2 = __ldg(reinterpret_cast<const float2*>(dflowfeat + li * 32 + 2 * l));
+        float2 g2 = make_float2(0.f, 0.f);
+        if (live) g2 = __ldg(reinterpret_cast<const float2*>(dflowfeat + li * 32 + 2 * l));
         uint32_t cx, cy, cz;
         float wx, wy, wz;
         grid_pos(L.scale, x, cx, wx);
         grid_pos(L.scale, y, cy, wy);
         grid_pos(L.scale, z, cz, wz);
+        const uint32_t px_ = __shfl_up_sync(0xffffffffu, cx, 1), py_ = __shfl_up_sync(0xffffffffu, cy, 1),
+                       pz_ = __shfl_up_sync(0xffffffffu, cz, 1);
+        const bool plive = __shfl_up_sync(0xffffffffu, (int)live, 1) != 0;
+        const bool head = lane == 0 || !live || !plive || px_ != cx || py_ != cy || pz_ != cz;
+        const Runs r = runs_from_heads(head, lane);
+        if (__popc(r.heads) <= 16) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const float w = ((c & 1) ? wx : 1.f - wx) * ((c & 2) ? wy : 1.f - wy) *
-                            ((c & 4) ? wz : 1.f - wz);
-            const uint32_t idx = L.offset + idx3(L, cx + (c & 1), cy + ((c >> 1) & 1), cz + (c >> 2));
-            red2(gflow + (size_t)idx * 2, w * g2.x, w * g2.y);
+            for (int c = 0; c < 8; ++c) {
+                const float w = ((c & 1) ? wx : 1.f - wx) * ((c & 2) ? wy : 1.f - wy) *
+                                ((c & 4) ? wz : 1.f - wz);
+                const float sx = seg_sum(w * g2.x, r), sy = seg_sum(w * g2.y, r);
+                if (head && live) {
+                    const uint32_t idx = L.offset + idx3(L, cx + (c & 1), cy + ((c >> 1) & 1), cz + (c >> 2));
+                    red2(gflow + (size_t)idx * 2, sx, sy);
+                }
+            }
+        } else if (live) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float w = ((c & 1) ? wx : 1.f - wx) * ((c & 2) ? wy : 1.f - wy) *
+                                ((c & 4) ? wz : 1.f - wz);
+                const uint32_t idx = L.offset + idx3(L, cx + (c & 1), cy + ((c >> 1) & 1), cz + (c >> 2));
+                red2(gflow + (size_t)idx * 2, w * g2.x, w * g2.y);
+            }
         }
     }
 }
@@ -1260,8 +1403,12 @@ int nvsf_render_uniform_backward(const nvsf_field_config_t* cfg, const void* wor
         // 4. encoders backward -> table gradients, d flow
         {
             const unsigned blocks = (unsigned)nvsf_div_up(count, (size_t)256);
-            k_encode_bwd<true><<<blocks, 256, 0, s>>>(*cfg, P, G, nullptr, rays_o, rays_d, nears, fars,
-                                                      noise, S, begin, count, flow, dgeo16, dfeat, dflow, scale_s);
+            if (g_enc_bwd_ctas == 3)
+                k_encode_bwd<true, 3><<<blocks, 256, 0, s>>>(*cfg, P, G, nullptr, rays_o, rays_d, nears, fars, noise,
+                                                             S, begin, count, flow, dgeo16, dfeat, dflow, scale_s);
+            else
+                k_encode_bwd<true, 2><<<blocks, 256, 0, s>>>(*cfg, P, G, nullptr, rays_o, rays_d, nears, fars, noise,
+                                                             S, begin, count, flow, dgeo16, dfeat, dflow, scale_s);
         }
         // 5. flow MLP backward -> d flow-grid features; 6. flow-grid scatter
         {
@@ -1301,3 +1448,17 @@ int nvsf_render_uniform_backward(const nvsf_field_config_t* cfg, const void* wor
 }
 
 }  // extern "C"
+
+// ---- tuning options of the backward kernels (nvsf_split_set_option falls through to here) --------
+int nvsf_train_set_option(const char* name, int value) {
+    if (std::string(name) == "enc_bwd_ctas") {
+        if (value != 2 && value != 3) return NVSF_E_INVALID;
+        g_enc_bwd_ctas = value;
+        return NVSF_OK;
+    }
+    return NVSF_E_INVALID;
+}
+int nvsf_train_get_option(const char* name) {
+    if (std::string(name) == "enc_bwd_ctas") return g_enc_bwd_ctas;
+    return NVSF_E_INVALID;
+}
