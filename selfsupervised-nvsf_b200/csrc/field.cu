@@ -463,6 +463,7 @@ FieldPtrs nvsf_make_field_ptrs(const nvsf_field_config_t* cfg, const void* works
     P.pld = reinterpret_cast<const float*>(w + L.pld);
     P.mlp = reinterpret_cast<const __half*>(w + L.mlp);
     P.mlp_tc = w + L.mlp_tc;
+    P.heads_tc = w + L.heads_tc;
     for (int s = 0; s < kPlScales; ++s) {
         P.pls_scale[s] = (uint32_t)L.pls_scale[s];
         P.pld_scale[s] = (uint32_t)L.pld_scale[s];
@@ -567,6 +568,7 @@ int nvsf_field_pack_params(const nvsf_field_config_t* cfg, const nvsf_field_para
         pack(heads[h] + H * in_pad + H * H, H, 0, n_out, H, hm + kHeadW3, kLdK64, 0);
     }
     nvsf_pack_sigma_tc(m, w + L.mlp_tc, s);  // swizzled K-major operand images of the sigma net
+    nvsf_pack_heads_tc(m, w + L.heads_tc, lidar ? 2 : 1, s);
     return nvsf_launch_status();
 }
 

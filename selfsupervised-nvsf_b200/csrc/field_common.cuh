@@ -39,6 +39,7 @@ struct WsLayout {
     size_t pls16;     // __half mirror of pls (same element offsets): one 16-byte texel
     size_t pld16;     // __half mirror of pld
     size_t flow16;    // __half2 [fl_entries]                       fp16 mirror of flow
+    size_t heads_tc;  // head-MLP operand images for tcgen05.mma (render.cu k_composite_tc), 36 KB
     size_t mlp_tc;    // sigma-net and flow-MLP operand images for tcgen05.mma (sigma_tc.cu), 2 x 18 KB
     size_t total;
     size_t pls_scale[NVSF_MAX_PLANE_SCALES];  // float offsets inside pls
@@ -108,6 +109,7 @@ static inline WsLayout make_ws_layout(const nvsf_field_config_t* c) {
     L.pld16 = off; off = ws_align(off + 3 * g * sizeof(__half));
     L.flow16 = off; off = ws_align(off + (size_t)c->fl_entries * sizeof(__half2));
     L.mlp_tc = off; off = ws_align(off + 2 * (size_t)(kHidden * kFeat + kGeo * kHidden) * sizeof(__half));
+    L.heads_tc = off; off = ws_align(off + (size_t)36864);  // render.cu kHImgBytes
     L.total = off;
     return L;
 }
@@ -125,6 +127,7 @@ struct FieldPtrs {
     const float* pld;
     const __half* mlp;
     const void* mlp_tc;
+    const void* heads_tc;
     const TimeInfo* ti;
     uint32_t pls_scale[kPlScales];
     uint32_t pld_scale[kPlScales];
@@ -158,6 +161,7 @@ int nvsf_launch_density_split(const nvsf_field_config_t* cfg, const void* worksp
 int nvsf_density_mode();
 // tcgen05 sigma stage (sigma_tc.cu)
 void nvsf_pack_sigma_tc(const __half* mlp, void* dst, cudaStream_t stream);
+void nvsf_pack_heads_tc(const __half* mlp, void* dst, int nets, cudaStream_t stream);  // render.cu
 int nvsf_launch_sigma_tc(const void* wimg, const __half* feat, size_t count, float* sigma,
                          __half* geo, int sms, cudaStream_t stream);
 // flow stage on tcgen05 (mode 2): flow [n,8] + planar query positions qpos[9][stride]
@@ -174,6 +178,8 @@ int nvsf_split_set_option(const char* name, int value);
 int nvsf_split_get_option(const char* name);
 int nvsf_train_set_option(const char* name, int value);  // train.cu
 int nvsf_train_get_option(const char* name);
+int nvsf_render_set_option(const char* name, int value);  // render.cu
+int nvsf_render_get_option(const char* name);
 // Compositing + heads launcher (render.cu); scratch = sigma f32 [N*S] then geo f16 [N*S,16];
 // rgbs (f32 [N*S,4], may be NULL) receives the per-sample colours for the backward pass.
 int nvsf_render_composite_launch(const nvsf_field_config_t* cfg, const void* workspace,

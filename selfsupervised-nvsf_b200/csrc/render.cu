@@ -11,8 +11,9 @@
 // layer 1.  Transmittance is an exclusive product scan over 32-sample chunks (warp shuffles) with
 // a running carry; chunks in which no sample passes the w > 1e-4 mask skip the heads entirely.
 #include <algorithm>
+#include <string>
 
-#include "field_common.cuh"
+#include "umma.cuh"
 
 namespace {
 
@@ -269,6 +270,372 @@ k_render_composite(const __grid_constant__ nvsf_field_config_t cfg, const __half
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The same renderer with the head MLPs on the 5th-generation tensor cores (tcgen05.mma, TMEM).
+//
+// One CTA per SM, four independent warpgroups; a warpgroup owns a ray and walks it in tiles of 128
+// samples (thread = sample = UMMA row = TMEM lane).  Per tile: transmittance by a 128-wide product
+// scan (shuffles + one exchange through shared memory) with a carry; if any sample passes the
+// w > 1e-4 mask (bar.red.or), the geo rows go into the swizzled K-major operand tile and the heads
+// of BOTH LiDAR nets run as three MMA batches, the hidden activations going TMEM -> tcgen05.ld ->
+// registers (+ per-ray direction term, relu, fp16) -> the operand tile:
+//   D1 [128 x 64 NETS] = geo [128 x 16] W1g^T      1 x tcgen05.mma (N = 128 for LiDAR)
+//   D2[net] [128 x 64] = H1[net] W2[net]^T         4 x tcgen05.mma per net
+//   D3[net] [128 x 16] = H2[net] W3[net]^T         4 x tcgen05.mma per net
+// The next tile's sigma / geo rows are loaded before the first wait, so they travel during the chain.
+// ------------------------------------------------------------------------------------------------
+using namespace umma;
+
+constexpr int kCWG = 4;
+constexpr int kCThreads = kCWG * kRows;
+constexpr uint32_t kHOffW1 = 0;                            // [128 rows][128 B]: rows 64.. = net 1, K = 16
+constexpr uint32_t kHOffW2 = kHOffW1 + 128 * 128;          // 2 x [64 rows][128 B]
+constexpr uint32_t kHOffW3 = kHOffW2 + 2 * kHidden * 128;  // 2 x [16 rows][128 B] (rows >= n_out zero)
+constexpr uint32_t kHImgBytes = kHOffW3 + 2 * 16 * 128;
+constexpr uint32_t kCOffW1d = kHImgBytes;                  // fp16 [2][64][72]: direction columns of layer 1
+constexpr uint32_t kCW1dBytes = 2 * kHidden * kHeadDirMax * 2;
+constexpr uint32_t kCOffTiles = kCOffW1d + kCW1dBytes;
+constexpr uint32_t kCTile = kRows * 128;                   // one [128 rows][128 B] operand tile
+constexpr uint32_t kCScratchFloats = 256;                  // per warpgroup: enc[72] u[128] ptot[4] red[4][8]
+static_assert(kHImgBytes % 1024 == 0 && kCOffTiles % 1024 == 0, "swizzled tiles start on 1024-byte boundaries");
+
+template <bool LIDAR>
+constexpr size_t composite_tc_smem() {
+    return kCOffTiles + (size_t)kCWG * (LIDAR ? 2 : 1) * kCTile + kCWG * kCScratchFloats * 4 + 8 * kCWG + 16 + 1024;
+}
+
+// head weights (fp16 image of field.cu) -> swizzled K-major operand images
+__global__ void k_pack_heads_tc(const __half* __restrict__ mlp, unsigned char* __restrict__ dst, int nets) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;  // one 16-byte chunk each
+    const uint32_t per_net = kHidden * 2 + kHidden * 8 + 8 * 8;
+    if (i >= per_net * (uint32_t)nets) return;
+    const uint32_t net = i / per_net, j = i - net * per_net;
+    const __half* hm = mlp + kHeadBase + net * kHeadHalves;
+    if (j < (uint32_t)kHidden * 2) {                       // W1g [64][16 of 24]
+        const uint32_t r = j >> 1, c = j & 1;
+        *reinterpret_cast<uint4*>(dst + kHOffW1 + swz(net * kHidden + r, c)) =
+            *reinterpret_cast<const uint4*>(hm + kHeadW1g + r * kLdK16 + c * 8);
+    } else if (j < (uint32_t)kHidden * 10) {               // W2 [64][64]
+        const uint32_t k = j - kHidden * 2, r = k >> 3, c = k & 7;
+        *reinterpret_cast<uint4*>(dst + kHOffW2 + net * (kHidden * 128) + swz(r, c)) =
+            *reinterpret_cast<const uint4*>(hm + kHeadW2 + r * kLdK64 + c * 8);
+    } else {                                               // W3 [8][64]
+        const uint32_t k = j - kHidden * 10, r = k >> 3, c = k & 7;
+        *reinterpret_cast<uint4*>(dst + kHOffW3 + net * (16 * 128) + swz(r, c)) =
+            *reinterpret_cast<const uint4*>(hm + kHeadW3 + r * kLdK64 + c * 8);
+    }
+}
+
+__device__ __forceinline__ float sh4_term(int k, float dx, float dy, float dz) {
+    // tcnn SphericalHarmonics degree 4 of 2*((d+1)/2)-1 (same expressions as k_render_composite)
+    const float x = ((dx + 1.0f) * 0.5f) * 2.0f - 1.0f, y = ((dy + 1.0f) * 0.5f) * 2.0f - 1.0f,
+                z = ((dz + 1.0f) * 0.5f) * 2.0f - 1.0f;
+    const float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
+    switch (k) {
+        case 0: return 0.28209479177387814f;
+        case 1: return -0.48860251190291987f * y;
+        case 2: return 0.48860251190291987f * z;
+        case 3: return -0.48860251190291987f * x;
+        case 4: return 1.0925484305920792f * xy;
+        case 5: return -1.0925484305920792f * yz;
+        case 6: return 0.94617469575755997f * z2 - 0.31539156525251999f;
+        case 7: return -1.0925484305920792f * xz;
+        case 8: return 0.54627421529603959f * x2 - 0.54627421529603959f * y2;
+        case 9: return 0.59004358992664352f * y * (-3.0f * x2 + y2);
+        case 10: return 2.8906114426405538f * xy * z;
+        case 11: return 0.45704579946446572f * y * (1.0f - 5.0f * z2);
+        case 12: return 0.3731763325901154f * z * (5.0f * z2 - 3.0f);
+        case 13: return 0.45704579946446572f * x * (1.0f - 5.0f * z2);
+        case 14: return 1.4453057213202769f * z * (x2 - y2);
+        default: return 0.59004358992664352f * x * (-x2 + 3.0f * y2);
+    }
+}
+
+// H[net] row `t` = fp16(relu(D[:, 0..63] (+ u))) from this thread's TMEM lane into the operand tile
+template <bool ADD_U>
+__device__ __forceinline__ void hidden_to_tile(uint32_t taddr, const float* __restrict__ u,
+                                               unsigned char* tile, uint32_t t) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        uint32_t v[16];
+        tmem_ld16(taddr + q * 16, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[8 * h + i]);
+            if (ADD_U) {
+                const float4 ua = *reinterpret_cast<const float4*>(u + q * 16 + 8 * h);
+                const float4 ub = *reinterpret_cast<const float4*>(u + q * 16 + 8 * h + 4);
+                f[0] += ua.x; f[1] += ua.y; f[2] += ua.z; f[3] += ua.w;
+                f[4] += ub.x; f[5] += ub.y; f[6] += ub.z; f[7] += ub.w;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
+            st_chunk(tile, t, 2 * q + h, f);
+        }
+    }
+}
+
+template <bool LIDAR>
+__global__ void __launch_bounds__(kCThreads, 1)
+k_composite_tc(const __grid_constant__ nvsf_field_config_t cfg, const unsigned char* __restrict__ wimg,
+               const __half* __restrict__ mlp, const float* __restrict__ rays_d,
+               const float* __restrict__ nears, const float* __restrict__ fars,
+               const float* __restrict__ noise, const float* __restrict__ sigma,
+               const __half* __restrict__ geo, uint32_t N, uint32_t S, float bg_color,
+               float* __restrict__ depth_out, float* __restrict__ image_out, float* __restrict__ ws_out,
+               float* __restrict__ weights_out, float* __restrict__ z_out, float* __restrict__ rgbs_out) {
+    constexpr int NETS = LIDAR ? 2 : 1;
+    constexpr int NDIR = LIDAR ? 72 : 16;
+    constexpr int NCH = LIDAR ? 2 : 3;
+    constexpr uint32_t kCols = NETS * kHidden;             // TMEM columns of one warpgroup
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    unsigned char* sm = smem_raw + (base - raw);
+    const uint32_t tid = threadIdx.x, wg = tid >> 7, t = tid & 127u, lane = tid & 31u, wq = (tid >> 5) & 3u;
+    constexpr uint32_t kOffScr = kCOffTiles + kCWG * NETS * kCTile;
+    constexpr uint32_t kOffBarC = kOffScr + kCWG * kCScratchFloats * 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + kOffBarC + 8 * kCWG);
+    float* scr = reinterpret_cast<float*>(sm + kOffScr) + wg * kCScratchFloats;
+    float* enc_s = scr;            // [72]
+    float* u_s = scr + 72;         // [NETS * 64]  (16-byte aligned: 72 * 4 = 288)
+    float* ptot = scr + 200;       // [4]
+    float* red = scr + 208;        // [4][8]
+    const __half* W1d = reinterpret_cast<const __half*>(sm + kCOffW1d);
+
+    for (uint32_t i = tid; i < kHImgBytes / 16; i += kCThreads)
+        reinterpret_cast<uint4*>(sm)[i] = __ldg(reinterpret_cast<const uint4*>(wimg) + i);
+    for (int net = 0; net < NETS; ++net)
+        for (uint32_t i = tid; i < (uint32_t)kHidden * kHeadDirMax / 8; i += kCThreads)
+            reinterpret_cast<uint4*>(sm + kCOffW1d)[net * (kHidden * kHeadDirMax / 8) + i] =
+                __ldg(reinterpret_cast<const uint4*>(mlp + kHeadBase + net * kHeadHalves + kHeadW1d) + i);
+    if (tid < (uint32_t)kCWG) mbar_init(base + kOffBarC + 8 * tid, 1);
+    if (tid < 32) {
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(
+                         smem_u32(tmem_slot)),
+                     "r"((uint32_t)(kCWG * kCols))
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t tcol = tmem + wg * kCols;
+    const uint32_t tlane = tcol + ((wq * 32u) << 16);
+    const uint32_t tiles = base + kCOffTiles + wg * NETS * kCTile;
+    unsigned char* tileg = sm + kCOffTiles + wg * NETS * kCTile;
+    const uint32_t bar = base + kOffBarC + 8 * wg;
+    constexpr uint32_t kIdesc1 = umma_idesc(kRows, NETS * kHidden), kIdesc2 = umma_idesc(kRows, kHidden),
+                       kIdesc3 = umma_idesc(kRows, 16);
+    const float kexp = cfg.active_sensor ? 2.0f : 1.0f;
+    uint32_t phase = 0;
+
+    for (uint32_t r = blockIdx.x * kCWG + wg; r < N; r += gridDim.x * kCWG) {
+        const float near = __ldg(nears + r), far = __ldg(fars + r);
+        const float dx = __ldg(rays_d + (size_t)r * 3), dy = __ldg(rays_d + (size_t)r * 3 + 1),
+                    dz = __ldg(rays_d + (size_t)r * 3 + 2);
+        // first tile's rows
+        float sg = 0.f;
+        uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0;
+        if (t < S) {
+            const size_t g = (size_t)r * S + t;
+            sg = __ldg(sigma + g);
+            a0 = __ldg(reinterpret_cast<const uint4*>(geo + g * kGeo));
+            a1 = __ldg(reinterpret_cast<const uint4*>(geo + g * kGeo) + 1);
+        }
+        wg_barrier(wg);  // the previous ray's readers of enc / u / red are done
+        if (LIDAR) {
+            if (t < (uint32_t)NDIR) {  // tcnn Frequency, 12 octaves: sin(2^k pi x + (j&1) pi/2), x = (d+1)/2
+                const int dim = t / 24, oct = (t >> 1) % 12;
+                const float v = ((dim == 0 ? dx : (dim == 1 ? dy : dz)) + 1.0f) * 0.5f;
+                enc_s[t] = sinpif(scalbnf(v, oct) + 0.5f * (float)(t & 1));
+            }
+        } else if (t < 16) {
+            enc_s[t] = sh4_term((int)t, dx, dy, dz);
+        }
+        wg_barrier(wg);
+        if (t < (uint32_t)(NETS * kHidden)) {  // u[net][n] = sum_j W1[n][dir j] * enc[j]
+            const __half* wrow = W1d + (size_t)t * kHeadDirMax;
+            float acc = 0.f;
+            for (int j = 0; j < NDIR; j += 2) {
+                const float2 w = __half22float2(*reinterpret_cast<const __half2*>(wrow + j));
+                acc = fmaf(w.x, enc_s[j], acc);
+                acc = fmaf(w.y, enc_s[j + 1], acc);
+            }
+            u_s[t] = acc;
+        }
+        float carry = 1.0f, ws = 0.f, dep = 0.f, img[NCH];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) img[c] = 0.f;
+
+        for (uint32_t c0 = 0; c0 < S; c0 += kRows) {
+            const uint32_t i = c0 + t;
+            const bool in = i < S;
+            const size_t g = (size_t)r * S + (in ? i : S - 1);
+            const float z = uniform_z2(near, far, in ? i : S - 1, S, noise, g);
+            float delta;
+            if (i + 1 < S) delta = uniform_z2(near, far, i + 1, S, noise, g + 1) - z;
+            else delta = (far - near) / (float)S;  // renderer_dynamic.py:160,182
+            const float alpha = in ? 1.0f - expf(((-kexp * delta) * cfg.density_scale) * sg) : 0.f;
+            const float v = (1.0f - alpha) + 1e-15f;
+            float incl = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const float o = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= (uint32_t)d) incl *= o;
+            }
+            float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+            if (lane == 0) excl = 1.0f;
+            if (lane == 31) ptot[wq] = incl;
+            wg_barrier(wg);
+            const float p0 = ptot[0], p1 = ptot[1], p2 = ptot[2], p3 = ptot[3];
+            const float pre = wq == 0 ? 1.0f : (wq == 1 ? p0 : (wq == 2 ? p0 * p1 : (p0 * p1) * p2));
+            const float T = (carry * pre) * excl;
+            carry *= ((p0 * p1) * p2) * p3;
+            const float w = in ? alpha * T : 0.f;
+            ws += w;
+            dep = fmaf(w, z, dep);
+            if (weights_out && in) { weights_out[g] = w; z_out[g] = z; }
+            const bool m = w > 1e-4f;  // renderer_dynamic.py:202
+            const bool any = wg_any(wg, m);   // also: every thread has read ptot
+            // geo rows of this tile -> operand tile; then the next tile's rows start travelling
+            if (any) {
+                *reinterpret_cast<uint4*>(tileg + swz(t, 0)) = a0;
+                *reinterpret_cast<uint4*>(tileg + swz(t, 1)) = a1;
+            }
+            {
+                const uint32_t in2 = c0 + kRows + t;
+                sg = 0.f; a0 = make_uint4(0, 0, 0, 0); a1 = a0;
+                if (in2 < S) {
+                    const size_t g2 = (size_t)r * S + in2;
+                    sg = __ldg(sigma + g2);
+                    a0 = __ldg(reinterpret_cast<const uint4*>(geo + g2 * kGeo));
+                    a1 = __ldg(reinterpret_cast<const uint4*>(geo + g2 * kGeo) + 1);
+                }
+            }
+            if (!any) {
+                if (rgbs_out && in) *reinterpret_cast<float4*>(rgbs_out + g * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+                continue;
+            }
+            fence_async_smem();
+            tc_fence_before();
+            wg_barrier(wg);
+            if (t == 0) {
+                tc_fence_after();
+                umma_f16(tcol, umma_desc(tiles), umma_desc(base + kHOffW1), kIdesc1, 0u);
+                umma_commit(bar);
+            }
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+            tc_fence_after();
+            // H1 = relu(D1 + u)
+#pragma unroll
+            for (int net = 0; net < NETS; ++net)
+                hidden_to_tile<true>(tlane + net * kHidden, u_s + net * kHidden, tileg + net * kCTile, t);
+            fence_async_smem();
+            tc_fence_before();
+            wg_barrier(wg);
+            if (t == 0) {
+                tc_fence_after();
+#pragma unroll
+                for (uint32_t net = 0; net < (uint32_t)NETS; ++net)
+#pragma unroll
+                    for (uint32_t k = 0; k < 4; ++k)
+                        umma_f16(tcol + net * kHidden, umma_desc(tiles + net * kCTile + k * 32),
+                                 umma_desc(base + kHOffW2 + net * (kHidden * 128) + k * 32), kIdesc2, k);
+                umma_commit(bar);
+            }
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+            tc_fence_after();
+            // H2 = relu(D2)
+#pragma unroll
+            for (int net = 0; net < NETS; ++net)
+                hidden_to_tile<false>(tlane + net * kHidden, nullptr, tileg + net * kCTile, t);
+            fence_async_smem();
+            tc_fence_before();
+            wg_barrier(wg);
+            if (t == 0) {
+                tc_fence_after();
+#pragma unroll
+                for (uint32_t net = 0; net < (uint32_t)NETS; ++net)
+#pragma unroll
+                    for (uint32_t k = 0; k < 4; ++k)
+                        umma_f16(tcol + net * 16, umma_desc(tiles + net * kCTile + k * 32),
+                                 umma_desc(base + kHOffW3 + net * (16 * 128) + k * 32), kIdesc3, k);
+                umma_commit(bar);
+            }
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+            tc_fence_after();
+            // colours of this thread's sample
+            const float wm = m ? w : 0.f;
+            float4 col = make_float4(0.f, 0.f, 0.f, 0.f);
+            {
+                uint32_t o[16];
+                tmem_ld16(tlane, o);
+                tmem_ld_wait();
+                if (LIDAR) {
+                    // h = [raydrop, intensity] (network_dynamic.py:317): net 0 = intensity -> channel 1
+                    uint32_t o2[16];
+                    tmem_ld16(tlane + 16, o2);
+                    tmem_ld_wait();
+                    const float s_int = sigmoidf_(__uint_as_float(o[0])), s_drop = sigmoidf_(__uint_as_float(o2[0]));
+                    img[1] += wm * s_int;
+                    img[0] += wm * s_drop;
+                    if (m) col = make_float4(s_drop, s_int, 0.f, 0.f);
+                } else {
+                    const float s0 = sigmoidf_(__uint_as_float(o[0])), s1 = sigmoidf_(__uint_as_float(o[1])),
+                                s2 = sigmoidf_(__uint_as_float(o[2]));
+                    img[0] += wm * s0; img[1] += wm * s1; img[2] += wm * s2;
+                    if (m) col = make_float4(s0, s1, s2, 0.f);
+                }
+            }
+            if (rgbs_out && in) *reinterpret_cast<float4*>(rgbs_out + g * 4) = col;
+            tc_fence_before();
+        }
+        // ---- reduce over the warpgroup and write the ray ----
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            ws += __shfl_xor_sync(0xffffffffu, ws, d);
+            dep += __shfl_xor_sync(0xffffffffu, dep, d);
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) img[c] += __shfl_xor_sync(0xffffffffu, img[c], d);
+        }
+        if (lane == 0) {
+            red[wq * 8 + 0] = ws; red[wq * 8 + 1] = dep;
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) red[wq * 8 + 2 + c] = img[c];
+        }
+        wg_barrier(wg);
+        if (t == 0) {
+            const float wsum = ((red[0] + red[8]) + red[16]) + red[24];
+            ws_out[r] = wsum;
+            depth_out[r] = ((red[1] + red[9]) + red[17]) + red[25];
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                const float v = ((red[2 + c] + red[10 + c]) + red[18 + c]) + red[26 + c];
+                image_out[(size_t)r * NCH + c] = LIDAR ? v : v + (1.0f - wsum) * bg_color;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (tid < 32)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem),
+                     "r"((uint32_t)(kCWG * kCols))
+                     : "memory");
+}
+
+int g_heads_tc = 1;  // nvsf_set_option("heads_tc", 0 | 1): head MLPs of the uniform renderer on tcgen05
+bool g_tc_attr2 = false;
+
 bool g_attr = false;
 int ensure_attrs() {
     if (g_attr) return NVSF_OK;
@@ -350,6 +717,28 @@ int nvsf_render_composite_launch(const nvsf_field_config_t* cfg, const void* wor
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_heads_tc) {
+        if (!g_tc_attr2) {
+            cudaError_t e = cudaFuncSetAttribute(k_composite_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)composite_tc_smem<true>());
+            if (e != cudaSuccess) return (int)e;
+            e = cudaFuncSetAttribute(k_composite_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)composite_tc_smem<false>());
+            if (e != cudaSuccess) return (int)e;
+            g_tc_attr2 = true;
+        }
+        const uint32_t grid = std::min<uint32_t>(nvsf_div_up(N, (uint32_t)kCWG), (uint32_t)sms);
+        const unsigned char* wimg = reinterpret_cast<const unsigned char*>(P.heads_tc);
+        if (lidar)
+            k_composite_tc<true><<<grid, kCThreads, composite_tc_smem<true>(), s>>>(
+                *cfg, wimg, P.mlp, rays_d, nears, fars, noise, sigma, geo, N, S, bg_color, depth, image,
+                weights_sum, weights, z_vals, reinterpret_cast<float*>(rgbs));
+        else
+            k_composite_tc<false><<<grid, kCThreads, composite_tc_smem<false>(), s>>>(
+                *cfg, wimg, P.mlp, rays_d, nears, fars, noise, sigma, geo, N, S, bg_color, depth, image,
+                weights_sum, weights, z_vals, reinterpret_cast<float*>(rgbs));
+        return nvsf_launch_status();
+    }
     const uint32_t blocks = std::min<uint32_t>(nvsf_div_up(N, (uint32_t)kRWarps), (uint32_t)sms * 4);
     if (lidar) {
         k_render_composite<true><<<blocks, kRWarps * 32, render_smem<true>(), s>>>(
@@ -380,3 +769,23 @@ int nvsf_render_uniform(const nvsf_field_config_t* cfg, const void* workspace, u
 }
 
 }  // extern "C"
+
+void nvsf_pack_heads_tc(const __half* mlp, void* dst, int nets, cudaStream_t stream) {
+    cudaMemsetAsync(dst, 0, kHImgBytes, stream);
+    const int chunks = nets * (kHidden * 2 + kHidden * 8 + 8 * 8);
+    k_pack_heads_tc<<<nvsf_div_up(chunks, 128), 128, 0, stream>>>(mlp, reinterpret_cast<unsigned char*>(dst), nets);
+}
+
+// ---- tuning options of the renderer (nvsf_train_set_option falls through to here) -----------------
+int nvsf_render_set_option(const char* name, int value) {
+    if (std::string(name) == "heads_tc") {
+        if (value != 0 && value != 1) return NVSF_E_INVALID;
+        g_heads_tc = value;
+        return NVSF_OK;
+    }
+    return NVSF_E_INVALID;
+}
+int nvsf_render_get_option(const char* name) {
+    if (std::string(name) == "heads_tc") return g_heads_tc;
+    return NVSF_E_INVALID;
+}

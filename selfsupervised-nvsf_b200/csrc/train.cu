@@ -112,10 +112,15 @@ k_mlp_bwd(const typename T::Args A, const bf16* __restrict__ w1g, const bf16* __
     __syncthreads();
 
     const size_t n_tiles = (n + kBwdRows - 1) / kBwdRows;
+    typename T::Pref pf;
+    if (blockIdx.x < n_tiles) T::load(A, (size_t)blockIdx.x * kBwdRows, n, pf, tid);
     for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const size_t row0 = tile * kBwdRows;
-        T::fill(A, row0, n, Xs, Ds, tid, scale);
+        T::fill(A, row0, n, Xs, Ds, tid, scale, pf);
         __syncthreads();
+        // the next tile's global rows travel while this one is computed (one CTA of 8 warps per SM
+        // hides no latency on its own: ncu had 24 % of the head kernel's samples on these loads)
+        if (tile + gridDim.x < n_tiles) T::load(A, (tile + gridDim.x) * kBwdRows, n, pf, tid);
 
         // ---- per-warp chain on rows [16 warp, 16 warp + 16) ----
         const int r0 = warp * 16;
@@ -210,8 +215,10 @@ struct SigmaT {
         const float* dgeo16;   // [n,16]
         float* dfeat;          // [n,128]
     };
+    struct Pref {};
+    static __device__ __forceinline__ void load(const Args&, size_t, size_t, Pref&, int) {}
     static __device__ __forceinline__ void fill(const Args& A, size_t row0, size_t n, bf16* Xs,
-                                                bf16* Ds, int tid, float scale) {
+                                                bf16* Ds, int tid, float scale, const Pref&) {
         constexpr int LDX = KIN + 8;
 #pragma unroll 4
         for (int i = tid; i < kBwdRows * 16; i += kBwdWarps * 32) {
@@ -247,8 +254,10 @@ struct FlowT {
         const float* dflow;      // [n,8]  (6 used, 2 zero)
         float* dflowfeat;        // [n,32]
     };
+    struct Pref {};
+    static __device__ __forceinline__ void load(const Args&, size_t, size_t, Pref&, int) {}
     static __device__ __forceinline__ void fill(const Args& A, size_t row0, size_t n, bf16* Xs,
-                                                bf16* Ds, int tid, float scale) {
+                                                bf16* Ds, int tid, float scale, const Pref&) {
         constexpr int LDX = KIN + 8;
         for (int i = tid; i < kBwdRows * 4; i += kBwdWarps * 32) {
             const int r = i >> 2, c = i & 3;
@@ -311,8 +320,37 @@ struct HeadT {
         int net;                // lidar: 0 = intensity_net (image channel 1), 1 = raydrop_net (channel 0)
         int accumulate;
     };
+    struct Pref {           // the global rows of one tile row, loaded one tile ahead
+        uint4 g0, g1;       // geo [16] halves
+        float w;            // weights[g]
+        float4 cc;          // kept colours
+        float gi[3];        // dL/dimage of the row's ray
+        float d[3];         // ray direction (camera: SH input)
+    };
+    static __device__ __forceinline__ void load(const Args& A, size_t row0, size_t n, Pref& pf, int tid) {
+        const int r = tid >> 1, half = tid & 1;
+        const size_t g = row0 + r;
+        if (g >= n) return;
+        const size_t ray = g / A.S;
+        pf.g0 = __ldg(reinterpret_cast<const uint4*>(A.geo + g * 16));
+        pf.g1 = __ldg(reinterpret_cast<const uint4*>(A.geo + g * 16) + 1);
+        if (!LIDAR) {
+            pf.d[0] = __ldg(A.rays_d + ray * 3); pf.d[1] = __ldg(A.rays_d + ray * 3 + 1);
+            pf.d[2] = __ldg(A.rays_d + ray * 3 + 2);
+        }
+        if (half == 0) {
+            pf.w = __ldg(A.weights + g);
+            pf.cc = __ldg(reinterpret_cast<const float4*>(A.rgbs + g * 4));
+            if (LIDAR) {
+                pf.gi[0] = __ldg(A.g_image + ray * 2 + (A.net == 0 ? 1 : 0));
+            } else {
+                pf.gi[0] = __ldg(A.g_image + ray * 3); pf.gi[1] = __ldg(A.g_image + ray * 3 + 1);
+                pf.gi[2] = __ldg(A.g_image + ray * 3 + 2);
+            }
+        }
+    }
     static __device__ __forceinline__ void fill(const Args& A, size_t row0, size_t n, bf16* Xs,
-                                                bf16* Ds, int tid, float scale) {
+                                                bf16* Ds, int tid, float scale, const Pref& pf) {
         constexpr int LDX = KIN + 8;
         const int r = tid >> 1, half = tid & 1;
         const size_t g = row0 + r;
@@ -346,16 +384,12 @@ struct HeadT {
             return;
         }
         const size_t ray = g / A.S;
-        const float dx = __ldg(A.rays_d + ray * 3), dy = __ldg(A.rays_d + ray * 3 + 1),
-                    dz = __ldg(A.rays_d + ray * 3 + 2);
         // geo features: 16 halves; cols NDIR + (0..14) = geo[1..15], col NDIR+15 = 0
-        const uint4 g0 = __ldg(reinterpret_cast<const uint4*>(A.geo + g * 16));
-        const uint4 g1 = __ldg(reinterpret_cast<const uint4*>(A.geo + g * 16) + 1);
-        const __half* gh0 = reinterpret_cast<const __half*>(&g0);
-        const __half* gh1 = reinterpret_cast<const __half*>(&g1);
+        const __half* gh0 = reinterpret_cast<const __half*>(&pf.g0);
+        const __half* gh1 = reinterpret_cast<const __half*>(&pf.g1);
         if (!LIDAR) {
             float sh[16];
-            sh4_eval(dx, dy, dz, sh);
+            sh4_eval(pf.d[0], pf.d[1], pf.d[2], sh);
 #pragma unroll
             for (int j = 0; j < 8; j += 2)
                 *reinterpret_cast<uint32_t*>(xr + half * 8 + j) =
@@ -369,20 +403,19 @@ struct HeadT {
                 *reinterpret_cast<uint32_t*>(xr + NDIR + j) = pack_bf2(a, b);
             }
             // output gradient: w * dL/dimage[ch] * c (1 - c) on the samples that passed the mask
-            const float w = __ldg(A.weights + g), ws = scale * w;
+            const float w = pf.w, ws = scale * w;
             uint4 o0 = make_uint4(0, 0, 0, 0);
             if (w > 1e-4f) {
-                const float4 cc = __ldg(reinterpret_cast<const float4*>(A.rgbs + g * 4));
+                const float4 cc = pf.cc;
                 const float2 c01 = make_float2(cc.x, cc.y), c23 = make_float2(cc.z, cc.w);
                 if (LIDAR) {
                     const int ch = A.net == 0 ? 1 : 0;
                     const float c = ch ? c01.y : c01.x;
-                    o0.x = pack_bf2(ws * __ldg(A.g_image + ray * 2 + ch) * c * (1.f - c), 0.f);
+                    o0.x = pack_bf2(ws * pf.gi[0] * c * (1.f - c), 0.f);
                 } else {
-                    const float* gi = A.g_image + ray * 3;
-                    o0.x = pack_bf2(ws * __ldg(gi) * c01.x * (1.f - c01.x),
-                                    ws * __ldg(gi + 1) * c01.y * (1.f - c01.y));
-                    o0.y = pack_bf2(ws * __ldg(gi + 2) * c23.x * (1.f - c23.x), 0.f);
+                    o0.x = pack_bf2(ws * pf.gi[0] * c01.x * (1.f - c01.x),
+                                    ws * pf.gi[1] * c01.y * (1.f - c01.y));
+                    o0.y = pack_bf2(ws * pf.gi[2] * c23.x * (1.f - c23.x), 0.f);
                 }
             }
             *reinterpret_cast<uint4*>(Ds + r * kLdD) = o0;
@@ -679,7 +712,7 @@ __device__ __forceinline__ void scatter2d(float* __restrict__ base, uint32_t R, 
         a01 = fmaf(v1, 1.f - wy, a01);
         a10 = fmaf(v0, wy, a10);
         a11 = fmaf(v1, wy, a11);
-        if (in.w & 4u) {
+        if (in.w & 4u) {   // (predicated reds instead of this branch measured slower: 4.0 -> 4.3 ms)
             float* t = base + (size_t)in.x * 8 + f;
             const uint32_t ox = (in.w & 1u) ? 8u : 0u, oy = (in.w & 2u) ? R * 8u : 0u;
             red1(t, a00);
@@ -886,11 +919,15 @@ k_encode_bwd(const __grid_constant__ nvsf_field_config_t cfg, const __grid_const
     // run with shuffles first and only the head lane of a run issues the reds.
     const bool plive = __shfl_up_sync(0xffffffffu, (int)live, 1) != 0;
     const bool edge = lane == 0 || !live || !plive;
+    // (the per-level gradient rows are loaded one iteration ahead: a dependent global load per
+    // level was the largest stall of this part)
+    float4 g4n = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) g4n = __ldg(reinterpret_cast<const float4*>(df + 64));
 #pragma unroll 1
     for (int l = 0; l < kHsLevels; ++l) {
         const LevelArgs L = lv(cfg.hs[l]);
-        float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (live) g4 = __ldg(reinterpret_cast<const float4*>(df + 64 + 4 * l));
+        const float4 g4 = g4n;
+        if (live && l + 1 < kHsLevels) g4n = __ldg(reinterpret_cast<const float4*>(df + 64 + 4 * (l + 1)));
         uint32_t cx, cy, cz;
         float wx, wy, wz;
         grid_pos(L.scale, x, cx, wx);
@@ -925,6 +962,7 @@ k_encode_bwd(const __grid_constant__ nvsf_field_config_t cfg, const __grid_const
     // (d) dynamic 2-D hashes: gradient through the un-warped query only; a missing neighbour
     // frame re-uses the un-warped feature (network_dynamic.py:238-239) -> factor 0.5 + 0.25 each
     const float fac = lv_ * (0.5f + (valid1 ? 0.f : 0.25f) + (valid2 ? 0.f : 0.25f));
+    float gsn = live ? __ldg(df + 96) : 0.f;
 #pragma unroll 1
     for (int p = 0; p < 3; ++p) {
         const float u = p == 2 ? y : x, w2 = p == 0 ? y : z;
@@ -932,7 +970,8 @@ k_encode_bwd(const __grid_constant__ nvsf_field_config_t cfg, const __grid_const
 #pragma unroll 1
         for (int l = 0; l < kHdLevels; ++l) {
             const LevelArgs L = lv(cfg.hd[p][l]);
-            const float gs = live ? fac * __ldg(df + 96 + 8 * p + l) : 0.f;
+            const float gs = fac * gsn;
+            if (live && 8 * p + l + 1 < 3 * kHdLevels) gsn = __ldg(df + 96 + 8 * p + l + 1);
             uint32_t cu, cv;
             float wu, wv;
             grid_pos(L.scale, u, cu, wu);
@@ -1003,11 +1042,13 @@ k_flowgrid_bwd(const __grid_constant__ nvsf_field_config_t cfg, float* __restric
     // samples per cell on level 0, 4 on level 9).  Where a warp holds at most 16 runs of equal
     // cells, the 16 corner x feature products are summed over each run with shuffles and only the
     // first lane of a run issues the 8 reds.
+    float2 g2n = make_float2(0.f, 0.f);
+    if (live) g2n = __ldg(reinterpret_cast<const float2*>(dflowfeat + li * 32));
 #pragma unroll 1
     for (int l = 0; l < kFlLevels; ++l) {
         const LevelArgs L = lv(cfg.fl[l]);
-        float2 g2 = make_float2(0.f, 0.f);
-        if (live) g2 = __ldg(reinterpret_cast<const float2*>(dflowfeat + li * 32 + 2 * l));
+        const float2 g2 = g2n;
+        if (live && l + 1 < kFlLevels) g2n = __ldg(reinterpret_cast<const float2*>(dflowfeat + li * 32 + 2 * (l + 1)));
         uint32_t cx, cy, cz;
         float wx, wy, wz;
         grid_pos(L.scale, x, cx, wx);
@@ -1456,9 +1497,9 @@ int nvsf_train_set_option(const char* name, int value) {
         g_enc_bwd_ctas = value;
         return NVSF_OK;
     }
-    return NVSF_E_INVALID;
+    return nvsf_render_set_option(name, value);
 }
 int nvsf_train_get_option(const char* name) {
     if (std::string(name) == "enc_bwd_ctas") return g_enc_bwd_ctas;
-    return NVSF_E_INVALID;
+    return nvsf_render_get_option(name);
 }

@@ -314,3 +314,39 @@ def test_tiny_and_ragged_point_counts(pkg, model, orc, n):
 def test_empty_point_set(model):
     r = model.density(torch.empty(0, 3, device="cuda"), 0.5, True)
     assert r["sigma"].shape == (0,) and r["geo_feat"].shape == (0, 15)
+
+
+@pytest.mark.parametrize("lidar", [True, False])
+@pytest.mark.parametrize("steps", [768, 200, 128, 37])
+def test_composite_heads_tcgen05_matches_mma_sync(pkg, model, lidar, steps):
+    """Compositing with the head MLPs on tcgen05.mma / TMEM (csrc/render.cu k_composite_tc, option
+    heads_tc: a warpgroup per ray, 128-sample UMMA tiles, three chained MMA batches per tile) against
+    the mma.sync renderer k_render_composite: same fp16 operands and masks; the transmittance scan is
+    128 instead of 32 samples wide and the fp32 sums run in a different order.  Covers whole tiles,
+    ragged last tiles (200, 37 samples), both modalities, weights / z_vals outputs and perturbation."""
+    L = pkg._lib.lib()
+    if lidar:
+        o, d = S.lidar_rays(333, seed=41)
+    else:
+        o, d = S.camera_rays(333, seed=42)
+    to, td = torch.from_numpy(o).cuda()[None], torch.from_numpy(d).cuda()[None]
+    noise = torch.rand(333, steps, device="cuda", generator=torch.Generator("cuda").manual_seed(5))
+    out = {}
+    try:
+        for tc in (0, 1):
+            assert L.nvsf_set_option(b"heads_tc", tc) == 0
+            assert L.nvsf_get_option(b"heads_tc") == tc
+            with torch.no_grad():
+                r = model.run(to, td, torch.tensor([[0.45]], device="cuda"), cal_lidar_color=lidar, num_steps=steps,
+                              perturb=True, noise=noise)
+            torch.cuda.synchronize()
+            sfx = "_lidar" if lidar else ""
+            out[tc] = (host(r["depth" + sfx]), host(r["image" + sfx]), host(r["weights_sum" + sfx]),
+                       host(r["weights"]), host(r["z_vals"]))
+    finally:
+        L.nvsf_set_option(b"heads_tc", 1)
+    assert np.abs(out[0][1]).max() > 1e-3
+    assert np.array_equal(out[1][4], out[0][4])
+    for a, b, name in zip(out[1], out[0], ("depth", "image", "weights_sum", "weights")):
+        close(a, b, 1e-4 if name != "image" else 2e-3, 1e-6 if name != "image" else 2e-3 * np.abs(b).max(),
+              f"heads tcgen05 vs mma.sync {name} (S={steps})")
