@@ -301,7 +301,7 @@ static_assert(kHImgBytes % 1024 == 0 && kCOffTiles % 1024 == 0, "swizzled tiles 
 
 template <bool LIDAR>
 constexpr size_t composite_tc_smem() {
-    return kCOffTiles + (size_t)kCWG * (LIDAR ? 2 : 1) * kCTile + kCWG * kCScratchFloats * 4 + 8 * kCWG + 16 + 1024;
+    return kCOffTiles + (size_t)kCWG * (LIDAR ? 2 : 1) * kCTile + kCWG * kCScratchFloats * 4 + 16 * kCWG + 16 + 1024;
 }
 
 // head weights (fp16 image of field.cu) -> swizzled K-major operand images
@@ -351,29 +351,38 @@ __device__ __forceinline__ float sh4_term(int k, float dx, float dy, float dz) {
     }
 }
 
+__device__ __forceinline__ uint32_t relu_h2(uint32_t h2) {
+    uint32_t r;
+    asm("max.f16x2 %0, %1, %2;" : "=r"(r) : "r"(h2), "r"(0u));
+    return r;
+}
+
 // H[net] row `t` = fp16(relu(D[:, 0..63] (+ u))) from this thread's TMEM lane into the operand tile
 template <bool ADD_U>
 __device__ __forceinline__ void hidden_to_tile(uint32_t taddr, const float* __restrict__ u,
                                                unsigned char* tile, uint32_t t) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        uint32_t v[16];
-        tmem_ld16(taddr + q * 16, v);
+    for (int q = 0; q < 4; q += 2) {
+        uint32_t v[2][16];
+        tmem_ld16(taddr + q * 16, v[0]);       // two loads in flight per wait
+        tmem_ld16(taddr + q * 16 + 16, v[1]);
         tmem_ld_wait();
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < 4; ++h) {
             float f[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[8 * h + i]);
+            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[h >> 1][8 * (h & 1) + i]);
             if (ADD_U) {
                 const float4 ua = *reinterpret_cast<const float4*>(u + q * 16 + 8 * h);
                 const float4 ub = *reinterpret_cast<const float4*>(u + q * 16 + 8 * h + 4);
                 f[0] += ua.x; f[1] += ua.y; f[2] += ua.z; f[3] += ua.w;
                 f[4] += ub.x; f[5] += ub.y; f[6] += ub.z; f[7] += ub.w;
             }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
-            st_chunk(tile, t, 2 * q + h, f);
+            // relu after the rounding to fp16 (monotonic, so identical) on packed halves: 4 instead of 8 max
+            uint4 o;
+            o.x = relu_h2(pack_half2(f[0], f[1])); o.y = relu_h2(pack_half2(f[2], f[3]));
+            o.z = relu_h2(pack_half2(f[4], f[5])); o.w = relu_h2(pack_half2(f[6], f[7]));
+            *reinterpret_cast<uint4*>(tile + swz(t, 2 * q + h)) = o;
         }
     }
 }
@@ -398,7 +407,7 @@ k_composite_tc(const __grid_constant__ nvsf_field_config_t cfg, const unsigned c
     const uint32_t tid = threadIdx.x, wg = tid >> 7, t = tid & 127u, lane = tid & 31u, wq = (tid >> 5) & 3u;
     constexpr uint32_t kOffScr = kCOffTiles + kCWG * NETS * kCTile;
     constexpr uint32_t kOffBarC = kOffScr + kCWG * kCScratchFloats * 4;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + kOffBarC + 8 * kCWG);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + kOffBarC + 16 * kCWG);
     float* scr = reinterpret_cast<float*>(sm + kOffScr) + wg * kCScratchFloats;
     float* enc_s = scr;            // [72]
     float* u_s = scr + 72;         // [NETS * 64]  (16-byte aligned: 72 * 4 = 288)
@@ -412,7 +421,7 @@ k_composite_tc(const __grid_constant__ nvsf_field_config_t cfg, const unsigned c
         for (uint32_t i = tid; i < (uint32_t)kHidden * kHeadDirMax / 8; i += kCThreads)
             reinterpret_cast<uint4*>(sm + kCOffW1d)[net * (kHidden * kHeadDirMax / 8) + i] =
                 __ldg(reinterpret_cast<const uint4*>(mlp + kHeadBase + net * kHeadHalves + kHeadW1d) + i);
-    if (tid < (uint32_t)kCWG) mbar_init(base + kOffBarC + 8 * tid, 1);
+    if (tid < (uint32_t)(2 * kCWG)) mbar_init(base + kOffBarC + 8 * tid, 1);
     if (tid < 32) {
         __syncwarp();
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(
@@ -430,9 +439,8 @@ k_composite_tc(const __grid_constant__ nvsf_field_config_t cfg, const unsigned c
     const uint32_t tlane = tcol + ((wq * 32u) << 16);
     const uint32_t tiles = base + kCOffTiles + wg * NETS * kCTile;
     unsigned char* tileg = sm + kCOffTiles + wg * NETS * kCTile;
-    const uint32_t bar = base + kOffBarC + 8 * wg;
-    constexpr uint32_t kIdesc1 = umma_idesc(kRows, NETS * kHidden), kIdesc2 = umma_idesc(kRows, kHidden),
-                       kIdesc3 = umma_idesc(kRows, 16);
+    const uint32_t bar = base + kOffBarC + 16 * wg;   // one mbarrier per net
+    constexpr uint32_t kIdesc2 = umma_idesc(kRows, kHidden), kIdesc3 = umma_idesc(kRows, 16);
     const float kexp = cfg.active_sensor ? 2.0f : 1.0f;
     uint32_t phase = 0;
 
@@ -503,12 +511,10 @@ k_composite_tc(const __grid_constant__ nvsf_field_config_t cfg, const unsigned c
             dep = fmaf(w, z, dep);
             if (weights_out && in) { weights_out[g] = w; z_out[g] = z; }
             const bool m = w > 1e-4f;  // renderer_dynamic.py:202
-            const bool any = wg_any(wg, m);   // also: every thread has read ptot
-            // geo rows of this tile -> operand tile; then the next tile's rows start travelling
-            if (any) {
-                *reinterpret_cast<uint4*>(tileg + swz(t, 0)) = a0;
-                *reinterpret_cast<uint4*>(tileg + swz(t, 1)) = a1;
-            }
+            // geo rows of this tile -> operand tile (it aliases the LAST net's hidden tile, see the
+            // hazards below); then the next tile's rows start travelling
+            *reinterpret_cast<uint4*>(tileg + (NETS - 1) * kCTile + swz(t, 0)) = a0;
+            *reinterpret_cast<uint4*>(tileg + (NETS - 1) * kCTile + swz(t, 1)) = a1;
             {
                 const uint32_t in2 = c0 + kRows + t;
                 sg = 0.f; a0 = make_uint4(0, 0, 0, 0); a1 = a0;
@@ -519,59 +525,66 @@ k_composite_tc(const __grid_constant__ nvsf_field_config_t cfg, const unsigned c
                     a1 = __ldg(reinterpret_cast<const uint4*>(geo + g2 * kGeo) + 1);
                 }
             }
-            if (!any) {
+            fence_async_smem();
+            tc_fence_before();
+            // one barrier: the tile rows are complete, every thread has read ptot, and the OR of the mask
+            if (!wg_any(wg, m)) {
                 if (rgbs_out && in) *reinterpret_cast<float4*>(rgbs_out + g * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
                 continue;
             }
-            fence_async_smem();
-            tc_fence_before();
-            wg_barrier(wg);
+            // The two LiDAR nets are independent chains with their own mbarrier: while one net's MMA
+            // batch is in flight the warpgroup runs the other net's epilogue.  Hazards: H[0] is
+            // written while MMA1(net 1) may still read the geo tile -> the geo tile lives in H[1];
+            // H[1] is written after bar 1, whose commit follows both layer-1 MMAs.
             if (t == 0) {
                 tc_fence_after();
-                umma_f16(tcol, umma_desc(tiles), umma_desc(base + kHOffW1), kIdesc1, 0u);
-                umma_commit(bar);
+#pragma unroll
+                for (uint32_t net = 0; net < (uint32_t)NETS; ++net) {
+                    umma_f16(tcol + net * kHidden, umma_desc(tiles + (NETS - 1) * kCTile),
+                             umma_desc(base + kHOffW1 + net * (kHidden * 128)), kIdesc2, 0u);
+                    umma_commit(bar + 8 * net);
+                }
             }
-            mbar_wait(bar, phase);
-            phase ^= 1u;
-            tc_fence_after();
-            // H1 = relu(D1 + u)
+            // H1 = relu(D1 + u) -> D2 = H1 W2^T
 #pragma unroll
-            for (int net = 0; net < NETS; ++net)
-                hidden_to_tile<true>(tlane + net * kHidden, u_s + net * kHidden, tileg + net * kCTile, t);
-            fence_async_smem();
-            tc_fence_before();
-            wg_barrier(wg);
-            if (t == 0) {
+            for (uint32_t net = 0; net < (uint32_t)NETS; ++net) {
+                mbar_wait(bar + 8 * net, phase);
                 tc_fence_after();
-#pragma unroll
-                for (uint32_t net = 0; net < (uint32_t)NETS; ++net)
+                hidden_to_tile<true>(tlane + net * kHidden, u_s + net * kHidden, tileg + net * kCTile, t);
+                fence_async_smem();
+                tc_fence_before();
+                wg_barrier(wg);
+                if (t == 0) {
+                    tc_fence_after();
 #pragma unroll
                     for (uint32_t k = 0; k < 4; ++k)
                         umma_f16(tcol + net * kHidden, umma_desc(tiles + net * kCTile + k * 32),
                                  umma_desc(base + kHOffW2 + net * (kHidden * 128) + k * 32), kIdesc2, k);
-                umma_commit(bar);
+                    umma_commit(bar + 8 * net);
+                }
             }
-            mbar_wait(bar, phase);
             phase ^= 1u;
-            tc_fence_after();
-            // H2 = relu(D2)
+            // H2 = relu(D2) -> D3 = H2 W3^T (16 columns at the start of the net's column block)
 #pragma unroll
-            for (int net = 0; net < NETS; ++net)
-                hidden_to_tile<false>(tlane + net * kHidden, nullptr, tileg + net * kCTile, t);
-            fence_async_smem();
-            tc_fence_before();
-            wg_barrier(wg);
-            if (t == 0) {
+            for (uint32_t net = 0; net < (uint32_t)NETS; ++net) {
+                mbar_wait(bar + 8 * net, phase);
                 tc_fence_after();
-#pragma unroll
-                for (uint32_t net = 0; net < (uint32_t)NETS; ++net)
+                hidden_to_tile<false>(tlane + net * kHidden, nullptr, tileg + net * kCTile, t);
+                fence_async_smem();
+                tc_fence_before();
+                wg_barrier(wg);
+                if (t == 0) {
+                    tc_fence_after();
 #pragma unroll
                     for (uint32_t k = 0; k < 4; ++k)
-                        umma_f16(tcol + net * 16, umma_desc(tiles + net * kCTile + k * 32),
+                        umma_f16(tcol + net * kHidden, umma_desc(tiles + net * kCTile + k * 32),
                                  umma_desc(base + kHOffW3 + net * (16 * 128) + k * 32), kIdesc3, k);
-                umma_commit(bar);
+                    umma_commit(bar + 8 * net);
+                }
             }
-            mbar_wait(bar, phase);
+            phase ^= 1u;
+#pragma unroll
+            for (uint32_t net = 0; net < (uint32_t)NETS; ++net) mbar_wait(bar + 8 * net, phase);
             phase ^= 1u;
             tc_fence_after();
             // colours of this thread's sample
@@ -584,7 +597,7 @@ k_composite_tc(const __grid_constant__ nvsf_field_config_t cfg, const unsigned c
                 if (LIDAR) {
                     // h = [raydrop, intensity] (network_dynamic.py:317): net 0 = intensity -> channel 1
                     uint32_t o2[16];
-                    tmem_ld16(tlane + 16, o2);
+                    tmem_ld16(tlane + kHidden, o2);
                     tmem_ld_wait();
                     const float s_int = sigmoidf_(__uint_as_float(o[0])), s_drop = sigmoidf_(__uint_as_float(o2[0]));
                     img[1] += wm * s_int;
