@@ -39,6 +39,8 @@ WORKLOAD = ("KITTI-360-shaped LiDAR range image 66x1030 full-frame render (depth
 #   outputs sigma f32 + geo f16[16]                             =   36
 DENSITY_BYTES_PER_SAMPLE = 512 + 1152 + 1024 + 1536 + 2304 + 36
 SURVEY_BYTES_PER_SAMPLE = 13312 + 48  # the reference's un-collapsed gathers
+HEADS_FLOP_PER_SAMPLE = 2 * 2 * (87 * 64 + 64 * 64 + 64 * 1)            # SURVEY.md 8(d), LiDAR heads
+HEADS_EXECUTED_FLOP_PER_SAMPLE = 2 * 2 * (16 * 64 + 64 * 64 + 64 * 16)  # what k_composite_tc issues per sample
 # Per-stage algorithmic bytes per sample of the staged density evaluation; the
 # roofline object describes whichever stage took the largest share of the timed steps.
 #   mode 1 (fp32 collapsed tables):  flow stage  = flow grid 16 x 8 x 8 B + 32 B flow out
@@ -479,6 +481,7 @@ def main():
         tr = json.load(open(tr_path)).get(top_kernel, {})
         traffic, limiter = tr.get("dram_bytes_per_launch"), tr.get("limiter")
     kernels_per_chunk = sum(1 for b, k in table.values() if k != "-")
+    tensor_peak = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops", 1590.0)))
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -503,6 +506,18 @@ def main():
                      "stages": {k: {"kernel": table[k][1], "ms_per_step": stage_step_ms[k], "bytes_per_sample": table[k][0],
                                     "achieved_gbs": (table[k][0] * n_samples / (stage_step_ms[k] * 1e-3) / 1e9
                                                      if stage_step_ms[k] > 0.1 else None)} for k in table},
+                     "heads": {"bound": "tensor",
+                               "kernel": "k_composite_tc" if int(L.nvsf_get_option(b"heads_tc")) else "k_render_composite",
+                               "ms_per_step": comp_ms, "flop_per_sample": HEADS_FLOP_PER_SAMPLE,
+                               "executed_flop_per_sample": HEADS_EXECUTED_FLOP_PER_SAMPLE,
+                               "achieved": HEADS_FLOP_PER_SAMPLE * n_samples / (comp_ms * 1e-3) / 1e12,
+                               "achieved_executed": HEADS_EXECUTED_FLOP_PER_SAMPLE * n_samples / (comp_ms * 1e-3) / 1e12,
+                               "peak": tensor_peak, "unit": "TFLOP/s", "peak_kind": "sustained dense bf16 (cuBLAS, measured)",
+                               "frac": HEADS_FLOP_PER_SAMPLE * n_samples / (comp_ms * 1e-3) / 1e12 / tensor_peak,
+                               "note": "compositing + intensity / raydrop heads of every sample (all pass the w > 1e-4 mask "
+                                       "with random-init weights); algorithmic flops are SURVEY 8(d)'s 2 nets x 2 (87*64 + "
+                                       "64*64 + 64*1); executed = 2 nets x 2 (16*64 + 64*64 + 64*16): the direction columns "
+                                       "of layer 1 are evaluated once per ray"},
                      "note": "algorithmic bytes are table gathers; the 40 MB of fp16 tables are L2 resident, so the "
                              "achieved figure may exceed the HBM peak while DRAM traffic stays far below it"},
     }
