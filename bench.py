@@ -185,8 +185,8 @@ def run_reference(args):
 
 def bench_train(pkg, S, cfg_kw, dev, rank, world, rays, steps, warmup):
     """Joint training step (BASELINE configs[2] at 4096+4096 rays, configs[4] at 32768+32768 rays per
-    GPU): per step, pinned host rays -> device, LiDAR render + loss + backward, camera render +
-    loss + backward (NeRFNetwork.render with autograd, 768 samples/ray, perturb=True), gradient
+    GPU): per step, pinned host rays -> device, LiDAR render + loss head + backward, camera render +
+    loss head + backward (NeRFNetwork.render with autograd, 768 samples/ray, perturb=True), gradient
     all-reduce over NCCL overlapped per group (dist.GradSync), Adam step (optim.FlatAdam), loss
     read back to the host.  Returns whole-job rays/s from the max-over-ranks device time."""
     import numpy as np
@@ -200,9 +200,11 @@ def bench_train(pkg, S, cfg_kw, dev, rank, world, rays, steps, warmup):
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
     lo_h, ld_h, co_h, cd_h = pin(lo), pin(ld), pin(co), pin(cd)
     g = torch.Generator(device=dev).manual_seed(7 + rank)
-    gt_d = torch.rand(rays, device=dev, generator=g) * 0.8
-    gt_i = torch.rand(rays, 2, device=dev, generator=g)
-    gt_c = torch.rand(rays, 3, device=dev, generator=g)
+    # images_lidar [1, N, 3] = (raydrop mask, intensity, depth) as the reference's train_step reads it
+    gt_l = torch.rand(1, rays, 3, device=dev, generator=g)
+    gt_l[..., 0] = (gt_l[..., 0] > 0.2).float()
+    gt_l[..., 2] *= 0.8
+    gt_c = torch.rand(1, rays, 3, device=dev, generator=g)
     loss_h = torch.zeros(1).pin_memory()
     t = torch.tensor([[0.4]], device=dev)
 
@@ -211,11 +213,12 @@ def bench_train(pkg, S, cfg_kw, dev, rank, world, rays, steps, warmup):
         c, d = co_h.to(dev, non_blocking=True), cd_h.to(dev, non_blocking=True)
         opt.zero_grad()
         ol = model.render(a[None], b[None], t, cal_lidar_color=True, staged=False, num_steps=NUM_STEPS, perturb=True)
-        l1 = (ol["depth_lidar"].view(-1) - gt_d).abs().mean() + ((ol["image_lidar"].view(-1, 2) - gt_i) ** 2).mean()
+        # loss head of trainer.py:184-216 / 503-504 (csrc/loss.cu: loss and its derivative in one kernel)
+        l1 = pkg.losses.lidar_loss(ol["depth_lidar"], ol["image_lidar"], gt_l).sum()
         l1.backward()
         opt.sync.reduce_group("lidar")      # overlaps the camera render
         oc = model.render(c[None], d[None], t, cal_lidar_color=False, staged=False, num_steps=NUM_STEPS, perturb=True)
-        l2 = ((oc["image"].view(-1, 3) - gt_c) ** 2).mean()
+        l2 = pkg.losses.rgb_loss(oc["image"], gt_c).sum()
         l2.backward()
         opt.sync.reduce_group("camera")
         opt.sync.reduce_group("shared")

@@ -33,7 +33,7 @@ extern "C" {
 #define NVSF_E_WORKSPACE (-2) /* workspace too small */
 
 /* ABI version of this header; bumped on any signature change. */
-#define NVSF_B200_ABI_VERSION 10
+#define NVSF_B200_ABI_VERSION 11
 int nvsf_abi_version(void);
 /* Human-readable text for a status returned by any nvsf_* call. */
 const char* nvsf_status_string(int status);
@@ -402,6 +402,39 @@ int nvsf_grid_update(float* density_grid, const float* tmp_grid, uint32_t n, flo
 size_t nvsf_compact_alive_workspace_bytes(uint32_t n);
 int nvsf_compact_alive(const int32_t* rays_alive, uint32_t n, int32_t* out, int32_t* n_out,
                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* Part 5 — loss head on the composited outputs              */
+/* ------------------------------------------------------------------------- */
+
+/* element-wise criteria of main_nvsf.py:205-212 (all reduction="none") */
+#define NVSF_LOSS_L1 0       /* torch.nn.L1Loss */
+#define NVSF_LOSS_MSE 1      /* torch.nn.MSELoss */
+#define NVSF_LOSS_SMOOTHL1 2 /* torch.nn.SmoothL1Loss(beta = param; reference 0.1) */
+#define NVSF_LOSS_HUBER 3    /* torch.nn.HuberLoss(delta = param; reference 0.2 * scale) */
+
+typedef struct nvsf_lidar_loss_cfg {
+    float alpha_d, alpha_r, alpha_i; /* main_nvsf.py:93-95 (1, 0.01, 0.1) */
+    float smooth;                    /* --smooth_factor (main_nvsf.py:76, 0.0) */
+    int32_t depth_kind, raydrop_kind, intensity_kind; /* --depth_loss l1, --raydrop_loss mse, --intensity_loss mse */
+    float depth_param, raydrop_param, intensity_param; /* beta / delta of smoothl1 / huber */
+} nvsf_lidar_loss_cfg_t;
+
+/* replaces the LiDAR supervision of Trainer.train_step (trainer.py:184-216):
+ *   m = gt[:,0]; loss[i] = alpha_d * crit_d(depth*m, gt[:,2]*m) + alpha_r * crit_r(image[:,0],
+ *   clamp(m, smooth, 1-smooth)) + alpha_i * crit_i(image[:,1]*m, gt[:,1]*m)
+ * depth [n] = outputs["depth_lidar"], image [n,2] = outputs["image_lidar"] (raydrop, intensity),
+ * gt [n,3] = images_lidar (raydrop mask, intensity, depth).  loss [n] is the per-ray lidar_loss the
+ * trainer keeps for its error map; g_depth [n] / g_image [n,2] are d loss[i] / d depth[i], d image[i]
+ * (the backward of loss.sum()). */
+int nvsf_loss_lidar(const float* depth, const float* image, const float* gt, uint32_t n,
+                    const nvsf_lidar_loss_cfg_t* cfg, float* loss, float* g_depth, float* g_image,
+                    void* stream);
+
+/* replaces alpha * criterion(pred, gt) with reduction="none" (trainer.py:503-504 rgb_loss, :514-518
+ * rgb_depth_loss on pre-masked inputs): loss [n], g_pred [n] = d loss[i] / d pred[i]. */
+int nvsf_loss_elementwise(const float* pred, const float* gt, size_t n, int kind, float param,
+                          float alpha, float* loss, float* g_pred, void* stream);
 
 #ifdef __cplusplus
 }

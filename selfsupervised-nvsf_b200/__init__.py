@@ -10,6 +10,7 @@ Sub-modules
     rays          get_lidar_rays / get_rays (reference dataset_utils.py) generated on the device
     dist          ray sharding + flat-buffer gradient all-reduce (one process per GPU)
     optim         Adam over the flat parameter / gradient buffers (CUDA kernel)
+    losses        lidar_loss / rgb_loss of the reference's train_step, loss + derivative in one kernel
     _lib          ctypes binding of the C ABI (include/nvsf_b200.h)
     build         compiles csrc/*.cu into libnvsf_b200.so with nvcc (sm_100a)
 """
@@ -19,6 +20,7 @@ from . import field  # noqa: F401
 from . import rays  # noqa: F401
 from . import dist  # noqa: F401
 from . import optim  # noqa: F401
+from . import losses  # noqa: F401
 from .field import NeRFNetwork  # noqa: F401
 
 __version__ = "0.1.0"

@@ -92,6 +92,9 @@ PROTOTYPES = {
     "nvsf_grid_update": (_int, [_p, _p, _u32, _f32, _f32, _p, _p, _p, _sz, _p]),
     "nvsf_compact_alive_workspace_bytes": (_sz, [_u32]),
     "nvsf_compact_alive": (_int, [_p, _u32, _p, _p, _p, _sz, _p]),
+    # Part 5 — loss head
+    "nvsf_loss_lidar": (_int, [_p, _p, _p, _u32, _p, _p, _p, _p, _p]),
+    "nvsf_loss_elementwise": (_int, [_p, _p, _sz, _int, _f32, _f32, _p, _p, _p]),
 }
 
 _lib = None
@@ -124,7 +127,7 @@ def lib():
     return _lib
 
 
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 
 def check(status, what=""):

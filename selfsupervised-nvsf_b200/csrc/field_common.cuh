@@ -172,7 +172,7 @@ int nvsf_launch_flow_tc(const nvsf_field_config_t* cfg, const FieldPtrs& P, cons
 // gather stage fused with the sigma MLP (mode 2 intermediates: query positions + dyn rows)
 int nvsf_launch_encode_sigma_tc(const nvsf_field_config_t* cfg, const FieldPtrs& P, const float* qpos,
                                 const void* dyn_in, size_t stride, size_t count, float* sigma,
-                                __half* geo, int sms, cudaStream_t stream);
+                                __half* geo, int sms, cudaStream_t stream, int half_math);
 void nvsf_stage_timing_enable(int on);
 int nvsf_split_set_option(const char* name, int value);
 int nvsf_split_get_option(const char* name);
@@ -444,6 +444,51 @@ __device__ __forceinline__ void plane1d_mul_h(const __half* __restrict__ base, u
     }
 }
 
+// Packed-half arithmetic for the fused gather + sigma stage (k_encode_sigma_tc<true>): the feature row
+// is stored as fp16 in the UMMA operand tile anyway and tcnn itself interpolates its grids in half
+// precision (`fma((T)weight, val, result)` with T = __half), so the interpolation runs on HFMA2 —
+// one instruction per two channels and no fp16 -> fp32 conversions (22 % of the fp32 kernel's
+// instructions).  Weights are formed in fp32 and rounded once.
+__device__ __forceinline__ void ld8h2(const __half* p, __half2 (&v)[4]) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(p));
+    v[0] = *reinterpret_cast<const __half2*>(&a.x); v[1] = *reinterpret_cast<const __half2*>(&a.y);
+    v[2] = *reinterpret_cast<const __half2*>(&a.z); v[3] = *reinterpret_cast<const __half2*>(&a.w);
+}
+__device__ __forceinline__ void plane2d_mul_h2(const __half* __restrict__ base, uint32_t R, float pa,
+                                               float pb, __half2 (&out)[4], bool first) {
+    uint32_t x0, x1, y0, y1;
+    float wx, wy;
+    plane_coord(pa, R, x0, x1, wx);
+    plane_coord(pb, R, y0, y1, wy);
+    __half2 a[4], b[4], c[4], d[4];
+    ld8h2(base + ((size_t)y0 * R + x0) * 8, a);
+    ld8h2(base + ((size_t)y0 * R + x1) * 8, b);
+    ld8h2(base + ((size_t)y1 * R + x0) * 8, c);
+    ld8h2(base + ((size_t)y1 * R + x1) * 8, d);
+    const __half2 w00 = __float2half2_rn((1.f - wx) * (1.f - wy)), w01 = __float2half2_rn(wx * (1.f - wy)),
+                  w10 = __float2half2_rn((1.f - wx) * wy), w11 = __float2half2_rn(wx * wy);
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+        const __half2 s = __hfma2(w11, d[f], __hfma2(w10, c[f], __hfma2(w01, b[f], __hmul2(w00, a[f]))));
+        out[f] = first ? s : __hmul2(out[f], s);
+    }
+}
+__device__ __forceinline__ void plane1d_mul_h2(const __half* __restrict__ base, uint32_t R, float pa,
+                                               __half2 (&out)[4], bool first) {
+    uint32_t x0, x1;
+    float wx;
+    plane_coord(pa, R, x0, x1, wx);
+    __half2 a[4], b[4];
+    ld8h2(base + (size_t)x0 * 8, a);
+    ld8h2(base + (size_t)x1 * 8, b);
+    const __half2 w0 = __float2half2_rn(1.f - wx), w1 = __float2half2_rn(wx);
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+        const __half2 s = __hfma2(w1, b[f], __hmul2(w0, a[f]));
+        out[f] = first ? s : __hmul2(out[f], s);
+    }
+}
+
 // Paired variant of hash3_f4 for hashed levels: the hash multiplies x by 1, so for even cx the two
 // x-corners of a cell edge are the entries i0 and i0 ^ 1 — one aligned 16-byte load fetches both;
 // odd cx needs a second, predicated 8-byte load (half of the lanes on a fine level).  Per edge the
@@ -510,6 +555,29 @@ __device__ __forceinline__ void hash3_f4(const uint2* __restrict__ tab, const Le
         a2 = fmaf(w, hi.x, a2); a3 = fmaf(w, hi.y, a3);
     }
     out[0] = a0; out[1] = a1; out[2] = a2; out[3] = a3;
+}
+
+// same level in packed-half arithmetic (see plane2d_mul_h2): out = 2 x half2
+__device__ __forceinline__ void hash3_f4_h2(const uint2* __restrict__ tab, const LevelArgs& L,
+                                            float x, float y, float z, __half2* out) {
+    uint32_t cx, cy, cz;
+    float wx, wy, wz;
+    grid_pos(L.scale, x, cx, wx);
+    grid_pos(L.scale, y, cy, wy);
+    grid_pos(L.scale, z, cz, wz);
+    uint2 v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        v[c] = __ldg(tab + L.offset + idx3(L, cx + (c & 1), cy + ((c >> 1) & 1), cz + (c >> 2)));
+    __half2 a0 = __float2half2_rn(0.f), a1 = a0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const __half2 w = __float2half2_rn(((c & 1) ? wx : 1.f - wx) * ((c & 2) ? wy : 1.f - wy) *
+                                           ((c & 4) ? wz : 1.f - wz));
+        a0 = __hfma2(w, *reinterpret_cast<const __half2*>(&v[c].x), a0);
+        a1 = __hfma2(w, *reinterpret_cast<const __half2*>(&v[c].y), a1);
+    }
+    out[0] = a0; out[1] = a1;
 }
 
 // one level of a time-collapsed 2-D dynamic hash grid (1 value)

@@ -635,6 +635,9 @@ int ensure_attrs() {
     return NVSF_OK;
 }
 
+int g_half_math = 0;   // option "half_math": packed-half interpolation in the fused gather + sigma stage
+                       // (k_encode_sigma_tc<true>): 27 % fewer instructions, measured 12.53 -> 12.67 ms —
+                       // the stage is bound by the L1 data pipe, not by issue slots; kept for A/B runs
 int g_flow_tc = 1;     // mode 2: flow stage on tcgen05 (sigma_tc.cu k_flow_tc, option "flow_tc")
 int g_fuse_sigma = 1;  // mode 2: gather stage fused with the sigma MLP on tcgen05 (option "fuse_sigma")
 int g_sigma_tc = 1;  // sigma stage on tcgen05 / TMEM (sigma_tc.cu) instead of mma.sync (option "sigma_tc"):
@@ -769,7 +772,7 @@ int nvsf_launch_density_split(const nvsf_field_config_t* cfg, const void* worksp
         }
         if (fused) {  // gather stage + sigma MLP in one tcgen05 kernel: the feature rows stay on the SM
             st = nvsf_launch_encode_sigma_tc(cfg, P, qpos_buf, dyn_buf, count, count, sigma + begin,
-                                             reinterpret_cast<__half*>(geo) + begin * kGeo, sms, stream);
+                                             reinterpret_cast<__half*>(geo) + begin * kGeo, sms, stream, g_half_math);
             if (st != NVSF_OK) return st;
         }
         if (g_prof.on) g_prof.next(stream);
@@ -814,6 +817,11 @@ int nvsf_split_set_option(const char* name, int value) {
         g_flow_tc = value;
         return NVSF_OK;
     }
+    if (k == "half_math") {
+        if (value != 0 && value != 1) return NVSF_E_INVALID;
+        g_half_math = value;
+        return NVSF_OK;
+    }
     if (k == "fuse_sigma") {
         if (value != 0 && value != 1) return NVSF_E_INVALID;
         g_fuse_sigma = value;
@@ -846,6 +854,7 @@ int nvsf_split_get_option(const char* name) {
     if (k == "sigma_tc") return g_sigma_tc;
     if (k == "fuse_sigma") return g_fuse_sigma;
     if (k == "flow_tc") return g_flow_tc;
+    if (k == "half_math") return g_half_math;
     return nvsf_train_get_option(name);
 }
 

@@ -198,6 +198,7 @@ constexpr uint32_t kFOffBar = kFOffX + kFusedWG * kFTile;
 constexpr size_t kFusedSmem = kFOffBar + 8 * kFusedWG + 16 + 1024;
 static_assert(kFOffX % 1024 == 0, "swizzled tiles start on 1024-byte boundaries");
 
+template <bool H2>
 __global__ void __launch_bounds__(kFusedThreads, 1)
 k_encode_sigma_tc(const __grid_constant__ nvsf_field_config_t cfg,
                   const __grid_constant__ FieldPtrs P, const float* __restrict__ qpos,
@@ -249,6 +250,36 @@ k_encode_sigma_tc(const __grid_constant__ nvsf_field_config_t cfg,
             qz[q] = __ldg(qpos + (size_t)(3 * q + 2) * stride + lc);
         }
         // ---- half 0: planes --------------------------------------------------------------------
+        if (H2) {
+#pragma unroll 1
+            for (int s = 0; s < kPlScales; ++s) {
+                const uint32_t R = cfg.pl_res[s];
+                const __half* b0 = P.pls16 + P.pls_scale[s];
+                __half2 v[4];
+                plane2d_mul_h2(b0, R, qx[0], qy[0], v, true);
+                plane2d_mul_h2(b0 + (size_t)R * R * 8, R, qx[0], qz[0], v, false);
+                plane2d_mul_h2(b0 + (size_t)2 * R * R * 8, R, qy[0], qz[0], v, false);
+                *reinterpret_cast<uint4*>(xg + swz(t, s)) = *reinterpret_cast<const uint4*>(v);
+            }
+#pragma unroll 1
+            for (int s = 0; s < kPlScales; ++s) {
+                const uint32_t R = cfg.pl_res[s];
+                __half2 acc[4];
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    const int qq = q == 0 ? 0 : (q == 1 ? qi1 : qi2);
+                    const __half* b0 = P.pld16 + (size_t)qq * P.pld_per_q + P.pld_scale[s];
+                    __half2 v[4];
+                    plane1d_mul_h2(b0, R, qx[q], v, true);
+                    plane1d_mul_h2(b0 + (size_t)R * 8, R, qy[q], v, false);
+                    plane1d_mul_h2(b0 + (size_t)2 * R * 8, R, qz[q], v, false);
+                    const __half2 wq = __float2half2_rn(q == 0 ? 0.5f : 0.25f);
+#pragma unroll
+                    for (int f = 0; f < 4; ++f) acc[f] = q == 0 ? __hmul2(wq, v[f]) : __hfma2(wq, v[f], acc[f]);
+                }
+                *reinterpret_cast<uint4*>(xg + swz(t, 4 + s)) = *reinterpret_cast<const uint4*>(acc);
+            }
+        } else {
 #pragma unroll 1
         for (int s = 0; s < kPlScales; ++s) {
             const uint32_t R = cfg.pl_res[s];
@@ -277,6 +308,7 @@ k_encode_sigma_tc(const __grid_constant__ nvsf_field_config_t cfg,
             }
             st_chunk(xg, t, 4 + s, acc8);
         }
+        }
         fence_async_smem();
         tc_fence_before();
         wg_barrier(wg);
@@ -291,13 +323,20 @@ k_encode_sigma_tc(const __grid_constant__ nvsf_field_config_t cfg,
 #pragma unroll 1
         for (int l = 0; l < kHsLevels; l += 2) {
             float v[8];
-            hash3_f4(P.hs16, lv(cfg.hs[l]), qx[0], qy[0], qz[0], v);
-            hash3_f4(P.hs16, lv(cfg.hs[l + 1]), qx[0], qy[0], qz[0], v + 4);
+            __half2 vh[4];
+            if (H2) {
+                hash3_f4_h2(P.hs16, lv(cfg.hs[l]), qx[0], qy[0], qz[0], vh);
+                hash3_f4_h2(P.hs16, lv(cfg.hs[l + 1]), qx[0], qy[0], qz[0], vh + 2);
+            } else {
+                hash3_f4(P.hs16, lv(cfg.hs[l]), qx[0], qy[0], qz[0], v);
+                hash3_f4(P.hs16, lv(cfg.hs[l + 1]), qx[0], qy[0], qz[0], v + 4);
+            }
             if (l == 0) {  // the first-half MMAs must have read the tile before it is refilled
                 mbar_wait(bar, phase);
                 phase ^= 1u;
             }
-            st_chunk(xg, t, l >> 1, v);
+            if (H2) *reinterpret_cast<uint4*>(xg + swz(t, l >> 1)) = *reinterpret_cast<const uint4*>(vh);
+            else st_chunk(xg, t, l >> 1, v);
         }
 #pragma unroll
         for (int p = 0; p < 3; ++p) {
@@ -560,17 +599,24 @@ int nvsf_launch_sigma_tc(const void* wimg, const __half* feat, size_t count, flo
 
 int nvsf_launch_encode_sigma_tc(const nvsf_field_config_t* cfg, const FieldPtrs& P, const float* qpos,
                                 const void* dyn_in, size_t stride, size_t count, float* sigma,
-                                __half* geo, int sms, cudaStream_t stream) {
+                                __half* geo, int sms, cudaStream_t stream, int half_math) {
     if (!g_fused_attr) {
-        cudaError_t e = cudaFuncSetAttribute(k_encode_sigma_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(k_encode_sigma_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)kFusedSmem);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaFuncSetAttribute(k_encode_sigma_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)kFusedSmem);
         if (e != cudaSuccess) return (int)e;
         g_fused_attr = true;
     }
     const size_t tiles = (count + kRows - 1) / kRows;
     const int grid = (int)std::min<size_t>((tiles + kFusedWG - 1) / kFusedWG, (size_t)sms);
-    k_encode_sigma_tc<<<grid, kFusedThreads, kFusedSmem, stream>>>(
-        *cfg, P, qpos, reinterpret_cast<const unsigned short*>(dyn_in), stride, count, sigma, geo);
+    if (half_math)
+        k_encode_sigma_tc<true><<<grid, kFusedThreads, kFusedSmem, stream>>>(
+            *cfg, P, qpos, reinterpret_cast<const unsigned short*>(dyn_in), stride, count, sigma, geo);
+    else
+        k_encode_sigma_tc<false><<<grid, kFusedThreads, kFusedSmem, stream>>>(
+            *cfg, P, qpos, reinterpret_cast<const unsigned short*>(dyn_in), stride, count, sigma, geo);
     return NVSF_OK;
 }
 

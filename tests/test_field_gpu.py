@@ -350,3 +350,34 @@ def test_composite_heads_tcgen05_matches_mma_sync(pkg, model, lidar, steps):
     for a, b, name in zip(out[1], out[0], ("depth", "image", "weights_sum", "weights")):
         close(a, b, 1e-4 if name != "image" else 2e-3, 1e-6 if name != "image" else 2e-3 * np.abs(b).max(),
               f"heads tcgen05 vs mma.sync {name} (S={steps})")
+
+
+@pytest.mark.parametrize("t", [0.45, 1.0])
+def test_fused_stage_packed_half_interpolation(pkg, model, orc, t):
+    """k_encode_sigma_tc<true> (option half_math, off by default): plane / static-hash interpolation on HFMA2
+    (tcnn interpolates its grids in half precision too) against the same kernel with fp32
+    interpolation, and against the CPU oracle at the north star's tolerance for MLP outputs (1e-2)."""
+    L = pkg._lib.lib()
+    x = pts(50001, 37)
+    xd = torch.from_numpy(x).cuda()
+    o, d = S.lidar_rays(400, seed=14)
+    to, td = torch.from_numpy(o).cuda()[None], torch.from_numpy(d).cuda()[None]
+    out = {}
+    try:
+        for hm in (0, 1):
+            assert L.nvsf_set_option(b"half_math", hm) == 0
+            den = model.density(xd, t, True)
+            with torch.no_grad():
+                r = model.render(to, td, torch.tensor([[t]], device="cuda"), cal_lidar_color=True, num_steps=256)
+            torch.cuda.synchronize()
+            out[hm] = (host(den["sigma"]), host(den["geo_feat"]), host(r["depth_lidar"]), host(r["image_lidar"]))
+    finally:
+        L.nvsf_set_option(b"half_math", 0)
+    gmax = np.abs(out[0][1]).max()
+    close(out[1][0], out[0][0], 5e-3, 0, "sigma half vs fp32 interpolation")
+    close(out[1][1], out[0][1], 5e-3, 5e-3 * gmax, "geo half vs fp32 interpolation")
+    close(out[1][2], out[0][2], 2e-3, 0, "depth half vs fp32 interpolation")
+    close(out[1][3], out[0][3], 2e-3, 2e-3 * np.abs(out[0][3]).max(), "image half vs fp32 interpolation")
+    with torch.no_grad():
+        ref = orc.density(torch.from_numpy(x[:4096]), t, True)
+    close(out[1][0][:4096], ref["sigma"].numpy(), 1e-2, 0, "sigma (half interpolation) vs oracle")
