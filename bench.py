@@ -213,7 +213,7 @@ def bench_train(pkg, S, cfg_kw, dev, rank, world, rays, steps, warmup):
         c, d = co_h.to(dev, non_blocking=True), cd_h.to(dev, non_blocking=True)
         opt.zero_grad()
         ol = model.render(a[None], b[None], t, cal_lidar_color=True, staged=False, num_steps=NUM_STEPS, perturb=True)
-        # loss head of trainer.py:184-216 / 503-504 (csrc/loss.cu: loss and its derivative in one kernel)
+        # loss head of trainer.py:188-219 / 503-504 (csrc/loss.cu: loss and its derivative in one kernel)
         l1 = pkg.losses.lidar_loss(ol["depth_lidar"], ol["image_lidar"], gt_l).sum()
         l1.backward()
         opt.sync.reduce_group("lidar")      # overlaps the camera render

@@ -420,7 +420,7 @@ typedef struct nvsf_lidar_loss_cfg {
     float depth_param, raydrop_param, intensity_param; /* beta / delta of smoothl1 / huber */
 } nvsf_lidar_loss_cfg_t;
 
-/* replaces the LiDAR supervision of Trainer.train_step (trainer.py:184-216):
+/* replaces the LiDAR supervision of Trainer.train_step (trainer.py:188-219):
  *   m = gt[:,0]; loss[i] = alpha_d * crit_d(depth*m, gt[:,2]*m) + alpha_r * crit_r(image[:,0],
  *   clamp(m, smooth, 1-smooth)) + alpha_i * crit_i(image[:,1]*m, gt[:,1]*m)
  * depth [n] = outputs["depth_lidar"], image [n,2] = outputs["image_lidar"] (raydrop, intensity),
@@ -431,10 +431,25 @@ int nvsf_loss_lidar(const float* depth, const float* image, const float* gt, uin
                     const nvsf_lidar_loss_cfg_t* cfg, float* loss, float* g_depth, float* g_image,
                     void* stream);
 
-/* replaces alpha * criterion(pred, gt) with reduction="none" (trainer.py:503-504 rgb_loss, :514-518
+/* replaces alpha * criterion(pred, gt) with reduction="none" (trainer.py:503 rgb_loss, :514-518
  * rgb_depth_loss on pre-masked inputs): loss [n], g_pred [n] = d loss[i] / d pred[i]. */
 int nvsf_loss_elementwise(const float* pred, const float* gt, size_t n, int kind, float param,
                           float alpha, float* loss, float* g_pred, void* stream);
+
+/* replaces the reference's Chamfer extension (nvsf/nerf/chamfer3D/chamfer3D.cu; pybind
+ * chamfer_cuda.cpp `forward` / `backward`; wrapper dist_chamfer_3D.py:42-95), called by train_step
+ * on predicted vs ground-truth LiDAR points (trainer.py:229-233) and on flow-warped clouds
+ * (:246-265).  xyz1 [b,n,3], xyz2 [b,m,3]; dist1 [b,n] / idx1 [b,n] = squared distance to and index
+ * of the nearest point of xyz2 (first minimum, bit-identical to the reference kernel), dist2 / idx2
+ * the other direction.  Backward ACCUMULATES into grad_xyz1 / grad_xyz2 (the reference wrapper
+ * zero-fills them, dist_chamfer_3D.py:76-80); either may be NULL. */
+size_t nvsf_chamfer_workspace_bytes(uint32_t b, uint32_t n, uint32_t m);
+int nvsf_chamfer_forward(const float* xyz1, const float* xyz2, uint32_t b, uint32_t n, uint32_t m,
+                         float* dist1, float* dist2, int32_t* idx1, int32_t* idx2, void* workspace,
+                         size_t workspace_bytes, void* stream);
+int nvsf_chamfer_backward(const float* xyz1, const float* xyz2, uint32_t b, uint32_t n, uint32_t m,
+                          const float* grad_dist1, const float* grad_dist2, const int32_t* idx1,
+                          const int32_t* idx2, float* grad_xyz1, float* grad_xyz2, void* stream);
 
 #ifdef __cplusplus
 }

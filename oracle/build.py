@@ -1,5 +1,5 @@
 """TEST INFRASTRUCTURE.  Builds the C oracle (gcc) and, when /root/reference is
-present (build container only), the reference extension via build_ref.sh."""
+present (build container only), the reference extensions via build_ref.sh / build_ref_chamfer.sh."""
 import os
 import subprocess
 import sys
@@ -31,11 +31,14 @@ def build_oracle(force=False):
 
 def build_ref():
     """Compile the unmodified reference extension for sm_100a (no-op off the build box)."""
-    r = subprocess.run(["bash", os.path.join(HERE, "build_ref.sh")], capture_output=True, text=True)
-    if r.returncode != 0:
-        sys.stderr.write(r.stdout + r.stderr)
-        raise RuntimeError("oracle/build_ref.sh failed")
-    return r.stdout.strip()
+    out = []
+    for script in ("build_ref.sh", "build_ref_chamfer.sh"):
+        r = subprocess.run(["bash", os.path.join(HERE, script)], capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError(f"oracle/{script} failed")
+        out.append(r.stdout.strip())
+    return "\n".join(out)
 
 
 if __name__ == "__main__":

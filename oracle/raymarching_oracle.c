@@ -454,3 +454,54 @@ ORACLE_API void oracle_composite_rays(uint32_t n_alive, uint32_t n_step, float T
         image[index * 3 + 2] = b;
     }
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Chamfer distance — restatement of nvsf/nerf/chamfer3D/chamfer3D.cu (TEST INFRASTRUCTURE).
+ *
+ * NmDistanceKernel (:9-150): for every point j of cloud A the squared distance to, and the index
+ * of, its nearest point in cloud B; targets are scanned in ascending k with a strict `<` inside a
+ * 512-point block (:43,:123) and a strict `>` across blocks (:129), i.e. the FIRST minimum wins.
+ * The distance is d = x2*x2 + y2*y2 + z2*z2 with x2 = b_k - a_j (:38-42), which the reference
+ * build contracts to FFMA(z2, z2, FFMA(y2, y2, FMUL(x2, x2))) (sm_100a SASS of the unmodified
+ * kernel, oracle/_ref/chamfer_3D_ref.so) — spelled out with fmaf() here.
+ * NmDistanceGradKernel (:151-178): g = 2 grad_dist[j]; grad_a[j] += g (a_j - b_idx),
+ * grad_b[idx] -= g (a_j - b_idx); chamfer_cuda_backward (:183-230) runs it in both directions.
+ * ---------------------------------------------------------------------------------------------- */
+ORACLE_API void oracle_chamfer_nn(const float* a, uint32_t n, const float* b, uint32_t m,
+                                  uint32_t batch, float* dist, int32_t* idx) {
+    for (uint32_t i = 0; i < batch; ++i) {
+#pragma omp parallel for schedule(static)
+        for (int64_t j = 0; j < (int64_t)n; ++j) {
+            const float* p = a + ((size_t)i * n + j) * 3;
+            float best = 0.f;
+            int32_t best_i = 0;
+            for (uint32_t k = 0; k < m; ++k) {
+                const float* q = b + ((size_t)i * m + k) * 3;
+                const float x2 = q[0] - p[0], y2 = q[1] - p[1], z2 = q[2] - p[2];
+                const float d = fmaf(z2, z2, fmaf(y2, y2, x2 * x2));
+                if (k == 0 || d < best) {
+                    best = d;
+                    best_i = (int32_t)k;
+                }
+            }
+            dist[(size_t)i * n + j] = best;
+            idx[(size_t)i * n + j] = best_i;
+        }
+    }
+}
+
+ORACLE_API void oracle_chamfer_grad(const float* a, uint32_t n, const float* b, uint32_t m,
+                                    uint32_t batch, const float* grad_dist, const int32_t* idx,
+                                    float* grad_a, float* grad_b) {
+    for (uint32_t i = 0; i < batch; ++i) {
+        for (uint32_t j = 0; j < n; ++j) {
+            const size_t ja = (size_t)i * n + j, jb = (size_t)i * m + (uint32_t)idx[ja];
+            const float g = grad_dist[ja] * 2.f;
+            for (int c = 0; c < 3; ++c) {
+                const float v = g * (a[ja * 3 + c] - b[jb * 3 + c]);
+                grad_a[ja * 3 + c] += v;
+                grad_b[jb * 3 + c] += -v;
+            }
+        }
+    }
+}

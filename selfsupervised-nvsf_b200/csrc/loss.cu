@@ -1,8 +1,8 @@
 // nvsf_b200 — loss head on the composited outputs (sm_100a).
 //
-// Replaces the per-ray supervision of Trainer.train_step (reference nvsf/nerf/trainer.py:184-216:
+// Replaces the per-ray supervision of Trainer.train_step (reference nvsf/nerf/trainer.py:188-219:
 // raydrop mask, label smoothing, depth / raydrop / intensity criteria weighted by alpha_d / alpha_r /
-// alpha_i; :503-504: alpha_rgb * criterion["rgb"](pred_rgb, gt_rgb)) with the element-wise criteria
+// alpha_i; :503: alpha_rgb * criterion["rgb"](pred_rgb, gt_rgb)) with the element-wise criteria
 // of main_nvsf.py:205-212 (reduction="none"): one streaming kernel writes the per-ray (per-element)
 // loss the trainer keeps for its error map AND the derivative of that loss with respect to the
 // renderer's outputs, so the backward pass of the renderer starts from these buffers without the
@@ -38,19 +38,19 @@ k_loss_lidar(const float* __restrict__ depth, const float* __restrict__ image,
              float* __restrict__ loss, float* __restrict__ g_depth, float* __restrict__ g_image) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float m = __ldg(gt + 3 * (size_t)i);               // gt_raydrop (trainer.py:184)
-    const float gi = __ldg(gt + 3 * (size_t)i + 1) * m;      // gt_intensity (:185)
-    const float gd = __ldg(gt + 3 * (size_t)i + 2) * m;      // gt_depth (:186)
+    const float m = __ldg(gt + 3 * (size_t)i);               // gt_raydrop (trainer.py:188)
+    const float gi = __ldg(gt + 3 * (size_t)i + 1) * m;      // gt_intensity (:189)
+    const float gd = __ldg(gt + 3 * (size_t)i + 2) * m;      // gt_depth (:190)
     const float2 im = __ldg(reinterpret_cast<const float2*>(image) + i);
-    const float pr = im.x;                                   // pred_raydrop (:200)
-    const float pi = im.y * m;                               // pred_intensity (:202)
-    const float pd = __ldg(depth + i) * m;                   // pred_depth (:203)
-    const float gs = fminf(fmaxf(m, c.smooth), 1.f - c.smooth);  // clamp(smooth, 1 - smooth) (:209-210)
+    const float pr = im.x;                                   // pred_raydrop (:206)
+    const float pi = im.y * m;                               // pred_intensity (:205)
+    const float pd = __ldg(depth + i) * m;                   // pred_depth (:206)
+    const float gs = fminf(fmaxf(m, c.smooth), 1.f - c.smooth);  // clamp(smooth, 1 - smooth) (:211-213)
     float ld, gdd, lr, gr, li, gii;
     crit(c.depth_kind, c.depth_param, pd, gd, ld, gdd);
     crit(c.raydrop_kind, c.raydrop_param, pr, gs, lr, gr);
     crit(c.intensity_kind, c.intensity_param, pi, gi, li, gii);
-    loss[i] = (c.alpha_d * ld + c.alpha_r * lr) + c.alpha_i * li;   // lidar_loss (:213-216)
+    loss[i] = (c.alpha_d * ld + c.alpha_r * lr) + c.alpha_i * li;   // lidar_loss (:216-219)
     g_depth[i] = c.alpha_d * gdd * m;
     reinterpret_cast<float2*>(g_image)[i] = make_float2(c.alpha_r * gr, c.alpha_i * gii * m);
 }

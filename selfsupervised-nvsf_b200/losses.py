@@ -1,9 +1,9 @@
 """Loss head on the composited outputs — host-side mirror of the supervision terms of the reference's
-`Trainer.train_step` (nvsf/nerf/trainer.py:184-216 LiDAR, :503-504 camera) with the element-wise
+`Trainer.train_step` (nvsf/nerf/trainer.py:188-219 LiDAR, :503 camera) with the element-wise
 criteria of `main_nvsf.py:205-212`.  Same argument meaning as the reference options (`--alpha_d`,
 `--alpha_r`, `--alpha_i`, `--alpha_rgb`, `--smooth_factor`, `--depth_loss`, `--raydrop_loss`,
 `--intensity_loss`, `--rgb_loss`); the results are the un-reduced tensors the trainer sums
-(`helper_loss(lidar_loss)`, trainer.py:540-543) and keeps for its error map (:556-570).
+(`helper_loss(lidar_loss)`, trainer.py:545-547) and keeps for its error map (:551-560).
 
 One CUDA kernel (csrc/loss.cu) computes the loss and its derivative with respect to the renderer's
 outputs; `backward` only scales those buffers by the incoming gradient.  No CPU / PyTorch fallback:
@@ -64,7 +64,7 @@ class _LidarLoss(torch.autograd.Function):
 
 def lidar_loss(depth_lidar, image_lidar, images_lidar, alpha_d=1.0, alpha_r=0.01, alpha_i=0.1, smooth_factor=0.0,
                depth_loss="l1", raydrop_loss="mse", intensity_loss="mse", scale=1.0):
-    """`lidar_loss` [B, N] of trainer.py:184-216 from `outputs_lidar["depth_lidar"]` [B, N],
+    """`lidar_loss` [B, N] of trainer.py:188-219 from `outputs_lidar["depth_lidar"]` [B, N],
     `outputs_lidar["image_lidar"]` [B, N, 2] (raydrop, intensity) and the ground truth `images_lidar`
     [B, N, 3] (raydrop mask, intensity, depth)."""
     cfg = LidarLossCfg()
@@ -97,6 +97,6 @@ class _ElemLoss(torch.autograd.Function):
 
 
 def rgb_loss(pred_rgb, gt_rgb, alpha_rgb=1.0, rgb_loss="mse", scale=1.0):
-    """`alpha_rgb * criterion["rgb"](pred_rgb, gt_rgb)` [B, N, 3] of trainer.py:503-504."""
+    """`alpha_rgb * criterion["rgb"](pred_rgb, gt_rgb)` [B, N, 3] of trainer.py:503."""
     kind, param = _kind(rgb_loss, scale)
     return _ElemLoss.apply(pred_rgb, gt_rgb, kind, float(param), float(alpha_rgb))

@@ -1,5 +1,5 @@
 """CPU: the loss oracle (oracle/loss_oracle.py) against hand-evaluated cases of the reference's
-train_step supervision (trainer.py:184-216, 503-504) and its autograd against closed forms."""
+train_step supervision (trainer.py:188-219, 503-504) and its autograd against closed forms."""
 import numpy as np
 import pytest
 

@@ -1,0 +1,63 @@
+"""Forward + backward timing of chamfer_3DDist (csrc/chamfer.cu) against the reference's own
+extension (oracle/_ref/chamfer_3D_ref.so, unmodified chamfer3D.cu built for sm_100a) at the
+trainer's batch (4096 points, BASELINE configs[2]) and at 64 K points (configs[4])."""
+import importlib
+import importlib.util
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+pkg = importlib.import_module("selfsupervised-nvsf_b200")
+
+
+def timed(fn, iters):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+ref = None
+so = os.path.join(ROOT, "oracle", "_ref", "chamfer_3D_ref.so")
+if os.path.exists(so):
+    spec = importlib.util.spec_from_file_location("chamfer_3D_ref", so)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+ch = pkg.chamfer.chamfer_3DDist()
+for n in (4096, 65536):
+    g = torch.Generator(device="cuda").manual_seed(n)
+    a = torch.rand(1, n, 3, device="cuda", generator=g).requires_grad_(True)
+    b = torch.rand(1, n, 3, device="cuda", generator=g)
+
+    def ours():
+        d1, d2, _, _ = ch(a, b)
+        ((d1 + d2).mean() * 0.5).backward()      # trainer.py:232-233
+        a.grad = None
+
+    row = {"points": n, "pairs_per_call": 2 * n * n, "ours_fwd_bwd_ms": timed(ours, 10)}
+    row["ours_gpairs_per_s"] = 2 * n * n / (row["ours_fwd_bwd_ms"] * 1e-3) / 1e9
+    if ref is not None:
+        d1, d2 = torch.zeros(1, n).cuda(), torch.zeros(1, n).cuda()
+        i1, i2 = torch.zeros(1, n, dtype=torch.int32).cuda(), torch.zeros(1, n, dtype=torch.int32).cuda()
+        ga, gb = torch.zeros(1, n, 3).cuda(), torch.zeros(1, n, 3).cuda()
+        g1 = torch.full((1, n), 0.5 / n).cuda()
+        ad = a.detach()
+
+        def theirs():   # kernels launch on the legacy default stream (chamfer3D.cu:161-166)
+            ref.forward(ad, b, d1, d2, i1, i2)
+            ref.backward(ad, b, ga, gb, g1, g1, i1, i2)
+            torch.cuda.synchronize()
+
+        row["reference_ext_fwd_bwd_ms"] = timed(theirs, 5)
+        row["speedup"] = row["reference_ext_fwd_bwd_ms"] / row["ours_fwd_bwd_ms"]
+    print(json.dumps(row))
