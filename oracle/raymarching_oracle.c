@@ -462,8 +462,9 @@ ORACLE_API void oracle_composite_rays(uint32_t n_alive, uint32_t n_step, float T
  * of, its nearest point in cloud B; targets are scanned in ascending k with a strict `<` inside a
  * 512-point block (:43,:123) and a strict `>` across blocks (:129), i.e. the FIRST minimum wins.
  * The distance is d = x2*x2 + y2*y2 + z2*z2 with x2 = b_k - a_j (:38-42), which the reference
- * build contracts to FFMA(z2, z2, FFMA(y2, y2, FMUL(x2, x2))) (sm_100a SASS of the unmodified
- * kernel, oracle/_ref/chamfer_3D_ref.so) — spelled out with fmaf() here.
+ * build contracts to FFMA(z2, z2, FFMA(x2, x2, FMUL(y2, y2))) (sm_100a SASS of the unmodified
+ * kernel, oracle/_ref/chamfer_3D_ref.so: the y term is the plain product; confirmed against the
+ * extension's outputs, tests/golden/chamfer_ref_sm100a.npz) — spelled out with fmaf() here.
  * NmDistanceGradKernel (:151-178): g = 2 grad_dist[j]; grad_a[j] += g (a_j - b_idx),
  * grad_b[idx] -= g (a_j - b_idx); chamfer_cuda_backward (:183-230) runs it in both directions.
  * ---------------------------------------------------------------------------------------------- */
@@ -478,7 +479,7 @@ ORACLE_API void oracle_chamfer_nn(const float* a, uint32_t n, const float* b, ui
             for (uint32_t k = 0; k < m; ++k) {
                 const float* q = b + ((size_t)i * m + k) * 3;
                 const float x2 = q[0] - p[0], y2 = q[1] - p[1], z2 = q[2] - p[2];
-                const float d = fmaf(z2, z2, fmaf(y2, y2, x2 * x2));
+                const float d = fmaf(z2, z2, fmaf(x2, x2, y2 * y2));
                 if (k == 0 || d < best) {
                     best = d;
                     best_i = (int32_t)k;

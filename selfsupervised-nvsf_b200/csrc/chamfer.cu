@@ -4,7 +4,7 @@
 // NmDistanceKernel, :151-195 NmDistanceGradKernel; wrapper dist_chamfer_3D.py:42-95), which
 // train_step calls on the predicted vs ground-truth LiDAR points (trainer.py:229-233) and on the
 // flow-warped point clouds (:246-265).  Same results: dist[j] = min_k |p_j - q_k|^2 evaluated as
-// the reference build evaluates it (x*x + y*y + z*z contracted to two FMAs), idx[j] = the first k
+// the reference build evaluates it (x*x + y*y + z*z contracted to FMUL(y) + two FMAs), idx[j] = the first k
 // that attains it (the reference scans k ascending with a strict `<`).
 //
 // The reference launches a fixed 32 x 16 grid of 512-thread CTAs in which blockIdx.x walks the
@@ -52,11 +52,12 @@ k_chamfer_nn(const float* __restrict__ xyz, uint32_t n, const float* __restrict_
         for (uint32_t k = 0; k < cnt; ++k) {
             const float tx = sx[k], ty = sy[k], tz = sz[k];
             // chamfer3D.cu:38-42: d = x2*x2 + y2*y2 + z2*z2 with x2 = buf - x1; nvcc contracts it to
-            // fma(z2, z2, fma(y2, y2, x2*x2)) (sm_100a SASS of the reference kernel: FMUL, FFMA, FFMA)
+            // fma(z2, z2, fma(x2, x2, y2*y2)) (sm_100a SASS of the reference kernel: FMUL on the y term,
+            // then FFMA x, FFMA z; confirmed bit for bit against the extension's outputs)
             const float ax = tx - x0, ay = ty - y0, az = tz - z0;
-            const float d0 = __fmaf_rn(az, az, __fmaf_rn(ay, ay, __fmul_rn(ax, ax)));
+            const float d0 = __fmaf_rn(az, az, __fmaf_rn(ax, ax, __fmul_rn(ay, ay)));
             const float bx = tx - x1, by = ty - y1, bz = tz - z1;
-            const float d1 = __fmaf_rn(bz, bz, __fmaf_rn(by, by, __fmul_rn(bx, bx)));
+            const float d1 = __fmaf_rn(bz, bz, __fmaf_rn(bx, bx, __fmul_rn(by, by)));
             if (d0 < best0) { best0 = d0; bi0 = k2 + k; }
             if (d1 < best1) { best1 = d1; bi1 = k2 + k; }
         }
@@ -68,13 +69,17 @@ k_chamfer_nn(const float* __restrict__ xyz, uint32_t n, const float* __restrict_
     }
 }
 
-__global__ void k_chamfer_unpack(const unsigned long long* __restrict__ keys, size_t count,
-                                 float* __restrict__ dist, int32_t* __restrict__ idx) {
+// keys [c1 | c2] -> (dist1, idx1) and (dist2, idx2) in one launch
+__global__ void k_chamfer_unpack(const unsigned long long* __restrict__ keys, size_t c1, size_t c2,
+                                 float* __restrict__ dist1, int32_t* __restrict__ idx1,
+                                 float* __restrict__ dist2, int32_t* __restrict__ idx2) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count) return;
+    if (i >= c1 + c2) return;
     const unsigned long long k = keys[i];
-    dist[i] = __uint_as_float((uint32_t)(k >> 32));
-    idx[i] = (int32_t)(uint32_t)k;
+    const float d = __uint_as_float((uint32_t)(k >> 32));
+    const int32_t id = (int32_t)(uint32_t)k;
+    if (i < c1) { dist1[i] = d; idx1[i] = id; }
+    else { dist2[i - c1] = d; idx2[i - c1] = id; }
 }
 
 // chamfer3D.cu:151-178: g = 2 * grad_dist[j]; grad_a[j] += g (a_j - b_idx); grad_b[idx] -= g (a_j - b_idx)
@@ -137,8 +142,8 @@ int nvsf_chamfer_forward(const float* xyz1, const float* xyz2, uint32_t b, uint3
     launch_nn(xyz1, n, xyz2, m, b, k1, sms, s);
     launch_nn(xyz2, m, xyz1, n, b, k2, sms, s);
     const size_t c1 = (size_t)b * n, c2 = (size_t)b * m;
-    k_chamfer_unpack<<<(unsigned)nvsf_div_up(c1, (size_t)256), 256, 0, s>>>(k1, c1, dist1, idx1);
-    k_chamfer_unpack<<<(unsigned)nvsf_div_up(c2, (size_t)256), 256, 0, s>>>(k2, c2, dist2, idx2);
+    k_chamfer_unpack<<<(unsigned)nvsf_div_up(c1 + c2, (size_t)256), 256, 0, s>>>(k1, c1, c2, dist1, idx1, dist2,
+                                                                              idx2);
     return nvsf_launch_status();
 }
 
