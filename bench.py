@@ -185,8 +185,8 @@ def run_reference(args):
 
 def bench_train(pkg, S, cfg_kw, dev, rank, world, rays, steps, warmup):
     """Joint training step (BASELINE configs[2] at 4096+4096 rays, configs[4] at 32768+32768 rays per
-    GPU): per step, pinned host rays -> device, LiDAR render + loss head + backward, camera render +
-    loss head + backward (NeRFNetwork.render with autograd, 768 samples/ray, perturb=True), gradient
+    GPU): per step, pinned host rays -> device, LiDAR render + loss head + Chamfer term + backward, camera
+    render + loss head + backward (NeRFNetwork.render with autograd, 768 samples/ray, perturb=True), gradient
     all-reduce over NCCL overlapped per group (dist.GradSync), Adam step (optim.FlatAdam), loss
     read back to the host.  Returns whole-job rays/s from the max-over-ranks device time."""
     import numpy as np
@@ -207,6 +207,9 @@ def bench_train(pkg, S, cfg_kw, dev, rank, world, rays, steps, warmup):
     gt_c = torch.rand(1, rays, 3, device=dev, generator=g)
     loss_h = torch.zeros(1).pin_memory()
     t = torch.tensor([[0.4]], device=dev)
+    cham = pkg.chamfer.chamfer_3DDist()
+    gt_pts = (torch.from_numpy(np.ascontiguousarray(ld)).to(dev)[None] * (gt_l[..., 2] * gt_l[..., 0]).unsqueeze(-1)
+              / S.SCALE).contiguous()
 
     def step():
         a, b = lo_h.to(dev, non_blocking=True), ld_h.to(dev, non_blocking=True)
@@ -215,6 +218,10 @@ def bench_train(pkg, S, cfg_kw, dev, rank, world, rays, steps, warmup):
         ol = model.render(a[None], b[None], t, cal_lidar_color=True, staged=False, num_steps=NUM_STEPS, perturb=True)
         # loss head of trainer.py:188-219 / 503-504 (csrc/loss.cu: loss and its derivative in one kernel)
         l1 = pkg.losses.lidar_loss(ol["depth_lidar"], ol["image_lidar"], gt_l).sum()
+        # Chamfer term between predicted and ground-truth points (trainer.py:206, 229-233), csrc/chamfer.cu
+        pred_depth = (ol["depth_lidar"] * gt_l[..., 0]).unsqueeze(-1)
+        d1, d2, _, _ = cham(b[None] * pred_depth / S.SCALE, gt_pts)
+        l1 = l1 + (d1 + d2).mean() * 0.5
         l1.backward()
         opt.sync.reduce_group("lidar")      # overlaps the camera render
         oc = model.render(c[None], d[None], t, cal_lidar_color=False, staged=False, num_steps=NUM_STEPS, perturb=True)
@@ -253,7 +260,7 @@ def bench_train(pkg, S, cfg_kw, dev, rank, world, rays, steps, warmup):
     return {"value": world * 2 * rays * steps / (ms_max * 1e-3), "unit": "rays/s", "ms_per_step": ms_max / steps,
             "rays_per_gpu": {"lidar": rays, "camera": rays}, "samples_per_ray": NUM_STEPS, "steps": steps,
             "final_loss": float(loss_h.item()), "allreduce_bytes_per_step": grad_bytes if world > 1 else 0,
-            "includes": "h2d rays, fwd+bwd of both modalities, grad all-reduce (N>1), Adam step, table re-pack, d2h loss"}
+            "includes": "h2d rays, fwd + loss head (+ Chamfer term, LiDAR) + bwd of both modalities, grad all-reduce (N>1), Adam step, table re-pack, d2h loss"}
 
 
 def bench_camera_march(pkg, S, model, dev, rank, world, steps, warmup):
