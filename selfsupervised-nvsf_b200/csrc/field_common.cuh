@@ -214,6 +214,13 @@ __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
     __half2 h = __floats2half2_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&h);
 }
+// fp16x2(relu(lo), relu(hi)) in ONE conversion (cvt.rn.relu.f16x2.f32): the hidden-layer epilogues of
+// the tcgen05 kernels are fp32 accumulator -> relu -> fp16 operand tile
+__device__ __forceinline__ uint32_t pack_half2_relu(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
 
 // One warp: acc[2 m-tiles][NT n-tiles] += A[32 x 16*KT] (registers) * W^T, W in smem [8*NT][ldw].
 template <int KT, int NT>

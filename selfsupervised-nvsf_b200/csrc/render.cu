@@ -351,38 +351,30 @@ __device__ __forceinline__ float sh4_term(int k, float dx, float dy, float dz) {
     }
 }
 
-__device__ __forceinline__ uint32_t relu_h2(uint32_t h2) {
-    uint32_t r;
-    asm("max.f16x2 %0, %1, %2;" : "=r"(r) : "r"(h2), "r"(0u));
-    return r;
-}
-
 // H[net] row `t` = fp16(relu(D[:, 0..63] (+ u))) from this thread's TMEM lane into the operand tile
 template <bool ADD_U>
 __device__ __forceinline__ void hidden_to_tile(uint32_t taddr, const float* __restrict__ u,
                                                unsigned char* tile, uint32_t t) {
 #pragma unroll
-    for (int q = 0; q < 4; q += 2) {
-        uint32_t v[2][16];
-        tmem_ld16(taddr + q * 16, v[0]);       // two loads in flight per wait
-        tmem_ld16(taddr + q * 16 + 16, v[1]);
+    for (int q = 0; q < 2; ++q) {
+        uint32_t v[32];
+        tmem_ld32(taddr + q * 32, v);          // 32 columns per load
         tmem_ld_wait();
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
             float f[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[h >> 1][8 * (h & 1) + i]);
+            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[8 * h + i]);
             if (ADD_U) {
-                const float4 ua = *reinterpret_cast<const float4*>(u + q * 16 + 8 * h);
-                const float4 ub = *reinterpret_cast<const float4*>(u + q * 16 + 8 * h + 4);
+                const float4 ua = *reinterpret_cast<const float4*>(u + q * 32 + 8 * h);
+                const float4 ub = *reinterpret_cast<const float4*>(u + q * 32 + 8 * h + 4);
                 f[0] += ua.x; f[1] += ua.y; f[2] += ua.z; f[3] += ua.w;
                 f[4] += ub.x; f[5] += ub.y; f[6] += ub.z; f[7] += ub.w;
             }
-            // relu after the rounding to fp16 (monotonic, so identical) on packed halves: 4 instead of 8 max
-            uint4 o;
-            o.x = relu_h2(pack_half2(f[0], f[1])); o.y = relu_h2(pack_half2(f[2], f[3]));
-            o.z = relu_h2(pack_half2(f[4], f[5])); o.w = relu_h2(pack_half2(f[6], f[7]));
-            *reinterpret_cast<uint4*>(tile + swz(t, 2 * q + h)) = o;
+            uint4 o;   // relu fused into the fp32 -> fp16x2 conversion
+            o.x = pack_half2_relu(f[0], f[1]); o.y = pack_half2_relu(f[2], f[3]);
+            o.z = pack_half2_relu(f[4], f[5]); o.w = pack_half2_relu(f[6], f[7]);
+            *reinterpret_cast<uint4*>(tile + swz(t, 4 * q + h)) = o;
         }
     }
 }
