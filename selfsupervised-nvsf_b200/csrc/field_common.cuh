@@ -143,7 +143,8 @@ int nvsf_launch_density(const nvsf_field_config_t* cfg, const void* workspace, c
                         const float* fars, const float* noise, uint32_t S, size_t n, float* sigma,
                         void* geo, void* features, float* flow, void* split_scratch,
                         cudaStream_t stream);
-constexpr size_t kSplitChunk = (size_t)4 << 20;  // samples per chunk of the staged variant
+constexpr size_t kSplitChunk = (size_t)64 << 20;  // largest samples-per-chunk option of the staged variant
+constexpr size_t kFeatChunk = (size_t)4 << 20;    // chunk of the un-fused path (its [chunk,128] fp16 feature rows)
 size_t nvsf_density_split_scratch_bytes(size_t n);
 size_t nvsf_density_keep_scratch_bytes(size_t n);  // mode-2 intermediates of the training forward
 // Intermediates of the staged evaluation that the training forward keeps for the backward pass.
