@@ -728,11 +728,14 @@ int nvsf_launch_density_split(const nvsf_field_config_t* cfg, const void* worksp
         const unsigned short* dyn_in = reinterpret_cast<const unsigned short*>(dyn_buf);
         const bool fused = dyn_pre && !keep && !features && g_fuse_sigma != 0;
         const bool flow_tc = dyn_pre && g_flow_tc != 0;
+        // the fused gather stage reads the (warped) query positions only: the 32 B/sample flow rows
+        // are written only when somebody reads them (1.7 GB per LiDAR frame)
+        float* flow_dst = (fused && !flow) ? nullptr : flow_buf;
         if (g_prof.on) g_prof.next(stream);
         if (x) {
             if (flow_tc) {
                 st = nvsf_launch_flow_tc(cfg, P, x, nullptr, nullptr, nullptr, nullptr, nullptr, 1, begin,
-                                         count, flow_buf, qpos_buf, count, ff, sms, stream);
+                                         count, flow_dst, qpos_buf, count, ff, sms, stream);
                 if (st != NVSF_OK) return st;
             } else if (dyn_pre)
                 k_flow_stage<false, true><<<grid_p, kSTile, kFlowStageSmem, stream>>>(
@@ -756,7 +759,7 @@ int nvsf_launch_density_split(const nvsf_field_config_t* cfg, const void* worksp
         } else {
             if (flow_tc) {
                 st = nvsf_launch_flow_tc(cfg, P, nullptr, rays_o, rays_d, nears, fars, noise, S, begin,
-                                         count, flow_buf, qpos_buf, count, ff, sms, stream);
+                                         count, flow_dst, qpos_buf, count, ff, sms, stream);
                 if (st != NVSF_OK) return st;
             } else if (dyn_pre)
                 k_flow_stage<true, true><<<grid_p, kSTile, kFlowStageSmem, stream>>>(

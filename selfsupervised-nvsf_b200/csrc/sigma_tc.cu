@@ -539,9 +539,11 @@ k_flow_tc(const __grid_constant__ nvsf_field_config_t cfg, const __grid_constant
                                               __uint_as_float(v[2]), __uint_as_float(v[3]));
                 const float4 f1 = make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]),
                                               __uint_as_float(v[6]), __uint_as_float(v[7]));
-                float4* d = reinterpret_cast<float4*>(flow_out + li * 8);
-                d[0] = f0;
-                d[1] = f1;
+                if (flow_out) {   // NULL when only the query positions are consumed (fused render path)
+                    float4* d = reinterpret_cast<float4*>(flow_out + li * 8);
+                    d[0] = f0;
+                    d[1] = f1;
+                }
                 float* q = qpos + li;
                 q[0] = x; q[stride] = y; q[2 * stride] = z;
                 q[3 * stride] = valid1 ? x + f0.x : x;
