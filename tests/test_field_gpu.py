@@ -381,3 +381,28 @@ def test_fused_stage_packed_half_interpolation(pkg, model, orc, t):
     with torch.no_grad():
         ref = orc.density(torch.from_numpy(x[:4096]), t, True)
     close(out[1][0][:4096], ref["sigma"].numpy(), 1e-2, 0, "sigma (half interpolation) vs oracle")
+
+
+def test_whole_frame_chunk_vs_feature_scratch_chunks(pkg, model):
+    """More samples than the [4 M,128] feature scratch of the un-fused path holds: the fused tcgen05
+    gather stage takes them as ONE chunk (default split_chunk = 64 M samples), the un-fused path
+    (fuse_sigma = 0) must fall back to 4 M-sample chunks, and small explicit chunks must give the same
+    rows — every sample is independent of how the batch is cut."""
+    L = pkg._lib.lib()
+    n = (4 << 20) + 70001
+    rng = torch.Generator(device="cuda").manual_seed(17)
+    x = (torch.rand(n, 3, device="cuda", generator=rng) * 2 - 1) * 1.9
+    out = {}
+    try:
+        for name, fuse, chunk in (("one_chunk", 1, 1024), ("unfused", 0, 1024), ("small_chunks", 1, 16)):
+            assert L.nvsf_set_option(b"fuse_sigma", fuse) == 0 and L.nvsf_set_option(b"split_chunk", chunk) == 0
+            den = model.density(x, 0.45, True)
+            torch.cuda.synchronize()
+            out[name] = (den["sigma"], den["geo_feat"])
+    finally:
+        L.nvsf_set_option(b"fuse_sigma", 1)
+        L.nvsf_set_option(b"split_chunk", 1024)
+    assert torch.equal(out["one_chunk"][0], out["small_chunks"][0]) and torch.equal(out["one_chunk"][1], out["small_chunks"][1])
+    close(host(out["one_chunk"][0]), host(out["unfused"][0]), 1e-3, 0, "sigma fused one chunk vs un-fused 4 M chunks")
+    g = host(out["unfused"][1])
+    close(host(out["one_chunk"][1]), g, 1e-3, 1e-3 * np.abs(g).max(), "geo fused one chunk vs un-fused 4 M chunks")
