@@ -15,7 +15,7 @@
 // coalesced store.  Tiles without any masked-in sample only write zeros.
 #include <algorithm>
 
-#include "field_common.cuh"
+#include "umma.cuh"
 
 namespace {
 
@@ -194,6 +194,175 @@ k_field_color(const __half* __restrict__ mlp, const float* __restrict__ dirs,
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// color_net (camera: SH-4 | geo -> 64 -> 64 -> 3) on tcgen05.mma / TMEM.  One CTA per SM, eight
+// independent warpgroups; a warpgroup owns 128-sample tiles (thread = sample = UMMA row = TMEM lane):
+// the thread encodes its direction and writes [SH 16 | geo 16] as the first 64 bytes of its row of
+// the swizzled K-major operand tile, then three MMA batches (K = 32, 64, 64) with the hidden
+// activations going TMEM -> tcgen05.ld -> relu/fp16 -> the same tile.  Operand images: the heads
+// image of render.cu (camera workspaces carry the whole first layer in its net-1 rows).
+// The mma.sync kernel above spends its time in ldmatrix / HMMA issue at 5.7 G samples/s.
+// ------------------------------------------------------------------------------------------------
+using namespace umma;
+constexpr int kKWG = 8;
+constexpr int kKThreads = kKWG * kRows;
+constexpr uint32_t kKImg = 128 * 128 + 2 * kHidden * 128 + 2 * 16 * 128;   // render.cu kHImgBytes
+constexpr uint32_t kKOffW1 = kHidden * 128;                                // net-1 rows: full layer 1
+constexpr uint32_t kKOffW2 = 128 * 128, kKOffW3 = kKOffW2 + 2 * kHidden * 128;
+constexpr uint32_t kKOffTiles = kKImg;
+constexpr uint32_t kKOffBar = kKOffTiles + kKWG * kRows * 128;
+constexpr size_t kColorTcSmem = kKOffBar + 8 * kKWG + 16 + 1024;
+static_assert(kKImg % 1024 == 0, "swizzled tiles start on 1024-byte boundaries");
+
+__global__ void __launch_bounds__(kKThreads, 1)
+k_color_tc(const unsigned char* __restrict__ wimg, const float* __restrict__ dirs,
+           const __half* __restrict__ geo, uint32_t geo_ld, uint32_t geo_off,
+           const uint8_t* __restrict__ mask, size_t n, float* __restrict__ out, uint32_t out_ld) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    unsigned char* sm = smem_raw + (base - raw);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + kKOffBar + 8 * kKWG);
+    const uint32_t tid = threadIdx.x, wg = tid >> 7, t = tid & 127u;
+    for (uint32_t i = tid; i < kKImg / 16; i += kKThreads)
+        reinterpret_cast<uint4*>(sm)[i] = __ldg(reinterpret_cast<const uint4*>(wimg) + i);
+    if (tid < (uint32_t)kKWG) mbar_init(base + kKOffBar + 8 * tid, 1);
+    if (tid < 32) {
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(
+                         smem_u32(tmem_slot)),
+                     "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t tcol = tmem + wg * 64u;
+    const uint32_t tlane = tcol + ((((tid >> 5) & 3u) * 32u) << 16);
+    const uint32_t xs = base + kKOffTiles + wg * (kRows * 128);
+    unsigned char* xg = sm + kKOffTiles + wg * (kRows * 128);
+    const uint32_t bar = base + kKOffBar + 8 * wg;
+    constexpr uint32_t kIdesc64 = umma_idesc(kRows, kHidden), kIdesc16 = umma_idesc(kRows, 16);
+    const bool fast_geo = geo_ld == 16 && geo_off == 1;
+    uint32_t phase = 0;
+    const size_t n_tiles = (n + kRows - 1) / kRows;
+    for (size_t tile = (size_t)blockIdx.x * kKWG + wg; tile < n_tiles; tile += (size_t)gridDim.x * kKWG) {
+        const size_t g = tile * kRows + t;
+        const bool in = g < n;
+        const bool m = in && (mask == nullptr || mask[g] != 0);
+        if (!wg_any(wg, m)) {
+            if (in)
+                for (uint32_t c = 0; c < out_ld; ++c) out[g * out_ld + c] = 0.f;
+            continue;
+        }
+        // ---- this thread's input row: [SH-4 of the direction | geo16 with column 0 zeroed] ----
+        {
+            float dx = 0.f, dy = 0.f, dz = 0.f;
+            if (m) { dx = __ldg(dirs + g * 3); dy = __ldg(dirs + g * 3 + 1); dz = __ldg(dirs + g * 3 + 2); }
+            // tcnn SphericalHarmonics degree 4 of 2*((d+1)/2) - 1 (same expressions as k_field_color)
+            const float x = ((dx + 1.0f) * 0.5f) * 2.0f - 1.0f, y = ((dy + 1.0f) * 0.5f) * 2.0f - 1.0f,
+                        z = ((dz + 1.0f) * 0.5f) * 2.0f - 1.0f;
+            const float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
+            float v[8];
+            v[0] = 0.28209479177387814f;
+            v[1] = -0.48860251190291987f * y;
+            v[2] = 0.48860251190291987f * z;
+            v[3] = -0.48860251190291987f * x;
+            v[4] = 1.0925484305920792f * xy;
+            v[5] = -1.0925484305920792f * yz;
+            v[6] = 0.94617469575755997f * z2 - 0.31539156525251999f;
+            v[7] = -1.0925484305920792f * xz;
+            st_chunk(xg, t, 0, v);
+            v[0] = 0.54627421529603959f * x2 - 0.54627421529603959f * y2;
+            v[1] = 0.59004358992664352f * y * (-3.0f * x2 + y2);
+            v[2] = 2.8906114426405538f * xy * z;
+            v[3] = 0.45704579946446572f * y * (1.0f - 5.0f * z2);
+            v[4] = 0.3731763325901154f * z * (5.0f * z2 - 3.0f);
+            v[5] = 0.45704579946446572f * x * (1.0f - 5.0f * z2);
+            v[6] = 1.4453057213202769f * z * (x2 - y2);
+            v[7] = 0.59004358992664352f * x * (-x2 + 3.0f * y2);
+            st_chunk(xg, t, 1, v);
+            uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0;
+            if (m) {
+                if (fast_geo) {
+                    const uint4* src = reinterpret_cast<const uint4*>(geo + g * 16);
+                    a0 = __ldg(src); a1 = __ldg(src + 1);
+                    a0.x &= 0xffff0000u;  // column 0 is the sigma logit, not a head input
+                } else {
+                    __align__(16) __half h[16];
+                    h[0] = __float2half(0.f);
+#pragma unroll
+                    for (int k = 0; k < 15; ++k) h[1 + k] = geo[g * geo_ld + geo_off + k];
+                    a0 = *reinterpret_cast<const uint4*>(h);
+                    a1 = *reinterpret_cast<const uint4*>(h + 8);
+                }
+            }
+            *reinterpret_cast<uint4*>(xg + swz(t, 2)) = a0;
+            *reinterpret_cast<uint4*>(xg + swz(t, 3)) = a1;
+        }
+        fence_async_smem();
+        tc_fence_before();
+        wg_barrier(wg);
+        if (t == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (uint32_t k = 0; k < 2; ++k)
+                umma_f16(tcol, umma_desc(xs + k * 32), umma_desc(base + kKOffW1 + k * 32), kIdesc64, k);
+            umma_commit(bar);
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+        tc_fence_after();
+#pragma unroll 1
+        for (int layer = 0; layer < 2; ++layer) {
+            // H = relu(D) -> tile; next batch: layer 2 (64 -> 64) or the output layer (64 -> 16)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint32_t v[16];
+                tmem_ld16(tlane + q * 16, v);
+                tmem_ld_wait();
+                st_chunk_relu(xg, t, 2 * q, v);
+                st_chunk_relu(xg, t, 2 * q + 1, v + 8);
+            }
+            fence_async_smem();
+            tc_fence_before();
+            wg_barrier(wg);
+            if (t == 0) {
+                tc_fence_after();
+                const uint32_t w = base + (layer == 0 ? kKOffW2 : kKOffW3);
+#pragma unroll
+                for (uint32_t k = 0; k < 4; ++k)
+                    umma_f16(tcol, umma_desc(xs + k * 32), umma_desc(w + k * 32), layer == 0 ? kIdesc64 : kIdesc16, k);
+                umma_commit(bar);
+            }
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+            tc_fence_after();
+        }
+        {
+            uint32_t o[16];
+            tmem_ld16(tlane, o);
+            tmem_ld_wait();
+            if (in) {
+                const float c[4] = {sigmoid_c(__uint_as_float(o[0])), sigmoid_c(__uint_as_float(o[1])),
+                                    sigmoid_c(__uint_as_float(o[2])), 0.f};
+                for (uint32_t k = 0; k < out_ld; ++k) out[g * out_ld + k] = (m && k < 3u) ? c[k] : 0.f;
+            }
+        }
+        tc_fence_before();   // the next tile's first MMA is issued behind a warpgroup barrier
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (tid < 32)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(512u)
+                     : "memory");
+}
+
+bool g_color_tc_attr = false;
+
 bool g_color_attr = false;
 int ensure_color_attrs() {
     if (g_color_attr) return NVSF_OK;
@@ -231,6 +400,20 @@ extern "C" int nvsf_field_color(const nvsf_field_config_t* cfg, const void* work
     const uint32_t blocks =
         (uint32_t)std::min<size_t>((tiles + kCWarps - 1) / kCWarps, (size_t)sms * 4);
     cudaStream_t s = (cudaStream_t)stream;
+    if (!lidar && nvsf_heads_tc()) {   // color_net on tcgen05 (option "heads_tc")
+        if (!g_color_tc_attr) {
+            cudaError_t e = cudaFuncSetAttribute(k_color_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)kColorTcSmem);
+            if (e != cudaSuccess) return (int)e;
+            g_color_tc_attr = true;
+        }
+        const size_t tiles128 = ((size_t)n + kRows - 1) / kRows;
+        const uint32_t grid = (uint32_t)std::min<size_t>((tiles128 + kKWG - 1) / kKWG, (size_t)sms);
+        k_color_tc<<<grid, kKThreads, kColorTcSmem, s>>>(reinterpret_cast<const unsigned char*>(P.heads_tc), dirs,
+                                                        reinterpret_cast<const __half*>(geo), geo_ld, geo_off,
+                                                        mask, n, out, out_ld);
+        return nvsf_launch_status();
+    }
     if (lidar)
         k_field_color<true><<<blocks, kCWarps * 32, ColorDims<true>::kSmem, s>>>(
             P.mlp, dirs, reinterpret_cast<const __half*>(geo), geo_ld, geo_off, mask, n, out, out_ld);

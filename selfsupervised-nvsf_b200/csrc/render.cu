@@ -308,6 +308,16 @@ constexpr size_t composite_tc_smem() {
 __global__ void k_pack_heads_tc(const __half* __restrict__ mlp, unsigned char* __restrict__ dst, int nets) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;  // one 16-byte chunk each
     const uint32_t per_net = kHidden * 2 + kHidden * 8 + 8 * 8;
+    if (nets == 1 && i >= per_net && i < per_net + (uint32_t)kHidden * 4) {
+        // camera workspaces: rows 64..127 of the layer-1 image (net 1 does not exist) hold the WHOLE
+        // first layer of color_net, K = 32 = [SH-4 direction columns | geo columns], for k_color_tc
+        const uint32_t k = i - per_net, r = k >> 2, c = k & 3;
+        const __half* hm = mlp + kHeadBase;
+        const uint4 v = c < 2 ? *reinterpret_cast<const uint4*>(hm + kHeadW1d + r * kHeadDirMax + c * 8)
+                              : *reinterpret_cast<const uint4*>(hm + kHeadW1g + r * kLdK16 + (c - 2) * 8);
+        *reinterpret_cast<uint4*>(dst + kHOffW1 + swz(kHidden + r, c)) = v;
+        return;
+    }
     if (i >= per_net * (uint32_t)nets) return;
     const uint32_t net = i / per_net, j = i - net * per_net;
     const __half* hm = mlp + kHeadBase + net * kHeadHalves;
@@ -777,7 +787,7 @@ int nvsf_render_uniform(const nvsf_field_config_t* cfg, const void* workspace, u
 
 void nvsf_pack_heads_tc(const __half* mlp, void* dst, int nets, cudaStream_t stream) {
     cudaMemsetAsync(dst, 0, kHImgBytes, stream);
-    const int chunks = nets * (kHidden * 2 + kHidden * 8 + 8 * 8);
+    const int chunks = nets * (kHidden * 2 + kHidden * 8 + 8 * 8) + (nets == 1 ? kHidden * 4 : 0);
     k_pack_heads_tc<<<nvsf_div_up(chunks, 128), 128, 0, stream>>>(mlp, reinterpret_cast<unsigned char*>(dst), nets);
 }
 
@@ -790,6 +800,7 @@ int nvsf_render_set_option(const char* name, int value) {
     }
     return NVSF_E_INVALID;
 }
+int nvsf_heads_tc() { return g_heads_tc; }
 int nvsf_render_get_option(const char* name) {
     if (std::string(name) == "heads_tc") return g_heads_tc;
     return NVSF_E_INVALID;

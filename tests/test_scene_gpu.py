@@ -335,3 +335,32 @@ def test_run_cuda_with_updated_grid(model):
     ws_m, ws_u = host(r["weights_sum_lidar"]), host(u["weights_sum_lidar"])
     assert np.isfinite(ws_m).all() and ws_m.max() <= 1 + 1e-5
     assert abs(ws_m.mean() - ws_u.mean()) < 0.25 * max(ws_u.mean(), 1e-3)
+
+
+def test_color_net_tcgen05_matches_mma_sync(pkg, model):
+    """color_net on tcgen05.mma / TMEM (csrc/color.cu k_color_tc, option heads_tc, camera) against the
+    mma.sync kernel k_field_color: same fp16 operands, fp32 accumulation in a different order; ragged
+    last tile, whole 128-sample tiles masked out, both geo layouts."""
+    L = pkg._lib.lib()
+    n = 100001
+    rng = np.random.default_rng(8)
+    x = ((rng.random((n, 3), dtype=np.float32) * 2 - 1) * np.float32(1.9)).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=-1, keepdims=True)
+    mask = rng.random(n) < 0.5
+    mask[1024:2048] = False
+    den = model.density(torch.from_numpy(x).cuda(), 0.3, False)
+    geo32 = den["geo_feat"].float().contiguous()
+    dd, mm = torch.from_numpy(d).cuda(), torch.from_numpy(mask).cuda()
+    out = {}
+    try:
+        for tc in (0, 1):
+            assert L.nvsf_set_option(b"heads_tc", tc) == 0
+            out[tc] = (host(model.color(None, dd, den["geo_feat"], None, False)),
+                       host(model.color(None, dd, geo32, mm, False)))
+    finally:
+        L.nvsf_set_option(b"heads_tc", 1)
+    assert np.abs(out[0][0]).max() > 0.1
+    close(out[1][0], out[0][0], 2e-3, 2e-3, "color_net tcgen05 vs mma.sync (geo16 view)")
+    close(out[1][1], out[0][1], 2e-3, 2e-3, "color_net tcgen05 vs mma.sync (fp32 geo, mask)")
+    assert not out[1][1][~mask].any()
