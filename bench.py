@@ -80,15 +80,38 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """SM clock / throttle reasons sampled during the timed region: NVML every 20 ms, or nvidia-smi
+    every 200 ms when pynvml is absent."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
+        self.nvml, self.stop_flag, self.samples = None, False, []
+
+    def _nvml_loop(self):
+        n = self.nvml
+        h = n.nvmlDeviceGetHandleByIndex(self.index)
+        get_reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        mx = n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)
+        while not self.stop_flag:
+            try:
+                self.samples.append((n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM), mx, int(get_reasons(h))))
+            except Exception:
+                pass
+            time.sleep(0.02)
 
     def start(self):
+        try:   # NVML directly: a sample every 20 ms (the timed region of the default run is ~0.3 s)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "200"],
@@ -103,6 +126,19 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            sm = sorted(x[0] for x in self.samples)
+            bits = 0
+            for x in self.samples:
+                bits |= x[2]
+            # nvml.h: SwPowerCap 0x4, HwSlowdown 0x8, SwThermalSlowdown 0x20, HwThermalSlowdown 0x40
+            reasons = [name for name, bit in (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40),
+                                              ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20)) if bits & bit]
+            return {"sm_mhz": float(sm[len(sm) // 2]) if sm else None,
+                    "sm_max_mhz": float(self.samples[0][1]) if self.samples else None,
+                    "reasons": sorted(reasons), "samples": len(sm), "source": "nvml, 20 ms"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
