@@ -453,8 +453,9 @@ k_dyn_stage(const __grid_constant__ nvsf_field_config_t cfg, const __grid_consta
 // Host side: pack consecutive levels of one plane into types whose tables fit the budget, and hand
 // the CTAs out in proportion to the per-sample cost of each type.  Returns false when a level does
 // not fit / is not 16-byte granular (the caller then uses the plain gather stage).
-int g_dyn_tile = 8192;       // samples per work item            (option "dyn_tile")
-int g_dyn_overhead = 6;      // per-sample fixed cost in gathers  (option "dyn_overhead")
+int g_dyn_tile = 32768;      // samples per work item (option "dyn_tile"); halved for small inputs, see make_dyn_plan
+                             // (whole-frame launches, 52 M samples: 8192 -> 7.3 ms, 32768 -> 6.8 ms, 262144 -> 7.2 ms)
+int g_dyn_overhead = 12;     // per-sample fixed cost in gathers  (option "dyn_overhead")
 size_t g_split_chunk = kSplitChunk;  // samples per chunk (option "split_chunk", units of 64 K): a whole
                                      // LiDAR frame (52 M samples) is one chunk, 29.4 -> 27.x ms against 4 M chunks
 
@@ -488,6 +489,8 @@ bool make_dyn_plan(const nvsf_field_config_t* cfg, const FieldPtrs& P, size_t co
     if ((P.dyn_per_q * sizeof(__half)) % 16) return false;
     plan.ntypes = (uint32_t)nt;
     plan.tile = (uint32_t)g_dyn_tile;
+    // small inputs: keep at least ~4 work items per CTA so that the dynamic hand-out can balance
+    while (plan.tile > 2048 && (size_t)nt * ((count + plan.tile - 1) / plan.tile) < (size_t)ctas * 4) plan.tile >>= 1;
     plan.tiles = (uint32_t)((count + plan.tile - 1) / plan.tile);
     plan.stride = (uint32_t)stride;
     double total = 0.0, acc = 0.0;

@@ -216,13 +216,13 @@ def test_dyn_stage_tiles_and_chunks(pkg, model):
     out = []
     try:
         assert L.nvsf_set_option(b"density_mode", 2) == 0
-        for tile, chunk in ((8192, 64), (1024, 1)):
+        for tile, chunk in ((32768, 1024), (1024, 1)):
             assert L.nvsf_set_option(b"dyn_tile", tile) == 0 and L.nvsf_set_option(b"split_chunk", chunk) == 0
             den = model.density(x, 0.6, False)
             r = model.render(to, td, torch.tensor([[0.6]], device="cuda"), cal_lidar_color=True, num_steps=128)
             out.append((host(den["sigma"]), host(den["geo_feat"]), host(r["depth_lidar"]), host(r["image_lidar"])))
     finally:
-        L.nvsf_set_option(b"dyn_tile", 8192); L.nvsf_set_option(b"split_chunk", 64)
+        L.nvsf_set_option(b"dyn_tile", 32768); L.nvsf_set_option(b"split_chunk", 1024)
         L.nvsf_set_option(b"density_mode", prev)
     for a, b in zip(*out):
         assert np.array_equal(a, b)
