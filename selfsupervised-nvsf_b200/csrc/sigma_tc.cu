@@ -173,8 +173,7 @@ k_sigma_stage_tc(const unsigned char* __restrict__ wimg, const __half* __restric
 bool g_tc_attr = false;
 
 // ---- gather stage fused with the sigma MLP ---------------------------------------------------------
-// The feature rows never leave the SM: a CTA of 8 warpgroups (1024 threads, one CTA per SM, 64
-// registers per thread like the plain gather stage) — every warpgroup is an independent 128-sample
+// The feature rows never leave the SM: a CTA of kFusedWG warpgroups (one CTA per SM) — every warpgroup is an independent 128-sample
 // UMMA tile with its own [128 rows][128 B] shared-memory operand tile, mbarrier, named barrier and
 // 64 TMEM columns.  A thread gathers the features of its own sample (its row); the sigma-net input
 // is consumed in two K halves that accumulate in TMEM:
@@ -185,13 +184,23 @@ bool g_tc_attr = false;
 // refill (4 of the 32 warps pause for the ~0.5 us of an MMA batch, the other 28 keep gathering).
 // Against the staged pair k_encode_stage -> k_sigma_stage this removes the 256 B/sample feature row
 // from DRAM (written with one L1 tag per lane, read back by the sigma stage) and one launch.
-constexpr int kFusedWG = 8;
+#ifndef NVSF_FUSED_WG
+#define NVSF_FUSED_WG 6   // warpgroups per CTA of the fused gather + sigma stage: 6 x 128 threads at 80 registers
+                          // (8 x 64 registers: 11.77 ms, 7: 11.52, 6: 11.47, 4: 14.4 ms per LiDAR frame)
+#endif
+constexpr int kFusedWG = NVSF_FUSED_WG;
 constexpr int kFusedThreads = kFusedWG * kRows;
 constexpr uint32_t kFTile = kRows * 128;                         // one K block of 128 rows
 constexpr uint32_t kFOffX = kOffW2 + kW2Bytes;
 constexpr uint32_t kFOffBar = kFOffX + kFusedWG * kFTile;
 constexpr size_t kFusedSmem = kFOffBar + 8 * kFusedWG + 16 + 1024;
 static_assert(kFOffX % 1024 == 0, "swizzled tiles start on 1024-byte boundaries");
+// the flow stage keeps 8 warpgroups (64 registers per thread): with 6 it measured 5.70 -> 5.97 ms,
+// while the gather + sigma stage gains from 6 x 85 registers (11.77 -> 11.50 ms)
+constexpr int kFlowWG = 8;
+constexpr int kFlowThreads = kFlowWG * kRows;
+constexpr uint32_t kLOffBar = kFOffX + kFlowWG * kFTile;
+constexpr size_t kFlowSmem = kLOffBar + 8 * kFlowWG + 16 + 1024;
 
 template <bool H2>
 __global__ void __launch_bounds__(kFusedThreads, 1)
@@ -424,7 +433,7 @@ bool g_fused_attr = false;
 // live in TMEM and the gather threads stay at 64 registers, 32 warps per SM.
 // Outputs: flow [n,8] f32 (6 used) and the three query positions, planar qpos[9][stride].
 template <bool FROM_RAYS>
-__global__ void __launch_bounds__(kFusedThreads, 1)
+__global__ void __launch_bounds__(kFlowThreads, 1)
 k_flow_tc(const __grid_constant__ nvsf_field_config_t cfg, const __grid_constant__ FieldPtrs P,
           const float* __restrict__ xin, const float* __restrict__ rays_o,
           const float* __restrict__ rays_d, const float* __restrict__ nears,
@@ -435,13 +444,13 @@ k_flow_tc(const __grid_constant__ nvsf_field_config_t cfg, const __grid_constant
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     unsigned char* sm = smem_raw + (base - raw);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + kFOffBar + 8 * kFusedWG);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + kLOffBar + 8 * kFlowWG);
     const uint32_t tid = threadIdx.x, wg = tid >> 7, t = tid & 127u;
     const unsigned char* wimg = reinterpret_cast<const unsigned char*>(P.mlp_tc) + (kW1Bytes + kW2Bytes);
 
-    for (uint32_t i = tid; i < (kW1Bytes + kW2Bytes) / 16; i += kFusedThreads)
+    for (uint32_t i = tid; i < (kW1Bytes + kW2Bytes) / 16; i += kFlowThreads)
         reinterpret_cast<uint4*>(sm)[i] = __ldg(reinterpret_cast<const uint4*>(wimg) + i);
-    if (tid < (uint32_t)kFusedWG) mbar_init(base + kFOffBar + 8 * tid, 1);
+    if (tid < (uint32_t)kFlowWG) mbar_init(base + kLOffBar + 8 * tid, 1);
     if (tid < 32) {
         __syncwarp();
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(
@@ -459,15 +468,15 @@ k_flow_tc(const __grid_constant__ nvsf_field_config_t cfg, const __grid_constant
     const uint32_t tlane = tcol + ((((tid >> 5) & 3u) * 32u) << 16);
     const uint32_t xs = base + kFOffX + wg * kFTile;
     unsigned char* xg = sm + kFOffX + wg * kFTile;
-    const uint32_t bar = base + kFOffBar + 8 * wg;
+    const uint32_t bar = base + kLOffBar + 8 * wg;
     const uint32_t w1 = base, w2 = base + kHidden * 128, w3 = base + 2 * kHidden * 128;
     constexpr uint32_t kIdesc64 = umma_idesc(kRows, kHidden), kIdesc16 = umma_idesc(kRows, 16);
     const int valid1 = P.ti->valid[1], valid2 = P.ti->valid[2];
 
     uint32_t phase = 0;
     const size_t n_tiles = (count + kRows - 1) / kRows;
-    for (size_t tile = (size_t)blockIdx.x * kFusedWG + wg; tile < n_tiles;
-         tile += (size_t)gridDim.x * kFusedWG) {
+    for (size_t tile = (size_t)blockIdx.x * kFlowWG + wg; tile < n_tiles;
+         tile += (size_t)gridDim.x * kFlowWG) {
         const size_t li = tile * kRows + t;
         const bool live = li < count;
         float x, y, z;
@@ -620,21 +629,21 @@ int nvsf_launch_flow_tc(const nvsf_field_config_t* cfg, const FieldPtrs& P, cons
                         float* qpos, size_t stride, __half* flowfeat, int sms, cudaStream_t stream) {
     if (!g_flow_attr) {
         cudaError_t e = cudaFuncSetAttribute(k_flow_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)kFusedSmem);
+                                             (int)kFlowSmem);
         if (e != cudaSuccess) return (int)e;
         e = cudaFuncSetAttribute(k_flow_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)kFusedSmem);
+                                 (int)kFlowSmem);
         if (e != cudaSuccess) return (int)e;
         g_flow_attr = true;
     }
     const size_t tiles = (count + kRows - 1) / kRows;
-    const int grid = (int)std::min<size_t>((tiles + kFusedWG - 1) / kFusedWG, (size_t)sms);
+    const int grid = (int)std::min<size_t>((tiles + kFlowWG - 1) / kFlowWG, (size_t)sms);
     if (x)
-        k_flow_tc<false><<<grid, kFusedThreads, kFusedSmem, stream>>>(
+        k_flow_tc<false><<<grid, kFlowThreads, kFlowSmem, stream>>>(
             *cfg, P, x, nullptr, nullptr, nullptr, nullptr, nullptr, 1, begin, count, flow_out, qpos, stride,
             flowfeat);
     else
-        k_flow_tc<true><<<grid, kFusedThreads, kFusedSmem, stream>>>(
+        k_flow_tc<true><<<grid, kFlowThreads, kFlowSmem, stream>>>(
             *cfg, P, nullptr, rays_o, rays_d, nears, fars, noise, S, begin, count, flow_out, qpos, stride,
             flowfeat);
     return NVSF_OK;
