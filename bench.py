@@ -47,7 +47,7 @@ HEADS_EXECUTED_FLOP_PER_SAMPLE = 2 * 2 * (16 * 64 + 64 * 64 + 64 * 16)  # what k
 #                                    encode stage = static hash 512 + collapsed dyn hash 1152 + space planes
 #                                                   1536 + time planes 2304 + flow in 32 + feature row out 256
 #                                    sigma stage  = feature row in 256 + sigma f32 + geo f16[16] out 36
-#   mode 2 (fp16 mirrors, default):  flow stage  = 16 x 8 x 4 B + flow out 32 + query positions out 36
+#   mode 2 (fp16 mirrors, default):  flow stage  = 16 x 8 x 4 B + query positions out 36 (+ flow out 32 un-fused)
 #                                    dyn stage   = 288 two-byte gathers from shared-memory tables (576) +
 #                                                  query positions in 36 + 24 fp16 values out 48
 #                                    encode stage (fused with the sigma MLP, tcgen05) = static hash 512 +
@@ -64,7 +64,9 @@ def stage_table(L):
                       "sigma_stage": (256 + 36, "k_sigma_stage_tc" if opt(b"sigma_tc") else "k_sigma_stage")}
     fused = bool(opt(b"fuse_sigma"))
     return mode, {
-        "flow_stage": (512 + 32 + 36, "k_flow_tc" if opt(b"flow_tc") else "k_flow_stage"),
+        # the flow rows (32 B) are written only when somebody reads them: not on the fused tcgen05 path
+        "flow_stage": (512 + 36 + (0 if fused and opt(b"flow_tc") else 32),
+                       "k_flow_tc" if opt(b"flow_tc") else "k_flow_stage"),
         "dyn_stage": (576 + 36 + 48, "k_dyn_stage"),
         "encode_stage": (512 + 768 + 1152 + 48 + 36 + (36 if fused else 256),
                          "k_encode_sigma_tc" if fused else "k_encode_stage"),
