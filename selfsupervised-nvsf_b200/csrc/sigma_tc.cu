@@ -197,7 +197,10 @@ constexpr size_t kFusedSmem = kFOffBar + 8 * kFusedWG + 16 + 1024;
 static_assert(kFOffX % 1024 == 0, "swizzled tiles start on 1024-byte boundaries");
 // the flow stage keeps 8 warpgroups (64 registers per thread): with 6 it measured 5.70 -> 5.97 ms,
 // while the gather + sigma stage gains from 6 x 85 registers (11.77 -> 11.50 ms)
-constexpr int kFlowWG = 8;
+#ifndef NVSF_FLOW_WG
+#define NVSF_FLOW_WG 8
+#endif
+constexpr int kFlowWG = NVSF_FLOW_WG;
 constexpr int kFlowThreads = kFlowWG * kRows;
 constexpr uint32_t kLOffBar = kFOffX + kFlowWG * kFTile;
 constexpr size_t kFlowSmem = kLOffBar + 8 * kFlowWG + 16 + 1024;
