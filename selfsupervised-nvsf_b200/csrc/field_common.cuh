@@ -173,7 +173,8 @@ int nvsf_launch_flow_tc(const nvsf_field_config_t* cfg, const FieldPtrs& P, cons
 // gather stage fused with the sigma MLP (mode 2 intermediates: query positions + dyn rows)
 int nvsf_launch_encode_sigma_tc(const nvsf_field_config_t* cfg, const FieldPtrs& P, const float* qpos,
                                 const void* dyn_in, size_t stride, size_t count, float* sigma,
-                                __half* geo, int sms, cudaStream_t stream, int half_math);
+                                __half* geo, int sms, cudaStream_t stream, int half_math,
+                                __half* feat_out /* [n,128] kept rows or NULL */);
 void nvsf_stage_timing_enable(int on);
 int nvsf_split_set_option(const char* name, int value);
 int nvsf_split_get_option(const char* name);

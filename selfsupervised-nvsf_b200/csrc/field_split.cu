@@ -639,6 +639,9 @@ int ensure_attrs() {
     return NVSF_OK;
 }
 
+int g_fuse_keep = 0;   // option "fuse_keep": training forward through the fused gather + sigma kernel, which then
+                       // also writes the kept feature rows; measured neutral (train step 21.04 vs 21.19 ms), so the
+                       // default stays k_encode_stage -> k_sigma_stage_tc
 int g_half_math = 0;   // option "half_math": packed-half interpolation in the fused gather + sigma stage
                        // (k_encode_sigma_tc<true>): 27 % fewer instructions, measured 12.53 -> 12.67 ms —
                        // the stage is bound by the L1 data pipe, not by issue slots; kept for A/B runs
@@ -710,7 +713,7 @@ int nvsf_launch_density_split(const nvsf_field_config_t* cfg, const void* worksp
     {   // only the fused gather + sigma kernel (and the training forward, which keeps its rows itself)
         // can take chunks beyond the [kFeatChunk,128] feature scratch of the un-fused path
         DynPlan probe;
-        const bool may_fuse = want_dyn && !keep && !features && g_fuse_sigma != 0 &&
+        const bool may_fuse = want_dyn && !features && g_fuse_sigma != 0 &&
                               make_dyn_plan(cfg, P, chunk, chunk, sms, probe);
         if (!may_fuse && !keep) chunk = std::min(chunk, kFeatChunk);
     }
@@ -729,11 +732,11 @@ int nvsf_launch_density_split(const nvsf_field_config_t* cfg, const void* worksp
         const int grid_d = dyn_pre ? (int)std::min<size_t>((size_t)plan.ntypes * plan.tiles, (size_t)sms) : 0;
         if (dyn_pre) cudaMemsetAsync(counters, 0, kDynMaxTypes * sizeof(uint32_t), stream);
         const unsigned short* dyn_in = reinterpret_cast<const unsigned short*>(dyn_buf);
-        const bool fused = dyn_pre && !keep && !features && g_fuse_sigma != 0;
+        const bool fused = dyn_pre && !features && g_fuse_sigma != 0 && (!keep || g_fuse_keep != 0);
         const bool flow_tc = dyn_pre && g_flow_tc != 0;
         // the fused gather stage reads the (warped) query positions only: the 32 B/sample flow rows
         // are written only when somebody reads them (1.7 GB per LiDAR frame)
-        float* flow_dst = (fused && !flow) ? nullptr : flow_buf;
+        float* flow_dst = (fused && !flow && !keep) ? nullptr : flow_buf;
         if (g_prof.on) g_prof.next(stream);
         if (x) {
             if (flow_tc) {
@@ -786,7 +789,8 @@ int nvsf_launch_density_split(const nvsf_field_config_t* cfg, const void* worksp
         }
         if (fused) {  // gather stage + sigma MLP in one tcgen05 kernel: the feature rows stay on the SM
             st = nvsf_launch_encode_sigma_tc(cfg, P, qpos_buf, dyn_buf, count, count, sigma + begin,
-                                             reinterpret_cast<__half*>(geo) + begin * kGeo, sms, stream, g_half_math);
+                                             reinterpret_cast<__half*>(geo) + begin * kGeo, sms, stream, g_half_math,
+                                             keep ? feat_buf : nullptr);
             if (st != NVSF_OK) return st;
         }
         if (g_prof.on) g_prof.next(stream);
@@ -836,6 +840,11 @@ int nvsf_split_set_option(const char* name, int value) {
         g_half_math = value;
         return NVSF_OK;
     }
+    if (k == "fuse_keep") {
+        if (value != 0 && value != 1) return NVSF_E_INVALID;
+        g_fuse_keep = value;
+        return NVSF_OK;
+    }
     if (k == "fuse_sigma") {
         if (value != 0 && value != 1) return NVSF_E_INVALID;
         g_fuse_sigma = value;
@@ -869,6 +878,7 @@ int nvsf_split_get_option(const char* name) {
     if (k == "fuse_sigma") return g_fuse_sigma;
     if (k == "flow_tc") return g_flow_tc;
     if (k == "half_math") return g_half_math;
+    if (k == "fuse_keep") return g_fuse_keep;
     return nvsf_train_get_option(name);
 }
 

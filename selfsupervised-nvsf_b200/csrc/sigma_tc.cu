@@ -210,7 +210,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1)
 k_encode_sigma_tc(const __grid_constant__ nvsf_field_config_t cfg,
                   const __grid_constant__ FieldPtrs P, const float* __restrict__ qpos,
                   const unsigned short* __restrict__ dyn_in, size_t stride, size_t count,
-                  float* __restrict__ sigma_out, __half* __restrict__ geo_out) {
+                  float* __restrict__ sigma_out, __half* __restrict__ geo_out,
+                  __half* __restrict__ feat_out /* [n,128] kept for the backward pass, or NULL */) {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -316,6 +317,11 @@ k_encode_sigma_tc(const __grid_constant__ nvsf_field_config_t cfg,
             st_chunk(xg, t, 4 + s, acc8);
         }
         }
+        if (feat_out && live) {   // training forward: the thread's own row (K half 0) also goes to global
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                *reinterpret_cast<uint4*>(feat_out + li * kFeat + 8 * c) = *reinterpret_cast<const uint4*>(xg + swz(t, c));
+        }
         fence_async_smem();
         tc_fence_before();
         wg_barrier(wg);
@@ -354,6 +360,11 @@ k_encode_sigma_tc(const __grid_constant__ nvsf_field_config_t cfg,
                 make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
         }
         *reinterpret_cast<uint4*>(xg + swz(t, 7)) = make_uint4(0, 0, 0, 0);
+        if (feat_out && live) {   // K half 1
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                *reinterpret_cast<uint4*>(feat_out + li * kFeat + 64 + 8 * c) = *reinterpret_cast<const uint4*>(xg + swz(t, c));
+        }
         fence_async_smem();
         tc_fence_before();
         wg_barrier(wg);
@@ -605,7 +616,7 @@ int nvsf_launch_sigma_tc(const void* wimg, const __half* feat, size_t count, flo
 
 int nvsf_launch_encode_sigma_tc(const nvsf_field_config_t* cfg, const FieldPtrs& P, const float* qpos,
                                 const void* dyn_in, size_t stride, size_t count, float* sigma,
-                                __half* geo, int sms, cudaStream_t stream, int half_math) {
+                                __half* geo, int sms, cudaStream_t stream, int half_math, __half* feat_out) {
     if (!g_fused_attr) {
         cudaError_t e = cudaFuncSetAttribute(k_encode_sigma_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)kFusedSmem);
@@ -619,10 +630,10 @@ int nvsf_launch_encode_sigma_tc(const nvsf_field_config_t* cfg, const FieldPtrs&
     const int grid = (int)std::min<size_t>((tiles + kFusedWG - 1) / kFusedWG, (size_t)sms);
     if (half_math)
         k_encode_sigma_tc<true><<<grid, kFusedThreads, kFusedSmem, stream>>>(
-            *cfg, P, qpos, reinterpret_cast<const unsigned short*>(dyn_in), stride, count, sigma, geo);
+            *cfg, P, qpos, reinterpret_cast<const unsigned short*>(dyn_in), stride, count, sigma, geo, feat_out);
     else
         k_encode_sigma_tc<false><<<grid, kFusedThreads, kFusedSmem, stream>>>(
-            *cfg, P, qpos, reinterpret_cast<const unsigned short*>(dyn_in), stride, count, sigma, geo);
+            *cfg, P, qpos, reinterpret_cast<const unsigned short*>(dyn_in), stride, count, sigma, geo, feat_out);
     return NVSF_OK;
 }
 
