@@ -33,7 +33,7 @@ extern "C" {
 #define NVSF_E_WORKSPACE (-2) /* workspace too small */
 
 /* ABI version of this header; bumped on any signature change. */
-#define NVSF_B200_ABI_VERSION 11
+#define NVSF_B200_ABI_VERSION 12
 int nvsf_abi_version(void);
 /* Human-readable text for a status returned by any nvsf_* call. */
 const char* nvsf_status_string(int status);
@@ -347,6 +347,23 @@ int nvsf_render_uniform_backward(const nvsf_field_config_t* cfg, const void* wor
                                  const nvsf_field_grads_t* grads, void* scratch,
                                  size_t scratch_bytes, void* stream);
 
+/* NeRFNetwork.flow (network_dynamic.py:197-211 -> FlowField.forward, flow_field.py:116-133) with its
+ * backward: what the scene-flow loss of train_step differentiates (trainer.py:237-265:
+ * `self.model.flow(pc, time_ego)` -> Chamfer distance of the warped cloud + |flow|.mean()).
+ * forward: x [n,3] in [-bound,bound] -> flow [n,8] f32 (forward xyz, backward xyz, 2 unused) and the
+ * kept flow-MLP inputs flowfeat [n,32] f16; `workspace` packed for the frame time.
+ * backward: dflow [n,8] f32 (columns 6,7 zero) -> accumulates into grads_flow_grid / grads_flow_mlp
+ * (layouts of nvsf_field_params_t.flow_grid / .flow_mlp). */
+size_t nvsf_field_flow_scratch_bytes(const nvsf_field_config_t* cfg, uint32_t n);
+int nvsf_field_flow_forward(const nvsf_field_config_t* cfg, const void* workspace, const float* x,
+                            uint32_t n, float* flow, void* flowfeat, void* scratch,
+                            size_t scratch_bytes, void* stream);
+int nvsf_field_flow_backward(const nvsf_field_config_t* cfg, const void* workspace,
+                             const float* flow_mlp, const float* x, uint32_t n,
+                             const void* flowfeat, const float* dflow, float* grads_flow_grid,
+                             float* grads_flow_mlp, void* scratch, size_t scratch_bytes,
+                             void* stream);
+
 /* torch.optim.Adam step as the reference configures it (main_nvsf.py:350-352: betas (0.9, 0.99),
  * eps 1e-15, no weight decay) over one flat fp32 segment of n parameters (16-byte aligned
  * pointers): m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
@@ -435,6 +452,41 @@ int nvsf_loss_lidar(const float* depth, const float* image, const float* gt, uin
  * rgb_depth_loss on pre-masked inputs): loss [n], g_pred [n] = d loss[i] / d pred[i]. */
 int nvsf_loss_elementwise(const float* pred, const float* gt, size_t n, int kind, float param,
                           float alpha, float* loss, float* g_pred, void* stream);
+
+/* Urban-Radiance-Fields line-of-sight loss of train_step (trainer.py:276-296) on the renderer's
+ * `weights` [R,T] and `z_vals` [R,T] with gt_depth [R] (= images_lidar[:,:,2] * raydrop mask) and
+ * eps = 0.02 * 0.1^min(step/iters, 1):  loss[0] = 0.1 * (sum (mask_empty w)^2 + sum (mask_near w -
+ * distr)^2) / #(gt_depth > 0), distr = the normal density of (z - gt_depth) with sigma = eps/3 divided
+ * by its maximum over all elements; g_weights [R,T] = d loss / d weights.  workspace: 16 bytes. */
+int nvsf_loss_los(const float* weights, const float* z_vals, const float* gt_depth, uint32_t R, uint32_t T,
+                  float eps, float* loss, float* g_weights, void* workspace, size_t workspace_bytes,
+                  void* stream);
+
+#define NVSF_LOSS_COS 4 /* torch.nn.CosineSimilarity() over the flattened patch (--depth_grad_loss cos) */
+
+/* options of the structural regularisation (main_nvsf.py:86,90,100-107; trainer.py:297-462) */
+typedef struct nvsf_patch_loss_cfg {
+    float scale;                                          /* opt.scale */
+    int32_t sobel, grad_norm_smooth, spatial_smooth, tv_loss, grad_loss;  /* flags */
+    float alpha_grad_norm, alpha_spatial, alpha_tv, alpha_grad;
+    int32_t grad_kind;                                    /* --depth_grad_loss: NVSF_LOSS_* */
+    float grad_param;
+} nvsf_patch_loss_cfg_t;
+
+/* ground-truth side of the gradient loss (trainer.py:392-428): from the range image pano_depth [H,W]
+ * (data['pano_frame'][0,...,2]) and the pixel ids rays_pano_inds [P*h*w] (int64) of P patches of h x w
+ * rays: mask_x / mask_y [P,h,w] = |second difference of the range image| < thresh (0.05). */
+int nvsf_patch_grad_masks(const float* pano_depth, uint32_t H, uint32_t W, const int64_t* rays_pano_inds,
+                          uint32_t P, uint32_t h, uint32_t w, float scale, float thresh, float* mask_x,
+                          float* mask_y, void* stream);
+
+/* structural regularisation of P depth patches of h x w rays (trainer.py:306-462): pred_depth [P,h,w]
+ * (= depth_lidar * raydrop mask), and for the gradient loss gt_depth, gt_raydrop, mask_x, mask_y
+ * [P,h,w].  loss_map [P,h,w] = the element-wise terms (grad_norm / spatial / tv), grad_loss [P] = each
+ * patch's share of `grad_loss.sum()`, g_pred [P,h,w] = d (loss_map.sum() + grad_loss.sum()) / d pred_depth. */
+int nvsf_loss_patch(const float* pred_depth, const float* gt_depth, const float* gt_raydrop, const float* mask_x,
+                    const float* mask_y, uint32_t P, uint32_t h, uint32_t w, const nvsf_patch_loss_cfg_t* cfg,
+                    float* loss_map, float* grad_loss, float* g_pred, void* stream);
 
 /* replaces the reference's Chamfer extension (nvsf/nerf/chamfer3D/chamfer3D.cu; pybind
  * chamfer_cuda.cpp `forward` / `backward`; wrapper dist_chamfer_3D.py:42-95), called by train_step

@@ -105,7 +105,7 @@ def hash_grid(table_flat, levels, D, F, x):
 def mlp(flat, shapes, x, n_out, fp16_weights=True):
     w = T._fp16_round(flat) if fp16_weights else flat
     pad = shapes[0][1] - x.shape[1]
-    h = Fnn.pad(x, (0, pad)) if pad else x
+    h = Fnn.pad(x, (0, pad), value=1.0) if pad else x   # tcnn pads Network inputs with 1 (tcnn_standin.Network)
     off = 0
     for li, (o, i) in enumerate(shapes):
         W = w[off:off + o * i].view(o, i)

@@ -22,7 +22,7 @@ from oracle.field_oracle import PLANE_COMBS  # noqa: E402
 from oracle.make_golden_field import config  # noqa: E402
 
 S = importlib.import_module("selfsupervised-nvsf_b200.synth")
-N_RAYS, N_STEPS = 24, 32
+N_RAYS, N_STEPS = 256, 64   # 16 K samples per case: one fp16 ReLU sign flip no longer moves a whole tensor
 CASES = [  # (tag, lidar, time, density_scale, perturb)
     ("l_mid", True, 0.3, 60.0, True),
     ("c_mid", False, 0.3, 60.0, False),

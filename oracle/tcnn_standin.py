@@ -21,9 +21,15 @@ Semantics (tcnn `grid.h`, `frequency.h`, `spherical_harmonics.h`, `fully_fused_m
              fp16 (here: rounded to fp16, arithmetic in fp32).
   Frequency  out[j] = sin(2^((j//2) % n_freq) * pi * x[j // (2 n_freq)] + (j % 2) * pi/2), n_freq=12.
   SH deg 4   16 real spherical-harmonics polynomials of 2x-1.
-  FullyFusedMLP  weights row-major [out, in] per layer, input width padded to a multiple of 16
-             with zeros, output padded to 16, no biases, ReLU hidden, linear output; fp16
+  FullyFusedMLP  weights row-major [out, in] per layer, input width padded to a multiple of 16,
+             output padded to 16, no biases, ReLU hidden, linear output; fp16
              weights/activations (here: fp16-rounded weights, fp32 arithmetic).
+  Network    the torch binding's `tcnn.Network(n_in, n_out, cfg)` is `create_network`, which wraps
+             the MLP in a NetworkWithInputEncoding with an "Identity" encoding (tcnn cpp_api.cu);
+             tcnn's encodings fill their padded outputs with the constant 1 (identity.h: "data_out(j, i)
+             = 1" for the padded columns; frequency.h documents "padding (value 1.f)"), so the padded
+             INPUT columns of the MLP are 1 and the weight columns behind them act as a learned
+             first-layer bias.  (Restated from the published source from memory: tcnn is not vendored.)
 Outputs are returned as float32 (tcnn returns fp16): the comparison tolerance for anything that
 passes through these modules is 1e-2 (BASELINE.json north_star), which covers that difference.
 """
@@ -177,7 +183,7 @@ class Network(nn.Module):
     def forward(self, x):
         x = x.to(torch.float32)
         pad = self.shapes[0][1] - x.shape[1]
-        h = torch.nn.functional.pad(x, (0, pad)) if pad else x
+        h = torch.nn.functional.pad(x, (0, pad), value=1.0) if pad else x   # Identity-encoding padding = 1
         w_all = _fp16_round(self.params)
         off = 0
         for li, (o, i) in enumerate(self.shapes):

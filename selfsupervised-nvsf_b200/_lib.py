@@ -6,6 +6,7 @@ crosses the boundary.  There is no fallback — if the library is missing or a
 call fails the caller gets an exception.
 """
 import ctypes
+import functools
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -81,6 +82,9 @@ PROTOTYPES = {
                                                  _sz, _p, _p, _p, _p, _p, _p]),
     "nvsf_render_uniform_backward": (_int, [_p, _p, _p, _u32, _p, _p, _p, _p, _p, _u32, _u32, _f32, _p,
                                             _sz, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "nvsf_field_flow_scratch_bytes": (_sz, [_p, _u32]),
+    "nvsf_field_flow_forward": (_int, [_p, _p, _p, _u32, _p, _p, _p, _sz, _p]),
+    "nvsf_field_flow_backward": (_int, [_p, _p, _p, _p, _u32, _p, _p, _p, _p, _p, _sz, _p]),
     "nvsf_adam_step": (_int, [_p, _p, _p, _p, _sz, _f32, _f32, _f32, _f32, _u32, _f32, _p]),
     "nvsf_field_color": (_int, [_p, _p, _u32, _p, _p, _u32, _u32, _p, _u32, _p, _u32, _p]),
     # Part 4 — ray generation, occupancy grid, alive-list compaction
@@ -95,6 +99,9 @@ PROTOTYPES = {
     # Part 5 — loss head
     "nvsf_loss_lidar": (_int, [_p, _p, _p, _u32, _p, _p, _p, _p, _p]),
     "nvsf_loss_elementwise": (_int, [_p, _p, _sz, _int, _f32, _f32, _p, _p, _p]),
+    "nvsf_loss_los": (_int, [_p, _p, _p, _u32, _u32, _f32, _p, _p, _p, _sz, _p]),
+    "nvsf_patch_grad_masks": (_int, [_p, _u32, _u32, _p, _u32, _u32, _u32, _f32, _f32, _p, _p, _p]),
+    "nvsf_loss_patch": (_int, [_p, _p, _p, _p, _p, _u32, _u32, _u32, _p, _p, _p, _p, _p]),
     "nvsf_chamfer_workspace_bytes": (_sz, [_u32, _u32, _u32]),
     "nvsf_chamfer_forward": (_int, [_p, _p, _u32, _u32, _u32, _p, _p, _p, _p, _p, _sz, _p]),
     "nvsf_chamfer_backward": (_int, [_p, _p, _u32, _u32, _u32, _p, _p, _p, _p, _p, _p, _p]),
@@ -130,7 +137,7 @@ def lib():
     return _lib
 
 
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 
 def check(status, what=""):
@@ -150,3 +157,30 @@ def stream_ptr():
     import torch
 
     return torch.cuda.current_stream().cuda_stream or None
+
+
+def device_guard(fn):
+    """Run `fn` with the CUDA device of its first CUDA tensor (or of the first nn.Module with CUDA
+    parameters) current, as torch's own extensions do through their device guard: the kernels behind
+    the C ABI launch on the current device and on its current stream (`stream_ptr`)."""
+    import torch
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        dev = None
+        for a in args:
+            if isinstance(a, torch.Tensor):
+                if a.is_cuda:
+                    dev = a.device
+                    break
+            elif isinstance(a, torch.nn.Module):
+                p = next(a.parameters(), None)
+                if p is not None and p.is_cuda:
+                    dev = p.device
+                    break
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+
+    return wrapper

@@ -24,7 +24,7 @@ constexpr int kCWarps = 4;
 template <bool LIDAR>
 struct ColorDims {
     static constexpr int kDirPad = LIDAR ? 80 : 16;         // 72 -> 80 (k-tiles of 16)
-    static constexpr int kK = kDirPad + 16;                 // + geo16 (col 0 = logit, zeroed)
+    static constexpr int kK = kDirPad + 16;                 // + geo16 (col 0: logit -> constant 1)
     static constexpr int kLd = kK + 8;                      // 104 / 40 halves: conflict-free ldmatrix
     static constexpr int kNets = LIDAR ? 2 : 1;
     static constexpr size_t kSmem =
@@ -64,7 +64,7 @@ k_field_color(const __half* __restrict__ mlp, const float* __restrict__ dirs,
                 for (uint32_t c = 0; c < out_ld; ++c) out[g * out_ld + c] = 0.f;
             continue;
         }
-        // ---- stage this lane's input row: [dir encoding | 0 pad | geo16 with col 0 zeroed] ----
+        // ---- stage this lane's input row: [dir encoding | 0 pad | geo16 with col 0 = 1] ----
         __half* row = At + lane * D::kLd;
         float dx = 0.f, dy = 0.f, dz = 0.f;
         if (m) {
@@ -121,10 +121,10 @@ k_field_color(const __half* __restrict__ mlp, const float* __restrict__ dirs,
                 if (fast_geo) {
                     const uint4* src = reinterpret_cast<const uint4*>(geo + g * 16);
                     a0 = __ldg(src); a1 = __ldg(src + 1);
-                    a0.x &= 0xffff0000u;  // column 0 is the sigma logit, not a head input
+                    a0.x = (a0.x & 0xffff0000u) | kOneH;  // column 0 (the sigma logit) becomes the constant-1 padding input
                 } else {
                     __align__(16) __half h[16];
-                    h[0] = __float2half(0.f);
+                    h[0] = __float2half(1.f);
 #pragma unroll
                     for (int k = 0; k < 15; ++k) h[1 + k] = geo[g * geo_ld + geo_off + k];
                     a0 = *reinterpret_cast<const uint4*>(h);
@@ -258,7 +258,7 @@ k_color_tc(const unsigned char* __restrict__ wimg, const float* __restrict__ dir
                 for (uint32_t c = 0; c < out_ld; ++c) out[g * out_ld + c] = 0.f;
             continue;
         }
-        // ---- this thread's input row: [SH-4 of the direction | geo16 with column 0 zeroed] ----
+        // ---- this thread's input row: [SH-4 of the direction | geo16 with column 0 = 1] ----
         {
             float dx = 0.f, dy = 0.f, dz = 0.f;
             if (m) { dx = __ldg(dirs + g * 3); dy = __ldg(dirs + g * 3 + 1); dz = __ldg(dirs + g * 3 + 2); }
@@ -290,10 +290,10 @@ k_color_tc(const unsigned char* __restrict__ wimg, const float* __restrict__ dir
                 if (fast_geo) {
                     const uint4* src = reinterpret_cast<const uint4*>(geo + g * 16);
                     a0 = __ldg(src); a1 = __ldg(src + 1);
-                    a0.x &= 0xffff0000u;  // column 0 is the sigma logit, not a head input
+                    a0.x = (a0.x & 0xffff0000u) | kOneH;  // column 0 (the sigma logit) becomes the constant-1 padding input
                 } else {
                     __align__(16) __half h[16];
-                    h[0] = __float2half(0.f);
+                    h[0] = __float2half(1.f);
 #pragma unroll
                     for (int k = 0; k < 15; ++k) h[1 + k] = geo[g * geo_ld + geo_off + k];
                     a0 = *reinterpret_cast<const uint4*>(h);

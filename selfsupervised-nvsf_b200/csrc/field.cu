@@ -185,6 +185,17 @@ __global__ void k_pack_matrix(const float* __restrict__ src, int src_ld, int src
     dst[r * dst_ld + dst_col0 + c] = __float2half_rn(__ldg(src + r * src_ld + src_col0 + c));
 }
 
+// dst[r][dst_col] = fp16(sum_c fp16(src[r][col0 + c])): the first-layer weight columns behind tcnn's
+// constant-1 input padding, folded into one column (see kOneH in field_common.cuh)
+__global__ void k_pack_padsum(const float* __restrict__ src, int src_ld, int col0, int ncols, int rows,
+                              __half* __restrict__ dst, int dst_ld, int dst_col) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    float s = 0.f;
+    for (int c = 0; c < ncols; ++c) s += round_h(__ldg(src + r * src_ld + col0 + c));
+    dst[r * dst_ld + dst_col] = __float2half_rn(s);
+}
+
 // ------------------------------------------------------------------------------------------------
 // per-sample encoders (device)
 // ------------------------------------------------------------------------------------------------
@@ -358,8 +369,8 @@ k_field_density(const __grid_constant__ nvsf_field_config_t cfg, const __grid_co
             }
         }
         {
-            const float zero8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            st8(xrow, 120, zero8);
+            const float one8[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};   // tcnn input padding = 1
+            st8(xrow, 120, one8);
         }
         __syncwarp();
         if (feat_out && live) {
@@ -563,7 +574,9 @@ int nvsf_field_pack_params(const nvsf_field_config_t* cfg, const nvsf_field_para
         if (!heads[h]) continue;
         __half* hm = m + kHeadBase + h * kHeadHalves;
         pack(heads[h], in_pad, 0, H, n_dir, hm + kHeadW1d, kHeadDirMax, 0);
-        pack(heads[h], in_pad, n_dir, H, 15, hm + kHeadW1g, kLdK16, 1);  // geo col 0 is the logit
+        pack(heads[h], in_pad, n_dir, H, 15, hm + kHeadW1g, kLdK16, 1);  // geo col 0 is the logit ...
+        // ... which the head kernels replace by the constant 1 of tcnn's input padding (87 -> 96, 31 -> 32)
+        k_pack_padsum<<<1, H, 0, s>>>(heads[h], in_pad, n_dir + 15, in_pad - n_dir - 15, H, hm + kHeadW1g, kLdK16, 0);
         pack(heads[h] + H * in_pad, H, 0, H, H, hm + kHeadW2, kLdK64, 0);
         pack(heads[h] + H * in_pad + H * H, H, 0, n_out, H, hm + kHeadW3, kLdK64, 0);
     }

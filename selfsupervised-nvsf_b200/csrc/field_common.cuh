@@ -6,7 +6,14 @@
 #include "common.cuh"
 
 constexpr int kHidden = 64;       // n_neurons of every MLP (main_nvsf.py:53-59)
-constexpr int kFeat = 128;        // sigma-net input: 120 features zero-padded to 128
+constexpr int kFeat = 128;        // sigma-net input: 120 features padded to 128 with ONES
+// tcnn pads the input of a Network up to a multiple of 16 with the constant 1 (the torch binding's
+// tcnn.Network wraps the MLP in an Identity encoding whose padded outputs are 1), so the weight columns
+// behind the padding act as a learned first-layer bias.  sigma_net: columns 120..127 of the feature row
+// are 1.  Head nets: the geo16 operand row (col 0 = sigma logit, never a head input) carries 1 in
+// column 0 and the packed geo weight image carries the SUM of the padded columns there.
+constexpr uint32_t kOnesH2 = 0x3C003C00u;  // (1.0h, 1.0h)
+constexpr uint32_t kOneH = 0x3C00u;
 constexpr int kGeo = 16;          // sigma-net output: logit + 15 geo features
 constexpr int kHashF = 4;         // features per hash level == temporal basis functions
 constexpr int kFlowF = 8;
@@ -59,7 +66,7 @@ constexpr int kDensityWHalves = kSigW2 + kGeo * kLdK64;      // end of the densi
 // head nets (2 slots; camera uses slot 0 only): per slot
 constexpr int kHeadDirMax = 72;                              // Frequency: 72, SH: 16
 constexpr int kHeadW1d = 0;                                  // [64][72]  direction part of layer 1
-constexpr int kHeadW1g = kHeadW1d + kHidden * kHeadDirMax;   // [64][24]  geo part (col 0 = 0)
+constexpr int kHeadW1g = kHeadW1d + kHidden * kHeadDirMax;   // [64][24]  geo part (col 0 = sum of the padded input columns)
 constexpr int kHeadW2 = kHeadW1g + kHidden * kLdK16;         // [64][72]
 constexpr int kHeadW3 = kHeadW2 + kHidden * kLdK64;          // [8][72]
 constexpr int kHeadHalves = kHeadW3 + 8 * kLdK64;

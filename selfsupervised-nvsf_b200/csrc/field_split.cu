@@ -228,7 +228,7 @@ k_encode_stage(const __grid_constant__ nvsf_field_config_t cfg,
         }
         st8g(row, 64 + 4 * l, v);
     }
-    // (d) collapsed 2-D hashes -> [96,120), zero pad [120,128)
+    // (d) collapsed 2-D hashes -> [96,120), padding [120,128) = 1
     if constexpr (DYN_PRE) {
 #pragma unroll
         for (int p = 0; p < 3; ++p) {
@@ -271,7 +271,7 @@ k_encode_stage(const __grid_constant__ nvsf_field_config_t cfg,
         *reinterpret_cast<uint4*>(row + 96 + 8 * p) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
     }
     }
-    *reinterpret_cast<uint4*>(row + 120) = make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4*>(row + 120) = make_uint4(kOnesH2, kOnesH2, kOnesH2, kOnesH2);  // tcnn input padding = 1
 }
 
 

@@ -173,6 +173,7 @@ k_render_composite(const __grid_constant__ nvsf_field_config_t cfg, const __half
                 if (in) {
                     const uint4* src = reinterpret_cast<const uint4*>(geo + g * kGeo);
                     a0 = __ldg(src); a1 = __ldg(src + 1);
+                    a0.x = (a0.x & 0xffff0000u) | kOneH;  // col 0: sigma logit -> the constant-1 padding input
                 }
                 uint4* dst = reinterpret_cast<uint4*>(geo_s + lane * kGeoLd);
                 dst[0] = a0; dst[1] = a1;
@@ -515,6 +516,7 @@ k_composite_tc(const __grid_constant__ nvsf_field_config_t cfg, const unsigned c
             const bool m = w > 1e-4f;  // renderer_dynamic.py:202
             // geo rows of this tile -> operand tile (it aliases the LAST net's hidden tile, see the
             // hazards below); then the next tile's rows start travelling
+            a0.x = (a0.x & 0xffff0000u) | kOneH;  // col 0: sigma logit -> the constant-1 padding input (weight = pad-column sum)
             *reinterpret_cast<uint4*>(tileg + (NETS - 1) * kCTile + swz(t, 0)) = a0;
             *reinterpret_cast<uint4*>(tileg + (NETS - 1) * kCTile + swz(t, 1)) = a1;
             {

@@ -178,7 +178,7 @@ bool g_tc_attr = false;
 // 64 TMEM columns.  A thread gathers the features of its own sample (its row); the sigma-net input
 // is consumed in two K halves that accumulate in TMEM:
 //   half 0: space planes (32) + collapsed time planes (32)   -> tile -> 4 x tcgen05.mma (D1  = ..)
-//   half 1: static hash (32) + dyn rows (24) + zero pad (8)  -> tile -> 4 x tcgen05.mma (D1 += ..)
+//   half 1: static hash (32) + dyn rows (24) + ones pad (8)  -> tile -> 4 x tcgen05.mma (D1 += ..)
 //   H = relu(D1) fp16 -> tile -> 4 x tcgen05.mma (D2 = H W2^T) -> sigma = exp(D2[:,0]), geo
 // The tile is re-used three times per sample block; a warpgroup waits on its own mbarrier before each
 // refill (4 of the 32 warps pause for the ~0.5 us of an MMA batch, the other 28 keep gathering).
@@ -359,7 +359,7 @@ k_encode_sigma_tc(const __grid_constant__ nvsf_field_config_t cfg,
             *reinterpret_cast<uint4*>(xg + swz(t, 4 + p)) =
                 make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
         }
-        *reinterpret_cast<uint4*>(xg + swz(t, 7)) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(xg + swz(t, 7)) = make_uint4(kOnesH2, kOnesH2, kOnesH2, kOnesH2);  // tcnn input padding = 1
         if (feat_out && live) {   // K half 1
 #pragma unroll
             for (int c = 0; c < 8; ++c)

@@ -384,7 +384,7 @@ struct HeadT {
             return;
         }
         const size_t ray = g / A.S;
-        // geo features: 16 halves; cols NDIR + (0..14) = geo[1..15], col NDIR+15 = 0
+        // geo features: 16 halves; cols NDIR + (0..14) = geo[1..15], col NDIR+15 = 1 (padding)
         const __half* gh0 = reinterpret_cast<const __half*>(&pf.g0);
         const __half* gh1 = reinterpret_cast<const __half*>(&pf.g1);
         if (!LIDAR) {
@@ -421,14 +421,14 @@ struct HeadT {
             *reinterpret_cast<uint4*>(Ds + r * kLdD) = o0;
             *reinterpret_cast<uint4*>(Ds + r * kLdD + 8) = make_uint4(0, 0, 0, 0);
         } else {
-            // geo[9..15] -> cols NDIR+8 .. NDIR+14, col NDIR+15 = 0; lidar: cols 88..95 = 0
+            // geo[9..15] -> cols NDIR+8 .. NDIR+14, col NDIR+15 = 1; lidar: cols 88..95 = 1 (tcnn input padding)
 #pragma unroll
             for (int j = 8; j < 16; j += 2) {
                 const float a = __half2float(gh1[j + 1 - 8]);
-                const float b = j + 2 < 16 ? __half2float(gh1[j + 2 - 8]) : 0.f;
+                const float b = j + 2 < 16 ? __half2float(gh1[j + 2 - 8]) : 1.f;   // tcnn input padding = 1
                 *reinterpret_cast<uint32_t*>(xr + NDIR + j) = pack_bf2(a, b);
             }
-            if (LIDAR) *reinterpret_cast<uint4*>(xr + 88) = make_uint4(0, 0, 0, 0);
+            if (LIDAR) *reinterpret_cast<uint4*>(xr + 88) = make_uint4(kOnesH2, kOnesH2, kOnesH2, kOnesH2);
         }
         if (LIDAR) {
             __syncthreads();
@@ -1485,6 +1485,82 @@ int nvsf_render_uniform_backward(const nvsf_field_config_t* cfg, const void* wor
     }
     k_expand_flow<<<nvsf_div_up(cfg->fl_entries, 256u), 256, 0, s>>>(
         reinterpret_cast<const float2*>(G.flow), cfg->fl_entries, P.ti, grads->flow_grid);
+    return nvsf_launch_status();
+}
+
+// ---- NeRFNetwork.flow with autograd (scene-flow loss, trainer.py:237-265) --------------------------
+// scratch: [scales 64 B][fp16 weight images][collapsed flow-grid gradient][qpos f32 [9][n] (forward) |
+// dflowfeat f32 [n,32] (backward)]
+size_t nvsf_field_flow_scratch_bytes(const nvsf_field_config_t* cfg, uint32_t n) {
+    if (!field_cfg_ok(cfg)) return 0;
+    return ws_align(64) + ws_align((size_t)kB_Total * sizeof(bf16)) +
+           ws_align((size_t)cfg->fl_entries * sizeof(float2)) + ws_align((size_t)n * 32 * sizeof(float)) +
+           ws_align((size_t)n * 9 * sizeof(float));
+}
+
+int nvsf_field_flow_forward(const nvsf_field_config_t* cfg, const void* workspace, const float* x,
+                            uint32_t n, float* flow, void* flowfeat, void* scratch,
+                            size_t scratch_bytes, void* stream) {
+    if (n == 0) return NVSF_OK;
+    if (!field_cfg_ok(cfg) || !workspace || !x || !flow || !flowfeat || !scratch) return NVSF_E_INVALID;
+    if (scratch_bytes < nvsf_field_flow_scratch_bytes(cfg, n)) return NVSF_E_WORKSPACE;
+    const FieldPtrs P = nvsf_make_field_ptrs(cfg, workspace);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    unsigned char* sc = reinterpret_cast<unsigned char*>(scratch);
+    float* qpos = reinterpret_cast<float*>(sc + nvsf_field_flow_scratch_bytes(cfg, n) -
+                                           ws_align((size_t)n * 9 * sizeof(float)));
+    int st = nvsf_launch_flow_tc(cfg, P, x, nullptr, nullptr, nullptr, nullptr, nullptr, 1, 0, n, flow, qpos, n,
+                                 reinterpret_cast<__half*>(flowfeat), sms, (cudaStream_t)stream);
+    if (st != NVSF_OK) return st;
+    return nvsf_launch_status();
+}
+
+int nvsf_field_flow_backward(const nvsf_field_config_t* cfg, const void* workspace,
+                             const float* flow_mlp, const float* x, uint32_t n,
+                             const void* flowfeat, const float* dflow, float* grads_flow_grid,
+                             float* grads_flow_mlp, void* scratch, size_t scratch_bytes,
+                             void* stream) {
+    if (n == 0) return NVSF_OK;
+    if (!field_cfg_ok(cfg) || !workspace || !flow_mlp || !x || !flowfeat || !dflow || !grads_flow_grid ||
+        !grads_flow_mlp || !scratch)
+        return NVSF_E_INVALID;
+    if (scratch_bytes < nvsf_field_flow_scratch_bytes(cfg, n)) return NVSF_E_WORKSPACE;
+    cudaStream_t s = (cudaStream_t)stream;
+    const FieldPtrs P = nvsf_make_field_ptrs(cfg, workspace);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    unsigned char* sc = reinterpret_cast<unsigned char*>(scratch);
+    size_t off = 0;
+    unsigned char* scl = sc + off; off += ws_align(64);
+    bf16* wimg = reinterpret_cast<bf16*>(sc + off); off += ws_align((size_t)kB_Total * sizeof(bf16));
+    float* gflow = reinterpret_cast<float*>(sc + off); off += ws_align((size_t)cfg->fl_entries * sizeof(float2));
+    float* dflowfeat = reinterpret_cast<float*>(sc + off);
+    const int H = kHidden;
+    cudaMemsetAsync(scl, 0, 64, s);
+    cudaMemsetAsync(wimg, 0, (size_t)kB_SigW1 * sizeof(bf16), s);
+    cudaMemsetAsync(gflow, 0, (size_t)cfg->fl_entries * sizeof(float2), s);
+    auto pack = [&](const float* src, int src_ld, int rows, int cols, bf16* dst, int dst_ld) {
+        k_pack_matrix_bf16<<<nvsf_div_up(rows * cols, 256), 256, 0, s>>>(src, src_ld, rows, cols, dst, dst_ld);
+    };
+    pack(flow_mlp, kFlowIn, H, kFlowIn, wimg + kB_FlowW1, kBLdK32);
+    pack(flow_mlp + H * kFlowIn, H, H, H, wimg + kB_FlowW2, kLdH);
+    pack(flow_mlp + H * kFlowIn + H * H, H, 6, H, wimg + kB_FlowW3, kLdH);
+    unsigned* mx = reinterpret_cast<unsigned*>(scl);
+    k_absmax<<<(unsigned)std::min<size_t>(nvsf_div_up((size_t)n * 8, (size_t)1024), (size_t)sms * 4), 256, 0, s>>>(
+        dflow, (size_t)n * 8, 1.0f, mx);
+    k_make_scale<<<1, 1, 0, s>>>(mx, reinterpret_cast<float*>(mx) + 2);
+    const float* scale_f = reinterpret_cast<const float*>(mx) + 2;
+    FlowT::Args A{reinterpret_cast<const __half*>(flowfeat), dflow, dflowfeat};
+    MlpGrads MG{grads_flow_mlp, grads_flow_mlp + H * kFlowIn, grads_flow_mlp + H * kFlowIn + H * H};
+    int st = launch_mlp_bwd<FlowT>(A, wimg + kB_FlowW1, wimg + kB_FlowW2, wimg + kB_FlowW3, n, MG, scale_f, sms, s);
+    if (st != NVSF_OK) return st;
+    k_flowgrid_bwd<false><<<(unsigned)nvsf_div_up((size_t)n, (size_t)256), 256, 0, s>>>(
+        *cfg, gflow, x, nullptr, nullptr, nullptr, nullptr, nullptr, 1, 0, n, dflow, dflowfeat, scale_f);
+    k_expand_flow<<<nvsf_div_up(cfg->fl_entries, 256u), 256, 0, s>>>(reinterpret_cast<const float2*>(gflow),
+                                                                   cfg->fl_entries, P.ti, grads_flow_grid);
     return nvsf_launch_status();
 }
 

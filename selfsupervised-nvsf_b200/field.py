@@ -150,6 +150,7 @@ class _RenderUniformTrain(torch.autograd.Function):
     receives None for that input."""
 
     @staticmethod
+    @_lib.device_guard
     def forward(ctx, model, lidar, o, d, nears, fars, noise, S, bg, *params):
         L = _setup_lib()
         dev = o.device
@@ -169,18 +170,20 @@ class _RenderUniformTrain(torch.autograd.Function):
                                                   ptr(z_vals), stream_ptr()), "render_uniform_train_forward")
         ctx.model, ctx.lidar, ctx.S, ctx.bg = model, lidar, S, bg
         ctx.tensors = (o, d, nears, fars, noise, saved, weights, ws)
-        ctx.time_key = model._packed[lidar]
+        ctx.pack_gen = model._pack_gen.get(lidar, 0)
         ctx.mark_non_differentiable(z_vals)
         return depth, image, wsum, weights, z_vals
 
     @staticmethod
+    @_lib.device_guard
     def backward(ctx, g_depth, g_image, g_wsum, g_weights, _g_z):
         L = _setup_lib()
         model, lidar, S = ctx.model, ctx.lidar, ctx.S
         o, d, nears, fars, noise, saved, weights, ws = ctx.tensors
-        if model._ws.get(lidar) is not ws or model._packed.get(lidar) != ctx.time_key:
-            raise _lib.NvsfError("the packed field tables changed between forward and backward "
-                                 "(another render of the same modality ran in between)")
+        if model._ws.get(lidar) is not ws or model._pack_gen.get(lidar, 0) != ctx.pack_gen:
+            raise _lib.NvsfError("the packed field tables were rebuilt between forward and backward (another "
+                                 "render / density / update_extra_state of the same modality ran in between): "
+                                 "call backward() of a render before the next pack of that modality")
         dev, N = o.device, o.shape[0]
         names = _param_names(lidar)
         params = [getattr(model, n) for n in names]
@@ -215,6 +218,54 @@ class _RenderUniformTrain(torch.autograd.Function):
             model._debug = dict(saved=saved, scratch=scratch, N=N, S=S)
         ctx.tensors = None
         return (None,) * 9 + tuple(ret)
+
+
+class _FlowTrain(torch.autograd.Function):
+    """NeRFNetwork.flow with autograd (network_dynamic.py:197-211): the scene-flow loss of train_step
+    (trainer.py:237-265) differentiates it with respect to flow_net's grid and MLP."""
+
+    @staticmethod
+    @_lib.device_guard
+    def forward(ctx, model, x, flow_grid, flow_mlp):
+        L = _setup_lib()
+        n = x.shape[0]
+        dev = x.device
+        ws = model._ws[True]
+        flow = torch.empty(n, 8, dtype=torch.float32, device=dev)
+        flowfeat = torch.empty(n, 32, dtype=torch.float16, device=dev)
+        sbytes = L.nvsf_field_flow_scratch_bytes(ctypes.byref(model._cfg), n)
+        scratch = torch.empty(sbytes, dtype=torch.uint8, device=dev)
+        check(L.nvsf_field_flow_forward(ctypes.byref(model._cfg), ptr(ws), ptr(x), n, ptr(flow), ptr(flowfeat),
+                                        ptr(scratch), sbytes, stream_ptr()), "field_flow_forward")
+        ctx.model, ctx.pack_gen, ctx.tensors = model, model._pack_gen.get(True, 0), (x, flowfeat, ws, scratch)
+        return flow[:, :6]
+
+    @staticmethod
+    @_lib.device_guard
+    def backward(ctx, g_flow):
+        L = _setup_lib()
+        model = ctx.model
+        x, flowfeat, ws, scratch = ctx.tensors
+        if model._ws.get(True) is not ws or model._pack_gen.get(True, 0) != ctx.pack_gen:
+            raise _lib.NvsfError("the packed field tables were rebuilt between flow() and its backward")
+        n = x.shape[0]
+        dflow = torch.zeros(n, 8, dtype=torch.float32, device=x.device)
+        dflow[:, :6] = g_flow.to(torch.float32)
+        fused = bool(getattr(model, "fused_grad_accumulation", False))
+        grads, ret = [], []
+        for p in (model.flow_grid, model.flow_mlp):
+            if fused and p.grad is not None and p.grad.is_contiguous() and p.grad.dtype == torch.float32:
+                grads.append(p.grad)
+                ret.append(None)
+            else:
+                g = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                grads.append(g)
+                ret.append(g)
+        check(L.nvsf_field_flow_backward(ctypes.byref(model._cfg), ptr(ws), ptr(model.flow_mlp), ptr(x), n,
+                                         ptr(flowfeat), ptr(dflow), ptr(grads[0]), ptr(grads[1]), ptr(scratch),
+                                         scratch.numel(), stream_ptr()), "field_flow_backward")
+        ctx.tensors = None
+        return None, None, ret[0], ret[1]
 
 
 class NeRFNetwork(nn.Module):
@@ -327,6 +378,8 @@ class NeRFNetwork(nn.Module):
         self.register_buffer("aabb_infer", self.aabb_train.clone())
         self._ws = {}      # modality -> workspace tensor
         self._packed = {}  # modality -> (param versions, time key)
+        self._pack_gen = {}  # modality -> number of times the workspace tables were (re)written; a training
+                             # forward records it and its backward refuses to run against newer tables
 
     # ------------------------------------------------------------------ parameters
     def load_flat_params(self, p):
@@ -339,6 +392,85 @@ class NeRFNetwork(nn.Module):
             for k in ("flow_grid", "flow_mlp", "sigma_net", "intensity_net", "raydrop_net", "color_net"):
                 getattr(self, k).copy_(torch.as_tensor(p[k]))
         self._packed.clear()
+
+    # reference checkpoint keys (Trainer.save_checkpoint stores model.state_dict() under "model",
+    # nvsf/nerf/utils.py:610-650; key names pinned by tests/golden/state_dict_manifest.json)
+    def _reference_keys(self):
+        """[(reference key, parameter name, offset, numel, shape)] in this module's concatenation order."""
+        T = self.time_resolution
+        out = []
+        for m in ("lidar", "camera"):
+            out.append((f"hash_encoder_{m}.hash_static.params", f"hash_static_{m}", 0,
+                        self.param_sizes["hash_static"], (self.param_sizes["hash_static"],)))
+            off = 0
+            for p in range(3):
+                per = self._cfg.hd_entries[p] * 4
+                for k in range(T):
+                    out.append((f"hash_encoder_{m}.hash_dynamic.{p}.hash_t.{k}.params", f"hash_dynamic_{m}", off, per,
+                                (per,)))
+                    off += per
+            off = 0
+            for s, R in enumerate(self._pl_res):
+                r = (R, R, R, T)
+                for c, (a, b) in enumerate(PLANE_COMBS):
+                    n = 8 * r[a] * r[b]
+                    out.append((f"planes_encoder_{m}.planes.{s}.{c}", f"planes_{m}", off, n, (1, 8, r[b], r[a])))
+                    off += n
+        out.append(("flow_net.grid_enc.params", "flow_grid", 0, self.param_sizes["flow_grid"],
+                    (self.param_sizes["flow_grid"],)))
+        off = 0
+        for li, (o, k) in zip((0, 2, 4), ((64, 32), (64, 64), (6, 64))):
+            out.append((f"flow_net.mlp.{li}.weight", "flow_mlp", off, o * k, (o, k)))
+            off += o * k
+        for n in ("sigma_net", "intensity_net", "raydrop_net", "color_net"):
+            out.append((f"{n}.params", n, 0, self.param_sizes[n], (self.param_sizes[n],)))
+        return out
+
+    def load_reference_state_dict(self, state_dict, strict=True):
+        """Load a checkpoint of the REFERENCE model: `torch.load(path)["model"]` (or the bare state
+        dict) as written by Trainer.save_checkpoint (utils.py:610-650) / read by load_checkpoint
+        (:682-747).  Returns (missing_keys, unexpected_keys) like nn.Module.load_state_dict; keys of
+        modules outside the hot path (the un-suffixed planes_encoder / hash_encoder that the reference
+        constructs but never optimises, view encoders without parameters, the U-Net, aabb buffers,
+        density grids) are reported as unexpected and ignored."""
+        sd = state_dict.get("model", state_dict) if isinstance(state_dict, dict) else state_dict
+        used, missing = set(), []
+        with torch.no_grad():
+            for key, name, off, n, shape in self._reference_keys():
+                if key not in sd:
+                    missing.append(key)
+                    continue
+                v = sd[key]
+                if tuple(v.shape) != tuple(shape):
+                    raise _lib.NvsfError(f"{key}: checkpoint shape {tuple(v.shape)} != {tuple(shape)}")
+                getattr(self, name).view(-1)[off:off + n].copy_(v.reshape(-1).to(torch.float32))
+                used.add(key)
+            for key in ("aabb_train", "aabb_infer"):
+                if key in sd:
+                    getattr(self, key).copy_(sd[key].to(torch.float32))
+                    used.add(key)
+        self._packed.clear()
+        unexpected = [k for k in sd.keys() if k not in used]
+        if strict and missing:
+            raise _lib.NvsfError(f"reference checkpoint lacks {len(missing)} keys, e.g. {missing[:3]}")
+        return missing, unexpected
+
+    def reference_state_dict(self):
+        """The hot-path parameters under the reference's state_dict keys and shapes (the inverse of
+        load_reference_state_dict; tensors are views of this module's parameters)."""
+        out = {"aabb_train": self.aabb_train, "aabb_infer": self.aabb_infer}
+        for key, name, off, n, shape in self._reference_keys():
+            out[key] = getattr(self, name).detach().view(-1)[off:off + n].view(*shape)
+        return out
+
+    def get_params(self, lr):
+        """Optimizer parameter groups of the reference (network_dynamic.py:335-357): encoders, sigma_net
+        and color_net at lr; flow_net, intensity_net and raydrop_net at 0.1 lr."""
+        g = lambda names, f: {"params": [getattr(self, n) for n in names], "lr": f * lr}
+        return [g(["planes_lidar"], 1.0), g(["hash_static_lidar", "hash_dynamic_lidar"], 1.0),
+                g(["planes_camera"], 1.0), g(["hash_static_camera", "hash_dynamic_camera"], 1.0),
+                g(["flow_grid", "flow_mlp"], 0.1), g(["sigma_net"], 1.0), g(["intensity_net"], 0.1),
+                g(["raydrop_net"], 0.1), g(["color_net"], 1.0)]
 
     def _params_c(self, lidar):
         m = "lidar" if lidar else "camera"
@@ -386,9 +518,11 @@ class NeRFNetwork(nn.Module):
             check(L.nvsf_field_pack_params(ctypes.byref(self._cfg), ctypes.byref(pc), int(lidar), ptr(ws),
                                            ws.numel(), st), "field_pack_params")
             prev = None
+            self._pack_gen[lidar] = self._pack_gen.get(lidar, 0) + 1
         if prev is None or t_key is None or prev[1] != t_key:
             check(L.nvsf_field_pack_time(ctypes.byref(self._cfg), ctypes.byref(pc), ptr(t_dev), ptr(ws),
                                          ws.numel(), st), "field_pack_time")
+            self._pack_gen[lidar] = self._pack_gen.get(lidar, 0) + 1
         self._packed[lidar] = (vkey, t_key)
         return ws
 
@@ -408,18 +542,43 @@ class NeRFNetwork(nn.Module):
                                    ptr(feats), ptr(flow), ptr(scratch), sbytes, stream_ptr()), "field_density")
         return sigma, geo, feats, flow
 
-    @torch.no_grad()
+    def _no_autograd(self, what, lidar):
+        """The per-sample entry points are forward-only (the differentiable path is run() / render() /
+        flow()); called under autograd on trainable parameters they would silently contribute no
+        gradient where the reference's versions do, so in training mode they refuse instead."""
+        if self.training and torch.is_grad_enabled() and \
+                any(getattr(self, n).requires_grad for n in _param_names(lidar)):
+            raise _lib.NvsfError(f"NeRFNetwork.{what}() is forward-only: in training mode call it under "
+                                 "torch.no_grad() (gradients flow through run() / render() / flow())")
+
+    @_lib.device_guard
     def density(self, x, t=None, cal_lidar_color=False, **kwargs):
         """x [N,3] in [-bound,bound] -> {'sigma' [N] f32, 'geo_feat' [N,15] f16}."""
+        self._no_autograd("density", bool(cal_lidar_color))
+        with torch.no_grad():
+            return self._density(x, t, cal_lidar_color)
+
+    def _density(self, x, t, cal_lidar_color):
         sigma, geo, _, _ = self._density_raw(x, t, bool(cal_lidar_color))
         return {"sigma": sigma, "geo_feat": geo[:, 1:]}
 
-    @torch.no_grad()
+    @_lib.device_guard
     def flow(self, x, t):
-        _, _, _, f = self._density_raw(x, t, True, want_flow=True)
+        """NeRFNetwork.flow (network_dynamic.py:197-211): x [N,3] in [-bound,bound] -> forward / backward
+        scene flow [N,3] each.  Differentiable with respect to flow_grid / flow_mlp when autograd is
+        enabled (the scene-flow loss, trainer.py:237-265); x itself is treated as data."""
+        if torch.is_grad_enabled() and (self.flow_grid.requires_grad or self.flow_mlp.requires_grad):
+            with torch.no_grad():
+                xx = x.detach().to(device=self.sigma_net.device, dtype=torch.float32).contiguous().view(-1, 3)
+                self.prepare(t, True)
+            f = _FlowTrain.apply(self, xx, self.flow_grid, self.flow_mlp)
+        else:
+            with torch.no_grad():
+                _, _, _, f = self._density_raw(x, t, True, want_flow=True)
         return {"flow_forward": f[:, :3], "flow_backward": f[:, 3:]}
 
     @torch.no_grad()
+    @_lib.device_guard
     def features(self, x, t, cal_lidar_color=False):
         """Debug/test hook: the 120 sigma-net inputs [N,120] (fp16) and the flow [N,6]."""
         _, _, feats, f = self._density_raw(x, t, bool(cal_lidar_color), want_features=True, want_flow=True)
@@ -436,8 +595,13 @@ class NeRFNetwork(nn.Module):
                                  geo_ld, geo_off, ptr(mask), n, ptr(out), out_ld, stream_ptr()), "field_color")
         return out
 
-    @torch.no_grad()
+    @_lib.device_guard
     def color(self, x, d, geo_feat, mask=None, cal_lidar_color=False, **kwargs):
+        self._no_autograd("color", bool(cal_lidar_color))
+        with torch.no_grad():
+            return self._color(x, d, geo_feat, mask, cal_lidar_color)
+
+    def _color(self, x, d, geo_feat, mask=None, cal_lidar_color=False):
         """NeRFNetwork.color (network_dynamic.py:290-332): d [N,3] view directions in [-1,1],
         geo_feat [N,15] (the slice `density()` returns, or any fp16/fp32 matrix), mask [N] bool
         or None -> [N, 2] (raydrop, intensity) or [N, 3] rgb, zeros where mask is False.  `x`
@@ -472,6 +636,7 @@ class NeRFNetwork(nn.Module):
         del keep
         return out
 
+    @_lib.device_guard
     def forward(self, x, d, t=None, cal_lidar_color=False, out_ld=None):
         """sigma [N] and colours [N, 2|3] of samples (x, d): density + color in two launches
         (what the march_rays* callers evaluate per batch of samples)."""
@@ -506,6 +671,7 @@ class NeRFNetwork(nn.Module):
         return self._grid_state(bool(cal_lidar_color))["stats"][0]
 
     @torch.no_grad()
+    @_lib.device_guard
     def update_extra_state(self, time=0.0, cal_lidar_color=False, decay=0.95, perturb=True, noise=None):
         """Full occupancy-grid update (torch-ngp NeRFRenderer.update_extra_state, the caller the
         reference's morton3D / packbits operators were written for): evaluate sigma at one
@@ -542,6 +708,7 @@ class NeRFNetwork(nn.Module):
 
     # ------------------------------------------------------------------ march_rays* render loops
     @torch.no_grad()
+    @_lib.device_guard
     def run_cuda(self, rays_o, rays_d, time, cal_lidar_color=False, dt_gamma=0.0, bg_color=None, perturb=False,
                  max_steps=1024, T_thresh=1e-4, one_shot=None, noises=None, density_bitfield=None,
                  step_scale=16, **kwargs):
@@ -632,6 +799,7 @@ class NeRFNetwork(nn.Module):
                 "weights_sum" + sfx: weights_sum}
 
     # ------------------------------------------------------------------ renderer API
+    @_lib.device_guard
     def run(self, rays_o, rays_d, time, cal_lidar_color=False, num_steps=768, upsample_steps=128,
             bg_color=None, perturb=False, noise=None, return_weights=True, **kwargs):
         """NeRFRenderer.run (renderer_dynamic.py:109-265).  `noise` [N,num_steps] optionally
@@ -662,16 +830,32 @@ class NeRFNetwork(nn.Module):
             noise = noise.detach().to(device=dev, dtype=torch.float32).contiguous()
         return o, d, nears, fars, noise
 
+    @staticmethod
+    def _split_bg(bg_color, n, dev):
+        """bg_color as NeRFRenderer.run accepts it (renderer_dynamic.py:236-237; train_step passes 1 or a
+        per-pixel random [B,N,3] tensor, trainer.py:484-489): a number goes to the kernel, a tensor is
+        blended outside it as (1 - weights_sum) * bg (differentiable through weights_sum)."""
+        if bg_color is None:
+            return 1.0, None
+        if torch.is_tensor(bg_color):
+            if bg_color.numel() == 1:
+                return float(bg_color), None
+            bg = bg_color.detach().to(device=dev, dtype=torch.float32)
+            return 0.0, (bg.reshape(-1, 3) if bg.numel() == 3 * n else bg.reshape(1, 3))
+        return float(bg_color), None
+
     def _run_train(self, rays_o, rays_d, time, lidar, S, bg_color, perturb, noise):
         self.out_dim = self.out_lidar_color_dim if lidar else self.out_color_dim
         prefix = rays_o.shape[:-1]
         with torch.no_grad():
             o, d, nears, fars, noise = self._rays_setup(rays_o, rays_d, lidar, S, perturb, noise)
             self.prepare(time, lidar)
-        bg = 1.0 if bg_color is None else float(bg_color)
+        bg, bg_t = self._split_bg(bg_color, o.shape[0], o.device)
         params = [getattr(self, n) for n in _param_names(lidar)]
         depth, image, wsum, weights, z_vals = _RenderUniformTrain.apply(self, lidar, o, d, nears, fars, noise, S,
                                                                         bg, *params)
+        if bg_t is not None and not lidar:
+            image = image + (1 - wsum).unsqueeze(-1) * bg_t
         sfx = "_lidar" if lidar else ""
         return {"depth" + sfx: depth.view(*prefix), "image" + sfx: image.view(*prefix, self.out_dim),
                 "weights_sum" + sfx: wsum, "weights": weights, "z_vals": z_vals}
@@ -695,11 +879,13 @@ class NeRFNetwork(nn.Module):
         z_vals = torch.empty(N, S, dtype=torch.float32, device=dev) if return_weights else None
         sbytes = L.nvsf_render_uniform_scratch_bytes(N, S)
         scratch = torch.empty(sbytes, dtype=torch.uint8, device=dev)
-        bg = 1.0 if bg_color is None else float(bg_color)
+        bg, bg_t = self._split_bg(bg_color, N, dev)
         check(L.nvsf_render_uniform(ctypes.byref(self._cfg), ptr(ws), int(lidar), ptr(o), ptr(d), ptr(nears),
                                     ptr(fars), ptr(noise), N, S, bg, ptr(scratch), sbytes, ptr(depth),
                                     ptr(image), ptr(wsum), ptr(weights), ptr(z_vals), stream_ptr()),
               "render_uniform")
+        if bg_t is not None and not lidar:
+            image = image + (1 - wsum).unsqueeze(-1) * bg_t
         sfx = "_lidar" if lidar else ""
         out = {"depth" + sfx: depth.view(*prefix), "image" + sfx: image.view(*prefix, nch),
                "weights_sum" + sfx: wsum}
@@ -707,6 +893,7 @@ class NeRFNetwork(nn.Module):
             out["weights"], out["z_vals"] = weights, z_vals
         return out
 
+    @_lib.device_guard
     def render(self, rays_o, rays_d, time, cal_lidar_color=False, staged=False, max_ray_batch=4096, **kwargs):
         """NeRFRenderer.render (renderer_dynamic.py:267-326).  staged=True returns only depth and
         image like the reference; the whole frame is rendered by one launch pair per

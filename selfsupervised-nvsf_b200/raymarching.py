@@ -28,11 +28,11 @@ _f32 = torch.float32
 
 
 def _fwd(fn):
-    return torch.amp.custom_fwd(fn, device_type="cuda", cast_inputs=_f32)
+    return torch.amp.custom_fwd(_lib.device_guard(fn), device_type="cuda", cast_inputs=_f32)
 
 
 def _bwd(fn):
-    return torch.amp.custom_bwd(fn, device_type="cuda")
+    return torch.amp.custom_bwd(_lib.device_guard(fn), device_type="cuda")
 
 
 def _cuda(t):

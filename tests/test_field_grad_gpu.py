@@ -17,13 +17,12 @@ pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
 S = FC.S
 
-# c_mid: one of its 68 contributing samples (ray 7, first sample, w = 0.99) has a colour-net layer-2
-# pre-activation of 1.5e-5 (layer scale 0.34); its ReLU sign in fp16 differs from the fp32
-# reference's, which moves every gradient of this tiny case by 5-10 % (tools/grad_debug.py c_mid:
-# all other rows agree to 1e-4).  tcnn's fp16 MLPs have the same property.
-CASE_FACTOR = {"c_mid": 8.0}
-RTOL = {"hash_static": 2e-2, "hash_dynamic": 2e-2, "planes": 2e-2, "flow_grid": 5e-2, "flow_mlp": 5e-2,
-        "sigma_net": 2e-2, "intensity_net": 2e-2, "raydrop_net": 2e-2, "color_net": 2e-2}
+# Cases of 256 rays x 64 samples (oracle/make_golden_grad.py): an fp16 ReLU whose sign differs from the
+# fp32 reference's on one sample (round 1's 24-ray cases moved by 5-10 % on such a flip) is one of
+# 16 K contributions here.
+CASE_FACTOR = {}
+RTOL = {"hash_static": 1e-2, "hash_dynamic": 1e-2, "planes": 1e-2, "flow_grid": 2e-2, "flow_mlp": 2e-2,
+        "sigma_net": 1e-2, "intensity_net": 1e-2, "raydrop_net": 1e-2, "color_net": 1e-2}
 
 
 @pytest.fixture(scope="module")

@@ -36,3 +36,37 @@ def test_rgb_loss_and_gradient():
     np.testing.assert_allclose(l.detach().numpy(), 2.0 * (p.detach().numpy() - g.numpy()) ** 2, rtol=1e-6)
     l.sum().backward()
     np.testing.assert_allclose(p.grad.numpy(), 4.0 * (p.detach().numpy() - g.numpy()), rtol=1e-6)
+
+
+# ---- hand-evaluated cases for the remaining terms (trainer.py:237-462) ---------------------------------
+def test_los_loss_by_hand():
+    # one ray, gt depth 0.5, eps 0.1: samples at 0.2 (empty), 0.45 (near), 0.5 (at the surface), 0.9 (empty)
+    z = torch.tensor([[0.2, 0.45, 0.5, 0.9]])
+    w = torch.tensor([[0.1, 0.3, 0.5, 0.05]])
+    gt = torch.tensor([[0.5]])
+    eps, sigma = 0.1, 0.1 / 3
+    distr = [0.0, np.exp(-(0.05 ** 2) / (2 * sigma ** 2)), 1.0, 0.0]   # normalised by its maximum (the peak)
+    empty = 0.1 ** 2 + 0.05 ** 2
+    near = (0.0 - distr[0]) ** 2 + (0.3 - distr[1]) ** 2 + (0.5 - 1.0) ** 2 + 0.0
+    want = 0.1 * empty / 1 + 0.1 * near / 1
+    np.testing.assert_allclose(LO.los_loss(w, z, gt, eps).item(), want, rtol=1e-5)
+
+
+def test_structural_loss_by_hand():
+    # one 2 x 2 patch, scale 1: d = [[1, 3], [2, 7]]; finite differences with the last column / row repeated
+    pred = torch.tensor([[1.0, 3.0, 2.0, 7.0]])
+    gx = np.array([[-2.0, -2.0], [-5.0, -5.0]])
+    gy = np.array([[-1.0, -4.0], [-1.0, -4.0]])
+    out = LO.structural_loss(pred, 2, 2, 1.0, tv_loss=True, spatial_smooth=True, alpha_tv=0.5,
+                                      alpha_spatial=2.0)
+    want = 0.5 * (np.abs(gx) + np.abs(gy)) + 2.0 * (gx ** 2 + gy ** 2)
+    np.testing.assert_allclose(out.numpy().reshape(2, 2), want, rtol=1e-6)
+    # gradient loss, l1, all masks on, gt = 0: alpha * sum(|gx| + |gy|)
+    ones = torch.ones(1, 1, 2, 2)
+    gl = LO.structural_loss(pred, 2, 2, 1.0, gt_depth=torch.zeros(1, 4), gt_raydrop=torch.ones(1, 4, 1),
+                                     grad_mask_x=ones, grad_mask_y=ones, grad_loss=True, alpha_grad=0.1)
+    np.testing.assert_allclose(gl.item(), 0.1 * (np.abs(gx).sum() + np.abs(gy).sum()), rtol=1e-6)
+    # Sobel at the centre of a 3 x 3 ramp d(y, x) = x: gx = 8, gy = 0
+    ramp = torch.tensor([[0.0, 1.0, 2.0] * 3])
+    sx, sy = LO._grads(ramp.reshape(1, 1, 3, 3), True)
+    assert sx[0, 0, 1, 1].item() == 8.0 and sy[0, 0, 1, 1].item() == 0.0
