@@ -103,9 +103,13 @@ def hash_grid(table_flat, levels, D, F, x):
 
 
 def mlp(flat, shapes, x, n_out, fp16_weights=True):
+    """Half-precision MLP as the reference runs it: tcnn FullyFusedMLP (fp16 weights, fp16 activations
+    between layers, fp16 output) or nn.Linear layers under fp16 autocast (trainer.py:1318 with
+    configs/kitti360_1908.txt:23).  Storage points are rounded to fp16, the products accumulate in fp32."""
     w = T._fp16_round(flat) if fp16_weights else flat
     pad = shapes[0][1] - x.shape[1]
     h = Fnn.pad(x, (0, pad), value=1.0) if pad else x   # tcnn pads Network inputs with 1 (tcnn_standin.Network)
+    h = T._fp16_round(h)
     off = 0
     for li, (o, i) in enumerate(shapes):
         W = w[off:off + o * i].view(o, i)
@@ -113,6 +117,7 @@ def mlp(flat, shapes, x, n_out, fp16_weights=True):
         h = h @ W.t()
         if li != len(shapes) - 1:
             h = torch.relu(h)
+        h = T._fp16_round(h)
     return h[:, :n_out]
 
 
@@ -179,7 +184,7 @@ class FieldOracle:
         h = sum(basis[i] * enc[:, :, i * nb:(i + 1) * nb] for i in range(4)).reshape(xn.shape[0], -1)
         hdim = c.hidden
         shapes = [(hdim, h.shape[1]), (hdim, hdim), (6, hdim)]
-        return mlp(self.p["flow_mlp"], shapes, h, 6, fp16_weights=False)
+        return mlp(self.p["flow_mlp"], shapes, h, 6)
 
     def flow(self, x, t):
         xn = (x + self.cfg.bound) / (2 * self.cfg.bound)

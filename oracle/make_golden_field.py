@@ -40,7 +40,8 @@ def main():
                                lidar_max_depth=S.LIDAR_MAX_DEPTH, density_scale=ds).eval()
         ref_import.load_params_into(model, cfg, p)
         tag = f"ds{int(ds)}_"
-        with torch.no_grad():
+        # the reference runs its model under fp16 autocast (configs/kitti360_1908.txt:23, trainer.py:929,1139,1318)
+        with torch.no_grad(), torch.autocast("cpu", dtype=torch.float16):
             if ds == 1.0:
                 for ti, t in enumerate(TIMES):
                     tt = torch.tensor([[t]], dtype=torch.float32)

@@ -29,6 +29,7 @@ CASES = [  # (tag, lidar, time, density_scale, perturb)
     ("l_first", True, 0.0, 1.0, False),
     ("c_last", False, 1.0, 60.0, True),
 ]
+LOSS_SCALE = 4096.0
 SHARED = ("flow_grid", "flow_mlp", "sigma_net", "intensity_net", "raydrop_net", "color_net")
 
 
@@ -43,7 +44,7 @@ def loss_coeffs(seed, n_ch):
 def flat_grads(model, cfg, mod):
     """Reference .grad tensors -> the flat layout of oracle/field_init.py (zeros where None)."""
     def g(p):
-        return (p.grad if p.grad is not None else torch.zeros_like(p)).detach().reshape(-1)
+        return (p.grad / LOSS_SCALE if p.grad is not None else torch.zeros_like(p)).detach().reshape(-1)
 
     he = getattr(model, f"hash_encoder_{mod}")
     out = {"hash_static": g(he.hash_static.params)}
@@ -85,15 +86,18 @@ def main():
         torch.manual_seed(5 + ci)
         noise = torch.rand(N_RAYS, N_STEPS).numpy() if perturb else None
         torch.manual_seed(5 + ci)   # NeRFRenderer.run draws the same torch.rand(N, S) when perturb
-        r = model.render(torch.from_numpy(o)[None], torch.from_numpy(d)[None], torch.tensor([[t]]),
-                         cal_lidar_color=lidar, staged=False, num_steps=N_STEPS, perturb=perturb)
+        # the reference trains under fp16 autocast with a GradScaler (configs/kitti360_1908.txt:23,
+        # trainer.py:119,1318,1332): same here, with a fixed power-of-two loss scale (exact to undo)
+        with torch.autocast("cpu", dtype=torch.float16):
+            r = model.render(torch.from_numpy(o)[None], torch.from_numpy(d)[None], torch.tensor([[t]]),
+                             cal_lidar_color=lidar, staged=False, num_steps=N_STEPS, perturb=perturb)
         sfx = "_lidar" if lidar else ""
         co = loss_coeffs(100 + ci, 2 if lidar else 3)
         loss = ((torch.from_numpy(co["a"]) * r["depth" + sfx].reshape(-1)).sum()
                 + (torch.from_numpy(co["b"]) * r["image" + sfx].reshape(N_RAYS, -1)).sum()
                 + (torch.from_numpy(co["c"]) * r["weights"]).sum()
                 + (torch.from_numpy(co["e"]) * r["weights_sum" + sfx]).sum())
-        loss.backward()
+        (loss * LOSS_SCALE).backward()
         k = f"{tag}_"
         out[k + "o"], out[k + "d"] = o, d
         out[k + "meta"] = np.array([float(lidar), t, ds, float(perturb)], np.float64)

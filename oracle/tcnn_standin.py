@@ -23,7 +23,8 @@ Semantics (tcnn `grid.h`, `frequency.h`, `spherical_harmonics.h`, `fully_fused_m
   SH deg 4   16 real spherical-harmonics polynomials of 2x-1.
   FullyFusedMLP  weights row-major [out, in] per layer, input width padded to a multiple of 16,
              output padded to 16, no biases, ReLU hidden, linear output; fp16
-             weights/activations (here: fp16-rounded weights, fp32 arithmetic).
+             weights/activations (here: weights, inputs and every layer's output rounded to fp16,
+             products accumulated in fp32 — tcnn's fully fused path even accumulates in fp16).
   Network    the torch binding's `tcnn.Network(n_in, n_out, cfg)` is `create_network`, which wraps
              the MLP in a NetworkWithInputEncoding with an "Identity" encoding (tcnn cpp_api.cu);
              tcnn's encodings fill their padded outputs with the constant 1 (identity.h: "data_out(j, i)
@@ -181,9 +182,15 @@ class Network(nn.Module):
         self.params = nn.Parameter(torch.cat(chunks))
 
     def forward(self, x):
+        # tcnn is a native extension: an enclosing torch.autocast region does not change its arithmetic
+        with torch.autocast("cpu", enabled=False):
+            return self._forward(x)
+
+    def _forward(self, x):
         x = x.to(torch.float32)
         pad = self.shapes[0][1] - x.shape[1]
         h = torch.nn.functional.pad(x, (0, pad), value=1.0) if pad else x   # Identity-encoding padding = 1
+        h = _fp16_round(h)                    # the Identity encoding writes network_precision_t = __half
         w_all = _fp16_round(self.params)
         off = 0
         for li, (o, i) in enumerate(self.shapes):
@@ -192,4 +199,5 @@ class Network(nn.Module):
             h = h @ W.t()
             if li != len(self.shapes) - 1:
                 h = torch.relu(h)
+            h = _fp16_round(h)                # activations live in shared memory as __half; the output is __half
         return h[:, :self.n_output_dims]

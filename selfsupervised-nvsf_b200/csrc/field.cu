@@ -294,7 +294,7 @@ k_field_density(const __grid_constant__ nvsf_field_config_t cfg, const __grid_co
         // ---- phase 3: the 120 sigma-net inputs ----
         float fl[6];
 #pragma unroll
-        for (int i = 0; i < 6; ++i) fl[i] = reinterpret_cast<const float*>(xrow + kFlowCol)[i];
+        for (int i = 0; i < 6; ++i) fl[i] = round_f16(reinterpret_cast<const float*>(xrow + kFlowCol)[i]);
         __syncwarp();
         if (flow_out && live) {
 #pragma unroll
@@ -408,7 +408,7 @@ k_field_density(const __grid_constant__ nvsf_field_config_t cfg, const __grid_co
                             const float c0 = o[mt][j][2 * hrow], c1 = o[mt][j][2 * hrow + 1];
                             *reinterpret_cast<uint32_t*>(geo_out + row * kGeo + 8 * j + 2 * tq) =
                                 pack_half2(c0, c1);
-                            if (j == 0 && tq == 0) sigma_out[row] = expf(c0);  // trunc_exp fwd
+                            if (j == 0 && tq == 0) sigma_out[row] = expf(round_f16(c0));  // trunc_exp fwd
                         }
                     }
                 }

@@ -220,6 +220,11 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// The reference's MLP outputs are half-precision tensors (tcnn returns __half; the flow MLP runs under
+// fp16 autocast, configs/kitti360_1908.txt:23 / trainer.py:1318): what leaves an MLP is rounded to fp16
+// before anything else reads it (trunc_exp of the sigma logit, x + flow of the warped queries).
+__device__ __forceinline__ float round_f16(float v) { return __half2float(__float2half_rn(v)); }
+
 __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
     __half2 h = __floats2half2_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&h);

@@ -92,9 +92,9 @@ k_flow_stage(const __grid_constant__ nvsf_field_config_t cfg, const __grid_const
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
             float* r0 = reinterpret_cast<float*>(Xs + (warp * 32 + mt * 16 + gq) * kFld + 32);
-            *reinterpret_cast<float2*>(r0 + 2 * tq) = make_float2(o[mt][0][0], o[mt][0][1]);
+            *reinterpret_cast<float2*>(r0 + 2 * tq) = make_float2(round_f16(o[mt][0][0]), round_f16(o[mt][0][1]));
             float* r1 = reinterpret_cast<float*>(Xs + (warp * 32 + mt * 16 + gq + 8) * kFld + 32);
-            *reinterpret_cast<float2*>(r1 + 2 * tq) = make_float2(o[mt][0][2], o[mt][0][3]);
+            *reinterpret_cast<float2*>(r1 + 2 * tq) = make_float2(round_f16(o[mt][0][2]), round_f16(o[mt][0][3]));
         }
         __syncwarp();
         if (live) {
@@ -583,7 +583,7 @@ k_sigma_stage(const __half* __restrict__ mlp, const __half* __restrict__ feat, s
                         const float c0 = o[mt][j][2 * hrow], c1 = o[mt][j][2 * hrow + 1];
                         *reinterpret_cast<uint32_t*>(geo_out + row * kGeo + 8 * j + 2 * tq) =
                             pack_half2(c0, c1);
-                        if (j == 0 && tq == 0) sigma_out[row] = expf(c0);
+                        if (j == 0 && tq == 0) sigma_out[row] = expf(round_f16(c0));
                     }
                 }
             }

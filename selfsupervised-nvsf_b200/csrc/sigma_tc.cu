@@ -147,7 +147,7 @@ k_sigma_stage_tc(const unsigned char* __restrict__ wimg, const __half* __restric
             tmem_ld_wait();
             const size_t row = row0 + tid;
             if (row < count) {
-                sigma_out[row] = expf(__uint_as_float(v[0]));
+                sigma_out[row] = expf(round_f16(__uint_as_float(v[0])));
                 uint4 a, b;
                 a.x = pack_half2(__uint_as_float(v[0]), __uint_as_float(v[1]));
                 a.y = pack_half2(__uint_as_float(v[2]), __uint_as_float(v[3]));
@@ -411,7 +411,7 @@ k_encode_sigma_tc(const __grid_constant__ nvsf_field_config_t cfg,
             tmem_ld16(tlane, v);
             tmem_ld_wait();
             if (live) {
-                sigma_out[li] = expf(__uint_as_float(v[0]));
+                sigma_out[li] = expf(round_f16(__uint_as_float(v[0])));
                 uint4 a, b;
                 a.x = pack_half2(__uint_as_float(v[0]), __uint_as_float(v[1]));
                 a.y = pack_half2(__uint_as_float(v[2]), __uint_as_float(v[3]));
@@ -558,10 +558,10 @@ k_flow_tc(const __grid_constant__ nvsf_field_config_t cfg, const __grid_constant
             tmem_ld16(tlane, v);
             tmem_ld_wait();
             if (live) {
-                const float4 f0 = make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]),
-                                              __uint_as_float(v[2]), __uint_as_float(v[3]));
-                const float4 f1 = make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]),
-                                              __uint_as_float(v[6]), __uint_as_float(v[7]));
+                const float4 f0 = make_float4(round_f16(__uint_as_float(v[0])), round_f16(__uint_as_float(v[1])),
+                                              round_f16(__uint_as_float(v[2])), round_f16(__uint_as_float(v[3])));
+                const float4 f1 = make_float4(round_f16(__uint_as_float(v[4])), round_f16(__uint_as_float(v[5])),
+                                              round_f16(__uint_as_float(v[6])), round_f16(__uint_as_float(v[7])));
                 if (flow_out) {   // NULL when only the query positions are consumed (fused render path)
                     float4* d = reinterpret_cast<float4*>(flow_out + li * 8);
                     d[0] = f0;

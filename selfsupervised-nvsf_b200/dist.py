@@ -29,6 +29,19 @@ def shard_range(n, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def shard_interleaved(n, rank, world, block):
+    """Ray ids of `rank` when blocks of `block` consecutive rays (e.g. one image row) are dealt round-robin:
+    block j goes to rank j % world.  A contiguous split of a camera frame is unbalanced under occupancy
+    skipping — the upper image rows miss the scene, the lower rows do not (per-rank sample counts max / mean
+    1.48 / 1.62 / 1.66 at 2 / 4 / 8 ranks on the street-shell grid) — while interleaved rows see the same mix.
+    Returns a sorted int64 index tensor; every ray belongs to exactly one rank."""
+    n, block = int(n), max(int(block), 1)
+    nblocks = (n + block - 1) // block
+    mine = torch.arange(rank, nblocks, world, dtype=torch.int64)
+    idx = (mine[:, None] * block + torch.arange(block, dtype=torch.int64)[None, :]).reshape(-1)
+    return idx[idx < n]
+
+
 def shard_rays(rays_o, rays_d, rank, world):
     """Slice [N,3] (or [1,N,3]) ray tensors to this rank's range."""
     n = rays_o.shape[-2]

@@ -711,7 +711,7 @@ class NeRFNetwork(nn.Module):
     @_lib.device_guard
     def run_cuda(self, rays_o, rays_d, time, cal_lidar_color=False, dt_gamma=0.0, bg_color=None, perturb=False,
                  max_steps=1024, T_thresh=1e-4, one_shot=None, noises=None, density_bitfield=None,
-                 step_scale=16, **kwargs):
+                 step_scale=16, sample_capacity=None, **kwargs):
         """Occupancy-skipping render built from the raymarching operators (the `cuda_ray` path of
         torch-ngp's NeRFRenderer.run_cuda, which raymarching.py:171-510 was written for).
 
@@ -724,6 +724,11 @@ class NeRFNetwork(nn.Module):
                        only when most rays terminate early.  n_step is `step_scale` x torch-ngp's
                        max(min(N // n_alive, 8), 1): the composited result does not depend on it (up to
                        fp32 rounding of the restart point), a B200 wants few, large launches.
+        sample_capacity (one_shot only): number of sample rows to provision WITHOUT reading the sample count
+                       back to the host (torch-ngp's `mean_count` protocol, raymarching.py:186-188,272-279): the
+                       frame is rendered with no host synchronisation at all; rays that would not fit are treated
+                       as empty by the operators (raymarching.cu:453,596).  `last_run_cuda_counter` keeps the
+                       device-side count so the caller can verify `samples <= capacity` whenever it likes.
         Outputs use run()'s keys: depth = sum w*t (absolute distance along the ray, not normalised),
         image [.., 2|3], weights_sum.
         LiDAR: near/far are the constants of renderer_dynamic.py:141-146 and no background is added."""
@@ -740,9 +745,11 @@ class NeRFNetwork(nn.Module):
         if noises is None and perturb:
             noises = torch.rand(N, dtype=torch.float32, device=dev)
         if one_shot:
+            cap = int(sample_capacity) if sample_capacity else -1
             xyzs, dirs, deltas, rays = raymarching.march_rays_train(
-                o, d, self.bound, bits, self.cascade, self.grid_size, nears, fars, None, -1, noises is not None,
-                -1, True, dt_gamma, max_steps, noises)
+                o, d, self.bound, bits, self.cascade, self.grid_size, nears, fars, None, cap, noises is not None,
+                -1, cap <= 0, dt_gamma, max_steps, noises)
+            self.last_run_cuda_counter = raymarching.last_step_counter
             sigmas, rgbs = self.forward(xyzs, dirs, time, lidar, out_ld=3)
             if self.density_scale != 1:
                 sigmas = sigmas * self.density_scale

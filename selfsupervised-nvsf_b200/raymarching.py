@@ -25,6 +25,7 @@ from . import _lib
 from ._lib import check, ptr, stream_ptr
 
 _f32 = torch.float32
+last_step_counter = None
 
 
 def _fwd(fn):
@@ -161,6 +162,9 @@ class _march_rays_train(Function):
         alloc = torch.empty if step_counter is None else torch.zeros
         if step_counter is None:
             step_counter = torch.zeros(2, dtype=torch.int32, device=dev)
+        global last_step_counter
+        last_step_counter = step_counter   # device-side (samples, rays) of the latest call, for callers that size
+                                           # M from `mean_count` and check the count later without a sync here
         if noises is None:
             noises = (torch.rand(N, dtype=_f32, device=dev) if perturb
                       else torch.zeros(N, dtype=_f32, device=dev))

@@ -21,11 +21,15 @@ def test_oracle_gradients_match_reference(gold, tag):
     assert abs(loss - float(gold[tag + "_loss"])) < 1e-4 * max(1.0, abs(float(gold[tag + "_loss"])))
     np.testing.assert_allclose(out["depth"].detach().numpy(), gold[tag + "_depth"], rtol=1e-4, atol=1e-6)
     for name in FC.GRAD_NAMES:
-        FC.check_grad_summary(gold, tag, name, g[name], 1e-4, "oracle")
-        # the same table entries are touched; a dense MLP tensor may hold an entry that cancels to an exact
-        # zero in one summation order and not in the other
-        slack = 0 if name in ("hash_static", "hash_dynamic", "planes", "flow_grid") else 2
-        assert abs(int(np.count_nonzero(g[name])) - int(gold[f"{tag}_g_{name}_nnz"])) <= slack, (tag, name)
+        # 5e-4: the golden run evaluates the flow MLP under fp16 autocast (forward and backward GEMMs on fp16
+        # operands), the oracle rounds the same storage points to fp16 but keeps its gradients in fp32
+        FC.check_grad_summary(gold, tag, name, g[name], 5e-4, "oracle")
+        # a dense MLP tensor may hold an entry that cancels to an exact zero in one summation order only
+        # (tables: the same entries are touched, up to a handful whose tiny gradient crosses the fp16 underflow
+        # threshold of the stand-in's half-precision table gradients on one side only)
+        nnz = int(gold[f"{tag}_g_{name}_nnz"])
+        slack = max(2, nnz // 100000)
+        assert abs(int(np.count_nonzero(g[name])) - nnz) <= slack, (tag, name)
 
 
 def test_warped_hash_queries_carry_no_gradient(gold):
