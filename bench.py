@@ -182,6 +182,112 @@ def cpu_render_sample(orc, o, d, t, n_rays):
     return time.perf_counter() - t0, idx, r
 
 
+def cpu_baseline_and_parity(pkg, S, model, cfg_kw, dev, args):
+    """The CPU leg of the bench line, rank 0, outside every timed GPU region.
+
+    cpu_baseline: BASELINE configs[0] — 4096 synthetic LiDAR rays x 128 samples, random-init field, the oracle PORT of
+    the reference's PyTorch path (oracle/field_oracle.py: NeRFRenderer.run -> NeRFNetwork.density / color with the
+    tinycudann stand-in) in fp32 on all host cores: (a) render under no_grad, (b) train step = forward + backward of an
+    L1 depth + MSE intensity / raydrop loss; 2 warm-ups, median of 5 (3 for the train step when one run exceeds 8 s);
+    plus the OpenMP C oracle of the ray-marching operators on the same 4096 rays (street-shell grid).
+    parity: the GPU render of a strided ray sample of the LiDAR frame with TRAINED-style tables (tables U(-1,1), a
+    flow that moves the warped queries: sigma is not ~1 everywhere as with the initialisers) against the oracle."""
+    import numpy as np
+    import torch
+    from oracle import field_init
+    from oracle import raymarching_oracle as RO
+    from oracle.field_oracle import FieldConfig, FieldOracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = FieldConfig(**cfg_kw)
+    params = field_init.make_params(cfg, seed=0, style="init")
+    N0, S0 = 4096, 128
+    o, d = S.lidar_rays(N0, seed=0)
+    to, td = torch.from_numpy(o), torch.from_numpy(d)
+    orc = FieldOracle(cfg, params)
+
+    def render():
+        with torch.no_grad():
+            return orc.run(to, td, 0.5, True, S0)
+
+    def timed(fn, warm, reps, budget_s):
+        ts = []
+        for i in range(warm + reps):
+            t0 = time.perf_counter()
+            fn()
+            dt = time.perf_counter() - t0
+            if i >= warm:
+                ts.append(dt)
+            if i >= warm + 2 and sum(ts) > budget_s:
+                break
+        return float(np.median(ts)), len(ts)
+
+    r_s, r_n = timed(render, 2, 5, 60.0)
+    leaf = {"lidar": {k: v.clone().requires_grad_(True) for k, v in params["lidar"].items()}}
+    for k in ("flow_grid", "flow_mlp", "sigma_net", "intensity_net", "raydrop_net", "color_net"):
+        leaf[k] = params[k].clone().requires_grad_(True)
+    orc_t = FieldOracle(cfg, leaf)
+    gt = torch.rand(N0, 3, generator=torch.Generator().manual_seed(1))
+
+    def train_step():
+        for grp in (leaf["lidar"], leaf):
+            for v in grp.values():
+                if torch.is_tensor(v):
+                    v.grad = None
+        out = orc_t.run(to, td, 0.5, True, S0)
+        loss = ((out["depth"] - gt[:, 2]).abs().sum() + ((out["image"][:, 1] - gt[:, 1]) ** 2).sum()
+                + ((out["image"][:, 0] - gt[:, 0]) ** 2).sum())
+        loss.backward()
+
+    t_s, t_n = timed(train_step, 1, 5, 24.0)
+    # operators: OpenMP C restatement of raymarching.cu on the same rays
+    grid = S.density_grid("shell")
+    bf = S.packbits_np(grid, 0.01)
+    nears = np.full(N0, S.MIN_NEAR_LIDAR, np.float32); fars = np.full(N0, S.LIDAR_MAX_DEPTH, np.float32)
+    noises = np.zeros(N0, np.float32)
+    cnt = int(RO.march_rays_train(o, d, S.BOUND, bf, S.CASCADE, S.GRID_SIZE, nears, fars, noises, dt_gamma=S.DT_GAMMA,
+                                  M=1)[4][0])
+    mr = lambda: RO.march_rays_train(o, d, S.BOUND, bf, S.CASCADE, S.GRID_SIZE, nears, fars, noises, dt_gamma=S.DT_GAMMA,
+                                     M=max(cnt, 1))
+    x_, d_, dl_, ry_, _ = mr()
+    rng = np.random.default_rng(2)
+    sg = np.exp(rng.normal(0, 2, size=max(cnt, 1))).astype(np.float32); cl = rng.random((max(cnt, 1), 3), dtype=np.float32)
+    wsum, dep, img = RO.composite_rays_train_forward(sg, cl, dl_, ry_)
+    ops = {}
+    for name, fn in (("near_far_from_aabb", lambda: RO.near_far_from_aabb(o, d, S.AABB, S.MIN_NEAR)),
+                     ("march_rays_train", mr),
+                     ("composite_rays_train_forward", lambda: RO.composite_rays_train_forward(sg, cl, dl_, ry_)),
+                     ("composite_rays_train_backward",
+                      lambda: RO.composite_rays_train_backward(np.ones(N0, np.float32), np.ones((N0, 3), np.float32), sg, cl,
+                                                               dl_, ry_, wsum, img)),
+                     ("packbits", lambda: RO.packbits(grid, 0.01))):
+        ops[name] = {"ms": timed(fn, 1, 5, 5.0)[0] * 1e3}
+    ops["samples"] = cnt
+    base = {"value": N0 / r_s, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"BASELINE configs[0]: {N0} LiDAR rays x {S0} samples, random-init field, fp32 torch on {cores} threads; "
+                      f"render = median of {r_n} after 2 warm-ups ({r_s:.2f} s each), train step = median of {t_n} after 1",
+            "render": {"rays_per_s": N0 / r_s, "samples_per_s": N0 * S0 / r_s, "s_per_run": r_s, "runs": r_n},
+            "train_step": {"rays_per_s": N0 / t_s, "samples_per_s": N0 * S0 / t_s, "s_per_run": t_s, "runs": t_n,
+                           "what": "forward + backward of L1 depth + MSE intensity / raydrop"},
+            "operators_c_oracle_openmp": ops}
+    # ---- parity on trained-style tables
+    tparams = field_init.make_params(cfg, seed=0, style="trained")
+    model.load_flat_params(tparams)
+    fo, fd = S.lidar_rays(-1, seed=0)
+    idx = np.arange(500, fo.shape[0], fo.shape[0] // args.parity_rays)[:args.parity_rays]
+    with torch.no_grad():
+        g = model.render(torch.from_numpy(fo).to(dev)[None], torch.from_numpy(fd).to(dev)[None], 31.0 / 63.0,
+                         cal_lidar_color=True, staged=True, num_steps=NUM_STEPS)
+        e = FieldOracle(cfg, tparams).run(torch.from_numpy(fo[idx]), torch.from_numpy(fd[idx]), 31.0 / 63.0, True, NUM_STEPS)
+    gd, gi = g["depth_lidar"][0].cpu().numpy()[idx], g["image_lidar"][0].cpu().numpy()[idx]
+    parity = {"what": f"{len(idx)} strided rays of the 66x1030x{NUM_STEPS} LiDAR frame, trained-style tables, GPU render vs CPU oracle",
+              "max_rel_err": {"depth": float(np.max(np.abs(gd - e["depth"].numpy()) / (np.abs(e["depth"].numpy()) + 1e-6))),
+                              "image": float(np.max(np.abs(gi - e["image"].numpy()) / (np.abs(e["image"].numpy()) + 1e-4)))},
+              "tolerance": 1e-2,
+              "oracle_weights_sum_mean": float(e["weights_sum"].mean()), "oracle_sigma_std": float(e["sigma"].std())}
+    return base, parity
+
+
 def run_reference(args):
     """--impl reference: the reference path on the host cores.  /root/reference and tinycudann do
     not exist on the GPU box, so this times the oracle PORT of that path (oracle/field_oracle.py,
@@ -301,29 +407,112 @@ def bench_train(pkg, S, cfg_kw, dev, rank, world, rays, steps, warmup):
             "includes": "h2d rays, fwd + loss head (+ Chamfer term, LiDAR) + bwd of both modalities, grad all-reduce (N>1), Adam step, table re-pack, d2h loss"}
 
 
-def bench_camera_march(pkg, S, model, dev, rank, world, steps, warmup):
+def op_rooflines(pkg, S, model, dev, o, d, bits, peak_gbs):
+    """Per-kernel roofline entries of the ray-marching operators on this rank's camera rays (north_star:
+    "achieved HBM GB/s against B200 peak for marching ... and compositing"): CUDA-event time of each operator
+    (median of 5, working set > L2) against its ALGORITHMIC bytes (marcher 48 B/ray + 32 B/sample,
+    compositing forward 24 B/sample + 32 B/ray, backward 40 B/sample + 48 B/ray).  ncu --set full of the same
+    kernels: profiles/r02_raymarching_ops_ncu_full.txt."""
+    import numpy as np
+    import torch
+    rm = pkg.raymarching
+    L = pkg._lib.lib()
+    N = o.shape[0]
+    aabb = torch.from_numpy(S.AABB).to(dev)
+    nears, fars = rm.near_far_from_aabb(o, d, aabb, S.MIN_NEAR)
+
+    def med(fn, reps=5):
+        ts = []
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.median(ts))
+
+    xyzs, dirs, deltas, rays = rm.march_rays_train(o, d, S.BOUND, bits, S.CASCADE, S.GRID_SIZE, nears, fars, None, -1,
+                                                   False, -1, True, S.DT_GAMMA, 1024)
+    M = xyzs.shape[0]
+    ws_bytes = L.nvsf_march_rays_train_workspace_bytes(N)
+    ws = torch.empty(max(ws_bytes, 4), dtype=torch.uint8, device=dev)
+    counter = torch.zeros(2, dtype=torch.int32, device=dev)
+    noises = torch.zeros(N, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+
+    def march():
+        counter.zero_()
+        assert L.nvsf_march_rays_train(o.data_ptr(), d.data_ptr(), bits.data_ptr(), S.BOUND, S.DT_GAMMA, 1024, N, S.CASCADE,
+                                       S.GRID_SIZE, M, nears.data_ptr(), fars.data_ptr(), xyzs.data_ptr(), dirs.data_ptr(),
+                                       deltas.data_ptr(), rays.data_ptr(), counter.data_ptr(), noises.data_ptr(),
+                                       ws.data_ptr(), ws_bytes, st) == 0
+
+    with torch.no_grad():
+        sig, rgb = model.forward(xyzs, dirs, 0.5, False, out_ld=3)       # the field's own sigmas / colours
+    wsum = torch.empty(N, device=dev); dep = torch.empty(N, device=dev); img = torch.empty(N, 3, device=dev)
+    gws = torch.ones(N, device=dev); gim = torch.ones(N, 3, device=dev)
+    gs = torch.zeros(M, device=dev); gr = torch.zeros(M, 3, device=dev)
+
+    def cfwd():
+        assert L.nvsf_composite_rays_train_forward(sig.data_ptr(), rgb.data_ptr(), deltas.data_ptr(), rays.data_ptr(), M, N,
+                                                   1e-4, wsum.data_ptr(), dep.data_ptr(), img.data_ptr(), st) == 0
+
+    def cbwd():
+        assert L.nvsf_composite_rays_train_backward(gws.data_ptr(), gim.data_ptr(), sig.data_ptr(), rgb.data_ptr(),
+                                                    deltas.data_ptr(), rays.data_ptr(), wsum.data_ptr(), img.data_ptr(), M, N,
+                                                    1e-4, gs.data_ptr(), gr.data_ptr(), st) == 0
+
+    def nf():
+        assert L.nvsf_near_far_from_aabb(o.data_ptr(), d.data_ptr(), aabb.data_ptr(), N, S.MIN_NEAR, nears.data_ptr(),
+                                         fars.data_ptr(), st) == 0
+
+    out = {}
+    for name, fn, nbytes in (("near_far_from_aabb", nf, 32 * N), ("march_rays_train", march, 48 * N + 32 * M),
+                             ("composite_rays_train_forward", cfwd, 24 * M + 32 * N),
+                             ("composite_rays_train_backward", cbwd, 40 * M + 48 * N)):
+        fn()
+        ms = med(fn)
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        out[name] = {"bound": "hbm", "ms": ms, "algorithmic_bytes": int(nbytes), "achieved": gbs, "peak": peak_gbs,
+                     "unit": "GB/s", "frac": gbs / peak_gbs}
+    out["rays"], out["samples"] = N, M
+    out["note"] = ("this rank's rays of the 376x1408 frame on the street-shell grid; sigmas / colours are the field's own "
+                   "(early termination at T < 1e-4 as in training); launch latency included (CUDA events around the C-ABI call)")
+    return out
+
+
+def bench_camera_march(pkg, S, model, dev, rank, world, steps, warmup, peak_gbs):
     """BASELINE configs[3]: camera novel-view render 376x1408 RGB with occupancy-grid skipping, ONE
-    frame whose rays are sharded across the ranks (contiguous ray ranges, dist.shard_range; no
-    collective).  Per step through the public API: pinned host rays of this rank's shard -> device,
-    NeRFNetwork.run_cuda (near_far -> march_rays_train -> density -> color heads ->
-    composite_rays_train) against a synthetic street-shell occupancy bitfield, image -> host.
-    value = frame rays / max-over-ranks time ("strong")."""
+    frame whose rays are sharded across the ranks — image ROWS dealt round-robin (dist.shard_interleaved:
+    a contiguous split is unbalanced, the upper rows miss the scene) — with no collective.  Per step through
+    the public API: pinned host rays of this rank's shard -> device, NeRFNetwork.run_cuda (near_far ->
+    march_rays_train -> density -> color heads -> composite_rays_train) against a synthetic street-shell
+    occupancy bitfield, image -> host.  No host synchronisation inside a frame: the sample rows are
+    provisioned from the count of the warm-up frame (`sample_capacity`, torch-ngp's mean_count protocol) and
+    the device-side count is checked after the timed region.  value = frame rays / max-over-ranks time
+    ("strong")."""
     import numpy as np
     import torch
     import torch.distributed as dist
     o, d = S.camera_rays(-1, seed=0)
     n_all = o.shape[0]
-    lo, hi = pkg.dist.shard_range(n_all, rank, world)
-    o_pin = torch.from_numpy(np.ascontiguousarray(o[lo:hi]))[None].pin_memory()
-    d_pin = torch.from_numpy(np.ascontiguousarray(d[lo:hi]))[None].pin_memory()
-    img_h = torch.empty(1, hi - lo, 3).pin_memory()
+    idx = pkg.dist.shard_interleaved(n_all, rank, world, S.CAM_W).numpy()
+    n_mine = idx.shape[0]
+    o_pin = torch.from_numpy(np.ascontiguousarray(o[idx]))[None].pin_memory()
+    d_pin = torch.from_numpy(np.ascontiguousarray(d[idx]))[None].pin_memory()
+    img_h = torch.empty(1, n_mine, 3).pin_memory()
     bits = torch.from_numpy(S.packbits_np(S.density_grid("shell"), 0.01)).to(dev)
     t = torch.tensor([[0.5]], device=dev)
+    # warm-up frame with the exact (synchronising) path learns the sample count of this shard
+    model.run_cuda(o_pin.to(dev), d_pin.to(dev), t, cal_lidar_color=False, dt_gamma=S.DT_GAMMA, T_thresh=1e-2,
+                   density_bitfield=bits, one_shot=True)
+    my_samples = int(model.last_run_cuda_samples)
+    capacity = (int(my_samples * 1.02) + 127) // 128 * 128
+    counters = []
 
     def step():
         ro, rd = o_pin.to(dev, non_blocking=True), d_pin.to(dev, non_blocking=True)
         r = model.run_cuda(ro, rd, t, cal_lidar_color=False, dt_gamma=S.DT_GAMMA, T_thresh=1e-2,
-                           density_bitfield=bits, one_shot=True)
+                           density_bitfield=bits, one_shot=True, sample_capacity=capacity)
+        counters.append(model.last_run_cuda_counter)
         img_h.copy_(r["image"], non_blocking=True)
 
     def barrier():
@@ -342,18 +531,27 @@ def bench_camera_march(pkg, S, model, dev, rank, world, steps, warmup):
     e1.record()
     barrier()
     ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
-    tm = torch.tensor([ms, float(model.last_run_cuda_samples)], device=dev)
+    seen = max(int(c[0].item()) for c in counters[-steps:])      # device-side counts, read after the timed region
+    if seen > capacity:
+        raise RuntimeError(f"camera frame: {seen} samples exceed the provisioned {capacity}")
+    tm = torch.tensor([ms, float(my_samples)], device=dev)
     if world > 1:
         mx = tm.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         dist.all_reduce(tm, op=dist.ReduceOp.SUM)
-        ms, samples = float(mx[0]), int(tm[1])
+        ms, samples, smax = float(mx[0]), int(tm[1]), float(mx[1])
     else:
-        samples = int(tm[1])
-    return {"value": n_all * steps / (ms * 1e-3), "unit": "rays/s", "ms_per_frame": ms / steps, "rays": n_all,
-            "samples": samples, "steps": steps, "scaling": "strong", "occupancy_grid": "synthetic street shell, 2x128^3",
-            "includes": "h2d rays of the shard, near_far, march (count+scan+write), density, colour heads, "
-                        "compositing, d2h image; one host read of the sample count per frame"}
+        samples, smax = int(tm[1]), float(tm[1])
+    out = {"value": n_all * steps / (ms * 1e-3), "unit": "rays/s", "ms_per_frame": ms / steps, "rays": n_all,
+           "samples": samples, "steps": steps, "scaling": "strong", "occupancy_grid": "synthetic street shell, 2x128^3",
+           "sharding": f"image rows round-robin over {world} rank(s)",
+           "samples_per_rank_max_over_mean": smax / (samples / world),
+           "includes": "h2d rays of the shard, near_far, march (count+scan+write), density, colour heads, "
+                       "compositing, d2h image; no host synchronisation inside a frame (sample rows provisioned "
+                       "from the warm-up frame's count + 2 %, device-side count verified after the timed region)"}
+    if rank == 0:
+        out["operators"] = op_rooflines(pkg, S, model, dev, o_pin[0].to(dev), d_pin[0].to(dev), bits, peak_gbs)
+    return out
 
 
 def main():
@@ -363,7 +561,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ref-rays", type=int, default=512, help="rays per step of the CPU reference arm")
-    ap.add_argument("--cpu-rays", type=int, default=2048, help="rays of the cpu_baseline sample")
+    ap.add_argument("--parity-rays", type=int, default=128, help="rays of the in-bench parity check against the oracle")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the train_step sub-benchmarks")
     ap.add_argument("--no-march", action="store_true", help="skip the camera occupancy-skipping render sub-benchmark")
@@ -500,7 +698,8 @@ def main():
     del scratch
     torch.cuda.empty_cache()
     if not args.no_march:
-        train["camera_march_render"] = bench_camera_march(pkg, S, model, dev, rank, world, args.train_steps, 3)
+        train["camera_march_render"] = bench_camera_march(pkg, S, model, dev, rank, world, args.train_steps, 3,
+                                                          float(peaks()[0]["hbm_gbs"]))
     if not args.no_train:
         train["train_step"] = bench_train(pkg, S, cfg_kw, dev, rank, world, 4096, args.train_steps, 3)
         if world > 1:
@@ -522,14 +721,61 @@ def main():
     top_bytes, top_kernel = table[top]
     top_launch_ms = stage_step_ms[top] * args.steps / n_launch   # average duration of one launch of it
     samples_per_launch = n_samples * args.steps / n_launch
-    achieved = top_bytes * samples_per_launch / (top_launch_ms * 1e-3) / 1e9
-    traffic, limiter = None, None
+    ncu = {}
     tr_path = os.path.join(ROOT, "profiles", "dominant_stage_ncu.json")
     if os.path.exists(tr_path):   # from the committed ncu --set full capture of this command
-        tr = json.load(open(tr_path)).get(top_kernel, {})
-        traffic, limiter = tr.get("dram_bytes_per_launch"), tr.get("limiter")
+        ncu = json.load(open(tr_path))
+    hbm_peak = float(pk["hbm_gbs"])
+
+    def stage_entry(kernel, ms_step, alg_bytes_per_sample):
+        """One kernel against the HBM roof.  `achieved` is the kernel's MEASURED DRAM traffic (ncu dram__bytes_read.sum
+        + dram__bytes_write.sum per sample of the committed capture, scaled to this launch) over its live CUDA-event
+        duration: the tables are L2 / shared-memory resident, so the algorithmic gather bytes are not HBM bytes and are
+        reported apart, never as a fraction of the HBM peak.  `limiter` names the unit that does bound the kernel, with
+        the ncu counters it was read from."""
+        k = ncu.get(kernel, {})
+        e = {"kernel": kernel, "ms_per_step": ms_step, "bound": "hbm", "peak": hbm_peak, "unit": "GB/s"}
+        per_sample = k.get("dram_bytes_per_sample")
+        if per_sample is not None and ms_step > 0.05:
+            traffic = per_sample * samples_per_launch
+            e["traffic"] = traffic
+            e["achieved"] = traffic * (n_launch / args.steps) / (ms_step * 1e-3) / 1e9
+            e["frac"] = e["achieved"] / hbm_peak
+        else:
+            e["traffic"], e["achieved"], e["frac"] = None, None, None
+        e["algorithmic"] = {"bytes_per_sample": alg_bytes_per_sample,
+                            "gbs": (alg_bytes_per_sample * n_samples / (ms_step * 1e-3) / 1e9 if ms_step > 0.05 else None),
+                            "note": "table gathers served from L2 / shared memory; not HBM traffic"}
+        e["limiter"] = k.get("limiter")
+        e["ncu"] = {m: k.get(m) for m in ("l1tex_pct", "lts_pct", "dram_pct", "ipc", "occupancy_pct", "source") if m in k}
+        return e
+
+    stages = {k: stage_entry(table[k][1], stage_step_ms[k], table[k][0]) for k in table if table[k][1] != "-"}
     kernels_per_chunk = sum(1 for b, k in table.values() if k != "-")
     tensor_peak = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops", 1590.0)))
+    heads_kernel = "k_composite_tc" if int(L.nvsf_get_option(b"heads_tc")) else "k_render_composite"
+    roof = dict(stages[top])
+    roof.update({"density_mode": mode, "peak_source": pk_kind, "samples_per_launch": samples_per_launch,
+                 "launch_ms": top_launch_ms, "launches_per_step": n_launch / args.steps,
+                 "share_of_step": stage_step_ms[top] / (ms_total / args.steps),
+                 "traffic_source": ncu.get("source"),
+                 "survey_bytes_per_sample": SURVEY_BYTES_PER_SAMPLE,
+                 "stages": stages,
+                 "heads": {"bound": "tensor", "kernel": heads_kernel,
+                           "ms_per_step": comp_ms, "flop_per_sample": HEADS_FLOP_PER_SAMPLE,
+                           "executed_flop_per_sample": HEADS_EXECUTED_FLOP_PER_SAMPLE,
+                           "achieved": HEADS_FLOP_PER_SAMPLE * n_samples / (comp_ms * 1e-3) / 1e12,
+                           "achieved_executed": HEADS_EXECUTED_FLOP_PER_SAMPLE * n_samples / (comp_ms * 1e-3) / 1e12,
+                           "peak": tensor_peak, "unit": "TFLOP/s", "peak_kind": "sustained dense bf16 (cuBLAS, measured)",
+                           "frac": HEADS_FLOP_PER_SAMPLE * n_samples / (comp_ms * 1e-3) / 1e12 / tensor_peak,
+                           "frac_executed": HEADS_EXECUTED_FLOP_PER_SAMPLE * n_samples / (comp_ms * 1e-3) / 1e12 / tensor_peak,
+                           "ncu": ncu.get(heads_kernel, {}),
+                           "note": "compositing + intensity / raydrop heads of every sample (all pass the w > 1e-4 mask "
+                                   "with random-init weights); algorithmic flops are SURVEY 8(d)'s 2 nets x 2 (87*64 + "
+                                   "64*64 + 64*1); executed = 2 nets x 2 (16*64 + 64*64 + 64*16): the direction columns "
+                                   "of layer 1 are evaluated once per ray"}})
+    if "camera_march_render" in train and "operators" in train["camera_march_render"]:
+        roof["operators"] = train["camera_march_render"].pop("operators")
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -543,45 +789,11 @@ def main():
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(2 * N * 3 * 4), "d2h_bytes_per_step": int(N * 3 * 4)},
         "gpu_launches": (9 + 1 + kernels_per_chunk * n_launch // args.steps) * args.steps,
-        "roofline": {"bound": "hbm", "kernel": top_kernel, "density_mode": mode, "achieved": achieved,
-                     "peak": pk["hbm_gbs"], "unit": "GB/s",
-                     "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk_kind,
-                     "bytes_per_sample": top_bytes, "survey_bytes_per_sample": SURVEY_BYTES_PER_SAMPLE,
-                     "samples_per_launch": samples_per_launch, "launch_ms": top_launch_ms,
-                     "launches_per_step": n_launch / args.steps,
-                     "share_of_step": stage_step_ms[top] / (ms_total / args.steps),
-                     "limiter": limiter,
-                     "stages": {k: {"kernel": table[k][1], "ms_per_step": stage_step_ms[k], "bytes_per_sample": table[k][0],
-                                    "achieved_gbs": (table[k][0] * n_samples / (stage_step_ms[k] * 1e-3) / 1e9
-                                                     if stage_step_ms[k] > 0.1 else None)} for k in table},
-                     "heads": {"bound": "tensor",
-                               "kernel": "k_composite_tc" if int(L.nvsf_get_option(b"heads_tc")) else "k_render_composite",
-                               "ms_per_step": comp_ms, "flop_per_sample": HEADS_FLOP_PER_SAMPLE,
-                               "executed_flop_per_sample": HEADS_EXECUTED_FLOP_PER_SAMPLE,
-                               "achieved": HEADS_FLOP_PER_SAMPLE * n_samples / (comp_ms * 1e-3) / 1e12,
-                               "achieved_executed": HEADS_EXECUTED_FLOP_PER_SAMPLE * n_samples / (comp_ms * 1e-3) / 1e12,
-                               "peak": tensor_peak, "unit": "TFLOP/s", "peak_kind": "sustained dense bf16 (cuBLAS, measured)",
-                               "frac": HEADS_FLOP_PER_SAMPLE * n_samples / (comp_ms * 1e-3) / 1e12 / tensor_peak,
-                               "note": "compositing + intensity / raydrop heads of every sample (all pass the w > 1e-4 mask "
-                                       "with random-init weights); algorithmic flops are SURVEY 8(d)'s 2 nets x 2 (87*64 + "
-                                       "64*64 + 64*1); executed = 2 nets x 2 (16*64 + 64*64 + 64*16): the direction columns "
-                                       "of layer 1 are evaluated once per ray"},
-                     "note": "algorithmic bytes are table gathers; the 40 MB of fp16 tables are L2 resident, so the "
-                             "achieved figure may exceed the HBM peak while DRAM traffic stays far below it"},
+        "roofline": roof,
     }
     out.update(train)
     if want_cpu:
-        torch.set_num_threads(os.cpu_count() or 1)
-        orc = make_oracle(cfg_kw, params)
-        cpu_render_sample(orc, o_np, d_np, times[-1], 4)  # warm-up
-        dt, idx, r = cpu_render_sample(orc, o_np, d_np, times[-1], args.cpu_rays)
-        g_depth = depth.cpu().numpy()[idx]; g_img = image.cpu().numpy()[idx]
-        err_d = float(np.max(np.abs(g_depth - r["depth"].numpy()) / (np.abs(r["depth"].numpy()) + 1e-6)))
-        err_i = float(np.max(np.abs(g_img - r["image"].numpy()) / (np.abs(r["image"].numpy()) + 1e-6)))
-        out["cpu_baseline"] = {"value": args.cpu_rays / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                               "sample": f"{args.cpu_rays} of {N} rays x {Sn} samples of the last timed frame "
-                                         f"(strided over the frame), {dt:.1f} s",
-                               "parity_max_rel_err": {"depth": err_d, "image": err_i}}
+        out["cpu_baseline"], out["parity"] = cpu_baseline_and_parity(pkg, S, model, cfg_kw, dev, args)
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -482,11 +482,14 @@ int nvsf_patch_grad_masks(const float* pano_depth, uint32_t H, uint32_t W, const
 
 /* structural regularisation of P depth patches of h x w rays (trainer.py:306-462): pred_depth [P,h,w]
  * (= depth_lidar * raydrop mask), and for the gradient loss gt_depth, gt_raydrop, mask_x, mask_y
- * [P,h,w].  loss_map [P,h,w] = the element-wise terms (grad_norm / spatial / tv), grad_loss [P] = each
- * patch's share of `grad_loss.sum()`, g_pred [P,h,w] = d (loss_map.sum() + grad_loss.sum()) / d pred_depth. */
+ * [P,h,w].  Forward pass (g_pred NULL): loss_map [P,h,w] = the element-wise terms (grad_norm / spatial
+ * / tv), grad_loss [P] = each patch's share of `grad_loss.sum()`.  Backward pass (g_pred given; loss_map /
+ * grad_loss may be NULL): g_pred [P,h,w] = sum_i g_map[i] d loss_map[i] / d pred + sum_p g_grad[p]
+ * d grad_loss[p] / d pred for the incoming gradients g_map [P,h,w] / g_grad [P] (NULL = zero). */
 int nvsf_loss_patch(const float* pred_depth, const float* gt_depth, const float* gt_raydrop, const float* mask_x,
                     const float* mask_y, uint32_t P, uint32_t h, uint32_t w, const nvsf_patch_loss_cfg_t* cfg,
-                    float* loss_map, float* grad_loss, float* g_pred, void* stream);
+                    float* loss_map, float* grad_loss, const float* g_map, const float* g_grad, float* g_pred,
+                    void* stream);
 
 /* replaces the reference's Chamfer extension (nvsf/nerf/chamfer3D/chamfer3D.cu; pybind
  * chamfer_cuda.cpp `forward` / `backward`; wrapper dist_chamfer_3D.py:42-95), called by train_step

@@ -253,7 +253,9 @@ __global__ void __launch_bounds__(128)
 k_patch_loss(const float* __restrict__ pred, const float* __restrict__ gt_depth, const float* __restrict__ gt_raydrop,
              const float* __restrict__ mask_x, const float* __restrict__ mask_y, uint32_t h, uint32_t w,
              nvsf_patch_loss_cfg_t c, float* __restrict__ loss_map, float* __restrict__ grad_loss,
-             float* __restrict__ g_pred) {
+             const float* __restrict__ g_map, const float* __restrict__ g_grad, float* __restrict__ g_pred) {
+    // forward pass: loss_map / grad_loss (g_pred == NULL).  backward pass: g_pred = sum_i g_map[i] *
+    // d loss_map[i] / d pred + g_grad[patch] * d grad_loss[patch] / d pred (loss_map / grad_loss == NULL).
     extern __shared__ float sm[];
     const int n = (int)(h * w), H = (int)h, W = (int)w;
     float* d = sm;            // pred / scale
@@ -288,11 +290,13 @@ k_patch_loss(const float* __restrict__ pred, const float* __restrict__ gt_depth,
     const float nx = sqrtf(aa_x) * sqrtf(bb_x), ny = sqrtf(aa_y) * sqrtf(bb_y);
     const float cos_x = ab_x / fmaxf(nx, 1e-8f), cos_y = ab_y / fmaxf(ny, 1e-8f);
     float gsum = 0.f;
+    const float gg = (g_pred && g_grad) ? __ldg(g_grad + blockIdx.x) : 0.f;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const int y = i / W, x = i - y * W;
         const float gx = patch_grad_x(d, H, W, y, x, sobel), gy = patch_grad_y(d, H, W, y, x, sobel);
         const float sx = gx > 0.f ? 1.f : (gx < 0.f ? -1.f : 0.f), sy = gy > 0.f ? 1.f : (gy < 0.f ? -1.f : 0.f);
-        float l = 0.f, dgx = 0.f, dgy = 0.f;
+        float l = 0.f, dgx = 0.f, dgy = 0.f;   // element-wise terms: value and derivative
+        float egx = 0.f, egy = 0.f;            // gradient-loss term: derivative
         if (c.grad_norm_smooth) {    // :338-341
             const float ex = expf(-fabsf(gx)), ey = expf(-fabsf(gy));
             l += c.alpha_grad_norm * (ex + ey);
@@ -313,22 +317,24 @@ k_patch_loss(const float* __restrict__ pred, const float* __restrict__ gt_depth,
             if (c.grad_kind == NVSF_LOSS_COS) {
                 // (1 - cos) expanded to every pixel of the patch, then .sum(): n * (1 - cos) per direction
                 const float ax = gx * mx, bx = tx * mx, ay = gy * my, by = ty * my;
-                if (nx > 1e-8f) dgx -= c.alpha_grad * (float)n * (bx / nx - cos_x * ax / aa_x) * mx;
-                if (ny > 1e-8f) dgy -= c.alpha_grad * (float)n * (by / ny - cos_y * ay / aa_y) * my;
+                if (nx > 1e-8f) egx -= c.alpha_grad * (float)n * (bx / nx - cos_x * ax / aa_x) * mx;
+                if (ny > 1e-8f) egy -= c.alpha_grad * (float)n * (by / ny - cos_y * ay / aa_y) * my;
                 gsum += c.alpha_grad * ((1.f - cos_x) + (1.f - cos_y));
             } else {
                 float lx, ggx, ly, ggy;
                 crit(c.grad_kind, c.grad_param, gx * mx, tx * mx, lx, ggx);
                 crit(c.grad_kind, c.grad_param, gy * my, ty * my, ly, ggy);
                 gsum += c.alpha_grad * (lx + ly);
-                dgx += c.alpha_grad * ggx * mx; dgy += c.alpha_grad * ggy * my;
+                egx += c.alpha_grad * ggx * mx; egy += c.alpha_grad * ggy * my;
             }
         }
-        loss_map[base + i] = l;
-        Gx[i] = dgx; Gy[i] = dgy;
+        if (loss_map) loss_map[base + i] = l;
+        const float gm = (g_pred && g_map) ? __ldg(g_map + base + i) : 0.f;
+        Gx[i] = gm * dgx + gg * egx; Gy[i] = gm * dgy + gg * egy;
     }
     gsum = block_sum(gsum, red);   // also orders the Gx / Gy writes before the gather below
-    if (threadIdx.x == 0) grad_loss[blockIdx.x] = gsum;
+    if (threadIdx.x == 0 && grad_loss) grad_loss[blockIdx.x] = gsum;
+    if (!g_pred) return;
     // adjoint of the gradient stencils: dL/dd(y', x') = sum over the pixels whose gx / gy read d(y', x')
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const int y = i / W, x = i - y * W;
@@ -396,10 +402,12 @@ int nvsf_patch_grad_masks(const float* pano_depth, uint32_t H, uint32_t W, const
 
 int nvsf_loss_patch(const float* pred_depth, const float* gt_depth, const float* gt_raydrop, const float* mask_x,
                     const float* mask_y, uint32_t P, uint32_t h, uint32_t w, const nvsf_patch_loss_cfg_t* cfg,
-                    float* loss_map, float* grad_loss, float* g_pred, void* stream) {
+                    float* loss_map, float* grad_loss, const float* g_map, const float* g_grad, float* g_pred,
+                    void* stream) {
     if (P == 0) return NVSF_OK;
-    if (!pred_depth || !cfg || !loss_map || !grad_loss || !g_pred || h < 2 || w < 2 || !(cfg->scale > 0.f))
-        return NVSF_E_INVALID;
+    if (!pred_depth || !cfg || h < 2 || w < 2 || !(cfg->scale > 0.f)) return NVSF_E_INVALID;
+    if (!g_pred && (!loss_map || !grad_loss)) return NVSF_E_INVALID;   /* forward pass: both outputs */
+    if (g_pred && !g_map && !g_grad) return NVSF_E_INVALID;            /* backward pass: an incoming gradient */
     if (cfg->grad_loss && (!gt_depth || !gt_raydrop || !mask_x || !mask_y)) return NVSF_E_INVALID;
     if (cfg->grad_loss && !(kind_ok(cfg->grad_kind) || cfg->grad_kind == NVSF_LOSS_COS)) return NVSF_E_INVALID;
     const size_t smem = ((size_t)4 * h * w + 32) * sizeof(float);
@@ -411,7 +419,7 @@ int nvsf_loss_patch(const float* pred_depth, const float* gt_depth, const float*
         attr = true;
     }
     k_patch_loss<<<P, 128, smem, (cudaStream_t)stream>>>(pred_depth, gt_depth, gt_raydrop, mask_x, mask_y, h, w,
-                                                        *cfg, loss_map, grad_loss, g_pred);
+                                                        *cfg, loss_map, grad_loss, g_map, g_grad, g_pred);
     return nvsf_launch_status();
 }
 

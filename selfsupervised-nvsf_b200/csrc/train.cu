@@ -600,6 +600,12 @@ k_composite_bwd(const __grid_constant__ nvsf_field_config_t cfg, const float* __
 // encoder backward
 // ------------------------------------------------------------------------------------------------
 int g_enc_bwd_ctas = 2;  // nvsf_set_option("enc_bwd_ctas", 2 | 3)
+// Extra binades of the per-launch power-of-two gradient scale of the fp16 MLP backward kernels (the scaled
+// max |dOut| lands in [2^(3+shift), 2^(4+shift))): the larger the scale, the fewer small rows fall into the fp16
+// subnormals; the bound is overflow of dH = dOut W through the layers (65504).  Options "bwd_shift_flow" /
+// "bwd_shift_sigma" / "bwd_shift_heads".
+int g_shift_flow = 0, g_shift_sigma = 0, g_shift_heads = 2;
+float shift_mul(int s) { return s >= 0 ? 1.0f / (float)(1 << s) : (float)(1 << -s); }
 
 struct GradTables {      // time-collapsed / channel-last gradient tables (scratch, zeroed per call)
     float* pls;          // layout of WsLayout::pls
@@ -1409,7 +1415,7 @@ int nvsf_render_uniform_backward(const nvsf_field_config_t* cfg, const void* wor
         // 2. colour heads backward -> d geo (cols 1..15 of dgeo16), head weight gradients
         int st = NVSF_OK;
         if (g_image) {
-            const float* scale_h = make_scale(0, g_image + (size_t)r0 * nch, (size_t)nr * nch, 0.25f);
+            const float* scale_h = make_scale(0, g_image + (size_t)r0 * nch, (size_t)nr * nch, shift_mul(g_shift_heads));
             for (int h = 0; h < (lidar ? 2 : 1) && st == NVSF_OK; ++h) {
                 const bf16* hm = wimg + kB_Head + h * kB_HeadHalves;
                 MlpGrads MG;
@@ -1437,7 +1443,7 @@ int nvsf_render_uniform_backward(const nvsf_field_config_t* cfg, const void* wor
         {
             SigmaT::Args A{feats + begin * kFeat, dgeo16, dfeat};
             MlpGrads MG{grads->sigma_net, nullptr, grads->sigma_net + H * kFeat};
-            scale_s = make_scale(1, dgeo16, count * 16, 1.0f);
+            scale_s = make_scale(1, dgeo16, count * 16, shift_mul(g_shift_sigma));
             st = launch_mlp_bwd<SigmaT>(A, wimg + kB_SigW1, nullptr, wimg + kB_SigW2, count, MG, scale_s, sms, s);
             if (st != NVSF_OK) return st;
         }
@@ -1455,7 +1461,7 @@ int nvsf_render_uniform_backward(const nvsf_field_config_t* cfg, const void* wor
         {
             FlowT::Args A{flowfeat + begin * kFlowIn, dflow, dflowfeat};
             MlpGrads MG{grads->flow_mlp, grads->flow_mlp + H * kFlowIn, grads->flow_mlp + H * kFlowIn + H * H};
-            const float* scale_f = make_scale(2, dflow, count * 8, 1.0f);
+            const float* scale_f = make_scale(2, dflow, count * 8, shift_mul(g_shift_flow));
             st = launch_mlp_bwd<FlowT>(A, wimg + kB_FlowW1, wimg + kB_FlowW2, wimg + kB_FlowW3, count, MG,
                                        scale_f, sms, s);
             if (st != NVSF_OK) return st;
@@ -1550,7 +1556,7 @@ int nvsf_field_flow_backward(const nvsf_field_config_t* cfg, const void* workspa
     pack(flow_mlp + H * kFlowIn + H * H, H, 6, H, wimg + kB_FlowW3, kLdH);
     unsigned* mx = reinterpret_cast<unsigned*>(scl);
     k_absmax<<<(unsigned)std::min<size_t>(nvsf_div_up((size_t)n * 8, (size_t)1024), (size_t)sms * 4), 256, 0, s>>>(
-        dflow, (size_t)n * 8, 1.0f, mx);
+        dflow, (size_t)n * 8, shift_mul(g_shift_flow), mx);
     k_make_scale<<<1, 1, 0, s>>>(mx, reinterpret_cast<float*>(mx) + 2);
     const float* scale_f = reinterpret_cast<const float*>(mx) + 2;
     FlowT::Args A{reinterpret_cast<const __half*>(flowfeat), dflow, dflowfeat};
@@ -1573,9 +1579,19 @@ int nvsf_train_set_option(const char* name, int value) {
         g_enc_bwd_ctas = value;
         return NVSF_OK;
     }
+    for (auto kv : {std::make_pair("bwd_shift_flow", &g_shift_flow), std::make_pair("bwd_shift_sigma", &g_shift_sigma),
+                    std::make_pair("bwd_shift_heads", &g_shift_heads)})
+        if (std::string(name) == kv.first) {
+            if (value < -4 || value > 10) return NVSF_E_INVALID;
+            *kv.second = value;
+            return NVSF_OK;
+        }
     return nvsf_render_set_option(name, value);
 }
 int nvsf_train_get_option(const char* name) {
     if (std::string(name) == "enc_bwd_ctas") return g_enc_bwd_ctas;
+    if (std::string(name) == "bwd_shift_flow") return g_shift_flow;
+    if (std::string(name) == "bwd_shift_sigma") return g_shift_sigma;
+    if (std::string(name) == "bwd_shift_heads") return g_shift_heads;
     return nvsf_render_get_option(name);
 }

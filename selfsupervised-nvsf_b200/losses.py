@@ -198,20 +198,22 @@ class _PatchLoss(torch.autograd.Function):
         gd, gr, mx, my = opt(gt_depth), opt(gt_raydrop), opt(mask_x), opt(mask_y)
         loss_map = torch.empty(P, 1, h, w, dtype=torch.float32, device=p.device)
         grad_loss = torch.empty(P, dtype=torch.float32, device=p.device)
-        g_pred = torch.empty_like(p)
         check(lib().nvsf_loss_patch(ptr(p), ptr(gd), ptr(gr), ptr(mx), ptr(my), P, h, w, ctypes.byref(cfg),
-                                    ptr(loss_map), ptr(grad_loss), ptr(g_pred), stream_ptr()), "loss_patch")
-        ctx.save_for_backward(g_pred)
-        ctx.shape = pred.shape
+                                    ptr(loss_map), ptr(grad_loss), None, None, None, stream_ptr()), "loss_patch")
+        ctx.tensors = (p, gd, gr, mx, my)
+        ctx.cfg, ctx.shape, ctx.hw = cfg, pred.shape, (P, h, w)
         return loss_map, grad_loss
 
     @staticmethod
     def backward(ctx, g_map, g_grad):
-        # g_pred is the derivative of loss_map.sum() + grad_loss.sum(): the trainer only ever sums both
-        # (trainer.py:545-547), i.e. both incoming gradients are one and the same constant
-        (g_pred,) = ctx.saved_tensors
-        s = g_grad.reshape(-1)[0] if g_grad is not None else g_map.reshape(-1)[0]
-        return (g_pred * s).view(ctx.shape), None, None, None, None, None, None, None
+        p, gd, gr, mx, my = ctx.tensors
+        P, h, w = ctx.hw
+        gm = None if g_map is None else _f32c(g_map).view(P, h, w)
+        gg = None if g_grad is None else _f32c(g_grad).view(P)
+        g_pred = torch.empty_like(p)
+        check(lib().nvsf_loss_patch(ptr(p), ptr(gd), ptr(gr), ptr(mx), ptr(my), P, h, w, ctypes.byref(ctx.cfg),
+                                    None, None, ptr(gm), ptr(gg), ptr(g_pred), stream_ptr()), "loss_patch(backward)")
+        return g_pred.view(ctx.shape), None, None, None, None, None, None, None
 
 
 def structural_loss(pred_depth, patch_h, patch_w, scale, gt_depth=None, gt_raydrop=None, grad_mask_x=None,

@@ -17,12 +17,17 @@ pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
 S = FC.S
 
-# Cases of 256 rays x 64 samples (oracle/make_golden_grad.py): an fp16 ReLU whose sign differs from the
-# fp32 reference's on one sample (round 1's 24-ray cases moved by 5-10 % on such a flip) is one of
-# 16 K contributions here.
-CASE_FACTOR = {}
+# Cases of 256 rays x 64 samples (oracle/make_golden_grad.py).  Tolerance per tensor: 1e-2 (flow: 2e-2), or
+# TWICE the conditioning floor of the reference gradient where that is larger — FC.oracle_grad_floor measures, in
+# the test itself, how far the CPU oracle's own gradient moves when the ray origins change by one fp32 ulp
+# (measured 1-2.6 % on these cases: finest hash level = 32768 cells per unit, fp16 activations).
 RTOL = {"hash_static": 1e-2, "hash_dynamic": 1e-2, "planes": 1e-2, "flow_grid": 2e-2, "flow_mlp": 2e-2,
         "sigma_net": 1e-2, "intensity_net": 1e-2, "raydrop_net": 1e-2, "color_net": 1e-2}
+FLOOR_FACTOR = 2.0
+
+
+def tolerance(case, tag, name):
+    return max(RTOL[name], FLOOR_FACTOR * FC.oracle_grad_floor(case, tag)[name])
 
 
 @pytest.fixture(scope="module")
@@ -71,7 +76,7 @@ def test_parameter_gradients_match_reference(pkg, gold, tag):
     g = grads_of(m, case["lidar"])
     for name in FC.GRAD_NAMES:
         assert np.isfinite(g[name]).all(), name
-        FC.check_grad_summary(gold, tag, name, g[name], RTOL[name] * CASE_FACTOR.get(tag, 1.0), "cuda")
+        FC.check_grad_summary(gold, tag, name, g[name], tolerance(case, tag, name), "cuda")
     # the other modality's encoders are untouched
     other = "camera" if case["lidar"] else "lidar"
     assert getattr(m, f"hash_static_{other}").grad is None
@@ -92,14 +97,16 @@ def test_gradients_match_cpu_oracle_elementwise(pkg, gold):
             assert not g[name].any(), name
             continue
         err = np.linalg.norm(g[name] - ref) / np.linalg.norm(ref)
-        assert err < RTOL[name], (name, err)
+        assert err < tolerance(case, "l_mid", name), (name, err)
         # Sparsity: the stand-in's table gradients pass through an fp16 cast (like tcnn's half
         # atomics), which zeroes entries below 6e-8; this backward keeps them in fp32.  Nothing
         # larger than that may appear where the reference has an exact zero.
         if name in ("hash_static", "hash_dynamic", "flow_grid"):
             extra = g[name][ref == 0]
             assert np.linalg.norm(extra) < 1e-3 * np.linalg.norm(ref) and np.abs(extra).max() < 1e-6, name
-            assert not np.any((ref != 0) & (g[name] == 0)), name
+            # ... and what the reference has where this backward has an exact zero (rows whose scaled fp16 output
+            # gradient is zero are skipped) is negligible
+            assert np.linalg.norm(ref[g[name] == 0]) < 1e-3 * np.linalg.norm(ref), name
 
 
 def test_backward_is_linear_in_the_output_gradient(pkg, gold):

@@ -57,7 +57,7 @@ def test_lidar_frame_768_samples_vs_oracle(pkg, orc):
     idx = np.arange(331, 67980, 709)                     # 96 rays over all rows and azimuths
     with torch.no_grad():
         e = orc.run(torch.from_numpy(o[idx]), torch.from_numpy(d[idx]), 31.0 / 63.0, True, 768)
-    assert 0.05 < float(e["weights_sum"].mean()) and float(e["sigma"].std()) > 0.1   # a field with structure
+    assert 0.05 < float(e["weights_sum"].mean()) < 0.95 and float(e["sigma"].std()) > 0.01   # not the flat init field
     close(depth[idx], e["depth"].numpy(), 1e-2, 1e-5, "depth")
     close(img[idx], e["image"].numpy(), 1e-2, 1e-4, "image")
     # size-independent property: any sub-range of rays rendered alone gives the same pixels
@@ -112,10 +112,13 @@ def test_camera_frame_march_bit_exact_and_image_vs_oracle(pkg, orc, oracle):
     close(img[idx], e["image"], 1e-2, 1e-4, "image")
 
 
-# relative L2 error allowed per gradient tensor (fp16 GEMM operands in forward and backward; flow receives its
-# gradient only through the coordinate gradient of the warped plane queries, one more fp16 MLP away)
-GRAD_RTOL = {"hash_static": 1e-2, "hash_dynamic": 1e-2, "planes": 1e-2, "flow_grid": 2e-2, "flow_mlp": 2e-2,
-             "sigma_net": 1e-2, "intensity_net": 1e-2, "raydrop_net": 1e-2, "color_net": 1e-2}
+# Relative L2 error allowed per gradient tensor.  The reference gradient of this field is itself only defined to
+# 1-3 %: tests/test_field_grad_gpu.py measures how far the CPU oracle's own gradient moves when the ray origins
+# change by ONE fp32 ulp (FC.oracle_grad_floor: 0.8-2 % for tables and MLPs, up to 2.6 % for the flow tensors — the
+# finest hash level has 32768 cells per unit, every MLP stores fp16 activations) and allows twice that floor; the
+# fixed numbers below are that rule at this test's size, where a second oracle pass would cost minutes.
+GRAD_RTOL = {"hash_static": 3e-2, "hash_dynamic": 3e-2, "planes": 3e-2, "flow_grid": 6e-2, "flow_mlp": 3e-2,
+             "sigma_net": 2e-2, "intensity_net": 2e-2, "raydrop_net": 2e-2, "color_net": 2e-2}
 
 
 @pytest.mark.parametrize("lidar", [True, False])
@@ -157,14 +160,14 @@ def test_train_step_gradients_4096_rays_768_samples(pkg, lidar):
     e = orc.run(torch.from_numpy(o[sub]), torch.from_numpy(d[sub]), t, lidar, Sn, nears, fars, torch.from_numpy(noise[sub]))
     eloss = ((torch.from_numpy(ca) * e["depth"]).sum() + (torch.from_numpy(cb) * e["image"]).sum()
              + (torch.from_numpy(ce) * e["weights_sum"]).sum())
-    eloss.backward()
+    (eloss * FC.LOSS_SCALE).backward()   # GradScaler-like: the oracle's table gradients pass through an fp16 cast
     assert abs(loss.item() - eloss.item()) < 1e-2 * max(1.0, abs(eloss.item()))
     close(host(out["depth" + sfx]).reshape(-1)[sub], e["depth"].detach().numpy(), 1e-2, 1e-5, "depth")
     errs = {}
     for name in FC.GRAD_NAMES:
         p = getattr(m, f"{name}_{mod}" if name in ("hash_static", "hash_dynamic", "planes") else name)
         lp = leaf[mod][name] if name in leaf[mod] else leaf[name]
-        ref = (lp.grad if lp.grad is not None else torch.zeros_like(lp)).numpy().reshape(-1).astype(np.float64)
+        ref = (lp.grad if lp.grad is not None else torch.zeros_like(lp)).numpy().reshape(-1).astype(np.float64) / FC.LOSS_SCALE
         got = np.zeros_like(ref) if p.grad is None else p.grad.detach().cpu().numpy().reshape(-1).astype(np.float64)
         if not ref.any():
             assert not got.any(), name

@@ -89,8 +89,10 @@ def test_structural_loss_matches_oracle(pkg, kw, h, w):
     out.sum().backward()
     assert out.shape == ref.shape
     np.testing.assert_allclose(out.detach().cpu().numpy(), ref.detach().numpy(), rtol=2e-5, atol=1e-6)
+    # atol: autograd's cosine backward leaves cancellation residue of ~1e-5 of the largest entry where the
+    # closed form is exactly zero
     scale = float(p0.grad.abs().max())
-    np.testing.assert_allclose(p1.grad.cpu().numpy(), p0.grad.numpy(), rtol=1e-4, atol=1e-5 * scale)
+    np.testing.assert_allclose(p1.grad.cpu().numpy(), p0.grad.numpy(), rtol=1e-4, atol=1e-4 * scale)
 
 
 # ---- scene-flow loss -----------------------------------------------------------------------------------
@@ -120,8 +122,16 @@ def test_flow_loss_matches_oracle(pkg, t, fwd, bwd):
     params = dict(base, **leaf)
     orc = FieldOracle(FC.oracle_config(), params)
     tt = lambda a: None if a is None else torch.from_numpy(a)
+    # The oracle's table gradients pass through an fp16 cast (as tcnn's do); like the reference's GradScaler
+    # (trainer.py:119,1332) the loss is scaled by a power of two so that they stay out of the fp16 subnormals.
     ref = LO.flow_loss(lambda x: orc.flow(x, t), _cham, tt(pc), tt(pcf), tt(pcb))
-    ref.backward()
+    (ref * FC.LOSS_SCALE).backward()
+    # conditioning floor: the oracle's own gradient when the cloud moves by one fp32 ulp
+    leaf2 = {k: base[k].clone().requires_grad_(True) for k in ("flow_grid", "flow_mlp")}
+    orc2 = FieldOracle(FC.oracle_config(), dict(base, **leaf2))
+    (LO.flow_loss(lambda x: orc2.flow(x, t), _cham, tt(np.nextafter(pc, np.float32(10)).astype(np.float32)), tt(pcf),
+                  tt(pcb)) * FC.LOSS_SCALE).backward()
+    floor = {k: float(torch.linalg.norm(leaf2[k].grad - leaf[k].grad) / torch.linalg.norm(leaf[k].grad)) for k in leaf}
     m = _model(pkg)
     cu = lambda a: None if a is None else torch.from_numpy(a).cuda()
     out = pkg.losses.flow_loss(m, cu(pc), torch.tensor([[t]], device="cuda"), cu(pcf), cu(pcb))
@@ -129,9 +139,9 @@ def test_flow_loss_matches_oracle(pkg, t, fwd, bwd):
     assert abs(out.item() - ref.item()) < 1e-2 * abs(ref.item())
     for name in ("flow_grid", "flow_mlp"):
         got = getattr(m, name).grad.detach().cpu().numpy().reshape(-1).astype(np.float64)
-        want = leaf[name].grad.numpy().reshape(-1).astype(np.float64)
+        want = leaf[name].grad.numpy().reshape(-1).astype(np.float64) / FC.LOSS_SCALE
         err = np.linalg.norm(got - want) / np.linalg.norm(want)
-        assert err < 2e-2, (name, err)
+        assert err < max(2e-2, 2.0 * floor[name]), (name, err, floor)
     # nothing but the flow network receives a gradient
     assert m.sigma_net.grad is None and m.hash_static_lidar.grad is None
 
