@@ -20,10 +20,11 @@ class chamfer_3DFunction(Function):
         b = xyz2.detach().to(dtype=torch.float32).contiguous()
         B, n, m = a.size(0), a.size(1), b.size(1)
         dev = a.device
-        dist1 = torch.zeros(B, n, device=dev)
-        dist2 = torch.zeros(B, m, device=dev)
-        idx1 = torch.zeros(B, n, dtype=torch.int32, device=dev)
-        idx2 = torch.zeros(B, m, dtype=torch.int32, device=dev)
+        # every element is written by the kernels (the reference wrapper zero-fills, dist_chamfer_3D.py:50-55)
+        dist1 = torch.empty(B, n, dtype=torch.float32, device=dev)
+        dist2 = torch.empty(B, m, dtype=torch.float32, device=dev)
+        idx1 = torch.empty(B, n, dtype=torch.int32, device=dev)
+        idx2 = torch.empty(B, m, dtype=torch.int32, device=dev)
         L = lib()
         wb = L.nvsf_chamfer_workspace_bytes(B, n, m)
         ws = torch.empty(max(wb, 8), dtype=torch.uint8, device=dev)

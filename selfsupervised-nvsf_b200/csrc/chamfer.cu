@@ -109,10 +109,12 @@ k_chamfer_grad(const float* __restrict__ a, uint32_t n, const float* __restrict_
 void launch_nn(const float* q, uint32_t n, const float* t, uint32_t m, uint32_t b,
                unsigned long long* keys, int sms, cudaStream_t s) {
     const uint32_t qblocks = nvsf_div_up(n, (uint32_t)kChQueries);
-    const uint32_t tiles = nvsf_div_up(m, (uint32_t)kChTile);
-    // enough target ranges to put ~2 CTAs on every SM, whole tiles each
-    uint32_t splits = std::max(1u, std::min(tiles, (2u * (uint32_t)sms) / std::max(1u, qblocks * b)));
-    const uint32_t per_split = nvsf_div_up(tiles, splits) * kChTile;
+    // enough target ranges to put ~2 CTAs on every SM; ranges are multiples of 128 targets (the trainer's single
+    // batch of 4096 x 4096 points became 8 x 4 = 32 CTAs with whole 1024-target tiles: 0.33 ms against the
+    // reference extension's 0.25 ms; 8 x 32 CTAs now)
+    const uint32_t gran = 128;
+    uint32_t splits = std::max(1u, std::min(nvsf_div_up(m, gran), (2u * (uint32_t)sms) / std::max(1u, qblocks * b)));
+    const uint32_t per_split = nvsf_div_up(nvsf_div_up(m, splits), gran) * gran;
     splits = nvsf_div_up(m, per_split);
     k_chamfer_nn<<<dim3(qblocks, splits, b), kChThreads, 0, s>>>(q, n, t, m, per_split, keys);
 }

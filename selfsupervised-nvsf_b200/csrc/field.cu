@@ -636,6 +636,7 @@ int nvsf_field_density(const nvsf_field_config_t* cfg, const void* workspace, co
 
 static int g_density_mode_value = 2;
 static int g_march_mode_value = 1;
+static int g_composite_mode_value = 2, g_composite_bwd_mode_value = 2;
 int nvsf_set_option(const char* name, int value) {
     if (!name) return NVSF_E_INVALID;
     if (std::string(name) == "density_mode") {
@@ -646,6 +647,16 @@ int nvsf_set_option(const char* name, int value) {
     if (std::string(name) == "march_mode") {
         if (value != 0 && value != 1) return NVSF_E_INVALID;
         g_march_mode_value = value;
+        return NVSF_OK;
+    }
+    if (std::string(name) == "composite_mode") {
+        if (value < 0 || value > 2) return NVSF_E_INVALID;
+        g_composite_mode_value = value;
+        return NVSF_OK;
+    }
+    if (std::string(name) == "composite_bwd_mode") {
+        if (value < 0 || value > 2) return NVSF_E_INVALID;
+        g_composite_bwd_mode_value = value;
         return NVSF_OK;
     }
     if (std::string(name) == "stage_timing") {
@@ -660,6 +671,8 @@ int nvsf_get_option(const char* name) {
     if (!name) return NVSF_E_INVALID;
     if (std::string(name) == "density_mode") return g_density_mode_value;
     if (std::string(name) == "march_mode") return g_march_mode_value;
+    if (std::string(name) == "composite_mode") return g_composite_mode_value;
+    if (std::string(name) == "composite_bwd_mode") return g_composite_bwd_mode_value;
     return nvsf_split_get_option(name);
 }
 
@@ -667,3 +680,5 @@ int nvsf_get_option(const char* name) {
 
 int nvsf_density_mode() { return g_density_mode_value; }
 int nvsf_march_mode() { return g_march_mode_value; }
+int nvsf_composite_mode() { return g_composite_mode_value; }
+int nvsf_composite_bwd_mode() { return g_composite_bwd_mode_value; }

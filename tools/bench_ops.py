@@ -20,6 +20,8 @@ pkg = importlib.import_module("selfsupervised-nvsf_b200")
 rm = pkg.raymarching
 L = pkg._lib.lib()
 C, H, BOUND = S.CASCADE, S.GRID_SIZE, S.BOUND
+DEFAULT_CMODE, DEFAULT_CBMODE = L.nvsf_get_option(b"composite_mode"), L.nvsf_get_option(b"composite_bwd_mode")
+SIG_SCALE = float(os.environ.get("SIG_SCALE", "30"))
 
 
 def load_ref():
@@ -48,6 +50,9 @@ def timeit(fn, iters=10, warm=3):
     ts = []
     for _ in range(iters):
         _flush.zero_()
+        # a spin kernel keeps the device busy while the host queues the call: what the events bracket is device
+        # time, not the host-side launch cost of either binding (ctypes here, pybind for the reference extension)
+        torch.cuda._sleep(200000)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); fn(); b.record(); torch.cuda.synchronize()
         ts.append(a.elapsed_time(b))
@@ -107,7 +112,7 @@ def main():
             res.append(row); print(json.dumps(row), flush=True)
             if M == 0:
                 continue
-            sig, rgb = cases.field_values(M, seed=3); sig *= 30
+            sig, rgb = cases.field_values(M, seed=3); sig *= SIG_SCALE
             t_s, t_c = dev(sig), dev(rgb)
             rm.march_rays_train(t_o, t_d, BOUND, t_bf, C, H, t_n, t_f, None, -1, False, -1, True, S.DT_GAMMA, 1024, t_no)
             rays = r.contiguous()
@@ -119,6 +124,10 @@ def main():
                                                            wsum.data_ptr(), dep.data_ptr(), img.data_ptr(), st) == 0
             t1 = timeit(cf)
             row = dict(op="composite_fwd", kind=kind, fill=fill, N=N, M=M, ms=t1, GBps=(24 * M + 32 * N) / t1 / 1e6)
+            for mode in (0, 1, 2):
+                assert L.nvsf_set_option(b"composite_mode", mode) == 0
+                row[f"mode{mode}_ms"] = timeit(cf)
+            assert L.nvsf_set_option(b"composite_mode", DEFAULT_CMODE) == 0
             if ref is not None:
                 row["ref_ms"] = timeit(lambda: ref.composite_rays_train_forward(t_s, t_c, l, rays, M, N, 1e-4, wsum, dep, img))
             res.append(row); print(json.dumps(row), flush=True)
@@ -131,6 +140,10 @@ def main():
                                                             gr.data_ptr(), st) == 0
             t2 = timeit(cb)
             row = dict(op="composite_bwd", kind=kind, fill=fill, N=N, M=M, ms=t2, GBps=(40 * M + 48 * N) / t2 / 1e6)
+            for mode in (0, 1, 2):
+                assert L.nvsf_set_option(b"composite_bwd_mode", mode) == 0
+                row[f"mode{mode}_ms"] = timeit(cb)
+            assert L.nvsf_set_option(b"composite_bwd_mode", DEFAULT_CBMODE) == 0
             if ref is not None:
                 row["ref_ms"] = timeit(lambda: ref.composite_rays_train_backward(gws, gim, t_s, t_c, l, rays, wsum, img, M, N, 1e-4, gs, gr))
             res.append(row); print(json.dumps(row), flush=True)
