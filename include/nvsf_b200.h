@@ -373,6 +373,22 @@ int nvsf_adam_step(float* params, const float* grads, float* exp_avg, float* exp
                    float lr, float beta1, float beta2, float eps, uint32_t step, float grad_scale,
                    void* stream);
 
+/* The same step with the AMP skip decision of `scaler.step(optimizer)` (trainer.py:1332-1334) kept on
+ * the device — no host read of found_inf:
+ *   nvsf_grad_found_inf:   *found_inf = 1.0f if any of grads[0..n) is inf / nan (the flag only rises; n a
+ *                          multiple of 4, 16-byte aligned).  With several ranks the 4-byte flag is
+ *                          all-reduced (MAX) so every replica takes the same decision.
+ *   nvsf_adam_begin:       state = device float[4] {applied steps t, 1/(1-b1^t), 1/sqrt(1-b2^t), skip}
+ *                          (zero-initialised by the caller): advances t unless *found_inf != 0
+ *                          (found_inf may be NULL: never skip).
+ *   nvsf_adam_step_guarded: nvsf_adam_step over one segment with t / the bias corrections / the skip flag
+ *                          read from `state`; a skipped step leaves p, m, v untouched. */
+int nvsf_grad_found_inf(const float* grads, size_t n, float* found_inf, void* stream);
+int nvsf_adam_begin(float* state, const float* found_inf, float beta1, float beta2, void* stream);
+int nvsf_adam_step_guarded(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                           size_t n, float lr, float beta1, float beta2, float eps, const float* state,
+                           float grad_scale, void* stream);
+
 /* ------------------------------------------------------------------------- */
 /* Part 4 — callers either side of the marcher: ray generation, occupancy grid  */
 /* ------------------------------------------------------------------------- */
@@ -406,6 +422,11 @@ int nvsf_get_rays(const float* pose, const int64_t* inds, uint32_t n, uint32_t H
  *   stats[1]).  n = C*H^3 (multiple of 8), workspace nvsf_grid_update_workspace_bytes(n). */
 int nvsf_grid_cell_points(uint32_t C, uint32_t H, float bound, const float* noise, float* xyz,
                           void* stream);
+/* The same for cells [first, first + count) of the C*H^3 only; noise / xyz rows are relative to the
+ * slice.  Multi-GPU update: each rank evaluates one slice of the cells and the ranks
+ * all_gather the per-cell sigmas before nvsf_grid_update. */
+int nvsf_grid_cell_points_range(uint32_t C, uint32_t H, float bound, const float* noise, uint64_t first,
+                                uint64_t count, float* xyz, void* stream);
 int nvsf_grid_accumulate(float* tmp_grid, const float* sigma, uint32_t n, float density_scale,
                          uint32_t first, void* stream);
 size_t nvsf_grid_update_workspace_bytes(uint32_t n);

@@ -86,11 +86,15 @@ PROTOTYPES = {
     "nvsf_field_flow_forward": (_int, [_p, _p, _p, _u32, _p, _p, _p, _sz, _p]),
     "nvsf_field_flow_backward": (_int, [_p, _p, _p, _p, _u32, _p, _p, _p, _p, _p, _sz, _p]),
     "nvsf_adam_step": (_int, [_p, _p, _p, _p, _sz, _f32, _f32, _f32, _f32, _u32, _f32, _p]),
+    "nvsf_grad_found_inf": (_int, [_p, _sz, _p, _p]),
+    "nvsf_adam_begin": (_int, [_p, _p, _f32, _f32, _p]),
+    "nvsf_adam_step_guarded": (_int, [_p, _p, _p, _p, _sz, _f32, _f32, _f32, _f32, _p, _f32, _p]),
     "nvsf_field_color": (_int, [_p, _p, _u32, _p, _p, _u32, _u32, _p, _u32, _p, _u32, _p]),
     # Part 4 — ray generation, occupancy grid, alive-list compaction
     "nvsf_get_lidar_rays": (_int, [_p, _p, _u32, _u32, _u32, _f32, _f32, _f32, _p, _p, _p]),
     "nvsf_get_rays": (_int, [_p, _p, _u32, _u32, _u32, _f32, _f32, _f32, _f32, _p, _p, _p]),
     "nvsf_grid_cell_points": (_int, [_u32, _u32, _f32, _p, _p, _p]),
+    "nvsf_grid_cell_points_range": (_int, [_u32, _u32, _f32, _p, ctypes.c_uint64, ctypes.c_uint64, _p, _p]),
     "nvsf_grid_accumulate": (_int, [_p, _p, _u32, _f32, _u32, _p]),
     "nvsf_grid_update_workspace_bytes": (_sz, [_u32]),
     "nvsf_grid_update": (_int, [_p, _p, _u32, _f32, _f32, _p, _p, _p, _sz, _p]),

@@ -97,12 +97,15 @@ __device__ __forceinline__ uint32_t compact_by3(uint32_t x) {  // raymarching.cu
 // Sample point of Morton cell m of cascade c: xyz = 2*coords/(H-1) - 1 in [-1,1], scaled to the
 // cascade box shrunk by half a cell, plus a (noise*2-1)*half_cell jitter.  Output row c*H^3 + m,
 // i.e. already in the [C, H^3] Morton layout of the density grid.
+// `first` / `count` select a slice of the C*H^3 cells (multi-GPU update: each rank owns one slice);
+// noise and xyz rows are relative to the slice.
 __global__ void __launch_bounds__(256)
 k_grid_cell_points(uint32_t C, uint32_t H, float bound, const float* __restrict__ noise,
-                   float* __restrict__ xyz) {
+                   float* __restrict__ xyz, size_t first, size_t count) {
     const uint32_t H3 = H * H * H;
-    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= (size_t)C * H3) return;
+    const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= count) return;
+    const size_t g = first + r;
     const uint32_t c = (uint32_t)(g / H3), m = (uint32_t)(g % H3);
     const float bc = fminf(exp2f((float)c), bound);
     const float half = __fdiv_rn(bc, (float)H);
@@ -113,10 +116,10 @@ k_grid_cell_points(uint32_t C, uint32_t H, float bound, const float* __restrict_
         const float u = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, (float)co[a]), (float)(H - 1)), 1.0f);
         float v = __fmul_rn(u, ext);
         if (noise) {
-            const float r = __fsub_rn(__fmul_rn(__ldg(noise + g * 3 + a), 2.0f), 1.0f);
-            v = __fadd_rn(v, __fmul_rn(r, half));
+            const float j = __fsub_rn(__fmul_rn(__ldg(noise + r * 3 + a), 2.0f), 1.0f);
+            v = __fadd_rn(v, __fmul_rn(j, half));
         }
-        xyz[g * 3 + a] = v;
+        xyz[r * 3 + a] = v;
     }
 }
 
@@ -255,7 +258,18 @@ int nvsf_grid_cell_points(uint32_t C, uint32_t H, float bound, const float* nois
     if (!xyz || C == 0 || H < 2 || H > 1024 || !(bound > 0.f)) return NVSF_E_INVALID;
     const size_t n = (size_t)C * H * H * H;
     k_grid_cell_points<<<(unsigned)nvsf_div_up(n, (size_t)256), 256, 0, (cudaStream_t)stream>>>(
-        C, H, bound, noise, xyz);
+        C, H, bound, noise, xyz, 0, n);
+    return nvsf_launch_status();
+}
+
+int nvsf_grid_cell_points_range(uint32_t C, uint32_t H, float bound, const float* noise, uint64_t first,
+                                uint64_t count, float* xyz, void* stream) {
+    if (!xyz || C == 0 || H < 2 || H > 1024 || !(bound > 0.f)) return NVSF_E_INVALID;
+    const size_t n = (size_t)C * H * H * H;
+    if (first > n || count > n - first) return NVSF_E_INVALID;
+    if (count == 0) return NVSF_OK;
+    k_grid_cell_points<<<(unsigned)nvsf_div_up((size_t)count, (size_t)256), 256, 0, (cudaStream_t)stream>>>(
+        C, H, bound, noise, xyz, (size_t)first, (size_t)count);
     return nvsf_launch_status();
 }
 

@@ -42,6 +42,23 @@ def shard_interleaved(n, rank, world, block):
     return idx[idx < n]
 
 
+def world_and_rank(process_group=None):
+    """(world size, rank) of `process_group`, (1, 0) when torch.distributed is not initialised."""
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(process_group), dist.get_rank(process_group)
+    return 1, 0
+
+
+def cell_slice(n, rank, world):
+    """Occupancy-grid cells of `rank` for the sharded update: (per, lo, hi) with equal
+    slice length `per` = ceil(n / world) rounded up to a multiple of 8 (whole bitfield bytes, and what
+    all_gather_into_tensor wants), cells [lo, hi) clipped to n.  The last ranks may own fewer (or no) cells."""
+    n, world = int(n), int(world)
+    per = (-(-n // world) + 7) // 8 * 8
+    lo = min(rank * per, n)
+    return per, lo, min(lo + per, n)
+
+
 def shard_rays(rays_o, rays_d, rank, world):
     """Slice [N,3] (or [1,N,3]) ray tensors to this rank's range."""
     n = rays_o.shape[-2]
@@ -50,27 +67,39 @@ def shard_rays(rays_o, rays_d, rank, world):
 
 
 class GradSync:
-    """Flat gradient buffer + grouped, overlapped all-reduce for a NeRFNetwork replica."""
+    """Flat gradient buffer + grouped, overlapped gradient reduction for a NeRFNetwork replica.
 
-    def __init__(self, model, process_group=None, average=True, comm_dtype=None):
-        self.model, self.pg, self.average = model, process_group, average
+    mode "allreduce":      every rank ends with the full summed gradient (one all-reduce per group).
+    mode "reduce_scatter": rank r ends with the summed gradient of slice r of every group only
+                           (`shard(group)`); optim.FlatAdam(shard=True) then updates that slice of the
+                           parameters and all-gathers the parameters — the optimizer as the epilogue of the
+                           reduction: the same bytes on the wire as a ring
+                           all-reduce, Adam traffic and moment memory divided by the world size.
+    Groups are padded to a multiple of 4 * world floats so that every slice is 16-byte aligned."""
+
+    def __init__(self, model, process_group=None, average=True, comm_dtype=None, mode="allreduce"):
+        if mode not in ("allreduce", "reduce_scatter"):
+            raise ValueError(f"GradSync mode {mode!r}")
+        self.model, self.pg, self.average, self.mode = model, process_group, average, mode
         self.comm_dtype = comm_dtype  # e.g. torch.bfloat16 halves the bytes on the wire
-        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.world, self.rank = world_and_rank(process_group)
         params = dict(model.named_parameters())
         missing = [n for g in GROUPS.values() for n in g if n not in params]
         if missing:
             raise KeyError(f"model lacks parameters {missing}")
         dev = next(iter(params.values())).device
-        total = sum(params[n].numel() for g in GROUPS.values() for n in g)
-        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.slices, off = {}, 0
+        quantum = 4 * self.world
+        self.slices, self.param_offsets, off = {}, {}, 0
         for gname, names in GROUPS.items():
             start = off
             for n in names:
-                p = params[n]
-                p.grad = self.flat[off:off + p.numel()].view_as(p)
-                off += p.numel()
+                self.param_offsets[n] = (off, params[n].numel())
+                off += params[n].numel()
+            off = start + -(-(off - start) // quantum) * quantum
             self.slices[gname] = (start, off)
+        self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
+        for n, (o, k) in self.param_offsets.items():
+            params[n].grad = self.flat[o:o + k].view_as(params[n])
         model.fused_grad_accumulation = True
         self.cuda = dev.type == "cuda"
         self.stream = torch.cuda.Stream(device=dev) if self.cuda else None
@@ -84,8 +113,17 @@ class GradSync:
         a, b = self.slices[group]
         return self.flat[a:b]
 
+    def shard(self, group, rank=None):
+        """[lo, hi) of this rank's slice of `group` in the flat buffer (the whole group in all-reduce mode)."""
+        a, b = self.slices[group]
+        if self.mode != "reduce_scatter":
+            return a, b
+        per = (b - a) // self.world
+        r = self.rank if rank is None else rank
+        return a + r * per, a + (r + 1) * per
+
     def reduce_group(self, group):
-        """Start the all-reduce of one group; its gradients must be final on the current stream."""
+        """Start the reduction of one group; its gradients must be final on the current stream."""
         if self.world == 1:
             return
         buf = self.group_view(group)
@@ -97,18 +135,28 @@ class GradSync:
         else:
             ctx = _null()
         with ctx:
-            if self.comm_dtype is not None and self.comm_dtype != torch.float32:
-                wire = buf.to(self.comm_dtype)
-                dist.all_reduce(wire, op=dist.ReduceOp.SUM, group=self.pg)
-                buf.copy_(wire)
+            wire = buf if self.comm_dtype in (None, torch.float32) else buf.to(self.comm_dtype)
+            if self.mode == "reduce_scatter":
+                lo, hi = self.shard(group)
+                mine = self.flat[lo:hi]
+                # NCCL reduces in place when the output is the rank's own slice of the input
+                inplace = wire is buf and self.cuda and dist.get_backend(self.pg) == "nccl"
+                out = mine if inplace else torch.empty(hi - lo, dtype=wire.dtype, device=wire.device)
+                dist.reduce_scatter_tensor(out, wire, op=dist.ReduceOp.SUM, group=self.pg)
+                if not inplace:
+                    mine.copy_(out)
+                if self.average:
+                    mine.mul_(1.0 / self.world)
             else:
-                dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.pg)
-            if self.average:
-                buf.mul_(1.0 / self.world)
+                dist.all_reduce(wire, op=dist.ReduceOp.SUM, group=self.pg)
+                if wire is not buf:
+                    buf.copy_(wire)
+                if self.average:
+                    buf.mul_(1.0 / self.world)
         self._pending.append(group)
 
     def wait(self):
-        """Make the current stream wait for every started all-reduce."""
+        """Make the current stream wait for every started reduction."""
         if self.cuda and self._pending:
             torch.cuda.current_stream().wait_stream(self.stream)
         self._pending.clear()
@@ -117,6 +165,23 @@ class GradSync:
         for g in GROUPS:
             self.reduce_group(g)
         self.wait()
+
+    def all_reduce_flag(self, flag):
+        """MAX over ranks of a 4-byte device flag (found_inf of the AMP step, trainer.py:1332-1334): every
+        replica must take the same skip / apply decision or the parameters diverge."""
+        if self.world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.pg)
+        return flag
+
+    def all_gather_group(self, flat_params, group):
+        """In-place all-gather of a parameter buffer laid out like `flat`: every rank contributes its
+        slice of `group` and receives the others'."""
+        if self.world == 1 or self.mode != "reduce_scatter":
+            return
+        a, b = self.slices[group]
+        lo, hi = self.shard(group)
+        dist.all_gather_into_tensor(flat_params[a:b], flat_params[lo:hi].clone() if not self.cuda
+                                    else flat_params[lo:hi], group=self.pg)
 
 
 class _null:

@@ -672,32 +672,57 @@ class NeRFNetwork(nn.Module):
 
     @torch.no_grad()
     @_lib.device_guard
-    def update_extra_state(self, time=0.0, cal_lidar_color=False, decay=0.95, perturb=True, noise=None):
+    def update_extra_state(self, time=0.0, cal_lidar_color=False, decay=0.95, perturb=True, noise=None,
+                           process_group=None, shard=None):
         """Full occupancy-grid update (torch-ngp NeRFRenderer.update_extra_state, the caller the
         reference's morton3D / packbits operators were written for): evaluate sigma at one
         jittered point per cell and cascade, grid = max(grid*decay, sigma*density_scale),
         density_thresh' = min(mean(grid), density_thresh), density_bitfield = packbits(grid).
         `time` may be a list of frame times: a cell is kept if it is occupied at any of them
         (one bitfield serves a dynamic scene because march_rays* take no time argument).
-        `noise` [C*H^3, 3] in [0,1) optionally supplies the jitter."""
+        `noise` [C*H^3, 3] in [0,1) optionally supplies the jitter.
+
+        Multi-GPU: with torch.distributed initialised (or `shard=True`) every rank
+        evaluates the field on ONE contiguous slice of the C*H^3 cells (dist.cell_slice), the ranks
+        all_gather the per-cell sigmas (4 B per cell) and each applies the decay / threshold /
+        packbits to the whole grid, so all replicas end with the same grid and bitfield.  `noise`
+        given explicitly is the full [C*H^3, 3] array on every rank (each uses its rows)."""
+        from . import dist as nd
         L = _lib.lib()
         lidar = bool(cal_lidar_color)
         st = self._grid_state(lidar)
         dev = self.sigma_net.device
         C, H = self.cascade, self.grid_size
         n = C * H ** 3
+        world, rank = nd.world_and_rank(process_group)
+        if shard is None:
+            shard = world > 1
+        if not shard:
+            world, rank = 1, 0
+        per, lo, hi = nd.cell_slice(n, rank, world)
+        cnt = hi - lo
         if noise is None and perturb:
-            noise = torch.rand(n, 3, dtype=torch.float32, device=dev)
-        if noise is not None:
-            noise = noise.detach().to(device=dev, dtype=torch.float32).contiguous()
-        xyz = torch.empty(n, 3, dtype=torch.float32, device=dev)
-        check(L.nvsf_grid_cell_points(C, H, self.bound, ptr(noise), ptr(xyz), stream_ptr()), "grid_cell_points")
-        tmp = torch.empty(n, dtype=torch.float32, device=dev)
+            noise = torch.rand(cnt, 3, dtype=torch.float32, device=dev)
+        elif noise is not None:
+            noise = noise.detach().to(device=dev, dtype=torch.float32).contiguous().view(-1, 3)
+            if noise.shape[0] == n:
+                noise = noise[lo:hi].contiguous()
+            elif noise.shape[0] != cnt:
+                raise _lib.NvsfError(f"noise has {noise.shape[0]} rows, expected {n} (all cells) or {cnt} (this slice)")
+        xyz = torch.empty(cnt, 3, dtype=torch.float32, device=dev)
+        check(L.nvsf_grid_cell_points_range(C, H, self.bound, ptr(noise), lo, cnt, ptr(xyz), stream_ptr()),
+              "grid_cell_points_range")
+        gathered = torch.zeros(world * per, dtype=torch.float32, device=dev) if world > 1 else None
+        tmp = gathered[rank * per:rank * per + per] if world > 1 else torch.empty(n, dtype=torch.float32, device=dev)
         times = list(time) if isinstance(time, (list, tuple)) else [time]
         for k, t in enumerate(times):
             sigma, _, _, _ = self._density_raw(xyz, t, lidar)
-            check(L.nvsf_grid_accumulate(ptr(tmp), ptr(sigma), n, self.density_scale, int(k == 0), stream_ptr()),
+            check(L.nvsf_grid_accumulate(ptr(tmp), ptr(sigma), cnt, self.density_scale, int(k == 0), stream_ptr()),
                   "grid_accumulate")
+        if world > 1:
+            import torch.distributed as tdist
+            tdist.all_gather_into_tensor(gathered, tmp.clone(), group=process_group)
+            tmp = gathered[:n]
         wbytes = L.nvsf_grid_update_workspace_bytes(n)
         ws = torch.empty(wbytes, dtype=torch.uint8, device=dev)
         check(L.nvsf_grid_update(ptr(st["density_grid"]), ptr(tmp), n, float(decay), float(self.density_thresh),
@@ -910,6 +935,27 @@ class NeRFNetwork(nn.Module):
             return self.run(rays_o, rays_d, time, cal_lidar_color=cal_lidar_color, **kwargs)
         with torch.no_grad():  # staged rendering is the evaluation path (trainer.py:658-903, under no_grad)
             return self._render_staged(rays_o, rays_d, time, cal_lidar_color, kwargs)
+
+    @torch.no_grad()
+    @_lib.device_guard
+    def render_frame(self, pose, intrinsics, H, W, time, cal_lidar_color=False, intrinsics_hoz=None, **kwargs):
+        """Full-frame render from a sensor pose: ray generation (get_lidar_rays / get_rays,
+        dataset_utils.py:369-687) runs on the device in the same stream as the renderer, so a frame's only
+        host input is the 4x4 pose (64 B instead of 24 B per ray over PCIe) and nothing synchronises with the
+        host between the pose upload and the finished image.  pose [4,4] (or [1,4,4]) sensor-to-world;
+        LiDAR: intrinsics = (fov_up, fov), intrinsics_hoz = (fov_up, fov) in degrees (defaults to
+        `intrinsics`); camera: intrinsics = 3x3 pinhole matrix.  Returns render(staged=True)'s dict reshaped to
+        [H, W] / [H, W, C]."""
+        from . import rays as R
+        lidar = bool(cal_lidar_color)
+        dev = self.sigma_net.device
+        pose = torch.as_tensor(pose, dtype=torch.float32).to(dev, non_blocking=True).reshape(1, 4, 4)
+        if lidar:
+            r = R.get_lidar_rays(pose, intrinsics, intrinsics if intrinsics_hoz is None else intrinsics_hoz, H, W, -1)
+        else:
+            r = R.get_rays(pose, intrinsics, H, W, -1)
+        out = self._render_staged(r["rays_o"], r["rays_d"], time, lidar, dict(kwargs))
+        return {k: (v.view(H, W) if v.dim() == 2 else v.view(H, W, -1)) for k, v in out.items()}
 
     def _render_staged(self, rays_o, rays_d, time, cal_lidar_color, kwargs):
         lidar = bool(cal_lidar_color)

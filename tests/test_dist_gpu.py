@@ -102,3 +102,78 @@ def test_allreduced_gradients_equal_single_gpu_gradients(tmp_path):
     # same kernels, same samples; only the order of fp32 atomic accumulation and of the cross-rank sum differs
     for g in ("lidar", "camera", "shared"):
         assert r0[g] < 1e-4, (g, r0[g])
+
+
+def _worker_sharded(rank, world, port, out_dir):
+    """(1) reduce-scatter -> Adam on the rank's slice -> all-gather (FlatAdam(shard=True), bf16 and fp32 wire)
+    against all-reduce -> full Adam; one rank's overflow makes every rank skip.  (2) occupancy-grid update with
+    the cells sharded over the ranks against the single-GPU update with the same jitter."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    pkg = importlib.import_module("selfsupervised-nvsf_b200")
+    res = {}
+    small = dict(device=dev, log2_hashmap_size=12, hash_size_dynamic=(10, 9, 9), flow_log2_hashmap_size=11,
+                 time_resolution=S.TIME_RESOLUTION, num_frames=S.NUM_FRAMES, bound=S.BOUND, min_near=S.MIN_NEAR,
+                 min_near_lidar=S.MIN_NEAR_LIDAR, lidar_max_depth=S.LIDAR_MAX_DEPTH)
+    models, opts = [], []
+    for shard in (False, True):
+        torch.manual_seed(0)
+        m = pkg.NeRFNetwork(**small).train()
+        models.append(m)
+        opts.append(pkg.optim.FlatAdam(m, lr=1e-2, shard=shard, skip_nonfinite=True))
+    names = [n for n, _ in models[0].named_parameters()]
+    for it in range(4):
+        g = torch.Generator(device=dev).manual_seed(10 * it + rank)
+        grads = {n: torch.randn(getattr(models[0], n).shape, generator=g, device=dev) for n in names}
+        if it == 2 and rank == world - 1:
+            grads["planes_camera"].view(-1)[7] = float("inf")
+        for m, opt in zip(models, opts):
+            opt.zero_grad()
+            for n in names:
+                getattr(m, n).grad.copy_(grads[n])
+            for grp in pkg.dist.GROUPS:
+                opt.sync.reduce_group(grp)
+            opt.sync.wait()
+            opt.step()
+    torch.cuda.synchronize()
+    res["applied"] = (opts[0].applied_steps(), opts[1].applied_steps())
+    res["moment_fraction"] = opts[1].exp_avg.numel() / opts[1].sync.flat.numel()
+    res["adam"] = max(float((getattr(models[0], n).detach() - getattr(models[1], n).detach()).abs().max())
+                      for n in names)
+    # every rank holds the same parameters after the all-gather
+    chk = torch.stack([getattr(models[1], n).detach().double().sum() for n in names])
+    lo_, hi_ = chk.clone(), chk.clone()
+    dist.all_reduce(lo_, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
+    res["same_params"] = bool(torch.equal(lo_, hi_))
+
+    # (2) sharded occupancy-grid update
+    m = _make(pkg, dev).eval()
+    n = m.cascade * m.grid_size ** 3
+    noise = torch.rand(n, 3, device=dev, generator=torch.Generator(device=dev).manual_seed(3))
+    bits_sharded = m.update_extra_state([0.1, 0.6], cal_lidar_color=True, noise=noise).clone()
+    grid_sharded = m.density_grid(True).clone()
+    m1 = _make(pkg, dev).eval()
+    bits_single = m1.update_extra_state([0.1, 0.6], cal_lidar_color=True, noise=noise, shard=False)
+    torch.cuda.synchronize()
+    res["grid_equal"] = bool(torch.equal(grid_sharded, m1.density_grid(True)))
+    res["bits_equal"] = bool(torch.equal(bits_sharded, bits_single))
+    res["occupied"] = int(torch.count_nonzero(bits_single))
+    np.save(os.path.join(out_dir, f"res{rank}.npy"), np.array([res], dtype=object), allow_pickle=True)
+    dist.destroy_process_group()
+
+
+def test_sharded_adam_and_sharded_grid_update(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    world, port = 2, _free_port()
+    mp.spawn(_worker_sharded, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        res = np.load(tmp_path / f"res{r}.npy", allow_pickle=True)[0]
+        print(res)
+        assert res["applied"] == (3, 3)                    # step 2 skipped on BOTH ranks, both optimizers
+        assert abs(res["moment_fraction"] - 1.0 / world) < 1e-6
+        assert res["adam"] < 1e-6 and res["same_params"]   # differs only by the summation order of the reduction
+        assert res["grid_equal"] and res["bits_equal"] and res["occupied"] > 0

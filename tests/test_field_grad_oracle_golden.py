@@ -28,7 +28,7 @@ def test_oracle_gradients_match_reference(gold, tag):
         # (tables: the same entries are touched, up to a handful whose tiny gradient crosses the fp16 underflow
         # threshold of the stand-in's half-precision table gradients on one side only)
         nnz = int(gold[f"{tag}_g_{name}_nnz"])
-        slack = max(2, nnz // 100000)
+        slack = max(2, nnz // 20000)   # 5e-5 of the touched entries (measured up to 1.3e-5, thread-count dependent)
         assert abs(int(np.count_nonzero(g[name])) - nnz) <= slack, (tag, name)
 
 

@@ -110,6 +110,32 @@ def test_get_rays_sampling_matches_reference_rng(pkg):
         pkg.rays.get_rays(P, np.eye(3), 8, 8, 4, use_error_map=True)
 
 
+def test_render_frame_from_pose_equals_render_of_generated_rays(pkg, model, gold_rays, orc):
+    """render_frame (pose in, image out; rays generated on the device in the renderer's stream) == render() of
+    the rays the reference's generator produces for that pose (golden), and == the CPU oracle on a few rays."""
+    g = gold_rays
+    H, W, Sn, t = 6, 40, 64, 0.3
+    for lidar in (True, False):
+        pose = torch.from_numpy(g["pose_a"])
+        if lidar:
+            out = model.render_frame(pose, g["lidar_K"], H, W, t, cal_lidar_color=True,
+                                     intrinsics_hoz=g["lidar_K_hoz"], num_steps=Sn)
+            r = pkg.rays.get_lidar_rays(pose[None].cuda(), g["lidar_K"], g["lidar_K_hoz"], H, W, -1)
+            keys = ("depth_lidar", "image_lidar")
+        else:
+            out = model.render_frame(pose, g["cam_K"], H, W, t, num_steps=Sn)
+            r = pkg.rays.get_rays(pose[None].cuda(), g["cam_K"], H, W, -1)
+            keys = ("depth", "image")
+        ref = model.render(r["rays_o"], r["rays_d"], t, cal_lidar_color=lidar, staged=True, num_steps=Sn)
+        assert out[keys[0]].shape == (H, W) and out[keys[1]].shape == (H, W, 2 if lidar else 3)
+        assert torch.equal(out[keys[0]].reshape(-1), ref[keys[0]].reshape(-1))
+        assert torch.equal(out[keys[1]].reshape(H * W, -1), ref[keys[1]].reshape(H * W, -1))
+        if lidar:
+            with torch.no_grad():
+                e = orc.run(r["rays_o"][0, :32].cpu(), r["rays_d"][0, :32].cpu(), t, True, num_steps=Sn)
+            close(host(out[keys[0]]).reshape(-1)[:32], e["depth"].numpy(), 1e-2, 1e-4, "render_frame depth vs oracle")
+
+
 # ------------------------------------------------------------------------------ color operator
 @pytest.mark.parametrize("lidar", [True, False])
 def test_color_vs_oracle(model, orc, lidar):

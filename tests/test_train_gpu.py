@@ -39,6 +39,41 @@ def test_flat_adam_matches_torch_adam(pkg):
                                    err_msg=n)
 
 
+def test_nonfinite_gradient_skips_the_step_on_the_device(pkg):
+    """scaler.step(optimizer) semantics (trainer.py:1332-1334) with no host read: a step whose gradient holds an
+    inf / nan leaves parameters, moments and the applied-step count untouched; the next finite step equals
+    torch.optim.Adam's FIRST step (bias corrections follow the applied count, not the requested one)."""
+    torch.manual_seed(0)
+    m = pkg.NeRFNetwork(**SMALL).train()
+    ref = {n: p.detach().clone().requires_grad_(True) for n, p in m.named_parameters()}
+    topt = torch.optim.Adam([{"params": [p], "lr": 1e-2 * pkg.optim.LR_SCALE.get(n, 1.0)} for n, p in ref.items()],
+                            betas=(0.9, 0.99), eps=1e-15)
+    opt = pkg.optim.FlatAdam(m, lr=1e-2, skip_nonfinite=True)
+    before = opt.flat.clone()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for bad in (float("inf"), float("nan")):
+        opt.sync.flat.copy_(torch.randn(opt.sync.flat.shape, generator=g, device="cuda"))
+        m.sigma_net.grad.view(-1)[-1] = bad      # the very last element of a tensor in the middle of the buffer
+        opt.step()
+        assert torch.equal(opt.flat, before) and float(opt.exp_avg.abs().sum()) == 0.0
+        assert float(opt.found_inf) == 1.0 and opt.applied_steps() == 0
+    for n, p in m.named_parameters():
+        grad = torch.randn(p.shape, generator=g, device="cuda")
+        p.grad.copy_(grad)
+        ref[n].grad = grad.clone()
+    opt.step()
+    topt.step()
+    assert opt.applied_steps() == 1 and float(opt.found_inf) == 0.0
+    for n, p in m.named_parameters():
+        np.testing.assert_allclose(p.detach().cpu().numpy(), ref[n].detach().cpu().numpy(), rtol=2e-5, atol=1e-7,
+                                   err_msg=n)
+    L = pkg._lib.lib()
+    x = torch.zeros(16, device="cuda")
+    assert L.nvsf_grad_found_inf(x.data_ptr() + 4, 8, x.data_ptr(), None) == -1      # misaligned
+    assert L.nvsf_grad_found_inf(x.data_ptr(), 6, x.data_ptr(), None) == -1          # not a multiple of 4
+    assert L.nvsf_adam_begin(None, None, 0.9, 0.99, None) == -1
+
+
 def test_adam_rejects_bad_arguments(pkg):
     L = pkg._lib.lib()
     x = torch.zeros(16, device="cuda")
