@@ -327,18 +327,13 @@ def run_reference(args):
     }))
 
 
-def bench_train(pkg, S, cfg_kw, dev, rank, world, rays, steps, warmup):
-    """Joint training step (BASELINE configs[2] at 4096+4096 rays, configs[4] at 32768+32768 rays per
-    GPU): per step, pinned host rays -> device, LiDAR render + loss head + Chamfer term + backward, camera
-    render + loss head + backward (NeRFNetwork.render with autograd, 768 samples/ray, perturb=True), gradient
-    all-reduce over NCCL overlapped per group (dist.GradSync), Adam step (optim.FlatAdam), loss
-    read back to the host.  Returns whole-job rays/s from the max-over-ranks device time."""
+def build_train_step(pkg, S, cfg_kw, dev, rank, world, rays, shard=False, comm_dtype=None):
+    """The joint training step of bench_train as a closure (also used by tools/prof_train_timeline.py)."""
     import numpy as np
     import torch
-    import torch.distributed as dist
     torch.manual_seed(0)   # same initial replica on every rank
     model = pkg.NeRFNetwork(device=dev, **cfg_kw).train()
-    opt = pkg.optim.FlatAdam(model, lr=1e-2)
+    opt = pkg.optim.FlatAdam(model, lr=1e-2, shard=shard and world > 1, skip_nonfinite=True, comm_dtype=comm_dtype)
     lo, ld = S.lidar_rays(rays, seed=100 + rank)
     co, cd = S.camera_rays(rays, seed=200 + rank)
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
@@ -374,8 +369,22 @@ def bench_train(pkg, S, cfg_kw, dev, rank, world, rays, steps, warmup):
         opt.sync.reduce_group("camera")
         opt.sync.reduce_group("shared")
         opt.sync.wait()
-        opt.step()
+        opt.step()      # found_inf check (4-byte MAX all-reduce at N > 1) + guarded Adam (+ parameter all-gather)
         loss_h.copy_((l1 + l2).detach().view(1), non_blocking=True)
+
+    return step, model, opt, loss_h
+
+
+def bench_train(pkg, S, cfg_kw, dev, rank, world, rays, steps, warmup, shard=False, comm_dtype=None):
+    """Joint training step (BASELINE configs[2] at 4096+4096 rays, configs[4] at 32768+32768 rays per
+    GPU): per step, pinned host rays -> device, LiDAR render + loss head + Chamfer term + backward, camera
+    render + loss head + backward (NeRFNetwork.render with autograd, 768 samples/ray, perturb=True), gradient
+    reduction over NCCL overlapped per group (dist.GradSync: all-reduce, or reduce-scatter with shard=True),
+    non-finite check + Adam step (optim.FlatAdam; with shard=True on the rank's slice, then the parameter
+    all-gather), loss read back to the host.  Returns whole-job rays/s from the max-over-ranks device time."""
+    import torch
+    import torch.distributed as dist
+    step, model, opt, loss_h = build_train_step(pkg, S, cfg_kw, dev, rank, world, rays, shard, comm_dtype)
 
     def barrier():
         if world > 1:
@@ -404,7 +413,10 @@ def bench_train(pkg, S, cfg_kw, dev, rank, world, rays, steps, warmup):
     return {"value": world * 2 * rays * steps / (ms_max * 1e-3), "unit": "rays/s", "ms_per_step": ms_max / steps,
             "rays_per_gpu": {"lidar": rays, "camera": rays}, "samples_per_ray": NUM_STEPS, "steps": steps,
             "final_loss": float(loss_h.item()), "allreduce_bytes_per_step": grad_bytes if world > 1 else 0,
-            "includes": "h2d rays, fwd + loss head (+ Chamfer term, LiDAR) + bwd of both modalities, grad all-reduce (N>1), Adam step, table re-pack, d2h loss"}
+            "gradient_reduction": ("none (1 rank)" if world == 1 else
+                                   ("reduce-scatter + sharded Adam + parameter all-gather" if shard else "all-reduce + full Adam")
+                                   + (", bf16 gradients on the wire" if comm_dtype is not None else ", fp32 wire")),
+            "includes": "h2d rays, fwd + loss head (+ Chamfer term, LiDAR) + bwd of both modalities, gradient reduction (N>1), device-side non-finite check (4-byte MAX all-reduce at N>1), guarded Adam step, table re-pack, d2h loss"}
 
 
 def op_rooflines(pkg, S, model, dev, o, d, bits, peak_gbs):
@@ -703,8 +715,15 @@ def main():
     if not args.no_train:
         train["train_step"] = bench_train(pkg, S, cfg_kw, dev, rank, world, 4096, args.train_steps, 3)
         if world > 1:
+            # the optimizer as the epilogue of the gradient reduction: reduce-scatter -> Adam on the rank's
+            # slice -> parameter all-gather (fp32 wire, then bf16 gradients on the wire)
+            train["train_step_sharded_adam"] = bench_train(pkg, S, cfg_kw, dev, rank, world, 4096,
+                                                           args.train_steps, 3, shard=True)
+            train["train_step_sharded_adam_bf16_wire"] = bench_train(pkg, S, cfg_kw, dev, rank, world, 4096,
+                                                                     args.train_steps, 3, shard=True,
+                                                                     comm_dtype=torch.bfloat16)
             train["train_step_64k_rays_per_gpu"] = bench_train(pkg, S, cfg_kw, dev, rank, world, 32768,
-                                                               max(args.train_steps // 2, 2), 2)
+                                                               max(args.train_steps // 2, 2), 2, shard=True)
 
     if rank != 0:
         if world > 1:
