@@ -772,7 +772,8 @@ def main():
     stages = {k: stage_entry(table[k][1], stage_step_ms[k], table[k][0]) for k in table if table[k][1] != "-"}
     kernels_per_chunk = sum(1 for b, k in table.values() if k != "-")
     tensor_peak = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops", 1590.0)))
-    heads_kernel = "k_composite_tc" if int(L.nvsf_get_option(b"heads_tc")) else "k_render_composite"
+    heads_kernel = {0: "k_render_composite", 1: "k_composite_tc", 6: "k_composite_ts"}.get(
+        int(L.nvsf_get_option(b"heads_tc")), "k_composite_tc8")
     roof = dict(stages[top])
     roof.update({"density_mode": mode, "peak_source": pk_kind, "samples_per_launch": samples_per_launch,
                  "launch_ms": top_launch_ms, "launches_per_step": n_launch / args.steps,

@@ -650,7 +650,617 @@ k_composite_tc(const __grid_constant__ nvsf_field_config_t cfg, const unsigned c
                      : "memory");
 }
 
-int g_heads_tc = 1;  // nvsf_set_option("heads_tc", 0 | 1): head MLPs of the uniform renderer on tcgen05
+// ---- eight warpgroups per CTA, nets one after the other (option heads_tc = 2) --------------------------
+// k_composite_tc keeps four tile contexts per SM (TMEM: 4 x 128 columns, 512 threads x 123 registers) and
+// ncu shows 49 % of its issue slots empty: 27 % of the warp samples spin on the MMA mbarriers, 17 % wait at
+// warpgroup barriers — the serial issue -> commit -> epilogue chain of a tile is exposed.  This form trades the
+// overlap of the two LiDAR nets inside a warpgroup for twice the warpgroups: a warpgroup owns 64 TMEM columns and
+// ONE operand tile and runs net 0 then net 1 of a tile through them (the geo rows stay in registers and are
+// written into the tile again for net 1), so eight independent chains per SM come from 32 warps instead of 16.
+// The per-ray direction term u[net][n] = W1[n][dir] . enc(d) enters layer 1 through the tensor core as well: the geo
+// operand's column 0 is the constant 1 (tcnn's input padding), so D1 = geo W1g^T + geo U^T with U[n][0] = u[n] and
+// zeros elsewhere adds u to every row of the tile.  U is a per-warpgroup [64][16] fp16 image in the un-swizzled
+// K-major core-matrix layout (8 rows x 16 B contiguous; row groups SBO = 256 B apart, the two K chunks LBO = 128 B
+// apart): 2 KB per net, 64 halves rewritten per ray.  The layer-1 epilogue loses its 64 FADD + 16 LDS per thread.
+constexpr uint32_t kCUImg = 2048;
+__device__ __forceinline__ uint64_t umma_desc_k_noswz(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(lbo >> 4) << 16;
+    d |= (uint64_t)(sbo >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+// 4 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+                 : "r"(taddr)
+                 : "memory");
+}
+
+template <int W>
+constexpr size_t composite_tc8_smem() {
+    return kCOffTiles + (size_t)W * kCTile + W * kCScratchFloats * 4 + (size_t)W * 2 * kCUImg + 8 * W + 16 + 1024;
+}
+
+// H row `t` = fp16(relu(D[:, 0..63] (+ u))) in 16-column steps (64-register budget)
+template <bool ADD_U>
+__device__ __forceinline__ void hidden_to_tile16(uint32_t taddr, const float* __restrict__ u,
+                                                 unsigned char* tile, uint32_t t) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        uint32_t v[16];
+        tmem_ld16(taddr + q * 16, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[8 * h + i]);
+            if (ADD_U) {
+                const float4 ua = *reinterpret_cast<const float4*>(u + q * 16 + 8 * h);
+                const float4 ub = *reinterpret_cast<const float4*>(u + q * 16 + 8 * h + 4);
+                f[0] += ua.x; f[1] += ua.y; f[2] += ua.z; f[3] += ua.w;
+                f[4] += ub.x; f[5] += ub.y; f[6] += ub.z; f[7] += ub.w;
+            }
+            uint4 o;
+            o.x = pack_half2_relu(f[0], f[1]); o.y = pack_half2_relu(f[2], f[3]);
+            o.z = pack_half2_relu(f[4], f[5]); o.w = pack_half2_relu(f[6], f[7]);
+            *reinterpret_cast<uint4*>(tile + swz(t, 2 * q + h)) = o;
+        }
+    }
+}
+
+template <bool LIDAR, int W>
+__global__ void __launch_bounds__(W * kRows, 1)
+k_composite_tc8(const __grid_constant__ nvsf_field_config_t cfg, const unsigned char* __restrict__ wimg,
+                const __half* __restrict__ mlp, const float* __restrict__ rays_d,
+                const float* __restrict__ nears, const float* __restrict__ fars,
+                const float* __restrict__ noise, const float* __restrict__ sigma,
+                const __half* __restrict__ geo, uint32_t N, uint32_t S, float bg_color,
+                float* __restrict__ depth_out, float* __restrict__ image_out, float* __restrict__ ws_out,
+                float* __restrict__ weights_out, float* __restrict__ z_out, float* __restrict__ rgbs_out) {
+    constexpr int NETS = LIDAR ? 2 : 1;
+    constexpr int NDIR = LIDAR ? 72 : 16;
+    constexpr int NCH = LIDAR ? 2 : 3;
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    unsigned char* sm = smem_raw + (base - raw);
+    const uint32_t tid = threadIdx.x, wg = tid >> 7, t = tid & 127u, lane = tid & 31u, wq = (tid >> 5) & 3u;
+    constexpr uint32_t kOffScr = kCOffTiles + W * kCTile;
+    constexpr uint32_t kOffU = kOffScr + W * kCScratchFloats * 4;           // [W][2] U images
+    constexpr uint32_t kOffBarC = kOffU + W * 2 * kCUImg;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + kOffBarC + 8 * W);
+    float* scr = reinterpret_cast<float*>(sm + kOffScr) + wg * kCScratchFloats;
+    float* enc_s = scr;            // [72]
+    float* ptot = scr + 200;       // [4]
+    float* red = scr + 208;        // [4][8]
+    const __half* W1d = reinterpret_cast<const __half*>(sm + kCOffW1d);
+
+    for (uint32_t i = tid; i < kHImgBytes / 16; i += (uint32_t)(W * kRows))
+        reinterpret_cast<uint4*>(sm)[i] = __ldg(reinterpret_cast<const uint4*>(wimg) + i);
+    for (int net = 0; net < NETS; ++net)
+        for (uint32_t i = tid; i < (uint32_t)kHidden * kHeadDirMax / 8; i += (uint32_t)(W * kRows))
+            reinterpret_cast<uint4*>(sm + kCOffW1d)[net * (kHidden * kHeadDirMax / 8) + i] =
+                __ldg(reinterpret_cast<const uint4*>(mlp + kHeadBase + net * kHeadHalves + kHeadW1d) + i);
+    for (uint32_t i = tid; i < (uint32_t)(W * 2 * kCUImg / 16); i += (uint32_t)(W * kRows))
+        reinterpret_cast<uint4*>(sm + kOffU)[i] = make_uint4(0, 0, 0, 0);
+    if (tid < (uint32_t)W) mbar_init(base + kOffBarC + 8 * tid, 1);
+    if (tid < 32) {
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(
+                         smem_u32(tmem_slot)),
+                     "r"((uint32_t)512)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t tcol = tmem + wg * kHidden;
+    const uint32_t tlane = tcol + ((wq * 32u) << 16);
+    const uint32_t tile_a = base + kCOffTiles + wg * kCTile;
+    unsigned char* tileg = sm + kCOffTiles + wg * kCTile;
+    const uint32_t bar = base + kOffBarC + 8 * wg;
+    constexpr uint32_t kIdesc2 = umma_idesc(kRows, kHidden), kIdesc3 = umma_idesc(kRows, 16);
+    const float kexp = cfg.active_sensor ? 2.0f : 1.0f;
+    uint32_t phase = 0;
+
+    for (uint32_t r = blockIdx.x * W + wg; r < N; r += gridDim.x * W) {
+        const float near = __ldg(nears + r), far = __ldg(fars + r);
+        float sg = 0.f;
+        uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0;
+        if (t < S) {
+            const size_t g = (size_t)r * S + t;
+            sg = __ldg(sigma + g);
+            a0 = __ldg(reinterpret_cast<const uint4*>(geo + g * kGeo));
+            a1 = __ldg(reinterpret_cast<const uint4*>(geo + g * kGeo) + 1);
+        }
+        wg_barrier(wg);  // the previous ray's readers of enc / u / red are done
+        {
+            const float dx = __ldg(rays_d + (size_t)r * 3), dy = __ldg(rays_d + (size_t)r * 3 + 1),
+                        dz = __ldg(rays_d + (size_t)r * 3 + 2);
+            if (LIDAR) {
+                if (t < (uint32_t)NDIR) {  // tcnn Frequency, 12 octaves: sin(2^k pi x + (j&1) pi/2), x = (d+1)/2
+                    const int dim = t / 24, oct = (t >> 1) % 12;
+                    const float v = ((dim == 0 ? dx : (dim == 1 ? dy : dz)) + 1.0f) * 0.5f;
+                    enc_s[t] = sinpif(scalbnf(v, oct) + 0.5f * (float)(t & 1));
+                }
+            } else if (t < 16) {
+                enc_s[t] = sh4_term((int)t, dx, dy, dz);
+            }
+        }
+        wg_barrier(wg);
+        if (t < (uint32_t)(NETS * kHidden)) {  // u[net][n] = sum_j W1[n][dir j] * enc[j]
+            const __half* wrow = W1d + (size_t)t * kHeadDirMax;
+            float acc = 0.f;
+            for (int j = 0; j < NDIR; j += 2) {
+                const float2 w = __half22float2(*reinterpret_cast<const __half2*>(wrow + j));
+                acc = fmaf(w.x, enc_s[j], acc);
+                acc = fmaf(w.y, enc_s[j + 1], acc);
+            }
+            // U[net][n][0] = u: row n = (group n / 8, row n % 8) of the core-matrix layout
+            const uint32_t net = t >> 6, n = t & 63u;
+            *reinterpret_cast<__half*>(sm + kOffU + (wg * 2 + net) * kCUImg + (n >> 3) * 256 + (n & 7u) * 16) =
+                __float2half_rn(acc);
+        }
+        float carry = 1.0f, ws = 0.f, dep = 0.f, img[NCH];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) img[c] = 0.f;
+
+        for (uint32_t c0 = 0; c0 < S; c0 += kRows) {
+            const uint32_t i = c0 + t;
+            const bool in = i < S;
+            const size_t g = (size_t)r * S + (in ? i : S - 1);
+            const float z = uniform_z2(near, far, in ? i : S - 1, S, noise, g);
+            float delta;
+            if (i + 1 < S) delta = uniform_z2(near, far, i + 1, S, noise, g + 1) - z;
+            else delta = (far - near) / (float)S;  // renderer_dynamic.py:160,182
+            const float alpha = in ? 1.0f - expf(((-kexp * delta) * cfg.density_scale) * sg) : 0.f;
+            const float v = (1.0f - alpha) + 1e-15f;
+            float incl = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const float o = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= (uint32_t)d) incl *= o;
+            }
+            float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+            if (lane == 0) excl = 1.0f;
+            if (lane == 31) ptot[wq] = incl;
+            wg_barrier(wg);
+            const float p0 = ptot[0], p1 = ptot[1], p2 = ptot[2], p3 = ptot[3];
+            const float pre = wq == 0 ? 1.0f : (wq == 1 ? p0 : (wq == 2 ? p0 * p1 : (p0 * p1) * p2));
+            const float T = (carry * pre) * excl;
+            carry *= ((p0 * p1) * p2) * p3;
+            const float w = in ? alpha * T : 0.f;
+            ws += w;
+            dep = fmaf(w, z, dep);
+            if (weights_out && in) { weights_out[g] = w; z_out[g] = z; }
+            const bool m = w > 1e-4f;  // renderer_dynamic.py:202
+            a0.x = (a0.x & 0xffff0000u) | kOneH;  // col 0: sigma logit -> the constant-1 padding input
+            // one barrier: every thread has read ptot, and the OR of the mask
+            const bool any = wg_any(wg, m);
+            float4 col = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (any) {
+                const float wm = m ? w : 0.f;
+#pragma unroll
+                for (uint32_t net = 0; net < (uint32_t)NETS; ++net) {
+                    // geo rows -> chunks 0, 1 of the tile (for net 1 again: H2 of net 0 has overwritten them; the
+                    // layer-3 MMA that read H2 has committed, see the wait below)
+                    *reinterpret_cast<uint4*>(tileg + swz(t, 0)) = a0;
+                    *reinterpret_cast<uint4*>(tileg + swz(t, 1)) = a1;
+                    fence_async_smem();
+                    tc_fence_before();
+                    wg_barrier(wg);
+                    if (t == 0) {
+                        tc_fence_after();
+                        umma_f16(tcol, umma_desc(tile_a), umma_desc(base + kHOffW1 + net * (kHidden * 128)), kIdesc2, 0u);
+                        umma_f16(tcol, umma_desc(tile_a),
+                                 umma_desc_k_noswz(base + kOffU + (wg * 2 + net) * kCUImg, 128u, 256u), kIdesc2, 1u);
+                        umma_commit(bar);
+                    }
+                    if (net == (uint32_t)NETS - 1) {   // the next tile's rows start travelling
+                        const uint32_t in2 = c0 + kRows + t;
+                        sg = 0.f; a0 = make_uint4(0, 0, 0, 0); a1 = a0;
+                        if (in2 < S) {
+                            const size_t g2 = (size_t)r * S + in2;
+                            sg = __ldg(sigma + g2);
+                            a0 = __ldg(reinterpret_cast<const uint4*>(geo + g2 * kGeo));
+                            a1 = __ldg(reinterpret_cast<const uint4*>(geo + g2 * kGeo) + 1);
+                        }
+                    }
+                    // H1 = relu(D1 + u) -> D2 = H1 W2^T
+                    mbar_wait(bar, phase); phase ^= 1u;
+                    tc_fence_after();
+                    hidden_to_tile16<false>(tlane, nullptr, tileg, t);
+                    fence_async_smem();
+                    tc_fence_before();
+                    wg_barrier(wg);
+                    if (t == 0) {
+                        tc_fence_after();
+#pragma unroll
+                        for (uint32_t k = 0; k < 4; ++k)
+                            umma_f16(tcol, umma_desc(tile_a + k * 32),
+                                     umma_desc(base + kHOffW2 + net * (kHidden * 128) + k * 32), kIdesc2, k);
+                        umma_commit(bar);
+                    }
+                    // H2 = relu(D2) -> D3 = H2 W3^T (16 columns)
+                    mbar_wait(bar, phase); phase ^= 1u;
+                    tc_fence_after();
+                    hidden_to_tile16<false>(tlane, nullptr, tileg, t);
+                    fence_async_smem();
+                    tc_fence_before();
+                    wg_barrier(wg);
+                    if (t == 0) {
+                        tc_fence_after();
+#pragma unroll
+                        for (uint32_t k = 0; k < 4; ++k)
+                            umma_f16(tcol, umma_desc(tile_a + k * 32),
+                                     umma_desc(base + kHOffW3 + net * (16 * 128) + k * 32), kIdesc3, k);
+                        umma_commit(bar);
+                    }
+                    mbar_wait(bar, phase); phase ^= 1u;
+                    tc_fence_after();
+                    uint32_t o[4];
+                    tmem_ld4(tlane, o);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    if (LIDAR) {
+                        // h = [raydrop, intensity] (network_dynamic.py:317): net 0 = intensity -> channel 1
+                        const float sv = sigmoidf_(__uint_as_float(o[0]));
+                        if (net == 0) { img[1] += wm * sv; if (m) col.y = sv; }
+                        else { img[0] += wm * sv; if (m) col.x = sv; }
+                    } else {
+                        const float s0 = sigmoidf_(__uint_as_float(o[0])), s1 = sigmoidf_(__uint_as_float(o[1])),
+                                    s2 = sigmoidf_(__uint_as_float(o[2]));
+                        img[0] += wm * s0; img[1] += wm * s1; img[2] += wm * s2;
+                        if (m) col = make_float4(s0, s1, s2, 0.f);
+                    }
+                }
+            } else {
+                const uint32_t in2 = c0 + kRows + t;
+                sg = 0.f; a0 = make_uint4(0, 0, 0, 0); a1 = a0;
+                if (in2 < S) {
+                    const size_t g2 = (size_t)r * S + in2;
+                    sg = __ldg(sigma + g2);
+                    a0 = __ldg(reinterpret_cast<const uint4*>(geo + g2 * kGeo));
+                    a1 = __ldg(reinterpret_cast<const uint4*>(geo + g2 * kGeo) + 1);
+                }
+            }
+            if (rgbs_out && in) *reinterpret_cast<float4*>(rgbs_out + g * 4) = col;
+        }
+        // ---- reduce over the warpgroup and write the ray ----
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            ws += __shfl_xor_sync(0xffffffffu, ws, d);
+            dep += __shfl_xor_sync(0xffffffffu, dep, d);
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) img[c] += __shfl_xor_sync(0xffffffffu, img[c], d);
+        }
+        if (lane == 0) {
+            red[wq * 8 + 0] = ws; red[wq * 8 + 1] = dep;
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) red[wq * 8 + 2 + c] = img[c];
+        }
+        wg_barrier(wg);
+        if (t == 0) {
+            const float wsum = ((red[0] + red[8]) + red[16]) + red[24];
+            ws_out[r] = wsum;
+            depth_out[r] = ((red[1] + red[9]) + red[17]) + red[25];
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                const float v = ((red[2 + c] + red[10 + c]) + red[18 + c]) + red[26 + c];
+                image_out[(size_t)r * NCH + c] = LIDAR ? v : v + (1.0f - wsum) * bg_color;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (tid < 32)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem),
+                     "r"((uint32_t)512)
+                     : "memory");
+}
+
+// ---- hidden activations as the A operand FROM TENSOR MEMORY (option heads_tc = 6) ----------------------
+// ncu on k_composite_tc8 (profiles/r02_composite_tc8_ncu.txt): l1tex 67 %, tensor pipe 25 %, and neither twice the
+// warpgroups, nor 40 % fewer epilogue instructions, nor half the TMEM reads moved its 2.65 ms: what a tile costs is
+// shared-memory bandwidth — 16 KB of fp16 activations written per layer (STS) and the MMA reading its A operand
+// back (M128 x K16 = 4 KB of A per 32-cycle N = 64 instruction: 192 B/clk asked of a 128 B/clk pipe), about
+// 172 KB per 128-sample LiDAR tile.  Here the activations never touch shared memory: a thread reads its
+// accumulator row (TMEM lane = sample), applies relu, packs to fp16 and stores it back into TMEM IN PLACE
+// (tcgen05.st; packed column j = elements 2j, 2j+1, which the thread has already consumed), and the next layer's
+// tcgen05.mma takes A from tensor memory (the .ts form: [d_tmem], [a_tmem], b_desc).  Shared memory keeps only
+// the weights (B operands), a 4 KB un-swizzled geo tile and the 2 KB direction image per net: 52 KB per tile.
+// TMEM per warpgroup, 96 columns:  D1 [0,64) -> H1 packed in place [0,32) -> D2 [32,96) -> H2 packed in place
+// [32,64) -> D3 [0,16).  Five warpgroups (480 columns, 640 threads x 96 registers), nets one after the other.
+constexpr int kTsWG = 5;
+constexpr uint32_t kTsCols = 96;
+constexpr uint32_t kTsGeoTile = 4096;   // [128 rows][16 halves], un-swizzled K-major core matrices
+constexpr size_t composite_ts_smem() {
+    return kCOffTiles + (size_t)kTsWG * (kTsGeoTile + 2 * kCUImg + kCScratchFloats * 4) + 8 * kTsWG + 16 + 1024;
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(taddr),
+                 "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() {
+    asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]^T
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// this thread's accumulator row D[src .. src + 64) -> relu -> fp16 -> packed row H[dst .. dst + 32), dst == src allowed
+__device__ __forceinline__ void hidden_to_tmem(uint32_t src, uint32_t dst) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        uint32_t v[16], o[8];
+        tmem_ld16(src + q * 16, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = pack_half2_relu(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+        tmem_st8(dst + q * 8, o);
+    }
+    tmem_st_wait();
+}
+
+template <bool LIDAR>
+__global__ void __launch_bounds__(kTsWG * kRows, 1)
+k_composite_ts(const __grid_constant__ nvsf_field_config_t cfg, const unsigned char* __restrict__ wimg,
+               const __half* __restrict__ mlp, const float* __restrict__ rays_d,
+               const float* __restrict__ nears, const float* __restrict__ fars,
+               const float* __restrict__ noise, const float* __restrict__ sigma,
+               const __half* __restrict__ geo, uint32_t N, uint32_t S, float bg_color,
+               float* __restrict__ depth_out, float* __restrict__ image_out, float* __restrict__ ws_out,
+               float* __restrict__ weights_out, float* __restrict__ z_out, float* __restrict__ rgbs_out) {
+    constexpr int NETS = LIDAR ? 2 : 1;
+    constexpr int NDIR = LIDAR ? 72 : 16;
+    constexpr int NCH = LIDAR ? 2 : 3;
+    constexpr int W = kTsWG;
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    unsigned char* sm = smem_raw + (base - raw);
+    const uint32_t tid = threadIdx.x, wg = tid >> 7, t = tid & 127u, lane = tid & 31u, wq = (tid >> 5) & 3u;
+    constexpr uint32_t kOffGeo = kCOffTiles;                                  // [W] geo tiles
+    constexpr uint32_t kOffU = kOffGeo + W * kTsGeoTile;                      // [W][2] U images
+    constexpr uint32_t kOffScr = kOffU + W * 2 * kCUImg;
+    constexpr uint32_t kOffBarC = kOffScr + W * kCScratchFloats * 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + kOffBarC + 8 * W);
+    float* scr = reinterpret_cast<float*>(sm + kOffScr) + wg * kCScratchFloats;
+    float* enc_s = scr;            // [72]
+    float* ptot = scr + 200;       // [4]
+    float* red = scr + 208;        // [4][8]
+    const __half* W1d = reinterpret_cast<const __half*>(sm + kCOffW1d);
+
+    for (uint32_t i = tid; i < kHImgBytes / 16; i += (uint32_t)(W * kRows))
+        reinterpret_cast<uint4*>(sm)[i] = __ldg(reinterpret_cast<const uint4*>(wimg) + i);
+    for (int net = 0; net < NETS; ++net)
+        for (uint32_t i = tid; i < (uint32_t)kHidden * kHeadDirMax / 8; i += (uint32_t)(W * kRows))
+            reinterpret_cast<uint4*>(sm + kCOffW1d)[net * (kHidden * kHeadDirMax / 8) + i] =
+                __ldg(reinterpret_cast<const uint4*>(mlp + kHeadBase + net * kHeadHalves + kHeadW1d) + i);
+    for (uint32_t i = tid; i < (uint32_t)(W * 2 * kCUImg / 16); i += (uint32_t)(W * kRows))
+        reinterpret_cast<uint4*>(sm + kOffU)[i] = make_uint4(0, 0, 0, 0);
+    if (tid < (uint32_t)W) mbar_init(base + kOffBarC + 8 * tid, 1);
+    if (tid < 32) {
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(
+                         smem_u32(tmem_slot)),
+                     "r"((uint32_t)512)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t tcol = tmem + wg * kTsCols;
+    const uint32_t tlane = tcol + ((wq * 32u) << 16);
+    const uint32_t geo_a = base + kOffGeo + wg * kTsGeoTile;
+    unsigned char* geo_p = sm + kOffGeo + wg * kTsGeoTile + (t >> 3) * 256 + (t & 7u) * 16;  // K chunk 0 of row t
+    const uint32_t bar = base + kOffBarC + 8 * wg;
+    constexpr uint32_t kIdesc2 = umma_idesc(kRows, kHidden), kIdesc3 = umma_idesc(kRows, 16);
+    const float kexp = cfg.active_sensor ? 2.0f : 1.0f;
+    uint32_t phase = 0;
+
+    for (uint32_t r = blockIdx.x * W + wg; r < N; r += gridDim.x * W) {
+        const float near = __ldg(nears + r), far = __ldg(fars + r);
+        float sg = 0.f;
+        uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0;
+        if (t < S) {
+            const size_t g = (size_t)r * S + t;
+            sg = __ldg(sigma + g);
+            a0 = __ldg(reinterpret_cast<const uint4*>(geo + g * kGeo));
+            a1 = __ldg(reinterpret_cast<const uint4*>(geo + g * kGeo) + 1);
+        }
+        wg_barrier(wg);  // the previous ray's readers of enc / red are done
+        {
+            const float dx = __ldg(rays_d + (size_t)r * 3), dy = __ldg(rays_d + (size_t)r * 3 + 1),
+                        dz = __ldg(rays_d + (size_t)r * 3 + 2);
+            if (LIDAR) {
+                if (t < (uint32_t)NDIR) {  // tcnn Frequency, 12 octaves: sin(2^k pi x + (j&1) pi/2), x = (d+1)/2
+                    const int dim = t / 24, oct = (t >> 1) % 12;
+                    const float v = ((dim == 0 ? dx : (dim == 1 ? dy : dz)) + 1.0f) * 0.5f;
+                    enc_s[t] = sinpif(scalbnf(v, oct) + 0.5f * (float)(t & 1));
+                }
+            } else if (t < 16) {
+                enc_s[t] = sh4_term((int)t, dx, dy, dz);
+            }
+        }
+        wg_barrier(wg);
+        if (t < (uint32_t)(NETS * kHidden)) {  // u[net][n] = sum_j W1[n][dir j] * enc[j] -> U[net][n][0]
+            const __half* wrow = W1d + (size_t)t * kHeadDirMax;
+            float acc = 0.f;
+            for (int j = 0; j < NDIR; j += 2) {
+                const float2 w = __half22float2(*reinterpret_cast<const __half2*>(wrow + j));
+                acc = fmaf(w.x, enc_s[j], acc);
+                acc = fmaf(w.y, enc_s[j + 1], acc);
+            }
+            const uint32_t net = t >> 6, n = t & 63u;
+            *reinterpret_cast<__half*>(sm + kOffU + (wg * 2 + net) * kCUImg + (n >> 3) * 256 + (n & 7u) * 16) =
+                __float2half_rn(acc);
+        }
+        float carry = 1.0f, ws = 0.f, dep = 0.f, img[NCH];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) img[c] = 0.f;
+
+        for (uint32_t c0 = 0; c0 < S; c0 += kRows) {
+            const uint32_t i = c0 + t;
+            const bool in = i < S;
+            const size_t g = (size_t)r * S + (in ? i : S - 1);
+            const float z = uniform_z2(near, far, in ? i : S - 1, S, noise, g);
+            float delta;
+            if (i + 1 < S) delta = uniform_z2(near, far, i + 1, S, noise, g + 1) - z;
+            else delta = (far - near) / (float)S;  // renderer_dynamic.py:160,182
+            const float alpha = in ? 1.0f - expf(((-kexp * delta) * cfg.density_scale) * sg) : 0.f;
+            const float v = (1.0f - alpha) + 1e-15f;
+            float incl = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const float o = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= (uint32_t)d) incl *= o;
+            }
+            float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+            if (lane == 0) excl = 1.0f;
+            if (lane == 31) ptot[wq] = incl;
+            wg_barrier(wg);
+            const float p0 = ptot[0], p1 = ptot[1], p2 = ptot[2], p3 = ptot[3];
+            const float pre = wq == 0 ? 1.0f : (wq == 1 ? p0 : (wq == 2 ? p0 * p1 : (p0 * p1) * p2));
+            const float T = (carry * pre) * excl;
+            carry *= ((p0 * p1) * p2) * p3;
+            const float w = in ? alpha * T : 0.f;
+            ws += w;
+            dep = fmaf(w, z, dep);
+            if (weights_out && in) { weights_out[g] = w; z_out[g] = z; }
+            const bool m = w > 1e-4f;  // renderer_dynamic.py:202
+            a0.x = (a0.x & 0xffff0000u) | kOneH;  // col 0: sigma logit -> the constant-1 padding input
+            // geo rows -> the un-swizzled A tile (read by the layer-1 MMA of both nets)
+            *reinterpret_cast<uint4*>(geo_p) = a0;
+            *reinterpret_cast<uint4*>(geo_p + 128) = a1;
+            {   // the next tile's rows start travelling
+                const uint32_t in2 = c0 + kRows + t;
+                sg = 0.f; a0 = make_uint4(0, 0, 0, 0); a1 = a0;
+                if (in2 < S) {
+                    const size_t g2 = (size_t)r * S + in2;
+                    sg = __ldg(sigma + g2);
+                    a0 = __ldg(reinterpret_cast<const uint4*>(geo + g2 * kGeo));
+                    a1 = __ldg(reinterpret_cast<const uint4*>(geo + g2 * kGeo) + 1);
+                }
+            }
+            fence_async_smem();
+            tc_fence_before();
+            // one barrier: the geo tile is complete, every thread has read ptot, and the OR of the mask
+            float4 col = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (wg_any(wg, m)) {
+                const float wm = m ? w : 0.f;
+#pragma unroll
+                for (uint32_t net = 0; net < (uint32_t)NETS; ++net) {
+                    if (t == 0) {   // D1 [0,64) = geo W1g^T + geo U^T
+                        tc_fence_after();
+                        const uint64_t ga = umma_desc_k_noswz(geo_a, 128u, 256u);
+                        umma_f16(tcol, ga, umma_desc(base + kHOffW1 + net * (kHidden * 128)), kIdesc2, 0u);
+                        umma_f16(tcol, ga, umma_desc_k_noswz(base + kOffU + (wg * 2 + net) * kCUImg, 128u, 256u),
+                                 kIdesc2, 1u);
+                        umma_commit(bar);
+                    }
+                    mbar_wait(bar, phase); phase ^= 1u;
+                    tc_fence_after();
+                    hidden_to_tmem(tlane, tlane);                 // H1 packed in place [0,32)
+                    tc_fence_before();
+                    wg_barrier(wg);
+                    if (t == 0) {   // D2 [32,96) = H1 W2^T, A from tensor memory (8 packed columns per K = 16)
+                        tc_fence_after();
+#pragma unroll
+                        for (uint32_t k = 0; k < 4; ++k)
+                            umma_f16_ts(tcol + 32, tcol + 8 * k,
+                                        umma_desc(base + kHOffW2 + net * (kHidden * 128) + k * 32), kIdesc2, k);
+                        umma_commit(bar);
+                    }
+                    mbar_wait(bar, phase); phase ^= 1u;
+                    tc_fence_after();
+                    hidden_to_tmem(tlane + 32, tlane + 32);       // H2 packed in place [32,64)
+                    tc_fence_before();
+                    wg_barrier(wg);
+                    if (t == 0) {   // D3 [0,16) = H2 W3^T
+                        tc_fence_after();
+#pragma unroll
+                        for (uint32_t k = 0; k < 4; ++k)
+                            umma_f16_ts(tcol, tcol + 32 + 8 * k,
+                                        umma_desc(base + kHOffW3 + net * (16 * 128) + k * 32), kIdesc3, k);
+                        umma_commit(bar);
+                    }
+                    mbar_wait(bar, phase); phase ^= 1u;
+                    tc_fence_after();
+                    uint32_t o[4];
+                    tmem_ld4(tlane, o);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    if (LIDAR) {
+                        // h = [raydrop, intensity] (network_dynamic.py:317): net 0 = intensity -> channel 1
+                        const float sv = sigmoidf_(__uint_as_float(o[0]));
+                        if (net == 0) { img[1] += wm * sv; if (m) col.y = sv; }
+                        else { img[0] += wm * sv; if (m) col.x = sv; }
+                        if (net == 0) wg_barrier(wg);   // every thread has read D3 before net 1's D1 overwrites it
+                    } else {
+                        const float s0 = sigmoidf_(__uint_as_float(o[0])), s1 = sigmoidf_(__uint_as_float(o[1])),
+                                    s2 = sigmoidf_(__uint_as_float(o[2]));
+                        img[0] += wm * s0; img[1] += wm * s1; img[2] += wm * s2;
+                        if (m) col = make_float4(s0, s1, s2, 0.f);
+                    }
+                }
+            }
+            if (rgbs_out && in) *reinterpret_cast<float4*>(rgbs_out + g * 4) = col;
+        }
+        // ---- reduce over the warpgroup and write the ray ----
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            ws += __shfl_xor_sync(0xffffffffu, ws, d);
+            dep += __shfl_xor_sync(0xffffffffu, dep, d);
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) img[c] += __shfl_xor_sync(0xffffffffu, img[c], d);
+        }
+        if (lane == 0) {
+            red[wq * 8 + 0] = ws; red[wq * 8 + 1] = dep;
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) red[wq * 8 + 2 + c] = img[c];
+        }
+        wg_barrier(wg);
+        if (t == 0) {
+            const float wsum = ((red[0] + red[8]) + red[16]) + red[24];
+            ws_out[r] = wsum;
+            depth_out[r] = ((red[1] + red[9]) + red[17]) + red[25];
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                const float v = ((red[2 + c] + red[10 + c]) + red[18 + c]) + red[26 + c];
+                image_out[(size_t)r * NCH + c] = LIDAR ? v : v + (1.0f - wsum) * bg_color;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (tid < 32)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"((uint32_t)512)
+                     : "memory");
+}
+
+int g_heads_tc = 6;  // nvsf_set_option("heads_tc", 0..6): head MLPs of the uniform renderer: 0 mma.sync; 1 tcgen05, four
+                     // warpgroups with the two nets overlapped; 2..5 eight / six / five / seven warpgroups, nets in turn, direction
+                     // term through a second layer-1 MMA; 6 (default) = 4 with the activations as the A operand from TMEM
+bool g_tc_attr8 = false, g_tc_attr_ts = false;
 bool g_tc_attr2 = false;
 
 bool g_attr = false;
@@ -734,6 +1344,61 @@ int nvsf_render_composite_launch(const nvsf_field_config_t* cfg, const void* wor
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_heads_tc == 6) {   // hidden activations as the A operand from tensor memory
+        if (!g_tc_attr_ts) {
+            cudaError_t e = cudaFuncSetAttribute(k_composite_ts<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)composite_ts_smem());
+            if (e != cudaSuccess) return (int)e;
+            e = cudaFuncSetAttribute(k_composite_ts<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)composite_ts_smem());
+            if (e != cudaSuccess) return (int)e;
+            g_tc_attr_ts = true;
+        }
+        const unsigned char* wimg = reinterpret_cast<const unsigned char*>(P.heads_tc);
+        const uint32_t grid = std::min<uint32_t>(nvsf_div_up(N, (uint32_t)kTsWG), (uint32_t)sms);
+        if (lidar)
+            k_composite_ts<true><<<grid, kTsWG * kRows, composite_ts_smem(), s>>>(
+                *cfg, wimg, P.mlp, rays_d, nears, fars, noise, sigma, geo, N, S, bg_color, depth, image,
+                weights_sum, weights, z_vals, reinterpret_cast<float*>(rgbs));
+        else
+            k_composite_ts<false><<<grid, kTsWG * kRows, composite_ts_smem(), s>>>(
+                *cfg, wimg, P.mlp, rays_d, nears, fars, noise, sigma, geo, N, S, bg_color, depth, image,
+                weights_sum, weights, z_vals, reinterpret_cast<float*>(rgbs));
+        return nvsf_launch_status();
+    }
+    if (g_heads_tc >= 2 && g_heads_tc <= 5) {   // 2..5 -> 8, 6, 5, 7 warpgroups per CTA
+        const int wsel = g_heads_tc - 2;
+        const uint32_t W = wsel == 0 ? 8u : (wsel == 1 ? 6u : (wsel == 2 ? 5u : 7u));
+        if (!g_tc_attr8) {
+            cudaError_t e = cudaSuccess;
+#define NVSF_ATTR_TC8(WW)                                                                                           \
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_composite_tc8<true, WW>,                                  \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)composite_tc8_smem<WW>()); \
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_composite_tc8<false, WW>,                                 \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)composite_tc8_smem<WW>());
+            NVSF_ATTR_TC8(8) NVSF_ATTR_TC8(6) NVSF_ATTR_TC8(5) NVSF_ATTR_TC8(7)
+#undef NVSF_ATTR_TC8
+            if (e != cudaSuccess) return (int)e;
+            g_tc_attr8 = true;
+        }
+        const unsigned char* wimg = reinterpret_cast<const unsigned char*>(P.heads_tc);
+        const uint32_t grid = std::min<uint32_t>(nvsf_div_up(N, W), (uint32_t)sms);
+#define NVSF_LAUNCH_TC8(LID, WW)                                                                              \
+        k_composite_tc8<LID, WW><<<grid, WW * kRows, composite_tc8_smem<WW>(), s>>>(                              \
+            *cfg, wimg, P.mlp, rays_d, nears, fars, noise, sigma, geo, N, S, bg_color, depth, image, weights_sum, \
+            weights, z_vals, reinterpret_cast<float*>(rgbs))
+#define NVSF_LAUNCH_TC8_W(LID)                                                           \
+        switch (W) {                                                                     \
+            case 8: NVSF_LAUNCH_TC8(LID, 8); break;                                      \
+            case 7: NVSF_LAUNCH_TC8(LID, 7); break;                                      \
+            case 6: NVSF_LAUNCH_TC8(LID, 6); break;                                      \
+            default: NVSF_LAUNCH_TC8(LID, 5); break;                                     \
+        }
+        if (lidar) { NVSF_LAUNCH_TC8_W(true) } else { NVSF_LAUNCH_TC8_W(false) }
+#undef NVSF_LAUNCH_TC8_W
+#undef NVSF_LAUNCH_TC8
+        return nvsf_launch_status();
+    }
     if (g_heads_tc) {
         if (!g_tc_attr2) {
             cudaError_t e = cudaFuncSetAttribute(k_composite_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -796,7 +1461,7 @@ void nvsf_pack_heads_tc(const __half* mlp, void* dst, int nets, cudaStream_t str
 // ---- tuning options of the renderer (nvsf_train_set_option falls through to here) -----------------
 int nvsf_render_set_option(const char* name, int value) {
     if (std::string(name) == "heads_tc") {
-        if (value != 0 && value != 1) return NVSF_E_INVALID;
+        if (value < 0 || value > 6) return NVSF_E_INVALID;
         g_heads_tc = value;
         return NVSF_OK;
     }

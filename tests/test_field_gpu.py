@@ -333,7 +333,8 @@ def test_composite_heads_tcgen05_matches_mma_sync(pkg, model, lidar, steps):
     noise = torch.rand(333, steps, device="cuda", generator=torch.Generator("cuda").manual_seed(5))
     out = {}
     try:
-        for tc in (0, 1):
+        for tc in (0, 1, 2, 3, 4, 5, 6):   # 6: hidden activations as the A operand from tensor memory; 2..5: eight / six / five / seven warpgroups per CTA, the nets one after the
+            # other, the per-ray direction term added by a second layer-1 MMA (fp16 u) instead of the epilogue
             assert L.nvsf_set_option(b"heads_tc", tc) == 0
             assert L.nvsf_get_option(b"heads_tc") == tc
             with torch.no_grad():
@@ -344,12 +345,19 @@ def test_composite_heads_tcgen05_matches_mma_sync(pkg, model, lidar, steps):
             out[tc] = (host(r["depth" + sfx]), host(r["image" + sfx]), host(r["weights_sum" + sfx]),
                        host(r["weights"]), host(r["z_vals"]))
     finally:
-        L.nvsf_set_option(b"heads_tc", 1)
+        L.nvsf_set_option(b"heads_tc", 6)
     assert np.abs(out[0][1]).max() > 1e-3
-    assert np.array_equal(out[1][4], out[0][4])
-    for a, b, name in zip(out[1], out[0], ("depth", "image", "weights_sum", "weights")):
-        close(a, b, 1e-4 if name != "image" else 2e-3, 1e-6 if name != "image" else 2e-3 * np.abs(b).max(),
-              f"heads tcgen05 vs mma.sync {name} (S={steps})")
+    for tc in (1, 2, 3, 4, 5, 6):
+        assert np.array_equal(out[tc][4], out[0][4])
+        for a, b, name in zip(out[tc], out[0], ("depth", "image", "weights_sum", "weights")):
+            close(a, b, 1e-4 if name != "image" else 2e-3, 1e-6 if name != "image" else 2e-3 * np.abs(b).max(),
+                  f"heads tcgen05 (mode {tc}) vs mma.sync {name} (S={steps})")
+    # the same tile arithmetic, only the number of warpgroups differs: these forms agree bit for bit
+    for tc in (3, 4, 5):
+        for a, b in zip(out[tc], out[2]):
+            assert np.array_equal(a, b)
+    for a, b in zip(out[6], out[2]):   # ... and so does the form that keeps the activations in tensor memory
+        assert np.array_equal(a, b)
 
 
 @pytest.mark.parametrize("t", [0.45, 1.0])

@@ -385,7 +385,7 @@ def test_color_net_tcgen05_matches_mma_sync(pkg, model):
             out[tc] = (host(model.color(None, dd, den["geo_feat"], None, False)),
                        host(model.color(None, dd, geo32, mm, False)))
     finally:
-        L.nvsf_set_option(b"heads_tc", 1)
+        L.nvsf_set_option(b"heads_tc", 6)
     assert np.abs(out[0][0]).max() > 0.1
     close(out[1][0], out[0][0], 2e-3, 2e-3, "color_net tcgen05 vs mma.sync (geo16 view)")
     close(out[1][1], out[0][1], 2e-3, 2e-3, "color_net tcgen05 vs mma.sync (fp32 geo, mask)")

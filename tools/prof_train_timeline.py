@@ -87,6 +87,13 @@ if a.profile:
             k = "<2us" if g < 2 else "2-5us" if g < 5 else "5-20us" if g < 20 else "20-100us" if g < 100 else ">100us"
             hist[k] += 1
             tot[k] += g
+        per = {}
+        for e in evs:
+            k = e.name[:70]
+            d = e.time_range.end - e.time_range.start
+            per[k] = (per.get(k, (0.0, 0))[0] + d, per.get(k, (0.0, 0))[1] + 1)
+        out["kernels_ms_per_step"] = [(k, round(v[0] / 3e3, 4), v[1] // 3)
+                                      for k, v in sorted(per.items(), key=lambda kv: -kv[1][0])[:40]]
         out["profile"] = {"steps": 3, "span_ms": span / 1e3, "gpu_busy_ms": busy / 1e3, "idle_ms": (span - busy) / 1e3,
                           "kernels": len(evs), "gap_count": hist, "gap_total_us": tot,
                           "top_gaps_us": [(k, round(v[0], 1), v[1]) for k, v in top]}
