@@ -983,40 +983,6 @@ constexpr uint32_t kTsGeoTile = 4096;   // [128 rows][16 halves], un-swizzled K-
 constexpr size_t composite_ts_smem() {
     return kCOffTiles + (size_t)kTsWG * (kTsGeoTile + 2 * kCUImg + kCScratchFloats * 4) + 8 * kTsWG + 16 + 1024;
 }
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(taddr),
-                 "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() {
-    asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
-}
-// D[tmem] (+)= A[tmem] * B[smem]^T
-__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b, uint32_t idesc,
-                                            uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d),
-        "r"(tmem_a), "l"(b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// this thread's accumulator row D[src .. src + 64) -> relu -> fp16 -> packed row H[dst .. dst + 32), dst == src allowed
-__device__ __forceinline__ void hidden_to_tmem(uint32_t src, uint32_t dst) {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        uint32_t v[16], o[8];
-        tmem_ld16(src + q * 16, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = pack_half2_relu(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
-        tmem_st8(dst + q * 8, o);
-    }
-    tmem_st_wait();
-}
-
 template <bool LIDAR>
 __global__ void __launch_bounds__(kTsWG * kRows, 1)
 k_composite_ts(const __grid_constant__ nvsf_field_config_t cfg, const unsigned char* __restrict__ wimg,

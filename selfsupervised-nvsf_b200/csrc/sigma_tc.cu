@@ -379,28 +379,17 @@ k_encode_sigma_tc(const __grid_constant__ nvsf_field_config_t cfg,
         mbar_wait(bar, phase);
         phase ^= 1u;
         tc_fence_after();
-        // ---- H = relu(D1) -> tile ----------------------------------------------------------------
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            uint32_t v[16];
-            tmem_ld16(tlane + q * 16, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                float f[8];   // (cvt.rn.relu here shifts this kernel's register allocation: 12.53 -> 12.74 ms)
-#pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = fmaxf(__uint_as_float(v[8 * h + j]), 0.f);
-                st_chunk(xg, t, 2 * q + h, f);
-            }
-        }
-        fence_async_smem();
+        // ---- H = relu(D1) -> fp16, packed IN PLACE into columns [0,32) of this thread's TMEM lane; the
+        // second layer takes it as its A operand from tensor memory (D2 = H W2^T into columns [32,48)):
+        // no shared-memory round trip of the activations (16 KB written + 16 KB read back per tile)
+        hidden_to_tmem(tlane, tlane);
         tc_fence_before();
         wg_barrier(wg);
         if (t == 0) {
             tc_fence_after();
 #pragma unroll
             for (uint32_t k = 0; k < 4; ++k)
-                umma_f16(tcol, umma_desc(xs + k * 32), umma_desc(base + kOffW2 + k * 32), kIdesc2, k);
+                umma_f16_ts(tcol + 32, tcol + 8 * k, umma_desc(base + kOffW2 + k * 32), kIdesc2, k);
             umma_commit(bar);
         }
         mbar_wait(bar, phase);
@@ -408,7 +397,7 @@ k_encode_sigma_tc(const __grid_constant__ nvsf_field_config_t cfg,
         tc_fence_after();
         {
             uint32_t v[16];
-            tmem_ld16(tlane, v);
+            tmem_ld16(tlane + 32, v);
             tmem_ld_wait();
             if (live) {
                 sigma_out[li] = expf(round_f16(__uint_as_float(v[0])));

@@ -688,15 +688,18 @@ struct Bilin {
     uint32_t x0, x1, y0, y1;
     float wx, wy;
 };
-__device__ __forceinline__ void sample2d(const float* __restrict__ base, uint32_t R, float pa, float pb,
+__device__ __forceinline__ void ld8t(const float* p, float (&v)[8]) { ld8(p, v); }
+__device__ __forceinline__ void ld8t(const __half* p, float (&v)[8]) { ld8h(p, v); }
+template <class TT>
+__device__ __forceinline__ void sample2d(const TT* __restrict__ base, uint32_t R, float pa, float pb,
                                          Bilin& b, float (&out)[8]) {
     plane_coord(pa, R, b.x0, b.x1, b.wx);
     plane_coord(pb, R, b.y0, b.y1, b.wy);
     float a[8], bb[8], c[8], d[8];
-    ld8(base + ((size_t)b.y0 * R + b.x0) * 8, a);
-    ld8(base + ((size_t)b.y0 * R + b.x1) * 8, bb);
-    ld8(base + ((size_t)b.y1 * R + b.x0) * 8, c);
-    ld8(base + ((size_t)b.y1 * R + b.x1) * 8, d);
+    ld8t(base + ((size_t)b.y0 * R + b.x0) * 8, a);
+    ld8t(base + ((size_t)b.y0 * R + b.x1) * 8, bb);
+    ld8t(base + ((size_t)b.y1 * R + b.x0) * 8, c);
+    ld8t(base + ((size_t)b.y1 * R + b.x1) * 8, d);
     const float w00 = (1.f - b.wx) * (1.f - b.wy), w01 = b.wx * (1.f - b.wy),
                 w10 = (1.f - b.wx) * b.wy, w11 = b.wx * b.wy;
 #pragma unroll
@@ -735,14 +738,15 @@ struct Lin {
     float wx;
     float dcoord;  // d(texel coordinate)/d(p): R-1 inside the grid, 0 where grid_sample clamps
 };
-__device__ __forceinline__ void sample1d(const float* __restrict__ base, uint32_t R, float pa, Lin& l,
+template <class TT>
+__device__ __forceinline__ void sample1d(const TT* __restrict__ base, uint32_t R, float pa, Lin& l,
                                          float (&out)[8], float (&slope)[8]) {
     plane_coord(pa, R, l.x0, l.x1, l.wx);
     const float f = ((pa * 2.0f - 1.0f) + 1.0f) * 0.5f * (float)(R - 1);
     l.dcoord = (f > 0.f && f < (float)(R - 1)) ? (float)(R - 1) : 0.f;
     float a[8], b[8];
-    ld8(base + (size_t)l.x0 * 8, a);
-    ld8(base + (size_t)l.x1 * 8, b);
+    ld8t(base + (size_t)l.x0 * 8, a);
+    ld8t(base + (size_t)l.x1 * 8, b);
 #pragma unroll
     for (int f2 = 0; f2 < 8; ++f2) {
         out[f2] = (1.f - l.wx) * a[f2] + l.wx * b[f2];
@@ -770,8 +774,27 @@ __device__ __forceinline__ void scatter1d(float* __restrict__ base, const Lin& l
     }
 }
 
+// The per-sample inputs of the encoder backward (610 B: 128 fp32 feature gradients, dgeo, flow) are read exactly
+// once: loaded evict-first (ld.global.cs) they do not push the gradient tables — 67 MB of fp32 static-hash
+// gradient that the reds hit at random — out of the L2 (tools/ubench_red.cu: random reds run at 189 G sectors/s
+// on an L2-resident table, 60 G/s on a 128 MB one, 25 G/s from DRAM).
+// (measured: k_encode_bwd 7.88 -> 7.60 ms per training step).
+// Where its time goes (training step of 2 x 3.1 M samples, each part left out in turn): time planes 2.46 ms, static
+// hash 2.06, dynamic hashes 1.57, space planes 1.04, sample set-up 0.4 of 7.53 ms.
+int g_enc_bwd_h16 = 1;   // option "enc_bwd_h16": plane texels of the product rule from the fp16 mirrors
+template <bool STREAM>
+__device__ __forceinline__ float4 lds4(const float4* p) { return STREAM ? __ldcs(p) : __ldg(p); }
+template <bool STREAM>
+__device__ __forceinline__ float lds1(const float* p) { return STREAM ? __ldcs(p) : __ldg(p); }
+template <bool STREAM>
+__device__ __forceinline__ void ld8s(const float* p, float (&v)[8]) {
+    const float4 a = lds4<STREAM>(reinterpret_cast<const float4*>(p)), b = lds4<STREAM>(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+#define NVSF_LDS4(p) lds4<STREAM>(p)
+#define NVSF_LDS1(p) lds1<STREAM>(p)
 // MIN_CTAS 2 = 128 registers / 16 warps per SM; 3 = 80 registers (80 bytes of spills) / 24 warps
-template <bool FROM_RAYS, int MIN_CTAS>
+template <bool FROM_RAYS, int MIN_CTAS, bool H16>
 __global__ void __launch_bounds__(256, MIN_CTAS)
 k_encode_bwd(const __grid_constant__ nvsf_field_config_t cfg, const __grid_constant__ FieldPtrs P,
              const GradTables G, const float* __restrict__ xin, const float* __restrict__ rays_o,
@@ -780,6 +803,7 @@ k_encode_bwd(const __grid_constant__ nvsf_field_config_t cfg, const __grid_const
              size_t begin, size_t count, const float* __restrict__ flow_in /* [.,8] global index */,
              const float* __restrict__ dgeo16 /* chunk-local */, const float* __restrict__ dfeat,
              float* __restrict__ dflow_out, const float* __restrict__ scale2) {
+    constexpr bool STREAM = true;
     const size_t li = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool inb = li < count;
     // Rows whose sigma-net output gradient is zero AS THE SIGMA BACKWARD SAW IT (scaled, fp16) have
@@ -790,7 +814,7 @@ k_encode_bwd(const __grid_constant__ nvsf_field_config_t cfg, const __grid_const
         const float4* d = reinterpret_cast<const float4*>(dgeo16 + li * 16);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const float4 v = __ldg(d + i);
+            const float4 v = NVSF_LDS4(d + i);
             live = live || ((pack_half2(sc * v.x, sc * v.y) | pack_half2(sc * v.z, sc * v.w)) & 0x7fff7fffu) != 0;
         }
     }
@@ -825,8 +849,8 @@ k_encode_bwd(const __grid_constant__ nvsf_field_config_t cfg, const __grid_const
         }
         const float inv2b = 1.0f / (2.0f * cfg.bound);
         x = (px + cfg.bound) * inv2b; y = (py + cfg.bound) * inv2b; z = (pz + cfg.bound) * inv2b;
-        f0 = __ldg(reinterpret_cast<const float4*>(flow_in + g * 8));
-        f1 = __ldg(reinterpret_cast<const float4*>(flow_in + g * 8) + 1);
+        f0 = NVSF_LDS4(reinterpret_cast<const float4*>(flow_in + g * 8));
+        f1 = NVSF_LDS4(reinterpret_cast<const float4*>(flow_in + g * 8) + 1);
     }
     const int valid1 = P.ti->valid[1], valid2 = P.ti->valid[2];
     float qx[3], qy[3], qz[3];
@@ -843,18 +867,27 @@ k_encode_bwd(const __grid_constant__ nvsf_field_config_t cfg, const __grid_const
 #pragma unroll 1
     for (int s = 0; s < kPlScales; ++s) {
         const uint32_t R = cfg.pl_res[s];
-        const float* base = P.pls + P.pls_scale[s];
+        // the texels of the product rule come from the fp16 mirrors the forward itself interpolates (one 16-byte
+        // load per texel instead of two): the re-gathers are 240 of this kernel's loads per sample
+        const float* base32 = P.pls + P.pls_scale[s];
+        const __half* base16 = P.pls16 + P.pls_scale[s];
         float* gbase = G.pls + P.pls_scale[s];
         float g8[8], A[8], B[8], C[8];
-        if (live) ld8(df + 8 * s, g8);
+        if (live) ld8s<STREAM>(df + 8 * s, g8);
         else {
 #pragma unroll
             for (int f = 0; f < 8; ++f) g8[f] = 0.f;
         }
         Bilin ba, bb, bc;
-        sample2d(base, R, x, y, ba, A);
-        sample2d(base + (size_t)R * R * 8, R, x, z, bb, B);
-        sample2d(base + (size_t)2 * R * R * 8, R, y, z, bc, C);
+        if (H16) {
+            sample2d(base16, R, x, y, ba, A);
+            sample2d(base16 + (size_t)R * R * 8, R, x, z, bb, B);
+            sample2d(base16 + (size_t)2 * R * R * 8, R, y, z, bc, C);
+        } else {
+            sample2d(base32, R, x, y, ba, A);
+            sample2d(base32 + (size_t)R * R * 8, R, x, z, bb, B);
+            sample2d(base32 + (size_t)2 * R * R * 8, R, y, z, bc, C);
+        }
         float d8[8];
 #pragma unroll
         for (int f = 0; f < 8; ++f) d8[f] = g8[f] * B[f] * C[f];
@@ -874,7 +907,7 @@ k_encode_bwd(const __grid_constant__ nvsf_field_config_t cfg, const __grid_const
     for (int s = 0; s < kPlScales; ++s) {
         const uint32_t R = cfg.pl_res[s];
         float g8[8];
-        if (live) ld8(df + 32 + 8 * s, g8);
+        if (live) ld8s<STREAM>(df + 32 + 8 * s, g8);
         else {
 #pragma unroll
             for (int f = 0; f < 8; ++f) g8[f] = 0.f;
@@ -882,14 +915,21 @@ k_encode_bwd(const __grid_constant__ nvsf_field_config_t cfg, const __grid_const
 #pragma unroll 1
         for (int q = 0; q < 3; ++q) {
             const size_t toff = (size_t)qi[q] * P.pld_per_q + P.pld_scale[s];
-            const float* base = P.pld + toff;
+            const float* base32 = P.pld + toff;
+            const __half* base16 = P.pld16 + toff;
             float* gbase = G.pld + toff;
             const float wq = q == 0 ? 0.5f : 0.25f;
             float A[8], B[8], C[8], sa[8], sb[8], sc[8];
             Lin la, lb, lc;
-            sample1d(base, R, qx[q], la, A, sa);
-            sample1d(base + (size_t)R * 8, R, qy[q], lb, B, sb);
-            sample1d(base + (size_t)2 * R * 8, R, qz[q], lc, C, sc);
+            if (H16) {
+                sample1d(base16, R, qx[q], la, A, sa);
+                sample1d(base16 + (size_t)R * 8, R, qy[q], lb, B, sb);
+                sample1d(base16 + (size_t)2 * R * 8, R, qz[q], lc, C, sc);
+            } else {
+                sample1d(base32, R, qx[q], la, A, sa);
+                sample1d(base32 + (size_t)R * 8, R, qy[q], lb, B, sb);
+                sample1d(base32 + (size_t)2 * R * 8, R, qz[q], lc, C, sc);
+            }
             float d8[8], gx = 0.f, gy = 0.f, gz = 0.f;
 #pragma unroll
             for (int f = 0; f < 8; ++f) {
@@ -915,8 +955,13 @@ k_encode_bwd(const __grid_constant__ nvsf_field_config_t cfg, const __grid_const
     }
     if (inb && live) {
         float4* o = reinterpret_cast<float4*>(dflow_out + li * 8);
-        o[0] = make_float4(dfl[0], dfl[1], dfl[2], dfl[3]);
-        o[1] = make_float4(dfl[4], dfl[5], 0.f, 0.f);
+        if (STREAM) {
+            __stcs(o, make_float4(dfl[0], dfl[1], dfl[2], dfl[3]));
+            __stcs(o + 1, make_float4(dfl[4], dfl[5], 0.f, 0.f));
+        } else {
+            o[0] = make_float4(dfl[0], dfl[1], dfl[2], dfl[3]);
+            o[1] = make_float4(dfl[4], dfl[5], 0.f, 0.f);
+        }
     }
     // (c) static 3-D hash: tcnn grid backward, fp32 vector reds into the caller's gradient.
     // The hash scatters are bound by atomic throughput (about one red lane-operation per two
@@ -928,12 +973,12 @@ k_encode_bwd(const __grid_constant__ nvsf_field_config_t cfg, const __grid_const
     // (the per-level gradient rows are loaded one iteration ahead: a dependent global load per
     // level was the largest stall of this part)
     float4 g4n = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (live) g4n = __ldg(reinterpret_cast<const float4*>(df + 64));
+    if (live) g4n = NVSF_LDS4(reinterpret_cast<const float4*>(df + 64));
 #pragma unroll 1
     for (int l = 0; l < kHsLevels; ++l) {
         const LevelArgs L = lv(cfg.hs[l]);
         const float4 g4 = g4n;
-        if (live && l + 1 < kHsLevels) g4n = __ldg(reinterpret_cast<const float4*>(df + 64 + 4 * (l + 1)));
+        if (live && l + 1 < kHsLevels) g4n = NVSF_LDS4(reinterpret_cast<const float4*>(df + 64 + 4 * (l + 1)));
         uint32_t cx, cy, cz;
         float wx, wy, wz;
         grid_pos(L.scale, x, cx, wx);
@@ -968,7 +1013,7 @@ k_encode_bwd(const __grid_constant__ nvsf_field_config_t cfg, const __grid_const
     // (d) dynamic 2-D hashes: gradient through the un-warped query only; a missing neighbour
     // frame re-uses the un-warped feature (network_dynamic.py:238-239) -> factor 0.5 + 0.25 each
     const float fac = lv_ * (0.5f + (valid1 ? 0.f : 0.25f) + (valid2 ? 0.f : 0.25f));
-    float gsn = live ? __ldg(df + 96) : 0.f;
+    float gsn = live ? NVSF_LDS1(df + 96) : 0.f;
 #pragma unroll 1
     for (int p = 0; p < 3; ++p) {
         const float u = p == 2 ? y : x, w2 = p == 0 ? y : z;
@@ -977,7 +1022,7 @@ k_encode_bwd(const __grid_constant__ nvsf_field_config_t cfg, const __grid_const
         for (int l = 0; l < kHdLevels; ++l) {
             const LevelArgs L = lv(cfg.hd[p][l]);
             const float gs = fac * gsn;
-            if (live && 8 * p + l + 1 < 3 * kHdLevels) gsn = __ldg(df + 96 + 8 * p + l + 1);
+            if (live && 8 * p + l + 1 < 3 * kHdLevels) gsn = NVSF_LDS1(df + 96 + 8 * p + l + 1);
             uint32_t cu, cv;
             float wu, wv;
             grid_pos(L.scale, u, cu, wu);
@@ -1450,12 +1495,12 @@ int nvsf_render_uniform_backward(const nvsf_field_config_t* cfg, const void* wor
         // 4. encoders backward -> table gradients, d flow
         {
             const unsigned blocks = (unsigned)nvsf_div_up(count, (size_t)256);
-            if (g_enc_bwd_ctas == 3)
-                k_encode_bwd<true, 3><<<blocks, 256, 0, s>>>(*cfg, P, G, nullptr, rays_o, rays_d, nears, fars, noise,
-                                                             S, begin, count, flow, dgeo16, dfeat, dflow, scale_s);
-            else
-                k_encode_bwd<true, 2><<<blocks, 256, 0, s>>>(*cfg, P, G, nullptr, rays_o, rays_d, nears, fars, noise,
-                                                             S, begin, count, flow, dgeo16, dfeat, dflow, scale_s);
+#define NVSF_ENC_BWD(C, ST)                                                                                     \
+            k_encode_bwd<true, C, ST><<<blocks, 256, 0, s>>>(*cfg, P, G, nullptr, rays_o, rays_d, nears, fars, noise, \
+                                                             S, begin, count, flow, dgeo16, dfeat, dflow, scale_s)
+            if (g_enc_bwd_ctas == 3) { if (g_enc_bwd_h16) NVSF_ENC_BWD(3, true); else NVSF_ENC_BWD(3, false); }
+            else { if (g_enc_bwd_h16) NVSF_ENC_BWD(2, true); else NVSF_ENC_BWD(2, false); }
+#undef NVSF_ENC_BWD
         }
         // 5. flow MLP backward -> d flow-grid features; 6. flow-grid scatter
         {
@@ -1579,6 +1624,11 @@ int nvsf_train_set_option(const char* name, int value) {
         g_enc_bwd_ctas = value;
         return NVSF_OK;
     }
+    if (std::string(name) == "enc_bwd_h16") {
+        if (value != 0 && value != 1) return NVSF_E_INVALID;
+        g_enc_bwd_h16 = value;
+        return NVSF_OK;
+    }
     for (auto kv : {std::make_pair("bwd_shift_flow", &g_shift_flow), std::make_pair("bwd_shift_sigma", &g_shift_sigma),
                     std::make_pair("bwd_shift_heads", &g_shift_heads)})
         if (std::string(name) == kv.first) {
@@ -1590,6 +1640,7 @@ int nvsf_train_set_option(const char* name, int value) {
 }
 int nvsf_train_get_option(const char* name) {
     if (std::string(name) == "enc_bwd_ctas") return g_enc_bwd_ctas;
+    if (std::string(name) == "enc_bwd_h16") return g_enc_bwd_h16;
     if (std::string(name) == "bwd_shift_flow") return g_shift_flow;
     if (std::string(name) == "bwd_shift_sigma") return g_shift_sigma;
     if (std::string(name) == "bwd_shift_heads") return g_shift_heads;
