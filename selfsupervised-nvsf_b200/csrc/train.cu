@@ -31,6 +31,7 @@
 #include <string>
 
 #include "mlp_bwd.cuh"
+#include "mlp_bwd_tc.cuh"
 
 namespace {
 
@@ -461,6 +462,166 @@ struct HeadT {
             const int r = i / 15, c = i - r * 15 + 1;
             if (row0 + r < n) A.dgeo16[(row0 + r) * 16 + c] = 0.f;
         }
+    }
+};
+
+
+// ------------------------------------------------------------------------------------------------
+// row-wise views of the same three MLPs for the tcgen05 backward (mlp_bwd_tc.cuh): thread = row
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tc_store_x(unsigned char* xg, uint32_t t, int chunk, uint4 v) {
+    *reinterpret_cast<uint4*>(xg + (chunk >> 3) * mlptc::kTile64 + umma::swz(t, (uint32_t)chunk & 7u)) = v;
+}
+struct SigmaTc {
+    static constexpr int KIN = 128, NHID = 1, LDG1 = 128, OUT_ROWS = 16, DX0 = 0, DXN = 128;
+    using Args = SigmaT::Args;
+    static __device__ __forceinline__ void fill_do(const Args& A, size_t row, float scale, uint4& o0, uint4& o1) {
+        const float4* g = reinterpret_cast<const float4*>(A.dgeo16 + row * 16);
+        const float4 a = __ldg(g), b = __ldg(g + 1), c = __ldg(g + 2), d = __ldg(g + 3);
+        o0 = make_uint4(pack_half2(scale * a.x, scale * a.y), pack_half2(scale * a.z, scale * a.w),
+                        pack_half2(scale * b.x, scale * b.y), pack_half2(scale * b.z, scale * b.w));
+        o1 = make_uint4(pack_half2(scale * c.x, scale * c.y), pack_half2(scale * c.z, scale * c.w),
+                        pack_half2(scale * d.x, scale * d.y), pack_half2(scale * d.z, scale * d.w));
+    }
+    static __device__ __forceinline__ void fill_x(const Args& A, size_t row, bool inb, size_t, size_t, unsigned char* xg,
+                                                  uint32_t t, uint32_t, unsigned char*) {
+#pragma unroll 4
+        for (int c = 0; c < 16; ++c) {
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (inb) v = __ldcs(reinterpret_cast<const uint4*>(A.feats + row * 128) + c);
+            tc_store_x(xg, t, c, v);
+        }
+    }
+    static __device__ __forceinline__ void sink_row(const Args& A, size_t row, int col0, const float (&f)[16], bool live) {
+        if (!live) return;   // k_encode_bwd tests dgeo16 itself and never reads the row
+        float4* d = reinterpret_cast<float4*>(A.dfeat + row * 128 + col0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) d[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+    }
+    static __device__ __forceinline__ void sink_dead(const Args&, size_t, bool) {}
+};
+struct FlowTc {
+    static constexpr int KIN = 32, NHID = 2, LDG1 = 32, OUT_ROWS = 6, DX0 = 0, DXN = 32;
+    using Args = FlowT::Args;
+    static __device__ __forceinline__ void fill_do(const Args& A, size_t row, float scale, uint4& o0, uint4& o1) {
+        const float4* g = reinterpret_cast<const float4*>(A.dflow + row * 8);
+        const float4 a = __ldg(g), b = __ldg(g + 1);
+        o0 = make_uint4(pack_half2(scale * a.x, scale * a.y), pack_half2(scale * a.z, scale * a.w),
+                        pack_half2(scale * b.x, scale * b.y), pack_half2(scale * b.z, scale * b.w));
+        o1 = make_uint4(0, 0, 0, 0);
+    }
+    static __device__ __forceinline__ void fill_x(const Args& A, size_t row, bool inb, size_t, size_t, unsigned char* xg,
+                                                  uint32_t t, uint32_t, unsigned char*) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (inb) v = __ldcs(reinterpret_cast<const uint4*>(A.flowfeat + row * 32) + c);
+            tc_store_x(xg, t, c, v);
+        }
+    }
+    static __device__ __forceinline__ void sink_row(const Args& A, size_t row, int col0, const float (&f)[16], bool live) {
+        if (!live) return;   // k_flowgrid_bwd applies the same zero test to dflow
+        float4* d = reinterpret_cast<float4*>(A.dflowfeat + row * 32 + col0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) d[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+    }
+    static __device__ __forceinline__ void sink_dead(const Args&, size_t, bool) {}
+};
+template <bool LIDAR>
+struct HeadTc {
+    static constexpr int KIN = LIDAR ? 96 : 32, NHID = 2, LDG1 = KIN, OUT_ROWS = 16;
+    static constexpr int NDIR = LIDAR ? 72 : 16;
+    static constexpr int DX0 = NDIR, DXN = 16;
+    using Args = typename HeadT<LIDAR>::Args;
+    static __device__ __forceinline__ void fill_do(const Args& A, size_t row, float scale, uint4& o0, uint4& o1) {
+        o0 = make_uint4(0, 0, 0, 0);
+        o1 = o0;
+        const float w = __ldg(A.weights + row);
+        if (!(w > 1e-4f)) return;   // only the samples that passed the colour mask carry gradient
+        const size_t ray = row / A.S;
+        const float4 cc = __ldg(reinterpret_cast<const float4*>(A.rgbs + row * 4));
+        const float ws = scale * w;
+        if (LIDAR) {
+            const int ch = A.net == 0 ? 1 : 0;
+            const float c = ch ? cc.y : cc.x;
+            o0.x = pack_half2(ws * __ldg(A.g_image + ray * 2 + ch) * c * (1.f - c), 0.f);
+        } else {
+            o0.x = pack_half2(ws * __ldg(A.g_image + ray * 3) * cc.x * (1.f - cc.x),
+                              ws * __ldg(A.g_image + ray * 3 + 1) * cc.y * (1.f - cc.y));
+            o0.y = pack_half2(ws * __ldg(A.g_image + ray * 3 + 2) * cc.z * (1.f - cc.z), 0.f);
+        }
+    }
+    // X row = [direction encoding (NDIR) | geo 1..15 | 1 (tcnn input padding) | lidar: 8 more ones]
+    static __device__ __forceinline__ void fill_x(const Args& A, size_t row, bool inb, size_t row0, size_t n,
+                                                  unsigned char* xg, uint32_t t, uint32_t wg, unsigned char* scratch) {
+        if (LIDAR) {
+            // tcnn Frequency (12 octaves) of (d + 1) / 2 is constant along a ray: the rays of the tile are encoded
+            // once, cooperatively, into scratch (the still unused Hb tile), then every row copies its ray's 144 bytes
+            const size_t last = (row0 + 128 < n ? row0 + 128 : n) - 1;
+            const size_t ray_a = row0 / A.S;
+            const int nr = (int)(last / A.S - ray_a) + 1;
+            for (int i = (int)t; i < nr * 36; i += 128) {
+                const int rl = i / 36, j = 2 * (i - rl * 36);
+                const int dim = j / 24, oct = (j >> 1) % 12;
+                const float v = (__ldg(A.rays_d + (ray_a + rl) * 3 + dim) + 1.0f) * 0.5f;
+                const float a = scalbnf(v, oct);
+                *reinterpret_cast<uint32_t*>(scratch + rl * 144 + j * 2) = pack_half2(sinpif(a), sinpif(a + 0.5f));
+            }
+            umma::wg_barrier(wg);
+            if (inb) {
+                const uint4* src = reinterpret_cast<const uint4*>(scratch + (row / A.S - ray_a) * 144);
+#pragma unroll
+                for (int c = 0; c < 9; ++c) tc_store_x(xg, t, c, src[c]);
+            } else {
+#pragma unroll
+                for (int c = 0; c < 9; ++c) tc_store_x(xg, t, c, make_uint4(0, 0, 0, 0));
+            }
+        } else {
+            uint4 s0 = make_uint4(0, 0, 0, 0), s1 = s0;
+            if (inb) {
+                const size_t ray = row / A.S;
+                float sh[16];
+                sh4_eval(__ldg(A.rays_d + ray * 3), __ldg(A.rays_d + ray * 3 + 1), __ldg(A.rays_d + ray * 3 + 2), sh);
+                s0 = make_uint4(pack_half2(sh[0], sh[1]), pack_half2(sh[2], sh[3]), pack_half2(sh[4], sh[5]), pack_half2(sh[6], sh[7]));
+                s1 = make_uint4(pack_half2(sh[8], sh[9]), pack_half2(sh[10], sh[11]), pack_half2(sh[12], sh[13]), pack_half2(sh[14], sh[15]));
+            }
+            tc_store_x(xg, t, 0, s0);
+            tc_store_x(xg, t, 1, s1);
+        }
+        // geo halves 1..15 then 1.0: the 16-half row shifted down by one half
+        uint4 g0 = make_uint4(0, 0, 0, 0), g1 = g0;
+        if (inb) {
+            g0 = __ldg(reinterpret_cast<const uint4*>(A.geo + row * 16));
+            g1 = __ldg(reinterpret_cast<const uint4*>(A.geo + row * 16) + 1);
+        }
+        const uint32_t w[9] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w, inb ? kOneH : 0u};
+        uint32_t o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = __funnelshift_r(w[i], w[i + 1], 16);
+        constexpr int c0 = NDIR / 8;
+        tc_store_x(xg, t, c0, make_uint4(o[0], o[1], o[2], o[3]));
+        tc_store_x(xg, t, c0 + 1, make_uint4(o[4], o[5], o[6], o[7]));
+        if (LIDAR) {
+            const uint32_t one2 = inb ? kOnesH2 : 0u;
+            tc_store_x(xg, t, 11, make_uint4(one2, one2, one2, one2));
+        }
+    }
+    static __device__ __forceinline__ void sink_row(const Args& A, size_t row, int, const float (&f)[16], bool live) {
+        float* p = A.dgeo16 + row * 16;
+        if (A.accumulate) {
+            if (!live) return;
+#pragma unroll
+            for (int i = 0; i < 15; ++i) p[1 + i] += f[i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < 15; ++i) p[1 + i] = f[i];
+        }
+    }
+    static __device__ __forceinline__ void sink_dead(const Args& A, size_t row, bool inb) {
+        if (A.accumulate || !inb) return;
+        float* p = A.dgeo16 + row * 16;
+#pragma unroll
+        for (int i = 1; i < 16; ++i) p[i] = 0.f;
     }
 };
 
@@ -1250,6 +1411,7 @@ constexpr size_t kBwdChunkSamples = (size_t)6 << 20;  // samples per backward ch
 struct BwdLayout {
     size_t scales;                     // 4 x {unsigned max bits, pad, float scale, float 1/scale}
     size_t wimg;                       // fp16 weight images
+    size_t wimg_tc;                    // 4 slots of operand images for the tcgen05 backward (flow, sigma, head a, head b)
     size_t g_pls, g_pld, g_dyn, g_flow; // collapsed gradient tables
     size_t tables_end;
     size_t dgeo16, dfeat, dflow, dflowfeat;
@@ -1262,6 +1424,7 @@ BwdLayout make_bwd(const nvsf_field_config_t* cfg, uint32_t N, uint32_t S) {
     size_t off = 0;
     L.scales = off; off = ws_align(off + 64);
     L.wimg = off; off = ws_align(off + (size_t)kB_Total * sizeof(bf16));
+    L.wimg_tc = off; off = ws_align(off + 4 * (size_t)mlptc::kImgSlot);
     L.g_pls = off; off = ws_align(off + W.pls_floats * sizeof(float));
     L.g_pld = off; off = ws_align(off + 3 * W.pld_floats_per_q * sizeof(float));
     L.g_dyn = off; off = ws_align(off + W.dyn_per_q * sizeof(float));
@@ -1295,6 +1458,27 @@ int launch_mlp_bwd(const typename T::Args& A, const bf16* w1, const bf16* w2, co
     const size_t tiles = (n + kBwdRows - 1) / kBwdRows;
     const int grid = (int)std::min<size_t>(tiles, (size_t)sms * per_sm);
     k_mlp_bwd<T><<<grid, kBwdWarps * 32, smem, s>>>(A, w1, w2, wo, n, G, scale2);
+    return NVSF_OK;
+}
+
+
+int g_mlp_bwd_tc = 1;   // option "mlp_bwd_tc": MLP backward on tcgen05 (mlp_bwd_tc.cuh) instead of mma.sync (k_mlp_bwd)
+
+template <class T, int W>
+int launch_mlp_bwd_tc(const typename T::Args& A, const unsigned char* img, size_t n, MlpGrads G, const float* scale2,
+                      int sms, cudaStream_t s) {
+    static bool attr = false;
+    constexpr size_t smem = mlptc::smem_bytes<T, W>();
+    static_assert(smem <= 227 * 1024, "shared memory budget");
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(mlptc::k_mlp_bwd_tc<T, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        attr = true;
+    }
+    const size_t tiles = (n + 127) / 128;
+    const int grid = (int)std::min<size_t>((tiles + W - 1) / W, (size_t)sms);
+    mlptc::Grads g{G.w1, G.w2, G.wo};
+    mlptc::k_mlp_bwd_tc<T, W><<<grid, W * 128, smem, s>>>(A, img, n, g, scale2);
     return NVSF_OK;
 }
 
@@ -1403,6 +1587,20 @@ int nvsf_render_uniform_backward(const nvsf_field_config_t* cfg, const void* wor
         pack(heads[h] + H * kin, H, H, H, hm + kB_HeadW2, kLdH);
         pack(heads[h] + H * kin + H * H, H, n_out, H, hm + kB_HeadW3, kLdH);
     }
+    // operand images of the tcgen05 backward
+    unsigned char* img_tc = sc + BL.wimg_tc;
+    if (g_mlp_bwd_tc) {
+        mlptc::pack_images<FlowTc>(params->flow_mlp, params->flow_mlp + H * kFlowIn,
+                                   params->flow_mlp + H * kFlowIn + H * H, img_tc, s);
+        mlptc::pack_images<SigmaTc>(params->sigma_net, nullptr, params->sigma_net + H * kFeat,
+                                    img_tc + mlptc::kImgSlot, s);
+        for (int h = 0; h < 2; ++h) {
+            if (!heads[h]) continue;
+            unsigned char* slot = img_tc + (2 + h) * (size_t)mlptc::kImgSlot;
+            if (lidar) mlptc::pack_images<HeadTc<true>>(heads[h], heads[h] + H * kin, heads[h] + H * kin + H * H, slot, s);
+            else mlptc::pack_images<HeadTc<false>>(heads[h], heads[h] + H * kin, heads[h] + H * kin + H * H, slot, s);
+        }
+    }
     // collapsed gradient tables
     cudaMemsetAsync(sc + BL.g_pls, 0, BL.tables_end - BL.g_pls, s);
     GradTables G;
@@ -1470,13 +1668,21 @@ int nvsf_render_uniform_backward(const nvsf_field_config_t* cfg, const void* wor
                 if (lidar) {
                     HeadT<true>::Args A{geo + begin * kGeo, rgbs + begin * 4, weights + begin,
                                         g_image + (size_t)r0 * 2, rays_d + (size_t)r0 * 3, dgeo16, S, h, h};
-                    st = launch_mlp_bwd<HeadT<true>>(A, hm + kB_HeadW1, hm + kB_HeadW2, hm + kB_HeadW3,
-                                                     count, MG, scale_h, sms, s);
+                    if (g_mlp_bwd_tc)
+                        st = launch_mlp_bwd_tc<HeadTc<true>, 2>(A, img_tc + (2 + h) * (size_t)mlptc::kImgSlot, count, MG,
+                                                                scale_h, sms, s);
+                    else
+                        st = launch_mlp_bwd<HeadT<true>>(A, hm + kB_HeadW1, hm + kB_HeadW2, hm + kB_HeadW3,
+                                                         count, MG, scale_h, sms, s);
                 } else {
                     HeadT<false>::Args A{geo + begin * kGeo, rgbs + begin * 4, weights + begin,
                                          g_image + (size_t)r0 * 3, rays_d + (size_t)r0 * 3, dgeo16, S, 0, 0};
-                    st = launch_mlp_bwd<HeadT<false>>(A, hm + kB_HeadW1, hm + kB_HeadW2, hm + kB_HeadW3,
-                                                      count, MG, scale_h, sms, s);
+                    if (g_mlp_bwd_tc)
+                        st = launch_mlp_bwd_tc<HeadTc<false>, 3>(A, img_tc + 2 * (size_t)mlptc::kImgSlot, count, MG, scale_h,
+                                                                 sms, s);
+                    else
+                        st = launch_mlp_bwd<HeadT<false>>(A, hm + kB_HeadW1, hm + kB_HeadW2, hm + kB_HeadW3,
+                                                          count, MG, scale_h, sms, s);
                 }
             }
         } else {
@@ -1489,7 +1695,10 @@ int nvsf_render_uniform_backward(const nvsf_field_config_t* cfg, const void* wor
             SigmaT::Args A{feats + begin * kFeat, dgeo16, dfeat};
             MlpGrads MG{grads->sigma_net, nullptr, grads->sigma_net + H * kFeat};
             scale_s = make_scale(1, dgeo16, count * 16, shift_mul(g_shift_sigma));
-            st = launch_mlp_bwd<SigmaT>(A, wimg + kB_SigW1, nullptr, wimg + kB_SigW2, count, MG, scale_s, sms, s);
+            if (g_mlp_bwd_tc)
+                st = launch_mlp_bwd_tc<SigmaTc, 3>(A, img_tc + mlptc::kImgSlot, count, MG, scale_s, sms, s);
+            else
+                st = launch_mlp_bwd<SigmaT>(A, wimg + kB_SigW1, nullptr, wimg + kB_SigW2, count, MG, scale_s, sms, s);
             if (st != NVSF_OK) return st;
         }
         // 4. encoders backward -> table gradients, d flow
@@ -1507,8 +1716,11 @@ int nvsf_render_uniform_backward(const nvsf_field_config_t* cfg, const void* wor
             FlowT::Args A{flowfeat + begin * kFlowIn, dflow, dflowfeat};
             MlpGrads MG{grads->flow_mlp, grads->flow_mlp + H * kFlowIn, grads->flow_mlp + H * kFlowIn + H * H};
             const float* scale_f = make_scale(2, dflow, count * 8, shift_mul(g_shift_flow));
-            st = launch_mlp_bwd<FlowT>(A, wimg + kB_FlowW1, wimg + kB_FlowW2, wimg + kB_FlowW3, count, MG,
-                                       scale_f, sms, s);
+            if (g_mlp_bwd_tc)
+                st = launch_mlp_bwd_tc<FlowTc, 3>(A, img_tc, count, MG, scale_f, sms, s);
+            else
+                st = launch_mlp_bwd<FlowT>(A, wimg + kB_FlowW1, wimg + kB_FlowW2, wimg + kB_FlowW3, count, MG,
+                                           scale_f, sms, s);
             if (st != NVSF_OK) return st;
             const unsigned blocks = (unsigned)nvsf_div_up(count, (size_t)256);
             k_flowgrid_bwd<true><<<blocks, 256, 0, s>>>(*cfg, G.flow, nullptr, rays_o, rays_d, nears, fars,
@@ -1629,6 +1841,11 @@ int nvsf_train_set_option(const char* name, int value) {
         g_enc_bwd_h16 = value;
         return NVSF_OK;
     }
+    if (std::string(name) == "mlp_bwd_tc") {
+        if (value != 0 && value != 1) return NVSF_E_INVALID;
+        g_mlp_bwd_tc = value;
+        return NVSF_OK;
+    }
     for (auto kv : {std::make_pair("bwd_shift_flow", &g_shift_flow), std::make_pair("bwd_shift_sigma", &g_shift_sigma),
                     std::make_pair("bwd_shift_heads", &g_shift_heads)})
         if (std::string(name) == kv.first) {
@@ -1641,6 +1858,7 @@ int nvsf_train_set_option(const char* name, int value) {
 int nvsf_train_get_option(const char* name) {
     if (std::string(name) == "enc_bwd_ctas") return g_enc_bwd_ctas;
     if (std::string(name) == "enc_bwd_h16") return g_enc_bwd_h16;
+    if (std::string(name) == "mlp_bwd_tc") return g_mlp_bwd_tc;
     if (std::string(name) == "bwd_shift_flow") return g_shift_flow;
     if (std::string(name) == "bwd_shift_sigma") return g_shift_sigma;
     if (std::string(name) == "bwd_shift_heads") return g_shift_heads;

@@ -172,3 +172,30 @@ def test_train_forward_equals_inference_forward(pkg, gold):
             assert out["depth"].requires_grad and not ref["depth"].requires_grad
     finally:
         L.nvsf_set_option(b"density_mode", prev)
+
+
+@pytest.mark.parametrize("tag", ["l_mid", "c_mid"])
+def test_mlp_backward_tcgen05_matches_mma_sync(pkg, gold, tag):
+    """The MLP backward on tcgen05 (csrc/mlp_bwd_tc.cuh: activations as the A operand from tensor memory, weight
+    gradients accumulated in tensor memory from MN-major views of the sample tiles; option mlp_bwd_tc, default)
+    against the mma.sync kernel k_mlp_bwd: the same fp16 operands and scales, fp32 sums in a different order."""
+    L = pkg._lib.lib()
+    case = FC.grad_case(gold, tag)
+    g = {}
+    try:
+        for tc in (0, 1):
+            assert L.nvsf_set_option(b"mlp_bwd_tc", tc) == 0 and L.nvsf_get_option(b"mlp_bwd_tc") == tc
+            m = make_model(pkg, case["ds"])
+            run_case(m, case)[0].backward()
+            g[tc] = grads_of(m, case["lidar"])
+    finally:
+        L.nvsf_set_option(b"mlp_bwd_tc", 1)
+    errs = {}
+    for name in FC.GRAD_NAMES:
+        if name not in g[0]:
+            continue
+        a, b = g[1][name].astype(np.float64), g[0][name].astype(np.float64)
+        errs[name] = float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+    print(tag, {k: f"{v:.2e}" for k, v in errs.items()})
+    for name, e in errs.items():
+        assert e < 5e-3, (name, e, errs)
