@@ -99,7 +99,7 @@ void pack_images(const float* W1, const float* W2, const float* Wo, unsigned cha
 
 template <class T, int W>
 __host__ __device__ constexpr size_t smem_bytes() {
-    return Img<T>::total + (size_t)W * (Img<T>::KB1 * kTile64 + (size_t)T::NHID * kTile64 + kDoTile) + 8 * W + 16 + 1024;
+    return Img<T>::total + (size_t)W * (Img<T>::KB1 * kTile64 + (size_t)T::NHID * kTile64 + kDoTile) + 64 + W * 128 + 1024;
 }
 template <class T, int W>
 __host__ __device__ constexpr uint32_t tmem_cols_needed() {
@@ -158,6 +158,7 @@ k_mlp_bwd_tc(const typename T::Args A, const unsigned char* __restrict__ wimg, s
     unsigned char* sm = smem_raw + (base - raw);
     const uint32_t tid = threadIdx.x, wg = tid >> 7, t = tid & 127u, wq = (tid >> 5) & 3u;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + kOffBar + 8 * W);
+    unsigned char* flags = sm + kOffBar + 64 + wg * 128;      // per row of the tile: carries gradient
 
     for (uint32_t i = tid; i < I::total / 16; i += W * 128)
         reinterpret_cast<uint4*>(sm)[i] = __ldg(reinterpret_cast<const uint4*>(wimg) + i);
@@ -202,20 +203,24 @@ k_mlp_bwd_tc(const typename T::Args A, const unsigned char* __restrict__ wimg, s
 
     const size_t n_tiles = (n + 127) / 128;
     for (size_t tile = (size_t)blockIdx.x * W + wg; tile < n_tiles; tile += (size_t)gridDim.x * W) {
-        const size_t row = tile * 128 + t;
-        const bool inb = row < n;
-        // ---- this thread's row of X and of the scaled output gradient -> the tiles ------------------------
-        uint4 o0 = make_uint4(0, 0, 0, 0), o1 = o0;
-        if (inb) T::fill_do(A, row, scale, o0, o1);
+        // ---- the scaled output gradients of the tile (loaded by the warpgroup, coalesced) --------------------
+        const size_t row0 = tile * 128;
+        T::load_do(A, row0, n, scale, dog, t);
+        wg_barrier(wg);
+        const uint4 o0 = *reinterpret_cast<const uint4*>(dog + dotile_off(t, 0));
+        const uint4 o1 = *reinterpret_cast<const uint4*>(dog + dotile_off(t, 1));
         const bool live = ((o0.x | o0.y | o0.z | o0.w | o1.x | o1.y | o1.z | o1.w) & 0x7fff7fffu) != 0;
+        flags[t] = live ? 1 : 0;
         tc_fence_before();
         if (!wg_any(wg, live)) {      // nothing flows back through this tile
-            T::sink_dead(A, row, inb);
+            T::store_dead(A, row0, n, t);
             continue;
         }
-        T::fill_x(A, row, inb, tile * 128, n, xg, t, wg, hbg);   // (heads: Hb is scratch for the per-ray encodings)
-        *reinterpret_cast<uint4*>(dog + dotile_off(t, 0)) = o0;
-        *reinterpret_cast<uint4*>(dog + dotile_off(t, 1)) = o1;
+        T::load_x(A, row0, n, xg, t, wg, hbg);   // (heads: Hb is scratch for the per-ray encodings)
+        {   // the next tile's rows start travelling towards the L2 while this one is computed
+            const size_t nrow0 = row0 + (size_t)gridDim.x * W * 128;
+            if (nrow0 < n) T::prefetch(A, nrow0, n, t);
+        }
         fence_async_smem();
         tc_fence_before();
         wg_barrier(wg);
@@ -315,18 +320,25 @@ k_mlp_bwd_tc(const typename T::Args A, const unsigned char* __restrict__ wimg, s
             }
             mbar_wait(bar, phase); phase ^= 1u;
             tc_fence_after();
+            // this thread's row of the chunk -> staging (the X tile: its last reader, the dW1 batch, has completed),
+            // 16-byte pieces XOR-swizzled by row so that neither side has bank conflicts; the warpgroup then
+            // writes the rows out coalesced
+            constexpr uint32_t kPieces = kDxChunk / 4;
 #pragma unroll
             for (uint32_t q = 0; q < kDxChunk / 16; ++q) {
                 uint32_t v[16];
                 tmem_ld16(tl + kDx + q * 16, v);
                 tmem_ld_wait();
-                float f[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) * inv_scale;
-                if (inb) T::sink_row(A, row, c * 64 + (int)q * 16, f, live);
+                for (uint32_t j = 0; j < 4; ++j)
+                    *reinterpret_cast<float4*>(xg + t * (kDxChunk * 4) + (((q * 4 + j) ^ (t & (kPieces - 1))) << 4)) =
+                        make_float4(__uint_as_float(v[4 * j]) * inv_scale, __uint_as_float(v[4 * j + 1]) * inv_scale,
+                                    __uint_as_float(v[4 * j + 2]) * inv_scale, __uint_as_float(v[4 * j + 3]) * inv_scale);
             }
             tc_fence_before();
-            if (c + 1 < kDxChunks) wg_barrier(wg);   // every thread has read the chunk before the next one lands
+            wg_barrier(wg);
+            T::store_dx(A, row0, n, c, xg, flags, t);
+            if (c + 1 < kDxChunks) wg_barrier(wg);   // staging and the chunk's TMEM columns are free again
         }
         // the next tile's first MMA batch is issued behind warpgroup barriers every thread reaches after these reads
     }

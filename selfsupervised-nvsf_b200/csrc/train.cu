@@ -469,63 +469,107 @@ struct HeadT {
 // ------------------------------------------------------------------------------------------------
 // row-wise views of the same three MLPs for the tcgen05 backward (mlp_bwd_tc.cuh): thread = row
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 __device__ __forceinline__ void tc_store_x(unsigned char* xg, uint32_t t, int chunk, uint4 v) {
     *reinterpret_cast<uint4*>(xg + (chunk >> 3) * mlptc::kTile64 + umma::swz(t, (uint32_t)chunk & 7u)) = v;
 }
 struct SigmaTc {
     static constexpr int KIN = 128, NHID = 1, LDG1 = 128, OUT_ROWS = 16, DX0 = 0, DXN = 128;
     using Args = SigmaT::Args;
-    static __device__ __forceinline__ void fill_do(const Args& A, size_t row, float scale, uint4& o0, uint4& o1) {
-        const float4* g = reinterpret_cast<const float4*>(A.dgeo16 + row * 16);
-        const float4 a = __ldg(g), b = __ldg(g + 1), c = __ldg(g + 2), d = __ldg(g + 3);
-        o0 = make_uint4(pack_half2(scale * a.x, scale * a.y), pack_half2(scale * a.z, scale * a.w),
-                        pack_half2(scale * b.x, scale * b.y), pack_half2(scale * b.z, scale * b.w));
-        o1 = make_uint4(pack_half2(scale * c.x, scale * c.y), pack_half2(scale * c.z, scale * c.w),
-                        pack_half2(scale * d.x, scale * d.y), pack_half2(scale * d.z, scale * d.w));
-    }
-    static __device__ __forceinline__ void fill_x(const Args& A, size_t row, bool inb, size_t, size_t, unsigned char* xg,
-                                                  uint32_t t, uint32_t, unsigned char*) {
-#pragma unroll 4
-        for (int c = 0; c < 16; ++c) {
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (inb) v = __ldcs(reinterpret_cast<const uint4*>(A.feats + row * 128) + c);
-            tc_store_x(xg, t, c, v);
+    // the warpgroup loads whole rows with consecutive lanes on consecutive 16 bytes (thread-per-row loads touch 32
+    // lines per instruction: ncu had this kernel at 79 % l1tex with 12 % of the issue slots used)
+    static __device__ __forceinline__ void load_do(const Args& A, size_t row0, size_t n, float scale, unsigned char* dog,
+                                                   uint32_t t) {
+        float4 g[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const size_t row = row0 + (t >> 2) + 32 * i;
+            g[i] = row < n ? __ldg(reinterpret_cast<const float4*>(A.dgeo16 + row * 16) + (t & 3)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t r = (t >> 2) + 32 * i, c4 = t & 3;
+            *reinterpret_cast<uint2*>(dog + mlptc::dotile_off(r, c4 >> 1) + (c4 & 1) * 8) =
+                make_uint2(pack_half2(scale * g[i].x, scale * g[i].y), pack_half2(scale * g[i].z, scale * g[i].w));
         }
     }
-    static __device__ __forceinline__ void sink_row(const Args& A, size_t row, int col0, const float (&f)[16], bool live) {
-        if (!live) return;   // k_encode_bwd tests dgeo16 itself and never reads the row
-        float4* d = reinterpret_cast<float4*>(A.dfeat + row * 128 + col0);
+    static __device__ __forceinline__ void load_x(const Args& A, size_t row0, size_t n, unsigned char* xg, uint32_t t,
+                                                  uint32_t, unsigned char*) {
+        uint4 v[16];   // all sixteen loads in flight before the first store
 #pragma unroll
-        for (int i = 0; i < 4; ++i) d[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+        for (int i = 0; i < 16; ++i) {
+            const size_t row = row0 + (t >> 4) + 8 * i;
+            v[i] = row < n ? __ldcs(reinterpret_cast<const uint4*>(A.feats + row * 128) + (t & 15)) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) tc_store_x(xg, (t >> 4) + 8 * i, (int)(t & 15), v[i]);
     }
-    static __device__ __forceinline__ void sink_dead(const Args&, size_t, bool) {}
+    static __device__ __forceinline__ void prefetch(const Args& A, size_t row0, size_t n, uint32_t t) {
+        const size_t rows = n - row0 < 128 ? n - row0 : 128;
+        if ((size_t)t * 64 < rows * 128) prefetch_l2(A.feats + row0 * 128 + (size_t)t * 64);
+        if ((size_t)(t + 128) * 64 < rows * 128) prefetch_l2(A.feats + row0 * 128 + (size_t)(t + 128) * 64);
+        if ((size_t)t * 32 < rows * 16) prefetch_l2(A.dgeo16 + row0 * 16 + (size_t)t * 32);
+    }
+    static __device__ __forceinline__ void store_dx(const Args& A, size_t row0, size_t n, int c, const unsigned char* stage,
+                                                    const unsigned char* flags, uint32_t t) {
+#pragma unroll 4
+        for (int i = 0; i < 16; ++i) {
+            const uint32_t r = (t >> 4) + 8 * i, j = t & 15;
+            // rows without gradient: k_encode_bwd tests dgeo16 itself and never reads them
+            if (row0 + r < n && flags[r])
+                *reinterpret_cast<float4*>(A.dfeat + (row0 + r) * 128 + 64 * c + 4 * j) =
+                    *reinterpret_cast<const float4*>(stage + r * 256 + ((j ^ (r & 15)) << 4));
+        }
+    }
+    static __device__ __forceinline__ void store_dead(const Args&, size_t, size_t, uint32_t) {}
 };
 struct FlowTc {
     static constexpr int KIN = 32, NHID = 2, LDG1 = 32, OUT_ROWS = 6, DX0 = 0, DXN = 32;
     using Args = FlowT::Args;
-    static __device__ __forceinline__ void fill_do(const Args& A, size_t row, float scale, uint4& o0, uint4& o1) {
-        const float4* g = reinterpret_cast<const float4*>(A.dflow + row * 8);
-        const float4 a = __ldg(g), b = __ldg(g + 1);
-        o0 = make_uint4(pack_half2(scale * a.x, scale * a.y), pack_half2(scale * a.z, scale * a.w),
-                        pack_half2(scale * b.x, scale * b.y), pack_half2(scale * b.z, scale * b.w));
-        o1 = make_uint4(0, 0, 0, 0);
-    }
-    static __device__ __forceinline__ void fill_x(const Args& A, size_t row, bool inb, size_t, size_t, unsigned char* xg,
-                                                  uint32_t t, uint32_t, unsigned char*) {
+    static __device__ __forceinline__ void load_do(const Args& A, size_t row0, size_t n, float scale, unsigned char* dog,
+                                                   uint32_t t) {
+        float4 g[2];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (inb) v = __ldcs(reinterpret_cast<const uint4*>(A.flowfeat + row * 32) + c);
-            tc_store_x(xg, t, c, v);
+        for (int i = 0; i < 2; ++i) {
+            const size_t row = row0 + (t >> 1) + 64 * i;
+            g[i] = row < n ? __ldg(reinterpret_cast<const float4*>(A.dflow + row * 8) + (t & 1)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+            *reinterpret_cast<uint2*>(dog + mlptc::dotile_off((t >> 1) + 64 * i, 0) + (t & 1) * 8) =
+                make_uint2(pack_half2(scale * g[i].x, scale * g[i].y), pack_half2(scale * g[i].z, scale * g[i].w));
+        *reinterpret_cast<uint4*>(dog + mlptc::dotile_off(t, 1)) = make_uint4(0, 0, 0, 0);
+    }
+    static __device__ __forceinline__ void load_x(const Args& A, size_t row0, size_t n, unsigned char* xg, uint32_t t,
+                                                  uint32_t, unsigned char*) {
+        uint4 v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const size_t row = row0 + (t >> 2) + 32 * i;
+            v[i] = row < n ? __ldcs(reinterpret_cast<const uint4*>(A.flowfeat + row * 32) + (t & 3)) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) tc_store_x(xg, (t >> 2) + 32 * i, (int)(t & 3), v[i]);
+    }
+    static __device__ __forceinline__ void prefetch(const Args& A, size_t row0, size_t n, uint32_t t) {
+        const size_t rows = n - row0 < 128 ? n - row0 : 128;
+        if ((size_t)t * 64 < rows * 32) prefetch_l2(A.flowfeat + row0 * 32 + (size_t)t * 64);
+        if ((size_t)t * 32 < rows * 8) prefetch_l2(A.dflow + row0 * 8 + (size_t)t * 32);
+    }
+    static __device__ __forceinline__ void store_dx(const Args& A, size_t row0, size_t n, int, const unsigned char* stage,
+                                                    const unsigned char* flags, uint32_t t) {
+#pragma unroll 4
+        for (int i = 0; i < 8; ++i) {
+            const uint32_t r = (t >> 3) + 16 * i, j = t & 7;
+            // rows without gradient: k_flowgrid_bwd applies the same zero test to dflow
+            if (row0 + r < n && flags[r])
+                *reinterpret_cast<float4*>(A.dflowfeat + (row0 + r) * 32 + 4 * j) =
+                    *reinterpret_cast<const float4*>(stage + r * 128 + ((j ^ (r & 7)) << 4));
         }
     }
-    static __device__ __forceinline__ void sink_row(const Args& A, size_t row, int col0, const float (&f)[16], bool live) {
-        if (!live) return;   // k_flowgrid_bwd applies the same zero test to dflow
-        float4* d = reinterpret_cast<float4*>(A.dflowfeat + row * 32 + col0);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) d[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-    }
-    static __device__ __forceinline__ void sink_dead(const Args&, size_t, bool) {}
+    static __device__ __forceinline__ void store_dead(const Args&, size_t, size_t, uint32_t) {}
 };
 template <bool LIDAR>
 struct HeadTc {
@@ -533,27 +577,39 @@ struct HeadTc {
     static constexpr int NDIR = LIDAR ? 72 : 16;
     static constexpr int DX0 = NDIR, DXN = 16;
     using Args = typename HeadT<LIDAR>::Args;
-    static __device__ __forceinline__ void fill_do(const Args& A, size_t row, float scale, uint4& o0, uint4& o1) {
-        o0 = make_uint4(0, 0, 0, 0);
-        o1 = o0;
-        const float w = __ldg(A.weights + row);
-        if (!(w > 1e-4f)) return;   // only the samples that passed the colour mask carry gradient
-        const size_t ray = row / A.S;
-        const float4 cc = __ldg(reinterpret_cast<const float4*>(A.rgbs + row * 4));
-        const float ws = scale * w;
-        if (LIDAR) {
-            const int ch = A.net == 0 ? 1 : 0;
-            const float c = ch ? cc.y : cc.x;
-            o0.x = pack_half2(ws * __ldg(A.g_image + ray * 2 + ch) * c * (1.f - c), 0.f);
-        } else {
-            o0.x = pack_half2(ws * __ldg(A.g_image + ray * 3) * cc.x * (1.f - cc.x),
-                              ws * __ldg(A.g_image + ray * 3 + 1) * cc.y * (1.f - cc.y));
-            o0.y = pack_half2(ws * __ldg(A.g_image + ray * 3 + 2) * cc.z * (1.f - cc.z), 0.f);
+    // weights / kept colours are 4 / 16 bytes per row: the row-per-thread loads are already coalesced
+    static __device__ __forceinline__ void load_do(const Args& A, size_t row0, size_t n, float scale, unsigned char* dog,
+                                                   uint32_t t) {
+        uint4 o0 = make_uint4(0, 0, 0, 0);
+        const size_t row = row0 + t;
+        const float w = row < n ? __ldg(A.weights + row) : 0.f;
+        if (w > 1e-4f) {   // only the samples that passed the colour mask carry gradient
+            const size_t ray = row / A.S;
+            const float4 cc = __ldg(reinterpret_cast<const float4*>(A.rgbs + row * 4));
+            const float ws = scale * w;
+            if (LIDAR) {
+                const int ch = A.net == 0 ? 1 : 0;
+                const float c = ch ? cc.y : cc.x;
+                o0.x = pack_half2(ws * __ldg(A.g_image + ray * 2 + ch) * c * (1.f - c), 0.f);
+            } else {
+                o0.x = pack_half2(ws * __ldg(A.g_image + ray * 3) * cc.x * (1.f - cc.x),
+                                  ws * __ldg(A.g_image + ray * 3 + 1) * cc.y * (1.f - cc.y));
+                o0.y = pack_half2(ws * __ldg(A.g_image + ray * 3 + 2) * cc.z * (1.f - cc.z), 0.f);
+            }
         }
+        *reinterpret_cast<uint4*>(dog + mlptc::dotile_off(t, 0)) = o0;
+        *reinterpret_cast<uint4*>(dog + mlptc::dotile_off(t, 1)) = make_uint4(0, 0, 0, 0);
     }
     // X row = [direction encoding (NDIR) | geo 1..15 | 1 (tcnn input padding) | lidar: 8 more ones]
-    static __device__ __forceinline__ void fill_x(const Args& A, size_t row, bool inb, size_t row0, size_t n,
-                                                  unsigned char* xg, uint32_t t, uint32_t wg, unsigned char* scratch) {
+    static __device__ __forceinline__ void load_x(const Args& A, size_t row0, size_t n, unsigned char* xg, uint32_t t,
+                                                  uint32_t wg, unsigned char* scratch) {
+        const size_t row = row0 + t;
+        const bool inb = row < n;
+        uint4 g0 = make_uint4(0, 0, 0, 0), g1 = g0;
+        if (inb) {
+            g0 = __ldg(reinterpret_cast<const uint4*>(A.geo + row * 16));
+            g1 = __ldg(reinterpret_cast<const uint4*>(A.geo + row * 16) + 1);
+        }
         if (LIDAR) {
             // tcnn Frequency (12 octaves) of (d + 1) / 2 is constant along a ray: the rays of the tile are encoded
             // once, cooperatively, into scratch (the still unused Hb tile), then every row copies its ray's 144 bytes
@@ -589,11 +645,6 @@ struct HeadTc {
             tc_store_x(xg, t, 1, s1);
         }
         // geo halves 1..15 then 1.0: the 16-half row shifted down by one half
-        uint4 g0 = make_uint4(0, 0, 0, 0), g1 = g0;
-        if (inb) {
-            g0 = __ldg(reinterpret_cast<const uint4*>(A.geo + row * 16));
-            g1 = __ldg(reinterpret_cast<const uint4*>(A.geo + row * 16) + 1);
-        }
         const uint32_t w[9] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w, inb ? kOneH : 0u};
         uint32_t o[8];
 #pragma unroll
@@ -606,22 +657,44 @@ struct HeadTc {
             tc_store_x(xg, t, 11, make_uint4(one2, one2, one2, one2));
         }
     }
-    static __device__ __forceinline__ void sink_row(const Args& A, size_t row, int, const float (&f)[16], bool live) {
-        float* p = A.dgeo16 + row * 16;
-        if (A.accumulate) {
-            if (!live) return;
+    static __device__ __forceinline__ void prefetch(const Args& A, size_t row0, size_t n, uint32_t t) {
+        const size_t rows = n - row0 < 128 ? n - row0 : 128;
+        if ((size_t)t * 32 < rows) prefetch_l2(A.weights + row0 + (size_t)t * 32);
+        if ((size_t)t * 32 < rows * 4) prefetch_l2(A.rgbs + row0 * 4 + (size_t)t * 32);
+        if ((size_t)t * 64 < rows * 16) prefetch_l2(A.geo + row0 * 16 + (size_t)t * 64);
+        if (A.accumulate && (size_t)t * 32 < rows * 16) prefetch_l2(A.dgeo16 + row0 * 16 + (size_t)t * 32);
+    }
+    // dgeo16[row][1..15] (=, +=) dX[row][0..14]; column 0 (the sigma-logit slot) is someone else's
+    static __device__ __forceinline__ void store_dx(const Args& A, size_t row0, size_t n, int, const unsigned char* stage,
+                                                    const unsigned char* flags, uint32_t t) {
 #pragma unroll
-            for (int i = 0; i < 15; ++i) p[1 + i] += f[i];
-        } else {
-#pragma unroll
-            for (int i = 0; i < 15; ++i) p[1 + i] = f[i];
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t r = (t >> 2) + 32 * i, j = t & 3;
+            if (row0 + r >= n || (A.accumulate && !flags[r])) continue;
+            auto dx = [&](int e) {   // staged element e of row r (pieces XOR-swizzled by row)
+                return *reinterpret_cast<const float*>(stage + r * 64 + ((((uint32_t)e >> 2) ^ (r & 3)) << 4) + (e & 3) * 4);
+            };
+            float4* p = reinterpret_cast<float4*>(A.dgeo16 + (row0 + r) * 16) + j;
+            float4 v = make_float4(j ? dx(4 * j - 1) : 0.f, dx(4 * j), dx(4 * j + 1), dx(4 * j + 2));
+            if (A.accumulate) {
+                const float4 o = *p;
+                v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+            } else if (j == 0) {
+                v.x = reinterpret_cast<const float*>(p)[0];
+            }
+            *p = v;
         }
     }
-    static __device__ __forceinline__ void sink_dead(const Args& A, size_t row, bool inb) {
-        if (A.accumulate || !inb) return;
-        float* p = A.dgeo16 + row * 16;
+    static __device__ __forceinline__ void store_dead(const Args& A, size_t row0, size_t n, uint32_t t) {
+        if (A.accumulate) return;
 #pragma unroll
-        for (int i = 1; i < 16; ++i) p[i] = 0.f;
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t r = (t >> 2) + 32 * i, j = t & 3;
+            if (row0 + r >= n) continue;
+            float* p = A.dgeo16 + (row0 + r) * 16 + 4 * j;
+            if (j) *reinterpret_cast<float4*>(p) = make_float4(0.f, 0.f, 0.f, 0.f);
+            else { p[1] = 0.f; p[2] = 0.f; p[3] = 0.f; }
+        }
     }
 };
 
