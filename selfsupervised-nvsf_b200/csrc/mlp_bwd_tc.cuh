@@ -35,7 +35,17 @@ using namespace umma;
 
 constexpr uint32_t kTile64 = 128 * 128;          // one [128 rows][64 halves] swizzled tile
 constexpr uint32_t kDoTile = 128 * 32;           // [128 rows][16 halves], un-swizzled core matrices (8 rows x 16 B)
+constexpr uint32_t kTile32 = 128 * 64;           // a [128 rows][32 halves] block, un-swizzled core matrices
 constexpr uint32_t kChain = 96;                  // TMEM columns of one warpgroup's chain
+// The X tile = KIN / 64 swizzled blocks of 64 columns, then (KIN % 64 == 32) one un-swizzled block of 32 columns
+// (8 KB instead of a half-empty 16 KB swizzled block: what lets a fourth chain fit for the 32-wide inputs).
+__host__ __device__ constexpr uint32_t x_bytes(int kin) { return (uint32_t)(kin / 64) * kTile64 + ((kin % 64) ? kTile32 : 0u); }
+// byte offset of 8-half chunk `chunk` of row `row` inside the X tile
+__device__ __forceinline__ uint32_t x_off(int kin, uint32_t row, uint32_t chunk) {
+    const uint32_t kb = chunk >> 3;
+    if (kb < (uint32_t)(kin / 64)) return kb * kTile64 + swz(row, chunk & 7u);
+    return (uint32_t)(kin / 64) * kTile64 + (row >> 3) * 512u + (chunk & 3u) * 128u + (row & 7u) * 16u;
+}
 
 __host__ __device__ constexpr uint32_t idesc_mn(int M, int N, int a_mn, int b_mn) {
     return (1u << 4) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |
@@ -99,7 +109,7 @@ void pack_images(const float* W1, const float* W2, const float* Wo, unsigned cha
 
 template <class T, int W>
 __host__ __device__ constexpr size_t smem_bytes() {
-    return Img<T>::total + (size_t)W * (Img<T>::KB1 * kTile64 + (size_t)T::NHID * kTile64 + kDoTile) + 64 + W * 128 + 1024;
+    return Img<T>::total + (size_t)W * (x_bytes(T::KIN) + (size_t)T::NHID * kTile64 + kDoTile) + 64 + W * 128 + 1024;
 }
 template <class T, int W>
 __host__ __device__ constexpr uint32_t tmem_cols_needed() {
@@ -148,7 +158,9 @@ k_mlp_bwd_tc(const typename T::Args A, const unsigned char* __restrict__ wimg, s
     using I = Img<T>;
     constexpr int KIN = T::KIN, NHID = T::NHID;
     constexpr uint32_t KB1 = I::KB1;
-    constexpr uint32_t kWgBytes = KB1 * kTile64 + NHID * kTile64 + kDoTile;
+    constexpr uint32_t kXBytes = x_bytes(KIN), KB64 = KIN / 64;
+    constexpr bool kStageInX = T::DXN > 32;                   // dX staging: the X tile if the chunk needs 32 KB, else Ha
+    constexpr uint32_t kWgBytes = kXBytes + NHID * kTile64 + kDoTile;
     constexpr uint32_t kOffBar = I::total + W * kWgBytes;
     static_assert(I::total % 1024 == 0 && kWgBytes % 1024 == 0, "swizzled tiles start on 1024-byte boundaries");
     static_assert(tmem_cols_needed<T, W>() <= 512, "tensor memory budget");
@@ -190,10 +202,10 @@ k_mlp_bwd_tc(const typename T::Args A, const unsigned char* __restrict__ wimg, s
     tc_fence_after();
 
     unsigned char* xg = sm + I::total + wg * kWgBytes;        // X tile(s)
-    unsigned char* hag = xg + KB1 * kTile64;                  // Ha: H1, later dH1
+    unsigned char* hag = xg + kXBytes;                        // Ha: H1, later dH1
     unsigned char* hbg = hag + kTile64;                       // Hb: H2, later dH2 (NHID == 2)
     unsigned char* dog = hag + NHID * kTile64;                // dO
-    const uint32_t xs = base + I::total + wg * kWgBytes, has = xs + KB1 * kTile64, hbs = has + kTile64,
+    const uint32_t xs = base + I::total + wg * kWgBytes, has = xs + kXBytes, hbs = has + kTile64,
                    dos = has + NHID * kTile64;
     const uint32_t bar = base + kOffBar + 8 * wg;
     const float scale = __ldg(scale2), inv_scale = __ldg(scale2 + 1);
@@ -227,9 +239,11 @@ k_mlp_bwd_tc(const typename T::Args A, const unsigned char* __restrict__ wimg, s
         if (t == 0) {   // D1 [0,64) = X W1^T
             tc_fence_after();
 #pragma unroll
-            for (uint32_t k = 0; k < (uint32_t)KIN / 16; ++k)
-                umma_f16(tc, umma_desc(xs + (k >> 2) * kTile64 + (k & 3) * 32),
-                         umma_desc(base + I::w1 + (k >> 2) * (64 * 128) + (k & 3) * 32), kId64, k);
+            for (uint32_t k = 0; k < (uint32_t)KIN / 16; ++k) {
+                const uint64_t a = (k >> 2) < KB64 ? umma_desc(xs + (k >> 2) * kTile64 + (k & 3) * 32)
+                                                   : desc_noswz(xs + KB64 * kTile64 + (k & 3) * 256, 128u, 512u);
+                umma_f16(tc, a, umma_desc(base + I::w1 + (k >> 2) * (64 * 128) + (k & 3) * 32), kId64, k);
+            }
             umma_commit(bar);
         }
         mbar_wait(bar, phase); phase ^= 1u;
@@ -306,9 +320,11 @@ k_mlp_bwd_tc(const typename T::Args A, const unsigned char* __restrict__ wimg, s
                         constexpr uint32_t last = KIN - (KB1 - 1) * 64;
                         const uint32_t nn = nb + 1 < KB1 ? 64u : last;
 #pragma unroll
-                        for (uint32_t k = 0; k < 8; ++k)
-                            umma_f16(acc_w1 + nb * 64, umma_desc(has + k * 2048), umma_desc(xs + nb * kTile64 + k * 2048),
-                                     idesc_mn(64, (int)nn, 1, 1), 1u);
+                        for (uint32_t k = 0; k < 8; ++k) {
+                            const uint64_t b = nb < KB64 ? umma_desc(xs + nb * kTile64 + k * 2048)
+                                                         : desc_noswz(xs + KB64 * kTile64 + k * 1024, 512u, 128u);
+                            umma_f16(acc_w1 + nb * 64, umma_desc(has + k * 2048), b, idesc_mn(64, (int)nn, 1, 1), 1u);
+                        }
                     }
                 }
                 // dX chunk = dH1 W1[:, DX0 + 64 c ...] : A from tensor memory, B = W1^T image rows
@@ -320,10 +336,11 @@ k_mlp_bwd_tc(const typename T::Args A, const unsigned char* __restrict__ wimg, s
             }
             mbar_wait(bar, phase); phase ^= 1u;
             tc_fence_after();
-            // this thread's row of the chunk -> staging (the X tile: its last reader, the dW1 batch, has completed),
+            // this thread's row of the chunk -> staging (the X or Ha tile: their last reader, the dW1 batch, has completed),
             // 16-byte pieces XOR-swizzled by row so that neither side has bank conflicts; the warpgroup then
             // writes the rows out coalesced
             constexpr uint32_t kPieces = kDxChunk / 4;
+            unsigned char* stage = kStageInX ? xg : hag;
 #pragma unroll
             for (uint32_t q = 0; q < kDxChunk / 16; ++q) {
                 uint32_t v[16];
@@ -331,13 +348,13 @@ k_mlp_bwd_tc(const typename T::Args A, const unsigned char* __restrict__ wimg, s
                 tmem_ld_wait();
 #pragma unroll
                 for (uint32_t j = 0; j < 4; ++j)
-                    *reinterpret_cast<float4*>(xg + t * (kDxChunk * 4) + (((q * 4 + j) ^ (t & (kPieces - 1))) << 4)) =
+                    *reinterpret_cast<float4*>(stage + t * (kDxChunk * 4) + (((q * 4 + j) ^ (t & (kPieces - 1))) << 4)) =
                         make_float4(__uint_as_float(v[4 * j]) * inv_scale, __uint_as_float(v[4 * j + 1]) * inv_scale,
                                     __uint_as_float(v[4 * j + 2]) * inv_scale, __uint_as_float(v[4 * j + 3]) * inv_scale);
             }
             tc_fence_before();
             wg_barrier(wg);
-            T::store_dx(A, row0, n, c, xg, flags, t);
+            T::store_dx(A, row0, n, c, stage, flags, t);
             if (c + 1 < kDxChunks) wg_barrier(wg);   // staging and the chunk's TMEM columns are free again
         }
         // the next tile's first MMA batch is issued behind warpgroup barriers every thread reaches after these reads

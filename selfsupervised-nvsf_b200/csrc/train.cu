@@ -472,8 +472,9 @@ struct HeadT {
 __device__ __forceinline__ void prefetch_l2(const void* p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
+template <int KIN>
 __device__ __forceinline__ void tc_store_x(unsigned char* xg, uint32_t t, int chunk, uint4 v) {
-    *reinterpret_cast<uint4*>(xg + (chunk >> 3) * mlptc::kTile64 + umma::swz(t, (uint32_t)chunk & 7u)) = v;
+    *reinterpret_cast<uint4*>(xg + mlptc::x_off(KIN, t, (uint32_t)chunk)) = v;
 }
 struct SigmaTc {
     static constexpr int KIN = 128, NHID = 1, LDG1 = 128, OUT_ROWS = 16, DX0 = 0, DXN = 128;
@@ -504,7 +505,7 @@ struct SigmaTc {
             v[i] = row < n ? __ldcs(reinterpret_cast<const uint4*>(A.feats + row * 128) + (t & 15)) : make_uint4(0, 0, 0, 0);
         }
 #pragma unroll
-        for (int i = 0; i < 16; ++i) tc_store_x(xg, (t >> 4) + 8 * i, (int)(t & 15), v[i]);
+        for (int i = 0; i < 16; ++i) tc_store_x<128>(xg, (t >> 4) + 8 * i, (int)(t & 15), v[i]);
     }
     static __device__ __forceinline__ void prefetch(const Args& A, size_t row0, size_t n, uint32_t t) {
         const size_t rows = n - row0 < 128 ? n - row0 : 128;
@@ -551,7 +552,7 @@ struct FlowTc {
             v[i] = row < n ? __ldcs(reinterpret_cast<const uint4*>(A.flowfeat + row * 32) + (t & 3)) : make_uint4(0, 0, 0, 0);
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) tc_store_x(xg, (t >> 2) + 32 * i, (int)(t & 3), v[i]);
+        for (int i = 0; i < 4; ++i) tc_store_x<32>(xg, (t >> 2) + 32 * i, (int)(t & 3), v[i]);
     }
     static __device__ __forceinline__ void prefetch(const Args& A, size_t row0, size_t n, uint32_t t) {
         const size_t rows = n - row0 < 128 ? n - row0 : 128;
@@ -627,10 +628,10 @@ struct HeadTc {
             if (inb) {
                 const uint4* src = reinterpret_cast<const uint4*>(scratch + (row / A.S - ray_a) * 144);
 #pragma unroll
-                for (int c = 0; c < 9; ++c) tc_store_x(xg, t, c, src[c]);
+                for (int c = 0; c < 9; ++c) tc_store_x<KIN>(xg, t, c, src[c]);
             } else {
 #pragma unroll
-                for (int c = 0; c < 9; ++c) tc_store_x(xg, t, c, make_uint4(0, 0, 0, 0));
+                for (int c = 0; c < 9; ++c) tc_store_x<KIN>(xg, t, c, make_uint4(0, 0, 0, 0));
             }
         } else {
             uint4 s0 = make_uint4(0, 0, 0, 0), s1 = s0;
@@ -641,8 +642,8 @@ struct HeadTc {
                 s0 = make_uint4(pack_half2(sh[0], sh[1]), pack_half2(sh[2], sh[3]), pack_half2(sh[4], sh[5]), pack_half2(sh[6], sh[7]));
                 s1 = make_uint4(pack_half2(sh[8], sh[9]), pack_half2(sh[10], sh[11]), pack_half2(sh[12], sh[13]), pack_half2(sh[14], sh[15]));
             }
-            tc_store_x(xg, t, 0, s0);
-            tc_store_x(xg, t, 1, s1);
+            tc_store_x<KIN>(xg, t, 0, s0);
+            tc_store_x<KIN>(xg, t, 1, s1);
         }
         // geo halves 1..15 then 1.0: the 16-half row shifted down by one half
         const uint32_t w[9] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w, inb ? kOneH : 0u};
@@ -650,11 +651,11 @@ struct HeadTc {
 #pragma unroll
         for (int i = 0; i < 8; ++i) o[i] = __funnelshift_r(w[i], w[i + 1], 16);
         constexpr int c0 = NDIR / 8;
-        tc_store_x(xg, t, c0, make_uint4(o[0], o[1], o[2], o[3]));
-        tc_store_x(xg, t, c0 + 1, make_uint4(o[4], o[5], o[6], o[7]));
+        tc_store_x<KIN>(xg, t, c0, make_uint4(o[0], o[1], o[2], o[3]));
+        tc_store_x<KIN>(xg, t, c0 + 1, make_uint4(o[4], o[5], o[6], o[7]));
         if (LIDAR) {
             const uint32_t one2 = inb ? kOnesH2 : 0u;
-            tc_store_x(xg, t, 11, make_uint4(one2, one2, one2, one2));
+            tc_store_x<KIN>(xg, t, 11, make_uint4(one2, one2, one2, one2));
         }
     }
     static __device__ __forceinline__ void prefetch(const Args& A, size_t row0, size_t n, uint32_t t) {
@@ -1742,7 +1743,7 @@ int nvsf_render_uniform_backward(const nvsf_field_config_t* cfg, const void* wor
                     HeadT<true>::Args A{geo + begin * kGeo, rgbs + begin * 4, weights + begin,
                                         g_image + (size_t)r0 * 2, rays_d + (size_t)r0 * 3, dgeo16, S, h, h};
                     if (g_mlp_bwd_tc)
-                        st = launch_mlp_bwd_tc<HeadTc<true>, 2>(A, img_tc + (2 + h) * (size_t)mlptc::kImgSlot, count, MG,
+                        st = launch_mlp_bwd_tc<HeadTc<true>, 3>(A, img_tc + (2 + h) * (size_t)mlptc::kImgSlot, count, MG,
                                                                 scale_h, sms, s);
                     else
                         st = launch_mlp_bwd<HeadT<true>>(A, hm + kB_HeadW1, hm + kB_HeadW2, hm + kB_HeadW3,
@@ -1751,7 +1752,7 @@ int nvsf_render_uniform_backward(const nvsf_field_config_t* cfg, const void* wor
                     HeadT<false>::Args A{geo + begin * kGeo, rgbs + begin * 4, weights + begin,
                                          g_image + (size_t)r0 * 3, rays_d + (size_t)r0 * 3, dgeo16, S, 0, 0};
                     if (g_mlp_bwd_tc)
-                        st = launch_mlp_bwd_tc<HeadTc<false>, 3>(A, img_tc + 2 * (size_t)mlptc::kImgSlot, count, MG, scale_h,
+                        st = launch_mlp_bwd_tc<HeadTc<false>, 4>(A, img_tc + 2 * (size_t)mlptc::kImgSlot, count, MG, scale_h,
                                                                  sms, s);
                     else
                         st = launch_mlp_bwd<HeadT<false>>(A, hm + kB_HeadW1, hm + kB_HeadW2, hm + kB_HeadW3,
@@ -1790,7 +1791,7 @@ int nvsf_render_uniform_backward(const nvsf_field_config_t* cfg, const void* wor
             MlpGrads MG{grads->flow_mlp, grads->flow_mlp + H * kFlowIn, grads->flow_mlp + H * kFlowIn + H * H};
             const float* scale_f = make_scale(2, dflow, count * 8, shift_mul(g_shift_flow));
             if (g_mlp_bwd_tc)
-                st = launch_mlp_bwd_tc<FlowTc, 3>(A, img_tc, count, MG, scale_f, sms, s);
+                st = launch_mlp_bwd_tc<FlowTc, 4>(A, img_tc, count, MG, scale_f, sms, s);
             else
                 st = launch_mlp_bwd<FlowT>(A, wimg + kB_FlowW1, wimg + kB_FlowW2, wimg + kB_FlowW3, count, MG,
                                            scale_f, sms, s);
