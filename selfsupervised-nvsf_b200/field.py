@@ -527,11 +527,13 @@ class NeRFNetwork(nn.Module):
         return ws
 
     # ------------------------------------------------------------------ field API
-    def _density_raw(self, x, t, lidar, want_features=False, want_flow=False):
+    def _density_raw(self, x, t, lidar, want_features=False, want_flow=False, prepared=False):
+        """`prepared`: the caller has just run prepare(t, lidar) itself (a frame time given as a CUDA tensor is
+        re-collapsed by every prepare() because its value is unknown on the host: once per frame is enough)."""
         L = _setup_lib()
         x = x.detach().to(device=self.sigma_net.device, dtype=torch.float32).contiguous().view(-1, 3)
         n = x.shape[0]
-        ws = self.prepare(t, lidar)
+        ws = self._ws[lidar] if prepared and self._ws.get(lidar) is not None else self.prepare(t, lidar)
         sigma = torch.empty(n, dtype=torch.float32, device=x.device)
         geo = torch.empty(n, 16, dtype=torch.float16, device=x.device)
         feats = torch.empty(n, 128, dtype=torch.float16, device=x.device) if want_features else None
@@ -637,12 +639,12 @@ class NeRFNetwork(nn.Module):
         return out
 
     @_lib.device_guard
-    def forward(self, x, d, t=None, cal_lidar_color=False, out_ld=None):
+    def forward(self, x, d, t=None, cal_lidar_color=False, out_ld=None, _prepared=False):
         """sigma [N] and colours [N, 2|3] of samples (x, d): density + color in two launches
         (what the march_rays* callers evaluate per batch of samples)."""
         lidar = bool(cal_lidar_color)
         with torch.no_grad():
-            sigma, geo16, _, _ = self._density_raw(x, t, lidar)
+            sigma, geo16, _, _ = self._density_raw(x, t, lidar, prepared=_prepared)
             d = d.detach().to(device=sigma.device, dtype=torch.float32).contiguous().view(-1, 3)
             rgbs = self._color_raw(d, geo16, lidar, out_ld=out_ld)
         return sigma, rgbs
@@ -775,7 +777,7 @@ class NeRFNetwork(nn.Module):
                 o, d, self.bound, bits, self.cascade, self.grid_size, nears, fars, None, cap, noises is not None,
                 -1, cap <= 0, dt_gamma, max_steps, noises)
             self.last_run_cuda_counter = raymarching.last_step_counter
-            sigmas, rgbs = self.forward(xyzs, dirs, time, lidar, out_ld=3)
+            sigmas, rgbs = self.forward(xyzs, dirs, time, lidar, out_ld=3, _prepared=True)
             if self.density_scale != 1:
                 sigmas = sigmas * self.density_scale
             weights_sum, depth, image = raymarching.composite_rays_train(sigmas, rgbs, deltas, rays, T_thresh)
@@ -808,7 +810,7 @@ class NeRFNetwork(nn.Module):
                 xyzs, dirs, deltas = raymarching.march_rays(
                     n_alive, n_step, rays_alive, rays_t, o, d, self.bound, bits, self.cascade, self.grid_size,
                     nears, fars, -1, nz is not None, dt_gamma, max_steps, nz)
-                sigmas, rgbs = self.forward(xyzs, dirs, time, lidar, out_ld=3)
+                sigmas, rgbs = self.forward(xyzs, dirs, time, lidar, out_ld=3, _prepared=True)
                 if self.density_scale != 1:
                     sigmas = sigmas * self.density_scale
                 raymarching.composite_rays(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum,

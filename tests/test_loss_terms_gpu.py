@@ -148,6 +148,15 @@ def test_flow_loss_matches_oracle(pkg, t, fwd, bwd):
         # uniform over the 16 levels and independent of the fp16 gradient scale; flow_mlp sums over all points: 2e-4
         tol = {"flow_grid": 5e-2, "flow_mlp": 1e-2}[name]
         assert err < max(tol, 2.0 * floor[name]), (name, err, floor)
+        if name == "flow_grid":
+            # ... and the error IS that tail, not a systematic offset: entry by entry the median relative error sits at
+            # the oracle's own fp16 resolution (measured 2.8e-4; the oracle's fp16 gradient cast alone gives 3.6e-4),
+            # 98 % of the touched entries agree within 1e-2 and the whole rel-L2 error lives in the ~1 % of entries
+            # behind a flipped ReLU (tools/flow_grad_debug.py prints the distribution)
+            nz = np.abs(want) > 1e-3 * np.abs(want).max()
+            r = np.abs(got[nz] - want[nz]) / np.abs(want[nz])
+            assert np.median(r) < 2e-3, np.median(r)
+            assert float((r > 1e-2).mean()) < 0.05, float((r > 1e-2).mean())
     # nothing but the flow network receives a gradient
     assert m.sigma_net.grad is None and m.hash_static_lidar.grad is None
 

@@ -47,3 +47,10 @@ print("ours vs oracle(fp16 grad cast)", rel(got, g16), " ours vs oracle(fp32 gra
 for l, lv in enumerate(cfg.flow_grid_levels):
     a, b = lv["offset"] * 8, (lv["offset"] + lv["size"]) * 8
     print(f"level {l:2d} res {lv['res']:5d} hashed {int(lv['hashed'])} |g| {np.linalg.norm(g32[a:b]):.3e} ours-vs-32 {rel(got[a:b], g32[a:b]):.4f} 16-vs-32 {rel(g16[a:b], g32[a:b]):.4f}")
+# per-entry distribution: a systematic error would move the median, flipped ReLUs leave it alone and sit in the tail
+nz = np.abs(g32) > 1e-3 * np.abs(g32).max()
+r = np.abs(got[nz] - g32[nz]) / np.abs(g32[nz])
+print("touched entries", int(nz.sum()), "median rel err", np.median(r), "p75", np.percentile(r, 75), "p90", np.percentile(r, 90),
+      "p99", np.percentile(r, 99), "frac > 1e-2", float((r > 1e-2).mean()), "frac > 5e-2", float((r > 5e-2).mean()))
+r16 = np.abs(g16[nz] - g32[nz]) / np.abs(g32[nz])
+print("oracle fp16-cast vs fp32: median", np.median(r16), "p90", np.percentile(r16, 90), "frac > 1e-2", float((r16 > 1e-2).mean()))
