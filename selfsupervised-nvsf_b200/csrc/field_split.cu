@@ -17,6 +17,8 @@
 
 #include "field_common.cuh"
 
+extern int g_flow_ts;   // sigma_tc.cu: option "flow_ts"
+
 namespace {
 
 #ifndef NVSF_ENC_UNROLL_D
@@ -835,6 +837,11 @@ int nvsf_split_set_option(const char* name, int value) {
         g_flow_tc = value;
         return NVSF_OK;
     }
+    if (k == "flow_ts") {
+        if (value != 0 && value != 1) return NVSF_E_INVALID;
+        g_flow_ts = value;
+        return NVSF_OK;
+    }
     if (k == "half_math") {
         if (value != 0 && value != 1) return NVSF_E_INVALID;
         g_half_math = value;
@@ -877,6 +884,7 @@ int nvsf_split_get_option(const char* name) {
     if (k == "sigma_tc") return g_sigma_tc;
     if (k == "fuse_sigma") return g_fuse_sigma;
     if (k == "flow_tc") return g_flow_tc;
+    if (k == "flow_ts") return g_flow_ts;
     if (k == "half_math") return g_half_math;
     if (k == "fuse_keep") return g_fuse_keep;
     return nvsf_train_get_option(name);

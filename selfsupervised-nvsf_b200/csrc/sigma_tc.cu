@@ -435,7 +435,10 @@ bool g_fused_attr = false;
 // accumulators and runs its gathers at 24 % occupancy (stall long_scoreboard); here the accumulators
 // live in TMEM and the gather threads stay at 64 registers, 32 warps per SM.
 // Outputs: flow [n,8] f32 (6 used) and the three query positions, planar qpos[9][stride].
-template <bool FROM_RAYS>
+// TS = true: the hidden activations stay in tensor memory (packed in place, the next layer's A operand) although a
+// warpgroup owns only 64 columns: the second layer runs as two N = 32 halves through columns [32,64), the first
+// half's packed result waiting in 16 registers, so that H1 [0,32) stays readable until both are done.
+template <bool FROM_RAYS, bool TS>
 __global__ void __launch_bounds__(kFlowThreads, 1)
 k_flow_tc(const __grid_constant__ nvsf_field_config_t cfg, const __grid_constant__ FieldPtrs P,
           const float* __restrict__ xin, const float* __restrict__ rays_o,
@@ -510,6 +513,57 @@ k_flow_tc(const __grid_constant__ nvsf_field_config_t cfg, const __grid_constant
                 umma_f16(tcol, umma_desc(xs + k * 32), umma_desc(w1 + k * 32), kIdesc64, k);
             umma_commit(bar);
         }
+        if (TS) {
+            constexpr uint32_t kIdesc32 = umma_idesc(kRows, 32);
+            mbar_wait(bar, phase); phase ^= 1u;
+            tc_fence_after();
+            hidden_to_tmem(tlane, tlane);                 // H1 packed in place [0,32)
+            tc_fence_before();
+            wg_barrier(wg);
+            uint32_t h2[2][16];
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                if (t == 0) {   // D2 half [32,64) = H1 W2[32 half .. 32 half + 32)^T, A from tensor memory
+                    tc_fence_after();
+#pragma unroll
+                    for (uint32_t k = 0; k < 4; ++k)
+                        umma_f16_ts(tcol + 32, tcol + 8 * k, umma_desc(w2 + half * (32 * 128) + k * 32), kIdesc32, k);
+                    umma_commit(bar);
+                }
+                mbar_wait(bar, phase); phase ^= 1u;
+                tc_fence_after();
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    uint32_t v[16];
+                    tmem_ld16(tlane + 32 + q * 16, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        h2[half][8 * q + i] = pack_half2_relu(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+                }
+                tc_fence_before();
+                wg_barrier(wg);   // every thread has read the half before the next MMA batch lands in [32,64)
+            }
+            {   // H2 = [half 0 | half 1] packed over H1 [0,32): both halves' MMAs have read it
+                uint32_t o[8];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) o[i] = h2[q >> 1][(q & 1) * 8 + i];
+                    tmem_st8(tlane + q * 8, o);
+                }
+                tmem_st_wait();
+            }
+            tc_fence_before();
+            wg_barrier(wg);
+            if (t == 0) {   // D3 [32,48) = H2 W3^T
+                tc_fence_after();
+#pragma unroll
+                for (uint32_t k = 0; k < 4; ++k)
+                    umma_f16_ts(tcol + 32, tcol + 8 * k, umma_desc(w3 + k * 32), kIdesc16, k);
+                umma_commit(bar);
+            }
+        } else {
         // two hidden layers: D -> relu -> fp16 tile -> next MMA batch
 #pragma unroll 1
         for (int layer = 0; layer < 2; ++layer) {
@@ -539,12 +593,13 @@ k_flow_tc(const __grid_constant__ nvsf_field_config_t cfg, const __grid_constant
                 umma_commit(bar);
             }
         }
+        }
         mbar_wait(bar, phase);
         phase ^= 1u;
         tc_fence_after();
         {
             uint32_t v[16];
-            tmem_ld16(tlane, v);
+            tmem_ld16(tlane + (TS ? 32u : 0u), v);
             tmem_ld_wait();
             if (live) {
                 const float4 f0 = make_float4(round_f16(__uint_as_float(v[0])), round_f16(__uint_as_float(v[1])),
@@ -577,6 +632,10 @@ k_flow_tc(const __grid_constant__ nvsf_field_config_t cfg, const __grid_constant
 bool g_flow_attr = false;
 
 }  // namespace
+
+int g_flow_ts = 0;   // option "flow_ts": hidden activations of the flow MLP kept in tensor memory (k_flow_tc<., true>);
+                     // measured neutral (5.73 vs 5.70 ms per LiDAR frame: the stage is bound by its 128 global gathers
+                     // per sample — 55 % of the L1 data pipe against 9 % + 11 % for the operand tiles), off by default
 
 size_t nvsf_sigma_tc_image_bytes() { return 2 * (size_t)(kW1Bytes + kW2Bytes); }
 
@@ -631,23 +690,29 @@ int nvsf_launch_flow_tc(const nvsf_field_config_t* cfg, const FieldPtrs& P, cons
                         const float* noise, uint32_t S, size_t begin, size_t count, float* flow_out,
                         float* qpos, size_t stride, __half* flowfeat, int sms, cudaStream_t stream) {
     if (!g_flow_attr) {
-        cudaError_t e = cudaFuncSetAttribute(k_flow_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(k_flow_tc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)kFlowSmem);
-        if (e != cudaSuccess) return (int)e;
-        e = cudaFuncSetAttribute(k_flow_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)kFlowSmem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(k_flow_tc<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFlowSmem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(k_flow_tc<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFlowSmem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(k_flow_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFlowSmem);
         if (e != cudaSuccess) return (int)e;
         g_flow_attr = true;
     }
     const size_t tiles = (count + kRows - 1) / kRows;
     const int grid = (int)std::min<size_t>((tiles + kFlowWG - 1) / kFlowWG, (size_t)sms);
-    if (x)
-        k_flow_tc<false><<<grid, kFlowThreads, kFlowSmem, stream>>>(
-            *cfg, P, x, nullptr, nullptr, nullptr, nullptr, nullptr, 1, begin, count, flow_out, qpos, stride,
-            flowfeat);
-    else
-        k_flow_tc<true><<<grid, kFlowThreads, kFlowSmem, stream>>>(
-            *cfg, P, nullptr, rays_o, rays_d, nears, fars, noise, S, begin, count, flow_out, qpos, stride,
-            flowfeat);
+#define NVSF_FLOW_TC(FR, TSV, XP, ...)                                                                      \
+    k_flow_tc<FR, TSV><<<grid, kFlowThreads, kFlowSmem, stream>>>(*cfg, P, XP, __VA_ARGS__, begin, count, flow_out, \
+                                                                  qpos, stride, flowfeat)
+    if (x) {
+        if (g_flow_ts) NVSF_FLOW_TC(false, true, x, nullptr, nullptr, nullptr, nullptr, nullptr, 1);
+        else NVSF_FLOW_TC(false, false, x, nullptr, nullptr, nullptr, nullptr, nullptr, 1);
+    } else {
+        if (g_flow_ts) NVSF_FLOW_TC(true, true, nullptr, rays_o, rays_d, nears, fars, noise, S);
+        else NVSF_FLOW_TC(true, false, nullptr, rays_o, rays_d, nears, fars, noise, S);
+    }
+#undef NVSF_FLOW_TC
     return NVSF_OK;
 }

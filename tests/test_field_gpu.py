@@ -288,12 +288,23 @@ def test_flow_stage_tcgen05_matches_mma_sync(pkg, model, t):
             torch.cuda.synchronize()
             out[tc] = (np.concatenate([host(f["flow_forward"]), host(f["flow_backward"])], -1),
                        host(den["sigma"]), host(den["geo_feat"]))
+        # option flow_ts: the hidden activations stay in tensor memory (second layer as two N = 32 halves): the
+        # same products and fp16 roundings as the shared-memory form -> bit-identical
+        assert L.nvsf_set_option(b"flow_ts", 1) == 0 and L.nvsf_get_option(b"flow_ts") == 1
+        f = model.flow(x, t)
+        den = model.density(x, t, True)
+        torch.cuda.synchronize()
+        out[2] = (np.concatenate([host(f["flow_forward"]), host(f["flow_backward"])], -1),
+                  host(den["sigma"]), host(den["geo_feat"]))
     finally:
         L.nvsf_set_option(b"flow_tc", 1)
+        L.nvsf_set_option(b"flow_ts", 0)
     assert np.abs(out[0][0]).max() > 1e-4
     close(out[1][0], out[0][0], 2e-3, 2e-3 * np.abs(out[0][0]).max(), "flow tcgen05 vs mma.sync")
     close(out[1][1], out[0][1], 2e-3, 0, "sigma")
     close(out[1][2], out[0][2], 2e-3, 2e-3 * np.abs(out[0][2]).max(), "geo")
+    for a, b in zip(out[2], out[1]):
+        assert np.array_equal(a, b)
 
 
 @pytest.mark.parametrize("n", [1, 7, 127, 129, 1025])
