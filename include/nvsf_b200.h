@@ -252,7 +252,17 @@ int nvsf_field_color(const nvsf_field_config_t* cfg, const void* workspace, uint
  * stage fused with the sigma MLP on tcgen05 (feature rows stay on the SM), "sigma_tc" = stand-alone
  * sigma stage on tcgen05 (when not fused).  "enc_pair" (default 0) = paired static-hash corner loads.
  * "dyn_tile" (samples per work item), "dyn_overhead", "split_chunk" (units of 64 K samples) tune
- * the staged evaluation.  nvsf_get_option returns the current value (NVSF_E_INVALID: unknown name). */
+ * the staged evaluation.  "flow_ts" (default 0) = hidden activations of the flow MLP kept in tensor memory.
+ * "heads_tc" = head MLPs of the compositor: 0 mma.sync; 1 tcgen05, four warpgroups, the two LiDAR nets
+ * overlapped; 2..5 eight / six / five / seven warpgroups, nets in turn, direction term through a second layer-1
+ * MMA; 6 (default) = five warpgroups with the activations as the A operand from tensor memory.
+ * Backward: "mlp_bwd_tc" (default 1) = MLP backward on tcgen05 with the weight gradients accumulated in tensor
+ * memory, 0 = mma.sync; "enc_bwd_h16" (default 1) = product-rule texels from the fp16 plane mirrors;
+ * "enc_bwd_ctas" (2 | 3); "bwd_shift_flow" / "_sigma" / "_heads" = extra binades of the fp16 gradient scale.
+ * "march_mode", "composite_mode", "composite_bwd_mode" pick the operator kernel variants (default: per size).
+ * These are process-wide development A/B switches (not per-model state; set them before starting worker
+ * threads); the defaults are the fastest measured configuration.
+ * nvsf_get_option returns the current value (NVSF_E_INVALID: unknown name). */
 int nvsf_set_option(const char* name, int value);
 int nvsf_get_option(const char* name);
 int nvsf_density_mode_get(void); /* current "density_mode" */
