@@ -705,6 +705,34 @@ def main():
         dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
     e2e_value = world * N * args.steps / (float(t_max.item()) * 1e-3)
 
+    # ---- the same frame from a sensor pose: rays generated on the device in the renderer's stream
+    #      (NeRFNetwork.render_frame; the frame's host input is the 4x4 pose, 64 bytes) ----
+    R_np, t_np = S.random_pose(rank)
+    pose_np = np.eye(4, dtype=np.float32)
+    pose_np[:3, :3], pose_np[:3, 3] = R_np.astype(np.float32), t_np.astype(np.float32)
+    pose_pin = torch.from_numpy(pose_np).pin_memory()
+    depth_f = torch.empty(S.LIDAR_H, S.LIDAR_W).pin_memory(); image_f = torch.empty(S.LIDAR_H, S.LIDAR_W, 2).pin_memory()
+
+    def pose_step(k):
+        r = model.render_frame(pose_pin, (S.LIDAR_FOV_UP, S.LIDAR_FOV), S.LIDAR_H, S.LIDAR_W, t_dev[k].view(1, 1),
+                               cal_lidar_color=True, intrinsics_hoz=(S.LIDAR_FOV_UP, S.LIDAR_FOV_HOZ), num_steps=Sn)
+        depth_f.copy_(r["depth_lidar"], non_blocking=True); image_f.copy_(r["image_lidar"], non_blocking=True)
+
+    for k in range(args.warmup):
+        pose_step(k)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for k in range(args.steps):
+        pose_step(args.warmup + k)
+    e1.record()
+    barrier()
+    pose_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
+    t_max = torch.tensor([pose_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
+    pose_value = world * N * args.steps / (float(t_max.item()) * 1e-3)
+
     # ---- joint training step (configs[2]; configs[4] = 64 K rays per GPU when N > 1) ----
     train = {}
     del scratch
@@ -808,6 +836,9 @@ def main():
                                  "time_collapse_and_gaps": ms_total / args.steps - dens_ms - comp_ms}},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(2 * N * 3 * 4), "d2h_bytes_per_step": int(N * 3 * 4)},
+        "e2e_from_pose": {"value": pose_value, "unit": UNIT, "h2d_bytes_per_step": 64, "d2h_bytes_per_step": int(N * 3 * 4),
+                          "what": "NeRFNetwork.render_frame: pinned 4x4 pose -> device, rays generated on the device in the "
+                                  "renderer's stream (get_lidar_rays kernel), render, depth / image -> host"},
         "gpu_launches": (9 + 1 + kernels_per_chunk * n_launch // args.steps) * args.steps,
         "roofline": roof,
     }

@@ -228,7 +228,8 @@ k_mlp_bwd_tc(const typename T::Args A, const unsigned char* __restrict__ wimg, s
             T::store_dead(A, row0, n, t);
             continue;
         }
-        T::load_x(A, row0, n, xg, t, wg, hbg);   // (heads: Hb is scratch for the per-ray encodings)
+        T::load_x(A, row0, n, xg, t, wg, hag);   // (heads: Ha + Hb, still unused, are scratch for the per-ray encodings:
+                                                 //  up to 128 rays x 144 B when every row is its own ray)
         {   // the next tile's rows start travelling towards the L2 while this one is computed
             const size_t nrow0 = row0 + (size_t)gridDim.x * W * 128;
             if (nrow0 < n) T::prefetch(A, nrow0, n, t);

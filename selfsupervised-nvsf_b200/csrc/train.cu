@@ -381,10 +381,14 @@ struct HeadT {
                 *reinterpret_cast<uint4*>(Ds + r * kLdD) = make_uint4(0, 0, 0, 0);
                 *reinterpret_cast<uint4*>(Ds + r * kLdD + 8) = make_uint4(0, 0, 0, 0);
             }
-            if (LIDAR) __syncthreads();
-            return;
+            // (no early return on the LiDAR path: the barrier below must be reached by every thread through the
+            //  SAME instruction — a tile whose last row falls inside a warp used to arrive at two different
+            //  __syncthreads() from one divergent warp and never left)
+            if (!LIDAR) return;
         }
-        const size_t ray = g / A.S;
+        const bool inb = g < n;
+        const size_t ray = inb ? g / A.S : 0;
+        if (inb) {
         // geo features: 16 halves; cols NDIR + (0..14) = geo[1..15], col NDIR+15 = 1 (padding)
         const __half* gh0 = reinterpret_cast<const __half*>(&pf.g0);
         const __half* gh1 = reinterpret_cast<const __half*>(&pf.g1);
@@ -431,10 +435,11 @@ struct HeadT {
             }
             if (LIDAR) *reinterpret_cast<uint4*>(xr + 88) = make_uint4(kOnesH2, kOnesH2, kOnesH2, kOnesH2);
         }
+        }
         if (LIDAR) {
             __syncthreads();
             const size_t first = ray * A.S > row0 ? ray * A.S : row0;
-            if (first != g) {   // 36 halves = 9 x 8 bytes of the ray's encoding
+            if (inb && first != g) {   // 36 halves = 9 x 8 bytes of the ray's encoding
                 const uint2* src = reinterpret_cast<const uint2*>(Xs + (first - row0) * LDX + half * 36);
                 uint2* dst = reinterpret_cast<uint2*>(xr + half * 36);
 #pragma unroll
@@ -613,7 +618,7 @@ struct HeadTc {
         }
         if (LIDAR) {
             // tcnn Frequency (12 octaves) of (d + 1) / 2 is constant along a ray: the rays of the tile are encoded
-            // once, cooperatively, into scratch (the still unused Hb tile), then every row copies its ray's 144 bytes
+            // once, cooperatively, into scratch (the still unused Ha / Hb tiles), then every row copies its ray's 144 bytes
             const size_t last = (row0 + 128 < n ? row0 + 128 : n) - 1;
             const size_t ray_a = row0 / A.S;
             const int nr = (int)(last / A.S - ray_a) + 1;

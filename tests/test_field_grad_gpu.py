@@ -199,3 +199,28 @@ def test_mlp_backward_tcgen05_matches_mma_sync(pkg, gold, tag):
     print(tag, {k: f"{v:.2e}" for k, v in errs.items()})
     for name, e in errs.items():
         assert e < 5e-3, (name, e, errs)
+
+
+@pytest.mark.parametrize("lidar,N,Sn", [(True, 5, 7), (False, 3, 50), (True, 2, 300), (False, 130, 1), (True, 300, 1)])
+def test_mlp_backward_tcgen05_tiny_and_ragged(pkg, lidar, N, Sn):
+    """Row counts below one 128-row tile, tiles that hold several rays (the per-ray direction encodings of the LiDAR
+    heads), rays longer than a tile, one sample per ray: tcgen05 backward == mma.sync backward on every gradient."""
+    L = pkg._lib.lib()
+    o, d = (S.lidar_rays if lidar else S.camera_rays)(N, seed=11)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    sfx = "_lidar" if lidar else ""
+    g = {}
+    try:
+        for tc in (0, 1):
+            assert L.nvsf_set_option(b"mlp_bwd_tc", tc) == 0
+            m = make_model(pkg, 1.0)
+            out = m.render(dev(o)[None], dev(d)[None], torch.tensor([[0.6]], device="cuda"), cal_lidar_color=lidar,
+                           staged=False, num_steps=Sn)
+            (out["depth" + sfx].sum() + 3.0 * out["image" + sfx].sum() + 0.5 * out["weights_sum" + sfx].sum()).backward()
+            g[tc] = grads_of(m, lidar)
+    finally:
+        L.nvsf_set_option(b"mlp_bwd_tc", 1)
+    for name in FC.GRAD_NAMES:
+        a, b = g[1][name].astype(np.float64), g[0][name].astype(np.float64)
+        assert np.isfinite(a).all()
+        assert np.linalg.norm(a - b) <= 5e-3 * max(np.linalg.norm(b), 1e-30), (name, np.linalg.norm(a - b), np.linalg.norm(b))

@@ -208,6 +208,17 @@ def test_grid_cell_points_bit_exact(pkg, SO):
         assert L.nvsf_grid_cell_points(C, H, bound, nz.data_ptr() if with_noise else None, xyz.data_ptr(),
                                        None) == 0
         assert_bits_equal(host(xyz), SO.grid_cell_points(C, H, bound, noise), f"cell points C={C} H={H}")
+        # a slice of the cells (multi-GPU update: one slice per rank) equals the same rows of the whole grid
+        first, count = n // 3 + 5, n // 5 + 3
+        part = torch.empty(count, 3, device="cuda")
+        nzp = nz[first:first + count].contiguous() if with_noise else None
+        assert L.nvsf_grid_cell_points_range(C, H, bound, nzp.data_ptr() if with_noise else None, first, count,
+                                             part.data_ptr(), None) == 0
+        assert torch.equal(part, xyz[first:first + count])
+    x = torch.empty(8, 3, device="cuda")
+    assert L.nvsf_grid_cell_points_range(1, 16, 1.0, None, 16 ** 3 + 1, 0, x.data_ptr(), None) == -1   # first > n
+    assert L.nvsf_grid_cell_points_range(1, 16, 1.0, None, 16 ** 3 - 4, 8, x.data_ptr(), None) == -1  # runs past the end
+    assert L.nvsf_grid_cell_points_range(1, 16, 1.0, None, 16 ** 3, 0, x.data_ptr(), None) == 0       # empty slice
 
 
 def test_grid_update_vs_oracle(pkg, SO):
