@@ -260,8 +260,11 @@ int nvsf_field_color(const nvsf_field_config_t* cfg, const void* workspace, uint
  * memory, 0 = mma.sync; "enc_bwd_h16" (default 1) = product-rule texels from the fp16 plane mirrors;
  * "enc_bwd_ctas" (2 | 3); "bwd_shift_flow" / "_sigma" / "_heads" = extra binades of the fp16 gradient scale.
  * "march_mode", "composite_mode", "composite_bwd_mode" pick the operator kernel variants (default: per size).
- * These are process-wide development A/B switches (not per-model state; set them before starting worker
- * threads); the defaults are the fastest measured configuration.
+ * In the C ABI these are process-wide switches that the launch code reads on the host at launch time (the
+ * defaults are the fastest measured configuration).  The host mirror gives them per-model meaning: a
+ * NeRFNetwork carries its own `options` and every one of its entry points (autograd backward included) runs
+ * inside `_lib.option_scope(model.options)` — one re-entrant lock around "apply the overrides, enqueue the
+ * launches, restore" — so two models / worker threads in one process never see each other's settings.
  * nvsf_get_option returns the current value (NVSF_E_INVALID: unknown name). */
 int nvsf_set_option(const char* name, int value);
 int nvsf_get_option(const char* name);

@@ -6,7 +6,9 @@ crosses the boundary.  There is no fallback — if the library is missing or a
 call fails the caller gets an exception.
 """
 import ctypes
+import contextlib
 import functools
+import threading
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -150,6 +152,47 @@ def check(status, what=""):
         raise NvsfError(f"{what}: {msg} (status {status})")
 
 
+# ---- tuning options: process-wide in the C ABI, per model in this host mirror ----------------------------------
+# nvsf_set_option writes process-wide switches that the launch code reads on the host at launch time.  The host
+# mirror gives them per-model meaning and makes them safe with worker threads: every entry point of NeRFNetwork
+# runs inside option_scope(model.options) — one re-entrant lock around "apply this model's overrides, enqueue the
+# launches, restore" (the kernels themselves run asynchronously, outside the lock).
+_OPTION_LOCK = threading.RLock()
+
+
+@contextlib.contextmanager
+def option_scope(overrides=None):
+    """Hold the option lock; with `overrides` ({name: int}) set them for the duration and restore the previous
+    values afterwards.  Unknown names / rejected values raise NvsfError before anything is launched."""
+    with _OPTION_LOCK:
+        if not overrides:
+            yield
+            return
+        L = lib()
+        saved = []
+        try:
+            for name, value in overrides.items():
+                key = name.encode()
+                old = L.nvsf_get_option(key)
+                check(L.nvsf_set_option(key, int(value)), f"set_option({name}={value})")
+                saved.append((key, old))
+            yield
+        finally:
+            for key, old in reversed(saved):
+                L.nvsf_set_option(key, old)
+
+
+def with_options(fn):
+    """Method decorator: run under option_scope(self.options) (see above)."""
+
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kwargs):
+        with option_scope(getattr(self, "options", None)):
+            return fn(self, *args, **kwargs)
+
+    return wrapper
+
+
 def ptr(t):
     """Raw device pointer of a tensor (None -> NULL)."""
     if t is None:
@@ -182,9 +225,11 @@ def device_guard(fn):
                 if p is not None and p.is_cuda:
                     dev = p.device
                     break
-        if dev is None or dev.index == torch.cuda.current_device():
-            return fn(*args, **kwargs)
-        with torch.cuda.device(dev):
-            return fn(*args, **kwargs)
+        # the option lock: a launch never observes another thread's model-scoped overrides half applied
+        with _OPTION_LOCK:
+            if dev is None or dev.index == torch.cuda.current_device():
+                return fn(*args, **kwargs)
+            with torch.cuda.device(dev):
+                return fn(*args, **kwargs)
 
     return wrapper

@@ -177,6 +177,11 @@ class _RenderUniformTrain(torch.autograd.Function):
     @staticmethod
     @_lib.device_guard
     def backward(ctx, g_depth, g_image, g_wsum, g_weights, _g_z):
+        with _lib.option_scope(ctx.model.options):   # the autograd thread runs under the model's own options too
+            return _RenderUniformTrain._backward(ctx, g_depth, g_image, g_wsum, g_weights, _g_z)
+
+    @staticmethod
+    def _backward(ctx, g_depth, g_image, g_wsum, g_weights, _g_z):
         L = _setup_lib()
         model, lidar, S = ctx.model, ctx.lidar, ctx.S
         o, d, nears, fars, noise, saved, weights, ws = ctx.tensors
@@ -243,6 +248,11 @@ class _FlowTrain(torch.autograd.Function):
     @staticmethod
     @_lib.device_guard
     def backward(ctx, g_flow):
+        with _lib.option_scope(ctx.model.options):
+            return _FlowTrain._backward(ctx, g_flow)
+
+    @staticmethod
+    def _backward(ctx, g_flow):
         L = _setup_lib()
         model = ctx.model
         x, flowfeat, ws, scratch = ctx.tensors
@@ -282,8 +292,11 @@ class NeRFNetwork(nn.Module):
                  lidar_max_depth=0.81, density_thresh=0.01, bg_radius=-1, active_sensor=False,
                  hash_size_dynamic=(15, 13, 13), flow_levels=16, flow_features=8,
                  flow_base_resolution=32, flow_max_resolution=8192, flow_log2_hashmap_size=18,
-                 device="cuda", **kwargs):
+                 device="cuda", options=None, **kwargs):
         super().__init__()
+        # per-model tuning options ({name: int}, the names of nvsf_set_option): applied around this model's launches
+        # only (_lib.option_scope); None / {} = the process defaults
+        self.options = dict(options) if options else {}
         fixed = dict(n_levels_plane=(n_levels_plane, 4), n_features_per_level_plane=(n_features_per_level_plane, 8),
                      n_levels_hash=(n_levels_hash, 8), n_features_per_level_hash=(n_features_per_level_hash, 4),
                      num_layers_flow=(num_layers_flow, 3), hidden_dim_flow=(hidden_dim_flow, 64),
@@ -554,6 +567,7 @@ class NeRFNetwork(nn.Module):
                                  "torch.no_grad() (gradients flow through run() / render() / flow())")
 
     @_lib.device_guard
+    @_lib.with_options
     def density(self, x, t=None, cal_lidar_color=False, **kwargs):
         """x [N,3] in [-bound,bound] -> {'sigma' [N] f32, 'geo_feat' [N,15] f16}."""
         self._no_autograd("density", bool(cal_lidar_color))
@@ -565,6 +579,7 @@ class NeRFNetwork(nn.Module):
         return {"sigma": sigma, "geo_feat": geo[:, 1:]}
 
     @_lib.device_guard
+    @_lib.with_options
     def flow(self, x, t):
         """NeRFNetwork.flow (network_dynamic.py:197-211): x [N,3] in [-bound,bound] -> forward / backward
         scene flow [N,3] each.  Differentiable with respect to flow_grid / flow_mlp when autograd is
@@ -581,6 +596,7 @@ class NeRFNetwork(nn.Module):
 
     @torch.no_grad()
     @_lib.device_guard
+    @_lib.with_options
     def features(self, x, t, cal_lidar_color=False):
         """Debug/test hook: the 120 sigma-net inputs [N,120] (fp16) and the flow [N,6]."""
         _, _, feats, f = self._density_raw(x, t, bool(cal_lidar_color), want_features=True, want_flow=True)
@@ -598,6 +614,7 @@ class NeRFNetwork(nn.Module):
         return out
 
     @_lib.device_guard
+    @_lib.with_options
     def color(self, x, d, geo_feat, mask=None, cal_lidar_color=False, **kwargs):
         self._no_autograd("color", bool(cal_lidar_color))
         with torch.no_grad():
@@ -639,6 +656,7 @@ class NeRFNetwork(nn.Module):
         return out
 
     @_lib.device_guard
+    @_lib.with_options
     def forward(self, x, d, t=None, cal_lidar_color=False, out_ld=None, _prepared=False):
         """sigma [N] and colours [N, 2|3] of samples (x, d): density + color in two launches
         (what the march_rays* callers evaluate per batch of samples)."""
@@ -674,6 +692,7 @@ class NeRFNetwork(nn.Module):
 
     @torch.no_grad()
     @_lib.device_guard
+    @_lib.with_options
     def update_extra_state(self, time=0.0, cal_lidar_color=False, decay=0.95, perturb=True, noise=None,
                            process_group=None, shard=None):
         """Full occupancy-grid update (torch-ngp NeRFRenderer.update_extra_state, the caller the
@@ -736,6 +755,7 @@ class NeRFNetwork(nn.Module):
     # ------------------------------------------------------------------ march_rays* render loops
     @torch.no_grad()
     @_lib.device_guard
+    @_lib.with_options
     def run_cuda(self, rays_o, rays_d, time, cal_lidar_color=False, dt_gamma=0.0, bg_color=None, perturb=False,
                  max_steps=1024, T_thresh=1e-4, one_shot=None, noises=None, density_bitfield=None,
                  step_scale=16, sample_capacity=None, **kwargs):
@@ -834,6 +854,7 @@ class NeRFNetwork(nn.Module):
 
     # ------------------------------------------------------------------ renderer API
     @_lib.device_guard
+    @_lib.with_options
     def run(self, rays_o, rays_d, time, cal_lidar_color=False, num_steps=768, upsample_steps=128,
             bg_color=None, perturb=False, noise=None, return_weights=True, **kwargs):
         """NeRFRenderer.run (renderer_dynamic.py:109-265).  `noise` [N,num_steps] optionally
@@ -928,6 +949,7 @@ class NeRFNetwork(nn.Module):
         return out
 
     @_lib.device_guard
+    @_lib.with_options
     def render(self, rays_o, rays_d, time, cal_lidar_color=False, staged=False, max_ray_batch=4096, **kwargs):
         """NeRFRenderer.render (renderer_dynamic.py:267-326).  staged=True returns only depth and
         image like the reference; the whole frame is rendered by one launch pair per
@@ -940,6 +962,7 @@ class NeRFNetwork(nn.Module):
 
     @torch.no_grad()
     @_lib.device_guard
+    @_lib.with_options
     def render_frame(self, pose, intrinsics, H, W, time, cal_lidar_color=False, intrinsics_hoz=None, **kwargs):
         """Full-frame render from a sensor pose: ray generation (get_lidar_rays / get_rays,
         dataset_utils.py:369-687) runs on the device in the same stream as the renderer, so a frame's only

@@ -88,3 +88,44 @@ def test_missing_library_fails_loudly(pkg, monkeypatch):
     monkeypatch.setattr(pkg._lib, "LIB_PATH", "/nonexistent/libnvsf_b200.so")
     with pytest.raises(ImportError):
         pkg._lib.lib()
+
+
+def test_option_scope_is_per_model_and_restores():
+    """Tuning options are process-wide in the C ABI; the host mirror applies a model's own overrides only around
+    that model's launches (one re-entrant lock) and restores the previous values — also when the body raises."""
+    import importlib
+    import threading
+    pkg = importlib.import_module("selfsupervised-nvsf_b200")
+    L = pkg._lib.lib()
+    base = L.nvsf_get_option(b"heads_tc"), L.nvsf_get_option(b"mlp_bwd_tc")
+    with pkg._lib.option_scope({"heads_tc": 2, "mlp_bwd_tc": 0}):
+        assert (L.nvsf_get_option(b"heads_tc"), L.nvsf_get_option(b"mlp_bwd_tc")) == (2, 0)
+        with pkg._lib.option_scope({"heads_tc": 4}):      # re-entrant (render -> autograd backward)
+            assert L.nvsf_get_option(b"heads_tc") == 4
+        assert L.nvsf_get_option(b"heads_tc") == 2
+    assert (L.nvsf_get_option(b"heads_tc"), L.nvsf_get_option(b"mlp_bwd_tc")) == base
+    with pytest.raises(pkg._lib.NvsfError):
+        with pkg._lib.option_scope({"heads_tc": 2, "no_such_option": 1}):
+            pass
+    assert L.nvsf_get_option(b"heads_tc") == base[0]      # the first override was rolled back
+    with pytest.raises(RuntimeError):
+        with pkg._lib.option_scope({"heads_tc": 3}):
+            raise RuntimeError("body failed")
+    assert L.nvsf_get_option(b"heads_tc") == base[0]
+
+    # another thread cannot observe (or disturb) the overrides of a scope in progress
+    seen, inside, go = [], threading.Event(), threading.Event()
+
+    def other():
+        inside.wait()
+        with pkg._lib.option_scope():          # what every NeRFNetwork entry point does
+            seen.append(L.nvsf_get_option(b"heads_tc"))
+
+    th = threading.Thread(target=other)
+    th.start()
+    with pkg._lib.option_scope({"heads_tc": 1}):
+        inside.set()
+        go.wait(0.2)                            # the other thread is blocked on the lock meanwhile
+        assert seen == []
+    th.join()
+    assert seen == [base[0]]

@@ -224,3 +224,30 @@ def test_mlp_backward_tcgen05_tiny_and_ragged(pkg, lidar, N, Sn):
         a, b = g[1][name].astype(np.float64), g[0][name].astype(np.float64)
         assert np.isfinite(a).all()
         assert np.linalg.norm(a - b) <= 5e-3 * max(np.linalg.norm(b), 1e-30), (name, np.linalg.norm(a - b), np.linalg.norm(b))
+
+
+@pytest.mark.parametrize("lidar,N,Sn", [(True, 37, 37), (False, 21, 150)])
+def test_ragged_shapes_match_cpu_oracle(pkg, lidar, N, Sn):
+    """Row counts that are no multiple of a warp or of a 128-row tile, tiles that straddle several rays (37 x 37), rays
+    that straddle tiles (21 x 150): every parameter gradient of the default (tcgen05) backward against the CPU oracle's
+    autograd, same tolerance rule as the golden cases."""
+    rng = np.random.default_rng(23)
+    o, d = (S.lidar_rays if lidar else S.camera_rays)(N, seed=5)
+    nch = 2 if lidar else 3
+    case = dict(lidar=lidar, t=0.45, ds=1.0, o=o, d=d, noise=None,
+                coef=dict(a=rng.normal(size=N).astype(np.float32), b=rng.normal(size=(N, nch)).astype(np.float32),
+                          c=(0.1 * rng.normal(size=(N, Sn))).astype(np.float32), e=rng.normal(size=N).astype(np.float32)))
+    tag = f"ragged_{int(lidar)}_{N}_{Sn}"
+    m = make_model(pkg, case["ds"])
+    loss, _ = run_case(m, case)
+    loss.backward()
+    g = grads_of(m, lidar)
+    e, eloss, _ = FC.oracle_grads(case)
+    assert abs(float(loss) - eloss) <= 1e-2 * max(abs(eloss), 1.0), (float(loss), eloss)
+    for name in FC.GRAD_NAMES:
+        ref = e[name].reshape(-1).astype(np.float64)
+        if not ref.any():
+            assert not g[name].any(), name
+            continue
+        err = np.linalg.norm(g[name] - ref) / np.linalg.norm(ref)
+        assert err < tolerance(case, tag, name), (name, err, tolerance(case, tag, name))
