@@ -708,10 +708,29 @@ struct HeadTc {
 // power-of-two gradient scale of one k_mlp_bwd launch: scale * max|dOut| ~ 16 (fp16 keeps 12 binades
 // of head-room for the growth through the layers and 14 + 10 below for the small rows)
 // ------------------------------------------------------------------------------------------------
-__global__ void k_absmax(const float* __restrict__ x, size_t n, float mul, unsigned* __restrict__ out) {
+__global__ void __launch_bounds__(256)
+k_absmax(const float* __restrict__ x, size_t n, float mul, unsigned* __restrict__ out) {
+    // a pure streaming read (200 MB of d sigma-net outputs per modality and step): 16-byte loads, four of them in
+    // flight per thread; scalar when the slice does not start on a 16-byte boundary (g_image + r0 * nch)
     float m = 0.f;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-        m = fmaxf(m, fabsf(__ldg(x + i)));
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+    size_t done = 0;
+    if ((reinterpret_cast<uintptr_t>(x) & 15u) == 0) {
+        const float4* x4 = reinterpret_cast<const float4*>(x);
+        const size_t n4 = n / 4;
+        auto fold = [&](const float4& v) {
+            m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+        };
+        size_t i = tid;
+        for (; i + 3 * nth < n4; i += 4 * nth) {
+            const float4 a = __ldg(x4 + i), b = __ldg(x4 + i + nth), c = __ldg(x4 + i + 2 * nth),
+                         d = __ldg(x4 + i + 3 * nth);
+            fold(a); fold(b); fold(c); fold(d);
+        }
+        for (; i < n4; i += nth) fold(__ldg(x4 + i));
+        done = n4 * 4;
+    }
+    for (size_t i = done + tid; i < n; i += nth) m = fmaxf(m, fabsf(__ldg(x + i)));
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
     m *= mul;
@@ -1729,7 +1748,7 @@ int nvsf_render_uniform_backward(const nvsf_field_config_t* cfg, const void* wor
         cudaMemsetAsync(scl, 0, 64, s);
         auto make_scale = [&](int slot, const float* x, size_t cnt, float mul) {
             unsigned* mx = reinterpret_cast<unsigned*>(scl + 16 * slot);
-            const unsigned blocks = (unsigned)std::min<size_t>(nvsf_div_up(cnt, (size_t)1024), (size_t)sms * 4);
+            const unsigned blocks = (unsigned)std::min<size_t>(nvsf_div_up(cnt, (size_t)4096), (size_t)sms * 8);
             k_absmax<<<blocks, 256, 0, s>>>(x, cnt, mul, mx);
             k_make_scale<<<1, 1, 0, s>>>(mx, reinterpret_cast<float*>(mx) + 2);
             return reinterpret_cast<const float*>(mx) + 2;

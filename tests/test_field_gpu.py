@@ -425,3 +425,36 @@ def test_whole_frame_chunk_vs_feature_scratch_chunks(pkg, model):
     close(host(out["one_chunk"][0]), host(out["unfused"][0]), 1e-3, 0, "sigma fused one chunk vs un-fused 4 M chunks")
     g = host(out["unfused"][1])
     close(host(out["one_chunk"][1]), g, 1e-3, 1e-3 * np.abs(g).max(), "geo fused one chunk vs un-fused 4 M chunks")
+
+
+def test_options_are_scoped_to_the_model(pkg, model):
+    """NeRFNetwork(options=...) applies its overrides only around its own launches: same bits as the process-wide switch,
+    the process defaults untouched afterwards, another model in the same process unaffected."""
+    L = pkg._lib.lib()
+    o, d = S.lidar_rays(97, seed=3)
+    to, td = torch.from_numpy(o).cuda()[None], torch.from_numpy(d).cuda()[None]
+    t = torch.tensor([[0.45]], device="cuda")
+    other = pkg.NeRFNetwork(time_resolution=S.TIME_RESOLUTION, num_frames=S.NUM_FRAMES, bound=S.BOUND,
+                            min_near=S.MIN_NEAR, min_near_lidar=S.MIN_NEAR_LIDAR, lidar_max_depth=S.LIDAR_MAX_DEPTH,
+                            options={"heads_tc": 0, "density_mode": 1})
+    other.load_flat_params(FC.oracle_params())
+    other.eval()
+    base = {k: L.nvsf_get_option(k) for k in (b"heads_tc", b"density_mode")}
+
+    def run(m):
+        with torch.no_grad():
+            r = m.run(to, td, t, cal_lidar_color=True, num_steps=200)
+        return host(r["depth_lidar"]), host(r["image_lidar"]), host(r["weights"])
+
+    r_def = run(model)
+    r_other = run(other)
+    assert {k: L.nvsf_get_option(k) for k in base} == base
+    assert all(np.array_equal(a, b) for a, b in zip(run(model), r_def))
+    try:
+        assert L.nvsf_set_option(b"heads_tc", 0) == 0 and L.nvsf_set_option(b"density_mode", 1) == 0
+        r_glob = run(model)
+    finally:
+        for k, v in base.items():
+            L.nvsf_set_option(k, v)
+    assert all(np.array_equal(a, b) for a, b in zip(r_other, r_glob))
+    close(r_other[0], r_def[0], 1e-3, 1e-6, "depth, model-scoped options vs defaults")
