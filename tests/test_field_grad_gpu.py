@@ -226,28 +226,74 @@ def test_mlp_backward_tcgen05_tiny_and_ragged(pkg, lidar, N, Sn):
         assert np.linalg.norm(a - b) <= 5e-3 * max(np.linalg.norm(b), 1e-30), (name, np.linalg.norm(a - b), np.linalg.norm(b))
 
 
+# Small cases do not average out the fp16 ReLU flips between two correct evaluations: measured against the CPU oracle on a
+# B200 (tools/dbg_ragged.py; identical for the tcgen05 and the mma.sync backward), aligned and ragged shapes alike:
+#   rays x samples   hash_static  hash_dynamic  planes  flow_grid  flow_mlp  sigma_net
+#   32 x 32          0.013        0.016         0.005   0.021      0.016     0.003
+#   37 x 37          0.012        0.013         0.006   0.040      0.038     0.006
+#   150 x 37         0.018        0.020         0.008   0.037      0.019     0.005
+#   128 x 128        0.015        0.014         0.003   0.024      0.005     0.003
+#   21 x 150 (cam)   0.014        0.014         0.004   0.019      0.013     0.003
+# A row-indexing mistake on a ragged tile gives errors of order one; the tolerances below sit between the two, and the
+# additivity test after this one pins ragged against aligned tilings of the SAME kernels at 5e-3.
+RAGGED_RTOL = {"flow_grid": 8e-2, "flow_mlp": 6e-2}
+
+
+def _ragged_case(lidar, N, Sn, seed=5):
+    rng = np.random.default_rng(23)
+    o, d = (S.lidar_rays if lidar else S.camera_rays)(N, seed=seed)
+    nch = 2 if lidar else 3
+    return dict(lidar=lidar, t=0.45, ds=1.0, o=o, d=d, noise=None,
+                coef=dict(a=rng.normal(size=N).astype(np.float32), b=rng.normal(size=(N, nch)).astype(np.float32),
+                          c=(0.1 * rng.normal(size=(N, Sn))).astype(np.float32), e=rng.normal(size=N).astype(np.float32)))
+
+
 @pytest.mark.parametrize("lidar,N,Sn", [(True, 37, 37), (False, 21, 150)])
 def test_ragged_shapes_match_cpu_oracle(pkg, lidar, N, Sn):
     """Row counts that are no multiple of a warp or of a 128-row tile, tiles that straddle several rays (37 x 37), rays
     that straddle tiles (21 x 150): every parameter gradient of the default (tcgen05) backward against the CPU oracle's
-    autograd, same tolerance rule as the golden cases."""
-    rng = np.random.default_rng(23)
-    o, d = (S.lidar_rays if lidar else S.camera_rays)(N, seed=5)
-    nch = 2 if lidar else 3
-    case = dict(lidar=lidar, t=0.45, ds=1.0, o=o, d=d, noise=None,
-                coef=dict(a=rng.normal(size=N).astype(np.float32), b=rng.normal(size=(N, nch)).astype(np.float32),
-                          c=(0.1 * rng.normal(size=(N, Sn))).astype(np.float32), e=rng.normal(size=N).astype(np.float32)))
-    tag = f"ragged_{int(lidar)}_{N}_{Sn}"
+    autograd."""
+    case = _ragged_case(lidar, N, Sn)
     m = make_model(pkg, case["ds"])
     loss, _ = run_case(m, case)
     loss.backward()
     g = grads_of(m, lidar)
     e, eloss, _ = FC.oracle_grads(case)
-    assert abs(float(loss) - eloss) <= 1e-2 * max(abs(eloss), 1.0), (float(loss), eloss)
+    assert abs(float(loss) - eloss) <= 1e-3 * max(abs(eloss), 1.0), (float(loss), eloss)
     for name in FC.GRAD_NAMES:
         ref = e[name].reshape(-1).astype(np.float64)
         if not ref.any():
             assert not g[name].any(), name
             continue
         err = np.linalg.norm(g[name] - ref) / np.linalg.norm(ref)
-        assert err < tolerance(case, tag, name), (name, err, tolerance(case, tag, name))
+        assert err < RAGGED_RTOL.get(name, 3e-2), (name, err)
+
+
+@pytest.mark.parametrize("lidar,Sn,Na,Nb", [(True, 37, 37, 91), (False, 150, 21, 43), (True, 1, 100, 156)])
+def test_gradients_are_additive_over_ragged_and_aligned_batches(pkg, lidar, Sn, Na, Nb):
+    """Size-independent property that isolates the tiling: the rays of a batch whose row count fills whole 128-row tiles
+    (Na + Nb rays) are also rendered as two ragged batches (Na and Nb rays: partial last tiles, partial warps); the
+    gradients of the parts must add up to the gradient of the whole.  Same kernels, same arithmetic per row — only the
+    tile partition and the per-launch power-of-two fp16 scale differ."""
+    assert ((Na + Nb) * Sn) % 128 == 0 and (Na * Sn) % 32 != 0
+    whole = _ragged_case(lidar, Na + Nb, Sn)
+
+    def part(lo, hi):
+        c = dict(whole, o=whole["o"][lo:hi], d=whole["d"][lo:hi])
+        c["coef"] = {k: v[lo:hi] for k, v in whole["coef"].items()}
+        return c
+
+    def grads(case):
+        m = make_model(pkg, 1.0)
+        loss, _ = run_case(m, case)
+        loss.backward()
+        return grads_of(m, lidar)
+
+    gw, ga, gb = grads(whole), grads(part(0, Na)), grads(part(Na, Na + Nb))
+    for name in FC.GRAD_NAMES:
+        want = gw[name].astype(np.float64)
+        if not want.any():
+            assert not ga[name].any() and not gb[name].any(), name
+            continue
+        err = np.linalg.norm(ga[name].astype(np.float64) + gb[name] - want) / np.linalg.norm(want)
+        assert err < 5e-3, (name, err)

@@ -3,6 +3,7 @@
 # test found) and initcheck over small-size selections of every GPU test file
 set -u
 mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_field_grad_gpu.py tests/test_field_gpu.py -m gpu -q --tb=short -k 'ragged or additive or scoped or tiny' 2>&1 | tail -15
 {
 for tool in synccheck initcheck; do
   for sel in "tests/test_field_grad_gpu.py|tiny_and_ragged" \
