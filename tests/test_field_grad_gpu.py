@@ -259,7 +259,7 @@ def test_ragged_shapes_match_cpu_oracle(pkg, lidar, N, Sn):
     loss.backward()
     g = grads_of(m, lidar)
     e, eloss, _ = FC.oracle_grads(case)
-    assert abs(float(loss) - eloss) <= 1e-3 * max(abs(eloss), 1.0), (float(loss), eloss)
+    assert abs(float(loss.detach()) - eloss) <= 1e-3 * max(abs(eloss), 1.0), (float(loss.detach()), eloss)
     for name in FC.GRAD_NAMES:
         ref = e[name].reshape(-1).astype(np.float64)
         if not ref.any():
