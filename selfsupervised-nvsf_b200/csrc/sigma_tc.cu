@@ -16,6 +16,10 @@
 
 #include "umma.cuh"
 
+#ifndef NVSF_TILE_ORDER
+#define NVSF_TILE_ORDER 0   // tile -> CTA map of the persistent density kernels: 0 interleaved, 1 contiguous per CTA
+#endif
+
 namespace {
 
 using namespace umma;
@@ -245,8 +249,14 @@ k_encode_sigma_tc(const __grid_constant__ nvsf_field_config_t cfg,
 
     uint32_t phase = 0;
     const size_t n_tiles = (count + kRows - 1) / kRows;
+#if NVSF_TILE_ORDER == 1   // A/B build: every CTA walks ONE contiguous range of tiles (adjacent rays in turn on one SM)
+    const size_t per_cta = ((n_tiles + gridDim.x - 1) / gridDim.x + kFusedWG - 1) / kFusedWG * kFusedWG;
+    const size_t t_end = min(n_tiles, ((size_t)blockIdx.x + 1) * per_cta);
+    for (size_t tile = (size_t)blockIdx.x * per_cta + wg; tile < t_end; tile += kFusedWG) {
+#else
     for (size_t tile = (size_t)blockIdx.x * kFusedWG + wg; tile < n_tiles;
          tile += (size_t)gridDim.x * kFusedWG) {
+#endif
         const size_t li = tile * kRows + t;
         const bool live = li < count;
         const size_t lc = live ? li : count - 1;   // dead rows of the last tile repeat a valid sample
@@ -481,8 +491,14 @@ k_flow_tc(const __grid_constant__ nvsf_field_config_t cfg, const __grid_constant
 
     uint32_t phase = 0;
     const size_t n_tiles = (count + kRows - 1) / kRows;
+#if NVSF_TILE_ORDER == 1
+    const size_t per_cta = ((n_tiles + gridDim.x - 1) / gridDim.x + kFlowWG - 1) / kFlowWG * kFlowWG;
+    const size_t t_end = min(n_tiles, ((size_t)blockIdx.x + 1) * per_cta);
+    for (size_t tile = (size_t)blockIdx.x * per_cta + wg; tile < t_end; tile += kFlowWG) {
+#else
     for (size_t tile = (size_t)blockIdx.x * kFlowWG + wg; tile < n_tiles;
          tile += (size_t)gridDim.x * kFlowWG) {
+#endif
         const size_t li = tile * kRows + t;
         const bool live = li < count;
         float x, y, z;
