@@ -253,6 +253,12 @@ k_encode_sigma_tc(const __grid_constant__ nvsf_field_config_t cfg,
     const size_t per_cta = ((n_tiles + gridDim.x - 1) / gridDim.x + kFusedWG - 1) / kFusedWG * kFusedWG;
     const size_t t_end = min(n_tiles, ((size_t)blockIdx.x + 1) * per_cta);
     for (size_t tile = (size_t)blockIdx.x * per_cta + wg; tile < t_end; tile += kFusedWG) {
+#elif NVSF_TILE_ORDER == 2   // A/B build: the warpgroups of a CTA walk ADJACENT rays (6 tiles = 768 samples each) in step
+    for (size_t j = 0;; ++j) {
+        const size_t v = (j / 6) * ((size_t)gridDim.x * kFusedWG) + (size_t)blockIdx.x * kFusedWG + wg;
+        if (v * 6 >= n_tiles) break;
+        const size_t tile = v * 6 + j % 6;
+        if (tile >= n_tiles) continue;
 #else
     for (size_t tile = (size_t)blockIdx.x * kFusedWG + wg; tile < n_tiles;
          tile += (size_t)gridDim.x * kFusedWG) {
@@ -495,6 +501,12 @@ k_flow_tc(const __grid_constant__ nvsf_field_config_t cfg, const __grid_constant
     const size_t per_cta = ((n_tiles + gridDim.x - 1) / gridDim.x + kFlowWG - 1) / kFlowWG * kFlowWG;
     const size_t t_end = min(n_tiles, ((size_t)blockIdx.x + 1) * per_cta);
     for (size_t tile = (size_t)blockIdx.x * per_cta + wg; tile < t_end; tile += kFlowWG) {
+#elif NVSF_TILE_ORDER == 2   // A/B build: the warpgroups of a CTA walk ADJACENT rays (6 tiles = 768 samples each) in step
+    for (size_t j = 0;; ++j) {
+        const size_t v = (j / 6) * ((size_t)gridDim.x * kFlowWG) + (size_t)blockIdx.x * kFlowWG + wg;
+        if (v * 6 >= n_tiles) break;
+        const size_t tile = v * 6 + j % 6;
+        if (tile >= n_tiles) continue;
 #else
     for (size_t tile = (size_t)blockIdx.x * kFlowWG + wg; tile < n_tiles;
          tile += (size_t)gridDim.x * kFlowWG) {
