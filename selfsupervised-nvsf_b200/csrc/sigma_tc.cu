@@ -13,6 +13,7 @@
 // math_pipe_throttle as its first stall (profiles/r01_stages_v2_ncu_full.txt); here one thread issues
 // twelve instructions per 128 samples and the other 127 only move data.
 #include <algorithm>
+#include <cstdlib>
 
 #include "umma.cuh"
 
@@ -441,6 +442,14 @@ k_encode_sigma_tc(const __grid_constant__ nvsf_field_config_t cfg,
                      : "memory");
 }
 
+
+// development knob: NVSF_CARVEOUT=<percent> in the environment sets cudaFuncAttributePreferredSharedMemoryCarveout of
+// the persistent density kernels (the rest of the 228 KB per SM is L1): measures how much the gathers owe to L1 capacity
+static void apply_carveout(const void* fn) {
+    static const char* e = getenv("NVSF_CARVEOUT");
+    if (e && *e) cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e));
+}
+
 bool g_fused_attr = false;
 
 // ---- flow stage on tcgen05 -------------------------------------------------------------------------
@@ -700,6 +709,8 @@ int nvsf_launch_encode_sigma_tc(const nvsf_field_config_t* cfg, const FieldPtrs&
         e = cudaFuncSetAttribute(k_encode_sigma_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)kFusedSmem);
         if (e != cudaSuccess) return (int)e;
+        apply_carveout((const void*)k_encode_sigma_tc<false>);
+        apply_carveout((const void*)k_encode_sigma_tc<true>);
         g_fused_attr = true;
     }
     const size_t tiles = (count + kRows - 1) / kRows;
@@ -727,6 +738,8 @@ int nvsf_launch_flow_tc(const nvsf_field_config_t* cfg, const FieldPtrs& P, cons
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(k_flow_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFlowSmem);
         if (e != cudaSuccess) return (int)e;
+        apply_carveout((const void*)k_flow_tc<true, false>);
+        apply_carveout((const void*)k_flow_tc<false, false>);
         g_flow_attr = true;
     }
     const size_t tiles = (count + kRows - 1) / kRows;
