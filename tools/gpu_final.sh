@@ -1,12 +1,13 @@
 #!/usr/bin/env bash
-# One gpurun call (development tool): whole GPU suite, smoke, the default bench line, the ncu launch
-# list of the same command.  Outputs under gpurun_out/.
+# the driver's round-end sequence on one fresh box: GPU suite, smoke(), reference arm, own arm
 set -u
 mkdir -p gpurun_out
-nvidia-smi -L > gpurun_out/gpu.txt
-(timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -8) > gpurun_out/tests_all.log 2>&1; tail -3 gpurun_out/tests_all.log
-timeout 300 python __graft_entry__.py smoke 2>&1 | tail -3
-timeout 900 python bench.py > gpurun_out/bench_v13.json 2> gpurun_out/bench_v13_err.log; tail -c 1500 gpurun_out/bench_v13.json; tail -3 gpurun_out/bench_v13_err.log
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_v13.csv \
-  python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-train --no-march > gpurun_out/launches_v13.log 2>&1
-python tools/launch_summary.py gpurun_out/launches_v13.csv | tail -12
+timeout 1200 python -m pytest tests -x -q -m gpu > gpurun_out/final_tests.log 2>&1; tail -2 gpurun_out/final_tests.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
+timeout 900 python bench.py --impl reference --gpus 1 --steps 3 --warmup 1 > gpurun_out/final_bench_ref.json 2> gpurun_out/final_bench_ref.err; tail -c 400 gpurun_out/final_bench_ref.json
+timeout 900 python bench.py --gpus 1 --steps 10 --warmup 3 > gpurun_out/final_bench.json 2> gpurun_out/final_bench.err
+python - <<P
+import json
+d=json.loads([l for l in open('gpurun_out/final_bench.json') if l.startswith('{')][-1])
+print(d['value'], d['ms_per_step'], d['e2e']['value'], d['train_step']['ms_per_step'], d['camera_march_render']['ms_per_frame'], d['clocks'])
+P
