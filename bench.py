@@ -38,6 +38,7 @@ WORKLOAD = ("KITTI-360-shaped LiDAR range image 66x1030 full-frame render (depth
 #   collapsed time planes 3 queries x 4 scales x 3 x 2 x 32 B   = 2304
 #   outputs sigma f32 + geo f16[16]                             =   36
 DENSITY_BYTES_PER_SAMPLE = 512 + 1152 + 1024 + 1536 + 2304 + 36
+GATHER_PEAK_GSECTORS = 290.2   # measured: random 4 / 8 / 16-byte gathers from a 32 MB (L2-resident) table, G sectors/s
 SURVEY_BYTES_PER_SAMPLE = 13312 + 48  # the reference's un-collapsed gathers
 HEADS_FLOP_PER_SAMPLE = 2 * 2 * (87 * 64 + 64 * 64 + 64 * 1)            # SURVEY.md 8(d), LiDAR heads
 HEADS_EXECUTED_FLOP_PER_SAMPLE = 2 * 2 * (16 * 64 + 64 * 64 + 64 * 16)  # what k_composite_tc issues per sample
@@ -795,6 +796,18 @@ def main():
                             "note": "table gathers served from L2 / shared memory; not HBM traffic"}
         e["limiter"] = k.get("limiter")
         e["ncu"] = {m: k.get(m) for m in ("l1tex_pct", "lts_pct", "dram_pct", "ipc", "occupancy_pct", "source") if m in k}
+        # The on-chip roof of a gather kernel: the chip's measured ceiling for random sector gathers out of an L2-resident
+        # table (tools/ubench_gather.cu: 1.00 sector per clock per SM = 290 G sectors/s, whatever the occupancy, the
+        # loads in flight or the access width) against the L1 sector accesses this kernel makes per sample (ncu
+        # l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum of the committed capture) over its live duration.  A frac
+        # above 1 means several sectors per L1 tag (coarse levels: whole lines), which the random ceiling does not see.
+        sec = k.get("l1_sectors_ld_per_sample")
+        if sec is not None and ms_step > 0.05:
+            ach = sec * n_samples / (ms_step * 1e-3) / 1e9
+            e["gather"] = {"bound": "l1 sector rate (random gathers from L2)", "peak": GATHER_PEAK_GSECTORS, "unit": "G sectors/s",
+                           "achieved": ach, "frac": ach / GATHER_PEAK_GSECTORS,
+                           "l1_sectors_per_sample": sec, "l2_sector_fetches_per_sample": k.get("l2_sectors_tex_read_per_sample"),
+                           "peak_source": "profiles/r02_ubench_gather.txt (tools/ubench_gather.cu on this pool's B200)"}
         return e
 
     stages = {k: stage_entry(table[k][1], stage_step_ms[k], table[k][0]) for k in table if table[k][1] != "-"}

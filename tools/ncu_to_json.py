@@ -59,6 +59,14 @@ def main():
             v = num(d.get(m, ""))
             if v is not None:
                 e[k] = v
+        # sector counts of the global loads: the gather kernels are measured against the random-sector ceiling of
+        # tools/ubench_gather.cu (profiles/r02_ubench_gather.txt)
+        for key, metric in (("l1_sectors_ld", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum"),
+                            ("l1_requests_ld", "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum"),
+                            ("l2_sectors_tex_read", "lts__t_sectors_srcunit_tex_op_read.sum")):
+            v = num(d.get(metric, ""))
+            if v is not None:
+                e[key + "_per_sample"] = v / spl
         stalls = sorted(((num(d[h]), h[len(STALL):-len("_per_issue_active.ratio")]) for h in hdr
                          if h.startswith(STALL) and h.endswith("_per_issue_active.ratio") and num(d[h]) is not None),
                         reverse=True)[:3]
