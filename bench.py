@@ -38,7 +38,8 @@ WORKLOAD = ("KITTI-360-shaped LiDAR range image 66x1030 full-frame render (depth
 #   collapsed time planes 3 queries x 4 scales x 3 x 2 x 32 B   = 2304
 #   outputs sigma f32 + geo f16[16]                             =   36
 DENSITY_BYTES_PER_SAMPLE = 512 + 1152 + 1024 + 1536 + 2304 + 36
-GATHER_PEAK_GSECTORS = 290.2   # measured: random 4 / 8 / 16-byte gathers from a 32 MB (L2-resident) table, G sectors/s
+GATHER_MISS_PEAK_GSECTORS = 290.2   # measured: random 4 / 8 / 16-byte gathers from a 32 MB (L2-resident) table, G sectors/s
+GATHER_HIT_PEAK_GSECTORS = 861.1    # measured: the same from a 64 KB (L1-resident) table
 SURVEY_BYTES_PER_SAMPLE = 13312 + 48  # the reference's un-collapsed gathers
 HEADS_FLOP_PER_SAMPLE = 2 * 2 * (87 * 64 + 64 * 64 + 64 * 1)            # SURVEY.md 8(d), LiDAR heads
 HEADS_EXECUTED_FLOP_PER_SAMPLE = 2 * 2 * (16 * 64 + 64 * 64 + 64 * 16)  # what k_composite_tc issues per sample
@@ -796,18 +797,25 @@ def main():
                             "note": "table gathers served from L2 / shared memory; not HBM traffic"}
         e["limiter"] = k.get("limiter")
         e["ncu"] = {m: k.get(m) for m in ("l1tex_pct", "lts_pct", "dram_pct", "ipc", "occupancy_pct", "source") if m in k}
-        # The on-chip roof of a gather kernel: the chip's measured ceiling for random sector gathers out of an L2-resident
-        # table (tools/ubench_gather.cu: 1.00 sector per clock per SM = 290 G sectors/s, whatever the occupancy, the
-        # loads in flight or the access width) against the L1 sector accesses this kernel makes per sample (ncu
-        # l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum of the committed capture) over its live duration.  A frac
-        # above 1 means several sectors per L1 tag (coarse levels: whole lines), which the random ceiling does not see.
-        sec = k.get("l1_sectors_ld_per_sample")
-        if sec is not None and ms_step > 0.05:
-            ach = sec * n_samples / (ms_step * 1e-3) / 1e9
-            e["gather"] = {"bound": "l1 sector rate (random gathers from L2)", "peak": GATHER_PEAK_GSECTORS, "unit": "G sectors/s",
-                           "achieved": ach, "frac": ach / GATHER_PEAK_GSECTORS,
-                           "l1_sectors_per_sample": sec, "l2_sector_fetches_per_sample": k.get("l2_sectors_tex_read_per_sample"),
-                           "peak_source": "profiles/r02_ubench_gather.txt (tools/ubench_gather.cu on this pool's B200)"}
+        # The on-chip roof of a gather kernel, from two measured ceilings of this chip (tools/ubench_gather.cu,
+        # profiles/r02_ubench_gather.txt + _ncu.txt): random sector gathers that MISS L1 run at 1.00 sector per clock per
+        # SM = 290 G sectors/s (the L1 -> crossbar request port is then 96-99 % busy, L2 78 %) whatever the occupancy,
+        # the loads in flight or the access width; gathers that HIT L1 at >= 2.96 per clock per SM = 861 G sectors/s.
+        # floor = misses / 290 + hits / 861 for the L1 sector counts of this kernel (ncu, committed capture);
+        # frac = floor / live duration.  `data_pipe_pct` is the unit ncu reports closest to saturation in the real
+        # kernel: the L1 data pipe (LSU wavefronts) — the 16-byte plane texels cost four wavefronts of register
+        # write-back per load however coherent the warp's addresses are.
+        miss, hit = k.get("l1_miss_sectors_ld_per_sample"), k.get("l1_hit_sectors_ld_per_sample")
+        if miss is not None and hit is not None and ms_step > 0.05:
+            floor_ms = (miss / GATHER_MISS_PEAK_GSECTORS + hit / GATHER_HIT_PEAK_GSECTORS) * n_samples * 1e-6
+            e["gather"] = {"bound": "l1 sector gathers (measured miss / hit ceilings)", "unit": "G sectors/s",
+                           "peak_miss": GATHER_MISS_PEAK_GSECTORS, "peak_hit": GATHER_HIT_PEAK_GSECTORS,
+                           "l1_miss_sectors_per_sample": miss, "l1_hit_sectors_per_sample": hit,
+                           "achieved": (miss + hit) * n_samples / (ms_step * 1e-3) / 1e9,
+                           "floor_ms": floor_ms, "frac": floor_ms / ms_step,
+                           "data_pipe_pct": k.get("l1_data_pipe_pct"), "xbar_req_pct": k.get("l1_xbar_req_pct"),
+                           "peak_source": "profiles/r02_ubench_gather.txt, r02_ubench_gather_ncu.txt (tools/ubench_gather.cu "
+                                          "on this pool's B200)"}
         return e
 
     stages = {k: stage_entry(table[k][1], stage_step_ms[k], table[k][0]) for k in table if table[k][1] != "-"}

@@ -63,10 +63,18 @@ def main():
         # tools/ubench_gather.cu (profiles/r02_ubench_gather.txt)
         for key, metric in (("l1_sectors_ld", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum"),
                             ("l1_requests_ld", "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum"),
+                            ("l1_miss_sectors_ld", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld_lookup_miss.sum"),
+                            ("l1_hit_sectors_ld", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld_lookup_hit.sum"),
                             ("l2_sectors_tex_read", "lts__t_sectors_srcunit_tex_op_read.sum")):
             v = num(d.get(metric, ""))
             if v is not None:
                 e[key + "_per_sample"] = v / spl
+        for key, metric in (("l1_data_pipe_pct", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"),
+                            ("l1_xbar_req_pct", "l1tex__m_l1tex2xbar_req_cycles_active.avg.pct_of_peak_sustained_elapsed"),
+                            ("l1_writeback_pct", "l1tex__lsu_writeback_active.avg.pct_of_peak_sustained_elapsed")):
+            v = num(d.get(metric, ""))
+            if v is not None:
+                e[key] = v
         stalls = sorted(((num(d[h]), h[len(STALL):-len("_per_issue_active.ratio")]) for h in hdr
                          if h.startswith(STALL) and h.endswith("_per_issue_active.ratio") and num(d[h]) is not None),
                         reverse=True)[:3]

@@ -71,6 +71,11 @@ int main() {
     cudaMalloc(&tab, max_bytes);
     cudaMalloc(&out, 4096);
     cudaMemset(tab, 1, max_bytes);
+    // L1-resident table (64 KB): the same ceiling holds for hits — it is the L1 tag stage (one 128-byte line per clock),
+    // not the L2 -> L1 fill path, that caps scattered loads
+    run<8, 8, 0>("8 B, every lane its own sector (L1 hits)", tab, (size_t)64 << 10, 768, 1, sms, out);
+    run<8, 16, 0>("8 B, every lane its own sector (L1 hits)", tab, (size_t)64 << 10, 1024, 2, sms, out);
+    run<4, 8, 2>("4 B, one random 128-byte line per warp (L1 hits)", tab, (size_t)64 << 10, 1024, 2, sms, out);
     for (size_t mb : {32, 128, 512}) {
         const size_t b = mb << 20;
         run<8, 8, 0>("8 B, every lane its own sector", tab, b, 768, 1, sms, out);
