@@ -17,6 +17,9 @@
 
 #include "umma.cuh"
 
+#ifndef NVSF_EXP_SKIP_TP
+#define NVSF_EXP_SKIP_TP 0
+#endif
 #ifndef NVSF_TILE_ORDER
 #define NVSF_TILE_ORDER 0   // tile -> CTA map of the persistent density kernels: 0 interleaved, 1 contiguous per CTA
 #endif
@@ -324,9 +327,18 @@ k_encode_sigma_tc(const __grid_constant__ nvsf_field_config_t cfg,
                 const int qq = q == 0 ? 0 : (q == 1 ? qi1 : qi2);
                 const __half* b0 = P.pld16 + (size_t)qq * P.pld_per_q + P.pld_scale[s];
                 float v[8];
+#if NVSF_EXP_SKIP_TP   // measurement only (wrong results): what the stage would gain if 48 of its 120 plane loads vanished
+                if (q == 0) {
+#endif
                 plane1d_mul_h(b0, R, qx[q], v, true);
                 plane1d_mul_h(b0 + (size_t)R * 8, R, qy[q], v, false);
                 plane1d_mul_h(b0 + (size_t)2 * R * 8, R, qz[q], v, false);
+#if NVSF_EXP_SKIP_TP
+                } else {
+#pragma unroll
+                    for (int f = 0; f < 8; ++f) v[f] = acc8[f] + qx[q];
+                }
+#endif
                 const float wq = q == 0 ? 0.5f : 0.25f;
 #pragma unroll
                 for (int f = 0; f < 8; ++f) acc8[f] = q == 0 ? wq * v[f] : fmaf(wq, v[f], acc8[f]);
