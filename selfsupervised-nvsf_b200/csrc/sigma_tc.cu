@@ -333,10 +333,31 @@ k_encode_sigma_tc(const __grid_constant__ nvsf_field_config_t cfg,
                 plane1d_mul_h(b0, R, qx[q], v, true);
                 plane1d_mul_h(b0 + (size_t)R * 8, R, qy[q], v, false);
                 plane1d_mul_h(b0 + (size_t)2 * R * 8, R, qz[q], v, false);
-#if NVSF_EXP_SKIP_TP
+#if NVSF_EXP_SKIP_TP == 1
                 } else {
 #pragma unroll
                     for (int f = 0; f < 8; ++f) v[f] = acc8[f] + qx[q];
+                }
+#elif NVSF_EXP_SKIP_TP == 2   // loads of query 0 (eliminated as common subexpressions), arithmetic of query q
+                } else {
+                    const float pq[3] = {qx[q], qy[q], qz[q]}, p0[3] = {qx[0], qy[0], qz[0]};
+#pragma unroll
+                    for (int ax = 0; ax < 3; ++ax) {
+                        uint32_t x0, x1, y0, y1;
+                        float w0, wq_;
+                        plane_coord(p0[ax], R, x0, x1, w0);
+                        plane_coord(pq[ax], R, y0, y1, wq_);
+                        const __half* bq = P.pld16 + P.pld_scale[s] + (size_t)ax * R * 8;   // query 0's table
+                        float a[8], b[8];
+                        ld8h(bq + (size_t)x0 * 8, a);
+                        ld8h(bq + (size_t)x1 * 8, b);
+                        wq_ += (float)(y0 & 1u) * 1e-9f;
+#pragma unroll
+                        for (int f = 0; f < 8; ++f) {
+                            const float sv = (1.f - wq_) * a[f] + wq_ * b[f];
+                            v[f] = ax == 0 ? sv : v[f] * sv;
+                        }
+                    }
                 }
 #endif
                 const float wq = q == 0 ? 0.5f : 0.25f;
