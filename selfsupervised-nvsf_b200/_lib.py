@@ -158,13 +158,23 @@ def check(status, what=""):
 # runs inside option_scope(model.options) — one re-entrant lock around "apply this model's overrides, enqueue the
 # launches, restore" (the kernels themselves run asynchronously, outside the lock).
 _OPTION_LOCK = threading.RLock()
+_OPTION_LOCK_TIMEOUT_S = 120.0
+
+
+def _acquire_option_lock():
+    if not _OPTION_LOCK.acquire(timeout=_OPTION_LOCK_TIMEOUT_S):
+        raise NvsfError(f"the option lock has been held by another thread for {_OPTION_LOCK_TIMEOUT_S:.0f} s "
+                        "(is .backward() running inside a hand-opened option_scope? pass options=... to the model)")
 
 
 @contextlib.contextmanager
 def option_scope(overrides=None):
     """Hold the option lock; with `overrides` ({name: int}) set them for the duration and restore the previous
     values afterwards.  Unknown names / rejected values raise NvsfError before anything is launched."""
-    with _OPTION_LOCK:
+    # (a bounded wait: a thread that opens a scope by hand and calls loss.backward() inside it would otherwise wait
+    #  forever for the autograd thread, which needs the same lock — give the MODEL its options instead)
+    _acquire_option_lock()
+    try:
         if not overrides:
             yield
             return
@@ -180,6 +190,8 @@ def option_scope(overrides=None):
         finally:
             for key, old in reversed(saved):
                 L.nvsf_set_option(key, old)
+    finally:
+        _OPTION_LOCK.release()
 
 
 def with_options(fn):
@@ -226,10 +238,13 @@ def device_guard(fn):
                     dev = p.device
                     break
         # the option lock: a launch never observes another thread's model-scoped overrides half applied
-        with _OPTION_LOCK:
+        _acquire_option_lock()
+        try:
             if dev is None or dev.index == torch.cuda.current_device():
                 return fn(*args, **kwargs)
             with torch.cuda.device(dev):
                 return fn(*args, **kwargs)
+        finally:
+            _OPTION_LOCK.release()
 
     return wrapper

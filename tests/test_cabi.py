@@ -129,3 +129,28 @@ def test_option_scope_is_per_model_and_restores():
         assert seen == []
     th.join()
     assert seen == [base[0]]
+
+
+def test_option_scope_wait_is_bounded(monkeypatch):
+    """A thread that cannot get the option lock raises instead of waiting forever (e.g. .backward() inside a
+    hand-opened scope: the autograd thread needs the same lock)."""
+    import importlib
+    import threading
+    pkg = importlib.import_module("selfsupervised-nvsf_b200")
+    monkeypatch.setattr(pkg._lib, "_OPTION_LOCK_TIMEOUT_S", 0.2)
+    err = []
+
+    def other():
+        try:
+            with pkg._lib.option_scope():
+                pass
+        except pkg._lib.NvsfError as e:
+            err.append(str(e))
+
+    with pkg._lib.option_scope({"heads_tc": 6}):
+        th = threading.Thread(target=other)
+        th.start()
+        th.join()
+    assert len(err) == 1 and "option lock" in err[0]
+    with pkg._lib.option_scope():      # and the lock is free again afterwards
+        pass
